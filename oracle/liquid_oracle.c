@@ -1,0 +1,773 @@
+/*
+ * liquid_oracle.c -- CPU restatement of liquid-dsp's polyphase-channelizer hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see liquid_oracle.h).  Parity status: PINNED against the
+ * reference's golden vectors and against the compiled reference (oracle/_ref).
+ *
+ * Written from the behaviour of the reference, not from its text: state is held as plain
+ * "last L samples, oldest first" arrays instead of the reference's power-of-two ring with
+ * memmove, FFT plans are replaced by a recursive function, objects are flat structs.
+ * Paths cited are relative to /root/reference.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared -pthread liquid_oracle.c -lm
+ *   (-ffp-contract=off keeps a*b+c as two roundings, as the SSE mul/add intrinsics of
+ *    src/dotprod/src/dotprod_crcf.mmx.c do.)
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "liquid_oracle.h"
+
+/* ------------------------------------------------------------------------------------ */
+/* small helpers                                                                         */
+/* ------------------------------------------------------------------------------------ */
+
+static orc_cf cf(float re, float im) { orc_cf v; v.re = re; v.im = im; return v; }
+
+static orc_cf cf_mul(orc_cf a, orc_cf b)
+{
+    /* C99 complex multiply as the reference's `float complex` products evaluate */
+    return cf(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+
+static void *xmalloc(size_t n)
+{
+    void *p = malloc(n ? n : 1);
+    if (!p) { fprintf(stderr, "oracle: out of memory\n"); abort(); }
+    return p;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* scalar math                                                                           */
+/* ------------------------------------------------------------------------------------ */
+
+/* floor(log2 x) + 1, 0 for x == 0.        src/utility/src/msb_index.c:110-135 */
+unsigned int orc_msb_index(unsigned int x)
+{
+    unsigned int bits = 0;
+    while (x) { bits++; x >>= 1; }
+    return bits;
+}
+
+/* ln Gamma(z): upward recursion to z >= 10, then a Stirling-type closed form.
+ * src/math/src/math.gamma.c:43-71 (the double-typed 0.5 and log() are kept) */
+float orc_lngammaf(float z)
+{
+    if (z < 0) return NAN;                      /* reference exits; the path never gets here */
+    if (z < 10.0f)
+        return orc_lngammaf(z + 1.0f) - logf(z);
+    float g = 0.5 * (logf(2 * M_PI) - log(z));
+    g += z * (logf(z + (1 / (12.0f * z - 0.1f / z))) - 1);
+    return g;
+}
+
+/* I0(z) by 32 terms of sum_k ((z/2)^k / k!)^2 evaluated through logs.
+ * src/math/src/math.bessel.c:86-105 */
+float orc_besseli0f(float z)
+{
+    if (z == 0.0f) return 1.0f;
+    float y = 0.0f;
+    for (unsigned int k = 0; k < 32; k++) {
+        float t = k * logf(0.5f * z) - orc_lngammaf((float)k + 1.0f);
+        y += expf(2 * t);
+    }
+    return y;
+}
+
+/* sin(pi x)/(pi x); three-cosine product below |x| < 0.01.   src/math/src/math.c:128-139 */
+float orc_sincf(float x)
+{
+    if (fabsf(x) < 0.01f)
+        return cosf(M_PI * x / 2.0f) * cosf(M_PI * x / 4.0f) * cosf(M_PI * x / 8.0f);
+    return sinf(M_PI * x) / (M_PI * x);
+}
+
+/* Kaiser window sample; note r = 2t/N (not N-1).    src/math/src/math.c:289-310 */
+float orc_kaiser(unsigned int n, unsigned int N, float beta, float mu)
+{
+    float t = (float)n - (float)(N - 1) / 2 + mu;
+    float r = 2.0f * t / (float)(N);
+    float a = orc_besseli0f(beta * sqrtf(1 - r * r));
+    float b = orc_besseli0f(beta);
+    return a / b;
+}
+
+/* src/filter/src/firdes.c:224-236 */
+float orc_kaiser_beta_As(float As)
+{
+    As = fabsf(As);
+    float beta;
+    if (As > 50.0f)      beta = 0.1102f * (As - 8.7f);
+    else if (As > 21.0f) beta = 0.5842 * powf(As - 21, 0.4f) + 0.07886f * (As - 21);
+    else                 beta = 0.0f;
+    return beta;
+}
+
+/* Kaiser-windowed sinc low-pass.   src/filter/src/firdes.c:244-280
+ * returns 0 on success, -1 on the argument errors the reference exits on */
+int orc_firdes_kaiser(unsigned int n, float fc, float As, float mu, float *h)
+{
+    if (mu < -0.5f || mu > 0.5f) return -1;
+    if (fc < 0.0f || fc > 0.5f)  return -1;
+    if (n == 0)                  return -1;
+    float beta = orc_kaiser_beta_As(As);
+    for (unsigned int i = 0; i < n; i++) {
+        float t  = (float)i - (float)(n - 1) / 2 + mu;
+        float h1 = orc_sincf(2.0f * fc * t);
+        float h2 = orc_kaiser(i, n, beta, mu);
+        h[i] = h1 * h2;
+    }
+    return 0;
+}
+
+/* square-root raised cosine, 2km+1 taps.   src/filter/src/rrcos.c:37-95 */
+int orc_firdes_rrcos(unsigned int k, unsigned int m, float beta, float dt, float *h)
+{
+    if (k < 1 || m < 1 || beta < 0.0f || beta > 1.0f) return -1;
+    unsigned int h_len = 2 * k * m + 1;
+    float T = 1.0f;
+    for (unsigned int n = 0; n < h_len; n++) {
+        float nf = (float)n, kf = (float)k, mf = (float)m;
+        float z  = (nf + dt) / kf - mf;
+        float t1 = cosf((1 + beta) * M_PI * z);
+        float t2 = sinf((1 - beta) * M_PI * z);
+        if (fabsf(z) < 1e-5) {
+            h[n] = 1 - beta + 4 * beta / M_PI;
+        } else {
+            float t3 = 1 / ((4 * beta * z));
+            float g  = 1 - 16 * beta * beta * z * z;
+            g *= g;
+            if (g < 1e-5) {
+                float g1 = 1 + 2.0f / M_PI;
+                float g2 = sinf(0.25f * M_PI / beta);
+                float g3 = 1 - 2.0f / M_PI;
+                float g4 = cosf(0.25f * M_PI / beta);
+                h[n] = beta / sqrtf(2.0f) * (g1 * g2 + g3 * g4);
+            } else {
+                float t4 = 4 * beta / (M_PI * sqrtf(T) * (1 - (16 * beta * beta * z * z)));
+                h[n] = t4 * (t1 + (t2 * t3));
+            }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* dot products                                                                          */
+/* ------------------------------------------------------------------------------------ */
+
+/* sequential sum.   src/dotprod/src/dotprod.c:41-56 */
+void orc_dotprod_crcf_run(const float *h, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    float re = 0.0f, im = 0.0f;
+    for (unsigned int i = 0; i < n; i++) {
+        re += h[i] * x[i].re;
+        im += h[i] * x[i].im;
+    }
+    *y = cf(re, im);
+}
+
+/* same order as _run (four per trip, then the tail).   src/dotprod/src/dotprod.c:63-89 */
+void orc_dotprod_crcf_run4(const float *h, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    orc_dotprod_crcf_run(h, x, n, y);
+}
+
+/* The x86 build keeps four float lanes {re,im,re,im} (sixteen when n >= 32), folds them
+ * at the end and finishes the tail sequentially.   src/dotprod/src/dotprod_crcf.mmx.c:144-287
+ * Here the 2n-float view of x is walked with explicit lane accumulators. */
+void orc_dotprod_crcf_run_sse_order(const float *h, const orc_cf *x, unsigned int n_taps, orc_cf *y)
+{
+    const float *xf = (const float *)x;
+    unsigned int n = 2 * n_taps;                 /* floats */
+    float w0, w1;
+    unsigned int i;
+    if (n_taps < 32) {
+        float s[4] = {0, 0, 0, 0};
+        unsigned int t = (n >> 2) << 2;
+        for (i = 0; i < t; i += 4)
+            for (unsigned int l = 0; l < 4; l++)
+                s[l] += xf[i + l] * h[(i + l) >> 1];
+        w0 = s[0] + s[2];
+        w1 = s[1] + s[3];
+    } else {
+        float s[4][4];
+        memset(s, 0, sizeof s);
+        unsigned int r = (n >> 4) << 2;
+        for (i = 0; i < r; i += 4)
+            for (unsigned int a = 0; a < 4; a++)
+                for (unsigned int l = 0; l < 4; l++) {
+                    unsigned int j = 4 * i + 4 * a + l;
+                    s[a][l] += xf[j] * h[j >> 1];
+                }
+        for (unsigned int l = 0; l < 4; l++) {
+            s[0][l] = s[0][l] + s[1][l];
+            s[2][l] = s[2][l] + s[3][l];
+            s[0][l] = s[0][l] + s[2][l];
+        }
+        w0 = s[0][0] + s[0][2];
+        w1 = s[0][1] + s[0][3];
+        i  = 4 * r;
+    }
+    for (; i < n; i += 2) {
+        w0 += xf[i] * h[i >> 1];
+        w1 += xf[i + 1] * h[(i + 1) >> 1];
+    }
+    *y = cf(w0, w1);
+}
+
+/* the dot product the filter objects use: x86 lane order, as configure selects on this
+ * platform (configure.ac:156-167) */
+static orc_cf dot_crcf(const float *h, const orc_cf *x, unsigned int n)
+{
+    orc_cf y;
+    orc_dotprod_crcf_run_sse_order(h, x, n, &y);
+    return y;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* FFT                                                                                   */
+/* ------------------------------------------------------------------------------------ */
+
+
+static unsigned int smallest_factor(unsigned int n)
+{
+    for (unsigned int f = 2; f * f <= n; f++)
+        if (n % f == 0) return f;
+    return n;
+}
+
+/* e^{j d 2 pi i / n} with the reference's float/double mix.   fft_mixed_radix.c:103-105 */
+static orc_cf twiddle_calc(int dir, unsigned int i, unsigned int n)
+{
+    float d   = (dir == ORC_FFT_FORWARD) ? -1.0f : 1.0f;
+    float arg = (float)((double)(d * 2) * M_PI * (double)(float)i / (double)(float)n);
+    return cf(cosf(arg), sinf(arg));
+}
+
+/* per-(n, dir) twiddle tables, built once (the reference builds them per plan) */
+struct tw_entry { unsigned int n; int dir; orc_cf *w; struct tw_entry *next; };
+static struct tw_entry *tw_head = NULL;
+static pthread_mutex_t tw_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static const orc_cf *twiddles(int dir, unsigned int n)
+{
+    pthread_mutex_lock(&tw_lock);
+    struct tw_entry *e;
+    for (e = tw_head; e; e = e->next)
+        if (e->n == n && e->dir == dir) break;
+    if (!e) {
+        e = xmalloc(sizeof *e);
+        e->n = n; e->dir = dir;
+        e->w = xmalloc(n * sizeof *e->w);
+        for (unsigned int i = 0; i < n; i++) e->w[i] = twiddle_calc(dir, i, n);
+        e->next = tw_head;
+        tw_head = e;
+    }
+    pthread_mutex_unlock(&tw_lock);
+    return e->w;
+}
+
+/* O(n^2) DFT in float.  Stands in for the codelets (fft_dft.c:158-520), the generic
+ * dotprod DFT (fft_dft.c:124-153) and Rader (fft_rader.c, fft_rader2.c): same transform,
+ * different float rounding (~1e-7 relative). */
+static void dft_direct(unsigned int n, const orc_cf *x, orc_cf *y, int dir)
+{
+    const orc_cf *w = twiddles(dir, n);
+    for (unsigned int k = 0; k < n; k++) {
+        float re = x[0].re, im = x[0].im;
+        for (unsigned int i = 1; i < n; i++) {
+            orc_cf p = cf_mul(x[i], w[(unsigned int)(((unsigned long long)k * i) % n)]);
+            re += p.re;
+            im += p.im;
+        }
+        y[k] = cf(re, im);
+    }
+}
+
+/* Planner + mixed-radix Cooley-Tukey.
+ *   method choice   src/fft/src/fft_utilities.c:34-68   (n<=8, 11, 13, 16, 17 -> DFT)
+ *   radix choice    src/fft/src/fft_mixed_radix.c:194-242 (16, 8, 4, 2, else least factor)
+ *   execute         src/fft/src/fft_mixed_radix.c:128-191 */
+static void fft_rec(unsigned int n, const orc_cf *x, orc_cf *y, int dir)
+{
+    if (n == 1) { y[0] = x[0]; return; }
+    unsigned int f = smallest_factor(n);
+    if (n <= 8 || n == 11 || n == 13 || n == 16 || n == 17 || f == n) {
+        dft_direct(n, x, y, dir);
+        return;
+    }
+    unsigned int Q;
+    if (n % 2 == 0) Q = (n % 16 == 0) ? 16 : (n % 8 == 0) ? 8 : (n % 4 == 0) ? 4 : 2;
+    else            Q = f;
+    unsigned int P = n / Q;
+    unsigned int tl = Q > P ? Q : P;
+    orc_cf *buf = xmalloc(n * sizeof *buf);
+    orc_cf *t0  = xmalloc(tl * sizeof *t0);
+    orc_cf *t1  = xmalloc(tl * sizeof *t1);
+    const orc_cf *w = twiddles(dir, n);
+    memcpy(buf, x, n * sizeof *buf);
+    /* Q strided P-point transforms, each followed by the twiddle W^(i k) */
+    for (unsigned int i = 0; i < Q; i++) {
+        for (unsigned int k = 0; k < P; k++) t0[k] = buf[Q * k + i];
+        fft_rec(P, t0, t1, dir);
+        for (unsigned int k = 0; k < P; k++) buf[Q * k + i] = cf_mul(t1[k], w[i * k]);
+    }
+    /* P contiguous Q-point transforms, written transposed */
+    for (unsigned int i = 0; i < P; i++) {
+        for (unsigned int k = 0; k < Q; k++) t0[k] = buf[Q * i + k];
+        fft_rec(Q, t0, t1, dir);
+        for (unsigned int k = 0; k < Q; k++) y[k * P + i] = t1[k];
+    }
+    free(buf); free(t0); free(t1);
+}
+
+/* unscaled DFT; FORWARD = e^{-j..}, BACKWARD = e^{+j..}.   src/fft/src/fft_common.c:285-316 */
+void orc_fft_run(unsigned int n, const orc_cf *x, orc_cf *y, int dir)
+{
+    if (n == 0) return;
+    if (x == y) {                                 /* allow in-place use */
+        orc_cf *tmp = xmalloc(n * sizeof *tmp);
+        memcpy(tmp, x, n * sizeof *tmp);
+        fft_rec(n, tmp, y, dir);
+        free(tmp);
+    } else {
+        fft_rec(n, x, y, dir);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* sliding window: "the last len samples, oldest first".  src/buffer/src/window.c:200-214 */
+/* ------------------------------------------------------------------------------------ */
+
+static void win_push(orc_cf *w, unsigned int len, orc_cf v)
+{
+    memmove(w, w + 1, (len - 1) * sizeof *w);
+    w[len - 1] = v;
+}
+
+/* branch i of a prototype, stored newest-tap-last so it lines up with an oldest-first
+ * window:  sub[len-1-n] = h[i + n M].   firpfbch.c:115-124, firpfbch2.c:101-109, firpfb.c:71-84 */
+static float *polyphase_split(const float *h, unsigned int M, unsigned int len)
+{
+    float *sub = xmalloc((size_t)M * len * sizeof *sub);
+    for (unsigned int i = 0; i < M; i++)
+        for (unsigned int n = 0; n < len; n++)
+            sub[(size_t)i * len + (len - 1 - n)] = h[i + n * M];
+    return sub;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* firfilt_crcf                                                                          */
+/* ------------------------------------------------------------------------------------ */
+
+struct orc_firfilt_s {
+    unsigned int n;
+    float *hr;          /* taps reversed: hr[n-1-k] = h[k]      firfilt.c:87-90 */
+    orc_cf *w;          /* last n samples, oldest first */
+    float scale;        /* firfilt.c:96 */
+};
+
+orc_firfilt orc_firfilt_create(const float *h, unsigned int n)
+{
+    if (n == 0) return NULL;                      /* firfilt.c:66-69 (reference exits) */
+    orc_firfilt q = xmalloc(sizeof *q);
+    q->n  = n;
+    q->hr = xmalloc(n * sizeof *q->hr);
+    q->w  = xmalloc(n * sizeof *q->w);
+    for (unsigned int k = 0; k < n; k++) q->hr[n - 1 - k] = h[k];
+    q->scale = 1;
+    orc_firfilt_reset(q);
+    return q;
+}
+
+/* firfilt.c:109-131 */
+orc_firfilt orc_firfilt_create_kaiser(unsigned int n, float fc, float As, float mu)
+{
+    if (n == 0) return NULL;
+    float *h = xmalloc(n * sizeof *h);
+    if (orc_firdes_kaiser(n, fc, As, mu, h)) { free(h); return NULL; }
+    orc_firfilt q = orc_firfilt_create(h, n);
+    free(h);
+    return q;
+}
+
+void orc_firfilt_destroy(orc_firfilt q) { if (q) { free(q->hr); free(q->w); free(q); } }
+void orc_firfilt_reset(orc_firfilt q) { memset(q->w, 0, q->n * sizeof *q->w); }   /* firfilt.c:253-263 */
+void orc_firfilt_set_scale(orc_firfilt q, float s) { q->scale = s; }               /* firfilt.c:288 */
+void orc_firfilt_push(orc_firfilt q, orc_cf x) { win_push(q->w, q->n, x); }        /* firfilt.c:297-317 */
+unsigned int orc_firfilt_get_length(orc_firfilt q) { return q->n; }
+
+/* firfilt.c:322-338: dot product, then the scale */
+void orc_firfilt_execute(orc_firfilt q, orc_cf *y)
+{
+    orc_cf r = dot_crcf(q->hr, q->w, q->n);
+    *y = cf(r.re * q->scale, r.im * q->scale);
+}
+
+/* firfilt.c:346-358; x == y allowed */
+void orc_firfilt_execute_block(orc_firfilt q, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    for (unsigned int i = 0; i < n; i++) {
+        orc_firfilt_push(q, x[i]);
+        orc_firfilt_execute(q, &y[i]);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* firpfb_crcf: M sub-filters sharing one window                                         */
+/* ------------------------------------------------------------------------------------ */
+
+struct orc_firpfb_s {
+    unsigned int M, sub_len;
+    float *sub;         /* [M][sub_len] */
+    orc_cf *w;
+    float scale;
+};
+
+/* firpfb.c:46-95; sub_len = h_len / M (integer division, trailing taps dropped) */
+orc_firpfb orc_firpfb_create(unsigned int M, const float *h, unsigned int h_len)
+{
+    if (M == 0 || h_len == 0) return NULL;
+    orc_firpfb q = xmalloc(sizeof *q);
+    q->M = M;
+    q->sub_len = h_len / M;
+    q->sub = polyphase_split(h, M, q->sub_len);
+    q->w = xmalloc((q->sub_len ? q->sub_len : 1) * sizeof *q->w);
+    q->scale = 1;
+    orc_firpfb_reset(q);
+    return q;
+}
+
+/* firpfb.c:105-137: 2Mm+1 taps, cut-off fc/M */
+orc_firpfb orc_firpfb_create_kaiser(unsigned int M, unsigned int m, float fc, float As)
+{
+    if (M == 0 || m == 0 || fc < 0.0f || fc > 0.5f || As < 0.0f) return NULL;
+    unsigned int H = 2 * M * m + 1;
+    float *h = xmalloc(H * sizeof *h);
+    orc_firdes_kaiser(H, fc / (float)M, As, 0.0f, h);
+    orc_firpfb q = orc_firpfb_create(M, h, H);
+    free(h);
+    return q;
+}
+
+void orc_firpfb_destroy(orc_firpfb q) { if (q) { free(q->sub); free(q->w); free(q); } }
+void orc_firpfb_reset(orc_firpfb q) { memset(q->w, 0, q->sub_len * sizeof *q->w); }
+void orc_firpfb_set_scale(orc_firpfb q, float s) { q->scale = s; }
+void orc_firpfb_push(orc_firpfb q, orc_cf x) { win_push(q->w, q->sub_len, x); }   /* firpfb.c:315-319 */
+
+/* firpfb.c:325-346 */
+void orc_firpfb_execute(orc_firpfb q, unsigned int i, orc_cf *y)
+{
+    orc_cf r = dot_crcf(q->sub + (size_t)i * q->sub_len, q->w, q->sub_len);
+    *y = cf(r.re * q->scale, r.im * q->scale);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* firpfbch_crcf: critically sampled channelizer                                         */
+/* ------------------------------------------------------------------------------------ */
+
+struct orc_firpfbch_s {
+    int type;
+    unsigned int M, p;
+    float *sub;                 /* [M][p] */
+    orc_cf *w;                  /* [M][p] windows */
+    unsigned int filter_index;  /* analyzer: window the next sample goes to */
+    orc_cf *X, *x;              /* transform in / out */
+};
+
+/* firpfbch.c:73-142 */
+orc_firpfbch orc_firpfbch_create(int type, unsigned int M, unsigned int p, const float *h)
+{
+    if ((type != ORC_ANALYZER && type != ORC_SYNTHESIZER) || M == 0 || p == 0) return NULL;
+    orc_firpfbch q = xmalloc(sizeof *q);
+    q->type = type; q->M = M; q->p = p;
+    q->sub = polyphase_split(h, M, p);
+    q->w = xmalloc((size_t)M * p * sizeof *q->w);
+    q->X = xmalloc(M * sizeof *q->X);
+    q->x = xmalloc(M * sizeof *q->x);
+    orc_firpfbch_reset(q);
+    return q;
+}
+
+/* firpfbch.c:150-184: 2Mm+1 Kaiser taps at fc = 0.5/M, not normalised, first 2Mm used */
+orc_firpfbch orc_firpfbch_create_kaiser(int type, unsigned int M, unsigned int m, float As)
+{
+    if (M == 0 || m == 0) return NULL;
+    As = fabsf(As);
+    unsigned int h_len = 2 * M * m + 1;
+    float *h = xmalloc(h_len * sizeof *h);
+    float fc = 0.5f / (float)M;
+    orc_firdes_kaiser(h_len, fc, As, 0.0f, h);
+    orc_firpfbch q = orc_firpfbch_create(type, M, 2 * m, h);
+    free(h);
+    return q;
+}
+
+/* firpfbch.c:193-256 with ftype = LIQUID_FIRFILT_RRC: RRC at k = M, first 2Mm taps,
+ * time-reversed for the analyzer */
+orc_firpfbch orc_firpfbch_create_rrc(int type, unsigned int M, unsigned int m, float beta)
+{
+    if ((type != ORC_ANALYZER && type != ORC_SYNTHESIZER) || M == 0 || m == 0) return NULL;
+    unsigned int h_len = 2 * M * m + 1, g_len = 2 * M * m;
+    float *h = xmalloc(h_len * sizeof *h);
+    float *g = xmalloc(g_len * sizeof *g);
+    if (orc_firdes_rrcos(M, m, beta, 0.0f, h)) { free(h); free(g); return NULL; }
+    for (unsigned int i = 0; i < g_len; i++)
+        g[i] = (type == ORC_SYNTHESIZER) ? h[i] : h[g_len - i - 1];
+    orc_firpfbch q = orc_firpfbch_create(type, M, 2 * m, g);
+    free(h); free(g);
+    return q;
+}
+
+void orc_firpfbch_destroy(orc_firpfbch q)
+{
+    if (q) { free(q->sub); free(q->w); free(q->X); free(q->x); free(q); }
+}
+
+/* firpfbch.c:284-293 */
+void orc_firpfbch_reset(orc_firpfbch q)
+{
+    memset(q->w, 0, (size_t)q->M * q->p * sizeof *q->w);
+    q->filter_index = q->M - 1;
+}
+
+/* firpfbch.c:369-377 */
+void orc_firpfbch_analyzer_push(orc_firpfbch q, orc_cf x)
+{
+    win_push(q->w + (size_t)q->filter_index * q->p, q->p, x);
+    q->filter_index = (q->filter_index + q->M - 1) % q->M;
+}
+
+/* firpfbch.c:383-409: branch i reads window (i+k)%M, lands in transform input M-1-i;
+ * forward transform, no scaling */
+void orc_firpfbch_analyzer_run(orc_firpfbch q, unsigned int k, orc_cf *y)
+{
+    for (unsigned int i = 0; i < q->M; i++) {
+        unsigned int idx = (i + k) % q->M;
+        q->X[q->M - i - 1] = dot_crcf(q->sub + (size_t)i * q->p, q->w + (size_t)idx * q->p, q->p);
+    }
+    orc_fft_run(q->M, q->X, q->x, ORC_FFT_FORWARD);
+    memcpy(y, q->x, q->M * sizeof *y);
+}
+
+/* firpfbch.c:346-359 */
+void orc_firpfbch_analyzer_execute(orc_firpfbch q, const orc_cf *x, orc_cf *y)
+{
+    for (unsigned int i = 0; i < q->M; i++) orc_firpfbch_analyzer_push(q, x[i]);
+    orc_firpfbch_analyzer_run(q, 0, y);
+}
+
+/* firpfbch.c:314-336: backward transform (unscaled), then one FIR step per branch */
+void orc_firpfbch_synthesizer_execute(orc_firpfbch q, const orc_cf *x, orc_cf *y)
+{
+    memcpy(q->X, x, q->M * sizeof *q->X);
+    orc_fft_run(q->M, q->X, q->x, ORC_FFT_BACKWARD);
+    for (unsigned int i = 0; i < q->M; i++) {
+        orc_cf *w = q->w + (size_t)i * q->p;
+        win_push(w, q->p, q->x[i]);
+        y[i] = dot_crcf(q->sub + (size_t)i * q->p, w, q->p);
+    }
+}
+
+void orc_firpfbch_execute_frames(orc_firpfbch q, const orc_cf *x, unsigned int n_frames, orc_cf *y)
+{
+    for (unsigned int t = 0; t < n_frames; t++) {
+        if (q->type == ORC_ANALYZER) orc_firpfbch_analyzer_execute(q, x + (size_t)t * q->M, y + (size_t)t * q->M);
+        else                         orc_firpfbch_synthesizer_execute(q, x + (size_t)t * q->M, y + (size_t)t * q->M);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* firpfbch2_crcf: channelizer with output rate 2 Fs / M                                 */
+/* ------------------------------------------------------------------------------------ */
+
+struct orc_firpfbch2_s {
+    int type;
+    unsigned int M, M2, m, len;     /* len = 2m taps per branch */
+    float *sub;                     /* [M][len] */
+    orc_cf *w0, *w1;                /* [M][len] windows (w1: synthesizer only) */
+    orc_cf *X, *x;
+    int flag;                       /* frame parity */
+};
+
+/* firpfbch2.c:66-128 */
+orc_firpfbch2 orc_firpfbch2_create(int type, unsigned int M, unsigned int m, const float *h)
+{
+    if ((type != ORC_ANALYZER && type != ORC_SYNTHESIZER) || M < 2 || (M % 2) || m < 1) return NULL;
+    orc_firpfbch2 q = xmalloc(sizeof *q);
+    q->type = type; q->M = M; q->M2 = M / 2; q->m = m; q->len = 2 * m;
+    q->sub = polyphase_split(h, M, q->len);
+    q->w0 = xmalloc((size_t)M * q->len * sizeof *q->w0);
+    q->w1 = xmalloc((size_t)M * q->len * sizeof *q->w1);
+    q->X = xmalloc(M * sizeof *q->X);
+    q->x = xmalloc(M * sizeof *q->x);
+    orc_firpfbch2_reset(q);
+    return q;
+}
+
+/* firpfbch2.c:135-183: 2Mm+1 Kaiser taps, fc = 1/M (analyzer) or 0.5/M (synthesizer),
+ * scaled so that the float32 running sum equals M, last tap unused */
+orc_firpfbch2 orc_firpfbch2_create_kaiser(int type, unsigned int M, unsigned int m, float As)
+{
+    if ((type != ORC_ANALYZER && type != ORC_SYNTHESIZER) || M < 2 || (M % 2) || m < 1) return NULL;
+    unsigned int h_len = 2 * M * m + 1;
+    float *hf = xmalloc(h_len * sizeof *hf);
+    float fc = (type == ORC_ANALYZER) ? 1.0f / (float)M : 0.5f / (float)M;
+    orc_firdes_kaiser(h_len, fc, As, 0.0f, hf);
+    float hf_sum = 0.0f;
+    for (unsigned int i = 0; i < h_len; i++) hf_sum += hf[i];
+    for (unsigned int i = 0; i < h_len; i++) hf[i] = hf[i] * (float)M / hf_sum;
+    orc_firpfbch2 q = orc_firpfbch2_create(type, M, m, hf);
+    free(hf);
+    return q;
+}
+
+void orc_firpfbch2_destroy(orc_firpfbch2 q)
+{
+    if (q) { free(q->sub); free(q->w0); free(q->w1); free(q->X); free(q->x); free(q); }
+}
+
+/* firpfbch2.c:213-225 */
+void orc_firpfbch2_reset(orc_firpfbch2 q)
+{
+    memset(q->w0, 0, (size_t)q->M * q->len * sizeof *q->w0);
+    memset(q->w1, 0, (size_t)q->M * q->len * sizeof *q->w1);
+    q->flag = 0;
+}
+
+/* firpfbch2.c:244-282 */
+static void pfbch2_analyze(orc_firpfbch2 q, const orc_cf *x, orc_cf *y)
+{
+    unsigned int M = q->M, M2 = q->M2, len = q->len;
+    /* M/2 new samples go into the lower (even frame) or upper (odd frame) half of the
+     * windows, walking downwards */
+    unsigned int base = q->flag ? M : M2;
+    for (unsigned int i = 0; i < M2; i++)
+        win_push(q->w0 + (size_t)(base - i - 1) * len, len, x[i]);
+    /* branch i meets window (offset+i)%M; the result sits at the window's index */
+    unsigned int offset = q->flag ? M2 : 0;
+    for (unsigned int i = 0; i < M; i++) {
+        unsigned int b = (offset + i) % M;
+        q->X[b] = dot_crcf(q->sub + (size_t)i * len, q->w0 + (size_t)b * len, len);
+    }
+    orc_fft_run(M, q->X, q->x, ORC_FFT_BACKWARD);
+    for (unsigned int i = 0; i < M; i++)
+        y[i] = cf(q->x[i].re / (float)M, q->x[i].im / (float)M);
+    q->flag = 1 - q->flag;
+}
+
+/* firpfbch2.c:287-335 */
+static void pfbch2_synthesize(orc_firpfbch2 q, const orc_cf *x, orc_cf *y)
+{
+    unsigned int M = q->M, M2 = q->M2, len = q->len;
+    memcpy(q->X, x, M * sizeof *q->X);
+    orc_fft_run(M, q->X, q->x, ORC_FFT_BACKWARD);
+    /* two separate float scalings, as the reference does them */
+    float g0 = 1.0f / (float)M, g1 = (float)M2;
+    for (unsigned int i = 0; i < M; i++) { q->x[i].re *= g0; q->x[i].im *= g0; }
+    for (unsigned int i = 0; i < M; i++) { q->x[i].re *= g1; q->x[i].im *= g1; }
+    orc_cf *buf = (q->flag == 0) ? q->w1 : q->w0;
+    for (unsigned int i = 0; i < M; i++)
+        win_push(buf + (size_t)i * len, len, q->x[i]);
+    for (unsigned int i = 0; i < M2; i++) {
+        unsigned int b = (q->flag == 0) ? i : i + M2;
+        const orc_cf *r0 = q->w0 + (size_t)b * len;
+        const orc_cf *r1 = q->w1 + (size_t)b * len;
+        const orc_cf *p0 = q->flag ? r0 : r1;
+        const orc_cf *p1 = q->flag ? r1 : r0;
+        orc_cf y0 = dot_crcf(q->sub + (size_t)i * len, p0, len);
+        orc_cf y1 = dot_crcf(q->sub + (size_t)(i + M2) * len, p1, len);
+        y[i] = cf(y0.re + y1.re, y0.im + y1.im);
+    }
+    q->flag = 1 - q->flag;
+}
+
+/* firpfbch2.c:342-358 */
+void orc_firpfbch2_execute(orc_firpfbch2 q, const orc_cf *x, orc_cf *y)
+{
+    if (q->type == ORC_ANALYZER) pfbch2_analyze(q, x, y);
+    else                         pfbch2_synthesize(q, x, y);
+}
+
+void orc_firpfbch2_execute_frames(orc_firpfbch2 q, const orc_cf *x, unsigned int n_frames, orc_cf *y)
+{
+    size_t in = (q->type == ORC_ANALYZER) ? q->M2 : q->M;
+    size_t out = (q->type == ORC_ANALYZER) ? q->M : q->M2;
+    for (unsigned int t = 0; t < n_frames; t++)
+        orc_firpfbch2_execute(q, x + t * in, y + t * out);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* synthetic input + CPU baseline driver (not a restatement: bench plumbing)             */
+/* ------------------------------------------------------------------------------------ */
+
+static unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+/* u(n,c) = (mix64(seed + 2n + c) >> 40) * 2^-24 - 0.5       */
+void orc_synth_input(unsigned long long seed, unsigned long long first, unsigned long long n, orc_cf *x)
+{
+    for (unsigned long long i = 0; i < n; i++) {
+        unsigned long long k = seed + 2 * (first + i);
+        x[i].re = (float)(mix64(k) >> 40) * (1.0f / 16777216.0f) - 0.5f;
+        x[i].im = (float)(mix64(k + 1) >> 40) * (1.0f / 16777216.0f) - 0.5f;
+    }
+}
+
+struct bench_arg { unsigned int M, m; float As; unsigned long long n; unsigned int id; double secs; };
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void *bench_thread(void *p)
+{
+    struct bench_arg *a = p;
+    orc_firpfbch2 q = orc_firpfbch2_create_kaiser(ORC_ANALYZER, a->M, a->m, a->As);
+    unsigned int M2 = a->M / 2;
+    unsigned long long frames = a->n / M2;
+    unsigned int blk = 256;                                    /* frames per generated block */
+    orc_cf *x = xmalloc((size_t)blk * M2 * sizeof *x);
+    orc_cf *y = xmalloc((size_t)blk * a->M * sizeof *y);
+    orc_synth_input(0x5EED0000ULL + a->id, 0, (unsigned long long)blk * M2, x);
+    double t0 = now_s();
+    for (unsigned long long f = 0; f < frames; f += blk) {
+        unsigned int nb = (frames - f) < blk ? (unsigned int)(frames - f) : blk;
+        orc_firpfbch2_execute_frames(q, x, nb, y);
+    }
+    a->secs = now_s() - t0;
+    free(x); free(y);
+    orc_firpfbch2_destroy(q);
+    return NULL;
+}
+
+double orc_bench_firpfbch2_analysis(unsigned int M, unsigned int m, float As,
+                                    unsigned long long n_samples, unsigned int n_threads)
+{
+    pthread_t *th = xmalloc(n_threads * sizeof *th);
+    struct bench_arg *args = xmalloc(n_threads * sizeof *args);
+    for (unsigned int i = 0; i < n_threads; i++) {
+        args[i].M = M; args[i].m = m; args[i].As = As; args[i].n = n_samples; args[i].id = i; args[i].secs = 0;
+        pthread_create(&th[i], NULL, bench_thread, &args[i]);
+    }
+    double worst = 0;
+    for (unsigned int i = 0; i < n_threads; i++) {
+        pthread_join(th[i], NULL);
+        if (args[i].secs > worst) worst = args[i].secs;
+    }
+    free(th); free(args);
+    return worst;
+}

@@ -1,0 +1,404 @@
+"""ctypes front-end to the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+  * ``liboracle.so``             -- our C restatement (oracle/liquid_oracle.c)
+  * ``_ref/libliquid_ref*.so``   -- the real reference compiled from /root/reference by
+                                    oracle/Makefile (present when built in the dev container;
+                                    travels to the GPU box as a prebuilt .so)
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this module, and only as the checker -- never as the thing measured or shipped.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ANALYZER, SYNTHESIZER = 0, 1
+FFT_FORWARD, FFT_BACKWARD = +1, -1
+
+c_cf_p = np.ctypeslib.ndpointer(dtype=np.complex64, flags="C_CONTIGUOUS")
+c_f_p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+
+class c_cf(C.Structure):
+    """complex float passed by value ({re, im}: same SysV class as C99 `float complex`)"""
+    _fields_ = [("re", C.c_float), ("im", C.c_float)]
+
+
+def build(ref=True):
+    """(re)build liboracle.so and, if /root/reference is present, oracle/_ref."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if ref:
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+def _cpu_flags():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+# ----------------------------------------------------------------------------------------
+# our restatement
+# ----------------------------------------------------------------------------------------
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        L = C.CDLL(path)
+        L.orc_lngammaf.restype = C.c_float; L.orc_lngammaf.argtypes = [C.c_float]
+        L.orc_besseli0f.restype = C.c_float; L.orc_besseli0f.argtypes = [C.c_float]
+        L.orc_sincf.restype = C.c_float; L.orc_sincf.argtypes = [C.c_float]
+        L.orc_kaiser.restype = C.c_float; L.orc_kaiser.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float]
+        L.orc_kaiser_beta_As.restype = C.c_float; L.orc_kaiser_beta_As.argtypes = [C.c_float]
+        L.orc_msb_index.restype = C.c_uint; L.orc_msb_index.argtypes = [C.c_uint]
+        L.orc_firdes_kaiser.restype = C.c_int
+        L.orc_firdes_kaiser.argtypes = [C.c_uint, C.c_float, C.c_float, C.c_float, c_f_p]
+        L.orc_firdes_rrcos.restype = C.c_int
+        L.orc_firdes_rrcos.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float, c_f_p]
+        for name in ("orc_dotprod_crcf_run", "orc_dotprod_crcf_run4", "orc_dotprod_crcf_run_sse_order"):
+            getattr(L, name).restype = None
+            getattr(L, name).argtypes = [c_f_p, c_cf_p, C.c_uint, c_cf_p]
+        L.orc_fft_run.restype = None; L.orc_fft_run.argtypes = [C.c_uint, c_cf_p, c_cf_p, C.c_int]
+        L.orc_firfilt_create.restype = C.c_void_p; L.orc_firfilt_create.argtypes = [c_f_p, C.c_uint]
+        L.orc_firfilt_create_kaiser.restype = C.c_void_p
+        L.orc_firfilt_create_kaiser.argtypes = [C.c_uint, C.c_float, C.c_float, C.c_float]
+        L.orc_firfilt_destroy.argtypes = [C.c_void_p]; L.orc_firfilt_reset.argtypes = [C.c_void_p]
+        L.orc_firfilt_set_scale.argtypes = [C.c_void_p, C.c_float]
+        L.orc_firfilt_execute_block.restype = None
+        L.orc_firfilt_execute_block.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
+        L.orc_firpfb_create.restype = C.c_void_p; L.orc_firpfb_create.argtypes = [C.c_uint, c_f_p, C.c_uint]
+        L.orc_firpfb_create_kaiser.restype = C.c_void_p
+        L.orc_firpfb_create_kaiser.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float]
+        L.orc_firpfb_destroy.argtypes = [C.c_void_p]; L.orc_firpfb_reset.argtypes = [C.c_void_p]
+        L.orc_firpfb_set_scale.argtypes = [C.c_void_p, C.c_float]
+        L.orc_firpfb_push.argtypes = [C.c_void_p, c_cf]
+        L.orc_firpfb_execute.argtypes = [C.c_void_p, C.c_uint, c_cf_p]
+        L.orc_firpfbch_create.restype = C.c_void_p
+        L.orc_firpfbch_create.argtypes = [C.c_int, C.c_uint, C.c_uint, c_f_p]
+        L.orc_firpfbch_create_kaiser.restype = C.c_void_p
+        L.orc_firpfbch_create_kaiser.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float]
+        L.orc_firpfbch_create_rrc.restype = C.c_void_p
+        L.orc_firpfbch_create_rrc.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float]
+        L.orc_firpfbch_destroy.argtypes = [C.c_void_p]; L.orc_firpfbch_reset.argtypes = [C.c_void_p]
+        L.orc_firpfbch_execute_frames.restype = None
+        L.orc_firpfbch_execute_frames.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
+        L.orc_firpfbch_analyzer_run.restype = None
+        L.orc_firpfbch_analyzer_run.argtypes = [C.c_void_p, C.c_uint, c_cf_p]
+        L.orc_firpfbch2_create.restype = C.c_void_p
+        L.orc_firpfbch2_create.argtypes = [C.c_int, C.c_uint, C.c_uint, c_f_p]
+        L.orc_firpfbch2_create_kaiser.restype = C.c_void_p
+        L.orc_firpfbch2_create_kaiser.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float]
+        L.orc_firpfbch2_destroy.argtypes = [C.c_void_p]; L.orc_firpfbch2_reset.argtypes = [C.c_void_p]
+        L.orc_firpfbch2_execute_frames.restype = None
+        L.orc_firpfbch2_execute_frames.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
+        L.orc_synth_input.restype = None
+        L.orc_synth_input.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, c_cf_p]
+        L.orc_bench_firpfbch2_analysis.restype = C.c_double
+        L.orc_bench_firpfbch2_analysis.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_ulonglong, C.c_uint]
+        _lib = L
+    return _lib
+
+
+def _cf(a):
+    return np.ascontiguousarray(a, dtype=np.complex64)
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def firdes_kaiser(n, fc, As, mu=0.0):
+    h = np.empty(n, np.float32)
+    if lib().orc_firdes_kaiser(n, fc, As, mu, h):
+        raise ValueError("liquid_firdes_kaiser: invalid arguments")
+    return h
+
+
+def firdes_rrcos(k, m, beta, dt=0.0):
+    h = np.empty(2 * k * m + 1, np.float32)
+    if lib().orc_firdes_rrcos(k, m, beta, dt, h):
+        raise ValueError("liquid_firdes_rrcos: invalid arguments")
+    return h
+
+
+def dotprod_crcf(h, x, order="run"):
+    y = np.zeros(1, np.complex64)
+    fn = {"run": "orc_dotprod_crcf_run", "run4": "orc_dotprod_crcf_run4",
+          "sse": "orc_dotprod_crcf_run_sse_order"}[order]
+    getattr(lib(), fn)(_f(h), _cf(x), len(h), y)
+    return y[0]
+
+
+def fft(x, direction=FFT_FORWARD):
+    x = _cf(x)
+    y = np.empty_like(x)
+    lib().orc_fft_run(x.size, x, y, direction)
+    return y
+
+
+def synth_input(n, seed=0x5EED0000, first=0):
+    x = np.empty(n, np.complex64)
+    lib().orc_synth_input(seed, first, n, x)
+    return x
+
+
+class _Obj:
+    _destroy = None
+
+    def __init__(self, handle):
+        if not handle:
+            raise ValueError("%s: invalid arguments" % type(self).__name__)
+        self.h = C.c_void_p(handle)
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            getattr(_lib, self._destroy)(self.h)
+            self.h = None
+
+
+class Firfilt(_Obj):
+    _destroy = "orc_firfilt_destroy"
+
+    def __init__(self, h=None, kaiser=None):
+        super().__init__(lib().orc_firfilt_create(_f(h), len(h)) if kaiser is None
+                         else lib().orc_firfilt_create_kaiser(*kaiser))
+
+    def reset(self):
+        lib().orc_firfilt_reset(self.h)
+
+    def set_scale(self, s):
+        lib().orc_firfilt_set_scale(self.h, s)
+
+    def execute_block(self, x):
+        x = _cf(x)
+        y = np.empty_like(x)
+        lib().orc_firfilt_execute_block(self.h, x, x.size, y)
+        return y
+
+
+class Firpfb(_Obj):
+    _destroy = "orc_firpfb_destroy"
+
+    def __init__(self, M, h=None, kaiser=None):
+        super().__init__(lib().orc_firpfb_create(M, _f(h), len(h)) if kaiser is None
+                         else lib().orc_firpfb_create_kaiser(M, *kaiser))
+
+    def reset(self):
+        lib().orc_firpfb_reset(self.h)
+
+    def set_scale(self, s):
+        lib().orc_firpfb_set_scale(self.h, s)
+
+    def push(self, v):
+        v = complex(v)
+        lib().orc_firpfb_push(self.h, c_cf(v.real, v.imag))
+
+    def execute(self, i):
+        y = np.zeros(1, np.complex64)
+        lib().orc_firpfb_execute(self.h, i, y)
+        return y[0]
+
+
+class Firpfbch(_Obj):
+    _destroy = "orc_firpfbch_destroy"
+
+    def __init__(self, type, M, p=None, h=None, kaiser=None, rrc=None):
+        self.type, self.M = type, M
+        if kaiser is not None:
+            hd = lib().orc_firpfbch_create_kaiser(type, M, *kaiser)
+        elif rrc is not None:
+            hd = lib().orc_firpfbch_create_rrc(type, M, *rrc)
+        else:
+            hd = lib().orc_firpfbch_create(type, M, p, _f(h))
+        super().__init__(hd)
+
+    def reset(self):
+        lib().orc_firpfbch_reset(self.h)
+
+    def execute_frames(self, x):
+        x = _cf(x).reshape(-1, self.M)
+        y = np.empty_like(x)
+        lib().orc_firpfbch_execute_frames(self.h, x, x.shape[0], y)
+        return y
+
+
+class Firpfbch2(_Obj):
+    _destroy = "orc_firpfbch2_destroy"
+
+    def __init__(self, type, M, m, h=None, As=None):
+        self.type, self.M = type, M
+        hd = (lib().orc_firpfbch2_create_kaiser(type, M, m, As) if h is None
+              else lib().orc_firpfbch2_create(type, M, m, _f(h)))
+        super().__init__(hd)
+
+    def reset(self):
+        lib().orc_firpfbch2_reset(self.h)
+
+    def execute_frames(self, x):
+        n_in = self.M // 2 if self.type == ANALYZER else self.M
+        n_out = self.M if self.type == ANALYZER else self.M // 2
+        x = _cf(x).reshape(-1, n_in)
+        y = np.empty((x.shape[0], n_out), np.complex64)
+        lib().orc_firpfbch2_execute_frames(self.h, x, x.shape[0], y)
+        return y
+
+
+def bench_firpfbch2_analysis(M, m, As, n_samples, n_threads):
+    """wall seconds for n_threads independent oracle instances, n_samples each ("port" baseline)."""
+    return lib().orc_bench_firpfbch2_analysis(M, m, As, n_samples, n_threads)
+
+
+# ----------------------------------------------------------------------------------------
+# the real reference (oracle/_ref), when it has been built
+# ----------------------------------------------------------------------------------------
+_ref = None
+_drv = None
+
+
+def ref_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libliquid_ref_sse.so"))
+
+
+def _ref_variant():
+    flags = _cpu_flags()
+    return "" if {"avx2", "fma", "bmi2"} <= flags else "_sse"
+
+
+def ref():
+    """ctypes handle on the compiled reference; raises if oracle/_ref was never built."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(HERE, "_ref", "libliquid_ref%s.so" % _ref_variant())
+        if not os.path.exists(path):
+            raise FileNotFoundError("oracle/_ref not built (run `make -C oracle ref` where /root/reference exists)")
+        R = C.CDLL(path)
+        R.liquid_firdes_kaiser.restype = None
+        R.liquid_firdes_kaiser.argtypes = [C.c_uint, C.c_float, C.c_float, C.c_float, c_f_p]
+        R.liquid_firdes_rrcos.restype = None
+        R.liquid_firdes_rrcos.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float, c_f_p]
+        R.liquid_besseli0f.restype = C.c_float; R.liquid_besseli0f.argtypes = [C.c_float]
+        R.liquid_lngammaf.restype = C.c_float; R.liquid_lngammaf.argtypes = [C.c_float]
+        R.kaiser_beta_As.restype = C.c_float; R.kaiser_beta_As.argtypes = [C.c_float]
+        R.kaiser.restype = C.c_float; R.kaiser.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float]
+        R.sincf.restype = C.c_float; R.sincf.argtypes = [C.c_float]
+        R.liquid_msb_index.restype = C.c_uint; R.liquid_msb_index.argtypes = [C.c_uint]
+        R.dotprod_crcf_run.argtypes = [c_f_p, c_cf_p, C.c_uint, c_cf_p]
+        R.dotprod_crcf_create.restype = C.c_void_p; R.dotprod_crcf_create.argtypes = [c_f_p, C.c_uint]
+        R.dotprod_crcf_execute.argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+        R.dotprod_crcf_destroy.argtypes = [C.c_void_p]
+        R.fft_run.argtypes = [C.c_uint, c_cf_p, c_cf_p, C.c_int, C.c_int]
+        R.firfilt_crcf_create.restype = C.c_void_p; R.firfilt_crcf_create.argtypes = [c_f_p, C.c_uint]
+        R.firfilt_crcf_create_kaiser.restype = C.c_void_p
+        R.firfilt_crcf_create_kaiser.argtypes = [C.c_uint, C.c_float, C.c_float, C.c_float]
+        R.firfilt_crcf_set_scale.argtypes = [C.c_void_p, C.c_float]
+        R.firfilt_crcf_execute_block.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
+        R.firfilt_crcf_destroy.argtypes = [C.c_void_p]
+        R.firpfb_crcf_create.restype = C.c_void_p; R.firpfb_crcf_create.argtypes = [C.c_uint, c_f_p, C.c_uint]
+        R.firpfb_crcf_push.argtypes = [C.c_void_p, c_cf]
+        R.firpfb_crcf_execute.argtypes = [C.c_void_p, C.c_uint, c_cf_p]
+        R.firpfb_crcf_destroy.argtypes = [C.c_void_p]
+        R.firpfbch_crcf_create.restype = C.c_void_p
+        R.firpfbch_crcf_create.argtypes = [C.c_int, C.c_uint, C.c_uint, c_f_p]
+        R.firpfbch_crcf_create_kaiser.restype = C.c_void_p
+        R.firpfbch_crcf_create_kaiser.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float]
+        R.firpfbch_crcf_create_rnyquist.restype = C.c_void_p
+        R.firpfbch_crcf_create_rnyquist.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_int]
+        R.firpfbch_crcf_analyzer_execute.argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+        R.firpfbch_crcf_synthesizer_execute.argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+        R.firpfbch_crcf_destroy.argtypes = [C.c_void_p]
+        R.firpfbch2_crcf_create.restype = C.c_void_p
+        R.firpfbch2_crcf_create.argtypes = [C.c_int, C.c_uint, C.c_uint, c_f_p]
+        R.firpfbch2_crcf_create_kaiser.restype = C.c_void_p
+        R.firpfbch2_crcf_create_kaiser.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float]
+        R.firpfbch2_crcf_execute.argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+        R.firpfbch2_crcf_destroy.argtypes = [C.c_void_p]
+        R.msequence_create_default.restype = C.c_void_p; R.msequence_create_default.argtypes = [C.c_uint]
+        R.msequence_generate_symbol.restype = C.c_uint
+        R.msequence_generate_symbol.argtypes = [C.c_void_p, C.c_uint]
+        R.msequence_destroy.argtypes = [C.c_void_p]
+        _ref = R
+    return _ref
+
+
+def ref_driver():
+    global _drv
+    if _drv is None:
+        path = os.path.join(HERE, "_ref", "libref_driver%s.so" % _ref_variant())
+        if not os.path.exists(path):
+            raise FileNotFoundError("oracle/_ref driver not built")
+        D = C.CDLL(path)
+        D.ref_bench.restype = C.c_double
+        D.ref_bench.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_ulonglong, C.c_uint]
+        D.ref_pfbch2_analysis.restype = None
+        D.ref_pfbch2_analysis.argtypes = [C.c_uint, C.c_uint, C.c_float, c_cf_p, C.c_uint, c_cf_p]
+        _drv = D
+    return _drv
+
+
+def ref_firpfbch2_frames(type, M, m, As, x, h=None):
+    R = ref()
+    q = R.firpfbch2_crcf_create_kaiser(type, M, m, As) if h is None else R.firpfbch2_crcf_create(type, M, m, _f(h))
+    q = C.c_void_p(q)
+    n_in = M // 2 if type == ANALYZER else M
+    n_out = M if type == ANALYZER else M // 2
+    x = _cf(x).reshape(-1, n_in)
+    y = np.empty((x.shape[0], n_out), np.complex64)
+    for t in range(x.shape[0]):
+        R.firpfbch2_crcf_execute(q, x[t], y[t])
+    R.firpfbch2_crcf_destroy(q)
+    return y
+
+
+def ref_firpfbch_frames(type, M, x, p=None, h=None, kaiser=None, rnyquist=None):
+    R = ref()
+    if kaiser is not None:
+        q = R.firpfbch_crcf_create_kaiser(type, M, *kaiser)
+    elif rnyquist is not None:
+        q = R.firpfbch_crcf_create_rnyquist(type, M, *rnyquist)
+    else:
+        q = R.firpfbch_crcf_create(type, M, p, _f(h))
+    q = C.c_void_p(q)
+    x = _cf(x).reshape(-1, M)
+    y = np.empty_like(x)
+    fn = R.firpfbch_crcf_analyzer_execute if type == ANALYZER else R.firpfbch_crcf_synthesizer_execute
+    for t in range(x.shape[0]):
+        fn(q, x[t], y[t])
+    R.firpfbch_crcf_destroy(q)
+    return y
+
+
+def ref_firfilt_block(x, h=None, kaiser=None, scale=None):
+    R = ref()
+    q = C.c_void_p(R.firfilt_crcf_create(_f(h), len(h)) if kaiser is None else R.firfilt_crcf_create_kaiser(*kaiser))
+    if scale is not None:
+        R.firfilt_crcf_set_scale(q, scale)
+    x = _cf(x)
+    y = np.empty_like(x)
+    R.firfilt_crcf_execute_block(q, x, x.size, y)
+    R.firfilt_crcf_destroy(q)
+    return y
+
+
+def ref_fft(x, direction=FFT_FORWARD):
+    x = _cf(x)
+    y = np.empty_like(x)
+    ref().fft_run(x.size, x, y, direction, 0)
+    return y
+
+
+def ref_bench(kind, M, m, As, n_samples, n_threads):
+    """wall seconds: n_threads reference instances, n_samples each (kind 0 pfbch2, 1 pfbch, 2 firfilt)."""
+    return ref_driver().ref_bench(kind, M, m, As, n_samples, n_threads)

@@ -1,0 +1,273 @@
+"""Pin the CPU oracle (oracle/liquid_oracle.c): against the reference's own golden vectors,
+against committed outputs of the compiled reference, against the live compiled reference when
+oracle/_ref is present, against float64 closed forms, and through the reference's autotest
+properties.  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import TOL_MAX_ABS, TOL_REL_RMS, cplx, max_abs_norm, rel_rms_per_channel
+import closed_form as CF
+
+
+# ---------------------------------------------------------------- reference golden vectors
+def test_kat_besseli0f(orc, kat):
+    for z, want in kat["besseli0f"]["points"]:
+        assert abs(orc.lib().orc_besseli0f(z) - want) < kat["besseli0f"]["tol"]
+
+
+def test_kat_firdes_rrcos(orc, kat):
+    k = kat["firdes_rrcos"]
+    h = orc.firdes_rrcos(k["k"], k["m"], k["beta"])
+    assert np.abs(h - np.array(k["h"])).max() < k["tol"]
+
+
+def test_kat_dotprod_crcf(orc, kat):
+    for case in kat["dotprod_crcf"]["cases"]:
+        want = complex(*case["y"])
+        for order in ("run", "run4", "sse"):
+            got = orc.dotprod_crcf(case["h"], cplx(case["x"]), order)
+            assert abs(got - want) < kat["dotprod_crcf"]["tol"]
+
+
+@pytest.mark.parametrize("tag", ["h4x8", "h7x16", "h13x32", "h23x64"])
+def test_kat_firfilt_crcf(orc, kat, tag):
+    case = kat["firfilt_crcf"]["cases"][tag]
+    y = orc.Firfilt(h=case["h"]).execute_block(cplx(case["x"]))
+    assert np.abs(y - cplx(case["y"])).max() < kat["firfilt_crcf"]["tol"]
+
+
+def test_kat_fft_all_sizes(orc, kat):
+    for n, case in kat["fft"]["cases"].items():
+        x, want = cplx(case["x"]), cplx(case["y"])
+        y = orc.fft(x, orc.FFT_FORWARD)
+        assert np.abs(y - want).max() < kat["fft"]["tol"], n
+        z = orc.fft(y, orc.FFT_BACKWARD) / np.float32(int(n))
+        assert np.abs(z - x).max() < kat["fft"]["tol"], n
+
+
+def test_kat_firpfb(orc, kat):
+    k = kat["firpfb"]
+    q = orc.Firpfb(k["M"], h=k["h"])
+    for v in k["x"]:
+        q.push(v)
+    for i, want in enumerate(k["y"]):
+        got = q.execute(i)
+        assert abs(got.real - want) < k["tol"] and abs(got.imag) < k["tol"]
+
+
+def test_msb_index(orc):
+    for x in [0, 1, 2, 3, 4, 7, 8, 14, 15, 16, 18, 1023, 1024, 2**31]:
+        assert orc.lib().orc_msb_index(x) == x.bit_length()
+
+
+# ---------------------------------------------------------------- committed reference outputs
+def test_fixture_kaiser_taps(orc, refout):
+    names = [k for k in refout if k.startswith("kaiser_") and not k.endswith("_args")]
+    assert len(names) >= 6
+    for name in names:
+        n, fc, As = refout[name + "_args"]
+        h = orc.firdes_kaiser(int(n), np.float32(fc), np.float32(As))
+        # float32 design; the compiled reference contracts a few FMAs -> allow 4 ulp of the peak
+        assert np.abs(h - refout[name]).max() <= 5e-7, name
+
+
+def test_fixture_rrcos_taps(orc, refout):
+    for name in [k for k in refout if k.startswith("rrcos_") and not k.endswith("_args")]:
+        k, m, beta = refout[name + "_args"]
+        h = orc.firdes_rrcos(int(k), int(m), np.float32(beta))
+        assert np.abs(h - refout[name]).max() <= 1e-6, name
+
+
+@pytest.mark.parametrize("M,m", [(8, 5), (16, 5), (64, 3), (6, 2), (256, 4)])
+def test_fixture_pfbch2(orc, refout, M, m):
+    for kind, typ in (("a", orc.ANALYZER), ("s", orc.SYNTHESIZER)):
+        x = refout["pfbch2_%s_M%d_m%d_x" % (kind, M, m)]
+        want = refout["pfbch2_%s_M%d_m%d_y" % (kind, M, m)]
+        y = orc.Firpfbch2(typ, M, m, As=60.0).execute_frames(x)
+        if kind == "a":
+            assert max_abs_norm(y, want, x) < 2e-6
+            assert rel_rms_per_channel(y, want).max() < 2e-6
+        else:
+            assert np.abs(y - want).max() / np.abs(want).max() < 2e-6
+
+
+@pytest.mark.parametrize("M,m", [(4, 3), (16, 4), (10, 2), (64, 5)])
+def test_fixture_pfbch(orc, refout, M, m):
+    x = refout["pfbch_a_M%d_m%d_x" % (M, m)]
+    for kind, typ in (("a", orc.ANALYZER), ("s", orc.SYNTHESIZER)):
+        want = refout["pfbch_%s_M%d_m%d_y" % (kind, M, m)]
+        y = orc.Firpfbch(typ, M, kaiser=(m, 60.0)).execute_frames(x)
+        assert np.abs(y - want).max() / np.abs(want).max() < 2e-6
+
+
+def test_fixture_pfbch_rrc(orc, refout):
+    x = refout["pfbch_rrc_M8_m3_x"]
+    for kind, typ in (("a", orc.ANALYZER), ("s", orc.SYNTHESIZER)):
+        want = refout["pfbch_rrc_%s_M8_m3_y" % kind]
+        y = orc.Firpfbch(typ, 8, rrc=(3, 0.4)).execute_frames(x)
+        assert np.abs(y - want).max() / np.abs(want).max() < 2e-6
+
+
+def test_fixture_firfilt(orc, refout):
+    x = refout["firfilt_k64_x"]
+    q = orc.Firfilt(kaiser=(64, 0.25, 60.0, 0.0))
+    assert np.abs(q.execute_block(x) - refout["firfilt_k64_y"]).max() < 1e-6
+    q.reset()
+    q.set_scale(0.375)
+    assert np.abs(q.execute_block(x) - refout["firfilt_k64_scale_y"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("n", [128, 256, 1024, 4096])
+def test_fixture_fft(orc, refout, n):
+    x = refout["fft_%d_x" % n]
+    for d, key in ((orc.FFT_FORWARD, "fwd"), (orc.FFT_BACKWARD, "bwd")):
+        want = refout["fft_%d_%s" % (n, key)]
+        y = orc.fft(x, d)
+        assert np.abs(y - want).max() / np.abs(want).max() < 2e-6
+
+
+def test_fixture_survey_fingerprints(orc, refout):
+    """SURVEY.md section 8c fingerprints of firpfbch2 analysis on the autotest LCG input"""
+    y = orc.Firpfbch2(orc.ANALYZER, 16, 5, As=60.0).execute_frames(refout["pfbch2_a_M16_m5_lcg_x"])
+    assert abs(y[0, 0] - (-7.94109947e-05)) < 1e-9
+    assert abs(y[21, 1] - (1.93961821e-02 - 8.78997445e-02j)) < 1e-7
+    assert abs(y[79, 2] - (-7.58994371e-02 - 8.95354375e-02j)) < 1e-7
+    assert np.abs(y - refout["pfbch2_a_M16_m5_lcg_y"]).max() < 1e-7
+
+
+# ---------------------------------------------------------------- live compiled reference
+def _need_ref(orc):
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref not built here")
+
+
+@pytest.mark.parametrize("M,m,nfr", [(32, 5, 64), (1024, 7, 40), (12, 3, 30)])
+def test_live_ref_pfbch2_analysis(orc, M, m, nfr):
+    _need_ref(orc)
+    x = orc.synth_input(nfr * M // 2, seed=77 + M)
+    y = orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0).execute_frames(x)
+    want = orc.ref_firpfbch2_frames(orc.ANALYZER, M, m, 60.0, x)
+    assert rel_rms_per_channel(y, want).max() < 2e-6
+    assert max_abs_norm(y, want, x) < 1e-6
+
+
+def test_live_ref_scalar_math(orc):
+    _need_ref(orc)
+    R, L = orc.ref(), orc.lib()
+    for z in [0.05, 0.5, 1.0, 2.5, 5.65, 9.99, 10.0, 33.3]:
+        assert abs(L.orc_lngammaf(z) - R.liquid_lngammaf(z)) <= 4e-6 * max(1.0, abs(R.liquid_lngammaf(z)))
+        assert abs(L.orc_besseli0f(z) - R.liquid_besseli0f(z)) <= 4e-6 * R.liquid_besseli0f(z)
+    for x in [0.0, 0.001, 0.0099, 0.01, 0.3, 1.0, 2.5, -7.25]:
+        assert abs(L.orc_sincf(x) - R.sincf(x)) <= 2e-7
+    for As in [10.0, 21.0, 35.0, 50.0, 60.0, 80.0, -60.0]:
+        assert L.orc_kaiser_beta_As(As) == pytest.approx(R.kaiser_beta_As(As), rel=1e-6)
+
+
+def test_live_ref_dotprod_orders(orc):
+    _need_ref(orc)
+    import ctypes as C
+    R = orc.ref()
+    rng = np.random.default_rng(5)
+    for n in [1, 2, 3, 7, 14, 18, 31, 32, 33, 64, 100, 512]:
+        h = rng.standard_normal(n).astype(np.float32)
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        want = np.zeros(1, np.complex64)
+        q = C.c_void_p(R.dotprod_crcf_create(h, n))
+        R.dotprod_crcf_execute(q, x, want)
+        R.dotprod_crcf_destroy(q)
+        got = orc.dotprod_crcf(h, x, "sse")
+        assert abs(got - want[0]) <= 2e-6 * np.sqrt(n) * 4
+
+
+# ---------------------------------------------------------------- float64 closed forms
+def test_closed_form_pfbch2_analysis(orc):
+    M, m = 16, 3
+    h = orc.firdes_kaiser(2 * M * m + 1, 1.0 / M, 60.0)
+    hs = (h.astype(np.float32) * np.float32(M) / np.float32(np.cumsum(h, dtype=np.float32)[-1]))
+    x = orc.synth_input(30 * M // 2, seed=3)
+    y = orc.Firpfbch2(orc.ANALYZER, M, m, h=hs[: 2 * M * m]).execute_frames(x)
+    want = CF.pfbch2_analysis(hs, M, m, x)
+    assert rel_rms_per_channel(y, want).max() < TOL_REL_RMS / 10
+    assert max_abs_norm(y, want, x) < TOL_MAX_ABS / 10
+
+
+def test_closed_form_pfbch2_synthesis(orc):
+    M, m = 8, 2
+    rng = np.random.default_rng(1)
+    h = rng.standard_normal(2 * M * m).astype(np.float32)
+    X = orc.synth_input(20 * M, seed=4)
+    y = orc.Firpfbch2(orc.SYNTHESIZER, M, m, h=h).execute_frames(X).reshape(-1)
+    want = CF.pfbch2_synthesis(h, M, m, X)
+    assert np.abs(y - want).max() / np.abs(want).max() < 1e-5
+
+
+def test_closed_form_pfbch(orc):
+    M, p = 12, 5
+    rng = np.random.default_rng(2)
+    h = rng.standard_normal(M * p).astype(np.float32)
+    x = orc.synth_input(25 * M, seed=5)
+    ya = orc.Firpfbch(orc.ANALYZER, M, p=p, h=h).execute_frames(x)
+    assert np.abs(ya - CF.pfbch_analysis(h, M, p, x)).max() / np.abs(ya).max() < 1e-5
+    ys = orc.Firpfbch(orc.SYNTHESIZER, M, p=p, h=h).execute_frames(x).reshape(-1)
+    assert np.abs(ys - CF.pfbch_synthesis(h, M, p, x)).max() / np.abs(ys).max() < 1e-5
+
+
+def test_firfilt_is_convolution(orc):
+    rng = np.random.default_rng(3)
+    h = rng.standard_normal(23).astype(np.float32)
+    x = orc.synth_input(500, seed=6)
+    y = orc.Firfilt(h=h).execute_block(x)
+    want = np.convolve(x.astype(np.complex128), h.astype(np.float64))[: x.size]
+    assert np.abs(y - want).max() < 1e-5
+
+
+# ---------------------------------------------------------------- reference autotest properties
+@pytest.mark.parametrize("M", [8, 16, 32, 64])
+def test_autotest_pfbch2_roundtrip(orc, M):
+    """firpfbch2_crcf_autotest.c:27-99: analysis -> synthesis reconstructs x delayed by
+    2Mm - M/2 + 1, tolerance 1e-3"""
+    m, As = 5, 60.0
+    n = M * 8 * m
+    s, x = 1, np.empty(n, np.complex64)
+    for i in range(n):
+        s = (s * 524287) % 1031
+        x[i] = np.float32(s) / np.float32(1031) - np.float32(0.5)
+    Y = orc.Firpfbch2(orc.ANALYZER, M, m, As=As).execute_frames(x)
+    y = orc.Firpfbch2(orc.SYNTHESIZER, M, m, As=As).execute_frames(Y).reshape(-1)
+    delay = 2 * M * m - M // 2 + 1
+    assert np.abs(y[:delay]).max() < 1e-3
+    assert np.abs(y[delay:] - x[: n - delay]).max() < 1e-3
+
+
+def test_autotest_pfbch_analyzer_equals_mixer_filter_decimate(orc):
+    """firpfbch_crcf_analyzer_autotest.c:29-152: channel c == mix down by c/M, FIR h, keep
+    every M-th; tolerance 1e-4"""
+    M, p, S = 4, 5, 40
+    rng = np.random.default_rng(9)
+    h = (rng.integers(0, 4, M * p) - 1.5).astype(np.float32)
+    x = (0.1 * np.sqrt(0.5) * ((rng.integers(0, 4, M * S) - 1.5) + 1j * (rng.integers(0, 4, M * S) - 1.5))).astype(np.complex64)
+    Y0 = orc.Firpfbch(orc.ANALYZER, M, p=p, h=h).execute_frames(x)
+    j = np.arange(M * S)
+    for c in range(M):
+        mixed = (x * np.exp(-2j * np.pi * c * j / M)).astype(np.complex64)
+        y = orc.Firfilt(h=h).execute_block(mixed)
+        assert np.abs(Y0[:, c] - y[M - 1::M]).max() < 1e-4
+
+
+def test_state_carry_and_reset(orc):
+    """k x execute == one block of k frames; reset returns to the zero state"""
+    M, m = 16, 4
+    x = orc.synth_input(40 * M // 2, seed=8)
+    q = orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0)
+    whole = q.execute_frames(x)
+    q.reset()
+    parts = np.concatenate([q.execute_frames(x[: 7 * M // 2]), q.execute_frames(x[7 * M // 2:])])
+    assert np.array_equal(whole, parts)
+
+
+def test_synth_input_is_deterministic_and_bounded(orc):
+    a = orc.synth_input(1000, seed=11)
+    b = orc.synth_input(500, seed=11, first=500)
+    assert np.array_equal(a[500:], b)
+    assert a.real.min() >= -0.5 and a.real.max() < 0.5 and abs(a.real.mean()) < 0.05
+    assert 0.07 < np.mean(np.abs(a) ** 2) < 0.25
