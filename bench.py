@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the channelizer hot path (BASELINE.json metric:
+"firpfbch2 M=1024 input MS/s @1/2/4/8 B200; % of HBM roofline").
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step is one pass of firpfbch2_crcf analysis (M=1024, m=7, As=60 dB Kaiser prototype) over one
+2^30-sample complex stream segment per GPU (BASELINE.json configs[2]); inputs are synthetic and
+already resident in HBM for `value`.  With N>1 the N segments are consecutive time segments of ONE
+long stream: every step each rank sends the last 2mM input samples of its segment to its right
+neighbour with NCCL send/recv (the filter-history halo), the interior frames run while the halo is in
+flight.  Weak scaling: per-GPU work is fixed.
+
+`e2e` is the same metric through the host-pointer C ABI call firpfbch2_crcf_execute_block with
+pinned host buffers: H2D of the input and D2H of the channelised output inside the timed region.
+
+Only the cpu_baseline leg and --impl reference execute anything under oracle/ (the compiled
+reference in oracle/_ref when present, else the oracle port) -- as the baseline, never as the
+thing measured.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+M, SEMI, AS = 1024, 7, 60.0
+BYTES_PER_SAMPLE = 24            # algorithmic: 8 B read + 16 B written per input sample
+METRIC = "firpfbch2_crcf analysis M=1024 m=7 input throughput"
+UNIT = "MS/s"
+
+
+def workload_name(n_samples, n_gpus):
+    return ("firpfbch2_crcf analysis M=%d m=%d As=%g Kaiser, 2^%d complex samples per GPU"
+            % (M, SEMI, AS, n_samples.bit_length() - 1)
+            + ("" if n_gpus == 1 else ", %d consecutive time segments of one stream, NCCL halo exchange" % n_gpus))
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region (NVML in a background thread; nvidia-smi CLI is too slow
+# for a region that lasts tens of milliseconds)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:          # noqa: BLE001
+            self.nv = None
+            self.err = str(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonGpuIdle", 0x1): "gpu_idle",
+            getattr(nv, "nvmlClocksEventReasonApplicationsClocksSetting", 0x2): "applications_clocks_setting",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSyncBoost", 0x10): "sync_boost",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:   # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:       # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline (reference implementation on the host cores) -- the one place oracle/ is executed
+# --------------------------------------------------------------------------------------------
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_cpu_reference(n_per_core, cores):
+    """(MS/s aggregate, kind, sample description): `cores` independent instances, one per core,
+    each on its own synthetic stream of n_per_core samples, started together"""
+    from oracle import oracle as O
+    if O.ref_available():
+        secs = O.ref_bench(0, M, SEMI, AS, n_per_core, cores)
+        kind = "reference"
+    else:
+        O.build(ref=False)
+        secs = O.bench_firpfbch2_analysis(M, SEMI, AS, n_per_core, cores)
+        kind = "port"
+    value = cores * n_per_core / secs / 1e6
+    sample = ("%d instances (one per host core), independent synthetic streams of 2^%d samples each, "
+              "wall time of the slowest thread %.3f s" % (cores, n_per_core.bit_length() - 1, secs))
+    return value, kind, sample
+
+
+def impl_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = cpu_cores()
+    n_per_core = 1 << args.ref_log2_samples
+    for _ in range(args.warmup):
+        run_cpu_reference(n_per_core // 4, cores)
+    t_total, kind, sample = 0.0, None, None
+    vals = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        v, kind, sample = run_cpu_reference(n_per_core, cores)
+        t_total += time.perf_counter() - t0
+        vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(1 << 30, 1),
+                   "note": "reference CPU implementation (liquid-dsp firpfbch2_crcf_execute, internal FFT, SSE dotprod) "
+                           "on the host cores; each step is a bounded sample of the workload: " + sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-samples", type=int, default=30, help="input samples per GPU per step (log2)")
+    ap.add_argument("--e2e-log2-samples", type=int, default=28, help="input samples per e2e step (log2)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-log2-samples", type=int, default=24, help="cpu_baseline samples per core (log2)")
+    ap.add_argument("--ref-log2-samples", type=int, default=22, help="--impl reference samples per core per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return impl_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import liquid_dsp_b200 as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    L.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = 1 << args.log2_samples                     # input samples per GPU per step
+    n_frames = n // (M // 2)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, SEMI, AS)
+    H = q.get_state_len()                          # 2mM samples of history = the halo
+    halo_frames = H // (M // 2)                    # 4m frames depend on the halo
+
+    # device-resident input with H samples of headroom in front (halo lands there), output [n_frames][M]
+    xbuf = torch.empty(2 * (H + n), dtype=torch.float32, device=dev)
+    ybuf = torch.empty(2 * n_frames * M, dtype=torch.float32, device=dev)
+    xbuf[: 2 * H].zero_()
+    stream = torch.cuda.current_stream()
+    d_halo = xbuf.data_ptr()
+    d_x = d_halo + 8 * H
+    d_y = ybuf.data_ptr()
+    # rank r holds samples [r*n, (r+1)*n) of the one long synthetic stream
+    L.synth_input_dev(d_x, n, seed=0x5EED0000, first=rank * n, stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+
+    first_frame = rank * n_frames                  # even: every segment starts with flag = 0
+    tail = xbuf[2 * n: 2 * (H + n)]                # last H samples of the local segment
+    head = xbuf[: 2 * H]
+
+    def step():
+        if world > 1:
+            reqs = []
+            if rank + 1 < world:
+                reqs.append(dist.isend(tail, rank + 1))
+            if rank > 0:
+                reqs.append(dist.irecv(head, rank - 1))
+            # interior frames do not see the halo: run them while it is in flight
+            q.execute_segment_dev(d_x + 8 * (halo_frames * (M // 2)) - 8 * H, d_x + 8 * halo_frames * (M // 2),
+                                  first_frame + halo_frames, n_frames - halo_frames,
+                                  d_y + 8 * halo_frames * M, stream.cuda_stream)
+            for r in reqs:
+                r.wait()
+            q.execute_segment_dev(d_halo, d_x, first_frame, halo_frames, d_y, stream.cuda_stream)
+        else:
+            q.execute_segment_dev(d_halo, d_x, first_frame, n_frames, d_y, stream.cuda_stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    sync_all()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = L.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    sampler.start()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    sync_all()
+    clocks = sampler.stop()
+    launches = L.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * n * args.steps / (total_ms * 1e-3) / 1e6          # MS/s, whole job
+
+    # roofline of the dominant kernel: algorithmic bytes per launch / average launch duration.
+    # One step on one GPU is one pass of the fused channelizer kernel(s) over n samples; the
+    # duration is the CUDA-event time of the step on the launching stream (this rank).
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    avg_step_ms = sum(step_ms) / len(step_ms)
+    achieved = BYTES_PER_SAMPLE * n / (avg_step_ms * 1e-3) / 1e9
+    kernels_per_step = launches / max(args.steps, 1)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "firpfbch2 analysis (%.0f launch(es) per step: %s)" % (
+                    kernels_per_step, "pfbch2_mac_kernel + fft_pow2_kernel" if kernels_per_step >= 2 else "fused"),
+                "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n,
+                "avg_launch_ms": avg_step_ms, "frac_of_8TBps_nominal": achieved / 8000.0}
+
+    # end to end through the host-pointer C ABI (pinned host buffers, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        ne = 1 << args.e2e_log2_samples
+        nfe = ne // (M // 2)
+        hx = L.pinned_empty(ne)
+        hy = L.pinned_empty(nfe * M)
+        # fill the pinned input with the same synthetic stream (generated on the device, copied back)
+        import ctypes as C
+        L.synth_input_dev(d_x, min(ne, n), seed=0x5EED0000, first=rank * n, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        L.lib.liquid_cuda_memcpy_d2h(hx.ctypes.data_as(C.c_void_p), d_x, min(ne, n) * 8)
+        qe = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, SEMI, AS)
+        qe.execute_block(hx, out=hy)                        # warm-up (allocates staging buffers)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            qe.execute_block(hx, out=hy)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * ne * args.e2e_steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": ne * 8, "d2h_bytes_per_step": nfe * M * 8,
+               "samples_per_step_per_gpu": ne, "steps": args.e2e_steps,
+               "api": "firpfbch2_crcf_execute_block (host pointers, pinned, chunked H2D/compute/D2H pipeline)"}
+        qe.destroy()
+        L.pinned_free(hx)
+        L.pinned_free(hy)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = cpu_cores()
+        v, kind, sample = run_cpu_reference(1 << args.cpu_log2_samples, cores)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(n, world),
+                       "l2": "inputs larger than L2: %d MiB read + %d MiB written per GPU per step, no flush needed"
+                             % (n * 8 >> 20, n * 16 >> 20),
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

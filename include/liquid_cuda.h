@@ -1,0 +1,218 @@
+/*
+ * liquid_cuda.h -- C ABI of libliquid_cuda.so: the B200 (sm_100a) implementation of liquid-dsp's
+ * polyphase filterbank channelizer hot path.
+ *
+ * Part 1 re-declares, with the reference's exact names and signatures, the slice of
+ * include/liquid.h (reference, /root/reference) that this library replaces; each block cites the
+ * reference declaration (liquid.h:line) and the reference definition it stands in for.
+ * A program that already includes <liquid.h> keeps doing so and simply links -lliquid_cuda ahead of
+ * -lliquid: Part 1 is skipped (guarded by __LIQUID_H__) and only Part 2 is added.
+ *
+ * Part 2 are the batched / device-pointer / state entry points a GPU needs (the reference's
+ * one-frame-per-call execute is kept for drop-in use but moves 4 KB per call).
+ *
+ * Conventions kept from the reference: create* allocates and returns an opaque handle, copies the
+ * taps (caller keeps its array); destroy frees everything; invalid arguments print
+ * "error: <fn>(), <msg>" to stderr and exit(1); execute functions return void; objects are not
+ * thread-safe, distinct objects are independent.  CUDA failures print the CUDA error and abort().
+ * There is no CPU fallback anywhere in this library: without a CUDA device every create aborts.
+ *
+ * All pointers are plain host pointers unless the name ends in _dev (device pointers, asynchronous
+ * on the given cudaStream_t passed as void*; NULL = the legacy default stream).
+ */
+#ifndef LIQUID_CUDA_H
+#define LIQUID_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ============================================================================================
+ * Part 1 -- the reference API surface (skipped when <liquid.h> is already included)
+ * ============================================================================================ */
+#ifndef __LIQUID_H__
+
+/* complex float: interleaved {re, im}, layout- and ABI-compatible with C99 `float complex`
+ * (liquid.h:77-88) */
+#if defined(__STDC_VERSION__) && !defined(__cplusplus) && !defined(LIQUID_CUDA_NO_COMPLEX_H)
+#  include <complex.h>
+typedef float _Complex liquid_float_complex;
+#else
+typedef struct { float real; float imag; } liquid_float_complex;
+#endif
+
+#define LIQUID_ANALYZER     0       /* liquid.h:5651 */
+#define LIQUID_SYNTHESIZER  1       /* liquid.h:5652 */
+#define LIQUID_FFT_FORWARD  (+1)    /* liquid.h:1122 */
+#define LIQUID_FFT_BACKWARD (-1)    /* liquid.h:1123 */
+#define LIQUID_FIRFILT_ARKAISER 7   /* liquid.h:1426 (enum liquid_firfilt_type) */
+#define LIQUID_FIRFILT_RKAISER  8
+#define LIQUID_FIRFILT_RRC      9   /* liquid.h:1428 */
+#define LIQUID_FIRFILT_hM3      10
+
+/* ---- prototype design: liquid.h:1476, :1548, :1580 -> src/filter/src/firdes.c:224-280, rrcos.c:37-95 */
+float kaiser_beta_As(float _As);
+void  liquid_firdes_kaiser(unsigned int _n, float _fc, float _As, float _mu, float *_h);
+void  liquid_firdes_rrcos(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+
+/* ---- firpfbch2_crcf: liquid.h:5754-5793 -> src/multichannel/src/firpfbch2.c:66-358 */
+typedef struct firpfbch2_crcf_s * firpfbch2_crcf;
+firpfbch2_crcf firpfbch2_crcf_create(int _type, unsigned int _M, unsigned int _m, float *_h);
+firpfbch2_crcf firpfbch2_crcf_create_kaiser(int _type, unsigned int _M, unsigned int _m, float _As);
+void firpfbch2_crcf_destroy(firpfbch2_crcf _q);
+void firpfbch2_crcf_reset(firpfbch2_crcf _q);
+void firpfbch2_crcf_print(firpfbch2_crcf _q);
+/* analyzer: _x[M/2] -> _y[M]; synthesizer: _x[M] -> _y[M/2] */
+void firpfbch2_crcf_execute(firpfbch2_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+
+/* ---- firpfbch_crcf: liquid.h:5667-5728 -> src/multichannel/src/firpfbch.c:73-409 */
+typedef struct firpfbch_crcf_s * firpfbch_crcf;
+firpfbch_crcf firpfbch_crcf_create(int _type, unsigned int _M, unsigned int _p, float *_h);
+firpfbch_crcf firpfbch_crcf_create_kaiser(int _type, unsigned int _M, unsigned int _m, float _As);
+firpfbch_crcf firpfbch_crcf_create_rnyquist(int _type, unsigned int _M, unsigned int _m, float _beta, int _ftype);
+void firpfbch_crcf_destroy(firpfbch_crcf _q);
+void firpfbch_crcf_reset(firpfbch_crcf _q);
+void firpfbch_crcf_print(firpfbch_crcf _q);
+void firpfbch_crcf_synthesizer_execute(firpfbch_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+void firpfbch_crcf_analyzer_execute(firpfbch_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+
+/* ---- firfilt_crcf: liquid.h:1985-2074 -> src/filter/src/firfilt.c:62-405 */
+typedef struct firfilt_crcf_s * firfilt_crcf;
+firfilt_crcf firfilt_crcf_create(float *_h, unsigned int _n);
+firfilt_crcf firfilt_crcf_create_kaiser(unsigned int _n, float _fc, float _As, float _mu);
+firfilt_crcf firfilt_crcf_create_rnyquist(int _type, unsigned int _k, unsigned int _m, float _beta, float _mu);
+firfilt_crcf firfilt_crcf_create_rect(unsigned int _n);
+firfilt_crcf firfilt_crcf_recreate(firfilt_crcf _q, float *_h, unsigned int _n);
+void firfilt_crcf_destroy(firfilt_crcf _q);
+void firfilt_crcf_reset(firfilt_crcf _q);
+void firfilt_crcf_print(firfilt_crcf _q);
+void firfilt_crcf_set_scale(firfilt_crcf _q, float _scale);
+void firfilt_crcf_push(firfilt_crcf _q, liquid_float_complex _x);
+void firfilt_crcf_execute(firfilt_crcf _q, liquid_float_complex *_y);
+void firfilt_crcf_execute_block(firfilt_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+unsigned int firfilt_crcf_get_length(firfilt_crcf _q);
+void  firfilt_crcf_freqresponse(firfilt_crcf _q, float _fc, liquid_float_complex *_H);
+float firfilt_crcf_groupdelay(firfilt_crcf _q, float _fc);
+
+/* ---- firpfb_crcf: liquid.h:2392-2470 -> src/filter/src/firpfb.c:46-346 */
+typedef struct firpfb_crcf_s * firpfb_crcf;
+firpfb_crcf firpfb_crcf_create(unsigned int _M, float *_h, unsigned int _h_len);
+firpfb_crcf firpfb_crcf_create_kaiser(unsigned int _M, unsigned int _m, float _fc, float _As);
+firpfb_crcf firpfb_crcf_create_rnyquist(int _type, unsigned int _M, unsigned int _k, unsigned int _m, float _beta);
+firpfb_crcf firpfb_crcf_recreate(firpfb_crcf _q, unsigned int _M, float *_h, unsigned int _h_len);
+void firpfb_crcf_destroy(firpfb_crcf _q);
+void firpfb_crcf_print(firpfb_crcf _q);
+void firpfb_crcf_set_scale(firpfb_crcf _q, float _g);
+void firpfb_crcf_reset(firpfb_crcf _q);
+void firpfb_crcf_push(firpfb_crcf _q, liquid_float_complex _x);
+void firpfb_crcf_execute(firpfb_crcf _q, unsigned int _i, liquid_float_complex *_y);
+
+/* ---- dotprod_crcf: liquid.h:503-541 -> src/dotprod/src/dotprod.c:41-168, dotprod_crcf.mmx.c:95-287 */
+typedef struct dotprod_crcf_s * dotprod_crcf;
+void dotprod_crcf_run(float *_h, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+void dotprod_crcf_run4(float *_h, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+dotprod_crcf dotprod_crcf_create(float *_h, unsigned int _n);
+dotprod_crcf dotprod_crcf_recreate(dotprod_crcf _q, float *_h, unsigned int _n);
+void dotprod_crcf_destroy(dotprod_crcf _q);
+void dotprod_crcf_print(dotprod_crcf _q);
+void dotprod_crcf_execute(dotprod_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+
+/* ---- complex FFT: liquid.h:1148-1215 -> src/fft/src/fft_common.c:109-316
+ * unscaled both ways; FORWARD = e^{-j}, BACKWARD = e^{+j}; the plan borrows _x/_y (not copied) */
+typedef struct fftplan_s * fftplan;
+fftplan fft_create_plan(unsigned int _n, liquid_float_complex *_x, liquid_float_complex *_y, int _dir, int _flags);
+void fft_destroy_plan(fftplan _p);
+void fft_print_plan(fftplan _p);
+void fft_execute(fftplan _p);
+void fft_run(unsigned int _n, liquid_float_complex *_x, liquid_float_complex *_y, int _dir, int _flags);
+void fft_shift(liquid_float_complex *_x, unsigned int _n);
+
+#endif /* __LIQUID_H__ */
+
+/* exported by the reference but absent from liquid.h (src/multichannel/src/firpfbch.c:369, :383;
+ * used by sandbox/firpfbch_analysis_alignment_test.c) */
+void firpfbch_crcf_analyzer_push(firpfbch_crcf _q, liquid_float_complex _x);
+void firpfbch_crcf_analyzer_run(firpfbch_crcf _q, unsigned int _k, liquid_float_complex *_X);
+
+/* ============================================================================================
+ * Part 2 -- batched / device / state extensions (not in the reference)
+ * ============================================================================================ */
+
+/* library / device plumbing */
+const char *liquid_cuda_version(void);
+int   liquid_cuda_device_count(void);
+void  liquid_cuda_set_device(int _device);            /* also honoured: env LIQUID_CUDA_DEVICE */
+void *liquid_cuda_malloc(unsigned long long _bytes);  /* device memory */
+void  liquid_cuda_free(void *_dptr);
+void *liquid_cuda_host_alloc(unsigned long long _bytes);   /* pinned host memory */
+void  liquid_cuda_host_free(void *_hptr);
+void  liquid_cuda_memcpy_h2d(void *_dst, const void *_src, unsigned long long _bytes);
+void  liquid_cuda_memcpy_d2h(void *_dst, const void *_src, unsigned long long _bytes);
+void  liquid_cuda_sync(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+unsigned long long liquid_cuda_launch_count(void);
+/* fill _x[_n] on the device with the bench's synthetic stream
+ * u(n,c) = (splitmix64(seed + 2n + c) >> 40) * 2^-24 - 0.5 ; _first = index of _x[0] in the stream */
+void  liquid_cuda_synth_input_dev(void *_d_x, unsigned long long _seed, unsigned long long _first,
+                                  unsigned long long _n, void *_stream);
+
+/* ---- firpfbch2_crcf ---- */
+/* n_frames consecutive execute() calls in one go; identical results and end state.
+ * analyzer: _x[n_frames*M/2] -> _y[n_frames*M]; synthesizer: _x[n_frames*M] -> _y[n_frames*M/2] */
+void firpfbch2_crcf_execute_block(firpfbch2_crcf _q, liquid_float_complex *_x,
+                                  unsigned int _n_frames, liquid_float_complex *_y);
+/* same on device pointers, asynchronous on _stream; state is carried in the object */
+void firpfbch2_crcf_execute_block_dev(firpfbch2_crcf _q, const void *_d_x,
+                                      unsigned long long _n_frames, void *_d_y, void *_stream);
+/* stateless segment form used for time-sharded multi-GPU runs (analyzer only): _d_halo holds the
+ * firpfbch2_crcf_get_state_len() input samples that precede _d_x[0] in the stream (zeros at the
+ * stream start); _first_frame gives the parity of the first frame.  Object state is not touched. */
+void firpfbch2_crcf_execute_segment_dev(firpfbch2_crcf _q, const void *_d_halo, const void *_d_x,
+                                        unsigned long long _first_frame, unsigned long long _n_frames,
+                                        void *_d_y, void *_stream);
+/* state = the last get_state_len() samples pushed (analyzer: input samples; synthesizer: scaled IDFT
+ * outputs) plus the frame parity flag -- the checkpoint, and the multi-GPU halo */
+unsigned int firpfbch2_crcf_get_state_len(firpfbch2_crcf _q);
+void firpfbch2_crcf_get_state(firpfbch2_crcf _q, liquid_float_complex *_hist, int *_flag);
+void firpfbch2_crcf_set_state(firpfbch2_crcf _q, const liquid_float_complex *_hist, int _flag);
+
+/* ---- firpfbch_crcf ---- */
+void firpfbch_crcf_analyzer_execute_block(firpfbch_crcf _q, liquid_float_complex *_x,
+                                          unsigned int _n_frames, liquid_float_complex *_y);
+void firpfbch_crcf_synthesizer_execute_block(firpfbch_crcf _q, liquid_float_complex *_x,
+                                             unsigned int _n_frames, liquid_float_complex *_y);
+/* device pointers; dispatches on the object's type */
+void firpfbch_crcf_execute_block_dev(firpfbch_crcf _q, const void *_d_x,
+                                     unsigned long long _n_frames, void *_d_y, void *_stream);
+unsigned int firpfbch_crcf_get_state_len(firpfbch_crcf _q);
+void firpfbch_crcf_get_state(firpfbch_crcf _q, liquid_float_complex *_hist);
+void firpfbch_crcf_set_state(firpfbch_crcf _q, const liquid_float_complex *_hist);
+
+/* ---- firfilt_crcf ---- */
+/* _n_streams independent streams of _n samples each (stream s at _d_x + s*_n), every stream filtered
+ * from the zero state with the object's taps and scale; the object's own state is not touched */
+void firfilt_crcf_execute_streams_dev(firfilt_crcf _q, const void *_d_x, unsigned int _n_streams,
+                                      unsigned long long _n, void *_d_y, void *_stream);
+/* stateful single-stream block on device pointers (what execute_block does after its H2D copy) */
+void firfilt_crcf_execute_block_dev(firfilt_crcf _q, const void *_d_x, unsigned long long _n,
+                                    void *_d_y, void *_stream);
+
+/* ---- firpfb_crcf ---- */
+/* for i < _n: push _x[i], then _y[i] = execute(_idx[i]) */
+void firpfb_crcf_execute_block(firpfb_crcf _q, liquid_float_complex *_x, const unsigned int *_idx,
+                               unsigned int _n, liquid_float_complex *_y);
+
+/* ---- dotprod_crcf ---- */
+/* _n_vec dot products: vector v starts at _d_x + v*_stride (complex samples) */
+void dotprod_crcf_execute_batch_dev(dotprod_crcf _q, const void *_d_x, unsigned long long _n_vec,
+                                    unsigned long long _stride, void *_d_y, void *_stream);
+
+/* ---- FFT ---- */
+/* _batch transforms of the plan's size on device pointers (row-major [batch][n]); in-place allowed */
+void fft_execute_batch_dev(fftplan _p, const void *_d_x, void *_d_y, unsigned long long _batch, void *_stream);
+void fft_execute_batch(fftplan _p, liquid_float_complex *_x, liquid_float_complex *_y, unsigned int _batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIQUID_CUDA_H */

@@ -1,0 +1,533 @@
+"""liquid_dsp_b200 -- Python host-side mirror of the liquid-dsp channelizer API over libliquid_cuda.so.
+
+The product is the C-ABI shared library (``include/liquid_cuda.h``); this module only binds it
+with ctypes and mirrors the reference's object interface (same names, argument meaning and error
+behaviour: invalid arguments make the library print ``error: <fn>(), <msg>`` and exit(1), as
+liquid-dsp does).  There is no CPU fallback: if the CUDA library is missing, importing fails; if no
+B200 is present, the first ``create`` aborts.
+
+Host arrays are numpy ``complex64`` / ``float32``; the ``*_dev`` methods take raw device pointers
+(``tensor.data_ptr()``) and a CUDA stream handle, so torch is plumbing only and never imported here.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libliquid_cuda.so")
+
+LIQUID_ANALYZER, LIQUID_SYNTHESIZER = 0, 1
+LIQUID_FFT_FORWARD, LIQUID_FFT_BACKWARD = +1, -1
+LIQUID_FIRFILT_RRC = 9
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "liquid_dsp_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `make -C liquid-dsp_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+_cf_p = np.ctypeslib.ndpointer(dtype=np.complex64, flags="C_CONTIGUOUS")
+_f_p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_u_p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+
+
+class _cf(C.Structure):
+    _fields_ = [("re", C.c_float), ("im", C.c_float)]
+
+
+_DECLARED = []
+
+
+def _sig(name, restype, *argtypes):
+    _DECLARED.append(name)
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+_vp, _u, _ull, _i, _fl = C.c_void_p, C.c_uint, C.c_ulonglong, C.c_int, C.c_float
+
+# every symbol include/liquid_cuda.h declares, with its signature
+_sig("kaiser_beta_As", _fl, _fl)
+_sig("liquid_firdes_kaiser", None, _u, _fl, _fl, _fl, _f_p)
+_sig("liquid_firdes_rrcos", None, _u, _u, _fl, _fl, _f_p)
+_sig("firpfbch2_crcf_create", _vp, _i, _u, _u, _f_p)
+_sig("firpfbch2_crcf_create_kaiser", _vp, _i, _u, _u, _fl)
+_sig("firpfbch2_crcf_destroy", None, _vp)
+_sig("firpfbch2_crcf_reset", None, _vp)
+_sig("firpfbch2_crcf_print", None, _vp)
+_sig("firpfbch2_crcf_execute", None, _vp, _cf_p, _cf_p)
+_sig("firpfbch2_crcf_execute_block", None, _vp, _vp, _u, _vp)
+_sig("firpfbch2_crcf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
+_sig("firpfbch2_crcf_execute_segment_dev", None, _vp, _vp, _vp, _ull, _ull, _vp, _vp)
+_sig("firpfbch2_crcf_get_state_len", _u, _vp)
+_sig("firpfbch2_crcf_get_state", None, _vp, _cf_p, C.POINTER(C.c_int))
+_sig("firpfbch2_crcf_set_state", None, _vp, _cf_p, _i)
+_sig("firpfbch_crcf_create", _vp, _i, _u, _u, _f_p)
+_sig("firpfbch_crcf_create_kaiser", _vp, _i, _u, _u, _fl)
+_sig("firpfbch_crcf_create_rnyquist", _vp, _i, _u, _u, _fl, _i)
+_sig("firpfbch_crcf_destroy", None, _vp)
+_sig("firpfbch_crcf_reset", None, _vp)
+_sig("firpfbch_crcf_print", None, _vp)
+_sig("firpfbch_crcf_synthesizer_execute", None, _vp, _cf_p, _cf_p)
+_sig("firpfbch_crcf_analyzer_execute", None, _vp, _cf_p, _cf_p)
+_sig("firpfbch_crcf_analyzer_push", None, _vp, _cf)
+_sig("firpfbch_crcf_analyzer_run", None, _vp, _u, _cf_p)
+_sig("firpfbch_crcf_analyzer_execute_block", None, _vp, _vp, _u, _vp)
+_sig("firpfbch_crcf_synthesizer_execute_block", None, _vp, _vp, _u, _vp)
+_sig("firpfbch_crcf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
+_sig("firpfbch_crcf_get_state_len", _u, _vp)
+_sig("firpfbch_crcf_get_state", None, _vp, _cf_p)
+_sig("firpfbch_crcf_set_state", None, _vp, _cf_p)
+_sig("firfilt_crcf_create", _vp, _f_p, _u)
+_sig("firfilt_crcf_create_kaiser", _vp, _u, _fl, _fl, _fl)
+_sig("firfilt_crcf_create_rnyquist", _vp, _i, _u, _u, _fl, _fl)
+_sig("firfilt_crcf_create_rect", _vp, _u)
+_sig("firfilt_crcf_recreate", _vp, _vp, _f_p, _u)
+_sig("firfilt_crcf_destroy", None, _vp)
+_sig("firfilt_crcf_reset", None, _vp)
+_sig("firfilt_crcf_print", None, _vp)
+_sig("firfilt_crcf_set_scale", None, _vp, _fl)
+_sig("firfilt_crcf_push", None, _vp, _cf)
+_sig("firfilt_crcf_execute", None, _vp, _cf_p)
+_sig("firfilt_crcf_execute_block", None, _vp, _vp, _u, _vp)
+_sig("firfilt_crcf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
+_sig("firfilt_crcf_execute_streams_dev", None, _vp, _vp, _u, _ull, _vp, _vp)
+_sig("firfilt_crcf_get_length", _u, _vp)
+_sig("firfilt_crcf_freqresponse", None, _vp, _fl, _cf_p)
+_sig("firfilt_crcf_groupdelay", _fl, _vp, _fl)
+_sig("firpfb_crcf_create", _vp, _u, _f_p, _u)
+_sig("firpfb_crcf_create_kaiser", _vp, _u, _u, _fl, _fl)
+_sig("firpfb_crcf_create_rnyquist", _vp, _i, _u, _u, _u, _fl)
+_sig("firpfb_crcf_recreate", _vp, _vp, _u, _f_p, _u)
+_sig("firpfb_crcf_destroy", None, _vp)
+_sig("firpfb_crcf_print", None, _vp)
+_sig("firpfb_crcf_set_scale", None, _vp, _fl)
+_sig("firpfb_crcf_reset", None, _vp)
+_sig("firpfb_crcf_push", None, _vp, _cf)
+_sig("firpfb_crcf_execute", None, _vp, _u, _cf_p)
+_sig("firpfb_crcf_execute_block", None, _vp, _cf_p, _u_p, _u, _cf_p)
+_sig("dotprod_crcf_run", None, _f_p, _cf_p, _u, _cf_p)
+_sig("dotprod_crcf_run4", None, _f_p, _cf_p, _u, _cf_p)
+_sig("dotprod_crcf_create", _vp, _f_p, _u)
+_sig("dotprod_crcf_recreate", _vp, _vp, _f_p, _u)
+_sig("dotprod_crcf_destroy", None, _vp)
+_sig("dotprod_crcf_print", None, _vp)
+_sig("dotprod_crcf_execute", None, _vp, _cf_p, _cf_p)
+_sig("dotprod_crcf_execute_batch_dev", None, _vp, _vp, _ull, _ull, _vp, _vp)
+_sig("fft_create_plan", _vp, _u, _vp, _vp, _i, _i)
+_sig("fft_destroy_plan", None, _vp)
+_sig("fft_print_plan", None, _vp)
+_sig("fft_execute", None, _vp)
+_sig("fft_run", None, _u, _cf_p, _cf_p, _i, _i)
+_sig("fft_shift", None, _cf_p, _u)
+_sig("fft_execute_batch_dev", None, _vp, _vp, _vp, _ull, _vp)
+_sig("fft_execute_batch", None, _vp, _cf_p, _cf_p, _u)
+_sig("liquid_cuda_version", C.c_char_p)
+_sig("liquid_cuda_device_count", _i)
+_sig("liquid_cuda_set_device", None, _i)
+_sig("liquid_cuda_malloc", _vp, _ull)
+_sig("liquid_cuda_free", None, _vp)
+_sig("liquid_cuda_host_alloc", _vp, _ull)
+_sig("liquid_cuda_host_free", None, _vp)
+_sig("liquid_cuda_memcpy_h2d", None, _vp, _vp, _ull)
+_sig("liquid_cuda_memcpy_d2h", None, _vp, _vp, _ull)
+_sig("liquid_cuda_sync", None)
+_sig("liquid_cuda_launch_count", _ull)
+_sig("liquid_cuda_synth_input_dev", None, _vp, _ull, _ull, _ull, _vp)
+
+#: names include/liquid_cuda.h declares (checked against the header and the .so by the CPU tests)
+DECLARED_SYMBOLS = sorted(_DECLARED)
+
+
+def version():
+    return lib.liquid_cuda_version().decode()
+
+
+def device_count():
+    return lib.liquid_cuda_device_count()
+
+
+def set_device(dev):
+    lib.liquid_cuda_set_device(int(dev))
+
+
+def launch_count():
+    return int(lib.liquid_cuda_launch_count())
+
+
+def _c64(a):
+    return np.ascontiguousarray(a, dtype=np.complex64)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def liquid_firdes_kaiser(n, fc, As, mu=0.0):
+    h = np.empty(n, np.float32)
+    lib.liquid_firdes_kaiser(n, fc, As, mu, h)
+    return h
+
+
+def liquid_firdes_rrcos(k, m, beta, dt=0.0):
+    h = np.empty(2 * k * m + 1, np.float32)
+    lib.liquid_firdes_rrcos(k, m, beta, dt, h)
+    return h
+
+
+def kaiser_beta_As(As):
+    return lib.kaiser_beta_As(As)
+
+
+def pinned_empty(n, dtype=np.complex64):
+    """numpy array over cudaHostAlloc'd (pinned) memory; keeps the allocation alive with the array"""
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    p = lib.liquid_cuda_host_alloc(nbytes)
+    buf = (C.c_char * nbytes).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+    _PINNED[arr.ctypes.data] = p
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr):
+    p = _PINNED.pop(arr.ctypes.data, None)
+    if p:
+        lib.liquid_cuda_host_free(p)
+
+
+class _Handle:
+    _destroy = None
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+
+    def destroy(self):
+        if getattr(self, "_h", None):
+            getattr(lib, self._destroy)(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class firpfbch2_crcf(_Handle):
+    """liquid.h:5754-5793.  analyzer: M/2 samples in, M out per frame; synthesizer: M in, M/2 out."""
+    _destroy = "firpfbch2_crcf_destroy"
+
+    def __init__(self, type, M, m, h):
+        self.type, self.M, self.m = type, M, m
+        super().__init__(lib.firpfbch2_crcf_create(type, M, m, _f32(h)))
+
+    @classmethod
+    def create(cls, type, M, m, h):
+        return cls(type, M, m, h)
+
+    @classmethod
+    def create_kaiser(cls, type, M, m, As):
+        q = cls.__new__(cls)
+        q.type, q.M, q.m = type, M, m
+        _Handle.__init__(q, lib.firpfbch2_crcf_create_kaiser(type, M, m, As))
+        return q
+
+    @property
+    def n_in(self):
+        return self.M // 2 if self.type == LIQUID_ANALYZER else self.M
+
+    @property
+    def n_out(self):
+        return self.M if self.type == LIQUID_ANALYZER else self.M // 2
+
+    def reset(self):
+        lib.firpfbch2_crcf_reset(self._h)
+
+    def print(self):
+        lib.firpfbch2_crcf_print(self._h)
+
+    def execute(self, x):
+        x = _c64(x)
+        assert x.size == self.n_in
+        y = np.empty(self.n_out, np.complex64)
+        lib.firpfbch2_crcf_execute(self._h, x, y)
+        return y
+
+    def execute_block(self, x, out=None):
+        x = _c64(x)
+        n_frames = x.size // self.n_in
+        assert n_frames * self.n_in == x.size
+        y = out if out is not None else np.empty(n_frames * self.n_out, np.complex64)
+        lib.firpfbch2_crcf_execute_block(self._h, _ptr(x), n_frames, _ptr(y))
+        return y.reshape(n_frames, self.n_out) if out is None else y
+
+    def execute_block_dev(self, d_x, n_frames, d_y, stream=0):
+        lib.firpfbch2_crcf_execute_block_dev(self._h, d_x, n_frames, d_y, stream)
+
+    def execute_segment_dev(self, d_halo, d_x, first_frame, n_frames, d_y, stream=0):
+        lib.firpfbch2_crcf_execute_segment_dev(self._h, d_halo, d_x, first_frame, n_frames, d_y, stream)
+
+    def get_state_len(self):
+        return lib.firpfbch2_crcf_get_state_len(self._h)
+
+    def get_state(self):
+        hist = np.empty(self.get_state_len(), np.complex64)
+        flag = C.c_int(0)
+        lib.firpfbch2_crcf_get_state(self._h, hist, C.byref(flag))
+        return hist, flag.value
+
+    def set_state(self, hist, flag):
+        lib.firpfbch2_crcf_set_state(self._h, _c64(hist), int(flag))
+
+
+class firpfbch_crcf(_Handle):
+    """liquid.h:5667-5728 (+ analyzer_push / analyzer_run, firpfbch.c:369, :383)."""
+    _destroy = "firpfbch_crcf_destroy"
+
+    def __init__(self, type, M, p, h):
+        self.type, self.M = type, M
+        super().__init__(lib.firpfbch_crcf_create(type, M, p, _f32(h)))
+
+    @classmethod
+    def create(cls, type, M, p, h):
+        return cls(type, M, p, h)
+
+    @classmethod
+    def create_kaiser(cls, type, M, m, As):
+        q = cls.__new__(cls)
+        q.type, q.M = type, M
+        _Handle.__init__(q, lib.firpfbch_crcf_create_kaiser(type, M, m, As))
+        return q
+
+    @classmethod
+    def create_rnyquist(cls, type, M, m, beta, ftype=LIQUID_FIRFILT_RRC):
+        q = cls.__new__(cls)
+        q.type, q.M = type, M
+        _Handle.__init__(q, lib.firpfbch_crcf_create_rnyquist(type, M, m, beta, ftype))
+        return q
+
+    def reset(self):
+        lib.firpfbch_crcf_reset(self._h)
+
+    def print(self):
+        lib.firpfbch_crcf_print(self._h)
+
+    def analyzer_execute(self, x):
+        y = np.empty(self.M, np.complex64)
+        lib.firpfbch_crcf_analyzer_execute(self._h, _c64(x), y)
+        return y
+
+    def synthesizer_execute(self, x):
+        y = np.empty(self.M, np.complex64)
+        lib.firpfbch_crcf_synthesizer_execute(self._h, _c64(x), y)
+        return y
+
+    def analyzer_push(self, v):
+        v = complex(v)
+        lib.firpfbch_crcf_analyzer_push(self._h, _cf(v.real, v.imag))
+
+    def analyzer_run(self, k):
+        y = np.empty(self.M, np.complex64)
+        lib.firpfbch_crcf_analyzer_run(self._h, k, y)
+        return y
+
+    def execute_block(self, x, out=None):
+        x = _c64(x)
+        n_frames = x.size // self.M
+        assert n_frames * self.M == x.size
+        y = out if out is not None else np.empty(x.size, np.complex64)
+        fn = (lib.firpfbch_crcf_analyzer_execute_block if self.type == LIQUID_ANALYZER
+              else lib.firpfbch_crcf_synthesizer_execute_block)
+        fn(self._h, _ptr(x), n_frames, _ptr(y))
+        return y.reshape(n_frames, self.M) if out is None else y
+
+    def execute_block_dev(self, d_x, n_frames, d_y, stream=0):
+        lib.firpfbch_crcf_execute_block_dev(self._h, d_x, n_frames, d_y, stream)
+
+    def get_state(self):
+        hist = np.empty(lib.firpfbch_crcf_get_state_len(self._h), np.complex64)
+        lib.firpfbch_crcf_get_state(self._h, hist)
+        return hist
+
+    def set_state(self, hist):
+        lib.firpfbch_crcf_set_state(self._h, _c64(hist))
+
+
+class firfilt_crcf(_Handle):
+    """liquid.h:1985-2074."""
+    _destroy = "firfilt_crcf_destroy"
+
+    def __init__(self, h):
+        super().__init__(lib.firfilt_crcf_create(_f32(h), len(h)))
+
+    @classmethod
+    def create(cls, h):
+        return cls(h)
+
+    @classmethod
+    def create_kaiser(cls, n, fc, As, mu=0.0):
+        q = cls.__new__(cls)
+        _Handle.__init__(q, lib.firfilt_crcf_create_kaiser(n, fc, As, mu))
+        return q
+
+    @classmethod
+    def create_rnyquist(cls, type, k, m, beta, mu=0.0):
+        q = cls.__new__(cls)
+        _Handle.__init__(q, lib.firfilt_crcf_create_rnyquist(type, k, m, beta, mu))
+        return q
+
+    @classmethod
+    def create_rect(cls, n):
+        q = cls.__new__(cls)
+        _Handle.__init__(q, lib.firfilt_crcf_create_rect(n))
+        return q
+
+    def recreate(self, h):
+        self._h = C.c_void_p(lib.firfilt_crcf_recreate(self._h, _f32(h), len(h)))
+        return self
+
+    def reset(self):
+        lib.firfilt_crcf_reset(self._h)
+
+    def print(self):
+        lib.firfilt_crcf_print(self._h)
+
+    def set_scale(self, s):
+        lib.firfilt_crcf_set_scale(self._h, s)
+
+    def get_length(self):
+        return lib.firfilt_crcf_get_length(self._h)
+
+    def push(self, v):
+        v = complex(v)
+        lib.firfilt_crcf_push(self._h, _cf(v.real, v.imag))
+
+    def execute(self):
+        y = np.empty(1, np.complex64)
+        lib.firfilt_crcf_execute(self._h, y)
+        return y[0]
+
+    def execute_block(self, x, out=None):
+        x = _c64(x)
+        y = out if out is not None else np.empty_like(x)
+        lib.firfilt_crcf_execute_block(self._h, _ptr(x), x.size, _ptr(y))
+        return y
+
+    def execute_block_dev(self, d_x, n, d_y, stream=0):
+        lib.firfilt_crcf_execute_block_dev(self._h, d_x, n, d_y, stream)
+
+    def execute_streams_dev(self, d_x, n_streams, n, d_y, stream=0):
+        lib.firfilt_crcf_execute_streams_dev(self._h, d_x, n_streams, n, d_y, stream)
+
+    def freqresponse(self, fc):
+        H = np.empty(1, np.complex64)
+        lib.firfilt_crcf_freqresponse(self._h, fc, H)
+        return H[0]
+
+    def groupdelay(self, fc):
+        return lib.firfilt_crcf_groupdelay(self._h, fc)
+
+
+class firpfb_crcf(_Handle):
+    """liquid.h:2392-2470."""
+    _destroy = "firpfb_crcf_destroy"
+
+    def __init__(self, M, h):
+        self.M = M
+        super().__init__(lib.firpfb_crcf_create(M, _f32(h), len(h)))
+
+    @classmethod
+    def create_kaiser(cls, M, m, fc, As):
+        q = cls.__new__(cls)
+        q.M = M
+        _Handle.__init__(q, lib.firpfb_crcf_create_kaiser(M, m, fc, As))
+        return q
+
+    def reset(self):
+        lib.firpfb_crcf_reset(self._h)
+
+    def set_scale(self, g):
+        lib.firpfb_crcf_set_scale(self._h, g)
+
+    def push(self, v):
+        v = complex(v)
+        lib.firpfb_crcf_push(self._h, _cf(v.real, v.imag))
+
+    def execute(self, i):
+        y = np.empty(1, np.complex64)
+        lib.firpfb_crcf_execute(self._h, i, y)
+        return y[0]
+
+    def execute_block(self, x, idx):
+        x = _c64(x)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        y = np.empty_like(x)
+        lib.firpfb_crcf_execute_block(self._h, x, idx, x.size, y)
+        return y
+
+
+class dotprod_crcf(_Handle):
+    """liquid.h:503-541."""
+    _destroy = "dotprod_crcf_destroy"
+
+    def __init__(self, h):
+        self.n = len(h)
+        super().__init__(lib.dotprod_crcf_create(_f32(h), len(h)))
+
+    def execute(self, x):
+        y = np.empty(1, np.complex64)
+        lib.dotprod_crcf_execute(self._h, _c64(x), y)
+        return y[0]
+
+    def execute_batch_dev(self, d_x, n_vec, stride, d_y, stream=0):
+        lib.dotprod_crcf_execute_batch_dev(self._h, d_x, n_vec, stride, d_y, stream)
+
+    @staticmethod
+    def run(h, x):
+        y = np.empty(1, np.complex64)
+        lib.dotprod_crcf_run(_f32(h), _c64(x), len(h), y)
+        return y[0]
+
+
+class fftplan(_Handle):
+    """liquid.h:1148-1215: the plan borrows x / y for its lifetime (fft_common.c:35-36)."""
+    _destroy = "fft_destroy_plan"
+
+    def __init__(self, n, x, y, direction, flags=0):
+        assert x.dtype == np.complex64 and y.dtype == np.complex64 and x.size >= n and y.size >= n
+        self.n, self.x, self.y = n, x, y
+        super().__init__(lib.fft_create_plan(n, _ptr(x), _ptr(y), direction, flags))
+
+    def execute(self):
+        lib.fft_execute(self._h)
+
+    def execute_batch(self, x, y=None):
+        x = _c64(x)
+        y = np.empty_like(x) if y is None else y
+        lib.fft_execute_batch(self._h, x, y, x.size // self.n)
+        return y
+
+    def execute_batch_dev(self, d_x, d_y, batch, stream=0):
+        lib.fft_execute_batch_dev(self._h, d_x, d_y, batch, stream)
+
+
+def fft_run(x, direction=LIQUID_FFT_FORWARD):
+    x = _c64(x)
+    y = np.empty_like(x)
+    lib.fft_run(x.size, x, y, direction, 0)
+    return y
+
+
+def synth_input_dev(d_x, n, seed=0x5EED0000, first=0, stream=0):
+    lib.liquid_cuda_synth_input_dev(d_x, seed, first, n, stream)

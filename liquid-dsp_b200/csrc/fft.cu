@@ -1,0 +1,276 @@
+// fft.cu -- batched complex FFT on the device + the fft_* C API.
+//
+// Stands in for src/fft/src/fft_common.c:109-316 (plan / execute / run / shift) and the
+// transforms behind it (fft_mixed_radix.c:128-191, fft_dft.c).  Conventions kept:
+// FORWARD = e^{-j 2 pi nk/N}, BACKWARD = e^{+j 2 pi nk/N}, both unscaled (fft_radix2.c:68-70).
+// The factorisation is NOT the reference's (any float32 FFT agrees with it to ~1e-7 relative):
+//   power-of-two N : Stockham autosort, radix-4 stages (+ one radix-2 stage when log2 N is odd),
+//                    whole transform in shared memory, several transforms per CTA when N is small
+//   other N        : table-driven O(N^2) DFT, one CTA per transform (slow, correct, on-device)
+// Twiddles come from a per-plan table computed in double on the host.
+#include <cmath>
+
+#include "lc_common.cuh"
+#include "../../include/liquid_cuda.h"
+
+namespace {
+
+constexpr int kFftThreads = 256;
+
+// post-processing of the last stage: 0 none, 1 divide by a, 2 multiply by a then by b
+__device__ __forceinline__ float2 fft_post(float2 v, int mode, float a, float b)
+{
+    if (mode == 1) { v.x = v.x / a; v.y = v.y / a; }
+    else if (mode == 2) { v.x *= a; v.y *= a; v.x *= b; v.y *= b; }
+    return v;
+}
+
+// multiply by s*j  (s = +1 or -1)
+__device__ __forceinline__ float2 mul_sj(float2 v, float s) { return make_float2(-s * v.y, s * v.x); }
+
+// Stockham autosort FFT of n = 2^log2n points per transform, `per_cta` transforms per CTA.
+// smem: 2 * per_cta * n float2.
+__global__ void __launch_bounds__(kFftThreads)
+fft_pow2_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const float2 *__restrict__ tw,
+                unsigned int n, unsigned int log2n, unsigned int per_cta, unsigned long long batch,
+                float sgn, int post_mode, float pa, float pb)
+{
+    extern __shared__ float2 smem[];
+    float2 *buf0 = smem;
+    float2 *buf1 = smem + (size_t)per_cta * n;
+    const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
+    const unsigned int total = per_cta * n;
+
+    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
+        unsigned long long b = first + i / n;
+        buf0[i] = (b < batch) ? x[b * n + (i % n)] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+
+    float2 *in = buf0, *out = buf1;
+    unsigned int Ns = 1;
+    unsigned int stages4 = log2n / 2;
+    for (unsigned int s = 0; s < stages4; s++, Ns <<= 2) {
+        const unsigned int q = n >> 2;                 // butterflies per transform
+        for (unsigned int i = threadIdx.x; i < per_cta * q; i += blockDim.x) {
+            unsigned int f = i / q, j = i % q;
+            const float2 *src = in + (size_t)f * n;
+            float2 *dst = out + (size_t)f * n;
+            unsigned int k = j & (Ns - 1);
+            unsigned int tstep = k * (n / (Ns << 2)); // index of W_n^(k n/(4Ns)) = W_{4Ns}^k
+            float2 v0 = src[j];
+            float2 v1 = lcd::cmul(src[j + q], tw[tstep]);
+            float2 v2 = lcd::cmul(src[j + 2 * q], tw[2 * tstep]);
+            float2 v3 = lcd::cmul(src[j + 3 * q], tw[3 * tstep]);
+            float2 a02 = lcd::cadd(v0, v2), s02 = lcd::csub(v0, v2);
+            float2 a13 = lcd::cadd(v1, v3), s13 = mul_sj(lcd::csub(v1, v3), sgn);
+            unsigned int d = ((j - k) << 2) + k;
+            dst[d]          = lcd::cadd(a02, a13);
+            dst[d + Ns]     = lcd::cadd(s02, s13);
+            dst[d + 2 * Ns] = lcd::csub(a02, a13);
+            dst[d + 3 * Ns] = lcd::csub(s02, s13);
+        }
+        __syncthreads();
+        float2 *t = in; in = out; out = t;
+    }
+    if (log2n & 1) {
+        const unsigned int q = n >> 1;
+        for (unsigned int i = threadIdx.x; i < per_cta * q; i += blockDim.x) {
+            unsigned int f = i / q, j = i % q;
+            const float2 *src = in + (size_t)f * n;
+            float2 *dst = out + (size_t)f * n;
+            unsigned int k = j & (Ns - 1);
+            float2 v0 = src[j];
+            float2 v1 = lcd::cmul(src[j + q], tw[k * (n / (Ns << 1))]);
+            unsigned int d = ((j - k) << 1) + k;
+            dst[d]      = lcd::cadd(v0, v1);
+            dst[d + Ns] = lcd::csub(v0, v1);
+        }
+        __syncthreads();
+        float2 *t = in; in = out; out = t;
+    }
+
+    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
+        unsigned long long b = first + i / n;
+        if (b < batch) y[b * n + (i % n)] = fft_post(in[i], post_mode, pa, pb);
+    }
+}
+
+// table-driven DFT, one CTA per transform; smem: n float2
+__global__ void __launch_bounds__(kFftThreads)
+dft_any_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const float2 *__restrict__ tw,
+               unsigned int n, int post_mode, float pa, float pb)
+{
+    extern __shared__ float2 smem[];
+    const unsigned long long b = blockIdx.x;
+    for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = x[b * n + i];
+    __syncthreads();
+    for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) {
+        float2 acc = smem[0];
+        unsigned int idx = 0;
+        for (unsigned int i = 1; i < n; i++) {
+            idx += k;
+            if (idx >= n) idx -= n;
+            acc = lcd::cadd(acc, lcd::cmul(smem[i], tw[idx]));
+        }
+        y[b * n + k] = fft_post(acc, post_mode, pa, pb);
+    }
+}
+
+}  // namespace
+
+namespace lc {
+
+void FftPlanDev::init(unsigned int n_, int sign_)
+{
+    ensure_device();
+    n = n_;
+    sign = sign_;
+    std::vector<float2> tw(n);
+    for (unsigned int i = 0; i < n; i++) {
+        double a = (double)sign * 2.0 * M_PI * (double)i / (double)n;
+        tw[i] = make_float2((float)cos(a), (float)sin(a));
+    }
+    LC_CUDA_CHECK(cudaMalloc(&d_tw, sizeof(float2) * n));
+    LC_CUDA_CHECK(cudaMemcpy(d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    if (is_pow2(n) && n >= 2) {
+        // transforms above 3072 points need more than the default 48 KB of dynamic smem
+        static bool attr_set = false;
+        if (!attr_set) {
+            LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+    }
+}
+
+void FftPlanDev::destroy()
+{
+    if (d_tw) cudaFree(d_tw);
+    d_tw = nullptr;
+}
+
+void FftPlanDev::run(const float2 *d_x, float2 *d_y, unsigned long long batch, cudaStream_t st,
+                     int post_mode, float a, float b) const
+{
+    if (batch == 0) return;
+    if (n == 1) {
+        // degenerate transform: copy (+ post) through the generic kernel
+        dft_any_kernel<<<(unsigned int)batch, 32, sizeof(float2), st>>>(d_x, d_y, d_tw, 1, post_mode, a, b);
+        LC_LAUNCH_CHECK();
+        return;
+    }
+    if (is_pow2(n) && (size_t)n * 16 <= 200 * 1024) {
+        unsigned int per_cta = 1;
+        while (per_cta * n < 2048 && per_cta < batch) per_cta <<= 1;   // aim at 2048 points per CTA
+        size_t smem = (size_t)2 * per_cta * n * sizeof(float2);
+        const unsigned long long max_grid = 1ull << 30;
+        unsigned long long done = 0;
+        while (done < batch) {      // grid.x limit is 2^31-1; keep launches below 2^30 CTAs
+            unsigned long long nb = batch - done;
+            unsigned long long ctas = (nb + per_cta - 1) / per_cta;
+            if (ctas > max_grid) { ctas = max_grid; nb = ctas * per_cta; }
+            fft_pow2_kernel<<<(unsigned int)ctas, kFftThreads, smem, st>>>(
+                d_x + done * n, d_y + done * n, d_tw, n, ilog2(n), per_cta, nb,
+                (float)sign, post_mode, a, b);
+            LC_LAUNCH_CHECK();
+            done += nb;
+        }
+        return;
+    }
+    if ((size_t)n * sizeof(float2) > 200 * 1024)
+        fatal("fft_execute", "transform size too large for this build (non power-of-two sizes above 25600 are not supported)");
+    dft_any_kernel<<<(unsigned int)batch, kFftThreads, n * sizeof(float2), st>>>(d_x, d_y, d_tw, n, post_mode, a, b);
+    LC_LAUNCH_CHECK();
+}
+
+}  // namespace lc
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: liquid.h:1148-1215
+// ------------------------------------------------------------------------------------------------
+struct fftplan_s {
+    unsigned int n;
+    int dir;
+    lc_cf *x, *y;          // borrowed host arrays (fft_common.c:35-36: "not allocated")
+    lc::FftPlanDev dev;
+    lc::DevBuf din, dout;
+    cudaStream_t stream;
+};
+
+extern "C" {
+
+fftplan fft_create_plan(unsigned int _n, liquid_float_complex *_x, liquid_float_complex *_y, int _dir, int _flags)
+{
+    (void)_flags;
+    if (_n == 0) lc::fatal("fft_create_plan", "fft size must be > 0");
+    if (_dir != LIQUID_FFT_FORWARD && _dir != LIQUID_FFT_BACKWARD)
+        lc::fatal("fft_create_plan", "unknown/invalid fft direction (only complex FORWARD/BACKWARD are provided)");
+    lc::ensure_device();
+    fftplan p = new fftplan_s();
+    p->n = _n;
+    p->dir = _dir;
+    p->x = reinterpret_cast<lc_cf *>(_x);
+    p->y = reinterpret_cast<lc_cf *>(_y);
+    p->dev.init(_n, _dir == LIQUID_FFT_FORWARD ? -1 : +1);
+    LC_CUDA_CHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    return p;
+}
+
+void fft_destroy_plan(fftplan _p)
+{
+    if (!_p) return;
+    _p->dev.destroy();
+    _p->din.release();
+    _p->dout.release();
+    cudaStreamDestroy(_p->stream);
+    delete _p;
+}
+
+void fft_print_plan(fftplan _p)
+{
+    printf("fft plan [%s], n=%u, %s\n", _p->dir == LIQUID_FFT_FORWARD ? "forward" : "reverse", _p->n,
+           lc::is_pow2(_p->n) ? "CUDA Stockham radix-4" : "CUDA DFT");
+}
+
+void fft_execute_batch_dev(fftplan _p, const void *_d_x, void *_d_y, unsigned long long _batch, void *_stream)
+{
+    _p->dev.run((const float2 *)_d_x, (float2 *)_d_y, _batch, lc::as_stream(_stream));
+}
+
+void fft_execute_batch(fftplan _p, liquid_float_complex *_x, liquid_float_complex *_y, unsigned int _batch)
+{
+    size_t bytes = (size_t)_batch * _p->n * sizeof(lc_cf);
+    float2 *din = (float2 *)_p->din.get(bytes);
+    float2 *dout = (float2 *)_p->dout.get(bytes);
+    LC_CUDA_CHECK(cudaMemcpyAsync(din, _x, bytes, cudaMemcpyHostToDevice, _p->stream));
+    _p->dev.run(din, dout, _batch, _p->stream);
+    LC_CUDA_CHECK(cudaMemcpyAsync(_y, dout, bytes, cudaMemcpyDeviceToHost, _p->stream));
+    LC_CUDA_CHECK(cudaStreamSynchronize(_p->stream));
+}
+
+void fft_execute(fftplan _p)
+{
+    fft_execute_batch(_p, reinterpret_cast<liquid_float_complex *>(_p->x),
+                      reinterpret_cast<liquid_float_complex *>(_p->y), 1);
+}
+
+void fft_run(unsigned int _n, liquid_float_complex *_x, liquid_float_complex *_y, int _dir, int _flags)
+{
+    fftplan p = fft_create_plan(_n, _x, _y, _dir, _flags);
+    fft_execute(p);
+    fft_destroy_plan(p);
+}
+
+// host-side index shuffle (fft_common.c:336-350)
+void fft_shift(liquid_float_complex *_x, unsigned int _n)
+{
+    lc_cf *x = reinterpret_cast<lc_cf *>(_x);
+    unsigned int n2 = (_n % 2) ? (_n - 1) / 2 : _n / 2;
+    for (unsigned int i = 0; i < n2; i++) {
+        lc_cf t = x[i];
+        x[i] = x[i + n2];
+        x[i + n2] = t;
+    }
+}
+
+}  // extern "C"

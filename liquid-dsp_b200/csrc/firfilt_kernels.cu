@@ -1,0 +1,211 @@
+// firfilt_kernels.cu -- FIR block filter, batched dot product and firpfb kernels.
+//
+// firfilt (src/filter/src/firfilt.c:346-358 = push + dotprod per sample) as a tiled convolution:
+// a CTA stages TILE + n_taps - 1 input samples of one stream in shared memory with coalesced
+// loads, the taps sit in shared memory (broadcast reads), each thread produces OPT consecutive
+// outputs from a register window that slides one sample per tap.
+#include "firfilt_kernels.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kOpt = 4;                       // outputs per thread
+constexpr int kTile = kThreads * kOpt;        // outputs per CTA tile
+
+// smem: taps[n_taps] floats, then samples [kTile + n_taps - 1] float2 stored transposed so that
+// thread t reading sample t*kOpt + j is conflict-free: slot(q) = (q % kOpt) * row + q / kOpt
+__global__ void __launch_bounds__(kThreads)
+firfilt_tiled_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                     const float *__restrict__ taps, unsigned int n_taps, float scale,
+                     float2 *__restrict__ y, unsigned long long n, unsigned long long tiles_per_stream)
+{
+    extern __shared__ float smem_f[];
+    float *h_s = smem_f;
+    const unsigned int n_samp = kTile + n_taps - 1;
+    const unsigned int row = (n_samp + kOpt - 1) / kOpt + 1;
+    float2 *xs = reinterpret_cast<float2 *>(smem_f + ((n_taps + 1) & ~1u));
+
+    const unsigned long long stream = blockIdx.x / tiles_per_stream;
+    const unsigned long long tile = blockIdx.x % tiles_per_stream;
+    const long long o0 = (long long)(tile * kTile);             // first output of the tile
+    const float2 *xstr = x + stream * n;
+    float2 *ystr = y + stream * n;
+
+    for (unsigned int k = threadIdx.x; k < n_taps; k += kThreads) h_s[k] = taps[k];
+    // sample q of the tile is stream sample o0 - (n_taps-1) + q
+    for (unsigned int q = threadIdx.x; q < n_samp; q += kThreads) {
+        long long idx = o0 - (long long)(n_taps - 1) + q;
+        float2 v = make_float2(0.f, 0.f);
+        if (idx >= (long long)n) v = make_float2(0.f, 0.f);
+        else if (idx >= 0) v = __ldg(xstr + idx);
+        else if (hist != nullptr && H + idx >= 0) v = __ldg(hist + (H + idx));
+        xs[(q % kOpt) * row + q / kOpt] = v;
+    }
+    __syncthreads();
+
+    // outputs o0 + t*kOpt + r, r < kOpt.  y[o] = sum_k h[k] xs_lin[o - o0 + (n_taps-1) - k]
+    const unsigned int t = threadIdx.x;
+    float2 acc[kOpt];
+    float2 win[kOpt];                        // win[r] = xs_lin[t*kOpt + r + (n_taps-1) - k]
+#pragma unroll
+    for (int r = 0; r < kOpt; r++) {
+        acc[r] = make_float2(0.f, 0.f);
+        unsigned int q = t * kOpt + r + (n_taps - 1);
+        win[r] = xs[(q % kOpt) * row + q / kOpt];
+    }
+    for (unsigned int k = 0; k < n_taps; k++) {
+        const float c = h_s[k];
+#pragma unroll
+        for (int r = 0; r < kOpt; r++) {
+            acc[r].x = fmaf(c, win[r].x, acc[r].x);
+            acc[r].y = fmaf(c, win[r].y, acc[r].y);
+        }
+        // slide one sample towards the past
+#pragma unroll
+        for (int r = kOpt - 1; r > 0; r--) win[r] = win[r - 1];
+        if (k + 1 < n_taps) {
+            unsigned int q = t * kOpt + (n_taps - 1) - (k + 1);
+            win[0] = xs[(q % kOpt) * row + q / kOpt];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kOpt; r++) {
+        long long o = o0 + (long long)t * kOpt + r;
+        if (o < (long long)n) ystr[o] = make_float2(acc[r].x * scale, acc[r].y * scale);
+    }
+}
+
+__global__ void firfilt_state_output_kernel(const float2 *__restrict__ hist, const float *__restrict__ taps,
+                                            unsigned int n_taps, float scale, float2 *__restrict__ y)
+{
+    // one warp; strided partial sums, then a shuffle reduction
+    float re = 0.f, im = 0.f;
+    for (unsigned int k = threadIdx.x; k < n_taps; k += 32) {
+        float2 s = hist[n_taps - 1 - k];
+        re = fmaf(taps[k], s.x, re);
+        im = fmaf(taps[k], s.y, im);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, o);
+        im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    if (threadIdx.x == 0) *y = make_float2(re * scale, im * scale);
+}
+
+// one warp per dot product when n >= 32, one thread per dot product otherwise
+__global__ void __launch_bounds__(kThreads)
+dotprod_batch_kernel(const float *__restrict__ h, unsigned int n, const float2 *__restrict__ x,
+                     unsigned long long n_vec, unsigned long long stride, float2 *__restrict__ y, int per_warp)
+{
+    if (per_warp) {
+        const unsigned int lane = threadIdx.x & 31;
+        unsigned long long v = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+        for (; v < n_vec; v += nw) {
+            const float2 *xv = x + v * stride;
+            float re = 0.f, im = 0.f;
+            for (unsigned int i = lane; i < n; i += 32) {
+                float2 s = __ldg(xv + i);
+                float c = __ldg(h + i);
+                re = fmaf(c, s.x, re);
+                im = fmaf(c, s.y, im);
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                re += __shfl_xor_sync(0xffffffffu, re, o);
+                im += __shfl_xor_sync(0xffffffffu, im, o);
+            }
+            if (lane == 0) y[v] = make_float2(re, im);
+        }
+    } else {
+        unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const unsigned long long nt = (unsigned long long)gridDim.x * blockDim.x;
+        for (; v < n_vec; v += nt) {
+            const float2 *xv = x + v * stride;
+            float re = 0.f, im = 0.f;
+            for (unsigned int i = 0; i < n; i++) {
+                float2 s = __ldg(xv + i);
+                float c = __ldg(h + i);
+                re = fmaf(c, s.x, re);
+                im = fmaf(c, s.y, im);
+            }
+            y[v] = make_float2(re, im);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+firpfb_block_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                    const float *__restrict__ sub, unsigned int sub_len, const unsigned int *__restrict__ idx,
+                    float scale, float2 *__restrict__ y, unsigned long long n)
+{
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        // sub[f][sub_len-1-k] multiplies the k-th newest sample (firpfb.c:71-84 stores branches reversed)
+        const float *hf = sub + (size_t)__ldg(idx + i) * sub_len;
+        float re = 0.f, im = 0.f;
+        for (unsigned int k = 0; k < sub_len; k++) {
+            float2 s = lcd::ld_stream(hist, x, (long long)i - (long long)(sub_len - 1) + k, H);  // oldest first
+            float c = __ldg(hf + k);
+            re = fmaf(c, s.x, re);
+            im = fmaf(c, s.y, im);
+        }
+        y[i] = make_float2(re * scale, im * scale);
+    }
+}
+
+inline unsigned int grid_cap(unsigned long long blocks)
+{
+    const unsigned long long cap = 148ull * 8 * 16;
+    return (unsigned int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+namespace lc {
+namespace firfilt {
+
+void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, unsigned int n_taps,
+            float scale, float2 *d_y, unsigned long long n, unsigned int n_streams, cudaStream_t st)
+{
+    const unsigned long long tiles = (n + kTile - 1) / kTile;
+    const unsigned int n_samp = kTile + n_taps - 1;
+    const unsigned int row = (n_samp + kOpt - 1) / kOpt + 1;
+    const size_t smem = sizeof(float) * ((n_taps + 1) & ~1u) + sizeof(float2) * (size_t)row * kOpt;
+    if (smem > 200 * 1024) fatal("firfilt_crcf_execute_block", "filter too long for this build (more than ~20000 taps)");
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        LC_CUDA_CHECK(cudaFuncSetAttribute(firfilt_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        smem_set = 200 * 1024;
+    }
+    unsigned long long total = tiles * n_streams;
+    const unsigned long long max_grid = 1ull << 30;
+    if (total > max_grid) fatal("firfilt_crcf_execute_streams_dev", "too many tiles for one launch");
+    firfilt_tiled_kernel<<<(unsigned int)total, kThreads, smem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n, tiles);
+    LC_LAUNCH_CHECK();
+}
+
+void launch_state_output(const float2 *d_hist, const float *d_taps, unsigned int n_taps, float scale,
+                         float2 *d_y, cudaStream_t st)
+{
+    firfilt_state_output_kernel<<<1, 32, 0, st>>>(d_hist, d_taps, n_taps, scale, d_y);
+    LC_LAUNCH_CHECK();
+}
+
+void launch_dotprod_batch(const float *d_h, unsigned int n, const float2 *d_x, unsigned long long n_vec,
+                          unsigned long long stride, float2 *d_y, cudaStream_t st)
+{
+    int per_warp = n >= 32;
+    unsigned long long threads = per_warp ? n_vec * 32 : n_vec;
+    dotprod_batch_kernel<<<grid_cap((threads + kThreads - 1) / kThreads), kThreads, 0, st>>>(d_h, n, d_x, n_vec, stride, d_y, per_warp);
+    LC_LAUNCH_CHECK();
+}
+
+void launch_firpfb_block(const float2 *d_hist, const float2 *d_x, int H, const float *d_sub, unsigned int sub_len,
+                         const unsigned int *d_idx, float scale, float2 *d_y, unsigned long long n, cudaStream_t st)
+{
+    firpfb_block_kernel<<<grid_cap((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(d_hist, d_x, H, d_sub, sub_len, d_idx, scale, d_y, n);
+    LC_LAUNCH_CHECK();
+}
+
+}  // namespace firfilt
+}  // namespace lc

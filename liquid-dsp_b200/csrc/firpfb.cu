@@ -1,0 +1,169 @@
+// firpfb.cu -- firpfb_crcf: bank of M sub-filters sharing one window (resampler / symsync building block).
+//
+// Replaces src/filter/src/firpfb.c (create :46-95, create_kaiser :105-137, create_rnyquist :146-185,
+// recreate :240-268, reset :308-311, set_scale, push :315-319, execute :325-346).
+// State = the last sub_len samples pushed.  Not used by the channelizers (they own one window per
+// branch); listed by north_star as a changed subsystem, provided for completeness with a batched
+// push+execute entry point.
+#include "lc_common.cuh"
+#include "../../include/liquid_cuda.h"
+#include "host_pipeline.cuh"
+#include "firfilt_kernels.cuh"
+
+struct firpfb_crcf_s {
+    unsigned int M, h_len, sub_len;
+    std::vector<float> sub;        // [M][sub_len], branch i reversed: sub[i][sub_len-1-n] = h[i + nM]
+    float scale = 1.0f;
+    float *d_sub = nullptr;
+    float2 *d_hist = nullptr;      // last sub_len samples, oldest first
+    lc::DevBuf dx, dy, didx, hist_tmp;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+void pfb_load(firpfb_crcf q, const float *h)
+{
+    q->sub.assign((size_t)q->M * q->sub_len, 0.0f);
+    for (unsigned int i = 0; i < q->M; i++)
+        for (unsigned int n = 0; n < q->sub_len; n++)
+            q->sub[(size_t)i * q->sub_len + (q->sub_len - 1 - n)] = h[i + n * q->M];
+    if (q->d_sub) LC_CUDA_CHECK(cudaFree(q->d_sub));
+    LC_CUDA_CHECK(cudaMalloc(&q->d_sub, sizeof(float) * (q->sub.size() ? q->sub.size() : 1)));
+    LC_CUDA_CHECK(cudaMemcpy(q->d_sub, q->sub.data(), sizeof(float) * q->sub.size(), cudaMemcpyHostToDevice));
+}
+}  // namespace
+
+extern "C" {
+
+firpfb_crcf firpfb_crcf_create(unsigned int _M, float *_h, unsigned int _h_len)
+{
+    if (_M == 0) lc::fatal("firpfb_crcf_create", "number of filters must be greater than zero");
+    if (_h_len == 0) lc::fatal("firpfb_crcf_create", "filter length must be greater than zero");
+    lc::ensure_device();
+    firpfb_crcf q = new firpfb_crcf_s();
+    q->M = _M;
+    q->h_len = _h_len;
+    q->sub_len = _h_len / _M;                  // integer division, trailing taps dropped (firpfb.c:68)
+    if (q->sub_len == 0) lc::fatal("firpfb_crcf_create", "filter length must be at least the number of filters");
+    pfb_load(q, _h);
+    LC_CUDA_CHECK(cudaMalloc(&q->d_hist, sizeof(float2) * q->sub_len));
+    LC_CUDA_CHECK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+    firpfb_crcf_reset(q);
+    return q;
+}
+
+firpfb_crcf firpfb_crcf_create_kaiser(unsigned int _M, unsigned int _m, float _fc, float _As)
+{
+    if (_M == 0) lc::fatal("firpfb_crcf_create_kaiser", "number of filters must be greater than zero");
+    if (_m == 0) lc::fatal("firpfb_crcf_create_kaiser", "filter delay must be greater than 0");
+    if (_fc < 0.0f || _fc > 0.5f) lc::fatal("firpfb_crcf_create_kaiser", "filter cut-off frequence must be in (0,0.5)");
+    if (_As < 0.0f) lc::fatal("firpfb_crcf_create_kaiser", "filter excess bandwidth factor must be in [0,1]");
+    unsigned int H_len = 2 * _M * _m + 1;
+    std::vector<float> Hf(H_len);
+    liquid_firdes_kaiser(H_len, _fc / (float)_M, _As, 0.0f, Hf.data());
+    return firpfb_crcf_create(_M, Hf.data(), H_len);
+}
+
+firpfb_crcf firpfb_crcf_create_rnyquist(int _type, unsigned int _M, unsigned int _k, unsigned int _m, float _beta)
+{
+    if (_M == 0) lc::fatal("firpfb_crcf_create_rnyquist", "number of filters must be greater than zero");
+    if (_k < 2) lc::fatal("firpfb_crcf_create_rnyquist", "filter samples/symbol must be greater than 1");
+    if (_m == 0) lc::fatal("firpfb_crcf_create_rnyquist", "filter delay must be greater than 0");
+    if (_beta < 0.0f || _beta > 1.0f) lc::fatal("firpfb_crcf_create_rnyquist", "filter excess bandwidth factor must be in [0,1]");
+    if (_type != LIQUID_FIRFILT_RRC)
+        lc::fatal("firpfb_crcf_create_rnyquist", "only LIQUID_FIRFILT_RRC prototypes are provided by liquid_cuda");
+    unsigned int H_len = 2 * _M * _k * _m + 1;
+    std::vector<float> Hf(H_len);
+    liquid_firdes_rrcos(_M * _k, _m, _beta, 0.0f, Hf.data());
+    return firpfb_crcf_create(_M, Hf.data(), H_len);
+}
+
+firpfb_crcf firpfb_crcf_recreate(firpfb_crcf _q, unsigned int _M, float *_h, unsigned int _h_len)
+{
+    if (_h_len != _q->h_len || _M != _q->M) {
+        firpfb_crcf_destroy(_q);
+        return firpfb_crcf_create(_M, _h, _h_len);
+    }
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+    pfb_load(_q, _h);
+    return _q;
+}
+
+void firpfb_crcf_destroy(firpfb_crcf _q)
+{
+    if (!_q) return;
+    cudaStreamSynchronize(_q->stream);
+    cudaFree(_q->d_sub);
+    cudaFree(_q->d_hist);
+    _q->dx.release();
+    _q->dy.release();
+    _q->didx.release();
+    _q->hist_tmp.release();
+    cudaStreamDestroy(_q->stream);
+    delete _q;
+}
+
+void firpfb_crcf_print(firpfb_crcf _q)
+{
+    printf("fir polyphase filterbank [%u] :\n", _q->M);
+    for (unsigned int i = 0; i < _q->M; i++) {
+        printf("  bank %3u: ", i);
+        for (unsigned int n = 0; n < _q->sub_len; n++) printf("%12.8f ", _q->sub[(size_t)i * _q->sub_len + n]);
+        printf("\n");
+    }
+}
+
+void firpfb_crcf_set_scale(firpfb_crcf _q, float _g) { _q->scale = _g; }
+
+void firpfb_crcf_reset(firpfb_crcf _q)
+{
+    LC_CUDA_CHECK(cudaMemsetAsync(_q->d_hist, 0, sizeof(float2) * _q->sub_len, _q->stream));
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+}
+
+void firpfb_crcf_execute_block(firpfb_crcf _q, liquid_float_complex *_x, const unsigned int *_idx,
+                               unsigned int _n, liquid_float_complex *_y)
+{
+    if (_n == 0) return;
+    for (unsigned int i = 0; i < _n; i++)
+        if (_idx[i] >= _q->M) {
+            fprintf(stderr, "error: firpfb_execute(), filterbank index (%u) exceeds maximum (%u)\n", _idx[i], _q->M);
+            exit(1);
+        }
+    float2 *dx = (float2 *)_q->dx.get(sizeof(float2) * _n);
+    float2 *dy = (float2 *)_q->dy.get(sizeof(float2) * _n);
+    unsigned int *di = (unsigned int *)_q->didx.get(sizeof(unsigned int) * _n);
+    LC_CUDA_CHECK(cudaMemcpyAsync(dx, _x, sizeof(float2) * _n, cudaMemcpyHostToDevice, _q->stream));
+    LC_CUDA_CHECK(cudaMemcpyAsync(di, _idx, sizeof(unsigned int) * _n, cudaMemcpyHostToDevice, _q->stream));
+    lc::firfilt::launch_firpfb_block(_q->d_hist, dx, (int)_q->sub_len, _q->d_sub, _q->sub_len, di, _q->scale, dy, _n, _q->stream);
+    lc::roll_history(_q->d_hist, _q->sub_len, _q->hist_tmp, dx, _n, _q->stream);
+    LC_CUDA_CHECK(cudaMemcpyAsync(_y, dy, sizeof(float2) * _n, cudaMemcpyDeviceToHost, _q->stream));
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+}
+
+void firpfb_crcf_push(firpfb_crcf _q, liquid_float_complex _x)
+{
+    float2 *dx = (float2 *)_q->dx.get(sizeof(float2));
+    LC_CUDA_CHECK(cudaMemcpyAsync(dx, &_x, sizeof(float2), cudaMemcpyHostToDevice, _q->stream));
+    lc::roll_history(_q->d_hist, _q->sub_len, _q->hist_tmp, dx, 1, _q->stream);
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+}
+
+void firpfb_crcf_execute(firpfb_crcf _q, unsigned int _i, liquid_float_complex *_y)
+{
+    if (_i >= _q->M) {
+        fprintf(stderr, "error: firpfb_execute(), filterbank index (%u) exceeds maximum (%u)\n", _i, _q->M);
+        exit(1);
+    }
+    // dot(sub[_i], window) on the state as it stands: a batch of one dot product over d_hist
+    float2 *dy = (float2 *)_q->dy.get(sizeof(float2));
+    lc::firfilt::launch_dotprod_batch(_q->d_sub + (size_t)_i * _q->sub_len, _q->sub_len, _q->d_hist, 1, _q->sub_len, dy, _q->stream);
+    lc_cf out;
+    LC_CUDA_CHECK(cudaMemcpyAsync(&out, dy, sizeof(float2), cudaMemcpyDeviceToHost, _q->stream));
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+    out.re *= _q->scale;
+    out.im *= _q->scale;
+    memcpy(_y, &out, sizeof out);
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// host_pipeline.cuh -- host-pointer block execution shared by the *_execute_block entry points.
+//
+// The caller's host arrays are cut into chunks; chunk c+1's H2D copy, chunk c's kernels and chunk
+// c-1's D2H copy run on three streams, double-buffered, so that with pinned host memory both copy
+// engines and the SMs overlap.  The per-chunk device work (`run`) carries the object's state in
+// stream order on `compute`.  Returns when all output has landed in `y`.
+#pragma once
+#include <algorithm>
+
+#include "lc_common.cuh"
+
+namespace lc {
+
+struct CopyStreams {
+    cudaStream_t in = nullptr, out = nullptr;
+    void ensure()
+    {
+        if (!in) {
+            LC_CUDA_CHECK(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
+            LC_CUDA_CHECK(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+        }
+    }
+};
+
+inline CopyStreams &copy_streams()
+{
+    static thread_local CopyStreams cs;
+    cs.ensure();
+    return cs;
+}
+
+// n_units units of work; unit u reads in_per complex samples at x + u*in_per and writes out_per at
+// y + u*out_per.  run(d_in, n_units_in_chunk, d_out, stream) enqueues the device work of one chunk.
+template <typename Run>
+void host_block(cudaStream_t compute, DevBuf &stage_in, DevBuf &stage_out, const lc_cf *x, lc_cf *y,
+                size_t n_units, size_t in_per, size_t out_per, Run run, size_t chunk_bytes = (32u << 20))
+{
+    if (n_units == 0) return;
+    const size_t per = std::max(in_per, out_per) * sizeof(float2);
+    const size_t chunk_units = std::max<size_t>(1, chunk_bytes / per);
+    const size_t n_chunks = (n_units + chunk_units - 1) / chunk_units;
+    const size_t bufs = n_chunks > 1 ? 2 : 1;
+    const size_t cu = std::min(chunk_units, n_units);
+    float2 *din = (float2 *)stage_in.get(bufs * cu * in_per * sizeof(float2));
+    float2 *dout = (float2 *)stage_out.get(bufs * cu * out_per * sizeof(float2));
+    CopyStreams &cs = copy_streams();
+    std::vector<cudaEvent_t> ev_in(n_chunks), ev_k(n_chunks), ev_out(n_chunks);
+    for (size_t c = 0; c < n_chunks; c++) {
+        LC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+        LC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming));
+        LC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_out[c], cudaEventDisableTiming));
+    }
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t u0 = c * chunk_units, nu = std::min(chunk_units, n_units - u0);
+        float2 *di = din + (c % bufs) * cu * in_per;
+        float2 *dob = dout + (c % bufs) * cu * out_per;
+        if (c >= bufs) {                               // buffer reuse: wait for its last consumers
+            LC_CUDA_CHECK(cudaStreamWaitEvent(cs.in, ev_k[c - bufs], 0));
+            LC_CUDA_CHECK(cudaStreamWaitEvent(compute, ev_out[c - bufs], 0));
+        }
+        LC_CUDA_CHECK(cudaMemcpyAsync(di, x + u0 * in_per, nu * in_per * sizeof(float2), cudaMemcpyHostToDevice, cs.in));
+        LC_CUDA_CHECK(cudaEventRecord(ev_in[c], cs.in));
+        LC_CUDA_CHECK(cudaStreamWaitEvent(compute, ev_in[c], 0));
+        run(di, nu, dob, compute);
+        LC_CUDA_CHECK(cudaEventRecord(ev_k[c], compute));
+        LC_CUDA_CHECK(cudaStreamWaitEvent(cs.out, ev_k[c], 0));
+        LC_CUDA_CHECK(cudaMemcpyAsync(y + u0 * out_per, dob, nu * out_per * sizeof(float2), cudaMemcpyDeviceToHost, cs.out));
+        LC_CUDA_CHECK(cudaEventRecord(ev_out[c], cs.out));
+    }
+    LC_CUDA_CHECK(cudaStreamSynchronize(cs.out));
+    LC_CUDA_CHECK(cudaStreamSynchronize(compute));
+    for (size_t c = 0; c < n_chunks; c++) {
+        cudaEventDestroy(ev_in[c]);
+        cudaEventDestroy(ev_k[c]);
+        cudaEventDestroy(ev_out[c]);
+    }
+}
+
+// new state = last H samples of [hist | x(n samples)], all on the device, in stream order
+inline void roll_history(float2 *d_hist, size_t H, DevBuf &tmpbuf, const float2 *d_x, unsigned long long n, cudaStream_t st)
+{
+    if (n == 0 || H == 0) return;
+    if (n >= H) {
+        LC_CUDA_CHECK(cudaMemcpyAsync(d_hist, d_x + (n - H), sizeof(float2) * H, cudaMemcpyDeviceToDevice, st));
+    } else {
+        float2 *tmp = (float2 *)tmpbuf.get(sizeof(float2) * H);
+        LC_CUDA_CHECK(cudaMemcpyAsync(tmp, d_hist + n, sizeof(float2) * (H - n), cudaMemcpyDeviceToDevice, st));
+        LC_CUDA_CHECK(cudaMemcpyAsync(tmp + (H - n), d_x, sizeof(float2) * n, cudaMemcpyDeviceToDevice, st));
+        LC_CUDA_CHECK(cudaMemcpyAsync(d_hist, tmp, sizeof(float2) * H, cudaMemcpyDeviceToDevice, st));
+    }
+}
+
+}  // namespace lc

@@ -1,0 +1,165 @@
+// pfb_kernels.cu -- generic polyphase multiply-accumulate kernels (any M, any tap count).
+//
+// One thread per output element, channel index fastest so that every load and store of a warp is
+// a contiguous run; samples are re-read through L1/L2 (each is used by 2m..4m outputs).  These are
+// the shape-agnostic kernels; the shapes the benchmarks run use the fused kernels in
+// pfbch2_fused.cu, which keep the sliding windows in registers.
+#include "pfb_kernels.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads)
+pfbch2_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                  const float *__restrict__ taps, float2 *__restrict__ X, unsigned int M, unsigned int L,
+                  unsigned long long n_frames, int parity0)
+{
+    const unsigned int M2 = M >> 1;
+    const unsigned long long total = n_frames * M;
+    for (unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long t = (long long)(gid / M);
+        const unsigned int w = (unsigned int)(gid % M);
+        const int par = (parity0 + (int)(t & 1)) & 1;
+        const bool lower = w < M2;                      // lower half is pushed on even frames
+        const long long tu = (par == (lower ? 0 : 1)) ? t : t - 1;     // frame of the newest sample
+        const long long off = lower ? (long long)(M2 - 1 - w) : (long long)(M - 1 - w);
+        const float *tp = taps + (size_t)par * L * M + w;
+        float re = 0.f, im = 0.f;
+        for (unsigned int n = 0; n < L; n++) {
+            long long idx = (tu - 2 * (long long)n) * (long long)M2 + off;
+            float2 s = lcd::ld_stream(hist, x, idx, H);
+            float c = __ldg(tp + (size_t)n * M);
+            re = fmaf(c, s.x, re);
+            im = fmaf(c, s.y, im);
+        }
+        X[gid] = make_float2(re, im);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+pfbch2_synth_fir_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ v, int hist_rows,
+                        const float *__restrict__ taps, float2 *__restrict__ y, unsigned int M,
+                        unsigned int n_taps, unsigned long long n_frames, int parity0)
+{
+    const unsigned int M2 = M >> 1;
+    const unsigned long long total = n_frames * M2;
+    for (unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long t = (long long)(gid / M2);
+        const unsigned int i = (unsigned int)(gid % M2);
+        const int par = (parity0 + (int)(t & 1)) & 1;
+        const unsigned int j = i + (par ? M2 : 0);
+        // even and odd taps are the reference's two dot products (dp[i], dp[i+M/2]); summed apart
+        float re0 = 0.f, im0 = 0.f, re1 = 0.f, im1 = 0.f;
+        for (unsigned int q = 0; q < n_taps; q++) {
+            long long r = t - (long long)q;
+            float2 s = (r >= 0) ? __ldg(v + (size_t)r * M + j) : __ldg(hist + (size_t)(hist_rows + r) * M + j);
+            float c = __ldg(taps + (size_t)q * M2 + i);
+            if (q & 1) { re1 = fmaf(c, s.x, re1); im1 = fmaf(c, s.y, im1); }
+            else       { re0 = fmaf(c, s.x, re0); im0 = fmaf(c, s.y, im0); }
+        }
+        y[gid] = make_float2(re0 + re1, im0 + im1);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+pfbch_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                 const float *__restrict__ taps, float2 *__restrict__ X, unsigned int M, unsigned int p,
+                 unsigned long long n_frames, unsigned int phase, unsigned int first, unsigned int k)
+{
+    const unsigned long long total = n_frames * M;
+    for (unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long s = (long long)(gid / M);
+        const unsigned int u = (unsigned int)(gid % M);         // transform input index
+        const unsigned int i = M - 1 - u;                       // branch
+        const unsigned int win = (i + k) % M;                   // window it reads (firpfbch.c:395)
+        // pushes are numbered from `phase` (push c goes to window M-1-(c mod M), firpfbch.c:369-377);
+        // x[0] is push number `phase`; run s happens after `first` + s*M samples of x, i.e. after
+        // pushes up to C-1
+        const long long C = (long long)phase + (long long)first + s * (long long)M;
+        const long long rr = (long long)(M - 1 - win);
+        long long d = (C - 1 - rr) % (long long)M;
+        if (d < 0) d += M;
+        const long long last = C - 1 - d - (long long)phase;    // index into x of the newest sample
+        const float *tp = taps + i;
+        float re = 0.f, im = 0.f;
+        for (unsigned int n = 0; n < p; n++) {
+            float2 smp = lcd::ld_stream(hist, x, last - (long long)n * M, H);
+            float c = __ldg(tp + (size_t)n * M);
+            re = fmaf(c, smp.x, re);
+            im = fmaf(c, smp.y, im);
+        }
+        X[gid] = make_float2(re, im);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+pfbch_synth_fir_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ v, int hist_rows,
+                       const float *__restrict__ taps, float2 *__restrict__ y, unsigned int M, unsigned int p,
+                       unsigned long long n_frames)
+{
+    const unsigned long long total = n_frames * M;
+    for (unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long s = (long long)(gid / M);
+        const unsigned int i = (unsigned int)(gid % M);
+        float re = 0.f, im = 0.f;
+        for (unsigned int n = 0; n < p; n++) {
+            long long r = s - (long long)n;
+            float2 smp = (r >= 0) ? __ldg(v + (size_t)r * M + i) : __ldg(hist + (size_t)(hist_rows + r) * M + i);
+            float c = __ldg(taps + (size_t)n * M + i);
+            re = fmaf(c, smp.x, re);
+            im = fmaf(c, smp.y, im);
+        }
+        y[gid] = make_float2(re, im);
+    }
+}
+
+inline unsigned int grid_for(unsigned long long total)
+{
+    unsigned long long b = (total + kThreads - 1) / kThreads;
+    const unsigned long long cap = 148ull * 8 * 16;     // grid-stride beyond this
+    return (unsigned int)(b < cap ? (b ? b : 1) : cap);
+}
+
+}  // namespace
+
+namespace lc {
+namespace pfb {
+
+void launch_pfbch2_mac(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, float2 *d_X,
+                       unsigned int M, unsigned int L, unsigned long long n_frames, int parity0, cudaStream_t st)
+{
+    pfbch2_mac_kernel<<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, L, n_frames, parity0);
+    LC_LAUNCH_CHECK();
+}
+
+void launch_pfbch2_synth_fir(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float *d_taps,
+                             float2 *d_y, unsigned int M, unsigned int n_taps, unsigned long long n_frames,
+                             int parity0, cudaStream_t st)
+{
+    pfbch2_synth_fir_kernel<<<grid_for(n_frames * (M / 2)), kThreads, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y,
+                                                                              M, n_taps, n_frames, parity0);
+    LC_LAUNCH_CHECK();
+}
+
+void launch_pfbch_mac(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, float2 *d_X,
+                      unsigned int M, unsigned int p, unsigned long long n_frames, unsigned int phase,
+                      unsigned int first, unsigned int k, cudaStream_t st)
+{
+    pfbch_mac_kernel<<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, p, n_frames, phase, first, k);
+    LC_LAUNCH_CHECK();
+}
+
+void launch_pfbch_synth_fir(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float *d_taps,
+                            float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st)
+{
+    pfbch_synth_fir_kernel<<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, p, n_frames);
+    LC_LAUNCH_CHECK();
+}
+
+}  // namespace pfb
+}  // namespace lc

@@ -1,0 +1,126 @@
+// runtime.cu -- device selection, memory helpers, launch counter, synthetic input generator.
+#include "lc_common.cuh"
+#include "../../include/liquid_cuda.h"
+
+namespace lc {
+
+std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_device_ready{0};
+
+void ensure_device()
+{
+    if (g_device_ready.load(std::memory_order_acquire)) return;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        fprintf(stderr, "liquid_cuda: no CUDA device available (%s); this library has no CPU fallback\n",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        abort();
+    }
+    const char *env = getenv("LIQUID_CUDA_DEVICE");
+    if (env) {
+        int dev = atoi(env);
+        if (dev < 0 || dev >= count) {
+            fprintf(stderr, "liquid_cuda: LIQUID_CUDA_DEVICE=%s out of range (have %d devices)\n", env, count);
+            abort();
+        }
+        LC_CUDA_CHECK(cudaSetDevice(dev));
+    }
+    int dev = 0;
+    LC_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    LC_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        fprintf(stderr, "liquid_cuda: device %d (%s) is sm_%d%d; this build carries sm_100a code only\n",
+                dev, prop.name, prop.major, prop.minor);
+        abort();
+    }
+    g_device_ready.store(1, std::memory_order_release);
+}
+
+}  // namespace lc
+
+// u(n,c) = (mix64(seed + 2n + c) >> 40) * 2^-24 - 0.5     
+__device__ __forceinline__ unsigned long long lc_mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__global__ void lc_synth_input_kernel(float2 *__restrict__ x, unsigned long long seed,
+                                      unsigned long long first, unsigned long long n)
+{
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        unsigned long long k = seed + 2 * (first + i);
+        float re = (float)(lc_mix64(k) >> 40) * (1.0f / 16777216.0f) - 0.5f;
+        float im = (float)(lc_mix64(k + 1) >> 40) * (1.0f / 16777216.0f) - 0.5f;
+        x[i] = make_float2(re, im);
+    }
+}
+
+extern "C" {
+
+const char *liquid_cuda_version(void) { return LC_VERSION; }
+
+int liquid_cuda_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
+void liquid_cuda_set_device(int _device)
+{
+    LC_CUDA_CHECK(cudaSetDevice(_device));
+    lc::ensure_device();
+}
+
+void *liquid_cuda_malloc(unsigned long long _bytes)
+{
+    lc::ensure_device();
+    void *p = nullptr;
+    LC_CUDA_CHECK(cudaMalloc(&p, _bytes ? _bytes : 1));
+    return p;
+}
+
+void liquid_cuda_free(void *_dptr) { if (_dptr) LC_CUDA_CHECK(cudaFree(_dptr)); }
+
+void *liquid_cuda_host_alloc(unsigned long long _bytes)
+{
+    lc::ensure_device();
+    void *p = nullptr;
+    LC_CUDA_CHECK(cudaHostAlloc(&p, _bytes ? _bytes : 1, cudaHostAllocDefault));
+    return p;
+}
+
+void liquid_cuda_host_free(void *_hptr) { if (_hptr) LC_CUDA_CHECK(cudaFreeHost(_hptr)); }
+
+void liquid_cuda_memcpy_h2d(void *_dst, const void *_src, unsigned long long _bytes)
+{
+    LC_CUDA_CHECK(cudaMemcpy(_dst, _src, _bytes, cudaMemcpyHostToDevice));
+}
+
+void liquid_cuda_memcpy_d2h(void *_dst, const void *_src, unsigned long long _bytes)
+{
+    LC_CUDA_CHECK(cudaMemcpy(_dst, _src, _bytes, cudaMemcpyDeviceToHost));
+}
+
+void liquid_cuda_sync(void) { LC_CUDA_CHECK(cudaDeviceSynchronize()); }
+
+unsigned long long liquid_cuda_launch_count(void) { return lc::g_launches.load(); }
+
+void liquid_cuda_synth_input_dev(void *_d_x, unsigned long long _seed, unsigned long long _first,
+                                 unsigned long long _n, void *_stream)
+{
+    lc::ensure_device();
+    if (_n == 0) return;
+    unsigned long long blocks = (_n + 255) / 256;
+    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    lc_synth_input_kernel<<<(unsigned int)blocks, 256, 0, lc::as_stream(_stream)>>>((float2 *)_d_x, _seed, _first, _n);
+    LC_LAUNCH_CHECK();
+}
+
+}  // extern "C"

@@ -1,0 +1,372 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on
+the same seeded inputs, against the committed reference fixtures and the reference's golden
+vectors, plus size-independent properties at larger sizes.
+
+Tolerances (BASELINE.json north_star): per-channel relative RMS error <= 1e-5 and
+max-abs error <= 1e-4 normalised to sqrt(input power), for the float32 channelizer outputs."""
+import numpy as np
+import pytest
+
+from conftest import TOL_MAX_ABS, TOL_REL_RMS, cplx, max_abs_norm, rel_rms_per_channel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    import liquid_dsp_b200
+    assert liquid_dsp_b200.device_count() > 0, "GPU tests need a CUDA device"
+    return liquid_dsp_b200
+
+
+def check_channels(y, want, x):
+    assert rel_rms_per_channel(y, want).max() < TOL_REL_RMS
+    assert max_abs_norm(y, want, x) < TOL_MAX_ABS
+
+
+# ------------------------------------------------------------------ firpfbch2 analysis (headline path)
+@pytest.mark.parametrize("M,m,nfr", [(8, 5, 80), (16, 5, 80), (32, 5, 64), (64, 5, 64), (6, 2, 50), (12, 3, 41),
+                                     (256, 4, 48), (1024, 7, 96), (4096, 9, 40), (2048, 3, 24), (128, 1, 33)])
+def test_pfbch2_analysis_vs_oracle(L, orc, M, m, nfr):
+    x = orc.synth_input(nfr * M // 2, seed=0xA0 + M)
+    want = orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0).execute_frames(x)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    got = q.execute_block(x)
+    check_channels(got, want, x)
+
+
+@pytest.mark.parametrize("M,m", [(8, 5), (16, 5), (64, 3), (6, 2), (256, 4)])
+def test_pfbch2_vs_reference_fixtures(L, refout, M, m):
+    x = refout["pfbch2_a_M%d_m%d_x" % (M, m)]
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    check_channels(q.execute_block(x), refout["pfbch2_a_M%d_m%d_y" % (M, m)], x)
+    X = refout["pfbch2_s_M%d_m%d_x" % (M, m)]
+    want = refout["pfbch2_s_M%d_m%d_y" % (M, m)]
+    qs = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+    got = qs.execute_block(X)
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+
+
+def test_pfbch2_survey_fingerprints(L, refout):
+    x = refout["pfbch2_a_M16_m5_lcg_x"]
+    y = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, 16, 5, 60.0).execute_block(x)
+    assert abs(y[0, 0] - (-7.94109947e-05)) < 1e-8
+    assert abs(y[21, 1] - (1.93961821e-02 - 8.78997445e-02j)) < 1e-6
+    assert abs(y[79, 2] - (-7.58994371e-02 - 8.95354375e-02j)) < 1e-6
+
+
+def test_pfbch2_single_frame_execute_equals_block_and_state_carry(L, orc):
+    """k x execute == execute_block(k), bit for bit, across odd splits (flag and history carried)"""
+    M, m = 32, 4
+    x = orc.synth_input(37 * M // 2, seed=5)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    whole = q.execute_block(x)
+    q.reset()
+    one = np.stack([q.execute(x[t * M // 2:(t + 1) * M // 2]) for t in range(37)])
+    assert np.array_equal(whole, one)
+    q.reset()
+    parts = np.concatenate([q.execute_block(x[:5 * M // 2]), q.execute_block(x[5 * M // 2:18 * M // 2]),
+                            q.execute_block(x[18 * M // 2:])])
+    assert np.array_equal(whole, parts)
+
+
+def test_pfbch2_get_set_state_resumes(L, orc):
+    M, m = 64, 3
+    x = orc.synth_input(40 * M // 2, seed=6)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    whole = q.execute_block(x)
+    q.reset()
+    a = q.execute_block(x[:13 * M // 2])
+    hist, flag = q.get_state()
+    assert flag == 1 and hist.size == q.get_state_len()
+    q2 = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    q2.set_state(hist, flag)
+    b = q2.execute_block(x[13 * M // 2:])
+    assert np.array_equal(whole, np.concatenate([a, b]))
+
+
+@pytest.mark.parametrize("M", [8, 16, 32, 64])
+def test_pfbch2_autotest_roundtrip(L, M):
+    """firpfbch2_crcf_autotest.c:27-99 run on the GPU objects: analysis -> synthesis reconstructs
+    the input delayed by 2Mm - M/2 + 1 within 1e-3, interleaving single-frame execute calls"""
+    m, As = 5, 60.0
+    n = M * 8 * m
+    s, x = 1, np.empty(n, np.complex64)
+    for i in range(n):
+        s = (s * 524287) % 1031
+        x[i] = np.float32(s) / np.float32(1031) - np.float32(0.5)
+    qa = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, As)
+    qs = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, As)
+    y = np.empty(n, np.complex64)
+    for i in range(0, n, M // 2):
+        Y = qa.execute(x[i:i + M // 2])
+        y[i:i + M // 2] = qs.execute(Y)
+    delay = 2 * M * m - M // 2 + 1
+    assert np.abs(y[:delay]).max() < 1e-3
+    assert np.abs(y[delay:] - x[:n - delay]).max() < 1e-3
+
+
+@pytest.mark.parametrize("M,m,nfr", [(16, 3, 60), (64, 2, 40), (10, 2, 33), (256, 4, 30)])
+def test_pfbch2_synthesis_vs_oracle(L, orc, M, m, nfr):
+    X = orc.synth_input(nfr * M, seed=0xB0 + M)
+    want = orc.Firpfbch2(orc.SYNTHESIZER, M, m, As=60.0).execute_frames(X)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+    got = np.concatenate([q.execute_block(X[:7 * M]), q.execute_block(X[7 * M:])])
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+
+
+def test_pfbch2_large_block_linearity_and_time_invariance(L, orc):
+    """size-independent properties at a large size (2^22 samples, M=1024, m=7): linearity, and
+    invariance to a shift by a whole number of frame pairs once the history is flushed"""
+    M, m = 1024, 7
+    n = 1 << 22
+    a = orc.synth_input(n, seed=21)
+    b = orc.synth_input(n, seed=22)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    ya = q.execute_block(a); q.reset()
+    yb = q.execute_block(b); q.reset()
+    yab = q.execute_block((a + 2 * b).astype(np.complex64)); q.reset()
+    assert np.abs(yab - (ya + 2 * yb)).max() < 2e-6 * 3
+    shift = 2 * 10                       # frames (even: same parity)
+    ys = q.execute_block(a[shift * M // 2:])
+    skip = 4 * m                          # frames needed to flush the zero history
+    assert np.abs(ys[skip:] - ya[shift + skip:]).max() < 1e-6
+    # a segment deep inside the stream against the oracle started 2mM samples earlier (SURVEY 8c trick)
+    f0 = 5000
+    start = f0 * M // 2 - 2 * m * M
+    seg = orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0).execute_frames(a[start:start + (4 * m + 64) * M // 2])
+    check_channels(ya[f0:f0 + 64], seg[4 * m:4 * m + 64], a[:4096])
+
+
+def test_pfbch2_segment_form_equals_stateful(L, orc):
+    """the stateless halo form used by the multi-GPU time sharding reproduces the stateful stream"""
+    import ctypes as C
+    M, m = 256, 4
+    nfr = 64
+    x = orc.synth_input(nfr * M // 2, seed=31)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    whole = q.execute_block(x)
+    H = q.get_state_len()
+    cut = 22 * M // 2                     # segment boundary (even frame), inside the stream
+    xin = np.concatenate([np.zeros(H, np.complex64), x]).astype(np.complex64)
+    d_in = L.lib.liquid_cuda_malloc(xin.nbytes)
+    d_out = L.lib.liquid_cuda_malloc((nfr - 22) * M * 8)
+    L.lib.liquid_cuda_memcpy_h2d(d_in, xin.ctypes.data_as(C.c_void_p), xin.nbytes)
+    d_x = d_in + 8 * (H + cut)
+    q.execute_segment_dev(d_x - 8 * H, d_x, 22, nfr - 22, d_out, 0)
+    L.lib.liquid_cuda_sync()
+    got = np.empty(((nfr - 22), M), np.complex64)
+    L.lib.liquid_cuda_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_out, got.nbytes)
+    L.lib.liquid_cuda_free(d_in); L.lib.liquid_cuda_free(d_out)
+    assert np.array_equal(got, whole[22:])
+
+
+# ------------------------------------------------------------------ firpfbch
+@pytest.mark.parametrize("M,m,nfr", [(4, 3, 40), (16, 4, 64), (10, 2, 33), (64, 5, 40), (256, 5, 48), (1024, 2, 20)])
+def test_pfbch_analysis_and_synthesis_vs_oracle(L, orc, M, m, nfr):
+    x = orc.synth_input(nfr * M, seed=0xC0 + M)
+    for typ_o, typ_l in ((orc.ANALYZER, L.LIQUID_ANALYZER), (orc.SYNTHESIZER, L.LIQUID_SYNTHESIZER)):
+        want = orc.Firpfbch(typ_o, M, kaiser=(m, 60.0)).execute_frames(x)
+        q = L.firpfbch_crcf.create_kaiser(typ_l, M, m, 60.0)
+        got = np.concatenate([q.execute_block(x[:9 * M]), q.execute_block(x[9 * M:])])
+        assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+        if typ_o == orc.ANALYZER:
+            assert rel_rms_per_channel(got, want).max() < TOL_REL_RMS
+
+
+@pytest.mark.parametrize("M,m", [(4, 3), (16, 4), (10, 2), (64, 5)])
+def test_pfbch_vs_reference_fixtures(L, refout, M, m):
+    x = refout["pfbch_a_M%d_m%d_x" % (M, m)]
+    for kind, typ in (("a", L.LIQUID_ANALYZER), ("s", L.LIQUID_SYNTHESIZER)):
+        want = refout["pfbch_%s_M%d_m%d_y" % (kind, M, m)]
+        got = L.firpfbch_crcf.create_kaiser(typ, M, m, 60.0).execute_block(x)
+        assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+
+
+def test_pfbch_rrc_vs_reference_fixture(L, refout):
+    x = refout["pfbch_rrc_M8_m3_x"]
+    for kind, typ in (("a", L.LIQUID_ANALYZER), ("s", L.LIQUID_SYNTHESIZER)):
+        want = refout["pfbch_rrc_%s_M8_m3_y" % kind]
+        got = L.firpfbch_crcf.create_rnyquist(typ, 8, 3, 0.4, L.LIQUID_FIRFILT_RRC).execute_block(x)
+        assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+
+
+def test_pfbch_analyzer_autotest_equivalence(L, orc):
+    """firpfbch_crcf_analyzer_autotest.c:29-152 on the GPU objects (firpfbch + firfilt), tol 1e-4"""
+    M, p, S = 4, 5, 40
+    rng = np.random.default_rng(9)
+    h = (rng.integers(0, 4, M * p) - 1.5).astype(np.float32)
+    x = (0.1 * np.sqrt(0.5) * ((rng.integers(0, 4, M * S) - 1.5) + 1j * (rng.integers(0, 4, M * S) - 1.5))).astype(np.complex64)
+    q = L.firpfbch_crcf.create(L.LIQUID_ANALYZER, M, p, h)
+    Y0 = np.stack([q.analyzer_execute(x[i * M:(i + 1) * M]) for i in range(S)])
+    f = L.firfilt_crcf.create(h)
+    j = np.arange(M * S)
+    for c in range(M):
+        f.reset()
+        mixed = (x * np.exp(-2j * np.pi * c * j / M)).astype(np.complex64)
+        y = f.execute_block(mixed)
+        assert np.abs(Y0[:, c] - y[M - 1::M]).max() < 1e-4
+
+
+def test_pfbch_push_run_alignment(L, orc):
+    """analyzer_push / analyzer_run(k) (firpfbch.c:369-409; sandbox/firpfbch_analysis_alignment_test.c)"""
+    import ctypes as C
+    M, m = 8, 2
+    x = orc.synth_input(5 * M + 3, seed=41)
+    q = L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    o = orc.Firpfbch(orc.ANALYZER, M, kaiser=(m, 60.0))
+    for i, v in enumerate(x):
+        q.analyzer_push(v)
+        orc.lib().orc_firpfbch_analyzer_push(o.h, orc.c_cf(v.real, v.imag))
+        if i % 5 == 4:
+            for k in (0, 3, M - 1):
+                want = np.empty(M, np.complex64)
+                orc.lib().orc_firpfbch_analyzer_run(o.h, k, want)
+                got = q.analyzer_run(k)
+                assert np.abs(got - want).max() < 1e-5 * max(1.0, np.abs(want).max())
+
+
+# ------------------------------------------------------------------ firfilt
+@pytest.mark.parametrize("tag", ["h4x8", "h7x16", "h13x32", "h23x64"])
+def test_firfilt_reference_golden_vectors(L, kat, tag):
+    case = kat["firfilt_crcf"]["cases"][tag]
+    y = L.firfilt_crcf.create(np.array(case["h"], np.float32)).execute_block(cplx(case["x"]))
+    assert np.abs(y - cplx(case["y"])).max() < kat["firfilt_crcf"]["tol"]
+    # push / execute, sample by sample (firfilt_runtest.c:82-90)
+    q = L.firfilt_crcf.create(np.array(case["h"], np.float32))
+    for xv, yv in zip(cplx(case["x"]), cplx(case["y"])):
+        q.push(xv)
+        assert abs(q.execute() - yv) < kat["firfilt_crcf"]["tol"]
+
+
+def test_firfilt_vs_reference_fixture_and_oracle(L, orc, refout):
+    x = refout["firfilt_k64_x"]
+    q = L.firfilt_crcf.create_kaiser(64, 0.25, 60.0, 0.0)
+    assert q.get_length() == 64
+    y = np.concatenate([q.execute_block(x[:100]), q.execute_block(x[100:101]), q.execute_block(x[101:])])
+    assert np.abs(y - refout["firfilt_k64_y"]).max() < 2e-6
+    q.reset(); q.set_scale(0.375)
+    assert np.abs(q.execute_block(x) - refout["firfilt_k64_scale_y"]).max() < 2e-6
+    # in place (x == y), firfilt.c:340-341
+    q.reset(); q.set_scale(1.0)
+    buf = x.copy()
+    q.execute_block(buf, out=buf)
+    assert np.abs(buf - refout["firfilt_k64_y"]).max() < 2e-6
+    for n_taps in (1, 2, 5, 31, 200, 1025):
+        h = np.random.default_rng(n_taps).standard_normal(n_taps).astype(np.float32)
+        xx = orc.synth_input(5000, seed=n_taps)
+        want = orc.Firfilt(h=h).execute_block(xx)
+        got = L.firfilt_crcf.create(h).execute_block(xx)
+        assert np.abs(got - want).max() < 2e-6 * np.sqrt(n_taps) * max(1.0, np.abs(want).max())
+
+
+def test_firfilt_streams_dev(L, orc):
+    import ctypes as C
+    n_streams, n = 7, 3000
+    x = orc.synth_input(n_streams * n, seed=51).reshape(n_streams, n)
+    q = L.firfilt_crcf.create_kaiser(64, 0.25, 60.0, 0.0)
+    d_x = L.lib.liquid_cuda_malloc(x.nbytes); d_y = L.lib.liquid_cuda_malloc(x.nbytes)
+    L.lib.liquid_cuda_memcpy_h2d(d_x, x.ctypes.data_as(C.c_void_p), x.nbytes)
+    q.execute_streams_dev(d_x, n_streams, n, d_y, 0)
+    L.lib.liquid_cuda_sync()
+    got = np.empty_like(x)
+    L.lib.liquid_cuda_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_y, x.nbytes)
+    L.lib.liquid_cuda_free(d_x); L.lib.liquid_cuda_free(d_y)
+    o = orc.Firfilt(kaiser=(64, 0.25, 60.0, 0.0))
+    for s in range(n_streams):
+        o.reset()
+        assert np.abs(got[s] - o.execute_block(x[s])).max() < 2e-6
+
+
+def test_firfilt_freqresponse_groupdelay(L):
+    h = np.array([0.1, 0.5, 1.0, 0.5, 0.1], np.float32)
+    q = L.firfilt_crcf.create(h)
+    H = q.freqresponse(0.1)
+    want = (h[::-1] * np.exp(2j * np.pi * 0.1 * np.arange(5))).sum()
+    assert abs(H - want) < 1e-5
+    assert abs(q.groupdelay(0.1) - 2.0) < 1e-4
+
+
+# ------------------------------------------------------------------ dotprod / firpfb / fft
+def test_dotprod_reference_kats(L, kat):
+    for case in kat["dotprod_crcf"]["cases"]:
+        h, x, want = np.array(case["h"], np.float32), cplx(case["x"]), complex(*case["y"])
+        assert abs(L.dotprod_crcf.run(h, x) - want) < kat["dotprod_crcf"]["tol"]
+        assert abs(L.dotprod_crcf(h).execute(x) - want) < kat["dotprod_crcf"]["tol"]
+
+
+def test_dotprod_struct_vs_ordinal(L):
+    """dotprod_crcf_autotest.c:160-166 (n = 1..512), tolerance 1e-4 relative to the vector norm"""
+    rng = np.random.default_rng(3)
+    for n in [1, 2, 3, 4, 7, 8, 15, 16, 31, 32, 33, 63, 64, 100, 255, 256, 512]:
+        h = rng.standard_normal(n).astype(np.float32)
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        want = (h.astype(np.float64) * x.astype(np.complex128)).sum()
+        assert abs(L.dotprod_crcf(h).execute(x) - want) < 1e-4 * max(1.0, np.sqrt(n))
+
+
+def test_firpfb_reference_kat_and_oracle(L, orc, kat):
+    k = kat["firpfb"]
+    q = L.firpfb_crcf(k["M"], np.array(k["h"], np.float32))
+    for v in k["x"]:
+        q.push(v)
+    for i, want in enumerate(k["y"]):
+        got = q.execute(i)
+        assert abs(got.real - want) < k["tol"] and abs(got.imag) < k["tol"]
+    # batched push+execute against the oracle
+    M, m = 8, 4
+    qo = orc.Firpfb(M, kaiser=(m, 0.3, 50.0))
+    ql = L.firpfb_crcf.create_kaiser(M, m, 0.3, 50.0)
+    ql.set_scale(0.5); qo.set_scale(0.5)
+    x = orc.synth_input(300, seed=61)
+    idx = (np.arange(300) * 5) % M
+    want = np.empty(300, np.complex64)
+    for i in range(300):
+        qo.push(x[i]); want[i] = qo.execute(int(idx[i]))
+    got = np.concatenate([ql.execute_block(x[:123], idx[:123]), ql.execute_block(x[123:], idx[123:])])
+    assert np.abs(got - want).max() < 2e-6
+
+
+def test_fft_reference_golden_vectors(L, kat):
+    """fft_runtest.c:30-66: forward vs golden, inverse round trip, every size the reference ships"""
+    for n, case in kat["fft"]["cases"].items():
+        x, want = cplx(case["x"]), cplx(case["y"])
+        y = L.fft_run(x, L.LIQUID_FFT_FORWARD)
+        assert np.abs(y - want).max() < kat["fft"]["tol"], n
+        z = L.fft_run(y, L.LIQUID_FFT_BACKWARD) / np.float32(int(n))
+        assert np.abs(z - x).max() < kat["fft"]["tol"], n
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_fft_pow2_vs_numpy_and_plan_api(L, orc, n):
+    x = orc.synth_input(n * 3, seed=70 + n)
+    xin, yout = x[:n].copy(), np.empty(n, np.complex64)
+    p = L.fftplan(n, xin, yout, L.LIQUID_FFT_FORWARD)
+    p.execute()
+    want = np.fft.fft(xin.astype(np.complex128))
+    assert np.abs(yout - want).max() / np.abs(want).max() < 2e-6
+    yb = p.execute_batch(x)                      # 3 transforms
+    wantb = np.fft.fft(x.reshape(3, n).astype(np.complex128), axis=1).reshape(-1)
+    assert np.abs(yb - wantb).max() / np.abs(wantb).max() < 2e-6
+    back = L.fft_run(yout, L.LIQUID_FFT_BACKWARD)
+    assert np.abs(back / n - xin).max() < 1e-5
+
+
+def test_fft_reference_fixtures(L, refout):
+    for n in (128, 256, 1024, 4096):
+        x = refout["fft_%d_x" % n]
+        for d, key in ((L.LIQUID_FFT_FORWARD, "fwd"), (L.LIQUID_FFT_BACKWARD, "bwd")):
+            want = refout["fft_%d_%s" % (n, key)]
+            assert np.abs(L.fft_run(x, d) - want).max() / np.abs(want).max() < 2e-6
+
+
+def test_synth_input_dev_matches_host_generator(L, orc):
+    import ctypes as C
+    n = 100000
+    d = L.lib.liquid_cuda_malloc(n * 8)
+    L.synth_input_dev(d, n, seed=0x5EED0000 + 3, first=12345)
+    L.lib.liquid_cuda_sync()
+    got = np.empty(n, np.complex64)
+    L.lib.liquid_cuda_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d, n * 8)
+    L.lib.liquid_cuda_free(d)
+    assert np.array_equal(got, orc.synth_input(n, seed=0x5EED0000 + 3, first=12345))
