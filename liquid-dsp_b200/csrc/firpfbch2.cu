@@ -10,11 +10,13 @@
 //   and branch (w+M/2)%M on odd frames;       the result is input w of an unscaled backward DFT;
 //   the output is divided by M.
 #include <cmath>
+#include <cstdint>
 
 #include "lc_common.cuh"
 #include "../../include/liquid_cuda.h"
 #include "pfb_kernels.cuh"
 #include "host_pipeline.cuh"
+#include "pfbch2_fused.cuh"
 
 struct firpfbch2_crcf_s {
     int type;
@@ -22,6 +24,9 @@ struct firpfbch2_crcf_s {
     unsigned int H;                // history length kept as state (samples)
     std::vector<float> h;          // prototype, first 2mM taps (host copy for print)
     float *d_taps = nullptr;       // analyzer: [2][L][M] (parity, tap, window); synthesizer: [4m][M/2]
+    float *d_taps_scaled = nullptr;// analyzer, fused kernel only: d_taps * (1/M)
+    float2 *d_tw_fused = nullptr;  // fused kernel's inter-stage twiddles
+    bool fused = false;
     float2 *d_hist = nullptr;      // last H samples (analyzer: inputs; synthesizer: scaled IDFT rows)
     int flag = 0;                  // frame parity (firpfbch2.c:57)
     lc::FftPlanDev fft;            // M-point backward transform
@@ -36,9 +41,17 @@ void analyze_dev(firpfbch2_crcf q, const float2 *d_hist, const float2 *d_x, int 
                  unsigned long long n_frames, float2 *d_y, cudaStream_t st)
 {
     if (n_frames == 0) return;
-    // v1 path: polyphase MAC into the output buffer, then an in-place batched backward FFT with /M
-    lc::pfb::launch_pfbch2_mac(d_hist, d_x, (int)q->H, q->d_taps, d_y, q->M, q->L, n_frames, parity0, st);
-    q->fft.run(d_y, d_y, n_frames, st, /*post: divide*/ 1, (float)q->M, 1.0f);
+    unsigned long long done = 0;
+    if (q->fused && n_frames >= 32 && ((uintptr_t)d_x % 16) == 0 && !getenv("LIQUID_CUDA_NO_FUSED"))
+        done = (unsigned long long)lc::pfb::launch_pfbch2_fused(d_hist, d_x, (int)q->H, q->d_taps_scaled, q->d_tw_fused,
+                                                                d_y, q->M, q->L, n_frames, parity0, st);
+    if (done == n_frames) return;
+    // shape-generic path (and the 0..3 frames the fused kernel leaves): polyphase MAC into the
+    // output buffer, then an in-place batched backward FFT with /M
+    float2 *d_yr = d_y + done * q->M;
+    lc::pfb::launch_pfbch2_mac(d_hist, d_x, (int)q->H, q->d_taps, d_yr, q->M, q->L, n_frames - done, parity0, st,
+                               (long long)done);
+    q->fft.run(d_yr, d_yr, n_frames - done, st, /*post: divide*/ 1, (float)q->M, 1.0f);
 }
 
 void synthesize_dev(firpfbch2_crcf q, const float2 *d_hist, const float2 *d_x, int parity0,
@@ -98,6 +111,18 @@ firpfbch2_crcf firpfbch2_crcf_create(int _type, unsigned int _M, unsigned int _m
     }
     LC_CUDA_CHECK(cudaMalloc(&q->d_taps, taps.size() * sizeof(float)));
     LC_CUDA_CHECK(cudaMemcpy(q->d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (_type == LIQUID_ANALYZER && lc::pfb::fused_pfbch2_supported(M, L)) {
+        // the fused kernel folds the 1/M output scale into the taps (exact: M is a power of two)
+        std::vector<float> ts(taps);
+        for (float &v : ts) v *= 1.0f / (float)M;
+        LC_CUDA_CHECK(cudaMalloc(&q->d_taps_scaled, ts.size() * sizeof(float)));
+        LC_CUDA_CHECK(cudaMemcpy(q->d_taps_scaled, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice));
+        std::vector<float2> tw;
+        lc::pfb::fused_pfbch2_make_twiddles(tw);
+        LC_CUDA_CHECK(cudaMalloc(&q->d_tw_fused, tw.size() * sizeof(float2)));
+        LC_CUDA_CHECK(cudaMemcpy(q->d_tw_fused, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        q->fused = true;
+    }
     LC_CUDA_CHECK(cudaMalloc(&q->d_hist, sizeof(float2) * q->H));
     q->fft.init(M, +1);                            // backward, unscaled (firpfbch2.c:115)
     LC_CUDA_CHECK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
@@ -132,6 +157,8 @@ void firpfbch2_crcf_destroy(firpfbch2_crcf _q)
     if (!_q) return;
     cudaStreamSynchronize(_q->stream);
     cudaFree(_q->d_taps);
+    cudaFree(_q->d_taps_scaled);
+    cudaFree(_q->d_tw_fused);
     cudaFree(_q->d_hist);
     _q->fft.destroy();
     _q->scratch.release();

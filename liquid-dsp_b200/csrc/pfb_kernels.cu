@@ -13,13 +13,13 @@ constexpr int kThreads = 256;
 __global__ void __launch_bounds__(kThreads)
 pfbch2_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
                   const float *__restrict__ taps, float2 *__restrict__ X, unsigned int M, unsigned int L,
-                  unsigned long long n_frames, int parity0)
+                  unsigned long long n_frames, int parity0, long long t_first)
 {
     const unsigned int M2 = M >> 1;
     const unsigned long long total = n_frames * M;
     for (unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
          gid += (unsigned long long)gridDim.x * blockDim.x) {
-        const long long t = (long long)(gid / M);
+        const long long t = t_first + (long long)(gid / M);     // frame index relative to x[0]
         const unsigned int w = (unsigned int)(gid % M);
         const int par = (parity0 + (int)(t & 1)) & 1;
         const bool lower = w < M2;                      // lower half is pushed on even frames
@@ -131,9 +131,10 @@ namespace lc {
 namespace pfb {
 
 void launch_pfbch2_mac(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, float2 *d_X,
-                       unsigned int M, unsigned int L, unsigned long long n_frames, int parity0, cudaStream_t st)
+                       unsigned int M, unsigned int L, unsigned long long n_frames, int parity0, cudaStream_t st,
+                       long long t_first)
 {
-    pfbch2_mac_kernel<<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, L, n_frames, parity0);
+    pfbch2_mac_kernel<<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, L, n_frames, parity0, t_first);
     LC_LAUNCH_CHECK();
 }
 

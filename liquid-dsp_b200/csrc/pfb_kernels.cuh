@@ -5,9 +5,11 @@
 namespace lc {
 namespace pfb {
 
-// firpfbch2 analysis MAC: X[t][w] = sum_n taps[par(t)][n][w] * (n-th newest sample of window w at frame t)
+// firpfbch2 analysis MAC: X[t][w] = sum_n taps[par(t)][n][w] * (n-th newest sample of window w at frame
+// t_first + t); parity0 is the parity of frame 0 (the frame that starts at x[0]); d_X points at row t_first
 void launch_pfbch2_mac(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, float2 *d_X,
-                       unsigned int M, unsigned int L, unsigned long long n_frames, int parity0, cudaStream_t st);
+                       unsigned int M, unsigned int L, unsigned long long n_frames, int parity0, cudaStream_t st,
+                       long long t_first = 0);
 
 // firpfbch2 synthesis FIR over scaled-IDFT rows v: y[t][i] = sum_q taps[q][i] * v[t-q][i + (par(t) ? M/2 : 0)]
 void launch_pfbch2_synth_fir(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float *d_taps,

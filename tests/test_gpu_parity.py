@@ -370,3 +370,36 @@ def test_synth_input_dev_matches_host_generator(L, orc):
     L.lib.liquid_cuda_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d, n * 8)
     L.lib.liquid_cuda_free(d)
     assert np.array_equal(got, orc.synth_input(n, seed=0x5EED0000 + 3, first=12345))
+
+
+# ------------------------------------------------------------------ fused M=1024 kernel specifics
+@pytest.mark.parametrize("m", [2, 4, 5, 7])
+def test_pfbch2_fused_1024_vs_oracle_odd_splits(L, orc, m):
+    """the fused kernel (M=1024) across: odd start parity, frame counts that are not a multiple of
+    the 4-frame group, several CTAs, state carried between calls"""
+    M = 1024
+    nfr = 33 + 100 + 515
+    x = orc.synth_input(nfr * M // 2, seed=0xF0 + m)
+    want = orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0).execute_frames(x)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    got = np.concatenate([q.execute_block(x[:33 * 512]), q.execute_block(x[33 * 512:133 * 512]),
+                          q.execute_block(x[133 * 512:])])
+    check_channels(got, want, x)
+    # one call over everything gives the same stream
+    q.reset()
+    whole = q.execute_block(x)
+    check_channels(whole, want, x)
+    assert np.abs(whole - got).max() < 1e-6
+
+
+def test_pfbch2_fused_matches_generic_path(L, orc, monkeypatch):
+    M, m = 1024, 7
+    x = orc.synth_input(3000 * M // 2, seed=0xFE)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    fused = q.execute_block(x)
+    q.reset()
+    monkeypatch.setenv("LIQUID_CUDA_NO_FUSED", "1")
+    generic = q.execute_block(x)
+    monkeypatch.delenv("LIQUID_CUDA_NO_FUSED")
+    assert rel_rms_per_channel(fused, generic).max() < 2e-6
+    assert np.abs(fused - generic).max() < 1e-6
