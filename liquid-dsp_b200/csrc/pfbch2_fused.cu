@@ -3,13 +3,17 @@
 // One persistent CTA per SM walks a contiguous range of frames.  Warp-specialised, producer /
 // consumer through shared memory with mbarriers (no CTA-wide barrier in the steady state):
 //
+//   input                        one lane of the first FFT warp streams the input with cp.async.bulk
+//                                (TMA engine): one 16 KB copy per group of 4 frames, four groups
+//                                ahead, into a 4-stage ring; completion is counted in bytes on an
+//                                mbarrier.  A stage is refilled once every MAC warp has published the
+//                                group that read it, so no second barrier is needed.
 //   16 MAC warps (512 threads)   thread j owns the window pair (j, j+512): two 2m-sample complex
 //                                histories and the two 2m-tap branches live in registers (6*2m
-//                                registers).  Per frame: one new sample (its own, read once from
-//                                HBM through a per-warp cp.async.bulk ring), two dot products
-//                                (8m FFMA), two 8-byte stores into the frame's slot of the X ring.
-//                                The 2m-slot circular histories are addressed statically by fully
-//                                unrolling one period (4m frames).
+//                                registers).  Per frame: one new sample (its own 8 bytes of the
+//                                staged frame), two dot products (8m FFMA), two 8-byte stores into
+//                                the frame's slot of the X ring.  The 2m-slot circular histories are
+//                                addressed statically by fully unrolling one period (4m frames).
 //    4 FFT warps (128 threads)   warp f transforms frame 4g+f of group g: 1024 = 32 x 32, thread =
 //                                32 points in registers, radix-2 DIT butterflies with constant
 //                                twiddles, one in-place transposition through the slot (padded
@@ -37,15 +41,15 @@ constexpr int kThreads = kMacThreads + 32 * kFftWarps;        // 640
 constexpr int kGroup = 4;                                      // frames per group (one per FFT warp)
 constexpr int kRingGroups = 4;                                 // X ring depth, in groups (power of two)
 constexpr int kSlotStride = 32 * 33;                           // float2 per frame slot (padded transpose)
-constexpr int kInStages = 4;                                   // per-warp input ring depth, in groups (= kRingGroups)
-constexpr int kInStageBytes = kGroup * 32 * 8;                 // 4 frames x 32 samples x 8 B per warp
+constexpr int kInStages = 4;                                   // input ring depth, in groups (= kRingGroups)
+constexpr int kInStageBytes = kGroup * kM2 * 8;                // 4 frames x 512 samples x 8 B = 16 KB
 
 // shared memory carve-up (bytes)
 constexpr int kOffTw = 0;                                      // float2 tw[32][32]
 constexpr int kOffX = kOffTw + 32 * 32 * 8;                    // X ring
 constexpr int kOffIn = kOffX + kRingGroups * kGroup * kSlotStride * 8;
-constexpr int kOffBar = kOffIn + kMacWarps * kInStages * kInStageBytes;
-constexpr int kNumBars = 2 * kRingGroups + kMacWarps * kInStages;
+constexpr int kOffBar = kOffIn + kInStages * kInStageBytes;
+constexpr int kNumBars = 2 * kRingGroups + kInStages;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8;
 
 // ---------------------------------------------------------------------------------- PTX helpers
@@ -186,33 +190,37 @@ struct FusedArgs {
     const float2 *tw;          // [32][32] inter-stage twiddles e^{+j 2 pi k1 n2 / 1024}
     int H;
     int par0;                  // parity of the segment's first frame
-    int n_groups;              // groups of 4 frames in the segment
-    int groups_per_cta;
+    int n_periods;             // periods (L/2 groups = 2L frames) in the segment
+    int periods_per_cta;
 };
+
+// unit (float2) offset of transform input n inside a frame slot: rows of 32 padded to 33
+__device__ __forceinline__ constexpr int slot_unit(int n) { return n + (n >> 5); }
 
 template <int L>
 __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const FusedArgs a)
 {
+    constexpr int P = L / 2;                               // groups per period
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_tw = s_base + kOffTw;
     const uint32_t s_x = s_base + kOffX;
     const uint32_t s_in = s_base + kOffIn;
     const uint32_t s_bar = s_base + kOffBar;
-    // barriers: full[g] at s_bar + 8g, empty[g] at s_bar + 8(R+g), in[w][s] after those
+    // barriers: X ring full[g] / empty[g], input ring in_full[s]
     auto bar_full = [&](int g) { return s_bar + 8u * g; };
     auto bar_empty = [&](int g) { return s_bar + 8u * (kRingGroups + g); };
-    auto bar_in = [&](int w, int s) { return s_bar + 8u * (2 * kRingGroups + w * kInStages + s); };
+    auto bar_in_full = [&](int s) { return s_bar + 8u * (2 * kRingGroups + s); };
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
-    const int g_begin = (int)blockIdx.x * a.groups_per_cta;
-    int g_end = g_begin + a.groups_per_cta;
-    if (g_end > a.n_groups) g_end = a.n_groups;
-    const int n_groups = g_end - g_begin;                  // > 0 by construction of the grid
-    const long long f_begin = (long long)g_begin * kGroup; // first frame of this CTA (even)
+    const int p_begin = (int)blockIdx.x * a.periods_per_cta;
+    int p_end = p_begin + a.periods_per_cta;
+    if (p_end > a.n_periods) p_end = a.n_periods;
+    const int n_periods = p_end - p_begin;                 // > 0 by construction of the grid
+    const long long f_begin = (long long)p_begin * (P * kGroup);   // first frame of this CTA (even)
 
     // ---- one-time setup
     {
@@ -224,20 +232,20 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
             mbar_init(bar_full(g), kMacWarps);
             mbar_init(bar_empty(g), kFftWarps);
         }
-        for (int w = 0; w < kMacWarps; w++)
-            for (int s = 0; s < kInStages; s++) mbar_init(bar_in(w, s), 1);
+        for (int s = 0; s < kInStages; s++) mbar_init(bar_in_full(s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp < kMacWarps) {
         // =========================================================================== MAC warps
-        // (no setmaxnreg: registers can only move between warpgroups of one CTA, and 640 x 96 is the launch allocation)
         const int j = tid;                                  // window pair (j, j + 512)
-        // byte offset, inside a frame slot, of this thread's first dot product (window j or j+512
-        // depending on the parity of the segment); the second one sits 512 windows away
-        const uint32_t w1off = (uint32_t)(j + (a.par0 ? kM2 : 0)) * 8;
-        const uint32_t w2delta = a.par0 ? (uint32_t)(-kM2 * 8) : (uint32_t)(kM2 * 8);   // warp-uniform
+        // this thread's first dot product belongs to window j (segment starts on an even frame) or
+        // j + 512 (odd); the second one to the other.  Byte offsets inside a frame slot:
+        const uint32_t x_thr = s_x + (uint32_t)(slot_unit(j) + (a.par0 ? slot_unit(kM2) : 0)) * 8;
+        const uint32_t w2delta = a.par0 ? (uint32_t)(-slot_unit(kM2) * 8) : (uint32_t)(slot_unit(kM2) * 8);
+        // this thread's sample inside a staged frame
+        const uint32_t in_thr = s_in + (uint32_t)(kM2 - 1 - j) * 8;
 
         float hA[L], hB[L];                                 // branch j, branch j + 512 (tap n = n-th newest)
         float2 dA[L], dB[L];                                // circular histories of the two windows
@@ -258,48 +266,24 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                 dB[L - 1 - n] = lcd::ld_stream(a.hist, a.x, base - (1LL + 2 * n) * kM2, a.H);
         }
 
-        // per-warp input ring: stage s holds this warp's 32 samples of the 4 frames of one group
-        const uint32_t in_warp = s_in + (uint32_t)warp * (kInStages * kInStageBytes);
-        auto issue_group = [&](int g) {                     // lane 0 only
-            const int s = g & (kInStages - 1);
-            const uint32_t bar = bar_in(warp, s);
-            // frame (f_begin + 4g + f), this warp: 32 samples starting at 512 - 32 (warp + 1)
-            const float2 *src = a.x + (f_begin + (long long)g * kGroup) * kM2 + (kM2 - 32 * (warp + 1));
-            mbar_arrive_expect_tx(bar, kInStageBytes);
-#pragma unroll
-            for (int f = 0; f < kGroup; f++)
-                bulk_g2s(in_warp + s * kInStageBytes + f * 256, src + f * kM2, 256, bar);
-        };
-        if (lane == 0) {
-            for (int g = 0; g < kInStages - 1 && g < n_groups; g++) issue_group(g);
-        }
-        const uint32_t in_lane = in_warp + (uint32_t)(31 - lane) * 8;
-        const uint32_t bar_in_w = bar_in(warp, 0);
-
-        int g = 0;
-        while (g < n_groups) {
-            // one period: L updates of each window = 2L frames = L/2 groups, fully unrolled
+        for (int p = 0; p < n_periods; p++) {
+            // one period: L updates of each window = 2L frames = L/2 groups, fully unrolled so that
+            // every history slot index below is a compile-time constant
 #pragma unroll
             for (int uu = 0; uu < L; uu++) {
-                const int fg = (uu & 1) * 2;                // frame-in-group of this double frame's even frame
+                const int g = p * P + (uu >> 1);            // group index inside this CTA
                 const int gq = g & (kRingGroups - 1);       // stage of both rings (same depth)
+                const int fg = (uu & 1) * 2;                // frame-in-group of this pair's even frame
                 if ((uu & 1) == 0) {
-                    if (g >= n_groups) break;
-                    // keep the input ring full: fetch group g + kInStages - 1 into the stage read last group
-                    __syncwarp();
-                    if (lane == 0 && g + kInStages - 1 < n_groups) {
-                        fence_proxy_async();
-                        issue_group(g + kInStages - 1);
-                    }
                     const uint32_t par = (uint32_t)(g >> 2) & 1u;
-                    mbar_wait(bar_in_w + 8u * gq, par);
-                    mbar_wait(bar_empty(gq), par ^ 1u);
+                    mbar_wait(bar_in_full(gq), par);          // the group's 16 KB of input have landed
+                    mbar_wait(bar_empty(gq), par ^ 1u);       // the FFT warps are done with this X slot
                 }
-                const uint32_t in_g = in_lane + (uint32_t)gq * kInStageBytes;
-                const uint32_t x_g = s_x + (uint32_t)gq * (kGroup * kSlotStride * 8) + w1off;
+                const uint32_t in_g = in_thr + (uint32_t)gq * kInStageBytes;
+                const uint32_t x_g = x_thr + (uint32_t)gq * (kGroup * kSlotStride * 8);
 
                 // ---- even frame of the pair: window 1 gets the new sample
-                dA[uu] = lds64(in_g + fg * 256);
+                dA[uu] = lds64(in_g + fg * (kM2 * 8));
                 {
                     float2 o1 = make_float2(0.f, 0.f), o2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -316,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                     sts64(slot + w2delta, o2);
                 }
                 // ---- odd frame of the pair: window 2 gets the new sample, branches swap
-                dB[uu] = lds64(in_g + (fg + 1) * 256);
+                dB[uu] = lds64(in_g + (fg + 1) * (kM2 * 8));
                 {
                     float2 o1 = make_float2(0.f, 0.f), o2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -333,36 +317,61 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                     sts64(slot + w2delta, o2);
                 }
                 if (uu & 1) {
-                    // group complete: publish it to the FFT warps
+                    // group complete: publish it to the FFT warps (this also hands the input stage back:
+                    // the producer refills stage gq only after full[gq] of this group has completed)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_full(gq));
-                    g++;
                 }
             }
         }
     } else {
         // =========================================================================== FFT warps
         const int fw = warp - kMacWarps;                    // frame-in-group handled by this warp
+        const int n_groups = n_periods * P;
         const uint32_t tw_lane = s_tw + (uint32_t)lane * 8; // tw[k1][lane] at + k1*256
+        const bool producer = (fw == 0 && lane == 0);       // streams the input, 4 groups ahead
+        auto fetch_group = [&](int gg) {
+            // 4 consecutive frames are contiguous in the stream: one 16 KB bulk copy
+            const int st = gg & (kInStages - 1);
+            const float2 *src = a.x + (f_begin + (long long)gg * kGroup) * kM2;
+            mbar_arrive_expect_tx(bar_in_full(st), kInStageBytes);
+            bulk_g2s(s_in + (uint32_t)st * kInStageBytes, src, kInStageBytes, bar_in_full(st));
+        };
+        if (producer) {
+            for (int gg = 0; gg < kInStages && gg < n_groups; gg++) fetch_group(gg);
+        }
         for (int g = 0; g < n_groups; g++) {
             const int gs = g & (kRingGroups - 1);
             mbar_wait(bar_full(gs), (uint32_t)(g >> 2) & 1u);
-            const uint32_t slot = s_x + (uint32_t)(gs * kGroup + fw) * (kSlotStride * 8);
+            // every MAC warp has finished group g, so input stage gs is free again
+            if (producer && g + kInStages < n_groups) fetch_group(g + kInStages);
+            const uint32_t slot = s_x + (uint32_t)(gs * kGroup + fw) * (kSlotStride * 8) + (uint32_t)lane * 8;
 
             float2 v[32];
-            // pass 1: lane = n2, points X[32 n1 + n2]; 32-point DFT over n1; twiddle W^(n2 k1)
+            // pass 1: lane = n2, points X[32 n1 + n2] (row n1 of the padded slot); DFT over n1
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) v[n1] = lds64(slot + (uint32_t)(32 * n1 + lane) * 8);
+            for (int n1 = 0; n1 < 32; n1++) v[n1] = lds64(slot + (uint32_t)(n1 * 33) * 8);
             RegDft<32, +1>::run(v);
-#pragma unroll
-            for (int k1 = 1; k1 < 32; k1++) v[k1] = lcd::cmul(v[k1], lds64(tw_lane + k1 * 256));
             __syncwarp();                                   // every lane has read its column
+            // twiddle W^(n2 k1), then store transposed: row n2 = lane, column k1
+            const uint32_t row = slot + (uint32_t)lane * (32 * 8);      // = slot base + lane*33*8
 #pragma unroll
-            for (int k1 = 0; k1 < 32; k1++) sts64(slot + (uint32_t)(k1 * 33 + lane) * 8, v[k1]);
+            for (int b = 0; b < 4; b++) {
+                float2 t[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (8 * b + i) t[i] = lds64(tw_lane + (8 * b + i) * 256);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int k1 = 8 * b + i;
+                    if (k1) v[k1] = lcd::cmul(v[k1], t[i]);
+                    sts64(row + (uint32_t)k1 * 8, v[k1]);
+                }
+            }
             __syncwarp();
-            // pass 2: lane = k1, points A[k1][n2]; 32-point DFT over n2 -> Y[k1 + 32 k2]
+            // pass 2: lane = k1, points A[k1][n2] (row n2, column k1): same addresses as pass 1
 #pragma unroll
-            for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(slot + (uint32_t)(lane * 33 + n2) * 8);
+            for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(slot + (uint32_t)(n2 * 33) * 8);
             RegDft<32, +1>::run(v);
             // the slot has been consumed (the DFT above needed every loaded value)
             __syncwarp();
@@ -411,17 +420,19 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
                               unsigned long long n_frames, int parity0, cudaStream_t st)
 {
     (void)M;
-    long long n_groups = (long long)(n_frames / kGroup);
-    if (n_groups == 0) return 0;
-    if (n_groups > (1ll << 30)) n_groups = 1ll << 30;      // the caller loops for the rest
+    const long long frames_per_period = 2ll * L;           // L/2 groups of 4 frames
+    long long n_periods = (long long)(n_frames / frames_per_period);
+    if (n_periods == 0) return 0;
+    if (n_periods > (1ll << 28)) n_periods = 1ll << 28;    // the caller finishes the rest
     int dev = 0, sms = 148;
     LC_CUDA_CHECK(cudaGetDevice(&dev));
     LC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    // at least 8 groups per CTA so the history prologue and the pipeline fill amortise
-    long long ctas = (n_groups + 7) / 8;
+    // at least ~32 frames per CTA so the history prologue and the pipeline fill amortise
+    const long long min_pp = (32 + frames_per_period - 1) / frames_per_period;
+    long long ctas = (n_periods + min_pp - 1) / min_pp;
     if (ctas > sms) ctas = sms;
-    long long per = (n_groups + ctas - 1) / ctas;
-    ctas = (n_groups + per - 1) / per;
+    long long per = (n_periods + ctas - 1) / ctas;
+    ctas = (n_periods + per - 1) / per;
     FusedArgs a;
     a.hist = d_hist;
     a.x = d_x;
@@ -430,8 +441,8 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
     a.tw = d_tw;
     a.H = H;
     a.par0 = parity0 & 1;
-    a.n_groups = (int)n_groups;
-    a.groups_per_cta = (int)per;
+    a.n_periods = (int)n_periods;
+    a.periods_per_cta = (int)per;
     switch (L) {
     case 4: launch_L<4>(a, (unsigned int)ctas, st); break;
     case 8: launch_L<8>(a, (unsigned int)ctas, st); break;
@@ -439,7 +450,7 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
     case 14: launch_L<14>(a, (unsigned int)ctas, st); break;
     default: fatal("launch_pfbch2_fused", "unsupported tap count");
     }
-    return n_groups * kGroup;
+    return n_periods * frames_per_period;
 }
 
 }  // namespace pfb
