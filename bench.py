@@ -280,8 +280,8 @@ def main():
     kernels_per_step = launches / max(args.steps, 1)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "kernel": "firpfbch2 analysis (%.0f launch(es) per step: %s)" % (
-                    kernels_per_step, "pfbch2_mac_kernel + fft_pow2_kernel" if kernels_per_step >= 2 else "fused"),
+                "kernel": "pfbch2_fused_1024_kernel<14> (fused polyphase MAC + 1024-point IFFT), "
+                          "%.0f launch(es) per step" % kernels_per_step,
                 "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n,
                 "avg_launch_ms": avg_step_ms, "frac_of_8TBps_nominal": achieved / 8000.0}
 

@@ -190,8 +190,8 @@ struct FusedArgs {
     const float2 *tw;          // [32][32] inter-stage twiddles e^{+j 2 pi k1 n2 / 1024}
     int H;
     int par0;                  // parity of the segment's first frame
-    int n_periods;             // periods (L/2 groups = 2L frames) in the segment
-    int periods_per_cta;
+    int n_groups;              // groups of 4 frames in the segment
+    int groups_per_cta;
 };
 
 // unit (float2) offset of transform input n inside a frame slot: rows of 32 padded to 33
@@ -216,11 +216,11 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
-    const int p_begin = (int)blockIdx.x * a.periods_per_cta;
-    int p_end = p_begin + a.periods_per_cta;
-    if (p_end > a.n_periods) p_end = a.n_periods;
-    const int n_periods = p_end - p_begin;                 // > 0 by construction of the grid
-    const long long f_begin = (long long)p_begin * (P * kGroup);   // first frame of this CTA (even)
+    const int g_begin = (int)blockIdx.x * a.groups_per_cta;
+    int g_end = g_begin + a.groups_per_cta;
+    if (g_end > a.n_groups) g_end = a.n_groups;
+    const int n_groups = g_end - g_begin;                  // > 0 by construction of the grid
+    const long long f_begin = (long long)g_begin * kGroup; // first frame of this CTA (even)
 
     // ---- one-time setup
     {
@@ -266,12 +266,14 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                 dB[L - 1 - n] = lcd::ld_stream(a.hist, a.x, base - (1LL + 2 * n) * kM2, a.H);
         }
 
+        const int n_periods = (n_groups + P - 1) / P;      // the last one may be partial
         for (int p = 0; p < n_periods; p++) {
             // one period: L updates of each window = 2L frames = L/2 groups, fully unrolled so that
             // every history slot index below is a compile-time constant
 #pragma unroll
             for (int uu = 0; uu < L; uu++) {
                 const int g = p * P + (uu >> 1);            // group index inside this CTA
+                if (g >= n_groups) continue;                // warp-uniform: tail of the last period
                 const int gq = g & (kRingGroups - 1);       // stage of both rings (same depth)
                 const int fg = (uu & 1) * 2;                // frame-in-group of this pair's even frame
                 if ((uu & 1) == 0) {
@@ -327,7 +329,6 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
     } else {
         // =========================================================================== FFT warps
         const int fw = warp - kMacWarps;                    // frame-in-group handled by this warp
-        const int n_groups = n_periods * P;
         const uint32_t tw_lane = s_tw + (uint32_t)lane * 8; // tw[k1][lane] at + k1*256
         const bool producer = (fw == 0 && lane == 0);       // streams the input, 4 groups ahead
         auto fetch_group = [&](int gg) {
@@ -420,19 +421,17 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
                               unsigned long long n_frames, int parity0, cudaStream_t st)
 {
     (void)M;
-    const long long frames_per_period = 2ll * L;           // L/2 groups of 4 frames
-    long long n_periods = (long long)(n_frames / frames_per_period);
-    if (n_periods == 0) return 0;
-    if (n_periods > (1ll << 28)) n_periods = 1ll << 28;    // the caller finishes the rest
+    long long n_groups = (long long)(n_frames / kGroup);
+    if (n_groups == 0) return 0;
+    if (n_groups > (1ll << 30)) n_groups = 1ll << 30;      // the caller finishes the rest
     int dev = 0, sms = 148;
     LC_CUDA_CHECK(cudaGetDevice(&dev));
     LC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    // at least ~32 frames per CTA so the history prologue and the pipeline fill amortise
-    const long long min_pp = (32 + frames_per_period - 1) / frames_per_period;
-    long long ctas = (n_periods + min_pp - 1) / min_pp;
+    // at least 8 groups (32 frames) per CTA so the history prologue and the pipeline fill amortise
+    long long ctas = (n_groups + 7) / 8;
     if (ctas > sms) ctas = sms;
-    long long per = (n_periods + ctas - 1) / ctas;
-    ctas = (n_periods + per - 1) / per;
+    long long per = (n_groups + ctas - 1) / ctas;
+    ctas = (n_groups + per - 1) / per;
     FusedArgs a;
     a.hist = d_hist;
     a.x = d_x;
@@ -441,8 +440,8 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
     a.tw = d_tw;
     a.H = H;
     a.par0 = parity0 & 1;
-    a.n_periods = (int)n_periods;
-    a.periods_per_cta = (int)per;
+    a.n_groups = (int)n_groups;
+    a.groups_per_cta = (int)per;
     switch (L) {
     case 4: launch_L<4>(a, (unsigned int)ctas, st); break;
     case 8: launch_L<8>(a, (unsigned int)ctas, st); break;
@@ -450,7 +449,7 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
     case 14: launch_L<14>(a, (unsigned int)ctas, st); break;
     default: fatal("launch_pfbch2_fused", "unsupported tap count");
     }
-    return n_periods * frames_per_period;
+    return n_groups * kGroup;
 }
 
 }  // namespace pfb
