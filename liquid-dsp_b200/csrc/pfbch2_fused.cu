@@ -11,12 +11,14 @@
 //   16 MAC warps (512 threads)   thread j owns the window pair (j, j+512): two 2m-sample complex
 //                                histories and the two 2m-tap branches live in registers (6*2m
 //                                registers).  Per frame: one new sample (its own 8 bytes of the
-//                                staged frame), two dot products (8m FFMA), two 8-byte stores into
+//                                staged frame), two dot products (4m packed FFMA2: tap broadcast x
+//                                {re, im} pair), two 8-byte stores into
 //                                the frame's slot of the X ring.  The 2m-slot circular histories are
 //                                addressed statically by fully unrolling one period (4m frames).
 //    4 FFT warps (128 threads)   warp f transforms frame 4g+f of group g: 1024 = 32 x 32, thread =
 //                                32 points in registers, radix-2 DIT butterflies with constant
-//                                twiddles, one in-place transposition through the slot (padded
+//                                twiddles in packed FP32x2 arithmetic (3 instructions per general
+//                                butterfly), one in-place transposition through the slot (padded
 //                                stride 33), inter-stage twiddles from a shared 32x32 table, then
 //                                32 coalesced 256-byte row stores per frame straight to HBM.
 //
@@ -138,6 +140,20 @@ __device__ constexpr float kSin32[16] = {0.0f,
                                          0.38268343236508977173f,
                                          0.19509032201612826785f};
 
+// packed FP32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): one instruction works on a {re, im} register
+// pair; ptxas folds make_float2(t, t) into a scalar-broadcast operand and make_float2(-a.y, a.x) into a
+// swapped, half-negated operand, so none of these cost extra moves.  The FMA pipe spends two cycles on
+// a packed instruction (same flop rate as two scalar ones) but it takes a single issue slot.
+__device__ __forceinline__ float2 bc(float t) { return make_float2(t, t); }
+__device__ __forceinline__ float2 rot90(float2 a) { return make_float2(-a.y, a.x); }      //  j * a
+__device__ __forceinline__ float2 rot270(float2 a) { return make_float2(a.y, -a.x); }     // -j * a
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+// complex product a * t
+__device__ __forceinline__ float2 cmul2(float2 a, float2 t)
+{
+    return __ffma2_rn(bc(t.y), rot90(a), __fmul2_rn(bc(t.x), a));
+}
+
 // N-point DFT of v[] in registers, natural order in and out, e^{SIGN j 2 pi nk/N}.
 // Decimation in time; every index is a compile-time constant, so the even/odd split is renaming.
 template <int N, int SIGN>
@@ -154,24 +170,21 @@ struct RegDft {
         RegDft<N / 2, SIGN>::run(o);
 #pragma unroll
         for (int k = 0; k < N / 2; k++) {
-            constexpr float s = (float)SIGN;
             if (k == 0) {
-                v[k] = make_float2(e[k].x + o[k].x, e[k].y + o[k].y);
-                v[k + N / 2] = make_float2(e[k].x - o[k].x, e[k].y - o[k].y);
+                v[k] = __fadd2_rn(e[k], o[k]);
+                v[k + N / 2] = __fadd2_rn(e[k], neg2(o[k]));
             } else if (4 * k == N) {
                 // w = SIGN * j
-                v[k] = make_float2(e[k].x - s * o[k].y, e[k].y + s * o[k].x);
-                v[k + N / 2] = make_float2(e[k].x + s * o[k].y, e[k].y - s * o[k].x);
+                const float2 r = (SIGN > 0) ? rot90(o[k]) : rot270(o[k]);
+                v[k] = __fadd2_rn(e[k], r);
+                v[k + N / 2] = __fadd2_rn(e[k], neg2(r));
             } else {
                 const float c = kCos32[k * (32 / N)];
-                const float sn = s * kSin32[k * (32 / N)];
-                // a + w b with two FMAs per component; a - w b = 2a - (a + w b)
-                float re = fmaf(c, o[k].x, e[k].x);
-                re = fmaf(-sn, o[k].y, re);
-                float im = fmaf(c, o[k].y, e[k].y);
-                im = fmaf(sn, o[k].x, im);
-                v[k] = make_float2(re, im);
-                v[k + N / 2] = make_float2(fmaf(2.0f, e[k].x, -re), fmaf(2.0f, e[k].y, -im));
+                const float sn = (float)SIGN * kSin32[k * (32 / N)];
+                // a + w b = a + c b + sn (j b) in two packed FMAs; a - w b = 2a - (a + w b) in one
+                const float2 t = __ffma2_rn(bc(c), o[k], e[k]);
+                v[k] = __ffma2_rn(bc(sn), rot90(o[k]), t);
+                v[k + N / 2] = __ffma2_rn(bc(2.0f), e[k], neg2(v[k]));
             }
         }
     }
@@ -292,10 +305,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                     for (int n = L - 1; n >= 0; n--) {
                         const float2 s1 = dA[(uu - n + L) % L];
                         const float2 s2 = dB[(uu - 1 - n + 2 * L) % L];
-                        o1.x = fmaf(hA[n], s1.x, o1.x);
-                        o1.y = fmaf(hA[n], s1.y, o1.y);
-                        o2.x = fmaf(hB[n], s2.x, o2.x);
-                        o2.y = fmaf(hB[n], s2.y, o2.y);
+                        o1 = __ffma2_rn(bc(hA[n]), s1, o1);
+                        o2 = __ffma2_rn(bc(hB[n]), s2, o2);
                     }
                     const uint32_t slot = x_g + (uint32_t)fg * (kSlotStride * 8);
                     sts64(slot, o1);
@@ -309,10 +320,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                     for (int n = L - 1; n >= 0; n--) {
                         const float2 s1 = dA[(uu - n + L) % L];
                         const float2 s2 = dB[(uu - n + L) % L];
-                        o1.x = fmaf(hB[n], s1.x, o1.x);
-                        o1.y = fmaf(hB[n], s1.y, o1.y);
-                        o2.x = fmaf(hA[n], s2.x, o2.x);
-                        o2.y = fmaf(hA[n], s2.y, o2.y);
+                        o1 = __ffma2_rn(bc(hB[n]), s1, o1);
+                        o2 = __ffma2_rn(bc(hA[n]), s2, o2);
                     }
                     const uint32_t slot = x_g + (uint32_t)(fg + 1) * (kSlotStride * 8);
                     sts64(slot, o1);
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int k1 = 8 * b + i;
-                    if (k1) v[k1] = lcd::cmul(v[k1], t[i]);
+                    if (k1) v[k1] = cmul2(v[k1], t[i]);
                     sts64(row + (uint32_t)k1 * 8, v[k1]);
                 }
             }
