@@ -184,6 +184,7 @@ def main():
     import torch
     import torch.distributed as dist
     import liquid_dsp_b200 as L
+    import liquid_dsp_b200.multi as multi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,11 +223,7 @@ def main():
 
     def step():
         if world > 1:
-            reqs = []
-            if rank + 1 < world:
-                reqs.append(dist.isend(tail, rank + 1))
-            if rank > 0:
-                reqs.append(dist.irecv(head, rank - 1))
+            reqs = multi.exchange_halo(dist, head, tail, rank, world)      # NCCL send/recv of 2mM samples
             # interior frames do not see the halo: run them while it is in flight
             q.execute_segment_dev(d_x + 8 * (halo_frames * (M // 2)) - 8 * H, d_x + 8 * halo_frames * (M // 2),
                                   first_frame + halo_frames, n_frames - halo_frames,
