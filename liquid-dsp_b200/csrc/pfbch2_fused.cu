@@ -1,26 +1,31 @@
 // pfbch2_fused.cu -- fused firpfbch2_crcf analysis kernel for M = 1024 (sm_100a).
 //
-// One persistent CTA per SM walks a contiguous range of frames.  Warp-specialised, producer /
-// consumer through shared memory with mbarriers (no CTA-wide barrier in the steady state):
+// One persistent CTA per SM (512 threads) walks a contiguous range of frames.  Warp-specialised,
+// producer / consumer through shared memory with mbarriers (no CTA-wide barrier in steady state);
+// registers are moved between the roles with setmaxnreg (launch 128/thread -> MAC 192, FFT 64):
 //
+//    8 MAC warps (256 threads)   thread j owns the four windows j, j+256, j+512, j+768, i.e. the window
+//                                pairs (j, j+512) and (j+256, j+768): per pair two 2m-sample complex
+//                                histories and the two 2m-tap branches live in registers (12*2m
+//                                registers).  Per frame: two new samples (its own 16 bytes of the
+//                                staged frame), four dot products (8m packed FFMA2: tap broadcast x
+//                                {re, im} pair).  The four results are exactly the inputs of one
+//                                radix-4 decimation-in-frequency butterfly of the 1024-point IDFT, so
+//                                the thread also does that butterfly and its three twiddles and stores
+//                                the frame as four independent 256-point problems.  The 2m-slot
+//                                circular histories are addressed statically by fully unrolling one
+//                                period (4m frames).
+//    8 FFT warps (256 threads)   two warps per frame, four frames in flight: 256 = 16 x 16, thread =
+//                                16 points in registers, radix-2 DIT butterflies with constant twiddles
+//                                in packed FP32x2 arithmetic (3 instructions per general butterfly), one
+//                                transposition through the frame slot (rows of 16 padded to 17), inter-
+//                                pass twiddles from a shared 16x16 table, then 16 coalesced 256-byte row
+//                                stores per thread straight to HBM.
 //   input                        one lane of the first FFT warp streams the input with cp.async.bulk
 //                                (TMA engine): one 16 KB copy per group of 4 frames, four groups
 //                                ahead, into a 4-stage ring; completion is counted in bytes on an
 //                                mbarrier.  A stage is refilled once every MAC warp has published the
 //                                group that read it, so no second barrier is needed.
-//   16 MAC warps (512 threads)   thread j owns the window pair (j, j+512): two 2m-sample complex
-//                                histories and the two 2m-tap branches live in registers (6*2m
-//                                registers).  Per frame: one new sample (its own 8 bytes of the
-//                                staged frame), two dot products (4m packed FFMA2: tap broadcast x
-//                                {re, im} pair), two 8-byte stores into
-//                                the frame's slot of the X ring.  The 2m-slot circular histories are
-//                                addressed statically by fully unrolling one period (4m frames).
-//    4 FFT warps (128 threads)   warp f transforms frame 4g+f of group g: 1024 = 32 x 32, thread =
-//                                32 points in registers, radix-2 DIT butterflies with constant
-//                                twiddles in packed FP32x2 arithmetic (3 instructions per general
-//                                butterfly), one in-place transposition through the slot (padded
-//                                stride 33), inter-stage twiddles from a shared 32x32 table, then
-//                                32 coalesced 256-byte row stores per frame straight to HBM.
 //
 // FP32 pipe and shared-memory pipe work of the two roles overlap by construction (the warp
 // scheduler interleaves them); per input sample the kernel reads 8 B and writes 16 B of HBM.
@@ -36,19 +41,21 @@ namespace {
 
 constexpr int kM = 1024;
 constexpr int kM2 = 512;
-constexpr int kMacThreads = 512;
-constexpr int kMacWarps = 16;
-constexpr int kFftWarps = 4;
-constexpr int kThreads = kMacThreads + 32 * kFftWarps;        // 640
-constexpr int kGroup = 4;                                      // frames per group (one per FFT warp)
+constexpr int kMacWarps = 8;
+constexpr int kFftWarps = 8;
+constexpr int kMacThreads = 32 * kMacWarps;                    // 256
+constexpr int kThreads = 32 * (kMacWarps + kFftWarps);         // 512
+constexpr int kGroup = 4;                                      // frames per group (two FFT warps each)
 constexpr int kRingGroups = 4;                                 // X ring depth, in groups (power of two)
-constexpr int kSlotStride = 32 * 33;                           // float2 per frame slot (padded transpose)
+constexpr int kSubStride = 276;                                // float2 per 256-point sub-problem: 16 rows of 17 (+4)
+constexpr int kSlotStride = 4 * kSubStride;                    // float2 per frame slot
 constexpr int kInStages = 4;                                   // input ring depth, in groups (= kRingGroups)
 constexpr int kInStageBytes = kGroup * kM2 * 8;                // 4 frames x 512 samples x 8 B = 16 KB
 
 // shared memory carve-up (bytes)
-constexpr int kOffTw = 0;                                      // float2 tw[32][32]
-constexpr int kOffX = kOffTw + 32 * 32 * 8;                    // X ring
+constexpr int kOffTw4 = 0;                                     // float2 tw4[3][256]: W1024^(j p), p = 1..3
+constexpr int kOffTw16 = kOffTw4 + 3 * 256 * 8;                // float2 tw16[16][16]: W256^(k1 r2)
+constexpr int kOffX = kOffTw16 + 16 * 16 * 8;                  // X ring
 constexpr int kOffIn = kOffX + kRingGroups * kGroup * kSlotStride * 8;
 constexpr int kOffBar = kOffIn + kInStages * kInStageBytes;
 constexpr int kNumBars = 2 * kRingGroups + kInStages;
@@ -200,23 +207,78 @@ struct FusedArgs {
     const float2 *x;           // segment input
     float2 *y;                 // [n_frames][1024]
     const float *taps;         // [2][L][1024] as in firpfbch2.cu, pre-scaled by 1/M
-    const float2 *tw;          // [32][32] inter-stage twiddles e^{+j 2 pi k1 n2 / 1024}
+    const float2 *tw;          // tw4[3][256] followed by tw16[16][16]
     int H;
-    int par0;                  // parity of the segment's first frame
     int n_groups;              // groups of 4 frames in the segment
     int groups_per_cta;
 };
 
-// unit (float2) offset of transform input n inside a frame slot: rows of 32 padded to 33
-__device__ __forceinline__ constexpr int slot_unit(int n) { return n + (n >> 5); }
+// unit (float2) offset of element r of a 256-point sub-problem: rows of 16 padded to 17
+__device__ __forceinline__ constexpr int sub_unit(int r) { return r + (r >> 4); }
+
+// MAC state of one window pair (w, w+512): histories and branches, all in registers
+template <int L>
+struct PairState {
+    float hA[L], hB[L];        // taps of branch w and branch w+512 (tap n multiplies the n-th newest sample)
+    float2 dA[L], dB[L];       // circular histories of the window pushed on even / odd local frames
+};
 
 template <int L>
+__device__ __forceinline__ void pair_load(PairState<L> &s, const FusedArgs &a, int w, long long f_begin)
+{
+#pragma unroll
+    for (int n = 0; n < L; n++) {
+        s.hA[n] = __ldg(a.taps + (size_t)n * kM + w);              // parity-0 table: window w -> branch w
+        s.hB[n] = __ldg(a.taps + (size_t)n * kM + w + kM2);        // window w+512 -> branch w+512
+    }
+    // history: the pair's sample of frame F is stream index F*512 + 511 - w
+    const long long base = f_begin * kM2 + (kM2 - 1 - w);
+#pragma unroll
+    for (int n = 1; n < L; n++) s.dA[L - n] = lcd::ld_stream(a.hist, a.x, base - 2LL * n * kM2, a.H);
+    s.dA[0] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int n = 0; n < L; n++) s.dB[L - 1 - n] = lcd::ld_stream(a.hist, a.x, base - (1LL + 2 * n) * kM2, a.H);
+}
+
+// the two dot products of a pair on the even (ODD = 0) or odd (ODD = 1) frame of double frame uu:
+// o1 belongs to the window pushed on even frames, o2 to the one pushed on odd frames
+template <int L, int ODD>
+__device__ __forceinline__ void pair_mac(const PairState<L> &s, int uu, float2 &o1, float2 &o2)
+{
+    o1 = make_float2(0.f, 0.f);
+    o2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int n = L - 1; n >= 0; n--) {
+        const float2 s1 = s.dA[(uu - n + L) % L];
+        const float2 s2 = s.dB[(uu - (ODD ? 0 : 1) - n + 2 * L) % L];
+        o1 = __ffma2_rn(bc(ODD ? s.hB[n] : s.hA[n]), s1, o1);
+        o2 = __ffma2_rn(bc(ODD ? s.hA[n] : s.hB[n]), s2, o2);
+    }
+}
+
+// radix-4 DIF butterfly over the four windows of a thread + the three twiddles, stored as four
+// 256-point sub-problems z_p[j], p = 0..3 (slot = this thread's address inside sub-problem 0)
+__device__ __forceinline__ void radix4_store(uint32_t slot, float2 a0, float2 a1, float2 a2, float2 a3,
+                                             float2 t1, float2 t2, float2 t3)
+{
+    const float2 s02 = __fadd2_rn(a0, a2), d02 = __fadd2_rn(a0, neg2(a2));
+    const float2 s13 = __fadd2_rn(a1, a3), d13 = __fadd2_rn(a1, neg2(a3));
+    const float2 u0 = __fadd2_rn(s02, s13);
+    const float2 u2 = __fadd2_rn(s02, neg2(s13));
+    const float2 u1 = __fadd2_rn(d02, rot90(d13));      // W4 = +j (backward transform)
+    const float2 u3 = __fadd2_rn(d02, rot270(d13));
+    sts64(slot, u0);
+    sts64(slot + 1 * (kSubStride * 8), cmul2(u1, t1));
+    sts64(slot + 2 * (kSubStride * 8), cmul2(u2, t2));
+    sts64(slot + 3 * (kSubStride * 8), cmul2(u3, t3));
+}
+
+template <int L, int PAR0>
 __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const FusedArgs a)
 {
     constexpr int P = L / 2;                               // groups per period
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t s_tw = s_base + kOffTw;
     const uint32_t s_x = s_base + kOffX;
     const uint32_t s_in = s_base + kOffIn;
     const uint32_t s_bar = s_base + kOffBar;
@@ -237,8 +299,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
 
     // ---- one-time setup
     {
-        float2 *tw_s = reinterpret_cast<float2 *>(smem + kOffTw);
-        for (int i = tid; i < 32 * 32; i += kThreads) tw_s[i] = a.tw[i];
+        float2 *tw_s = reinterpret_cast<float2 *>(smem + kOffTw4);
+        for (int i = tid; i < 3 * 256 + 16 * 16; i += kThreads) tw_s[i] = a.tw[i];
     }
     if (tid == 0) {
         for (int g = 0; g < kRingGroups; g++) {
@@ -252,32 +314,15 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
 
     if (warp < kMacWarps) {
         // =========================================================================== MAC warps
-        const int j = tid;                                  // window pair (j, j + 512)
-        // this thread's first dot product belongs to window j (segment starts on an even frame) or
-        // j + 512 (odd); the second one to the other.  Byte offsets inside a frame slot:
-        const uint32_t x_thr = s_x + (uint32_t)(slot_unit(j) + (a.par0 ? slot_unit(kM2) : 0)) * 8;
-        const uint32_t w2delta = a.par0 ? (uint32_t)(-slot_unit(kM2) * 8) : (uint32_t)(slot_unit(kM2) * 8);
-        // this thread's sample inside a staged frame
-        const uint32_t in_thr = s_in + (uint32_t)(kM2 - 1 - j) * 8;
-
-        float hA[L], hB[L];                                 // branch j, branch j + 512 (tap n = n-th newest)
-        float2 dA[L], dB[L];                                // circular histories of the two windows
-#pragma unroll
-        for (int n = 0; n < L; n++) {
-            hA[n] = __ldg(a.taps + (size_t)n * kM + j);                 // parity-0 table, window j -> branch j
-            hB[n] = __ldg(a.taps + (size_t)n * kM + j + kM2);           // window j+512 -> branch j+512
-        }
-        // history: this thread's sample of frame F is stream index F*512 + 511 - j
-        {
-            const long long base = f_begin * kM2 + (kM2 - 1 - j);
-#pragma unroll
-            for (int n = 1; n < L; n++)                     // window 1: frames f_begin - 2n
-                dA[L - n] = lcd::ld_stream(a.hist, a.x, base - 2LL * n * kM2, a.H);
-            dA[0] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int n = 0; n < L; n++)                     // window 2: frames f_begin - 1 - 2n
-                dB[L - 1 - n] = lcd::ld_stream(a.hist, a.x, base - (1LL + 2 * n) * kM2, a.H);
-        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+        const int j = tid;                                  // windows j, j+256, j+512, j+768
+        PairState<L> s0, s1;                                // pairs (j, j+512) and (j+256, j+768)
+        pair_load(s0, a, j, f_begin);
+        pair_load(s1, a, j + 256, f_begin);
+        // this thread's two samples inside a staged frame, its z_0 element inside a frame slot, its twiddles
+        const uint32_t in_thr = s_in + (uint32_t)(kM2 - 1 - j) * 8;       // pair 1 sits 256 samples lower
+        const uint32_t x_thr = s_x + (uint32_t)sub_unit(j) * 8;
+        const uint32_t tw_thr = s_base + kOffTw4 + (uint32_t)j * 8;
 
         const int n_periods = (n_groups + P - 1) / P;      // the last one may be partial
         for (int p = 0; p < n_periods; p++) {
@@ -296,37 +341,27 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                 }
                 const uint32_t in_g = in_thr + (uint32_t)gq * kInStageBytes;
                 const uint32_t x_g = x_thr + (uint32_t)gq * (kGroup * kSlotStride * 8);
+                const float2 t1 = lds64(tw_thr), t2 = lds64(tw_thr + 256 * 8), t3 = lds64(tw_thr + 512 * 8);
+                float2 o1, o2, o3, o4;
 
-                // ---- even frame of the pair: window 1 gets the new sample
-                dA[uu] = lds64(in_g + fg * (kM2 * 8));
-                {
-                    float2 o1 = make_float2(0.f, 0.f), o2 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int n = L - 1; n >= 0; n--) {
-                        const float2 s1 = dA[(uu - n + L) % L];
-                        const float2 s2 = dB[(uu - 1 - n + 2 * L) % L];
-                        o1 = __ffma2_rn(bc(hA[n]), s1, o1);
-                        o2 = __ffma2_rn(bc(hB[n]), s2, o2);
-                    }
-                    const uint32_t slot = x_g + (uint32_t)fg * (kSlotStride * 8);
-                    sts64(slot, o1);
-                    sts64(slot + w2delta, o2);
-                }
-                // ---- odd frame of the pair: window 2 gets the new sample, branches swap
-                dB[uu] = lds64(in_g + (fg + 1) * (kM2 * 8));
-                {
-                    float2 o1 = make_float2(0.f, 0.f), o2 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int n = L - 1; n >= 0; n--) {
-                        const float2 s1 = dA[(uu - n + L) % L];
-                        const float2 s2 = dB[(uu - n + L) % L];
-                        o1 = __ffma2_rn(bc(hB[n]), s1, o1);
-                        o2 = __ffma2_rn(bc(hA[n]), s2, o2);
-                    }
-                    const uint32_t slot = x_g + (uint32_t)(fg + 1) * (kSlotStride * 8);
-                    sts64(slot, o1);
-                    sts64(slot + w2delta, o2);
-                }
+                // ---- even local frame: the window pushed on even frames gets the new sample
+                s0.dA[uu] = lds64(in_g + fg * (kM2 * 8));
+                s1.dA[uu] = lds64(in_g + fg * (kM2 * 8) - 256 * 8);
+                pair_mac<L, 0>(s0, uu, o1, o2);
+                pair_mac<L, 0>(s1, uu, o3, o4);
+                // o1/o3 belong to windows j, j+256 when the segment starts on an even frame (PAR0 = 0),
+                // to windows j+512, j+768 otherwise
+                if (PAR0 == 0) radix4_store(x_g + (uint32_t)fg * (kSlotStride * 8), o1, o3, o2, o4, t1, t2, t3);
+                else           radix4_store(x_g + (uint32_t)fg * (kSlotStride * 8), o2, o4, o1, o3, t1, t2, t3);
+
+                // ---- odd local frame: the other window of each pair gets the new sample, branches swap
+                s0.dB[uu] = lds64(in_g + (fg + 1) * (kM2 * 8));
+                s1.dB[uu] = lds64(in_g + (fg + 1) * (kM2 * 8) - 256 * 8);
+                pair_mac<L, 1>(s0, uu, o1, o2);
+                pair_mac<L, 1>(s1, uu, o3, o4);
+                if (PAR0 == 0) radix4_store(x_g + (uint32_t)(fg + 1) * (kSlotStride * 8), o1, o3, o2, o4, t1, t2, t3);
+                else           radix4_store(x_g + (uint32_t)(fg + 1) * (kSlotStride * 8), o2, o4, o1, o3, t1, t2, t3);
+
                 if (uu & 1) {
                     // group complete: publish it to the FFT warps (this also hands the input stage back:
                     // the producer refills stage gq only after full[gq] of this group has completed)
@@ -337,9 +372,19 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
         }
     } else {
         // =========================================================================== FFT warps
-        const int fw = warp - kMacWarps;                    // frame-in-group handled by this warp
-        const uint32_t tw_lane = s_tw + (uint32_t)lane * 8; // tw[k1][lane] at + k1*256
-        const bool producer = (fw == 0 && lane == 0);       // streams the input, 4 groups ahead
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        const int fwarp = warp - kMacWarps;                 // 0..7
+        const int f = fwarp >> 1;                           // frame-in-group handled by this warp pair
+        const int h = fwarp & 1;                            // which half of the work
+        // pass A: lane = (sub, r2): sub-problem p = 2h + sub, column r2
+        const int pA = 2 * h + (lane >> 4), r2 = lane & 15;
+        const uint32_t offA = (uint32_t)(pA * kSubStride + r2) * 8;           // + r1 * 17 * 8 (loads)
+        const uint32_t offAt = (uint32_t)(pA * kSubStride + r2 * 17) * 8;      // + k1 * 8 (transposed stores)
+        const uint32_t tw_lane = s_base + kOffTw16 + (uint32_t)r2 * 8;         // tw16[k1][r2] at + k1 * 128
+        // pass B: lane = (k1 - 8h, p): row k1 = 8h + lane/4 of sub-problem p = lane % 4
+        const int pB = lane & 3, k1B = 8 * h + (lane >> 2);
+        const uint32_t offB = (uint32_t)(pB * kSubStride + k1B) * 8;           // + r2 * 17 * 8
+        const bool producer = (fwarp == 0 && lane == 0);    // streams the input, 4 groups ahead
         auto fetch_group = [&](int gg) {
             // 4 consecutive frames are contiguous in the stream: one 16 KB bulk copy
             const int st = gg & (kInStages - 1);
@@ -355,53 +400,46 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
             mbar_wait(bar_full(gs), (uint32_t)(g >> 2) & 1u);
             // every MAC warp has finished group g, so input stage gs is free again
             if (producer && g + kInStages < n_groups) fetch_group(g + kInStages);
-            const uint32_t slot = s_x + (uint32_t)(gs * kGroup + fw) * (kSlotStride * 8) + (uint32_t)lane * 8;
+            const uint32_t slot = s_x + (uint32_t)(gs * kGroup + f) * (kSlotStride * 8);
 
-            float2 v[32];
-            // pass 1: lane = n2, points X[32 n1 + n2] (row n1 of the padded slot); DFT over n1
+            float2 v[16];
+            // pass A: 16-point DFT down the column r2 of sub-problem pA, then twiddle W256^(r2 k1)
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) v[n1] = lds64(slot + (uint32_t)(n1 * 33) * 8);
-            RegDft<32, +1>::run(v);
-            __syncwarp();                                   // every lane has read its column
-            // twiddle W^(n2 k1), then store transposed: row n2 = lane, column k1
-            const uint32_t row = slot + (uint32_t)lane * (32 * 8);      // = slot base + lane*33*8
+            for (int r1 = 0; r1 < 16; r1++) v[r1] = lds64(slot + offA + (uint32_t)(r1 * 17) * 8);
+            RegDft<16, +1>::run(v);
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                float2 t[8];
+            for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul2(v[k1], lds64(tw_lane + k1 * 128));
+            __syncwarp();                                   // both sub-problems of this warp fully read
+            // transposed store: row r2, column k1 (conflict-free: lanes are 17 units apart)
 #pragma unroll
-                for (int i = 0; i < 8; i++)
-                    if (8 * b + i) t[i] = lds64(tw_lane + (8 * b + i) * 256);
+            for (int k1 = 0; k1 < 16; k1++) sts64(slot + offAt + (uint32_t)k1 * 8, v[k1]);
+            // the other warp of this frame holds the other two sub-problems
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + f) : "memory");
+            // pass B: row k1 of sub-problem pB: 16-point DFT over r2 -> Y[4 (k1 + 16 k2) + p]
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int k1 = 8 * b + i;
-                    if (k1) v[k1] = cmul2(v[k1], t[i]);
-                    sts64(row + (uint32_t)k1 * 8, v[k1]);
-                }
-            }
-            __syncwarp();
-            // pass 2: lane = k1, points A[k1][n2] (row n2, column k1): same addresses as pass 1
-#pragma unroll
-            for (int n2 = 0; n2 < 32; n2++) v[n2] = lds64(slot + (uint32_t)(n2 * 33) * 8);
-            RegDft<32, +1>::run(v);
+            for (int q = 0; q < 16; q++) v[q] = lds64(slot + offB + (uint32_t)(q * 17) * 8);
+            RegDft<16, +1>::run(v);
             // the slot has been consumed (the DFT above needed every loaded value)
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty(gs));
-            float2 *yf = a.y + ((f_begin + (long long)g * kGroup + fw) * (long long)kM) + lane;
+            float2 *yf = a.y + ((f_begin + (long long)g * kGroup + f) * (long long)kM) + 32 * h + lane;
 #pragma unroll
-            for (int k2 = 0; k2 < 32; k2++) __stcs(yf + 32 * k2, v[k2]);
+            for (int k2 = 0; k2 < 16; k2++) __stcs(yf + 64 * k2, v[k2]);
         }
     }
 }
 
 template <int L>
-void launch_L(const FusedArgs &a, unsigned int grid, cudaStream_t st)
+void launch_L(const FusedArgs &a, int par0, unsigned int grid, cudaStream_t st)
 {
     static bool configured = false;
     if (!configured) {
-        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_fused_1024_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_fused_1024_kernel<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_fused_1024_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         configured = true;
     }
-    pfbch2_fused_1024_kernel<L><<<grid, kThreads, kSmemBytes, st>>>(a);
+    if (par0) pfbch2_fused_1024_kernel<L, 1><<<grid, kThreads, kSmemBytes, st>>>(a);
+    else      pfbch2_fused_1024_kernel<L, 0><<<grid, kThreads, kSmemBytes, st>>>(a);
     LC_LAUNCH_CHECK();
 }
 
@@ -417,11 +455,17 @@ bool fused_pfbch2_supported(unsigned int M, unsigned int L)
 
 void fused_pfbch2_make_twiddles(std::vector<float2> &tw)
 {
-    tw.resize(32 * 32);
-    for (int k1 = 0; k1 < 32; k1++)
-        for (int n2 = 0; n2 < 32; n2++) {
-            double ang = 2.0 * M_PI * (double)(k1 * n2) / 1024.0;
-            tw[k1 * 32 + n2] = make_float2((float)cos(ang), (float)sin(ang));
+    // tw4[p-1][j] = e^{+j 2 pi j p / 1024}, p = 1..3, j < 256; then tw16[k1][r2] = e^{+j 2 pi k1 r2 / 256}
+    tw.resize(3 * 256 + 16 * 16);
+    for (int p = 1; p <= 3; p++)
+        for (int j = 0; j < 256; j++) {
+            double ang = 2.0 * M_PI * (double)(j * p) / 1024.0;
+            tw[(p - 1) * 256 + j] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    for (int k1 = 0; k1 < 16; k1++)
+        for (int r2 = 0; r2 < 16; r2++) {
+            double ang = 2.0 * M_PI * (double)(k1 * r2) / 256.0;
+            tw[3 * 256 + k1 * 16 + r2] = make_float2((float)cos(ang), (float)sin(ang));
         }
 }
 
@@ -448,14 +492,13 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
     a.taps = d_taps_scaled;
     a.tw = d_tw;
     a.H = H;
-    a.par0 = parity0 & 1;
     a.n_groups = (int)n_groups;
     a.groups_per_cta = (int)per;
     switch (L) {
-    case 4: launch_L<4>(a, (unsigned int)ctas, st); break;
-    case 8: launch_L<8>(a, (unsigned int)ctas, st); break;
-    case 10: launch_L<10>(a, (unsigned int)ctas, st); break;
-    case 14: launch_L<14>(a, (unsigned int)ctas, st); break;
+    case 4: launch_L<4>(a, parity0 & 1, (unsigned int)ctas, st); break;
+    case 8: launch_L<8>(a, parity0 & 1, (unsigned int)ctas, st); break;
+    case 10: launch_L<10>(a, parity0 & 1, (unsigned int)ctas, st); break;
+    case 14: launch_L<14>(a, parity0 & 1, (unsigned int)ctas, st); break;
     default: fatal("launch_pfbch2_fused", "unsupported tap count");
     }
     return n_groups * kGroup;
