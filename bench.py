@@ -33,8 +33,8 @@ if ROOT not in sys.path:
 M, SEMI, AS = 1024, 7, 60.0
 BYTES_PER_SAMPLE = 24            # algorithmic: 8 B read + 16 B written per input sample
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel from one `ncu --set full` capture
-# (profiles/r01_ncu_fused_v6_summary.txt: 1.090224 GB + 2.089392 GB for 2^27 samples) -> bytes per sample
-NCU_DRAM_BYTES_PER_SAMPLE = (1.090224e9 + 2.089392e9) / (1 << 27)
+# (profiles/r01_ncu_fused_v7_summary.txt: 1.090287 GB + 2.090002 GB for 2^27 samples) -> bytes per sample
+NCU_DRAM_BYTES_PER_SAMPLE = (1.090287e9 + 2.090002e9) / (1 << 27)
 METRIC = "firpfbch2_crcf analysis M=1024 m=7 input throughput"
 UNIT = "MS/s"
 
@@ -280,10 +280,10 @@ def main():
     kernels_per_step = launches / max(args.steps, 1)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_SAMPLE * n / 1e9, "traffic_unit": "GB per launch",
-                "traffic_source": "ncu --set full capture at 2^27 samples per launch (profiles/r01_ncu_fused_v6_summary.txt), "
+                "traffic_source": "ncu --set full capture at 2^27 samples per launch (profiles/r01_ncu_fused_v7_summary.txt), "
                                   "scaled per sample",
                 "peak_source": peak_src,
-                "kernel": "pfbch2_fused_1024_kernel<14> (fused polyphase MAC + 1024-point IFFT), "
+                "kernel": "pfbch2_fused_1024_kernel<14,0> (fused polyphase MAC + 1024-point IFFT), "
                           "%.0f launch(es) per step" % kernels_per_step,
                 "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n,
                 "avg_launch_ms": avg_step_ms, "frac_of_8TBps_nominal": achieved / 8000.0}
