@@ -130,18 +130,12 @@ void firfilt_crcf_execute_block_dev(firfilt_crcf _q, const void *_d_x, unsigned 
     if (_n == 0) return;
     cudaStream_t st = lc::as_stream(_stream);
     const float2 *d_x = (const float2 *)_d_x;
-    // x == y is allowed: the history is rolled from x before y is written only if they differ, so
-    // when aliased keep a copy of the tail first
-    if (_d_x == _d_y) {
-        float2 *tail = (float2 *)_q->one.get(sizeof(float2) * _q->n * 2);
-        unsigned long long keep = _n < _q->n ? _n : _q->n;
-        LC_CUDA_CHECK(cudaMemcpyAsync(tail, d_x + (_n - keep), sizeof(float2) * keep, cudaMemcpyDeviceToDevice, st));
-        lc::firfilt::launch(_q->d_hist, d_x, (int)_q->n, _q->d_taps, _q->n, _q->scale, (float2 *)_d_y, _n, 1, st);
-        lc::roll_history(_q->d_hist, _q->n, _q->hist_tmp, tail, keep, st);
-    } else {
-        lc::firfilt::launch(_q->d_hist, d_x, (int)_q->n, _q->d_taps, _q->n, _q->scale, (float2 *)_d_y, _n, 1, st);
-        lc::roll_history(_q->d_hist, _q->n, _q->hist_tmp, d_x, _n, st);
-    }
+    // the kernels are tiled: a tile reads the tail of its left neighbour's input, so the device form
+    // cannot run in place (the host form firfilt_crcf_execute_block stages through separate device
+    // buffers and keeps the reference's x == y allowance, firfilt.c:340-341)
+    if (_d_x == _d_y) lc::fatal("firfilt_crcf_execute_block_dev", "in-place operation is not supported on device pointers");
+    lc::firfilt::launch(_q->d_hist, d_x, (int)_q->n, _q->d_taps, _q->n, _q->scale, (float2 *)_d_y, _n, 1, st);
+    lc::roll_history(_q->d_hist, _q->n, _q->hist_tmp, d_x, _n, st);
 }
 
 void firfilt_crcf_execute_streams_dev(firfilt_crcf _q, const void *_d_x, unsigned int _n_streams,

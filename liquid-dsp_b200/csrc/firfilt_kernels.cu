@@ -6,6 +6,8 @@
 // outputs from a register window that slides one sample per tap.
 #include "firfilt_kernels.cuh"
 
+#include <cstdint>
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -72,6 +74,114 @@ firfilt_tiled_kernel(const float2 *__restrict__ hist, const float2 *__restrict__
     for (int r = 0; r < kOpt; r++) {
         long long o = o0 + (long long)t * kOpt + r;
         if (o < (long long)n) ystr[o] = make_float2(acc[r].x * scale, acc[r].y * scale);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register-blocked FIR for short filters (NT <= 64 taps, zero-padded up to NT): the FP32-pipe-bound
+// shape of BASELINE config 2.  Each thread produces RO = 8 consecutive outputs; the NT taps sit in
+// registers (the same in every thread), samples come from the staged tile one LDS.64 per RO packed
+// FFMA2 (tap broadcast x {re, im} pair).  Everything is unrolled, so tap and accumulator indices are
+// compile-time constants:  y[o+r] += h[k] x[o+r-k]  is visited sample by sample (s = o+r-k).
+constexpr int kRbThreads = 256;
+constexpr int kRbOut = 8;                      // outputs per thread
+constexpr int kRbTile = kRbThreads * kRbOut;   // 2048 outputs per CTA tile
+
+__device__ __forceinline__ void cp_async8_zfill(float2 *dst_smem, const float2 *src, bool valid)
+{
+    // 8-byte asynchronous global->shared copy; when !valid nothing is read and zeros are written
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
+    const int bytes = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+// persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the next tile is fetched
+// with cp.async into the other shared buffer while the current one is filtered
+template <int NT>
+__global__ void __launch_bounds__(kRbThreads, 2)
+firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                        const float *__restrict__ taps, unsigned int n_taps, float scale,
+                        float2 *__restrict__ y, unsigned long long n, unsigned long long tiles_per_stream,
+                        unsigned long long n_tiles)
+{
+    // staged samples, transposed so that thread t reading sample t*8 + i is conflict-free:
+    // slot(q) = (q % 8) * ROW + q / 8
+    constexpr int NS = kRbTile + NT - 1;
+    // ROW = 2 (mod 16) makes the 8-byte cp.async fill (16 lanes = 8 rows x 2 columns) conflict-free too
+    constexpr int ROW0 = (NS + kRbOut - 1) / kRbOut;
+    constexpr int ROW = ROW0 + ((2 - ROW0 % 16) + 16) % 16;
+    constexpr int NPASS = (NS + kRbThreads - 1) / kRbThreads;
+    constexpr int NBUF = 3;                     // three buffers: one barrier per tile is enough
+    extern __shared__ float2 xs_dyn[];          // NBUF buffers of kRbOut * ROW samples
+    float2 (*xs)[kRbOut * ROW] = reinterpret_cast<float2 (*)[kRbOut * ROW]>(xs_dyn);
+
+    float h[NT];
+#pragma unroll
+    for (int k = 0; k < NT; k++) h[k] = (k < (int)n_taps) ? __ldg(taps + k) * scale : 0.0f;
+
+    auto prefetch = [&](unsigned long long tile_id, int buf) {
+        const unsigned long long stream = tile_id / tiles_per_stream;
+        const long long first = (long long)((tile_id % tiles_per_stream) * kRbTile) - (long long)(NT - 1);
+        const float2 *xstr = x + stream * n;
+#pragma unroll
+        for (int i = 0; i < NPASS; i++) {
+            const int q = threadIdx.x + i * kRbThreads;
+            if (q < NS) {
+                const long long idx = first + q;
+                const float2 *src = xstr;
+                bool valid = false;
+                if (idx >= 0 && idx < (long long)n) { src = xstr + idx; valid = true; }
+                else if (idx < 0 && hist != nullptr && H + idx >= 0) { src = hist + (H + idx); valid = true; }
+                cp_async8_zfill(&xs[buf][(q % kRbOut) * ROW + q / kRbOut], src, valid);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    unsigned long long tile_id = blockIdx.x;
+    int buf = 0;
+    if (tile_id < n_tiles) prefetch(tile_id, 0);
+    for (; tile_id < n_tiles; tile_id += gridDim.x, buf = (buf + 1 == NBUF) ? 0 : buf + 1) {
+        const unsigned long long next = tile_id + gridDim.x;
+        if (next < n_tiles) {
+            // the buffer written here was read two tiles ago; every thread has passed the barrier of
+            // the previous tile since, so nobody still reads it
+            prefetch(next, (buf + 1 == NBUF) ? 0 : buf + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+
+        const int t = threadIdx.x;
+        const float2 *xb = xs[buf];
+        float2 acc[kRbOut];
+#pragma unroll
+        for (int r = 0; r < kRbOut; r++) acc[r] = make_float2(0.f, 0.f);
+        // tile-relative sample i = t*8 + d, d = 0 .. NT+6, feeds output r with tap k = (NT-1) + r - d
+#pragma unroll
+        for (int d = 0; d < NT - 1 + kRbOut; d++) {
+            const float2 sv = xb[(d % kRbOut) * ROW + t + d / kRbOut];
+#pragma unroll
+            for (int r = 0; r < kRbOut; r++) {
+                const int k = (NT - 1) + r - d;
+                if (k >= 0 && k < NT) acc[r] = __ffma2_rn(make_float2(h[k], h[k]), sv, acc[r]);
+            }
+        }
+        // the scale is folded into the taps: (h[k] * scale) * x differs from scale * (sum h x) only by
+        // float rounding of the products (well inside the parity tolerance of the tests)
+        const unsigned long long stream = tile_id / tiles_per_stream;
+        const long long o0 = (long long)((tile_id % tiles_per_stream) * kRbTile);
+        float2 *ystr = y + stream * n;
+#pragma unroll
+        for (int r = 0; r < kRbOut; r += 2) {
+            long long o = o0 + (long long)t * kRbOut + r;
+            if (o + 1 < (long long)n) {
+                __stcs(reinterpret_cast<float4 *>(ystr + o), make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y));
+            } else if (o < (long long)n) {
+                ystr[o] = acc[r];
+            }
+        }
     }
 }
 
@@ -167,6 +277,31 @@ namespace firfilt {
 void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, unsigned int n_taps,
             float scale, float2 *d_y, unsigned long long n, unsigned int n_streams, cudaStream_t st)
 {
+    // short filters on 16-byte aligned, even-length streams: register-blocked packed kernel
+    if (n_taps <= 64 && (n % 2) == 0 && ((uintptr_t)d_y % 16) == 0 && !getenv("LIQUID_CUDA_NO_REGBLOCK")) {
+        const unsigned long long tiles_rb = (n + kRbTile - 1) / kRbTile;
+        const unsigned long long total_rb = tiles_rb * n_streams;
+        {
+            int dev = 0, sms = 148;
+            LC_CUDA_CHECK(cudaGetDevice(&dev));
+            LC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            unsigned long long grid = (unsigned long long)sms * 2;      // two resident CTAs per SM
+            if (grid > total_rb) grid = total_rb;
+            auto run = [&](auto kern, int NT) {
+                const int NS = kRbTile + NT - 1;
+                const int ROW0 = (NS + kRbOut - 1) / kRbOut;
+                const int ROW = ROW0 + ((2 - ROW0 % 16) + 16) % 16;
+                const size_t smem = (size_t)3 * kRbOut * ROW * sizeof(float2);
+                LC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<(unsigned int)grid, kRbThreads, smem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n, tiles_rb, total_rb);
+            };
+            if (n_taps <= 16) run(firfilt_regblock_kernel<16>, 16);
+            else if (n_taps <= 32) run(firfilt_regblock_kernel<32>, 32);
+            else run(firfilt_regblock_kernel<64>, 64);
+            LC_LAUNCH_CHECK();
+            return;
+        }
+    }
     const unsigned long long tiles = (n + kTile - 1) / kTile;
     const unsigned int n_samp = kTile + n_taps - 1;
     const unsigned int row = (n_samp + kOpt - 1) / kOpt + 1;

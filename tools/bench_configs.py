@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Secondary benchmarks: the other BASELINE.json configs (parity-test cases in bench.py's contract,
+measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
+events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
+
+  python tools/bench_configs.py [c1] [c2] [c4] [c5] [--steps K]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="*", default=["c1", "c2", "c4", "c5"])
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    import liquid_dsp_b200 as L
+    L.set_device(0)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream()
+    peak = 6531.6
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peak = float(json.load(open(p))["hbm_gbs"])
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.launch_count()
+        e0.record(st)
+        for _ in range(args.steps):
+            fn()
+        e1.record(st)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, (L.launch_count() - l0) / args.steps
+
+    def report(name, n_in, bytes_per_sample, ms, launches, extra=None):
+        gbs = bytes_per_sample * n_in / (ms * 1e-3) / 1e9
+        line = {"config": name, "metric": "input throughput", "value": n_in / (ms * 1e-3) / 1e6, "unit": "MS/s",
+                "ms_per_step": ms, "launches_per_step": launches,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                             "algorithmic_bytes_per_sample": bytes_per_sample}}
+        if extra:
+            line.update(extra)
+        print(json.dumps(line), flush=True)
+
+    if "c1" in args.configs:
+        # firpfbch_crcf analysis M=16, m=4 (p=8), one long stream (BASELINE configs[0] shape, GPU-sized)
+        M, m, n = 16, 4, 1 << 28
+        q = L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+        x = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr(), n, stream=st.cuda_stream)
+        ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
+        report("c1: firpfbch_crcf analysis M=16 m=4, 2^28 samples", n, 16, ms, ln)
+        del x, y
+    if "c2" in args.configs:
+        # firfilt_crcf_execute_block, 64-tap Kaiser low-pass, 1024 independent streams x 2^20 samples
+        ns, n = 1024, 1 << 20
+        q = L.firfilt_crcf.create_kaiser(64, 0.25, 60.0, 0.0)
+        x = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr(), ns * n, stream=st.cuda_stream)
+        ms, ln = timed(lambda: q.execute_streams_dev(x.data_ptr(), ns, n, y.data_ptr(), st.cuda_stream))
+        fp_peak = 148 * 4 * 0.5 * 32 * 1.92e9 / 64 / 1e6      # MS/s at 100 % FMA-pipe use (64 packed FMA per sample)
+        report("c2: firfilt_crcf 64 taps, 1024 streams x 2^20 samples", ns * n, 16, ms, ln,
+               {"fp32_pipe_bound_MSps": fp_peak})
+        del x, y
+    if "c4" in args.configs:
+        # firpfbch_crcf synthesis + analysis round trip, M=256, m=5, 32 streams x 2^22 samples on this GPU
+        M, m, ns, n = 256, 5, 32, 1 << 22
+        qs = [L.firpfbch_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0) for _ in range(ns)]
+        qa = [L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0) for _ in range(ns)]
+        x = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+        t = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr(), ns * n, stream=st.cuda_stream)
+
+        def rt():
+            for s in range(ns):
+                off = 8 * s * n
+                qs[s].execute_block_dev(x.data_ptr() + off, n // M, t.data_ptr() + off, st.cuda_stream)
+                qa[s].execute_block_dev(t.data_ptr() + off, n // M, y.data_ptr() + off, st.cuda_stream)
+        ms, ln = timed(rt)
+        report("c4: firpfbch_crcf synthesis+analysis round trip M=256 m=5, 32 streams x 2^22 samples", ns * n, 32, ms, ln)
+        del x, t, y
+    if "c5" in args.configs:
+        # firpfbch2_crcf analysis M=4096, m=9 on a 2^29-sample segment (one GPU's share of the sharded stream)
+        M, m, n = 4096, 9, 1 << 29
+        q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+        H = q.get_state_len()
+        x = torch.zeros(2 * (H + n), dtype=torch.float32, device=dev)
+        y = torch.empty(4 * n, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
+        ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
+        report("c5: firpfbch2_crcf analysis M=4096 m=9, 2^29-sample segment", n, 24, ms, ln)
+
+
+if __name__ == "__main__":
+    main()
