@@ -79,6 +79,7 @@ _sig("firpfbch_crcf_analyzer_run", None, _vp, _u, _cf_p)
 _sig("firpfbch_crcf_analyzer_execute_block", None, _vp, _vp, _u, _vp)
 _sig("firpfbch_crcf_synthesizer_execute_block", None, _vp, _vp, _u, _vp)
 _sig("firpfbch_crcf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
+_sig("firpfbch_crcf_execute_streams_dev", None, _vp, _vp, _u, _ull, _vp, _vp)
 _sig("firpfbch_crcf_get_state_len", _u, _vp)
 _sig("firpfbch_crcf_get_state", None, _vp, _cf_p)
 _sig("firpfbch_crcf_set_state", None, _vp, _cf_p)
@@ -354,6 +355,9 @@ class firpfbch_crcf(_Handle):
 
     def execute_block_dev(self, d_x, n_frames, d_y, stream=0):
         lib.firpfbch_crcf_execute_block_dev(self._h, d_x, n_frames, d_y, stream)
+
+    def execute_streams_dev(self, d_x, n_streams, n_frames, d_y, stream=0):
+        lib.firpfbch_crcf_execute_streams_dev(self._h, d_x, n_streams, n_frames, d_y, stream)
 
     def get_state(self):
         hist = np.empty(lib.firpfbch_crcf_get_state_len(self._h), np.complex64)

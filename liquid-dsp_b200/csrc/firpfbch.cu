@@ -9,11 +9,13 @@
 //            sum_n h[i+nM] * (n-th newest of that window) into input M-1-i of an unscaled forward DFT.
 // Synthesizer: v_s = unscaled backward DFT of frame s; y[sM+i] = sum_n h[i+nM] v_{s-n}[i].
 #include <cmath>
+#include <cstdint>
 
 #include "lc_common.cuh"
 #include "../../include/liquid_cuda.h"
 #include "pfb_kernels.cuh"
 #include "host_pipeline.cuh"
+#include "pfbch_fused.cuh"
 
 struct firpfbch_crcf_s {
     int type;
@@ -22,6 +24,9 @@ struct firpfbch_crcf_s {
     std::vector<float> h;           // M*p prototype taps (host copy, for print)
     float *d_taps = nullptr;        // [p][M]: taps[n][i] = h[i + nM]
     float2 *d_hist = nullptr;
+    float2 *d_zero = nullptr;       // H zeros: the reset state, for the stateless multi-stream form
+    float2 *d_tw_fused = nullptr;   // fused M = 256 kernel's inter-pass twiddles
+    bool fused = false;
     unsigned int phase = 0;         // analyzer: pushes since reset, mod M
     lc::FftPlanDev fft;
     lc::DevBuf scratch, stage_in, stage_out, hist_tmp, one;
@@ -51,6 +56,15 @@ firpfbch_crcf firpfbch_crcf_create(int _type, unsigned int _M, unsigned int _p, 
     LC_CUDA_CHECK(cudaMalloc(&q->d_taps, sizeof(float) * q->h.size()));
     LC_CUDA_CHECK(cudaMemcpy(q->d_taps, q->h.data(), sizeof(float) * q->h.size(), cudaMemcpyHostToDevice));
     LC_CUDA_CHECK(cudaMalloc(&q->d_hist, sizeof(float2) * q->H));
+    LC_CUDA_CHECK(cudaMalloc(&q->d_zero, sizeof(float2) * q->H));
+    LC_CUDA_CHECK(cudaMemset(q->d_zero, 0, sizeof(float2) * q->H));
+    if (_type == LIQUID_ANALYZER && lc::pfb::fused_pfbch_supported(_M, _p)) {
+        std::vector<float2> tw;
+        lc::pfb::fused_pfbch_make_twiddles(tw);
+        LC_CUDA_CHECK(cudaMalloc(&q->d_tw_fused, tw.size() * sizeof(float2)));
+        LC_CUDA_CHECK(cudaMemcpy(q->d_tw_fused, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        q->fused = true;
+    }
     q->fft.init(_M, _type == LIQUID_ANALYZER ? -1 : +1);     // firpfbch.c:131-135
     LC_CUDA_CHECK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
     firpfbch_crcf_reset(q);
@@ -108,6 +122,8 @@ void firpfbch_crcf_destroy(firpfbch_crcf _q)
     cudaStreamSynchronize(_q->stream);
     cudaFree(_q->d_taps);
     cudaFree(_q->d_hist);
+    cudaFree(_q->d_zero);
+    cudaFree(_q->d_tw_fused);
     _q->fft.destroy();
     _q->scratch.release();
     _q->stage_in.release();
@@ -154,16 +170,52 @@ void firpfbch_crcf_execute_block_dev(firpfbch_crcf _q, const void *_d_x, unsigne
     const float2 *d_x = (const float2 *)_d_x;
     float2 *d_y = (float2 *)_d_y;
     if (_q->type == LIQUID_ANALYZER) {
-        // M pushes then run(k=0) per frame; MAC into y, forward FFT in place, unscaled
-        lc::pfb::launch_pfbch_mac(_q->d_hist, d_x, (int)_q->H, _q->d_taps, d_y, _q->M, _q->p, _n_frames,
-                                  _q->phase, _q->M, 0, st);
-        _q->fft.run(d_y, d_y, _n_frames, st);
+        // M pushes then run(k=0) per frame
+        unsigned long long done = 0;
+        if (_q->fused && _q->phase == 0 && _n_frames >= 16 && ((uintptr_t)d_x % 16) == 0 && ((uintptr_t)d_y % 16) == 0 &&
+            !getenv("LIQUID_CUDA_NO_FUSED"))
+            done = (unsigned long long)lc::pfb::launch_pfbch_fused(_q->d_hist, d_x, (int)_q->H, _q->d_taps, _q->d_tw_fused,
+                                                                   d_y, _q->M, _q->p, _n_frames, 1, 0, st);
+        if (done < _n_frames) {
+            // shape-generic path (and the < 16 frames the fused kernel leaves): MAC into y, forward
+            // FFT in place, unscaled
+            lc::pfb::launch_pfbch_mac(_q->d_hist, d_x, (int)_q->H, _q->d_taps, d_y + done * _q->M, _q->M, _q->p,
+                                      _n_frames - done, _q->phase, (unsigned int)((done + 1) * _q->M), 0, st);
+            _q->fft.run(d_y + done * _q->M, d_y + done * _q->M, _n_frames - done, st);
+        }
         lc::roll_history(_q->d_hist, _q->H, _q->hist_tmp, d_x, _n_frames * _q->M, st);
     } else {
         float2 *d_v = (float2 *)_q->scratch.get(sizeof(float2) * _n_frames * _q->M);
         _q->fft.run(d_x, d_v, _n_frames, st);
         lc::pfb::launch_pfbch_synth_fir(_q->d_hist, d_v, (int)_q->p, _q->d_taps, d_y, _q->M, _q->p, _n_frames, st);
         lc::roll_history(_q->d_hist, _q->H, _q->hist_tmp, d_v, _n_frames * _q->M, st);
+    }
+}
+
+// n_streams independent streams of n_frames frames each, every stream from the reset state; the
+// object's own state is not touched (analyzer only)
+void firpfbch_crcf_execute_streams_dev(firpfbch_crcf _q, const void *_d_x, unsigned int _n_streams,
+                                       unsigned long long _n_frames, void *_d_y, void *_stream)
+{
+    if (_q->type != LIQUID_ANALYZER)
+        lc::fatal("firpfbch_crcf_execute_streams_dev", "the multi-stream form is provided for the analyzer only");
+    if (_n_frames == 0 || _n_streams == 0) return;
+    cudaStream_t st = lc::as_stream(_stream);
+    const float2 *d_x = (const float2 *)_d_x;
+    float2 *d_y = (float2 *)_d_y;
+    const long long stride = (long long)_n_frames * _q->M;
+    unsigned long long done = 0;
+    if (_q->fused && _n_frames >= 16 && ((uintptr_t)d_x % 16) == 0 && ((uintptr_t)d_y % 16) == 0 && (stride % 2) == 0 &&
+        !getenv("LIQUID_CUDA_NO_FUSED"))
+        done = (unsigned long long)lc::pfb::launch_pfbch_fused(nullptr, d_x, 0, _q->d_taps, _q->d_tw_fused, d_y, _q->M,
+                                                               _q->p, _n_frames, _n_streams, stride, st);
+    if (done < _n_frames) {
+        for (unsigned int s = 0; s < _n_streams; s++) {
+            float2 *ys = d_y + s * stride + done * _q->M;
+            lc::pfb::launch_pfbch_mac(_q->d_zero, d_x + s * stride, (int)_q->H, _q->d_taps, ys, _q->M, _q->p,
+                                      _n_frames - done, 0, (unsigned int)((done + 1) * _q->M), 0, st);
+            _q->fft.run(ys, ys, _n_frames - done, st);
+        }
     }
 }
 

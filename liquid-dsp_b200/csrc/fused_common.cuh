@@ -1,0 +1,150 @@
+// fused_common.cuh -- device building blocks shared by the fused channelizer kernels:
+// mbarrier / bulk-copy PTX wrappers, packed FP32x2 arithmetic, and the register DFT.
+#pragma once
+#include <cstdint>
+
+#include "lc_common.cuh"
+
+namespace lcf {
+
+// ---------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float2 v)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// ---------------------------------------------------------------------------------- register DFT
+// cos / sin of 2 pi k / 32, k = 0..15
+__device__ constexpr float kCos32[16] = {1.0f,
+                                         0.98078528040323044913f,
+                                         0.92387953251128675613f,
+                                         0.83146961230254523708f,
+                                         0.70710678118654752440f,
+                                         0.55557023301960222474f,
+                                         0.38268343236508977173f,
+                                         0.19509032201612826785f,
+                                         0.0f,
+                                         -0.19509032201612826785f,
+                                         -0.38268343236508977173f,
+                                         -0.55557023301960222474f,
+                                         -0.70710678118654752440f,
+                                         -0.83146961230254523708f,
+                                         -0.92387953251128675613f,
+                                         -0.98078528040323044913f};
+__device__ constexpr float kSin32[16] = {0.0f,
+                                         0.19509032201612826785f,
+                                         0.38268343236508977173f,
+                                         0.55557023301960222474f,
+                                         0.70710678118654752440f,
+                                         0.83146961230254523708f,
+                                         0.92387953251128675613f,
+                                         0.98078528040323044913f,
+                                         1.0f,
+                                         0.98078528040323044913f,
+                                         0.92387953251128675613f,
+                                         0.83146961230254523708f,
+                                         0.70710678118654752440f,
+                                         0.55557023301960222474f,
+                                         0.38268343236508977173f,
+                                         0.19509032201612826785f};
+
+// packed FP32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): one instruction works on a {re, im} register
+// pair; ptxas folds make_float2(t, t) into a scalar-broadcast operand and make_float2(-a.y, a.x) into a
+// swapped, half-negated operand, so none of these cost extra moves.  The FMA pipe spends two cycles on
+// a packed instruction (same flop rate as two scalar ones) but it takes a single issue slot.
+__device__ __forceinline__ float2 bc(float t) { return make_float2(t, t); }
+__device__ __forceinline__ float2 rot90(float2 a) { return make_float2(-a.y, a.x); }      //  j * a
+__device__ __forceinline__ float2 rot270(float2 a) { return make_float2(a.y, -a.x); }     // -j * a
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+// complex product a * t
+__device__ __forceinline__ float2 cmul2(float2 a, float2 t)
+{
+    return __ffma2_rn(bc(t.y), rot90(a), __fmul2_rn(bc(t.x), a));
+}
+
+// N-point DFT of v[] in registers, natural order in and out, e^{SIGN j 2 pi nk/N}.
+// Decimation in time; every index is a compile-time constant, so the even/odd split is renaming.
+template <int N, int SIGN>
+struct RegDft {
+    static __device__ __forceinline__ void run(float2 (&v)[N])
+    {
+        float2 e[N / 2], o[N / 2];
+#pragma unroll
+        for (int i = 0; i < N / 2; i++) {
+            e[i] = v[2 * i];
+            o[i] = v[2 * i + 1];
+        }
+        RegDft<N / 2, SIGN>::run(e);
+        RegDft<N / 2, SIGN>::run(o);
+#pragma unroll
+        for (int k = 0; k < N / 2; k++) {
+            if (k == 0) {
+                v[k] = __fadd2_rn(e[k], o[k]);
+                v[k + N / 2] = __fadd2_rn(e[k], neg2(o[k]));
+            } else if (4 * k == N) {
+                // w = SIGN * j
+                const float2 r = (SIGN > 0) ? rot90(o[k]) : rot270(o[k]);
+                v[k] = __fadd2_rn(e[k], r);
+                v[k + N / 2] = __fadd2_rn(e[k], neg2(r));
+            } else {
+                const float c = kCos32[k * (32 / N)];
+                const float sn = (float)SIGN * kSin32[k * (32 / N)];
+                // a + w b = a + c b + sn (j b) in two packed FMAs; a - w b = 2a - (a + w b) in one
+                const float2 t = __ffma2_rn(bc(c), o[k], e[k]);
+                v[k] = __ffma2_rn(bc(sn), rot90(o[k]), t);
+                v[k + N / 2] = __ffma2_rn(bc(2.0f), e[k], neg2(v[k]));
+            }
+        }
+    }
+};
+template <int SIGN>
+struct RegDft<1, SIGN> {
+    static __device__ __forceinline__ void run(float2 (&)[1]) {}
+};
+
+}  // namespace lcf

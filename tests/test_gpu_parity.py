@@ -403,3 +403,41 @@ def test_pfbch2_fused_matches_generic_path(L, orc, monkeypatch):
     monkeypatch.delenv("LIQUID_CUDA_NO_FUSED")
     assert rel_rms_per_channel(fused, generic).max() < 2e-6
     assert np.abs(fused - generic).max() < 1e-6
+
+
+# ------------------------------------------------------------------ fused firpfbch analysis kernels
+@pytest.mark.parametrize("M,m,nfr", [(16, 4, 16 * 37 + 5), (16, 2, 16 * 300), (256, 5, 16 * 21 + 3), (256, 2, 16 * 40)])
+def test_pfbch_fused_analysis_vs_oracle_and_generic(L, orc, monkeypatch, M, m, nfr):
+    """fused M=16 / M=256 analyzers: many tiles and instances, a tail that is not a multiple of the
+    16-frame tile, state carried across calls; against the oracle and against the generic kernels"""
+    x = orc.synth_input(nfr * M, seed=0xD0 + M + m)
+    want = orc.Firpfbch(orc.ANALYZER, M, kaiser=(m, 60.0)).execute_frames(x)
+    q = L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    cut = 16 * 5 + 7
+    got = np.concatenate([q.execute_block(x[:cut * M]), q.execute_block(x[cut * M:])])
+    assert rel_rms_per_channel(got, want).max() < TOL_REL_RMS
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+    q.reset()
+    monkeypatch.setenv("LIQUID_CUDA_NO_FUSED", "1")
+    generic = q.execute_block(x)
+    monkeypatch.delenv("LIQUID_CUDA_NO_FUSED")
+    assert np.abs(got - generic).max() / np.abs(want).max() < 2e-6
+
+
+@pytest.mark.parametrize("M,m", [(16, 4), (256, 5), (64, 3)])
+def test_pfbch_streams_dev(L, orc, M, m):
+    """stateless multi-stream analyzer form (BASELINE config 4 shape): every stream from the reset state"""
+    import ctypes as C
+    n_streams, nfr = 5, 16 * 9 + 4
+    x = orc.synth_input(n_streams * nfr * M, seed=0xE0 + M).reshape(n_streams, nfr * M)
+    q = L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    d_x = L.lib.liquid_cuda_malloc(x.nbytes); d_y = L.lib.liquid_cuda_malloc(x.nbytes)
+    L.lib.liquid_cuda_memcpy_h2d(d_x, x.ctypes.data_as(C.c_void_p), x.nbytes)
+    q.execute_streams_dev(d_x, n_streams, nfr, d_y, 0)
+    L.lib.liquid_cuda_sync()
+    got = np.empty_like(x)
+    L.lib.liquid_cuda_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_y, x.nbytes)
+    L.lib.liquid_cuda_free(d_x); L.lib.liquid_cuda_free(d_y)
+    for s in range(n_streams):
+        want = orc.Firpfbch(orc.ANALYZER, M, kaiser=(m, 60.0)).execute_frames(x[s])
+        assert np.abs(got[s].reshape(nfr, M) - want).max() / np.abs(want).max() < 1e-5

@@ -89,9 +89,12 @@ def main():
             for s in range(ns):
                 off = 8 * s * n
                 qs[s].execute_block_dev(x.data_ptr() + off, n // M, t.data_ptr() + off, st.cuda_stream)
-                qa[s].execute_block_dev(t.data_ptr() + off, n // M, y.data_ptr() + off, st.cuda_stream)
+            # analysis half: all streams in one launch (stateless multi-stream form)
+            qa[0].execute_streams_dev(t.data_ptr(), ns, n // M, y.data_ptr(), st.cuda_stream)
         ms, ln = timed(rt)
         report("c4: firpfbch_crcf synthesis+analysis round trip M=256 m=5, 32 streams x 2^22 samples", ns * n, 32, ms, ln)
+        ms, ln = timed(lambda: qa[0].execute_streams_dev(t.data_ptr(), ns, n // M, y.data_ptr(), st.cuda_stream))
+        report("c4a: analysis half only (firpfbch_crcf analysis M=256 m=5, 32 streams x 2^22 samples)", ns * n, 16, ms, ln)
         del x, t, y
     if "c5" in args.configs:
         # firpfbch2_crcf analysis M=4096, m=9 on a 2^29-sample segment (one GPU's share of the sharded stream)
