@@ -184,8 +184,8 @@ void firpfbch_crcf_synthesizer_execute_block(firpfbch_crcf _q, liquid_float_comp
 /* device pointers; dispatches on the object's type */
 void firpfbch_crcf_execute_block_dev(firpfbch_crcf _q, const void *_d_x,
                                      unsigned long long _n_frames, void *_d_y, void *_stream);
-/* analyzer only: _n_streams independent streams of _n_frames frames each (stream s at
- * _d_x + s*_n_frames*M, same for _d_y), every stream from the reset state; object state untouched */
+/* _n_streams independent streams of _n_frames frames each (stream s at _d_x + s*_n_frames*M, same for
+ * _d_y), every stream from the reset state; dispatches on the object's type; object state untouched */
 void firpfbch_crcf_execute_streams_dev(firpfbch_crcf _q, const void *_d_x, unsigned int _n_streams,
                                        unsigned long long _n_frames, void *_d_y, void *_stream);
 unsigned int firpfbch_crcf_get_state_len(firpfbch_crcf _q);

@@ -58,9 +58,10 @@ firpfbch_crcf firpfbch_crcf_create(int _type, unsigned int _M, unsigned int _p, 
     LC_CUDA_CHECK(cudaMalloc(&q->d_hist, sizeof(float2) * q->H));
     LC_CUDA_CHECK(cudaMalloc(&q->d_zero, sizeof(float2) * q->H));
     LC_CUDA_CHECK(cudaMemset(q->d_zero, 0, sizeof(float2) * q->H));
-    if (_type == LIQUID_ANALYZER && lc::pfb::fused_pfbch_supported(_M, _p)) {
+    if ((_type == LIQUID_ANALYZER && lc::pfb::fused_pfbch_supported(_M, _p)) ||
+        (_type == LIQUID_SYNTHESIZER && lc::pfb::fused_pfbch_synth_supported(_M, _p))) {
         std::vector<float2> tw;
-        lc::pfb::fused_pfbch_make_twiddles(tw);
+        lc::pfb::fused_pfbch_make_twiddles(tw, _type == LIQUID_ANALYZER ? -1 : +1);
         LC_CUDA_CHECK(cudaMalloc(&q->d_tw_fused, tw.size() * sizeof(float2)));
         LC_CUDA_CHECK(cudaMemcpy(q->d_tw_fused, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
         q->fused = true;
@@ -185,36 +186,65 @@ void firpfbch_crcf_execute_block_dev(firpfbch_crcf _q, const void *_d_x, unsigne
         }
         lc::roll_history(_q->d_hist, _q->H, _q->hist_tmp, d_x, _n_frames * _q->M, st);
     } else {
-        float2 *d_v = (float2 *)_q->scratch.get(sizeof(float2) * _n_frames * _q->M);
-        _q->fft.run(d_x, d_v, _n_frames, st);
-        lc::pfb::launch_pfbch_synth_fir(_q->d_hist, d_v, (int)_q->p, _q->d_taps, d_y, _q->M, _q->p, _n_frames, st);
-        lc::roll_history(_q->d_hist, _q->H, _q->hist_tmp, d_v, _n_frames * _q->M, st);
+        const unsigned int M = _q->M, p = _q->p;
+        unsigned long long done = 0;
+        if (_q->fused && _n_frames >= 16 && ((uintptr_t)d_x % 16) == 0 && !getenv("LIQUID_CUDA_NO_FUSED"))
+            done = (unsigned long long)lc::pfb::launch_pfbch_synth_fused(_q->d_hist, (int)p, d_x, _q->d_taps, _q->d_tw_fused,
+                                                                         d_y, M, p, _n_frames, 1, 0, st);
+        // rows of v the generic tail and the new state need: frames [v0, n)
+        const unsigned long long v0 = (done > p) ? done - p : 0;
+        float2 *d_v = (float2 *)_q->scratch.get(sizeof(float2) * (_n_frames - v0 + p) * M);
+        if (done < _n_frames || v0 < _n_frames) _q->fft.run(d_x + v0 * M, d_v, _n_frames - v0, st);
+        if (done < _n_frames) {
+            // shape-generic path (and the < 16 frames the fused kernel leaves)
+            const float2 *hist_rows = (done == 0) ? _q->d_hist : d_v + (done - v0 - p) * M;   // p rows before frame `done`
+            lc::pfb::launch_pfbch_synth_fir(hist_rows, d_v + (done - v0) * M, (int)p, _q->d_taps, d_y + done * M, M, p,
+                                            _n_frames - done, st);
+        }
+        // new state: the last p rows of v (d_v holds frames [v0, n))
+        lc::roll_history(_q->d_hist, _q->H, _q->hist_tmp, d_v, (_n_frames - v0) * M, st);
     }
 }
 
 // n_streams independent streams of n_frames frames each, every stream from the reset state; the
-// object's own state is not touched (analyzer only)
+// object's own state is not touched
 void firpfbch_crcf_execute_streams_dev(firpfbch_crcf _q, const void *_d_x, unsigned int _n_streams,
                                        unsigned long long _n_frames, void *_d_y, void *_stream)
 {
-    if (_q->type != LIQUID_ANALYZER)
-        lc::fatal("firpfbch_crcf_execute_streams_dev", "the multi-stream form is provided for the analyzer only");
     if (_n_frames == 0 || _n_streams == 0) return;
     cudaStream_t st = lc::as_stream(_stream);
     const float2 *d_x = (const float2 *)_d_x;
     float2 *d_y = (float2 *)_d_y;
-    const long long stride = (long long)_n_frames * _q->M;
+    const unsigned int M = _q->M, p = _q->p;
+    const long long stride = (long long)_n_frames * M;
+    const bool ok = _q->fused && _n_frames >= 16 && ((uintptr_t)d_x % 16) == 0 && ((uintptr_t)d_y % 16) == 0 &&
+                    (stride % 2) == 0 && !getenv("LIQUID_CUDA_NO_FUSED");
     unsigned long long done = 0;
-    if (_q->fused && _n_frames >= 16 && ((uintptr_t)d_x % 16) == 0 && ((uintptr_t)d_y % 16) == 0 && (stride % 2) == 0 &&
-        !getenv("LIQUID_CUDA_NO_FUSED"))
-        done = (unsigned long long)lc::pfb::launch_pfbch_fused(nullptr, d_x, 0, _q->d_taps, _q->d_tw_fused, d_y, _q->M,
-                                                               _q->p, _n_frames, _n_streams, stride, st);
-    if (done < _n_frames) {
-        for (unsigned int s = 0; s < _n_streams; s++) {
-            float2 *ys = d_y + s * stride + done * _q->M;
-            lc::pfb::launch_pfbch_mac(_q->d_zero, d_x + s * stride, (int)_q->H, _q->d_taps, ys, _q->M, _q->p,
-                                      _n_frames - done, 0, (unsigned int)((done + 1) * _q->M), 0, st);
-            _q->fft.run(ys, ys, _n_frames - done, st);
+    if (_q->type == LIQUID_ANALYZER) {
+        if (ok)
+            done = (unsigned long long)lc::pfb::launch_pfbch_fused(nullptr, d_x, 0, _q->d_taps, _q->d_tw_fused, d_y, M, p,
+                                                                   _n_frames, _n_streams, stride, st);
+        if (done < _n_frames) {
+            for (unsigned int s = 0; s < _n_streams; s++) {
+                float2 *ys = d_y + s * stride + done * M;
+                lc::pfb::launch_pfbch_mac(_q->d_zero, d_x + s * stride, (int)_q->H, _q->d_taps, ys, M, p,
+                                          _n_frames - done, 0, (unsigned int)((done + 1) * M), 0, st);
+                _q->fft.run(ys, ys, _n_frames - done, st);
+            }
+        }
+    } else {
+        if (ok)
+            done = (unsigned long long)lc::pfb::launch_pfbch_synth_fused(nullptr, 0, d_x, _q->d_taps, _q->d_tw_fused, d_y, M, p,
+                                                                         _n_frames, _n_streams, stride, st);
+        if (done < _n_frames) {
+            const unsigned long long v0 = (done > p) ? done - p : 0;
+            float2 *d_v = (float2 *)_q->scratch.get(sizeof(float2) * (_n_frames - v0 + p) * M);
+            for (unsigned int s = 0; s < _n_streams; s++) {
+                _q->fft.run(d_x + s * stride + v0 * M, d_v, _n_frames - v0, st);
+                const float2 *hist_rows = (done == 0) ? _q->d_zero : d_v + (done - v0 - p) * M;
+                lc::pfb::launch_pfbch_synth_fir(hist_rows, d_v + (done - v0) * M, (int)p, _q->d_taps,
+                                                d_y + s * stride + done * M, M, p, _n_frames - done, st);
+            }
         }
     }
 }

@@ -191,6 +191,98 @@ __global__ void __launch_bounds__(kThreads) pfbch_fused_256_kernel(const PfbArgs
     }
 }
 
+// ------------------------------------------------------------------------------------------ M = 256 synthesis
+// firpfbch.c:314-336: v_s = unscaled backward DFT of frame s; y[sM + i] = sum_n h[i + nM] v_{s-n}[i].
+//   phase A  16 threads per frame: the 256-point backward DFT straight from global memory (two passes of
+//            16-point register DFTs, transposition through the padded tile), result rows left in the tile
+//   phase B  thread i owns branch i: a register window of p-1+16 rows of v[.][i] and its p taps; 16 outputs
+//            per tile, stored as coalesced rows.
+// An instance that starts inside the stream first transforms the 16 frames before its range to rebuild the
+// p-1 rows of history (6 % extra transforms at 256 frames per instance); the first instance takes them
+// from the object's state (or zeros).
+struct SynArgs {
+    const float2 *hist_rows;   // hist_rows rows of v preceding frame 0 (single-stream stateful use), or null
+    const float2 *x;           // [n_streams][stream_stride] channelised input frames
+    float2 *y;
+    const float *taps;         // [P][M]: taps[n][i] = h[i + nM]
+    const float2 *tw;          // tw[k1][r2] = e^{+j 2 pi k1 r2 / 256}
+    int n_hist_rows;
+    int n_tiles;
+    int tiles_per_inst;
+    long long stream_stride;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kThreads) pfbch_synth_fused_256_kernel(const SynArgs a)
+{
+    constexpr int M = 256;
+    constexpr int FR = 16 * 17;
+    __shared__ float2 tile[kTile * FR];
+
+    const int u = threadIdx.x;
+    const int t0 = (int)((long long)blockIdx.x * a.tiles_per_inst);
+    int nt = a.n_tiles - t0;
+    if (nt > a.tiles_per_inst) nt = a.tiles_per_inst;
+    const float2 *x = a.x + (long long)blockIdx.y * a.stream_stride;
+    float2 *y = a.y + (long long)blockIdx.y * a.stream_stride;
+
+    float h[P];
+#pragma unroll
+    for (int n = 0; n < P; n++) h[n] = __ldg(a.taps + n * M + u);
+    float2 win[P - 1 + kTile];
+    const int f2 = u >> 4, r2 = u & 15;
+    const float2 *twp = a.tw + r2;
+
+    // phase A for the 16 frames starting at frame s0: rows of v left in tile[f*FR + 0..255]
+    auto transform_tile = [&](long long s0) {
+        float2 *fr = tile + f2 * FR;
+        const float2 *xf = x + (s0 + f2) * M + r2;
+        float2 v[16];
+#pragma unroll
+        for (int r1 = 0; r1 < 16; r1++) v[r1] = __ldg(xf + 16 * r1);
+        RegDft<16, +1>::run(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul2(v[k1], __ldg(twp + 16 * k1));
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) fr[r2 * 17 + k1] = v[k1];
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 16; c++) v[c] = fr[c * 17 + r2];
+        RegDft<16, +1>::run(v);
+        __syncwarp();                                      // the group has read everything it transposed
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) fr[r2 + 16 * k2] = v[k2];     // v[f][k1 + 16 k2], natural order
+    };
+
+    if (t0 > 0) {
+        transform_tile((long long)t0 * kTile - kTile);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < P - 1; i++) win[i] = tile[(kTile - (P - 1) + i) * FR + u];
+        __syncthreads();
+    } else {
+#pragma unroll
+        for (int i = 0; i < P - 1; i++) {
+            const int r = a.n_hist_rows - (P - 1) + i;
+            win[i] = (a.hist_rows != nullptr && r >= 0) ? __ldg(a.hist_rows + (long long)r * M + u) : make_float2(0.f, 0.f);
+        }
+    }
+    for (int it = 0; it < nt; it++) {
+        const long long s0 = (long long)(t0 + it) * kTile;
+        transform_tile(s0);
+        __syncthreads();
+#pragma unroll
+        for (int f = 0; f < kTile; f++) win[P - 1 + f] = tile[f * FR + u];
+        float2 out[kTile];
+        mac_tile<M, P>(h, win, out);
+#pragma unroll
+        for (int f = 0; f < kTile; f++) __stcs(y + (s0 + f) * M + u, out[f]);
+#pragma unroll
+        for (int i = 0; i < P - 1; i++) win[i] = win[kTile + i];
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 namespace lc {
@@ -201,12 +293,17 @@ bool fused_pfbch_supported(unsigned int M, unsigned int p)
     return (M == 16 && (p == 4 || p == 8)) || (M == 256 && (p == 4 || p == 10));
 }
 
-void fused_pfbch_make_twiddles(std::vector<float2> &tw)
+bool fused_pfbch_synth_supported(unsigned int M, unsigned int p)
+{
+    return M == 256 && (p == 4 || p == 10);
+}
+
+void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign)
 {
     tw.resize(16 * 16);
     for (int k1 = 0; k1 < 16; k1++)
         for (int r2 = 0; r2 < 16; r2++) {
-            double ang = -2.0 * M_PI * (double)(k1 * r2) / 256.0;
+            double ang = (double)sign * 2.0 * M_PI * (double)(k1 * r2) / 256.0;
             tw[k1 * 16 + r2] = make_float2((float)cos(ang), (float)sin(ang));
         }
 }
@@ -239,6 +336,34 @@ long long launch_pfbch_fused(const float2 *d_hist, const float2 *d_x, int H, con
     else if (M == 256 && p == 4) pfbch_fused_256_kernel<4><<<grid, kThreads, 0, st>>>(a);
     else if (M == 256 && p == 10) pfbch_fused_256_kernel<10><<<grid, kThreads, 0, st>>>(a);
     else fatal("launch_pfbch_fused", "unsupported shape");
+    LC_LAUNCH_CHECK();
+    return n_tiles * kTile;
+}
+
+long long launch_pfbch_synth_fused(const float2 *d_hist_rows, int n_hist_rows, const float2 *d_x, const float *d_taps,
+                                   const float2 *d_tw, float2 *d_y, unsigned int M, unsigned int p,
+                                   unsigned long long n_frames, unsigned int n_streams, long long stream_stride,
+                                   cudaStream_t st)
+{
+    (void)M;
+    const long long n_tiles = (long long)(n_frames / kTile);
+    if (n_tiles == 0 || n_tiles > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;
+    SynArgs a;
+    a.hist_rows = d_hist_rows;
+    a.n_hist_rows = n_hist_rows;
+    a.x = d_x;
+    a.y = d_y;
+    a.taps = d_taps;
+    a.tw = d_tw;
+    a.n_tiles = (int)n_tiles;
+    a.stream_stride = stream_stride;
+    long long tpi = 16;
+    while (tpi > 1 && (n_tiles / tpi) * n_streams < 148ll * 8) tpi >>= 1;
+    a.tiles_per_inst = (int)tpi;
+    dim3 grid((unsigned int)((n_tiles + tpi - 1) / tpi), n_streams, 1);
+    if (p == 4) pfbch_synth_fused_256_kernel<4><<<grid, kThreads, 0, st>>>(a);
+    else if (p == 10) pfbch_synth_fused_256_kernel<10><<<grid, kThreads, 0, st>>>(a);
+    else fatal("launch_pfbch_synth_fused", "unsupported shape");
     LC_LAUNCH_CHECK();
     return n_tiles * kTile;
 }

@@ -441,3 +441,28 @@ def test_pfbch_streams_dev(L, orc, M, m):
     for s in range(n_streams):
         want = orc.Firpfbch(orc.ANALYZER, M, kaiser=(m, 60.0)).execute_frames(x[s])
         assert np.abs(got[s].reshape(nfr, M) - want).max() / np.abs(want).max() < 1e-5
+
+
+@pytest.mark.parametrize("M,m,nfr", [(256, 5, 16 * 40 + 9), (256, 2, 16 * 33), (64, 3, 50)])
+def test_pfbch_synthesis_fused_and_streams(L, orc, M, m, nfr):
+    """fused M=256 synthesizer (many tiles / instances, tail, state carry) and the multi-stream form"""
+    import ctypes as C
+    X = orc.synth_input(nfr * M, seed=0xC5 + M + m)
+    want = orc.Firpfbch(orc.SYNTHESIZER, M, kaiser=(m, 60.0)).execute_frames(X)
+    q = L.firpfbch_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+    cut = 16 * 2 + 5
+    got = np.concatenate([q.execute_block(X[:cut * M]), q.execute_block(X[cut * M:cut * M + 3 * M]),
+                          q.execute_block(X[(cut + 3) * M:])])
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+    n_streams = 3
+    xs = orc.synth_input(n_streams * nfr * M, seed=0xC9).reshape(n_streams, nfr * M)
+    d_x = L.lib.liquid_cuda_malloc(xs.nbytes); d_y = L.lib.liquid_cuda_malloc(xs.nbytes)
+    L.lib.liquid_cuda_memcpy_h2d(d_x, xs.ctypes.data_as(C.c_void_p), xs.nbytes)
+    q.execute_streams_dev(d_x, n_streams, nfr, d_y, 0)
+    L.lib.liquid_cuda_sync()
+    out = np.empty_like(xs)
+    L.lib.liquid_cuda_memcpy_d2h(out.ctypes.data_as(C.c_void_p), d_y, xs.nbytes)
+    L.lib.liquid_cuda_free(d_x); L.lib.liquid_cuda_free(d_y)
+    for s in range(n_streams):
+        w = orc.Firpfbch(orc.SYNTHESIZER, M, kaiser=(m, 60.0)).execute_frames(xs[s])
+        assert np.abs(out[s].reshape(nfr, M) - w).max() / np.abs(w).max() < 1e-5

@@ -86,10 +86,8 @@ def main():
         L.synth_input_dev(x.data_ptr(), ns * n, stream=st.cuda_stream)
 
         def rt():
-            for s in range(ns):
-                off = 8 * s * n
-                qs[s].execute_block_dev(x.data_ptr() + off, n // M, t.data_ptr() + off, st.cuda_stream)
-            # analysis half: all streams in one launch (stateless multi-stream form)
+            # all streams of each half in one launch (stateless multi-stream form)
+            qs[0].execute_streams_dev(x.data_ptr(), ns, n // M, t.data_ptr(), st.cuda_stream)
             qa[0].execute_streams_dev(t.data_ptr(), ns, n // M, y.data_ptr(), st.cuda_stream)
         ms, ln = timed(rt)
         report("c4: firpfbch_crcf synthesis+analysis round trip M=256 m=5, 32 streams x 2^22 samples", ns * n, 32, ms, ln)
