@@ -17,6 +17,7 @@
 #include "pfb_kernels.cuh"
 #include "host_pipeline.cuh"
 #include "pfbch2_fused.cuh"
+#include "pfbch2_cluster.cuh"
 
 struct firpfbch2_crcf_s {
     int type;
@@ -26,7 +27,8 @@ struct firpfbch2_crcf_s {
     float *d_taps = nullptr;       // analyzer: [2][L][M] (parity, tap, window); synthesizer: [4m][M/2]
     float *d_taps_scaled = nullptr;// analyzer, fused kernel only: d_taps * (1/M)
     float2 *d_tw_fused = nullptr;  // fused kernel's inter-stage twiddles
-    bool fused = false;
+    bool fused = false;            // M = 1024: one CTA per frame (pfbch2_fused.cu)
+    bool clustered = false;        // M = 4096: one frame per cluster of 8 CTAs (pfbch2_cluster.cu)
     float2 *d_hist = nullptr;      // last H samples (analyzer: inputs; synthesizer: scaled IDFT rows)
     int flag = 0;                  // frame parity (firpfbch2.c:57)
     lc::FftPlanDev fft;            // M-point backward transform
@@ -45,6 +47,9 @@ void analyze_dev(firpfbch2_crcf q, const float2 *d_hist, const float2 *d_x, int 
     if (q->fused && n_frames >= 32 && ((uintptr_t)d_x % 16) == 0 && !getenv("LIQUID_CUDA_NO_FUSED"))
         done = (unsigned long long)lc::pfb::launch_pfbch2_fused(d_hist, d_x, (int)q->H, q->d_taps_scaled, q->d_tw_fused,
                                                                 d_y, q->M, q->L, n_frames, parity0, st);
+    else if (q->clustered && n_frames >= 32 && !getenv("LIQUID_CUDA_NO_FUSED"))
+        done = (unsigned long long)lc::pfb::launch_pfbch2_cluster(d_hist, d_x, (int)q->H, q->d_taps_scaled, q->d_tw_fused,
+                                                                  d_y, q->M, q->L, n_frames, parity0, st);
     if (done == n_frames) return;
     // shape-generic path (and the 0..3 frames the fused kernel leaves): polyphase MAC into the
     // output buffer, then an in-place batched backward FFT with /M
@@ -111,17 +116,21 @@ firpfbch2_crcf firpfbch2_crcf_create(int _type, unsigned int _M, unsigned int _m
     }
     LC_CUDA_CHECK(cudaMalloc(&q->d_taps, taps.size() * sizeof(float)));
     LC_CUDA_CHECK(cudaMemcpy(q->d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
-    if (_type == LIQUID_ANALYZER && lc::pfb::fused_pfbch2_supported(M, L)) {
-        // the fused kernel folds the 1/M output scale into the taps (exact: M is a power of two)
+    const bool want_fused = _type == LIQUID_ANALYZER && lc::pfb::fused_pfbch2_supported(M, L);
+    const bool want_cluster = _type == LIQUID_ANALYZER && lc::pfb::cluster_pfbch2_supported(M, L);
+    if (want_fused || want_cluster) {
+        // the fused kernels fold the 1/M output scale into the taps (exact: M is a power of two)
         std::vector<float> ts(taps);
         for (float &v : ts) v *= 1.0f / (float)M;
         LC_CUDA_CHECK(cudaMalloc(&q->d_taps_scaled, ts.size() * sizeof(float)));
         LC_CUDA_CHECK(cudaMemcpy(q->d_taps_scaled, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice));
         std::vector<float2> tw;
-        lc::pfb::fused_pfbch2_make_twiddles(tw);
+        if (want_fused) lc::pfb::fused_pfbch2_make_twiddles(tw);
+        else            lc::pfb::cluster_pfbch2_make_twiddles(tw);
         LC_CUDA_CHECK(cudaMalloc(&q->d_tw_fused, tw.size() * sizeof(float2)));
         LC_CUDA_CHECK(cudaMemcpy(q->d_tw_fused, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        q->fused = true;
+        q->fused = want_fused;
+        q->clustered = want_cluster;
     }
     LC_CUDA_CHECK(cudaMalloc(&q->d_hist, sizeof(float2) * q->H));
     q->fft.init(M, +1);                            // backward, unscaled (firpfbch2.c:115)

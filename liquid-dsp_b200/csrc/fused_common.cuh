@@ -147,4 +147,52 @@ struct RegDft<1, SIGN> {
     static __device__ __forceinline__ void run(float2 (&)[1]) {}
 };
 
+// ---------------------------------------------------------------------------------- firpfbch2 MAC state
+// MAC state of one window pair (w, w+M/2) of the firpfbch2 analyzer: histories and branches, all in
+// registers.  The pair receives stream sample F*M/2 + M/2-1-w on frame F; the window pushed on even
+// local frames keeps its 2m samples in dA, the one pushed on odd local frames in dB (circular, slot
+// index = double frame mod L).
+template <int L>
+struct PairState {
+    float hA[L], hB[L];        // taps of branch w and branch w+M/2 (tap n multiplies the n-th newest sample)
+    float2 dA[L], dB[L];       // circular histories of the window pushed on even / odd local frames
+};
+
+// taps: analyzer table [2][L][M] (parity, tap, window), f_begin: first (even-local) frame of the range
+template <int L, int M>
+__device__ __forceinline__ void pair_load(PairState<L> &s, const float *__restrict__ taps,
+                                          const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                                          int w, long long f_begin)
+{
+    constexpr int M2 = M / 2;
+#pragma unroll
+    for (int n = 0; n < L; n++) {
+        s.hA[n] = __ldg(taps + (size_t)n * M + w);                // parity-0 table: window w -> branch w
+        s.hB[n] = __ldg(taps + (size_t)n * M + w + M2);           // window w+M/2 -> branch w+M/2
+    }
+    // history: the pair's sample of frame F is stream index F*M/2 + M/2-1 - w
+    const long long base = f_begin * M2 + (M2 - 1 - w);
+#pragma unroll
+    for (int n = 1; n < L; n++) s.dA[L - n] = lcd::ld_stream(hist, x, base - 2LL * n * M2, H);
+    s.dA[0] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int n = 0; n < L; n++) s.dB[L - 1 - n] = lcd::ld_stream(hist, x, base - (1LL + 2 * n) * M2, H);
+}
+
+// the two dot products of a pair on the even (ODD = 0) or odd (ODD = 1) frame of double frame uu:
+// o1 belongs to the window pushed on even frames, o2 to the one pushed on odd frames
+template <int L, int ODD>
+__device__ __forceinline__ void pair_mac(const PairState<L> &s, int uu, float2 &o1, float2 &o2)
+{
+    o1 = make_float2(0.f, 0.f);
+    o2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int n = L - 1; n >= 0; n--) {
+        const float2 s1 = s.dA[(uu - n + L) % L];
+        const float2 s2 = s.dB[(uu - (ODD ? 0 : 1) - n + 2 * L) % L];
+        o1 = __ffma2_rn(bc(ODD ? s.hB[n] : s.hA[n]), s1, o1);
+        o2 = __ffma2_rn(bc(ODD ? s.hA[n] : s.hB[n]), s2, o2);
+    }
+}
+
 }  // namespace lcf

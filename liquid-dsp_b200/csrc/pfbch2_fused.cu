@@ -79,46 +79,6 @@ struct FusedArgs {
 // unit (float2) offset of element r of a 256-point sub-problem: rows of 16 padded to 17
 __device__ __forceinline__ constexpr int sub_unit(int r) { return r + (r >> 4); }
 
-// MAC state of one window pair (w, w+512): histories and branches, all in registers
-template <int L>
-struct PairState {
-    float hA[L], hB[L];        // taps of branch w and branch w+512 (tap n multiplies the n-th newest sample)
-    float2 dA[L], dB[L];       // circular histories of the window pushed on even / odd local frames
-};
-
-template <int L>
-__device__ __forceinline__ void pair_load(PairState<L> &s, const FusedArgs &a, int w, long long f_begin)
-{
-#pragma unroll
-    for (int n = 0; n < L; n++) {
-        s.hA[n] = __ldg(a.taps + (size_t)n * kM + w);              // parity-0 table: window w -> branch w
-        s.hB[n] = __ldg(a.taps + (size_t)n * kM + w + kM2);        // window w+512 -> branch w+512
-    }
-    // history: the pair's sample of frame F is stream index F*512 + 511 - w
-    const long long base = f_begin * kM2 + (kM2 - 1 - w);
-#pragma unroll
-    for (int n = 1; n < L; n++) s.dA[L - n] = lcd::ld_stream(a.hist, a.x, base - 2LL * n * kM2, a.H);
-    s.dA[0] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int n = 0; n < L; n++) s.dB[L - 1 - n] = lcd::ld_stream(a.hist, a.x, base - (1LL + 2 * n) * kM2, a.H);
-}
-
-// the two dot products of a pair on the even (ODD = 0) or odd (ODD = 1) frame of double frame uu:
-// o1 belongs to the window pushed on even frames, o2 to the one pushed on odd frames
-template <int L, int ODD>
-__device__ __forceinline__ void pair_mac(const PairState<L> &s, int uu, float2 &o1, float2 &o2)
-{
-    o1 = make_float2(0.f, 0.f);
-    o2 = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int n = L - 1; n >= 0; n--) {
-        const float2 s1 = s.dA[(uu - n + L) % L];
-        const float2 s2 = s.dB[(uu - (ODD ? 0 : 1) - n + 2 * L) % L];
-        o1 = __ffma2_rn(bc(ODD ? s.hB[n] : s.hA[n]), s1, o1);
-        o2 = __ffma2_rn(bc(ODD ? s.hA[n] : s.hB[n]), s2, o2);
-    }
-}
-
 // radix-4 DIF butterfly over the four windows of a thread + the three twiddles, stored as four
 // 256-point sub-problems z_p[j], p = 0..3 (slot = this thread's address inside sub-problem 0)
 __device__ __forceinline__ void radix4_store(uint32_t slot, float2 a0, float2 a1, float2 a2, float2 a3,
@@ -180,8 +140,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
         asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
         const int j = tid;                                  // windows j, j+256, j+512, j+768
         PairState<L> s0, s1;                                // pairs (j, j+512) and (j+256, j+768)
-        pair_load(s0, a, j, f_begin);
-        pair_load(s1, a, j + 256, f_begin);
+        pair_load<L, kM>(s0, a.taps, a.hist, a.x, a.H, j, f_begin);
+        pair_load<L, kM>(s1, a.taps, a.hist, a.x, a.H, j + 256, f_begin);
         // this thread's two samples inside a staged frame, its z_0 element inside a frame slot, its twiddles
         const uint32_t in_thr = s_in + (uint32_t)(kM2 - 1 - j) * 8;       // pair 1 sits 256 samples lower
         const uint32_t x_thr = s_x + (uint32_t)sub_unit(j) * 8;

@@ -405,6 +405,42 @@ def test_pfbch2_fused_matches_generic_path(L, orc, monkeypatch):
     assert np.abs(fused - generic).max() < 1e-6
 
 
+# ------------------------------------------------------------------ cluster-of-8 M=4096 kernel specifics
+@pytest.mark.parametrize("m", [4, 7, 9])
+def test_pfbch2_cluster_4096_vs_oracle_odd_splits(L, orc, m):
+    """the cluster kernel (M=4096, one frame per 8 CTAs, DSMEM exchange) across: odd start parity,
+    frame counts that are not a multiple of the 4-frame group, several clusters, state carried
+    between calls"""
+    M = 4096
+    nfr = 33 + 61 + 170
+    x = orc.synth_input(nfr * M // 2, seed=0xC0 + m)
+    want = orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0).execute_frames(x)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    got = np.concatenate([q.execute_block(x[:33 * 2048]), q.execute_block(x[33 * 2048:94 * 2048]),
+                          q.execute_block(x[94 * 2048:])])
+    check_channels(got, want, x)
+    q.reset()
+    whole = q.execute_block(x)
+    check_channels(whole, want, x)
+    assert np.abs(whole - got).max() < 1e-6
+
+
+def test_pfbch2_cluster_matches_generic_path(L, orc, monkeypatch):
+    """many groups per cluster (ring wrap-around, credits) against the two-kernel generic path"""
+    M, m = 4096, 9
+    x = orc.synth_input(3000 * M // 2, seed=0xCE)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    launches0 = L.launch_count()
+    fused = q.execute_block(x)
+    q.reset()
+    monkeypatch.setenv("LIQUID_CUDA_NO_FUSED", "1")
+    generic = q.execute_block(x)
+    monkeypatch.delenv("LIQUID_CUDA_NO_FUSED")
+    assert rel_rms_per_channel(fused, generic).max() < 2e-6
+    assert np.abs(fused - generic).max() < 1e-6
+    assert L.launch_count() > launches0
+
+
 # ------------------------------------------------------------------ fused firpfbch analysis kernels
 @pytest.mark.parametrize("M,m,nfr", [(16, 4, 16 * 37 + 5), (16, 2, 16 * 300), (256, 5, 16 * 21 + 3), (256, 2, 16 * 40)])
 def test_pfbch_fused_analysis_vs_oracle_and_generic(L, orc, monkeypatch, M, m, nfr):
