@@ -103,21 +103,9 @@ __device__ __forceinline__ void st_async64(uint32_t raddr, float2 v, uint32_t rb
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
-}
-// wait that also orders against writes made by other CTAs of the cluster
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAITC_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAITC_DONE;\n\t"
-        "bra WAITC_LOOP;\n\t"
-        "WAITC_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity)
-        : "memory");
+    // relaxed: the credit only guards a write-after-read hazard and is issued after the values read from
+    // the slot have been consumed (a release here costs MEMBAR.ALL.GPU + ERRBAR per arrive)
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
 }
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
 {
@@ -191,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
         PairState<L> s;
         pair_load<L, kM>(s, a.taps, a.hist, a.x, a.H, j, f_begin);
         const float2 *src = a.x + f_begin * kM2 + (kM2 - 1 - j);         // this pair's sample of local frame 0
-        const uint32_t in_thr = s_in + (uint32_t)tid * 8;                 // + (2 * dslot + odd) * 2048
+        const uint32_t in_thr = s_in + (uint32_t)(tid ^ 7) * 8;           // stream order inside a 64-byte run; + (2 * dslot + odd) * 2048
         const uint32_t x_thr = s_x + (uint32_t)(n0l * kXStride + n1 + (n1 >> 3)) * 8;   // X[n0][n1]; X[n0][n1+32] is 36 units on
         const int n_dbl = n_frames / 2;
 
@@ -258,7 +246,9 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
         const int n0l = n0_of(h, i);
         const uint32_t p1_col = (uint32_t)(n0l * kXStride + q) * 8;          // cell (p, q): + 9 p units
         const uint32_t p1_row = (uint32_t)(n0l * kXStride + 9 * q) * 8;      // cell (r = q, qq): + qq units
-        const uint32_t tw64_lane = s_tw64 + (uint32_t)q * 64;                // tw64[q][r] at + 8 r
+        float2 tw_p1[8];                                                     // W64^(q r), r = 1..7
+#pragma unroll
+        for (int r = 1; r < 8; r++) tw_p1[r] = lds64(s_tw64 + (uint32_t)(q * 8 + r) * 8);
         float2 tw_z[8];                                                      // W4096^(n0 (q + 8 s)), s = 0..7
 #pragma unroll
         for (int s = 0; s < 8; s++) tw_z[s] = __ldg(a.tw + 64 + (8 * crank + n0l) * 64 + q + 8 * s);
@@ -272,7 +262,9 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
                                 : ((z == 0) ? 2 : (z == 1) ? 7 : (z == 2) ? 3 : 6);
         const uint32_t p2_col = (uint32_t)(recv_pos(qp) + q) * 8;            // cell (p', q'): + 72 p' units
         const uint32_t p2_row = (uint32_t)(qp * kRecvStride + q) * 8;        // cell (r2 = q', q''): + recv_pos(q'') units
-        const uint32_t tw64_p2 = s_tw64 + (uint32_t)qp * 64;
+        float2 tw_p2[8];                                                     // W64^(q' r2), r2 = 1..7
+#pragma unroll
+        for (int r = 1; r < 8; r++) tw_p2[r] = lds64(s_tw64 + (uint32_t)(qp * 8 + r) * 8);
         float2 *y_thr = a.y + f_begin * (long long)kM + (8 * crank + q) + 64 * qp;   // + frame * 4096 + 512 s2
 
         for (int it = 0; it < n_groups + kLag; it++) {
@@ -287,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
                 for (int p = 0; p < 8; p++) v[p] = lds64(slot + p1_col + (uint32_t)(9 * p) * 8);
                 RegDft<8, +1>::run(v);
 #pragma unroll
-                for (int r = 1; r < 8; r++) v[r] = cmul2(v[r], lds64(tw64_lane + 8 * r));
+                for (int r = 1; r < 8; r++) v[r] = cmul2(v[r], tw_p1[r]);
                 // in-place transposition: this thread rewrites exactly the cells it read
 #pragma unroll
                 for (int r = 0; r < 8; r++) sts64(slot + p1_col + (uint32_t)(9 * r) * 8, v[r]);
@@ -300,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
                 // receive slot of frame f in every CTA; wait until all 8 receivers have handed it back
                 const int rs = (it & (kRecvGroups - 1)) * kGroup + fp;
                 const uint32_t use = (uint32_t)it / kRecvGroups;
-                if (use > 0) mbar_wait_cluster(bar_recv_free(rs), (use - 1u) & 1u);
+                if (use > 0) mbar_wait(bar_recv_free(rs), (use - 1u) & 1u);
                 const uint32_t dst = send_off + (uint32_t)rs * (kRecvSlotUnits * 8);
                 const uint32_t dbar = (uint32_t)kOffBar + 8u * (2 * kXSlots + rs);
 #pragma unroll
@@ -315,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
                 const int rs = (g & (kRecvGroups - 1)) * kGroup + fp;
                 const uint32_t use = (uint32_t)g / kRecvGroups;
                 const uint32_t slot = s_recv + (uint32_t)rs * (kRecvSlotUnits * 8);
-                mbar_wait_cluster(bar_recv_full(rs), use & 1u);
+                mbar_wait(bar_recv_full(rs), use & 1u);
                 // re-arm the slot for its next use (bytes can only arrive after the credits below)
                 if (h == 0 && lane == 0) mbar_arrive_expect_tx(bar_recv_full(rs), kFrameBytes);
                 float2 v[8];
@@ -323,17 +315,18 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
                 for (int p = 0; p < 8; p++) v[p] = lds64(slot + p2_col + (uint32_t)(kRecvStride * p) * 8);
                 RegDft<8, +1>::run(v);
 #pragma unroll
-                for (int r = 1; r < 8; r++) v[r] = cmul2(v[r], lds64(tw64_p2 + 8 * r));
+                for (int r = 1; r < 8; r++) v[r] = cmul2(v[r], tw_p2[r]);
 #pragma unroll
                 for (int r = 0; r < 8; r++) sts64(slot + p2_col + (uint32_t)(kRecvStride * r) * 8, v[r]);
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + fp) : "memory");   // the DFT of one k1 spans both warps
 #pragma unroll
                 for (int qq = 0; qq < 8; qq++) v[qq] = lds64(slot + p2_row + (uint32_t)recv_pos(qq) * 8);
+                RegDft<8, +1>::run(v);
                 __syncwarp();
-                // hand the slot back to the 8 senders: lane s credits CTA s
+                // hand the slot back to the 8 senders (every value read from it has been consumed by the
+                // DFT above): lane s credits CTA s
                 if (lane < kCluster)
                     mbar_arrive_remote(rbase + (uint32_t)lane * rstep + (uint32_t)kOffBar + 8u * (2 * kXSlots + kRecvSlots + rs));
-                RegDft<8, +1>::run(v);
                 float2 *yf = y_thr + (long long)(g * kGroup + fp) * kM;
 #pragma unroll
                 for (int s2 = 0; s2 < 8; s2++) __stcs(yf + 512 * s2, v[s2]);
