@@ -15,7 +15,7 @@ void cluster_pfbch2_make_twiddles(std::vector<float2> &tw);
 // clusters of 8 CTAs the device keeps resident (-1 before the first launch, 0 = cannot be scheduled)
 int cluster_pfbch2_max_clusters();
 
-// Runs the kernel over the largest multiple of 4 frames <= n_frames and returns how many frames it
+// Runs the kernel over the largest multiple of 8 frames <= n_frames and returns how many frames it
 // covered (0 when clusters of 8 cannot be scheduled; the caller finishes the rest with the generic
 // kernels).  d_taps_scaled: analyzer tap table [2][L][M] already multiplied by 1/M.
 long long launch_pfbch2_cluster(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps_scaled,
