@@ -195,4 +195,24 @@ __device__ __forceinline__ void pair_mac(const PairState<L> &s, int uu, float2 &
     }
 }
 
+// same dot products with two accumulators per output (even / odd taps, summed at the end): four
+// independent FFMA2 chains for a thread that owns a single pair
+template <int L, int ODD>
+__device__ __forceinline__ void pair_mac_split(const PairState<L> &s, int uu, float2 &o1, float2 &o2)
+{
+    static_assert(L % 2 == 0, "tap count per branch is 2m");
+    float2 e1 = make_float2(0.f, 0.f), e2 = e1, f1 = e1, f2 = e1;
+#pragma unroll
+    for (int n = L - 1; n >= 1; n -= 2) {
+        const float2 a1 = s.dA[(uu - n + L) % L], b1 = s.dA[(uu - (n - 1) + L) % L];
+        const float2 a2 = s.dB[(uu - (ODD ? 0 : 1) - n + 2 * L) % L], b2 = s.dB[(uu - (ODD ? 0 : 1) - (n - 1) + 2 * L) % L];
+        e1 = __ffma2_rn(bc(ODD ? s.hB[n] : s.hA[n]), a1, e1);
+        e2 = __ffma2_rn(bc(ODD ? s.hA[n] : s.hB[n]), a2, e2);
+        f1 = __ffma2_rn(bc(ODD ? s.hB[n - 1] : s.hA[n - 1]), b1, f1);
+        f2 = __ffma2_rn(bc(ODD ? s.hA[n - 1] : s.hB[n - 1]), b2, f2);
+    }
+    o1 = __fadd2_rn(e1, f1);
+    o2 = __fadd2_rn(e2, f2);
+}
+
 }  // namespace lcf

@@ -71,9 +71,9 @@ constexpr int kOffBarRecvFull = 0;                             // [kRecvSlots]
 constexpr int kOffBarRecvFree = kOffBarRecvFull + 8 * kRecvSlots;
 constexpr int kOffBarXFull = kOffBarRecvFree + 8 * kRecvSlots; // [XS]
 constexpr int kOffBarXEmpty = kOffBarXFull + 8 * kMaxXS;       // [XS]
-constexpr int kOffTw8 = 1024;                                  // float4 tw8[8][8]: W64^(q r) as {c, -s, s, 0} at [r][q]
-constexpr int kOffTz = kOffTw8 + 64 * 16;                      // float4 tz[2][8][32]: W4096^(n0 k1) of (half, s, lane)
-constexpr int kOffRecv = kOffTz + 2 * 8 * 32 * 16;
+constexpr int kOffTw8 = 1024;                                  // float2 tw8[8][8]: W64^(q r) at [r][q]
+constexpr int kOffTz = kOffTw8 + 64 * 8;                       // float2 tz[2][8][32]: W4096^(n0 k1) of (half, s, lane)
+constexpr int kOffRecv = kOffTz + 2 * 8 * 32 * 8;
 constexpr int kOffX = kOffRecv + kRecvSlots * kRecvSlotUnits * 8;
 template <int L> struct Smem {
     static constexpr int kOffIn = kOffX + Rings<L>::XS * kXSlotUnits * 8;
@@ -86,7 +86,7 @@ struct ClusterArgs {
     const float2 *x;           // segment input
     float2 *y;                 // [n_frames][4096]
     const float *taps;         // [2][L][4096] as in firpfbch2.cu, pre-scaled by 1/M
-    const float2 *tw;          // float4 tw8[8][8] (128 float2) followed by float2 tw4096[64][64] (n0, k1)
+    const float2 *tw;          // tw8[8][8] (r, q) followed by tw4096[64][64] (n0, k1)
     int H;
     int n_groups;              // groups of 8 frames in the segment
     int groups_per_cluster;
@@ -146,11 +146,10 @@ __device__ __forceinline__ float2 cmul3(float2 a, float c, float2 ms_s)
 {
     return __ffma2_rn(ms_s, make_float2(a.y, a.x), __fmul2_rn(bc(c), a));
 }
-__device__ __forceinline__ float4 lds128(uint32_t addr)
+// same with the twiddle as loaded from a {c, s} table: the {-s, s} pair costs one integer sign flip (ALU pipe)
+__device__ __forceinline__ float2 cmul_cs(float2 a, float2 t)
 {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
+    return cmul3(a, t.x, make_float2(__int_as_float(__float_as_int(t.y) ^ (int)0x80000000), t.y));
 }
 
 template <int L, int PAR0>
@@ -185,13 +184,13 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
     const long long f_begin = (long long)g_begin * kGroup; // first frame of this cluster (even)
 
     // ---- one-time setup
-    if (tid < 128) reinterpret_cast<float2 *>(smem + kOffTw8)[tid] = a.tw[tid];
+    if (tid < 64) reinterpret_cast<float2 *>(smem + kOffTw8)[tid] = a.tw[tid];
     {
         // tz[half][s][lane]: the phase-1 output twiddle W4096^(n0 k1) of FFT lane (i, q) in half `half`:
-        // n0 = 8c + n0_of(half, i), k1 = q + 8 s; stored as {c, -s, s, 0}
+        // n0 = 8c + n0_of(half, i), k1 = q + 8 s
         const int half = tid >> 8, sd = (tid >> 5) & 7, ln = tid & 31;
-        const float2 t = __ldg(a.tw + 128 + (8 * crank + n0_of(half, ln >> 3)) * 64 + (ln & 7) + 8 * sd);
-        reinterpret_cast<float4 *>(smem + kOffTz)[tid] = make_float4(t.x, -t.y, t.y, 0.0f);
+        reinterpret_cast<float2 *>(smem + kOffTz)[tid] =
+            __ldg(a.tw + 64 + (8 * crank + n0_of(half, ln >> 3)) * 64 + (ln & 7) + 8 * sd);
     }
     if (tid == 0) {
         for (int s = 0; s < XS; s++) {
@@ -259,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
                 {
                     const int fl = 2 * uu, xs = fl % XS;              // constants after unrolling
                     s.dA[uu] = xe;
-                    pair_mac<L, 0>(s, uu, o1, o2);
+                    pair_mac_split<L, 0>(s, uu, o1, o2);
                     mbar_wait(bar_x_empty(xs), (pk ^ (uint32_t)((fl / XS) & 1)) ^ 1u);
                     const uint32_t xa = x_thr + (uint32_t)xs * (kXSlotUnits * 8);
                     // o1 is window j when the segment starts on an even frame (PAR0 = 0), window j + 2048 otherwise
@@ -272,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
                 {
                     const int fl = 2 * uu + 1, xs = fl % XS;
                     s.dB[uu] = xo;
-                    pair_mac<L, 1>(s, uu, o1, o2);
+                    pair_mac_split<L, 1>(s, uu, o1, o2);
                     mbar_wait(bar_x_empty(xs), (pk ^ (uint32_t)((fl / XS) & 1)) ^ 1u);
                     const uint32_t xa = x_thr + (uint32_t)xs * (kXSlotUnits * 8);
                     sts64(xa, PAR0 == 0 ? o1 : o2);
@@ -295,8 +294,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
         const uint32_t p1_colB = s_x + (uint32_t)(n0_of(1, i) * kXStride + q) * 8;
         const uint32_t p1_rowA = s_x + (uint32_t)(n0_of(0, i) * kXStride + 9 * q) * 8;   // cell (r = q, qq): + qq units
         const uint32_t p1_rowB = s_x + (uint32_t)(n0_of(1, i) * kXStride + 9 * q) * 8;
-        const uint32_t tw_p1 = s_tw8 + (uint32_t)q * 16;                                  // tw8[r][q] at + 128 r
-        const uint32_t tz_lane = s_base + kOffTz + (uint32_t)lane * 16;                   // tz[half][s][lane] at + 4096 half + 512 s
+        const uint32_t tw_p1 = s_tw8 + (uint32_t)q * 8;                                   // tw8[r][q] at + 64 r
+        const uint32_t tz_lane = s_base + kOffTz + (uint32_t)lane * 8;                    // tz[half][s][lane] at + 2048 half + 256 s
         // exchange: Z[n0][q + 8 s] goes to CTA s, position (half, lane) of source block `crank`
         const uint32_t send_off = (uint32_t)kOffRecv + (uint32_t)(crank * kRecvStride + lane) * 8;   // + 256 half
         const uint32_t rbase = map_to_cta(s_base, 0);                                     // CTA windows are equally spaced
@@ -309,15 +308,14 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
         const uint32_t p2_colB = s_recv + (uint32_t)(recv_pos(qpB) + q) * 8;
         const uint32_t p2_rowA = s_recv + (uint32_t)(qpA * kRecvStride + q) * 8;          // cell (r2 = q', q''): + recv_pos(q'') units
         const uint32_t p2_rowB = s_recv + (uint32_t)(qpB * kRecvStride + q) * 8;
-        const uint32_t tw_p2A = s_tw8 + (uint32_t)qpA * 16;
-        const uint32_t tw_p2B = s_tw8 + (uint32_t)qpB * 16;
+        const uint32_t tw_p2A = s_tw8 + (uint32_t)qpA * 8;
+        const uint32_t tw_p2B = s_tw8 + (uint32_t)qpB * 8;
         float2 *y_thr = a.y + (f_begin + fw - (long long)kLag * kGroup) * (long long)kM + (8 * crank + q);   // + it * 8 frames + 64 q' + 512 s2
 
         auto twiddle8 = [&](float2 (&v)[8], uint32_t tw) {
 #pragma unroll
             for (int r = 1; r < 8; r++) {
-                const float4 t = lds128(tw + 128 * r);
-                v[r] = cmul3(v[r], t.x, make_float2(t.y, t.z));
+                v[r] = cmul_cs(v[r], lds64(tw + 64 * r));
             }
         };
 
@@ -368,9 +366,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
 #pragma unroll
                 for (int s = 0; s < 8; s++) {
                     const uint32_t rcta = rbase + (uint32_t)s * rstep;
-                    const float4 ta = lds128(tz_lane + 512 * s), tb = lds128(tz_lane + 4096 + 512 * s);
-                    st_async64(rcta + dst, cmul3(va[s], ta.x, make_float2(ta.y, ta.z)), rcta + dbar);
-                    st_async64(rcta + dst + 256, cmul3(vb[s], tb.x, make_float2(tb.y, tb.z)), rcta + dbar);
+                    st_async64(rcta + dst, cmul_cs(va[s], lds64(tz_lane + 256 * s)), rcta + dbar);
+                    st_async64(rcta + dst + 256, cmul_cs(vb[s], lds64(tz_lane + 2048 + 256 * s)), rcta + dbar);
                 }
                 xs += kGroup;
                 if (xs >= XS) {
@@ -507,19 +504,17 @@ bool cluster_pfbch2_supported(unsigned int M, unsigned int L)
 
 void cluster_pfbch2_make_twiddles(std::vector<float2> &tw)
 {
-    // float4 tw8[r][q] = {c, -s, s, 0} with c + j s = e^{+j 2 pi q r / 64} (stored as two float2);
-    // then float2 tw4096[n0][k1] = e^{+j 2 pi n0 k1 / 4096}
-    tw.resize(128 + 64 * 64);
+    // tw8[r][q] = e^{+j 2 pi q r / 64}; then tw4096[n0][k1] = e^{+j 2 pi n0 k1 / 4096}
+    tw.resize(64 + 64 * 64);
     for (int r = 0; r < 8; r++)
         for (int q = 0; q < 8; q++) {
             double ang = 2.0 * M_PI * (double)(q * r) / 64.0;
-            tw[2 * (r * 8 + q)] = make_float2((float)cos(ang), -(float)sin(ang));
-            tw[2 * (r * 8 + q) + 1] = make_float2((float)sin(ang), 0.0f);
+            tw[r * 8 + q] = make_float2((float)cos(ang), (float)sin(ang));
         }
     for (int n0 = 0; n0 < 64; n0++)
         for (int k1 = 0; k1 < 64; k1++) {
             double ang = 2.0 * M_PI * (double)(n0 * k1) / 4096.0;
-            tw[128 + n0 * 64 + k1] = make_float2((float)cos(ang), (float)sin(ang));
+            tw[64 + n0 * 64 + k1] = make_float2((float)cos(ang), (float)sin(ang));
         }
 }
 
