@@ -35,8 +35,24 @@ BYTES_PER_SAMPLE = 24            # algorithmic: 8 B read + 16 B written per inpu
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel from one `ncu --set full` capture
 # (profiles/r01_ncu_fused_v7_summary.txt: 1.090287 GB + 2.090002 GB for 2^27 samples) -> bytes per sample
 NCU_DRAM_BYTES_PER_SAMPLE = (1.090287e9 + 2.090002e9) / (1 << 27)
+NCU_SOURCE = "profiles/r01_ncu_fused_v7_summary.txt"
+NCU_LOG2 = 27
+KERNEL = "pfbch2_fused_1024_kernel<14,0> (fused polyphase MAC + 1024-point IFFT)"
 METRIC = "firpfbch2_crcf analysis M=1024 m=7 input throughput"
 UNIT = "MS/s"
+
+
+def select_workload(name):
+    """--workload c3 (default, the headline: BASELINE.json configs[2]) or c5 (configs[4]: M=4096, m=9,
+    the wideband channelizer that is time-sharded across GPUs)"""
+    global M, SEMI, NCU_DRAM_BYTES_PER_SAMPLE, NCU_SOURCE, NCU_LOG2, KERNEL, METRIC
+    if name == "c5":
+        M, SEMI = 4096, 9
+        # profiles/r01_ncu_cluster_4096_v4_summary.txt: 4.304220 GB + 8.536757 GB for 2^29 samples
+        NCU_DRAM_BYTES_PER_SAMPLE = (4.304220e9 + 8.536757e9) / (1 << 29)
+        NCU_SOURCE, NCU_LOG2 = "profiles/r01_ncu_cluster_4096_v4_summary.txt", 29
+        KERNEL = "pfbch2_cluster_4096_kernel<18,0> (cluster of 8 CTAs per frame: polyphase MAC + 64x64 IFFT over DSMEM)"
+        METRIC = "firpfbch2_crcf analysis M=4096 m=9 input throughput"
 
 
 def workload_name(n_samples, n_gpus):
@@ -180,7 +196,10 @@ def main():
     ap.add_argument("--ref-log2-samples", type=int, default=22, help="--impl reference samples per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
+                    help="c3 = headline (M=1024, m=7); c5 = BASELINE.json configs[4] (M=4096, m=9)")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         return impl_reference(args)
 
@@ -280,11 +299,10 @@ def main():
     kernels_per_step = launches / max(args.steps, 1)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_SAMPLE * n / 1e9, "traffic_unit": "GB per launch",
-                "traffic_source": "ncu --set full capture at 2^27 samples per launch (profiles/r01_ncu_fused_v7_summary.txt), "
-                                  "scaled per sample",
+                "traffic_source": "ncu --set full capture at 2^%d samples per launch (%s), scaled per sample"
+                                  % (NCU_LOG2, NCU_SOURCE),
                 "peak_source": peak_src,
-                "kernel": "pfbch2_fused_1024_kernel<14,0> (fused polyphase MAC + 1024-point IFFT), "
-                          "%.0f launch(es) per step" % kernels_per_step,
+                "kernel": KERNEL + ", %.0f launch(es) per step" % kernels_per_step,
                 "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n,
                 "avg_launch_ms": avg_step_ms, "frac_of_8TBps_nominal": achieved / 8000.0}
 

@@ -101,10 +101,13 @@ __device__ __forceinline__ float2 bc(float t) { return make_float2(t, t); }
 __device__ __forceinline__ float2 rot90(float2 a) { return make_float2(-a.y, a.x); }      //  j * a
 __device__ __forceinline__ float2 rot270(float2 a) { return make_float2(a.y, -a.x); }     // -j * a
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
-// complex product a * t
+// complex product a * t: FMUL2 (t.x broadcast) + FFMA2 with the pair {-t.y, t.y} against the swapped a.
+// The sign flip is an integer XOR (ALU pipe), so the FMA pipe sees exactly two packed instructions;
+// writing it as t.y * {-a.y, a.x} makes ptxas negate a.y with a scalar FADD on the FMA pipe instead.
 __device__ __forceinline__ float2 cmul2(float2 a, float2 t)
 {
-    return __ffma2_rn(bc(t.y), rot90(a), __fmul2_rn(bc(t.x), a));
+    const float2 ms_s = make_float2(__int_as_float(__float_as_int(t.y) ^ (int)0x80000000), t.y);
+    return __ffma2_rn(ms_s, make_float2(a.y, a.x), __fmul2_rn(bc(t.x), a));
 }
 
 // N-point DFT of v[] in registers, natural order in and out, e^{SIGN j 2 pi nk/N}.

@@ -22,6 +22,8 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2-samples", type=int, default=24)
+    ap.add_argument("--channels", type=int, default=1024)
+    ap.add_argument("--semi", type=int, default=7)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -29,7 +31,7 @@ def main():
     import liquid_dsp_b200.multi as multi
     from oracle import oracle as O
 
-    M, m = 1024, 7
+    M, m = args.channels, args.semi
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     L.set_device(local)
