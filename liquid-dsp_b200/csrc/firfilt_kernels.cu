@@ -79,91 +79,119 @@ firfilt_tiled_kernel(const float2 *__restrict__ hist, const float2 *__restrict__
 
 // ---------------------------------------------------------------------------------------------
 // Register-blocked FIR for short filters (NT <= 64 taps, zero-padded up to NT): the FP32-pipe-bound
-// shape of BASELINE config 2.  Each thread produces RO = 8 consecutive outputs; the NT taps sit in
-// registers (the same in every thread), samples come from the staged tile one LDS.64 per RO packed
-// FFMA2 (tap broadcast x {re, im} pair).  Everything is unrolled, so tap and accumulator indices are
-// compile-time constants:  y[o+r] += h[k] x[o+r-k]  is visited sample by sample (s = o+r-k).
+// shape of BASELINE config 2.  Each thread produces RO = 16 consecutive outputs; the NT taps sit in
+// registers (the same in every thread), samples come from a staged tile: one LDS.64 per up to RO packed
+// FFMA2 (tap broadcast x {re, im} pair), NT + RO - 1 loads for NT * RO multiply-adds.  Everything is
+// unrolled, so tap and accumulator indices are compile-time constants:  y[o+r] += h[k] x[o+r-k]  is
+// visited sample by sample (s = o+r-k).
+//
+// Every warp is its own pipeline: it owns a private double buffer, fetches its own 32*RO + NT-1 samples
+// with cp.async (256-byte runs) and only ever reads what it fetched itself, so cp.async.wait_group +
+// __syncwarp is all the synchronisation there is -- no block barrier, warps never wait for each other.
+// The NT-1 samples of overlap between neighbouring warp tiles are re-read through L2, not from HBM.
 constexpr int kRbThreads = 256;
-constexpr int kRbOut = 8;                      // outputs per thread
-constexpr int kRbTile = kRbThreads * kRbOut;   // 2048 outputs per CTA tile
+constexpr int kRbWarps = kRbThreads / 32;
 
-__device__ __forceinline__ void cp_async8_zfill(float2 *dst_smem, const float2 *src, bool valid)
+template <int NT, int RO>
+struct RbCfg {
+    static constexpr int kWarpTile = 32 * RO;               // outputs per warp tile
+    static constexpr int NS = kWarpTile + NT - 1;           // staged samples per warp tile
+    // staged transposed so that lane l reading sample l*RO + d is conflict-free:
+    //   slot(q) = (q % RO) * ROW + q / RO
+    // and ROW odd makes the 8-byte cp.async fill (a half-warp = 16 consecutive q = 16 rows) conflict-free too
+    static constexpr int ROW = ((NS + RO - 1) / RO) | 1;
+    static constexpr int NPASS = (NS + 31) / 32;
+    static constexpr unsigned int kBufBytes = RO * ROW * 8;
+    static constexpr size_t kSmem = (size_t)kRbWarps * 2 * kBufBytes;
+    static_assert(RO == 16, "fill pattern is written for 16 outputs per thread");
+};
+
+__device__ __forceinline__ void cp_async8_zfill(unsigned int dst_smem, const float2 *src, bool valid)
 {
     // 8-byte asynchronous global->shared copy; when !valid nothing is read and zeros are written
-    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
     const int bytes = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8_plain(unsigned int dst_smem, const float2 *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 
-// persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the next tile is fetched
-// with cp.async into the other shared buffer while the current one is filtered
-template <int NT>
+// persistent: warp gw of the grid walks warp tiles gw, gw + W, gw + 2W, ...
+template <int NT, int RO>
 __global__ void __launch_bounds__(kRbThreads, 2)
 firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
                         const float *__restrict__ taps, unsigned int n_taps, float scale,
-                        float2 *__restrict__ y, unsigned long long n, unsigned long long tiles_per_stream,
-                        unsigned long long n_tiles)
+                        float2 *__restrict__ y, unsigned long long n_, unsigned long long tiles_per_stream_,
+                        unsigned long long n_tiles_)
 {
-    // staged samples, transposed so that thread t reading sample t*8 + i is conflict-free:
-    // slot(q) = (q % 8) * ROW + q / 8
-    constexpr int NS = kRbTile + NT - 1;
-    // ROW = 2 (mod 16) makes the 8-byte cp.async fill (16 lanes = 8 rows x 2 columns) conflict-free too
-    constexpr int ROW0 = (NS + kRbOut - 1) / kRbOut;
-    constexpr int ROW = ROW0 + ((2 - ROW0 % 16) + 16) % 16;
-    constexpr int NPASS = (NS + kRbThreads - 1) / kRbThreads;
-    constexpr int NBUF = 3;                     // three buffers: one barrier per tile is enough
-    extern __shared__ float2 xs_dyn[];          // NBUF buffers of kRbOut * ROW samples
-    float2 (*xs)[kRbOut * ROW] = reinterpret_cast<float2 (*)[kRbOut * ROW]>(xs_dyn);
+    using C = RbCfg<NT, RO>;
+    constexpr int ROW = C::ROW, NS = C::NS, NPASS = C::NPASS, kWarpTile = C::kWarpTile;
+    extern __shared__ float2 xs_dyn[];          // per warp: 2 buffers of RO * ROW samples
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int xs_warp = (unsigned int)__cvta_generic_to_shared(xs_dyn) + (unsigned int)warp * (2 * C::kBufBytes);
+    // sample q = lane + 32 i of a tile goes to slot (lane % RO) * ROW + lane / RO + i * (32 / RO)
+    const unsigned int fill_thr = xs_warp + (unsigned int)((lane % RO) * ROW + lane / RO) * 8;
+    const unsigned int read_thr = xs_warp + (unsigned int)lane * 8;
+    // keep the loop-invariant parameters in registers (constant-bank reloads inside the loop stall it)
+    long long n = (long long)n_;
+    unsigned long long tiles_per_stream = tiles_per_stream_, n_tiles = n_tiles_;
+    asm volatile("" : "+l"(n), "+l"(tiles_per_stream), "+l"(n_tiles));
+    const unsigned long long stride = (unsigned long long)gridDim.x * kRbWarps;
 
     float h[NT];
 #pragma unroll
     for (int k = 0; k < NT; k++) h[k] = (k < (int)n_taps) ? __ldg(taps + k) * scale : 0.0f;
 
-    auto prefetch = [&](unsigned long long tile_id, int buf) {
+    auto prefetch = [&](unsigned long long tile_id, unsigned int dst) {
         const unsigned long long stream = tile_id / tiles_per_stream;
-        const long long first = (long long)((tile_id % tiles_per_stream) * kRbTile) - (long long)(NT - 1);
-        const float2 *xstr = x + stream * n;
+        const long long first = (long long)((tile_id - stream * tiles_per_stream) * kWarpTile) - (long long)(NT - 1);
+        const float2 *xstr = x + stream * (unsigned long long)n;
+        if (first >= 0 && first + NS <= n) {
+            // interior tile: every sample comes from the stream; addresses are base + immediates
+            const float2 *src = xstr + first + lane;
 #pragma unroll
-        for (int i = 0; i < NPASS; i++) {
-            const int q = threadIdx.x + i * kRbThreads;
-            if (q < NS) {
-                const long long idx = first + q;
-                const float2 *src = xstr;
-                bool valid = false;
-                if (idx >= 0 && idx < (long long)n) { src = xstr + idx; valid = true; }
-                else if (idx < 0 && hist != nullptr && H + idx >= 0) { src = hist + (H + idx); valid = true; }
-                cp_async8_zfill(&xs[buf][(q % kRbOut) * ROW + q / kRbOut], src, valid);
+            for (int i = 0; i < NPASS; i++)
+                if (i < NPASS - 1 || lane + i * 32 < NS)
+                    cp_async8_plain(dst + (unsigned int)(i * (32 / RO)) * 8, src + i * 32);
+        } else {
+            // first / last tile of a stream: history or zeros in front, zeros past the end
+#pragma unroll 1
+            for (int i = 0; i < NPASS; i++) {
+                const int q = lane + i * 32;
+                if (q < NS) {
+                    const long long idx = first + q;
+                    const float2 *src = xstr;
+                    bool valid = false;
+                    if (idx >= 0 && idx < n) { src = xstr + idx; valid = true; }
+                    else if (idx < 0 && hist != nullptr && H + idx >= 0) { src = hist + (H + idx); valid = true; }
+                    cp_async8_zfill(dst + (unsigned int)(i * (32 / RO)) * 8, src, valid);
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    unsigned long long tile_id = blockIdx.x;
-    int buf = 0;
-    if (tile_id < n_tiles) prefetch(tile_id, 0);
-    for (; tile_id < n_tiles; tile_id += gridDim.x, buf = (buf + 1 == NBUF) ? 0 : buf + 1) {
-        const unsigned long long next = tile_id + gridDim.x;
-        if (next < n_tiles) {
-            // the buffer written here was read two tiles ago; every thread has passed the barrier of
-            // the previous tile since, so nobody still reads it
-            prefetch(next, (buf + 1 == NBUF) ? 0 : buf + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
+    unsigned long long tile_id = (unsigned long long)blockIdx.x * kRbWarps + warp;
+    unsigned int buf = 0;                        // byte offset of the current buffer: 0 or kBufBytes
+    if (tile_id < n_tiles) prefetch(tile_id, fill_thr);
+    for (; tile_id < n_tiles; tile_id += stride, buf ^= C::kBufBytes) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();                            // this tile is visible to the whole warp, and every lane has
+                                                 // finished reading the other buffer (previous tile)
+        if (tile_id + stride < n_tiles) prefetch(tile_id + stride, fill_thr + (buf ^ C::kBufBytes));
 
-        const int t = threadIdx.x;
-        const float2 *xb = xs[buf];
-        float2 acc[kRbOut];
+        const unsigned int xb = read_thr + buf;
+        float2 acc[RO];
 #pragma unroll
-        for (int r = 0; r < kRbOut; r++) acc[r] = make_float2(0.f, 0.f);
-        // tile-relative sample i = t*8 + d, d = 0 .. NT+6, feeds output r with tap k = (NT-1) + r - d
+        for (int r = 0; r < RO; r++) acc[r] = make_float2(0.f, 0.f);
+        // tile-relative sample i = lane*RO + d, d = 0 .. NT+RO-2, feeds output r with tap k = (NT-1) + r - d
 #pragma unroll
-        for (int d = 0; d < NT - 1 + kRbOut; d++) {
-            const float2 sv = xb[(d % kRbOut) * ROW + t + d / kRbOut];
+        for (int d = 0; d < NT - 1 + RO; d++) {
+            float2 sv;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sv.x), "=f"(sv.y) : "r"(xb + (unsigned int)((d % RO) * ROW + d / RO) * 8));
 #pragma unroll
-            for (int r = 0; r < kRbOut; r++) {
+            for (int r = 0; r < RO; r++) {
                 const int k = (NT - 1) + r - d;
                 if (k >= 0 && k < NT) acc[r] = __ffma2_rn(make_float2(h[k], h[k]), sv, acc[r]);
             }
@@ -171,16 +199,16 @@ firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restric
         // the scale is folded into the taps: (h[k] * scale) * x differs from scale * (sum h x) only by
         // float rounding of the products (well inside the parity tolerance of the tests)
         const unsigned long long stream = tile_id / tiles_per_stream;
-        const long long o0 = (long long)((tile_id % tiles_per_stream) * kRbTile);
-        float2 *ystr = y + stream * n;
+        const long long o0 = (long long)((tile_id - stream * tiles_per_stream) * kWarpTile) + (long long)lane * RO;
+        float2 *yo = y + stream * (unsigned long long)n + o0;
+        if (o0 + RO <= n) {
 #pragma unroll
-        for (int r = 0; r < kRbOut; r += 2) {
-            long long o = o0 + (long long)t * kRbOut + r;
-            if (o + 1 < (long long)n) {
-                __stcs(reinterpret_cast<float4 *>(ystr + o), make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y));
-            } else if (o < (long long)n) {
-                ystr[o] = acc[r];
-            }
+            for (int r = 0; r < RO; r += 2)
+                __stcs(reinterpret_cast<float4 *>(yo + r), make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y));
+        } else {
+#pragma unroll
+            for (int r = 0; r < RO; r++)
+                if (o0 + r < n) yo[r] = acc[r];
         }
     }
 }
@@ -279,28 +307,24 @@ void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps,
 {
     // short filters on 16-byte aligned, even-length streams: register-blocked packed kernel
     if (n_taps <= 64 && (n % 2) == 0 && ((uintptr_t)d_y % 16) == 0 && !getenv("LIQUID_CUDA_NO_REGBLOCK")) {
-        const unsigned long long tiles_rb = (n + kRbTile - 1) / kRbTile;
-        const unsigned long long total_rb = tiles_rb * n_streams;
-        {
-            int dev = 0, sms = 148;
-            LC_CUDA_CHECK(cudaGetDevice(&dev));
-            LC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int dev = 0, sms = 148;
+        LC_CUDA_CHECK(cudaGetDevice(&dev));
+        LC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        auto run = [&](auto kern, auto cfg) {
+            using C = decltype(cfg);
+            const unsigned long long tiles_rb = (n + C::kWarpTile - 1) / C::kWarpTile;     // warp tiles per stream
+            const unsigned long long total_rb = tiles_rb * n_streams;
             unsigned long long grid = (unsigned long long)sms * 2;      // two resident CTAs per SM
-            if (grid > total_rb) grid = total_rb;
-            auto run = [&](auto kern, int NT) {
-                const int NS = kRbTile + NT - 1;
-                const int ROW0 = (NS + kRbOut - 1) / kRbOut;
-                const int ROW = ROW0 + ((2 - ROW0 % 16) + 16) % 16;
-                const size_t smem = (size_t)3 * kRbOut * ROW * sizeof(float2);
-                LC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<(unsigned int)grid, kRbThreads, smem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n, tiles_rb, total_rb);
-            };
-            if (n_taps <= 16) run(firfilt_regblock_kernel<16>, 16);
-            else if (n_taps <= 32) run(firfilt_regblock_kernel<32>, 32);
-            else run(firfilt_regblock_kernel<64>, 64);
-            LC_LAUNCH_CHECK();
-            return;
-        }
+            const unsigned long long need = (total_rb + kRbWarps - 1) / kRbWarps;
+            if (grid > need) grid = need;
+            LC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+            kern<<<(unsigned int)grid, kRbThreads, C::kSmem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n, tiles_rb, total_rb);
+        };
+        if (n_taps <= 16) run(firfilt_regblock_kernel<16, 16>, RbCfg<16, 16>{});
+        else if (n_taps <= 32) run(firfilt_regblock_kernel<32, 16>, RbCfg<32, 16>{});
+        else run(firfilt_regblock_kernel<64, 16>, RbCfg<64, 16>{});
+        LC_LAUNCH_CHECK();
+        return;
     }
     const unsigned long long tiles = (n + kTile - 1) / kTile;
     const unsigned int n_samp = kTile + n_taps - 1;
