@@ -122,8 +122,8 @@ template <int NT, int RO>
 __global__ void __launch_bounds__(kRbThreads, 2)
 firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
                         const float *__restrict__ taps, unsigned int n_taps, float scale,
-                        float2 *__restrict__ y, unsigned long long n_, unsigned long long tiles_per_stream_,
-                        unsigned long long n_tiles_)
+                        float2 *__restrict__ y, unsigned long long n_, unsigned int tiles_per_stream_,
+                        unsigned int n_tiles_)
 {
     using C = RbCfg<NT, RO>;
     constexpr int ROW = C::ROW, NS = C::NS, NPASS = C::NPASS, kWarpTile = C::kWarpTile;
@@ -135,17 +135,17 @@ firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restric
     const unsigned int read_thr = xs_warp + (unsigned int)lane * 8;
     // keep the loop-invariant parameters in registers (constant-bank reloads inside the loop stall it)
     long long n = (long long)n_;
-    unsigned long long tiles_per_stream = tiles_per_stream_, n_tiles = n_tiles_;
-    asm volatile("" : "+l"(n), "+l"(tiles_per_stream), "+l"(n_tiles));
-    const unsigned long long stride = (unsigned long long)gridDim.x * kRbWarps;
+    unsigned int tiles_per_stream = tiles_per_stream_, n_tiles = n_tiles_;
+    asm volatile("" : "+l"(n), "+r"(tiles_per_stream), "+r"(n_tiles));
+    const unsigned int stride = gridDim.x * kRbWarps;
 
     float h[NT];
 #pragma unroll
     for (int k = 0; k < NT; k++) h[k] = (k < (int)n_taps) ? __ldg(taps + k) * scale : 0.0f;
 
-    auto prefetch = [&](unsigned long long tile_id, unsigned int dst) {
-        const unsigned long long stream = tile_id / tiles_per_stream;
-        const long long first = (long long)((tile_id - stream * tiles_per_stream) * kWarpTile) - (long long)(NT - 1);
+    auto prefetch = [&](unsigned int tile_id, unsigned int dst) {
+        const unsigned int stream = tile_id / tiles_per_stream;
+        const long long first = (long long)(tile_id - stream * tiles_per_stream) * kWarpTile - (long long)(NT - 1);
         const float2 *xstr = x + stream * (unsigned long long)n;
         if (first >= 0 && first + NS <= n) {
             // interior tile: every sample comes from the stream; addresses are base + immediates
@@ -172,7 +172,8 @@ firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restric
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    unsigned long long tile_id = (unsigned long long)blockIdx.x * kRbWarps + warp;
+    // (tile ids fit 32 bits: the launcher checks; n_tiles + stride does not wrap because both are < 2^31)
+    unsigned int tile_id = blockIdx.x * kRbWarps + warp;
     unsigned int buf = 0;                        // byte offset of the current buffer: 0 or kBufBytes
     if (tile_id < n_tiles) prefetch(tile_id, fill_thr);
     for (; tile_id < n_tiles; tile_id += stride, buf ^= C::kBufBytes) {
@@ -198,8 +199,8 @@ firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restric
         }
         // the scale is folded into the taps: (h[k] * scale) * x differs from scale * (sum h x) only by
         // float rounding of the products (well inside the parity tolerance of the tests)
-        const unsigned long long stream = tile_id / tiles_per_stream;
-        const long long o0 = (long long)((tile_id - stream * tiles_per_stream) * kWarpTile) + (long long)lane * RO;
+        const unsigned int stream = tile_id / tiles_per_stream;
+        const long long o0 = (long long)(tile_id - stream * tiles_per_stream) * kWarpTile + (long long)lane * RO;
         float2 *yo = y + stream * (unsigned long long)n + o0;
         if (o0 + RO <= n) {
 #pragma unroll
@@ -306,7 +307,9 @@ void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps,
             float scale, float2 *d_y, unsigned long long n, unsigned int n_streams, cudaStream_t st)
 {
     // short filters on 16-byte aligned, even-length streams: register-blocked packed kernel
-    if (n_taps <= 64 && (n % 2) == 0 && ((uintptr_t)d_y % 16) == 0 && !getenv("LIQUID_CUDA_NO_REGBLOCK")) {
+    // (tile ids are 32-bit inside the kernel: streams * ceil(n / 512) must stay below 2^31)
+    if (n_taps <= 64 && (n % 2) == 0 && ((uintptr_t)d_y % 16) == 0 && ((n + 511) / 512) * n_streams < (1ull << 31) &&
+        !getenv("LIQUID_CUDA_NO_REGBLOCK")) {
         int dev = 0, sms = 148;
         LC_CUDA_CHECK(cudaGetDevice(&dev));
         LC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -318,7 +321,8 @@ void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps,
             const unsigned long long need = (total_rb + kRbWarps - 1) / kRbWarps;
             if (grid > need) grid = need;
             LC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-            kern<<<(unsigned int)grid, kRbThreads, C::kSmem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n, tiles_rb, total_rb);
+            kern<<<(unsigned int)grid, kRbThreads, C::kSmem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n,
+                                                                    (unsigned int)tiles_rb, (unsigned int)total_rb);
         };
         if (n_taps <= 16) run(firfilt_regblock_kernel<16, 16>, RbCfg<16, 16>{});
         else if (n_taps <= 32) run(firfilt_regblock_kernel<32, 16>, RbCfg<32, 16>{});
