@@ -45,15 +45,35 @@ typedef struct { float real; float imag; } liquid_float_complex;
 #define LIQUID_SYNTHESIZER  1       /* liquid.h:5652 */
 #define LIQUID_FFT_FORWARD  (+1)    /* liquid.h:1122 */
 #define LIQUID_FFT_BACKWARD (-1)    /* liquid.h:1123 */
-#define LIQUID_FIRFILT_ARKAISER 7   /* liquid.h:1426 (enum liquid_firfilt_type) */
-#define LIQUID_FIRFILT_RKAISER  8
-#define LIQUID_FIRFILT_RRC      9   /* liquid.h:1428 */
-#define LIQUID_FIRFILT_hM3      10
+/* enum liquid_firfilt_type, liquid.h:1414-1435 (values only; prototypes marked * are designed here) */
+#define LIQUID_FIRFILT_UNKNOWN   0
+#define LIQUID_FIRFILT_KAISER    1  /* * */
+#define LIQUID_FIRFILT_PM        2
+#define LIQUID_FIRFILT_RCOS      3
+#define LIQUID_FIRFILT_FEXP      4
+#define LIQUID_FIRFILT_FSECH     5
+#define LIQUID_FIRFILT_FARCSECH  6
+#define LIQUID_FIRFILT_ARKAISER  7  /* * */
+#define LIQUID_FIRFILT_RKAISER   8  /* * */
+#define LIQUID_FIRFILT_RRC       9  /* * */
+#define LIQUID_FIRFILT_hM3       10
+#define LIQUID_FIRFILT_GMSKTX    11
+#define LIQUID_FIRFILT_GMSKRX    12
+#define LIQUID_FIRFILT_RFEXP     13
+#define LIQUID_FIRFILT_RFSECH    14
+#define LIQUID_FIRFILT_RFARCSECH 15
 
 /* ---- prototype design: liquid.h:1476, :1548, :1580 -> src/filter/src/firdes.c:224-280, rrcos.c:37-95 */
 float kaiser_beta_As(float _As);
 void  liquid_firdes_kaiser(unsigned int _n, float _fc, float _As, float _mu, float *_h);
 void  liquid_firdes_rrcos(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+/* root-Nyquist Kaiser prototypes and their helpers: liquid.h:1463, :1583, :1586, :1664, :1444
+ * -> src/filter/src/rkaiser.c:47-148, :339-516, firdes.c:80-116, :290-370, :503-531 */
+float estimate_req_filter_As(float _df, unsigned int _N);
+void  liquid_filter_isi(float *_h, unsigned int _k, unsigned int _m, float *_rms, float *_max);
+void  liquid_firdes_arkaiser(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+void  liquid_firdes_rkaiser(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+void  liquid_firdes_prototype(int _type, unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
 
 /* ---- firpfbch2_crcf: liquid.h:5754-5793 -> src/multichannel/src/firpfbch2.c:66-358 */
 typedef struct firpfbch2_crcf_s * firpfbch2_crcf;

@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(_HERE, "libliquid_cuda.so")
 
 LIQUID_ANALYZER, LIQUID_SYNTHESIZER = 0, 1
 LIQUID_FFT_FORWARD, LIQUID_FFT_BACKWARD = +1, -1
-LIQUID_FIRFILT_RRC = 9
+LIQUID_FIRFILT_KAISER, LIQUID_FIRFILT_ARKAISER, LIQUID_FIRFILT_RKAISER = 1, 7, 8
+LIQUID_FIRFILT_RRC, LIQUID_FIRFILT_hM3 = 9, 10
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -54,6 +55,11 @@ _vp, _u, _ull, _i, _fl = C.c_void_p, C.c_uint, C.c_ulonglong, C.c_int, C.c_float
 _sig("kaiser_beta_As", _fl, _fl)
 _sig("liquid_firdes_kaiser", None, _u, _fl, _fl, _fl, _f_p)
 _sig("liquid_firdes_rrcos", None, _u, _u, _fl, _fl, _f_p)
+_sig("estimate_req_filter_As", _fl, _fl, _u)
+_sig("liquid_filter_isi", None, _f_p, _u, _u, C.POINTER(C.c_float), C.POINTER(C.c_float))
+_sig("liquid_firdes_arkaiser", None, _u, _u, _fl, _fl, _f_p)
+_sig("liquid_firdes_rkaiser", None, _u, _u, _fl, _fl, _f_p)
+_sig("liquid_firdes_prototype", None, _i, _u, _u, _fl, _fl, _f_p)
 _sig("firpfbch2_crcf_create", _vp, _i, _u, _u, _f_p)
 _sig("firpfbch2_crcf_create_kaiser", _vp, _i, _u, _u, _fl)
 _sig("firpfbch2_crcf_destroy", None, _vp)
@@ -182,6 +188,30 @@ def liquid_firdes_rrcos(k, m, beta, dt=0.0):
     h = np.empty(2 * k * m + 1, np.float32)
     lib.liquid_firdes_rrcos(k, m, beta, dt, h)
     return h
+
+
+def liquid_firdes_arkaiser(k, m, beta, dt=0.0):
+    h = np.empty(2 * k * m + 1, np.float32)
+    lib.liquid_firdes_arkaiser(k, m, beta, dt, h)
+    return h
+
+
+def liquid_firdes_rkaiser(k, m, beta, dt=0.0):
+    h = np.empty(2 * k * m + 1, np.float32)
+    lib.liquid_firdes_rkaiser(k, m, beta, dt, h)
+    return h
+
+
+def liquid_firdes_prototype(ftype, k, m, beta, dt=0.0):
+    h = np.empty(2 * k * m + 1, np.float32)
+    lib.liquid_firdes_prototype(ftype, k, m, beta, dt, h)
+    return h
+
+
+def liquid_filter_isi(h, k, m):
+    rms, peak = C.c_float(0.0), C.c_float(0.0)
+    lib.liquid_filter_isi(np.ascontiguousarray(h, np.float32), k, m, C.byref(rms), C.byref(peak))
+    return rms.value, peak.value
 
 
 def kaiser_beta_As(As):

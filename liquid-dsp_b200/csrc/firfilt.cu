@@ -64,11 +64,9 @@ firfilt_crcf firfilt_crcf_create_rnyquist(int _type, unsigned int _k, unsigned i
     if (_m == 0) lc::fatal("firfilt_crcf_create_rnyquist", "filter delay must be greater than 0");
     if (_beta < 0.0f || _beta > 1.0f)
         lc::fatal("firfilt_crcf_create_rnyquist", "filter excess bandwidth factor must be in [0,1]");
-    if (_type != LIQUID_FIRFILT_RRC)
-        lc::fatal("firfilt_crcf_create_rnyquist", "only LIQUID_FIRFILT_RRC prototypes are provided by liquid_cuda");
     unsigned int h_len = 2 * _k * _m + 1;
     std::vector<float> h(h_len);
-    liquid_firdes_rrcos(_k, _m, _beta, _mu, h.data());
+    liquid_firdes_prototype(_type, _k, _m, _beta, _mu, h.data());   // firfilt.c:161
     return firfilt_crcf_create(h.data(), h_len);
 }
 

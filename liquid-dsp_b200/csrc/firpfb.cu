@@ -70,11 +70,9 @@ firpfb_crcf firpfb_crcf_create_rnyquist(int _type, unsigned int _M, unsigned int
     if (_k < 2) lc::fatal("firpfb_crcf_create_rnyquist", "filter samples/symbol must be greater than 1");
     if (_m == 0) lc::fatal("firpfb_crcf_create_rnyquist", "filter delay must be greater than 0");
     if (_beta < 0.0f || _beta > 1.0f) lc::fatal("firpfb_crcf_create_rnyquist", "filter excess bandwidth factor must be in [0,1]");
-    if (_type != LIQUID_FIRFILT_RRC)
-        lc::fatal("firpfb_crcf_create_rnyquist", "only LIQUID_FIRFILT_RRC prototypes are provided by liquid_cuda");
     unsigned int H_len = 2 * _M * _k * _m + 1;
     std::vector<float> Hf(H_len);
-    liquid_firdes_rrcos(_M * _k, _m, _beta, 0.0f, Hf.data());
+    liquid_firdes_prototype(_type, _M * _k, _m, _beta, 0.0f, Hf.data());   // firpfb.c:170
     return firpfb_crcf_create(_M, Hf.data(), H_len);
 }
 

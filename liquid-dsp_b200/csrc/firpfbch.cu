@@ -97,15 +97,16 @@ firpfbch_crcf firpfbch_crcf_create_rnyquist(int _type, unsigned int _M, unsigned
     }
     unsigned int h_len = 2 * _M * _m + 1;
     std::vector<float> h(h_len);
-    switch (_ftype) {
-    case LIQUID_FIRFILT_RRC:
-        liquid_firdes_rrcos(_M, _m, _beta, 0.0f, h.data());
-        break;
+    switch (_ftype) {                                   // firpfbch.c:216-235
     case LIQUID_FIRFILT_ARKAISER:
     case LIQUID_FIRFILT_RKAISER:
+    case LIQUID_FIRFILT_RRC:
+        liquid_firdes_prototype(_ftype, _M, _m, _beta, 0.0f, h.data());
+        break;
     case LIQUID_FIRFILT_hM3:
         lc::fatal("firpfbch_crcf_create_rnyquist",
-                  "arkaiser/rkaiser/hM3 prototypes are not provided by liquid_cuda yet (use LIQUID_FIRFILT_RRC or firpfbch_crcf_create with external taps)");
+                  "the hM3 prototype needs the Parks-McClellan designer, which liquid_cuda does not carry "
+                  "(use ARKAISER, RKAISER or RRC, or firpfbch_crcf_create with external taps)");
     default:
         fprintf(stderr, "error: firpfbch_%s_create_rnyquist(), unknown/invalid prototype (%d)\n", "crcf", _ftype);
         exit(1);

@@ -84,6 +84,11 @@ inline unsigned int ilog2(unsigned int n)
 float kaiser_beta_As(float As);
 int firdes_kaiser(unsigned int n, float fc, float As, float mu, float *h);   // 0 ok, else message id
 int firdes_rrcos(unsigned int k, unsigned int m, float beta, float dt, float *h);
+float estimate_req_filter_As(float df, unsigned int N);
+void filter_isi(const float *h, unsigned int k, unsigned int m, float *rms, float *peak);
+float rkaiser_approximate_rho(unsigned int m, float beta);
+int firdes_arkaiser(unsigned int k, unsigned int m, float beta, float dt, float *h);          // 0 ok, else message id
+int firdes_rkaiser(unsigned int k, unsigned int m, float beta, float dt, float *h, float *rho_out);
 
 // ---- batched FFT building block shared by the channelizers and the fft_* API : fft.cu ----
 // d_tw: twiddle table of n entries e^{sign j 2 pi i/n} (only used for non power-of-two n)

@@ -156,6 +156,153 @@ int orc_firdes_rrcos(unsigned int k, unsigned int m, float beta, float dt, float
     return 0;
 }
 
+/* stop-band attenuation a Kaiser design of N taps reaches over a transition band df: 20 bisection
+ * steps on Kaiser's length estimate N = (As - 7.95) / (14.26 df).   src/filter/src/firdes.c:80-116, :163-177 */
+float orc_estimate_req_filter_As(float df, unsigned int N)
+{
+    float lo = 0.01f, hi = 200.0f, As = 0.0f;
+    for (unsigned int it = 0; it < 20; it++) {
+        As = 0.5f * (hi + lo);
+        float n_hat = (As - 7.95f) / (14.26f * df);
+        if (n_hat < (float)N) lo = As;
+        else                  hi = As;
+    }
+    return As;
+}
+
+/* auto-correlation of h at a lag (float32 running sum).   firdes.c:420-438 */
+static float orc_filter_autocorr(const float *h, unsigned int n, unsigned int lag)
+{
+    if (lag >= n) return 0.0f;
+    float r = 0.0f;
+    for (unsigned int i = lag; i < n; i++) r += h[i] * h[i - lag];
+    return r;
+}
+
+/* RMS and peak inter-symbol interference of a 2km+1-tap filter: normalised auto-correlation at the
+ * symbol lags k, 2k, ..., 2mk.   firdes.c:503-531 */
+void orc_filter_isi(const float *h, unsigned int k, unsigned int m, float *rms, float *peak)
+{
+    unsigned int n = 2 * k * m + 1;
+    float r0 = orc_filter_autocorr(h, n, 0);
+    float acc = 0.0f, mx = 0.0f;
+    for (unsigned int i = 1; i <= 2 * m; i++) {
+        float e = fabsf(orc_filter_autocorr(h, n, i * k) / r0);
+        acc += e * e;
+        if (i == 1 || e > mx) mx = e;
+    }
+    *rms = sqrtf(acc / (float)(2 * m));
+    *peak = mx;
+}
+
+/* tabulated bandwidth-adjustment estimate rho(m, beta) = c0 + c1 ln(beta) + c2 ln^2(beta), clamped to
+ * [0,1].   src/filter/src/rkaiser.c:155-210 */
+float orc_rkaiser_approximate_rho(unsigned int m, float beta)
+{
+    static const float tab[22][3] = {
+        {0.75749731f, 0.06134303f, -0.08729663f}, {0.81151861f, 0.07437658f, -0.01427088f},
+        {0.84249538f, 0.07684185f, -0.00536879f}, {0.86140782f, 0.07144126f, -0.00558652f},
+        {0.87457740f, 0.06578694f, -0.00650447f}, {0.88438797f, 0.06074265f, -0.00736405f},
+        {0.89216620f, 0.05669236f, -0.00791222f}, {0.89874983f, 0.05361696f, -0.00815301f},
+        {0.90460032f, 0.05167952f, -0.00807893f}, {0.91034430f, 0.05130753f, -0.00746192f},
+        {0.91587675f, 0.05180436f, -0.00670711f}, {0.92121875f, 0.05273801f, -0.00588351f},
+        {0.92638195f, 0.05400764f, -0.00508452f}, {0.93123555f, 0.05516163f, -0.00437306f},
+        {0.93564993f, 0.05596561f, -0.00388152f}, {0.93976742f, 0.05662274f, -0.00348280f},
+        {0.94351703f, 0.05694120f, -0.00318821f}, {0.94557273f, 0.05227591f, -0.00400676f},
+        {0.95001614f, 0.05681641f, -0.00300628f}, {0.95281708f, 0.05637607f, -0.00304790f},
+        {0.95536256f, 0.05575880f, -0.00312988f}, {0.95754206f, 0.05426060f, -0.00385945f}};
+    float c0, c1, c2;
+    if (m >= 1 && m <= 22) {
+        c0 = tab[m - 1][0]; c1 = tab[m - 1][1]; c2 = tab[m - 1][2];
+    } else {
+        c0 = 0.056873 * logf(m + 1e-3f) + 0.781388;
+        c1 = 0.05426f;
+        c2 = -0.00386f;
+    }
+    float b = logf(beta);
+    float rho = c0 + c1 * b + c2 * b * b;
+    if (rho < 0.0f) rho = 0.0f;
+    else if (rho > 1.0f) rho = 1.0f;
+    return rho;
+}
+
+/* Kaiser-windowed sinc whose transition band is rho * beta / k wide, cut-off moved so that the filter is
+ * (approximately) root-Nyquist; returns its RMS ISI.   rkaiser.c:482-516 */
+static float orc_rkaiser_design_isi(unsigned int k, unsigned int m, float beta, float dt, float rho, float *h)
+{
+    unsigned int n = 2 * k * m + 1;
+    float kf = (float)k;
+    float del = beta * rho / kf;
+    float As = orc_estimate_req_filter_As(del, n);
+    float fc = 0.5f * (1 + beta * (1.0f - rho)) / kf;
+    orc_firdes_kaiser(n, fc, As, dt, h);
+    float rms, peak;
+    orc_filter_isi(h, k, m, &rms, &peak);
+    return rms;
+}
+
+/* scale to energy k.   rkaiser.c:144-147, :468-470 */
+static void orc_normalize_energy(float *h, unsigned int n, unsigned int k)
+{
+    float e2 = 0.0f;
+    for (unsigned int i = 0; i < n; i++) e2 += h[i] * h[i];
+    for (unsigned int i = 0; i < n; i++) h[i] *= sqrtf(k / e2);
+}
+
+/* approximate root-Nyquist Kaiser: rho from a closed-form fit, one design.   rkaiser.c:82-148 */
+int orc_firdes_arkaiser(unsigned int k, unsigned int m, float beta, float dt, float *h)
+{
+    if (k < 2 || m < 1 || beta <= 0.0f || beta >= 1.0f || dt < -1.0f || dt > 1.0f) return -1;
+    float c0 = 0.762886 + 0.067663 * logf(m);
+    float c1 = 0.065515;
+    float c2 = logf(1 - 0.088 * powf(m, -1.6));
+    float lb = logf(beta);
+    float rho = c0 + c1 * lb + c2 * lb * lb;
+    if (rho <= 0.0f || rho >= 1.0f) rho = orc_rkaiser_approximate_rho(m, beta);
+    unsigned int n = 2 * k * m + 1;
+    float kf = (float)k;
+    float del = beta * rho / kf;
+    float As = orc_estimate_req_filter_As(del, n);
+    float fc = 0.5f * (1 + beta * (1.0f - rho)) / kf;
+    orc_firdes_kaiser(n, fc, As, dt, h);
+    orc_normalize_energy(h, n, k);
+    return 0;
+}
+
+/* root-Nyquist Kaiser: rho found by a bracketed parabolic search (at most 14 rounds of three designs)
+ * for the least RMS ISI, then one more design at the best rho seen.   rkaiser.c:47-76, :339-474 */
+int orc_firdes_rkaiser(unsigned int k, unsigned int m, float beta, float dt, float *h, float *rho_out)
+{
+    if (k < 2 || m < 1 || beta <= 0.0f || beta >= 1.0f || dt < -1.0f || dt > 1.0f) return -1;
+    unsigned int n = 2 * k * m + 1;
+    float rho_hat = orc_rkaiser_approximate_rho(m, beta);
+    float rho_opt = rho_hat, y_opt = 0.0f;
+    float x1 = rho_hat, dx = 0.2f;
+    const float tol = 1e-6f;
+    for (unsigned int p = 0; p < 14; p++) {
+        float x0 = x1 - dx, x2 = x1 + dx;
+        if (x0 <= 0.0f) x0 = 0.01f;
+        if (x2 >= 1.0f) x2 = 0.99f;
+        float y0 = orc_rkaiser_design_isi(k, m, beta, dt, x0, h);
+        float y1 = orc_rkaiser_design_isi(k, m, beta, dt, x1, h);
+        float y2 = orc_rkaiser_design_isi(k, m, beta, dt, x2, h);
+        if (p == 0 || y1 < y_opt) { rho_opt = x1; y_opt = y1; }
+        /* vertex of the parabola through the three points (float arithmetic, widened to double only for the division) */
+        double ta = y0 * (x1 * x1 - x2 * x2) + y1 * (x2 * x2 - x0 * x0) + y2 * (x0 * x0 - x1 * x1);
+        double tb = y0 * (x1 - x2) + y1 * (x2 - x0) + y2 * (x0 - x1);
+        float x_hat = 0.5f * ta / tb;
+        if (x_hat < x0 || x_hat > x2) break;
+        float del = x_hat - x1;
+        if (p > 3 && fabsf(del) < tol) break;
+        x1 = x_hat;
+        dx *= 0.5f;
+    }
+    orc_rkaiser_design_isi(k, m, beta, dt, rho_opt, h);
+    orc_normalize_energy(h, n, k);
+    if (rho_out) *rho_out = rho_opt;
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* dot products                                                                          */
 /* ------------------------------------------------------------------------------------ */
@@ -508,20 +655,30 @@ orc_firpfbch orc_firpfbch_create_kaiser(int type, unsigned int M, unsigned int m
     return q;
 }
 
-/* firpfbch.c:193-256 with ftype = LIQUID_FIRFILT_RRC: RRC at k = M, first 2Mm taps,
- * time-reversed for the analyzer */
-orc_firpfbch orc_firpfbch_create_rrc(int type, unsigned int M, unsigned int m, float beta)
+/* firpfbch.c:193-256: root-Nyquist prototype at k = M (ftype 7 = arkaiser, 8 = rkaiser, 9 = RRC; hM3 is
+ * not restated), first 2Mm taps, time-reversed for the analyzer */
+orc_firpfbch orc_firpfbch_create_rnyquist(int type, unsigned int M, unsigned int m, float beta, int ftype)
 {
     if ((type != ORC_ANALYZER && type != ORC_SYNTHESIZER) || M == 0 || m == 0) return NULL;
     unsigned int h_len = 2 * M * m + 1, g_len = 2 * M * m;
     float *h = xmalloc(h_len * sizeof *h);
     float *g = xmalloc(g_len * sizeof *g);
-    if (orc_firdes_rrcos(M, m, beta, 0.0f, h)) { free(h); free(g); return NULL; }
+    int rc;
+    if (ftype == 7)      rc = orc_firdes_arkaiser(M, m, beta, 0.0f, h);
+    else if (ftype == 8) rc = orc_firdes_rkaiser(M, m, beta, 0.0f, h, NULL);
+    else if (ftype == 9) rc = orc_firdes_rrcos(M, m, beta, 0.0f, h);
+    else                 rc = -1;
+    if (rc) { free(h); free(g); return NULL; }
     for (unsigned int i = 0; i < g_len; i++)
         g[i] = (type == ORC_SYNTHESIZER) ? h[i] : h[g_len - i - 1];
     orc_firpfbch q = orc_firpfbch_create(type, M, 2 * m, g);
     free(h); free(g);
     return q;
+}
+
+orc_firpfbch orc_firpfbch_create_rrc(int type, unsigned int M, unsigned int m, float beta)
+{
+    return orc_firpfbch_create_rnyquist(type, M, m, beta, 9);
 }
 
 void orc_firpfbch_destroy(orc_firpfbch q)

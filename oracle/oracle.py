@@ -68,6 +68,16 @@ def lib():
         L.orc_firdes_kaiser.argtypes = [C.c_uint, C.c_float, C.c_float, C.c_float, c_f_p]
         L.orc_firdes_rrcos.restype = C.c_int
         L.orc_firdes_rrcos.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float, c_f_p]
+        L.orc_firdes_arkaiser.restype = C.c_int
+        L.orc_firdes_arkaiser.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float, c_f_p]
+        L.orc_firdes_rkaiser.restype = C.c_int
+        L.orc_firdes_rkaiser.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float, c_f_p, C.POINTER(C.c_float)]
+        L.orc_estimate_req_filter_As.restype = C.c_float
+        L.orc_estimate_req_filter_As.argtypes = [C.c_float, C.c_uint]
+        L.orc_rkaiser_approximate_rho.restype = C.c_float
+        L.orc_rkaiser_approximate_rho.argtypes = [C.c_uint, C.c_float]
+        L.orc_filter_isi.restype = None
+        L.orc_filter_isi.argtypes = [c_f_p, C.c_uint, C.c_uint, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         for name in ("orc_dotprod_crcf_run", "orc_dotprod_crcf_run4", "orc_dotprod_crcf_run_sse_order"):
             getattr(L, name).restype = None
             getattr(L, name).argtypes = [c_f_p, c_cf_p, C.c_uint, c_cf_p]
@@ -92,6 +102,8 @@ def lib():
         L.orc_firpfbch_create_kaiser.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float]
         L.orc_firpfbch_create_rrc.restype = C.c_void_p
         L.orc_firpfbch_create_rrc.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float]
+        L.orc_firpfbch_create_rnyquist.restype = C.c_void_p
+        L.orc_firpfbch_create_rnyquist.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_int]
         L.orc_firpfbch_destroy.argtypes = [C.c_void_p]; L.orc_firpfbch_reset.argtypes = [C.c_void_p]
         L.orc_firpfbch_execute_frames.restype = None
         L.orc_firpfbch_execute_frames.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
@@ -132,6 +144,27 @@ def firdes_rrcos(k, m, beta, dt=0.0):
     if lib().orc_firdes_rrcos(k, m, beta, dt, h):
         raise ValueError("liquid_firdes_rrcos: invalid arguments")
     return h
+
+
+def firdes_arkaiser(k, m, beta, dt=0.0):
+    h = np.empty(2 * k * m + 1, np.float32)
+    if lib().orc_firdes_arkaiser(k, m, beta, dt, h):
+        raise ValueError("liquid_firdes_arkaiser: invalid arguments")
+    return h
+
+
+def firdes_rkaiser(k, m, beta, dt=0.0, return_rho=False):
+    h = np.empty(2 * k * m + 1, np.float32)
+    rho = C.c_float(0.0)
+    if lib().orc_firdes_rkaiser(k, m, beta, dt, h, C.byref(rho)):
+        raise ValueError("liquid_firdes_rkaiser: invalid arguments")
+    return (h, rho.value) if return_rho else h
+
+
+def filter_isi(h, k, m):
+    rms, peak = C.c_float(0.0), C.c_float(0.0)
+    lib().orc_filter_isi(_f(h), k, m, C.byref(rms), C.byref(peak))
+    return rms.value, peak.value
 
 
 def dotprod_crcf(h, x, order="run"):
@@ -215,10 +248,12 @@ class Firpfb(_Obj):
 class Firpfbch(_Obj):
     _destroy = "orc_firpfbch_destroy"
 
-    def __init__(self, type, M, p=None, h=None, kaiser=None, rrc=None):
+    def __init__(self, type, M, p=None, h=None, kaiser=None, rrc=None, rnyquist=None):
         self.type, self.M = type, M
         if kaiser is not None:
             hd = lib().orc_firpfbch_create_kaiser(type, M, *kaiser)
+        elif rnyquist is not None:                      # (m, beta, ftype)
+            hd = lib().orc_firpfbch_create_rnyquist(type, M, *rnyquist)
         elif rrc is not None:
             hd = lib().orc_firpfbch_create_rrc(type, M, *rrc)
         else:
@@ -273,6 +308,9 @@ def ref_available():
 
 
 def _ref_variant():
+    forced = os.environ.get("LIQUID_ORACLE_REF_VARIANT")      # "" (AVX2+FMA build) or "_sse" (baseline x86-64)
+    if forced is not None:
+        return forced
     flags = _cpu_flags()
     return "" if {"avx2", "fma", "bmi2"} <= flags else "_sse"
 
@@ -289,6 +327,11 @@ def ref():
         R.liquid_firdes_kaiser.argtypes = [C.c_uint, C.c_float, C.c_float, C.c_float, c_f_p]
         R.liquid_firdes_rrcos.restype = None
         R.liquid_firdes_rrcos.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float, c_f_p]
+        for fn in ("liquid_firdes_arkaiser", "liquid_firdes_rkaiser"):
+            getattr(R, fn).restype = None
+            getattr(R, fn).argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float, c_f_p]
+        R.estimate_req_filter_As.restype = C.c_float; R.estimate_req_filter_As.argtypes = [C.c_float, C.c_uint]
+        R.rkaiser_approximate_rho.restype = C.c_float; R.rkaiser_approximate_rho.argtypes = [C.c_uint, C.c_float]
         R.liquid_besseli0f.restype = C.c_float; R.liquid_besseli0f.argtypes = [C.c_float]
         R.liquid_lngammaf.restype = C.c_float; R.liquid_lngammaf.argtypes = [C.c_float]
         R.kaiser_beta_As.restype = C.c_float; R.kaiser_beta_As.argtypes = [C.c_float]

@@ -30,6 +30,13 @@ def refout():
 
 
 @pytest.fixture(scope="session")
+def refrn():
+    """root-Nyquist Kaiser prototypes and channelizers built on them, from the compiled reference
+    (oracle/gen_golden_rnyquist.py)"""
+    return dict(np.load(os.path.join(GOLDEN, "ref_outputs_rnyquist.npz")))
+
+
+@pytest.fixture(scope="session")
 def orc():
     """the CPU oracle (checker only)"""
     from oracle import oracle as O

@@ -405,6 +405,29 @@ def test_pfbch2_fused_matches_generic_path(L, orc, monkeypatch):
     assert np.abs(fused - generic).max() < 1e-6
 
 
+# ------------------------------------------------------------------ root-Nyquist Kaiser prototypes
+def test_pfbch_rnyquist_kaiser_prototypes_vs_reference(L, orc, refrn):
+    """firpfbch_crcf_create_rnyquist with ARKAISER / RKAISER against the compiled reference's outputs and
+    the oracle; firfilt / firpfb accept the same prototypes"""
+    for name in sorted(k for k in refrn if k.startswith("pfbch_") and k.endswith("_args")):
+        M, m, beta, ftype = refrn[name]
+        M, m, ftype, beta = int(M), int(m), int(ftype), np.float32(beta)
+        proto = name.split("_")[1]
+        x = refrn[name[:-5] + "_x"]
+        for typ, key, otyp in ((L.LIQUID_ANALYZER, "a", orc.ANALYZER), (L.LIQUID_SYNTHESIZER, "s", orc.SYNTHESIZER)):
+            want = refrn["pfbch_%s_%s_M%d_m%d_y" % (proto, key, M, m)]
+            got = L.firpfbch_crcf.create_rnyquist(typ, M, m, beta, ftype).execute_block(x)
+            assert np.abs(got - want).max() <= 4e-6 * np.abs(want).max(), (name, key)
+            worc = orc.Firpfbch(otyp, M, rnyquist=(m, beta, ftype)).execute_frames(x)
+            assert np.abs(got - worc).max() <= 2e-6 * np.abs(worc).max(), (name, key)
+    # firfilt with an RKAISER prototype == firfilt with the oracle's taps
+    x = orc.synth_input(3000, seed=0xAB)
+    h = orc.firdes_rkaiser(4, 5, np.float32(0.3))
+    got = L.firfilt_crcf.create_rnyquist(L.LIQUID_FIRFILT_RKAISER, 4, 5, 0.3).execute_block(x)
+    want = orc.Firfilt(h=h).execute_block(x)
+    assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
+
+
 # ------------------------------------------------------------------ cluster-of-8 M=4096 kernel specifics
 @pytest.mark.parametrize("m", [4, 7, 9])
 def test_pfbch2_cluster_4096_vs_oracle_odd_splits(L, orc, m):

@@ -97,3 +97,21 @@ def test_fft_shift_host(L):
         want = x.copy()
         want[:n2], want[n2:2 * n2] = x[n2:2 * n2].copy(), x[:n2].copy()
         assert np.array_equal(y, want)
+
+
+def test_host_design_rnyquist_kaiser(L, orc, refrn):
+    """liquid_firdes_arkaiser / _rkaiser / _prototype(KAISER) of the library (host code, no GPU needed)
+    equal the reference fixture and the oracle bit for bit"""
+    for name in sorted(k for k in refrn if k.startswith("args_")):
+        tag = name[5:]
+        k, m, beta, dt = refrn[name]
+        k, m, beta, dt = int(k), int(m), np.float32(beta), np.float32(dt)
+        assert np.array_equal(L.liquid_firdes_arkaiser(k, m, beta, dt), refrn["taps_arkaiser_" + tag]), tag
+        assert np.array_equal(L.liquid_firdes_rkaiser(k, m, beta, dt), refrn["taps_rkaiser_" + tag]), tag
+        assert np.array_equal(L.liquid_firdes_prototype(L.LIQUID_FIRFILT_KAISER, k, m, beta, dt), refrn["taps_nkaiser_" + tag]), tag
+        assert np.array_equal(L.liquid_firdes_prototype(L.LIQUID_FIRFILT_RKAISER, k, m, beta, dt),
+                              orc.firdes_rkaiser(k, m, beta, dt))
+        rms, peak = L.liquid_filter_isi(refrn["taps_rkaiser_" + tag], k, m)
+        assert np.allclose([rms, peak], refrn["isi_rkaiser_" + tag], rtol=1e-6)
+    for df, N, want in refrn["req_As"]:
+        assert L.lib.estimate_req_filter_As(df, int(N)) == np.float32(want)

@@ -271,3 +271,66 @@ def test_synth_input_is_deterministic_and_bounded(orc):
     assert np.array_equal(a[500:], b)
     assert a.real.min() >= -0.5 and a.real.max() < 0.5 and abs(a.real.mean()) < 0.05
     assert 0.07 < np.mean(np.abs(a) ** 2) < 0.25
+
+
+# ------------------------------------------------------------------ root-Nyquist Kaiser prototypes
+def _rn_cases(refrn):
+    for name in sorted(k for k in refrn if k.startswith("args_")):
+        k, m, beta, dt = refrn[name]
+        yield name[5:], int(k), int(m), np.float32(beta), np.float32(dt)
+
+
+def test_fixture_rkaiser_helpers(orc, refrn):
+    for df, N, want in refrn["req_As"]:
+        assert orc.lib().orc_estimate_req_filter_As(df, int(N)) == np.float32(want)
+    for m, b, want in refrn["approx_rho"]:
+        assert orc.lib().orc_rkaiser_approximate_rho(int(m), b) == np.float32(want)
+
+
+def test_fixture_arkaiser_rkaiser_taps_bit_exact(orc, refrn):
+    """the restatement equals the reference (baseline x86-64 build, no FMA contraction) bit for bit,
+    including the rho found by the 14-round parabolic search of rkaiser"""
+    for tag, k, m, beta, dt in _rn_cases(refrn):
+        assert np.array_equal(orc.firdes_arkaiser(k, m, beta, dt), refrn["taps_arkaiser_" + tag]), tag
+        assert np.array_equal(orc.firdes_rkaiser(k, m, beta, dt), refrn["taps_rkaiser_" + tag]), tag
+        rms, peak = orc.filter_isi(refrn["taps_rkaiser_" + tag], k, m)
+        assert np.allclose([rms, peak], refrn["isi_rkaiser_" + tag], rtol=1e-6)
+
+
+def test_rkaiser_properties(orc):
+    """what the reference's autotests check for its root-Nyquist designs (src/filter/tests/
+    firdes_autotest.c: ISI of the matched pair below a threshold): energy k, small ISI, and rkaiser is
+    no worse than arkaiser"""
+    for k, m, beta in [(2, 9, 0.3), (4, 7, 0.25), (10, 5, 0.5)]:
+        ha, hr = orc.firdes_arkaiser(k, m, beta), orc.firdes_rkaiser(k, m, beta)
+        for h in (ha, hr):
+            assert abs(float((h.astype(np.float64) ** 2).sum()) - k) < 1e-4 * k
+        isi_a, isi_r = orc.filter_isi(ha, k, m)[0], orc.filter_isi(hr, k, m)[0]
+        assert isi_r <= isi_a * 1.0001 and isi_r < 10 ** (-30 / 20)
+
+
+def test_live_reference_rkaiser(orc):
+    """against the compiled reference of THIS host (may contract FMAs): taps agree to float rounding;
+    the rkaiser search is allowed the resulting 1e-5 wobble of its optimum"""
+    if not orc.ref_available():
+        pytest.skip("compiled reference not present")
+    import ctypes as C
+    R = orc.ref()
+    for k, m, beta in [(2, 3, 0.3), (16, 7, 0.25), (64, 4, 0.9)]:
+        for name, fn, tol in (("arkaiser", orc.firdes_arkaiser, 2e-6), ("rkaiser", orc.firdes_rkaiser, 5e-5)):
+            want = np.empty(2 * k * m + 1, np.float32)
+            getattr(R, "liquid_firdes_" + name)(k, m, beta, 0.0, want)
+            assert np.abs(fn(k, m, np.float32(beta)) - want).max() <= tol * np.abs(want).max(), (name, k, m)
+
+
+def test_fixture_pfbch_rnyquist_channelizers(orc, refrn):
+    for name in sorted(k for k in refrn if k.startswith("pfbch_") and k.endswith("_args")):
+        M, m, beta, ftype = refrn[name]
+        M, m, ftype = int(M), int(m), int(ftype)
+        stem = name[:-5]                                  # pfbch_<proto>_M<M>_m<m>
+        proto = stem.split("_")[1]
+        x = refrn[stem + "_x"]
+        for typ, key in ((orc.ANALYZER, "a"), (orc.SYNTHESIZER, "s")):
+            want = refrn["pfbch_%s_%s_M%d_m%d_y" % (proto, key, M, m)]
+            got = orc.Firpfbch(typ, M, rnyquist=(m, np.float32(beta), ftype)).execute_frames(x)
+            assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max(), (stem, key)
