@@ -96,6 +96,21 @@ void firpfbch_crcf_print(firpfbch_crcf _q);
 void firpfbch_crcf_synthesizer_execute(firpfbch_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
 void firpfbch_crcf_analyzer_execute(firpfbch_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
 
+/* ---- firpfbch_cccf (complex taps): liquid.h:5660-5664, :5682-5728 -> src/multichannel/src/firpfbch_cccf.c:35-52
+ *      instantiating firpfbch.c:73-409 with TC = float complex and dotprod_cccf.  SURVEY.md 8(f) item 1. */
+typedef struct firpfbch_cccf_s * firpfbch_cccf;
+firpfbch_cccf firpfbch_cccf_create(int _type, unsigned int _M, unsigned int _p, liquid_float_complex *_h);
+firpfbch_cccf firpfbch_cccf_create_kaiser(int _type, unsigned int _M, unsigned int _m, float _As);
+firpfbch_cccf firpfbch_cccf_create_rnyquist(int _type, unsigned int _M, unsigned int _m, float _beta, int _ftype);
+void firpfbch_cccf_destroy(firpfbch_cccf _q);
+void firpfbch_cccf_reset(firpfbch_cccf _q);
+void firpfbch_cccf_print(firpfbch_cccf _q);
+void firpfbch_cccf_synthesizer_execute(firpfbch_cccf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+void firpfbch_cccf_analyzer_execute(firpfbch_cccf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+/* exported by the reference but absent from liquid.h, as for crcf (firpfbch.c:369, :383) */
+void firpfbch_cccf_analyzer_push(firpfbch_cccf _q, liquid_float_complex _x);
+void firpfbch_cccf_analyzer_run(firpfbch_cccf _q, unsigned int _k, liquid_float_complex *_X);
+
 /* ---- firfilt_crcf: liquid.h:1985-2074 -> src/filter/src/firfilt.c:62-405 */
 typedef struct firfilt_crcf_s * firfilt_crcf;
 firfilt_crcf firfilt_crcf_create(float *_h, unsigned int _n);
@@ -211,6 +226,14 @@ void firpfbch_crcf_execute_streams_dev(firpfbch_crcf _q, const void *_d_x, unsig
 unsigned int firpfbch_crcf_get_state_len(firpfbch_crcf _q);
 void firpfbch_crcf_get_state(firpfbch_crcf _q, liquid_float_complex *_hist);
 void firpfbch_crcf_set_state(firpfbch_crcf _q, const liquid_float_complex *_hist);
+
+/* ---- firpfbch_cccf ---- */
+void firpfbch_cccf_analyzer_execute_block(firpfbch_cccf _q, liquid_float_complex *_x,
+                                          unsigned int _n_frames, liquid_float_complex *_y);
+void firpfbch_cccf_synthesizer_execute_block(firpfbch_cccf _q, liquid_float_complex *_x,
+                                             unsigned int _n_frames, liquid_float_complex *_y);
+void firpfbch_cccf_execute_block_dev(firpfbch_cccf _q, const void *_d_x,
+                                     unsigned long long _n_frames, void *_d_y, void *_stream);
 
 /* ---- firfilt_crcf ---- */
 /* _n_streams independent streams of _n samples each (stream s at _d_x + s*_n), every stream filtered

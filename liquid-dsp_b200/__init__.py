@@ -89,6 +89,19 @@ _sig("firpfbch_crcf_execute_streams_dev", None, _vp, _vp, _u, _ull, _vp, _vp)
 _sig("firpfbch_crcf_get_state_len", _u, _vp)
 _sig("firpfbch_crcf_get_state", None, _vp, _cf_p)
 _sig("firpfbch_crcf_set_state", None, _vp, _cf_p)
+_sig("firpfbch_cccf_create", _vp, _i, _u, _u, _cf_p)
+_sig("firpfbch_cccf_create_kaiser", _vp, _i, _u, _u, _fl)
+_sig("firpfbch_cccf_create_rnyquist", _vp, _i, _u, _u, _fl, _i)
+_sig("firpfbch_cccf_destroy", None, _vp)
+_sig("firpfbch_cccf_reset", None, _vp)
+_sig("firpfbch_cccf_print", None, _vp)
+_sig("firpfbch_cccf_synthesizer_execute", None, _vp, _cf_p, _cf_p)
+_sig("firpfbch_cccf_analyzer_execute", None, _vp, _cf_p, _cf_p)
+_sig("firpfbch_cccf_analyzer_push", None, _vp, _cf)
+_sig("firpfbch_cccf_analyzer_run", None, _vp, _u, _cf_p)
+_sig("firpfbch_cccf_analyzer_execute_block", None, _vp, _vp, _u, _vp)
+_sig("firpfbch_cccf_synthesizer_execute_block", None, _vp, _vp, _u, _vp)
+_sig("firpfbch_cccf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
 _sig("firfilt_crcf_create", _vp, _f_p, _u)
 _sig("firfilt_crcf_create_kaiser", _vp, _u, _fl, _fl, _fl)
 _sig("firfilt_crcf_create_rnyquist", _vp, _i, _u, _u, _fl, _fl)
@@ -397,6 +410,71 @@ class firpfbch_crcf(_Handle):
     def set_state(self, hist):
         lib.firpfbch_crcf_set_state(self._h, _c64(hist))
 
+
+
+class firpfbch_cccf(_Handle):
+    """liquid.h:5660-5728, complex taps (+ analyzer_push / analyzer_run, firpfbch.c:369, :383)."""
+    _destroy = "firpfbch_cccf_destroy"
+
+    def __init__(self, type, M, p, h):
+        self.type, self.M = type, M
+        super().__init__(lib.firpfbch_cccf_create(type, M, p, _c64(h)))
+
+    @classmethod
+    def create(cls, type, M, p, h):
+        return cls(type, M, p, h)
+
+    @classmethod
+    def create_kaiser(cls, type, M, m, As):
+        q = cls.__new__(cls)
+        q.type, q.M = type, M
+        _Handle.__init__(q, lib.firpfbch_cccf_create_kaiser(type, M, m, As))
+        return q
+
+    @classmethod
+    def create_rnyquist(cls, type, M, m, beta, ftype=LIQUID_FIRFILT_RRC):
+        q = cls.__new__(cls)
+        q.type, q.M = type, M
+        _Handle.__init__(q, lib.firpfbch_cccf_create_rnyquist(type, M, m, beta, ftype))
+        return q
+
+    def reset(self):
+        lib.firpfbch_cccf_reset(self._h)
+
+    def print(self):
+        lib.firpfbch_cccf_print(self._h)
+
+    def analyzer_execute(self, x):
+        y = np.empty(self.M, np.complex64)
+        lib.firpfbch_cccf_analyzer_execute(self._h, _c64(x), y)
+        return y
+
+    def synthesizer_execute(self, x):
+        y = np.empty(self.M, np.complex64)
+        lib.firpfbch_cccf_synthesizer_execute(self._h, _c64(x), y)
+        return y
+
+    def analyzer_push(self, v):
+        v = complex(v)
+        lib.firpfbch_cccf_analyzer_push(self._h, _cf(v.real, v.imag))
+
+    def analyzer_run(self, k):
+        y = np.empty(self.M, np.complex64)
+        lib.firpfbch_cccf_analyzer_run(self._h, k, y)
+        return y
+
+    def execute_block(self, x, out=None):
+        x = _c64(x)
+        n_frames = x.size // self.M
+        assert n_frames * self.M == x.size
+        y = out if out is not None else np.empty(x.size, np.complex64)
+        fn = (lib.firpfbch_cccf_analyzer_execute_block if self.type == LIQUID_ANALYZER
+              else lib.firpfbch_cccf_synthesizer_execute_block)
+        fn(self._h, _ptr(x), n_frames, _ptr(y))
+        return y.reshape(n_frames, self.M) if out is None else y
+
+    def execute_block_dev(self, d_x, n_frames, d_y, stream=0):
+        lib.firpfbch_cccf_execute_block_dev(self._h, d_x, n_frames, d_y, stream)
 
 class firfilt_crcf(_Handle):
     """liquid.h:1985-2074."""

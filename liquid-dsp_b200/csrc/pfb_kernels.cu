@@ -10,6 +10,20 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// acc += tap * sample for real (crcf) and complex (cccf: plain product, no conjugate) taps
+__device__ __forceinline__ void tap_mac(float c, float2 s, float &re, float &im)
+{
+    re = fmaf(c, s.x, re);
+    im = fmaf(c, s.y, im);
+}
+__device__ __forceinline__ void tap_mac(float2 c, float2 s, float &re, float &im)
+{
+    re = fmaf(c.x, s.x, re);
+    re = fmaf(-c.y, s.y, re);
+    im = fmaf(c.x, s.y, im);
+    im = fmaf(c.y, s.x, im);
+}
+
 __global__ void __launch_bounds__(kThreads)
 pfbch2_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
                   const float *__restrict__ taps, float2 *__restrict__ X, unsigned int M, unsigned int L,
@@ -64,9 +78,10 @@ pfbch2_synth_fir_kernel(const float2 *__restrict__ hist, const float2 *__restric
     }
 }
 
+template <typename TapT>
 __global__ void __launch_bounds__(kThreads)
 pfbch_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
-                 const float *__restrict__ taps, float2 *__restrict__ X, unsigned int M, unsigned int p,
+                 const TapT *__restrict__ taps, float2 *__restrict__ X, unsigned int M, unsigned int p,
                  unsigned long long n_frames, unsigned int phase, unsigned int first, unsigned int k)
 {
     const unsigned long long total = n_frames * M;
@@ -84,21 +99,20 @@ pfbch_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, 
         long long d = (C - 1 - rr) % (long long)M;
         if (d < 0) d += M;
         const long long last = C - 1 - d - (long long)phase;    // index into x of the newest sample
-        const float *tp = taps + i;
+        const TapT *tp = taps + i;
         float re = 0.f, im = 0.f;
         for (unsigned int n = 0; n < p; n++) {
             float2 smp = lcd::ld_stream(hist, x, last - (long long)n * M, H);
-            float c = __ldg(tp + (size_t)n * M);
-            re = fmaf(c, smp.x, re);
-            im = fmaf(c, smp.y, im);
+            tap_mac(__ldg(tp + (size_t)n * M), smp, re, im);
         }
         X[gid] = make_float2(re, im);
     }
 }
 
+template <typename TapT>
 __global__ void __launch_bounds__(kThreads)
 pfbch_synth_fir_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ v, int hist_rows,
-                       const float *__restrict__ taps, float2 *__restrict__ y, unsigned int M, unsigned int p,
+                       const TapT *__restrict__ taps, float2 *__restrict__ y, unsigned int M, unsigned int p,
                        unsigned long long n_frames)
 {
     const unsigned long long total = n_frames * M;
@@ -110,9 +124,7 @@ pfbch_synth_fir_kernel(const float2 *__restrict__ hist, const float2 *__restrict
         for (unsigned int n = 0; n < p; n++) {
             long long r = s - (long long)n;
             float2 smp = (r >= 0) ? __ldg(v + (size_t)r * M + i) : __ldg(hist + (size_t)(hist_rows + r) * M + i);
-            float c = __ldg(taps + (size_t)n * M + i);
-            re = fmaf(c, smp.x, re);
-            im = fmaf(c, smp.y, im);
+            tap_mac(__ldg(taps + (size_t)n * M + i), smp, re, im);
         }
         y[gid] = make_float2(re, im);
     }
@@ -151,14 +163,29 @@ void launch_pfbch_mac(const float2 *d_hist, const float2 *d_x, int H, const floa
                       unsigned int M, unsigned int p, unsigned long long n_frames, unsigned int phase,
                       unsigned int first, unsigned int k, cudaStream_t st)
 {
-    pfbch_mac_kernel<<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, p, n_frames, phase, first, k);
+    pfbch_mac_kernel<float><<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, p, n_frames, phase, first, k);
+    LC_LAUNCH_CHECK();
+}
+
+void launch_pfbch_mac_cc(const float2 *d_hist, const float2 *d_x, int H, const float2 *d_taps, float2 *d_X,
+                         unsigned int M, unsigned int p, unsigned long long n_frames, unsigned int phase,
+                         unsigned int first, unsigned int k, cudaStream_t st)
+{
+    pfbch_mac_kernel<float2><<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, p, n_frames, phase, first, k);
     LC_LAUNCH_CHECK();
 }
 
 void launch_pfbch_synth_fir(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float *d_taps,
                             float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st)
 {
-    pfbch_synth_fir_kernel<<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, p, n_frames);
+    pfbch_synth_fir_kernel<float><<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, p, n_frames);
+    LC_LAUNCH_CHECK();
+}
+
+void launch_pfbch_synth_fir_cc(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float2 *d_taps,
+                               float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st)
+{
+    pfbch_synth_fir_kernel<float2><<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, p, n_frames);
     LC_LAUNCH_CHECK();
 }
 

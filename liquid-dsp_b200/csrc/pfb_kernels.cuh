@@ -27,5 +27,12 @@ void launch_pfbch_mac(const float2 *d_hist, const float2 *d_x, int H, const floa
 void launch_pfbch_synth_fir(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float *d_taps,
                             float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st);
 
+// the same two with complex taps (firpfbch_cccf): plain complex product, no conjugate
+void launch_pfbch_mac_cc(const float2 *d_hist, const float2 *d_x, int H, const float2 *d_taps, float2 *d_X,
+                         unsigned int M, unsigned int p, unsigned long long n_frames, unsigned int phase,
+                         unsigned int first, unsigned int k, cudaStream_t st);
+void launch_pfbch_synth_fir_cc(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float2 *d_taps,
+                               float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st);
+
 }  // namespace pfb
 }  // namespace lc

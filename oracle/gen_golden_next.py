@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Golden vectors for the root-Nyquist Kaiser prototypes, generated HERE by the
+"""Golden vectors for the first "next" row of SURVEY.md 8(f): the root-Nyquist Kaiser prototypes and
+firpfbch_cccf (complex taps), generated HERE by the
 real reference compiled into oracle/_ref (make -C oracle ref) and committed as
-tests/golden/ref_outputs_rnyquist.npz.  /root/reference does not exist on the GPU box; this script is
+tests/golden/ref_outputs_next.npz.  /root/reference does not exist on the GPU box; this script is
 the record of how the fixture was made.
 
   taps_*     liquid_firdes_arkaiser / liquid_firdes_rkaiser / liquid_firdes_prototype(KAISER) from the
@@ -11,6 +12,7 @@ the record of how the fixture was made.
              baseline build (with FMA contraction the rkaiser search settles on a rho that differs in the
              5th digit, which moves every tap by ~1e-5: fine for a filter, useless as a pin)
   scalars    estimate_req_filter_As, rkaiser_approximate_rho, liquid_filter_isi points
+  cccf_*     firpfbch_cccf_create with seeded complex taps: analysis and synthesis outputs
 """
 import ctypes as C
 import os
@@ -68,6 +70,16 @@ for ftype, name in ((ARKAISER, "arkaiser"), (RKAISER, "rkaiser")):
         out["pfbch_%s_s_M%d_m%d_y" % (name, M, m)] = O.ref_firpfbch_frames(O.SYNTHESIZER, M, x, rnyquist=(m, beta, ftype))
         out["pfbch_%s_M%d_m%d_args" % (name, M, m)] = np.array([M, m, beta, ftype], np.float64)
 
-path = os.path.join(HERE, "..", "tests", "golden", "ref_outputs_rnyquist.npz")
+# firpfbch_cccf with genuinely complex taps
+rng = np.random.default_rng(20261018)
+for M, p in [(8, 6), (16, 8), (12, 5), (64, 4)]:
+    h = ((rng.standard_normal(M * p) + 1j * rng.standard_normal(M * p)) / p).astype(np.complex64)
+    x = O.synth_input(40 * M, seed=0x5EED8000 + M)
+    out["cccf_M%d_p%d_h" % (M, p)] = h
+    out["cccf_M%d_p%d_x" % (M, p)] = x
+    out["cccf_M%d_p%d_a_y" % (M, p)] = O.ref_firpfbch_cccf_frames(O.ANALYZER, M, p, h, x)
+    out["cccf_M%d_p%d_s_y" % (M, p)] = O.ref_firpfbch_cccf_frames(O.SYNTHESIZER, M, p, h, x)
+
+path = os.path.join(HERE, "..", "tests", "golden", "ref_outputs_next.npz")
 np.savez_compressed(path, **out)
 print("wrote", os.path.normpath(path), "%d arrays, %.0f KB" % (len(out), os.path.getsize(path) / 1024))

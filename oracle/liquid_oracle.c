@@ -740,6 +740,83 @@ void orc_firpfbch_execute_frames(orc_firpfbch q, const orc_cf *x, unsigned int n
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* firpfbch_cccf: the same channelizer with complex taps                                 */
+/* src/multichannel/src/firpfbch_cccf.c:35-52 instantiates firpfbch.c with TC = float     */
+/* complex and dotprod_cccf (src/dotprod/src/dotprod_cccf.c -> dotprod.c:162-168:         */
+/* r += h[i] * x[i], plain complex product, no conjugate)                                 */
+/* ------------------------------------------------------------------------------------ */
+
+struct orc_firpfbch_cccf_s {
+    int type;
+    unsigned int M, p;
+    orc_cf *sub;                /* [M][p], newest tap last */
+    orc_cf *w;                  /* [M][p] windows */
+    unsigned int filter_index;
+    orc_cf *X, *x;
+};
+
+static orc_cf dot_cccf(const orc_cf *h, const orc_cf *x, unsigned int n)
+{
+    orc_cf r = cf(0.0f, 0.0f);
+    for (unsigned int i = 0; i < n; i++) {
+        r.re += h[i].re * x[i].re - h[i].im * x[i].im;
+        r.im += h[i].re * x[i].im + h[i].im * x[i].re;
+    }
+    return r;
+}
+
+/* firpfbch.c:73-142 with complex h */
+orc_firpfbch_cccf orc_firpfbch_cccf_create(int type, unsigned int M, unsigned int p, const orc_cf *h)
+{
+    if ((type != ORC_ANALYZER && type != ORC_SYNTHESIZER) || M == 0 || p == 0) return NULL;
+    orc_firpfbch_cccf q = xmalloc(sizeof *q);
+    q->type = type; q->M = M; q->p = p;
+    q->sub = xmalloc((size_t)M * p * sizeof *q->sub);
+    for (unsigned int i = 0; i < M; i++)
+        for (unsigned int n = 0; n < p; n++)
+            q->sub[(size_t)i * p + (p - 1 - n)] = h[i + n * M];      /* firpfbch.c:115-124 */
+    q->w = xmalloc((size_t)M * p * sizeof *q->w);
+    q->X = xmalloc(M * sizeof *q->X);
+    q->x = xmalloc(M * sizeof *q->x);
+    memset(q->w, 0, (size_t)M * p * sizeof *q->w);
+    q->filter_index = M - 1;
+    return q;
+}
+
+void orc_firpfbch_cccf_destroy(orc_firpfbch_cccf q)
+{
+    if (q) { free(q->sub); free(q->w); free(q->X); free(q->x); free(q); }
+}
+
+/* firpfbch.c:346-409 (analyzer: M pushes, run with k = 0) and :314-336 (synthesizer) */
+void orc_firpfbch_cccf_execute_frames(orc_firpfbch_cccf q, const orc_cf *x, unsigned int n_frames, orc_cf *y)
+{
+    const unsigned int M = q->M, p = q->p;
+    for (unsigned int t = 0; t < n_frames; t++) {
+        const orc_cf *xt = x + (size_t)t * M;
+        orc_cf *yt = y + (size_t)t * M;
+        if (q->type == ORC_ANALYZER) {
+            for (unsigned int i = 0; i < M; i++) {
+                win_push(q->w + (size_t)q->filter_index * p, p, xt[i]);
+                q->filter_index = (q->filter_index + M - 1) % M;
+            }
+            for (unsigned int i = 0; i < M; i++)
+                q->X[M - i - 1] = dot_cccf(q->sub + (size_t)i * p, q->w + (size_t)i * p, p);
+            orc_fft_run(M, q->X, q->x, ORC_FFT_FORWARD);
+            memcpy(yt, q->x, M * sizeof *yt);
+        } else {
+            memcpy(q->X, xt, M * sizeof *q->X);
+            orc_fft_run(M, q->X, q->x, ORC_FFT_BACKWARD);
+            for (unsigned int i = 0; i < M; i++) {
+                orc_cf *w = q->w + (size_t)i * p;
+                win_push(w, p, q->x[i]);
+                yt[i] = dot_cccf(q->sub + (size_t)i * p, w, p);
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* firpfbch2_crcf: channelizer with output rate 2 Fs / M                                 */
 /* ------------------------------------------------------------------------------------ */
 

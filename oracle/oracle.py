@@ -104,6 +104,11 @@ def lib():
         L.orc_firpfbch_create_rrc.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float]
         L.orc_firpfbch_create_rnyquist.restype = C.c_void_p
         L.orc_firpfbch_create_rnyquist.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_int]
+        L.orc_firpfbch_cccf_create.restype = C.c_void_p
+        L.orc_firpfbch_cccf_create.argtypes = [C.c_int, C.c_uint, C.c_uint, c_cf_p]
+        L.orc_firpfbch_cccf_destroy.argtypes = [C.c_void_p]
+        L.orc_firpfbch_cccf_execute_frames.restype = None
+        L.orc_firpfbch_cccf_execute_frames.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
         L.orc_firpfbch_destroy.argtypes = [C.c_void_p]; L.orc_firpfbch_reset.argtypes = [C.c_void_p]
         L.orc_firpfbch_execute_frames.restype = None
         L.orc_firpfbch_execute_frames.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
@@ -270,6 +275,21 @@ class Firpfbch(_Obj):
         return y
 
 
+class FirpfbchCccf(_Obj):
+    """firpfbch_cccf: complex taps h[M*p]"""
+    _destroy = "orc_firpfbch_cccf_destroy"
+
+    def __init__(self, type, M, p, h):
+        self.type, self.M = type, M
+        super().__init__(lib().orc_firpfbch_cccf_create(type, M, p, _cf(h)))
+
+    def execute_frames(self, x):
+        x = _cf(x).reshape(-1, self.M)
+        y = np.empty_like(x)
+        lib().orc_firpfbch_cccf_execute_frames(self.h, x, x.shape[0], y)
+        return y
+
+
 class Firpfbch2(_Obj):
     _destroy = "orc_firpfbch2_destroy"
 
@@ -420,6 +440,24 @@ def ref_firpfbch_frames(type, M, x, p=None, h=None, kaiser=None, rnyquist=None):
     for t in range(x.shape[0]):
         fn(q, x[t], y[t])
     R.firpfbch_crcf_destroy(q)
+    return y
+
+
+def ref_firpfbch_cccf_frames(type, M, p, h, x):
+    """the compiled reference's firpfbch_cccf (complex taps h[M*p]) over whole frames"""
+    R = ref()
+    R.firpfbch_cccf_create.restype = C.c_void_p
+    R.firpfbch_cccf_create.argtypes = [C.c_int, C.c_uint, C.c_uint, c_cf_p]
+    R.firpfbch_cccf_analyzer_execute.argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+    R.firpfbch_cccf_synthesizer_execute.argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+    R.firpfbch_cccf_destroy.argtypes = [C.c_void_p]
+    q = C.c_void_p(R.firpfbch_cccf_create(type, M, p, _cf(h)))
+    x = _cf(x).reshape(-1, M)
+    y = np.empty_like(x)
+    fn = R.firpfbch_cccf_analyzer_execute if type == ANALYZER else R.firpfbch_cccf_synthesizer_execute
+    for t in range(x.shape[0]):
+        fn(q, x[t], y[t])
+    R.firpfbch_cccf_destroy(q)
     return y
 
 

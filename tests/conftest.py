@@ -32,8 +32,8 @@ def refout():
 @pytest.fixture(scope="session")
 def refrn():
     """root-Nyquist Kaiser prototypes and channelizers built on them, from the compiled reference
-    (oracle/gen_golden_rnyquist.py)"""
-    return dict(np.load(os.path.join(GOLDEN, "ref_outputs_rnyquist.npz")))
+    (oracle/gen_golden_next.py)"""
+    return dict(np.load(os.path.join(GOLDEN, "ref_outputs_next.npz")))
 
 
 @pytest.fixture(scope="session")

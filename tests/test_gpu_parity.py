@@ -428,6 +428,59 @@ def test_pfbch_rnyquist_kaiser_prototypes_vs_reference(L, orc, refrn):
     assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
 
 
+# ------------------------------------------------------------------ firpfbch_cccf
+def test_pfbch_cccf_vs_reference_and_oracle(L, orc, refrn):
+    """complex taps: generic complex-tap kernels against the compiled reference's outputs and the oracle,
+    in one block and split across calls (state carry)"""
+    for name in sorted(k for k in refrn if k.startswith("cccf_") and k.endswith("_h")):
+        M, p = (int(v[1:]) for v in name.split("_")[1:3])
+        h, x = refrn[name], refrn["cccf_M%d_p%d_x" % (M, p)]
+        for typ, key, otyp in ((L.LIQUID_ANALYZER, "a", orc.ANALYZER), (L.LIQUID_SYNTHESIZER, "s", orc.SYNTHESIZER)):
+            want = refrn["cccf_M%d_p%d_%s_y" % (M, p, key)]
+            q = L.firpfbch_cccf.create(typ, M, p, h)
+            got = q.execute_block(x)
+            assert np.abs(got - want).max() <= 4e-6 * np.abs(want).max(), (M, p, key)
+            q.reset()
+            parts = np.concatenate([q.execute_block(x[:7 * M]), q.execute_block(x[7 * M:8 * M]), q.execute_block(x[8 * M:])])
+            assert np.array_equal(parts, got)
+            worc = orc.FirpfbchCccf(otyp, M, p, h).execute_frames(x)
+            assert np.abs(got - worc).max() <= 4e-6 * np.abs(worc).max()
+            # one frame at a time through the reference's own entry points
+            q.reset()
+            fn = q.analyzer_execute if typ == L.LIQUID_ANALYZER else q.synthesizer_execute
+            single = np.stack([fn(x[t * M:(t + 1) * M]) for t in range(5)])
+            assert np.array_equal(single, got[:5])
+
+
+def test_pfbch_cccf_real_taps_take_the_crcf_path(L, orc, monkeypatch):
+    """create_kaiser / create_rnyquist (real prototypes) equal firpfbch_crcf bit for bit (same kernels), and
+    the generic complex-tap kernels agree with them to float rounding; push/run alignment works too"""
+    M, m = 256, 5
+    x = orc.synth_input(16 * 40 * M // 16, seed=0xCD)
+    for typ in (L.LIQUID_ANALYZER, L.LIQUID_SYNTHESIZER):
+        a = L.firpfbch_cccf.create_kaiser(typ, M, m, 60.0).execute_block(x)
+        b = L.firpfbch_crcf.create_kaiser(typ, M, m, 60.0).execute_block(x)
+        assert np.array_equal(a, b)
+        monkeypatch.setenv("LIQUID_CUDA_CCCF_GENERIC", "1")
+        g = L.firpfbch_cccf.create_kaiser(typ, M, m, 60.0).execute_block(x)
+        monkeypatch.delenv("LIQUID_CUDA_CCCF_GENERIC")
+        assert np.abs(g - b).max() <= 2e-6 * np.abs(b).max()
+    a = L.firpfbch_cccf.create_rnyquist(L.LIQUID_ANALYZER, 8, 3, 0.4, L.LIQUID_FIRFILT_ARKAISER).execute_block(x[:320])
+    b = L.firpfbch_crcf.create_rnyquist(L.LIQUID_ANALYZER, 8, 3, 0.4, L.LIQUID_FIRFILT_ARKAISER).execute_block(x[:320])
+    assert np.array_equal(a, b)
+    # analyzer_push / analyzer_run(k) with complex taps against the oracle-free identity run(0) after M pushes
+    rng = np.random.default_rng(3)
+    M, p = 8, 4
+    h = ((rng.standard_normal(M * p) + 1j * rng.standard_normal(M * p)) / p).astype(np.complex64)
+    q = L.firpfbch_cccf.create(L.LIQUID_ANALYZER, M, p, h)
+    xs = orc.synth_input(3 * M, seed=0xCE)
+    want = L.firpfbch_cccf.create(L.LIQUID_ANALYZER, M, p, h).execute_block(xs)
+    for t in range(3):
+        for v in xs[t * M:(t + 1) * M]:
+            q.analyzer_push(v)
+        assert np.array_equal(q.analyzer_run(0), want[t])
+
+
 # ------------------------------------------------------------------ cluster-of-8 M=4096 kernel specifics
 @pytest.mark.parametrize("m", [4, 7, 9])
 def test_pfbch2_cluster_4096_vs_oracle_odd_splits(L, orc, m):

@@ -334,3 +334,29 @@ def test_fixture_pfbch_rnyquist_channelizers(orc, refrn):
             want = refrn["pfbch_%s_%s_M%d_m%d_y" % (proto, key, M, m)]
             got = orc.Firpfbch(typ, M, rnyquist=(m, np.float32(beta), ftype)).execute_frames(x)
             assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max(), (stem, key)
+
+
+# ------------------------------------------------------------------ firpfbch_cccf
+def _cccf_cases(refrn):
+    for name in sorted(k for k in refrn if k.startswith("cccf_") and k.endswith("_h")):
+        M, p = (int(v[1:]) for v in name.split("_")[1:3])
+        yield M, p, refrn[name], refrn["cccf_M%d_p%d_x" % (M, p)]
+
+
+def test_fixture_pfbch_cccf(orc, refrn):
+    for M, p, h, x in _cccf_cases(refrn):
+        for typ, key in ((orc.ANALYZER, "a"), (orc.SYNTHESIZER, "s")):
+            want = refrn["cccf_M%d_p%d_%s_y" % (M, p, key)]
+            got = orc.FirpfbchCccf(typ, M, p, h).execute_frames(x)
+            assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max(), (M, p, key)
+
+
+def test_pfbch_cccf_real_taps_equal_crcf(orc):
+    """with real taps the cccf channelizer is the crcf one"""
+    M, m = 16, 3
+    h = orc.firdes_kaiser(2 * M * m + 1, 0.5 / M, 60.0)[: 2 * M * m]
+    x = orc.synth_input(30 * M, seed=0xCC)
+    for typ in (orc.ANALYZER, orc.SYNTHESIZER):
+        a = orc.FirpfbchCccf(typ, M, 2 * m, h.astype(np.complex64)).execute_frames(x)
+        b = orc.Firpfbch(typ, M, p=2 * m, h=h).execute_frames(x)
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
