@@ -11,22 +11,13 @@
 #include <cmath>
 
 #include "lc_common.cuh"
+#include "fft_device.cuh"
 #include "../../include/liquid_cuda.h"
 
 namespace {
 
-constexpr int kFftThreads = 256;
-
-// post-processing of the last stage: 0 none, 1 divide by a, 2 multiply by a then by b
-__device__ __forceinline__ float2 fft_post(float2 v, int mode, float a, float b)
-{
-    if (mode == 1) { v.x = v.x / a; v.y = v.y / a; }
-    else if (mode == 2) { v.x *= a; v.y *= a; v.x *= b; v.y *= b; }
-    return v;
-}
-
-// multiply by s*j  (s = +1 or -1)
-__device__ __forceinline__ float2 mul_sj(float2 v, float s) { return make_float2(-s * v.y, s * v.x); }
+using lcfft::fft_post;
+using lcfft::kFftThreads;
 
 // Stockham autosort FFT of n = 2^log2n points per transform, `per_cta` transforms per CTA.
 // smem: 2 * per_cta * n float2.
@@ -47,48 +38,7 @@ fft_pow2_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const floa
     }
     __syncthreads();
 
-    float2 *in = buf0, *out = buf1;
-    unsigned int Ns = 1;
-    unsigned int stages4 = log2n / 2;
-    for (unsigned int s = 0; s < stages4; s++, Ns <<= 2) {
-        const unsigned int q = n >> 2;                 // butterflies per transform
-        for (unsigned int i = threadIdx.x; i < per_cta * q; i += blockDim.x) {
-            unsigned int f = i / q, j = i % q;
-            const float2 *src = in + (size_t)f * n;
-            float2 *dst = out + (size_t)f * n;
-            unsigned int k = j & (Ns - 1);
-            unsigned int tstep = k * (n / (Ns << 2)); // index of W_n^(k n/(4Ns)) = W_{4Ns}^k
-            float2 v0 = src[j];
-            float2 v1 = lcd::cmul(src[j + q], tw[tstep]);
-            float2 v2 = lcd::cmul(src[j + 2 * q], tw[2 * tstep]);
-            float2 v3 = lcd::cmul(src[j + 3 * q], tw[3 * tstep]);
-            float2 a02 = lcd::cadd(v0, v2), s02 = lcd::csub(v0, v2);
-            float2 a13 = lcd::cadd(v1, v3), s13 = mul_sj(lcd::csub(v1, v3), sgn);
-            unsigned int d = ((j - k) << 2) + k;
-            dst[d]          = lcd::cadd(a02, a13);
-            dst[d + Ns]     = lcd::cadd(s02, s13);
-            dst[d + 2 * Ns] = lcd::csub(a02, a13);
-            dst[d + 3 * Ns] = lcd::csub(s02, s13);
-        }
-        __syncthreads();
-        float2 *t = in; in = out; out = t;
-    }
-    if (log2n & 1) {
-        const unsigned int q = n >> 1;
-        for (unsigned int i = threadIdx.x; i < per_cta * q; i += blockDim.x) {
-            unsigned int f = i / q, j = i % q;
-            const float2 *src = in + (size_t)f * n;
-            float2 *dst = out + (size_t)f * n;
-            unsigned int k = j & (Ns - 1);
-            float2 v0 = src[j];
-            float2 v1 = lcd::cmul(src[j + q], tw[k * (n / (Ns << 1))]);
-            unsigned int d = ((j - k) << 1) + k;
-            dst[d]      = lcd::cadd(v0, v1);
-            dst[d + Ns] = lcd::csub(v0, v1);
-        }
-        __syncthreads();
-        float2 *t = in; in = out; out = t;
-    }
+    float2 *in = lcfft::stockham_pow2(buf0, buf1, tw, n, log2n, per_cta, sgn);
 
     for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
         unsigned long long b = first + i / n;
@@ -159,10 +109,9 @@ void FftPlanDev::run(const float2 *d_x, float2 *d_y, unsigned long long batch, c
         LC_LAUNCH_CHECK();
         return;
     }
-    if (is_pow2(n) && (size_t)n * 16 <= 200 * 1024) {
-        unsigned int per_cta = 1;
-        while (per_cta * n < 2048 && per_cta < batch) per_cta <<= 1;   // aim at 2048 points per CTA
-        size_t smem = (size_t)2 * per_cta * n * sizeof(float2);
+    if (lcfft::pow2_in_smem(n)) {
+        const unsigned int per_cta = lcfft::per_cta_for(n, batch);     // aim at 2048 points per CTA
+        const size_t smem = lcfft::smem_for(n, per_cta);
         const unsigned long long max_grid = 1ull << 30;
         unsigned long long done = 0;
         while (done < batch) {      // grid.x limit is 2^31-1; keep launches below 2^30 CTAs

@@ -33,6 +33,23 @@ struct firpfbch_crcf_s {
     cudaStream_t stream = nullptr;
 };
 
+namespace {
+
+// shape-generic analyzer step: n runs of (M pushes, run(k)) -- one kernel when M is a power of two that
+// fits shared memory, else polyphase MAC into y followed by an in-place forward DFT; unscaled
+void analyze_generic(firpfbch_crcf q, const float2 *d_hist, const float2 *d_x, float2 *d_y, unsigned long long n,
+                     unsigned int phase, unsigned int first, unsigned int k, cudaStream_t st)
+{
+    if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL")) {
+        lc::pfb::launch_pfbch_analyze_pow2(d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_tw, d_y, q->M, q->p, n, phase, first, k, st);
+        return;
+    }
+    lc::pfb::launch_pfbch_mac(d_hist, d_x, (int)q->H, q->d_taps, d_y, q->M, q->p, n, phase, first, k, st);
+    q->fft.run(d_y, d_y, n, st);
+}
+
+}  // namespace
+
 extern "C" {
 
 firpfbch_crcf firpfbch_crcf_create(int _type, unsigned int _M, unsigned int _p, float *_h)
@@ -179,11 +196,9 @@ void firpfbch_crcf_execute_block_dev(firpfbch_crcf _q, const void *_d_x, unsigne
             done = (unsigned long long)lc::pfb::launch_pfbch_fused(_q->d_hist, d_x, (int)_q->H, _q->d_taps, _q->d_tw_fused,
                                                                    d_y, _q->M, _q->p, _n_frames, 1, 0, st);
         if (done < _n_frames) {
-            // shape-generic path (and the < 16 frames the fused kernel leaves): MAC into y, forward
-            // FFT in place, unscaled
-            lc::pfb::launch_pfbch_mac(_q->d_hist, d_x, (int)_q->H, _q->d_taps, d_y + done * _q->M, _q->M, _q->p,
-                                      _n_frames - done, _q->phase, (unsigned int)((done + 1) * _q->M), 0, st);
-            _q->fft.run(d_y + done * _q->M, d_y + done * _q->M, _n_frames - done, st);
+            // shape-generic path (and the < 16 frames the fused kernel leaves)
+            analyze_generic(_q, _q->d_hist, d_x, d_y + done * _q->M, _n_frames - done, _q->phase,
+                            (unsigned int)((done + 1) * _q->M), 0, st);
         }
         lc::roll_history(_q->d_hist, _q->H, _q->hist_tmp, d_x, _n_frames * _q->M, st);
     } else {
@@ -228,9 +243,7 @@ void firpfbch_crcf_execute_streams_dev(firpfbch_crcf _q, const void *_d_x, unsig
         if (done < _n_frames) {
             for (unsigned int s = 0; s < _n_streams; s++) {
                 float2 *ys = d_y + s * stride + done * M;
-                lc::pfb::launch_pfbch_mac(_q->d_zero, d_x + s * stride, (int)_q->H, _q->d_taps, ys, M, p,
-                                          _n_frames - done, 0, (unsigned int)((done + 1) * M), 0, st);
-                _q->fft.run(ys, ys, _n_frames - done, st);
+                analyze_generic(_q, _q->d_zero, d_x + s * stride, ys, _n_frames - done, 0, (unsigned int)((done + 1) * M), 0, st);
             }
         }
     } else {
@@ -300,9 +313,7 @@ void firpfbch_crcf_analyzer_run(firpfbch_crcf _q, unsigned int _k, liquid_float_
     if (_q->type != LIQUID_ANALYZER) lc::fatal("firpfbch_crcf_analyzer_run", "object is not an analyzer");
     float2 *d_y = (float2 *)_q->stage_out.get(sizeof(float2) * _q->M);
     // no new samples: one run on the state as it stands (first = 0), alignment index _k
-    lc::pfb::launch_pfbch_mac(_q->d_hist, _q->d_hist /*unused*/, (int)_q->H, _q->d_taps, d_y, _q->M, _q->p, 1,
-                              _q->phase, 0, _k % _q->M, _q->stream);
-    _q->fft.run(d_y, d_y, 1, _q->stream);
+    analyze_generic(_q, _q->d_hist, _q->d_hist /*unused*/, d_y, 1, _q->phase, 0, _k % _q->M, _q->stream);
     LC_CUDA_CHECK(cudaMemcpyAsync(_X, d_y, sizeof(float2) * _q->M, cudaMemcpyDeviceToHost, _q->stream));
     LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
 }

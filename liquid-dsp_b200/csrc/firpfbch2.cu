@@ -51,9 +51,15 @@ void analyze_dev(firpfbch2_crcf q, const float2 *d_hist, const float2 *d_x, int 
         done = (unsigned long long)lc::pfb::launch_pfbch2_cluster(d_hist, d_x, (int)q->H, q->d_taps_scaled, q->d_tw_fused,
                                                                   d_y, q->M, q->L, n_frames, parity0, st);
     if (done == n_frames) return;
-    // shape-generic path (and the 0..3 frames the fused kernel leaves): polyphase MAC into the
-    // output buffer, then an in-place batched backward FFT with /M
+    // shape-generic path (and the few frames the fused kernels leave)
     float2 *d_yr = d_y + done * q->M;
+    if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL")) {
+        // power-of-two M: polyphase MAC, backward FFT and /M in one kernel (shared memory)
+        lc::pfb::launch_pfbch2_analyze_pow2(d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_tw, d_yr, q->M, q->L,
+                                            n_frames - done, parity0, st, (long long)done);
+        return;
+    }
+    // any other M: polyphase MAC into the output buffer, then an in-place batched backward DFT with /M
     lc::pfb::launch_pfbch2_mac(d_hist, d_x, (int)q->H, q->d_taps, d_yr, q->M, q->L, n_frames - done, parity0, st,
                                (long long)done);
     q->fft.run(d_yr, d_yr, n_frames - done, st, /*post: divide*/ 1, (float)q->M, 1.0f);

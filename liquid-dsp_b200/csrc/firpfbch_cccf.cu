@@ -35,6 +35,24 @@ struct firpfbch_cccf_s {
     cudaStream_t stream = nullptr;
 };
 
+namespace {
+
+// complex-tap analyzer step: one kernel when M is a power of two that fits shared memory, else polyphase
+// MAC into y followed by an in-place forward DFT; unscaled
+void analyze_generic_cc(firpfbch_cccf q, const float2 *d_x, float2 *d_y, unsigned long long n, unsigned int first,
+                        unsigned int k, cudaStream_t st)
+{
+    if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL")) {
+        lc::pfb::launch_pfbch_analyze_pow2_cc(q->d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_tw, d_y, q->M, q->p, n,
+                                              q->phase, first, k, st);
+        return;
+    }
+    lc::pfb::launch_pfbch_mac_cc(q->d_hist, d_x, (int)q->H, q->d_taps, d_y, q->M, q->p, n, q->phase, first, k, st);
+    q->fft.run(d_y, d_y, n, st);
+}
+
+}  // namespace
+
 extern "C" {
 
 firpfbch_cccf firpfbch_cccf_create(int _type, unsigned int _M, unsigned int _p, liquid_float_complex *_h)
@@ -165,9 +183,8 @@ void firpfbch_cccf_execute_block_dev(firpfbch_cccf _q, const void *_d_x, unsigne
     float2 *d_y = (float2 *)_d_y;
     const unsigned int M = _q->M, p = _q->p;
     if (_q->type == LIQUID_ANALYZER) {
-        // per frame: M pushes, then run(k = 0): polyphase MAC into y, forward FFT in place, unscaled
-        lc::pfb::launch_pfbch_mac_cc(_q->d_hist, d_x, (int)_q->H, _q->d_taps, d_y, M, p, _n_frames, _q->phase, M, 0, st);
-        _q->fft.run(d_y, d_y, _n_frames, st);
+        // per frame: M pushes, then run(k = 0): polyphase MAC, forward FFT, unscaled
+        analyze_generic_cc(_q, d_x, d_y, _n_frames, M, 0, st);
         lc::roll_history(_q->d_hist, _q->H, _q->hist_tmp, d_x, _n_frames * M, st);
     } else {
         // v = IDFT(X) per frame, then y[s][i] = sum_n h[i + nM] v[s-n][i]; new state = last p rows of v
@@ -240,9 +257,7 @@ void firpfbch_cccf_analyzer_run(firpfbch_cccf _q, unsigned int _k, liquid_float_
     }
     float2 *d_y = (float2 *)_q->stage_out.get(sizeof(float2) * _q->M);
     // no new samples: one run on the state as it stands (first = 0), alignment index _k
-    lc::pfb::launch_pfbch_mac_cc(_q->d_hist, _q->d_hist /*unused*/, (int)_q->H, _q->d_taps, d_y, _q->M, _q->p, 1,
-                                 _q->phase, 0, _k % _q->M, _q->stream);
-    _q->fft.run(d_y, d_y, 1, _q->stream);
+    analyze_generic_cc(_q, _q->d_hist /*unused*/, d_y, 1, 0, _k % _q->M, _q->stream);
     LC_CUDA_CHECK(cudaMemcpyAsync(_X, d_y, sizeof(float2) * _q->M, cudaMemcpyDeviceToHost, _q->stream));
     LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
 }

@@ -5,6 +5,7 @@
 // the shape-agnostic kernels; the shapes the benchmarks run use the fused kernels in
 // pfbch2_fused.cu, which keep the sliding windows in registers.
 #include "pfb_kernels.cuh"
+#include "fft_device.cuh"
 
 namespace {
 
@@ -24,31 +25,62 @@ __device__ __forceinline__ void tap_mac(float2 c, float2 s, float &re, float &im
     im = fmaf(c.y, s.x, im);
 }
 
+// transform input w of frame t (relative to x[0]) of the firpfbch2 analyzer       firpfbch2.c:253-271
+__device__ __forceinline__ float2 pfbch2_mac_elem(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                                                  const float *__restrict__ taps, unsigned int M, unsigned int L,
+                                                  int parity0, long long t, unsigned int w)
+{
+    const unsigned int M2 = M >> 1;
+    const int par = (parity0 + (int)(t & 1)) & 1;
+    const bool lower = w < M2;                      // lower half is pushed on even frames
+    const long long tu = (par == (lower ? 0 : 1)) ? t : t - 1;     // frame of the newest sample
+    const long long off = lower ? (long long)(M2 - 1 - w) : (long long)(M - 1 - w);
+    const float *tp = taps + (size_t)par * L * M + w;
+    float re = 0.f, im = 0.f;
+    for (unsigned int n = 0; n < L; n++) {
+        long long idx = (tu - 2 * (long long)n) * (long long)M2 + off;
+        float2 s = lcd::ld_stream(hist, x, idx, H);
+        float c = __ldg(tp + (size_t)n * M);
+        re = fmaf(c, s.x, re);
+        im = fmaf(c, s.y, im);
+    }
+    return make_float2(re, im);
+}
+
 __global__ void __launch_bounds__(kThreads)
 pfbch2_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
                   const float *__restrict__ taps, float2 *__restrict__ X, unsigned int M, unsigned int L,
                   unsigned long long n_frames, int parity0, long long t_first)
 {
-    const unsigned int M2 = M >> 1;
     const unsigned long long total = n_frames * M;
     for (unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-         gid += (unsigned long long)gridDim.x * blockDim.x) {
-        const long long t = t_first + (long long)(gid / M);     // frame index relative to x[0]
-        const unsigned int w = (unsigned int)(gid % M);
-        const int par = (parity0 + (int)(t & 1)) & 1;
-        const bool lower = w < M2;                      // lower half is pushed on even frames
-        const long long tu = (par == (lower ? 0 : 1)) ? t : t - 1;     // frame of the newest sample
-        const long long off = lower ? (long long)(M2 - 1 - w) : (long long)(M - 1 - w);
-        const float *tp = taps + (size_t)par * L * M + w;
-        float re = 0.f, im = 0.f;
-        for (unsigned int n = 0; n < L; n++) {
-            long long idx = (tu - 2 * (long long)n) * (long long)M2 + off;
-            float2 s = lcd::ld_stream(hist, x, idx, H);
-            float c = __ldg(tp + (size_t)n * M);
-            re = fmaf(c, s.x, re);
-            im = fmaf(c, s.y, im);
-        }
-        X[gid] = make_float2(re, im);
+         gid += (unsigned long long)gridDim.x * blockDim.x)
+        X[gid] = pfbch2_mac_elem(hist, x, H, taps, M, L, parity0, t_first + (long long)(gid / M), (unsigned int)(gid % M));
+}
+
+// firpfbch2 analyzer for power-of-two M in ONE kernel: the polyphase MACs of `per_cta` frames are written
+// straight into shared memory, transformed there (Stockham, backward) and stored divided by M -- the
+// transform input never visits HBM.  Samples are re-read through L1/L2 (2m uses each).
+__global__ void __launch_bounds__(lcfft::kFftThreads)
+pfbch2_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                           const float *__restrict__ taps, const float2 *__restrict__ tw, float2 *__restrict__ y,
+                           unsigned int M, unsigned int log2M, unsigned int L, unsigned int per_cta,
+                           unsigned long long n_frames, int parity0, long long t_first)
+{
+    extern __shared__ float2 smem_f2[];
+    float2 *buf0 = smem_f2, *buf1 = smem_f2 + (size_t)per_cta * M;
+    const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
+    const unsigned int total = per_cta * M;
+    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
+        const unsigned long long f = first + i / M;
+        buf0[i] = (f < n_frames) ? pfbch2_mac_elem(hist, x, H, taps, M, L, parity0, t_first + (long long)f, i % M)
+                                 : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const float2 *res = lcfft::stockham_pow2(buf0, buf1, tw, M, log2M, per_cta, +1.0f);
+    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
+        const unsigned long long f = first + i / M;
+        if (f < n_frames) y[f * M + (i % M)] = lcfft::fft_post(res[i], 1, (float)M, 1.0f);
     }
 }
 
@@ -78,6 +110,32 @@ pfbch2_synth_fir_kernel(const float2 *__restrict__ hist, const float2 *__restric
     }
 }
 
+// transform input u of run s of the firpfbch analyzer (M pushes per run, alignment index k)  firpfbch.c:369-409
+template <typename TapT>
+__device__ __forceinline__ float2 pfbch_mac_elem(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                                                 const TapT *__restrict__ taps, unsigned int M, unsigned int p,
+                                                 unsigned int phase, unsigned int first, unsigned int k,
+                                                 long long s, unsigned int u)
+{
+    const unsigned int i = M - 1 - u;                       // branch
+    const unsigned int win = (i + k) % M;                   // window it reads (firpfbch.c:395)
+    // pushes are numbered from `phase` (push c goes to window M-1-(c mod M), firpfbch.c:369-377);
+    // x[0] is push number `phase`; run s happens after `first` + s*M samples of x, i.e. after
+    // pushes up to C-1
+    const long long C = (long long)phase + (long long)first + s * (long long)M;
+    const long long rr = (long long)(M - 1 - win);
+    long long d = (C - 1 - rr) % (long long)M;
+    if (d < 0) d += M;
+    const long long last = C - 1 - d - (long long)phase;    // index into x of the newest sample
+    const TapT *tp = taps + i;
+    float re = 0.f, im = 0.f;
+    for (unsigned int n = 0; n < p; n++) {
+        float2 smp = lcd::ld_stream(hist, x, last - (long long)n * M, H);
+        tap_mac(__ldg(tp + (size_t)n * M), smp, re, im);
+    }
+    return make_float2(re, im);
+}
+
 template <typename TapT>
 __global__ void __launch_bounds__(kThreads)
 pfbch_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
@@ -86,26 +144,33 @@ pfbch_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, 
 {
     const unsigned long long total = n_frames * M;
     for (unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-         gid += (unsigned long long)gridDim.x * blockDim.x) {
-        const long long s = (long long)(gid / M);
-        const unsigned int u = (unsigned int)(gid % M);         // transform input index
-        const unsigned int i = M - 1 - u;                       // branch
-        const unsigned int win = (i + k) % M;                   // window it reads (firpfbch.c:395)
-        // pushes are numbered from `phase` (push c goes to window M-1-(c mod M), firpfbch.c:369-377);
-        // x[0] is push number `phase`; run s happens after `first` + s*M samples of x, i.e. after
-        // pushes up to C-1
-        const long long C = (long long)phase + (long long)first + s * (long long)M;
-        const long long rr = (long long)(M - 1 - win);
-        long long d = (C - 1 - rr) % (long long)M;
-        if (d < 0) d += M;
-        const long long last = C - 1 - d - (long long)phase;    // index into x of the newest sample
-        const TapT *tp = taps + i;
-        float re = 0.f, im = 0.f;
-        for (unsigned int n = 0; n < p; n++) {
-            float2 smp = lcd::ld_stream(hist, x, last - (long long)n * M, H);
-            tap_mac(__ldg(tp + (size_t)n * M), smp, re, im);
-        }
-        X[gid] = make_float2(re, im);
+         gid += (unsigned long long)gridDim.x * blockDim.x)
+        X[gid] = pfbch_mac_elem<TapT>(hist, x, H, taps, M, p, phase, first, k, (long long)(gid / M), (unsigned int)(gid % M));
+}
+
+// firpfbch analyzer for power-of-two M in ONE kernel (see pfbch2_analyze_pow2_kernel): MAC into shared
+// memory, forward Stockham FFT there, unscaled store
+template <typename TapT>
+__global__ void __launch_bounds__(lcfft::kFftThreads)
+pfbch_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                          const TapT *__restrict__ taps, const float2 *__restrict__ tw, float2 *__restrict__ y,
+                          unsigned int M, unsigned int log2M, unsigned int p, unsigned int per_cta,
+                          unsigned long long n_frames, unsigned int phase, unsigned int first_in, unsigned int k)
+{
+    extern __shared__ float2 smem_f2[];
+    float2 *buf0 = smem_f2, *buf1 = smem_f2 + (size_t)per_cta * M;
+    const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
+    const unsigned int total = per_cta * M;
+    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
+        const unsigned long long f = first + i / M;
+        buf0[i] = (f < n_frames) ? pfbch_mac_elem<TapT>(hist, x, H, taps, M, p, phase, first_in, k, (long long)f, i % M)
+                                 : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const float2 *res = lcfft::stockham_pow2(buf0, buf1, tw, M, log2M, per_cta, -1.0f);
+    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
+        const unsigned long long f = first + i / M;
+        if (f < n_frames) y[f * M + (i % M)] = res[i];
     }
 }
 
@@ -187,6 +252,61 @@ void launch_pfbch_synth_fir_cc(const float2 *d_hist_rows, const float2 *d_v, int
 {
     pfbch_synth_fir_kernel<float2><<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, p, n_frames);
     LC_LAUNCH_CHECK();
+}
+
+namespace {
+template <typename Kern>
+void ensure_big_smem(Kern kern)
+{
+    // transforms above 3072 points need more than the default 48 KB of dynamic shared memory
+    LC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+}
+}  // namespace
+
+bool analyze_pow2_supported(unsigned int M) { return lcfft::pow2_in_smem(M); }
+
+void launch_pfbch2_analyze_pow2(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, const float2 *d_tw,
+                                float2 *d_y, unsigned int M, unsigned int L, unsigned long long n_frames, int parity0,
+                                cudaStream_t st, long long t_first)
+{
+    static bool once = (ensure_big_smem(pfbch2_analyze_pow2_kernel), true);
+    (void)once;
+    const unsigned int per_cta = lcfft::per_cta_for(M, n_frames);
+    const unsigned long long ctas = (n_frames + per_cta - 1) / per_cta;
+    if (ctas >= (1ull << 31)) fatal("firpfbch2_crcf_execute_block", "too many frames for one launch");
+    pfbch2_analyze_pow2_kernel<<<(unsigned int)ctas, lcfft::kFftThreads, lcfft::smem_for(M, per_cta), st>>>(
+        d_hist, d_x, H, d_taps, d_tw, d_y, M, ilog2(M), L, per_cta, n_frames, parity0, t_first);
+    LC_LAUNCH_CHECK();
+}
+
+template <typename TapT>
+static void launch_pfbch_analyze_pow2_t(const float2 *d_hist, const float2 *d_x, int H, const TapT *d_taps,
+                                        const float2 *d_tw, float2 *d_y, unsigned int M, unsigned int p,
+                                        unsigned long long n_frames, unsigned int phase, unsigned int first,
+                                        unsigned int k, cudaStream_t st)
+{
+    static bool once = (ensure_big_smem(pfbch_analyze_pow2_kernel<TapT>), true);
+    (void)once;
+    const unsigned int per_cta = lcfft::per_cta_for(M, n_frames);
+    const unsigned long long ctas = (n_frames + per_cta - 1) / per_cta;
+    if (ctas >= (1ull << 31)) fatal("firpfbch_analyzer_execute_block", "too many frames for one launch");
+    pfbch_analyze_pow2_kernel<TapT><<<(unsigned int)ctas, lcfft::kFftThreads, lcfft::smem_for(M, per_cta), st>>>(
+        d_hist, d_x, H, d_taps, d_tw, d_y, M, ilog2(M), p, per_cta, n_frames, phase, first, k);
+    LC_LAUNCH_CHECK();
+}
+
+void launch_pfbch_analyze_pow2(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, const float2 *d_tw,
+                               float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
+                               unsigned int phase, unsigned int first, unsigned int k, cudaStream_t st)
+{
+    launch_pfbch_analyze_pow2_t<float>(d_hist, d_x, H, d_taps, d_tw, d_y, M, p, n_frames, phase, first, k, st);
+}
+
+void launch_pfbch_analyze_pow2_cc(const float2 *d_hist, const float2 *d_x, int H, const float2 *d_taps, const float2 *d_tw,
+                                  float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
+                                  unsigned int phase, unsigned int first, unsigned int k, cudaStream_t st)
+{
+    launch_pfbch_analyze_pow2_t<float2>(d_hist, d_x, H, d_taps, d_tw, d_y, M, p, n_frames, phase, first, k, st);
 }
 
 }  // namespace pfb

@@ -27,6 +27,20 @@ void launch_pfbch_mac(const float2 *d_hist, const float2 *d_x, int H, const floa
 void launch_pfbch_synth_fir(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float *d_taps,
                             float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st);
 
+// One-kernel analyzers for power-of-two M whose transform fits shared memory (M <= 4096 at 2 buffers):
+// polyphase MAC straight into shared memory, Stockham FFT there, scaled store.  d_tw: the FftPlanDev
+// table of the object (backward for firpfbch2, forward for firpfbch).
+bool analyze_pow2_supported(unsigned int M);
+void launch_pfbch2_analyze_pow2(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, const float2 *d_tw,
+                                float2 *d_y, unsigned int M, unsigned int L, unsigned long long n_frames, int parity0,
+                                cudaStream_t st, long long t_first = 0);
+void launch_pfbch_analyze_pow2(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, const float2 *d_tw,
+                               float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
+                               unsigned int phase, unsigned int first, unsigned int k, cudaStream_t st);
+void launch_pfbch_analyze_pow2_cc(const float2 *d_hist, const float2 *d_x, int H, const float2 *d_taps, const float2 *d_tw,
+                                  float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
+                                  unsigned int phase, unsigned int first, unsigned int k, cudaStream_t st);
+
 // the same two with complex taps (firpfbch_cccf): plain complex product, no conjugate
 void launch_pfbch_mac_cc(const float2 *d_hist, const float2 *d_x, int H, const float2 *d_taps, float2 *d_X,
                          unsigned int M, unsigned int p, unsigned long long n_frames, unsigned int phase,

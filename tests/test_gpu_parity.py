@@ -428,6 +428,29 @@ def test_pfbch_rnyquist_kaiser_prototypes_vs_reference(L, orc, refrn):
     assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
 
 
+# ------------------------------------------------------------------ one-kernel shape-generic analyzers
+@pytest.mark.parametrize("M,m,nfr", [(8, 5, 37), (64, 3, 50), (256, 4, 33), (2048, 3, 19), (512, 6, 21)])
+def test_generic_one_kernel_analyzers_equal_two_kernel_path(L, orc, monkeypatch, M, m, nfr):
+    """power-of-two M without a dedicated fused kernel: MAC + FFT in one kernel (shared memory) gives the
+    same bits as polyphase-MAC kernel + batched FFT kernel, for firpfbch2 and firpfbch analysis, and
+    matches the oracle"""
+    x2 = orc.synth_input(nfr * M // 2, seed=0x61 + M)
+    x1 = orc.synth_input(nfr * M, seed=0x62 + M)
+    q2 = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    q1 = L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    monkeypatch.setenv("LIQUID_CUDA_NO_FUSED", "1")          # keep the dedicated fused kernels out of it
+    one2, one1 = q2.execute_block(x2), q1.execute_block(x1)
+    q2.reset()
+    q1.reset()
+    monkeypatch.setenv("LIQUID_CUDA_TWO_KERNEL", "1")
+    two2, two1 = q2.execute_block(x2), q1.execute_block(x1)
+    monkeypatch.delenv("LIQUID_CUDA_TWO_KERNEL")
+    monkeypatch.delenv("LIQUID_CUDA_NO_FUSED")
+    assert np.array_equal(one2, two2) and np.array_equal(one1, two1)
+    check_channels(one2, orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0).execute_frames(x2), x2)
+    check_channels(one1, orc.Firpfbch(orc.ANALYZER, M, kaiser=(m, 60.0)).execute_frames(x1), x1)
+
+
 # ------------------------------------------------------------------ firpfbch_cccf (SURVEY 8f item 1)
 def test_pfbch_cccf_vs_reference_and_oracle(L, orc, refrn):
     """complex taps: generic complex-tap kernels against the compiled reference's outputs and the oracle,

@@ -3,7 +3,7 @@
 measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
 events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
 
-  python tools/bench_configs.py [c1] [c2] [c4] [c5] [--steps K]
+  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
 """
 import argparse
 import json
@@ -104,6 +104,34 @@ def main():
         L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
         ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
         report("c5: firpfbch2_crcf analysis M=4096 m=9, 2^29-sample segment", n, 24, ms, ln)
+    if "g" in args.configs:
+        # shapes without a dedicated fused kernel: the one-kernel shape-generic analyzers (power-of-two M)
+        for M, m, n in ((256, 4, 1 << 27), (64, 5, 1 << 27), (2048, 3, 1 << 27)):
+            q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+            H = q.get_state_len()
+            x = torch.zeros(2 * (H + n), dtype=torch.float32, device=dev)
+            y = torch.empty(4 * n, dtype=torch.float32, device=dev)
+            L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
+            ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
+            report("g: firpfbch2_crcf analysis M=%d m=%d (shape-generic), 2^27 samples" % (M, m), n, 24, ms, ln)
+            del x, y
+    if "f1" in args.configs:
+        # firpfbch_cccf analysis, M=256, p=10, one stream of 2^27 samples --
+        # (a) a real prototype (create_kaiser): rides the crcf fused kernel; (b) complex taps: generic kernels
+        import numpy as np
+        M, m, n = 256, 5, 1 << 27
+        x = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr(), n, stream=st.cuda_stream)
+        q = L.firpfbch_cccf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+        ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
+        report("f1a: firpfbch_cccf analysis M=256 m=5, real Kaiser prototype (crcf fused kernel), 2^27 samples", n, 16, ms, ln)
+        rng = np.random.default_rng(1)
+        h = ((rng.standard_normal(M * 2 * m) + 1j * rng.standard_normal(M * 2 * m)) / (2 * m)).astype(np.complex64)
+        q = L.firpfbch_cccf.create(L.LIQUID_ANALYZER, M, 2 * m, h)
+        ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
+        report("f1b: firpfbch_cccf analysis M=256 p=10, complex taps (shape-generic MAC + FFT kernels), 2^27 samples", n, 16, ms, ln)
+        del x, y
 
 
 if __name__ == "__main__":
