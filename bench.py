@@ -66,8 +66,9 @@ def workload_name(n_samples, n_gpus):
 # for a region that lasts tens of milliseconds)
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
         self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.period = period
         self.max_mhz = None
         self.thread = None
         try:
@@ -104,7 +105,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:       # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         if self.nv:
@@ -196,6 +197,9 @@ def main():
     ap.add_argument("--ref-log2-samples", type=int, default=22, help="--impl reference samples per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--debug-steps", action="store_true", help="N>1: print every rank's per-step times to stderr")
+    ap.add_argument("--reserve-sms", type=int, default=2,
+                    help="N>1 only: SMs the persistent kernel leaves to the NCCL kernels and the halo launch")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
                     help="c3 = headline (M=1024, m=7); c5 = BASELINE.json configs[4] (M=4096, m=9)")
     args = ap.parse_args()
@@ -219,6 +223,12 @@ def main():
     L.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # The halo is 112-576 KB: one NCCL channel (= one CTA per rank) moves it.  With the default channel
+        # count the send/recv kernel is a grid of CTAs that must all be co-resident with their peers'; next
+        # to a persistent kernel that owns (almost) every SM they are not, and ranks stall each other for a
+        # whole kernel duration.  One channel + --reserve-sms 2 lets the exchange run beside the interior frames.
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "1")
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     n = 1 << args.log2_samples                     # input samples per GPU per step
@@ -243,16 +253,26 @@ def main():
     tail = xbuf[2 * n: 2 * (H + n)]                # last H samples of the local segment
     head = xbuf[: 2 * H]
 
+    # N > 1: the halo exchange and the 4m halo-dependent frames live on a side stream, and the persistent
+    # channelizer kernel leaves two SMs free (--reserve-sms), so that the NCCL send/recv kernels and the
+    # small halo launch run BESIDE the interior frames instead of queueing behind a kernel that owns every SM
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    if world > 1:
+        L.set_reserved_sms(args.reserve_sms)
+
     def step():
         if world > 1:
-            reqs = multi.exchange_halo(dist, head, tail, rank, world)      # NCCL send/recv of 2mM samples
+            with torch.cuda.stream(side):
+                reqs = multi.exchange_halo(dist, head, tail, rank, world)      # NCCL send/recv of 2mM samples
             # interior frames do not see the halo: run them while it is in flight
             q.execute_segment_dev(d_x + 8 * (halo_frames * (M // 2)) - 8 * H, d_x + 8 * halo_frames * (M // 2),
                                   first_frame + halo_frames, n_frames - halo_frames,
                                   d_y + 8 * halo_frames * M, stream.cuda_stream)
-            for r in reqs:
-                r.wait()
-            q.execute_segment_dev(d_halo, d_x, first_frame, halo_frames, d_y, stream.cuda_stream)
+            with torch.cuda.stream(side):
+                for r in reqs:
+                    r.wait()
+                q.execute_segment_dev(d_halo, d_x, first_frame, halo_frames, d_y, side.cuda_stream)
+            stream.wait_stream(side)                      # the step ends when both parts have
         else:
             q.execute_segment_dev(d_halo, d_x, first_frame, n_frames, d_y, stream.cuda_stream)
 
@@ -266,20 +286,25 @@ def main():
         step()
     sync_all()
 
-    sampler = ClockSampler(local_rank)
+    # N > 1: rank 0 alone samples, and less often -- eight processes polling NVML every 2 ms contend for the
+    # driver's locks and stall each other's kernel launches for milliseconds at a time
+    sampler = ClockSampler(local_rank, period=0.002 if world == 1 else 0.010) if rank == 0 else None
     launches0 = L.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    sampler.start()
+    if sampler:
+        sampler.start()
     ev[0].record(stream)
     for i in range(args.steps):
         step()
         ev[i + 1].record(stream)
     sync_all()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     launches = L.launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     if world > 1:
+        if args.debug_steps:
+            print("rank %d step ms: %s" % (rank, " ".join("%.2f" % v for v in step_ms)), file=sys.stderr, flush=True)
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())

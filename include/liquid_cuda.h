@@ -186,6 +186,10 @@ void  liquid_cuda_memcpy_d2h(void *_dst, const void *_src, unsigned long long _b
 void  liquid_cuda_sync(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long liquid_cuda_launch_count(void);
+/* SMs the persistent one-CTA-per-SM kernels leave free (default 0): set to 1-2 when a collective (NCCL
+ * send/recv of the halo) or a side-stream launch should run beside the channelizer kernel, not after it */
+void  liquid_cuda_set_reserved_sms(int _n);
+int   liquid_cuda_get_reserved_sms(void);
 /* fill _x[_n] on the device with the bench's synthetic stream
  * u(n,c) = (splitmix64(seed + 2n + c) >> 40) * 2^-24 - 0.5 ; _first = index of _x[0] in the stream */
 void  liquid_cuda_synth_input_dev(void *_d_x, unsigned long long _seed, unsigned long long _first,

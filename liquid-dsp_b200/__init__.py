@@ -157,6 +157,8 @@ _sig("liquid_cuda_memcpy_h2d", None, _vp, _vp, _ull)
 _sig("liquid_cuda_memcpy_d2h", None, _vp, _vp, _ull)
 _sig("liquid_cuda_sync", None)
 _sig("liquid_cuda_launch_count", _ull)
+_sig("liquid_cuda_set_reserved_sms", None, _i)
+_sig("liquid_cuda_get_reserved_sms", _i)
 _sig("liquid_cuda_synth_input_dev", None, _vp, _ull, _ull, _ull, _vp)
 
 #: names include/liquid_cuda.h declares (checked against the header and the .so by the CPU tests)
@@ -165,6 +167,11 @@ DECLARED_SYMBOLS = sorted(_DECLARED)
 
 def version():
     return lib.liquid_cuda_version().decode()
+
+
+def set_reserved_sms(n):
+    """SMs the persistent kernels leave free for a collective / side-stream launch (default 0)"""
+    lib.liquid_cuda_set_reserved_sms(n)
 
 
 def device_count():

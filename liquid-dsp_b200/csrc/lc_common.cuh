@@ -40,6 +40,14 @@ namespace lc {
 void ensure_device();
 
 extern std::atomic<unsigned long long> g_launches;
+// SMs the persistent one-CTA-per-SM kernels leave free (liquid_cuda_set_reserved_sms): room for a
+// collective's kernels or a small side-stream launch to run beside them instead of after them
+extern std::atomic<int> g_reserved_sms;
+inline int usable_sms(int sms)
+{
+    const int r = g_reserved_sms.load(std::memory_order_relaxed);
+    return (r > 0 && r < sms) ? sms - r : sms;
+}
 inline void count_launch(unsigned long long n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // after every kernel launch

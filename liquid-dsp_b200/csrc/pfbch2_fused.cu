@@ -303,6 +303,7 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
     int dev = 0, sms = 148;
     LC_CUDA_CHECK(cudaGetDevice(&dev));
     LC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms = usable_sms(sms);
     // at least 8 groups (32 frames) per CTA so the history prologue and the pipeline fill amortise
     long long ctas = (n_groups + 7) / 8;
     if (ctas > sms) ctas = sms;

@@ -31,9 +31,11 @@ def exchange_halo(dist, head, tail, rank, world):
     """send `tail` (last halo samples of this rank's segment) to rank+1, receive the left neighbour's
     tail into `head` (rank 0's head stays zero = the reference's reset state).  Returns the pending
     requests so the caller can run the interior frames before waiting."""
-    reqs = []
+    ops = []
     if rank + 1 < world:
-        reqs.append(dist.isend(tail, rank + 1))
+        ops.append(dist.P2POp(dist.isend, tail, rank + 1))
     if rank > 0:
-        reqs.append(dist.irecv(head, rank - 1))
-    return reqs
+        ops.append(dist.P2POp(dist.irecv, head, rank - 1))
+    # one batched group (ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd): the send and the receive of a
+    # middle rank progress together instead of being serialised as two independent operations
+    return dist.batch_isend_irecv(ops) if ops else []
