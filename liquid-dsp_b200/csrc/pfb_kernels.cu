@@ -71,10 +71,45 @@ pfbch2_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__rest
     float2 *buf0 = smem_f2, *buf1 = smem_f2 + (size_t)per_cta * M;
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
     const unsigned int total = per_cta * M;
-    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
-        const unsigned long long f = first + i / M;
-        buf0[i] = (f < n_frames) ? pfbch2_mac_elem(hist, x, H, taps, M, L, parity0, t_first + (long long)f, i % M)
-                                 : make_float2(0.f, 0.f);
+    {
+        // fill: thread = (window, frame lane); everything that depends on the window alone is hoisted out of
+        // the frame loop and the taps walk by pointer -- the same fmaf sequence as pfbch2_mac_elem, bit for bit
+        const unsigned int M2 = M >> 1;
+        const unsigned int nw = M < blockDim.x ? M : blockDim.x;       // windows covered per pass (power of two)
+        const unsigned int fl = blockDim.x / nw;                        // frame lanes
+        const unsigned int w0 = threadIdx.x % nw, f0 = threadIdx.x / nw;
+        for (unsigned int w = w0; w < M; w += nw) {
+            const bool lower = w < M2;                                  // lower half is pushed on even frames
+            const long long off = lower ? (long long)(M2 - 1 - w) : (long long)(M - 1 - w);
+            for (unsigned int fi = f0; fi < per_cta; fi += fl) {
+                const unsigned long long f = first + fi;
+                float re = 0.f, im = 0.f;
+                if (f < n_frames) {
+                    const long long t = t_first + (long long)f;
+                    const int par = (parity0 + (int)(t & 1)) & 1;
+                    const long long tu = (par == (lower ? 0 : 1)) ? t : t - 1;      // frame of the newest sample
+                    const long long idx0 = tu * (long long)M2 + off;              // tap n reads idx0 - n M
+                    const float *tp = taps + (size_t)par * L * M + w;
+                    if (idx0 - (long long)(L - 1) * M >= 0) {
+                        const float2 *sp = x + idx0;
+                        for (unsigned int n = 0; n < L; n++, sp -= M, tp += M) {
+                            const float2 sv = __ldg(sp);
+                            const float c = __ldg(tp);
+                            re = fmaf(c, sv.x, re);
+                            im = fmaf(c, sv.y, im);
+                        }
+                    } else {
+                        for (unsigned int n = 0; n < L; n++, tp += M) {
+                            const float2 sv = lcd::ld_stream(hist, x, idx0 - (long long)n * M, H);
+                            const float c = __ldg(tp);
+                            re = fmaf(c, sv.x, re);
+                            im = fmaf(c, sv.y, im);
+                        }
+                    }
+                }
+                buf0[fi * M + w] = make_float2(re, im);
+            }
+        }
     }
     __syncthreads();
     const float2 *res = lcfft::stockham_pow2(buf0, buf1, tw, M, log2M, per_cta, +1.0f);
@@ -161,10 +196,38 @@ pfbch_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restr
     float2 *buf0 = smem_f2, *buf1 = smem_f2 + (size_t)per_cta * M;
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
     const unsigned int total = per_cta * M;
-    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
-        const unsigned long long f = first + i / M;
-        buf0[i] = (f < n_frames) ? pfbch_mac_elem<TapT>(hist, x, H, taps, M, p, phase, first_in, k, (long long)f, i % M)
-                                 : make_float2(0.f, 0.f);
+    {
+        // fill: thread = (transform input u, frame lane).  The window branch M-1-u reads and the offset d of its
+        // newest sample do not depend on the run index (C = phase + first + s M is congruent mod M for all s),
+        // so they are hoisted; same tap_mac sequence as pfbch_mac_elem, bit for bit
+        const unsigned int nw = M < blockDim.x ? M : blockDim.x;
+        const unsigned int fl = blockDim.x / nw;
+        const unsigned int u0 = threadIdx.x % nw, f0 = threadIdx.x / nw;
+        for (unsigned int u = u0; u < M; u += nw) {
+            const unsigned int i = M - 1 - u;                           // branch
+            const unsigned int win = (i + k) % M;                       // window it reads (firpfbch.c:395)
+            const long long rr = (long long)(M - 1 - win);
+            long long d = ((long long)phase + (long long)first_in - 1 - rr) % (long long)M;
+            if (d < 0) d += M;
+            const long long last0 = (long long)first_in - 1 - d;        // newest sample of run 0 (index into x)
+            const TapT *tp0 = taps + i;
+            for (unsigned int fi = f0; fi < per_cta; fi += fl) {
+                const unsigned long long f = first + fi;
+                float re = 0.f, im = 0.f;
+                if (f < n_frames) {
+                    const long long last = last0 + (long long)f * M;
+                    const TapT *tp = tp0;
+                    if (last - (long long)(p - 1) * M >= 0) {
+                        const float2 *sp = x + last;
+                        for (unsigned int n = 0; n < p; n++, sp -= M, tp += M) tap_mac(__ldg(tp), __ldg(sp), re, im);
+                    } else {
+                        for (unsigned int n = 0; n < p; n++, tp += M)
+                            tap_mac(__ldg(tp), lcd::ld_stream(hist, x, last - (long long)n * M, H), re, im);
+                    }
+                }
+                buf0[fi * M + u] = make_float2(re, im);
+            }
+        }
     }
     __syncthreads();
     const float2 *res = lcfft::stockham_pow2(buf0, buf1, tw, M, log2M, per_cta, -1.0f);
