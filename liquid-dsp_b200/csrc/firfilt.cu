@@ -19,6 +19,7 @@ struct firfilt_crcf_s {
     float scale = 1.0f;
     float *d_taps = nullptr;       // h[0..n) on the device
     float2 *d_hist = nullptr;      // last n samples pushed, oldest first
+    unsigned int *d_tile_counter = nullptr;   // work counter of the persistent short-filter kernel
     lc::DevBuf stage_in, stage_out, hist_tmp, one;
     cudaStream_t stream = nullptr;
 };
@@ -45,6 +46,7 @@ firfilt_crcf firfilt_crcf_create(float *_h, unsigned int _n)
     q->h.assign(_h, _h + _n);
     upload_taps(q);
     LC_CUDA_CHECK(cudaMalloc(&q->d_hist, sizeof(float2) * _n));
+    LC_CUDA_CHECK(cudaMalloc(&q->d_tile_counter, sizeof(unsigned int)));
     LC_CUDA_CHECK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
     firfilt_crcf_reset(q);
     return q;
@@ -98,6 +100,7 @@ void firfilt_crcf_destroy(firfilt_crcf _q)
     cudaStreamSynchronize(_q->stream);
     cudaFree(_q->d_taps);
     cudaFree(_q->d_hist);
+    cudaFree(_q->d_tile_counter);
     _q->stage_in.release();
     _q->stage_out.release();
     _q->hist_tmp.release();
@@ -132,7 +135,7 @@ void firfilt_crcf_execute_block_dev(firfilt_crcf _q, const void *_d_x, unsigned 
     // cannot run in place (the host form firfilt_crcf_execute_block stages through separate device
     // buffers and keeps the reference's x == y allowance, firfilt.c:340-341)
     if (_d_x == _d_y) lc::fatal("firfilt_crcf_execute_block_dev", "in-place operation is not supported on device pointers");
-    lc::firfilt::launch(_q->d_hist, d_x, (int)_q->n, _q->d_taps, _q->n, _q->scale, (float2 *)_d_y, _n, 1, st);
+    lc::firfilt::launch(_q->d_hist, d_x, (int)_q->n, _q->d_taps, _q->n, _q->scale, (float2 *)_d_y, _n, 1, st, _q->d_tile_counter);
     lc::roll_history(_q->d_hist, _q->n, _q->hist_tmp, d_x, _n, st);
 }
 
@@ -142,7 +145,7 @@ void firfilt_crcf_execute_streams_dev(firfilt_crcf _q, const void *_d_x, unsigne
     if (_n == 0 || _n_streams == 0) return;
     if (_d_x == _d_y) lc::fatal("firfilt_crcf_execute_streams_dev", "in-place operation is not supported for the multi-stream form");
     lc::firfilt::launch(nullptr, (const float2 *)_d_x, 0, _q->d_taps, _q->n, _q->scale, (float2 *)_d_y, _n,
-                        _n_streams, lc::as_stream(_stream));
+                        _n_streams, lc::as_stream(_stream), _q->d_tile_counter);
 }
 
 void firfilt_crcf_execute_block(firfilt_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y)

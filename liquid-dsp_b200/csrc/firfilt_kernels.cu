@@ -117,13 +117,15 @@ __device__ __forceinline__ void cp_async8_plain(unsigned int dst_smem, const flo
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 
-// persistent: warp gw of the grid walks warp tiles gw, gw + W, gw + 2W, ...
+// persistent: every warp draws its next tile from a global counter (one atomicAdd per 512 outputs), so warps
+// that the schedulers favour simply do more tiles and all of them finish together; with static striding
+// (tile_counter == nullptr) a quarter of the warp slots sat empty on average while the slowest warps finished
 template <int NT, int RO>
 __global__ void __launch_bounds__(kRbThreads, 2)
 firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
                         const float *__restrict__ taps, unsigned int n_taps, float scale,
                         float2 *__restrict__ y, unsigned long long n_, unsigned int tiles_per_stream_,
-                        unsigned int n_tiles_)
+                        unsigned int n_tiles_, unsigned int *__restrict__ tile_counter)
 {
     using C = RbCfg<NT, RO>;
     constexpr int ROW = C::ROW, NS = C::NS, NPASS = C::NPASS, kWarpTile = C::kWarpTile;
@@ -173,14 +175,21 @@ firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restric
     };
 
     // (tile ids fit 32 bits: the launcher checks; n_tiles + stride does not wrap because both are < 2^31)
-    unsigned int tile_id = blockIdx.x * kRbWarps + warp;
+    auto next_tile = [&](unsigned int current) -> unsigned int {
+        if (tile_counter == nullptr) return current + stride;
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    unsigned int tile_id = (tile_counter == nullptr) ? blockIdx.x * kRbWarps + warp : next_tile(0);
     unsigned int buf = 0;                        // byte offset of the current buffer: 0 or kBufBytes
     if (tile_id < n_tiles) prefetch(tile_id, fill_thr);
-    for (; tile_id < n_tiles; tile_id += stride, buf ^= C::kBufBytes) {
+    while (tile_id < n_tiles) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();                            // this tile is visible to the whole warp, and every lane has
                                                  // finished reading the other buffer (previous tile)
-        if (tile_id + stride < n_tiles) prefetch(tile_id + stride, fill_thr + (buf ^ C::kBufBytes));
+        const unsigned int upcoming = next_tile(tile_id);
+        if (upcoming < n_tiles) prefetch(upcoming, fill_thr + (buf ^ C::kBufBytes));
 
         const unsigned int xb = read_thr + buf;
         float2 acc[RO];
@@ -211,6 +220,8 @@ firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restric
             for (int r = 0; r < RO; r++)
                 if (o0 + r < n) yo[r] = acc[r];
         }
+        tile_id = upcoming;
+        buf ^= C::kBufBytes;
     }
 }
 
@@ -304,7 +315,8 @@ namespace lc {
 namespace firfilt {
 
 void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, unsigned int n_taps,
-            float scale, float2 *d_y, unsigned long long n, unsigned int n_streams, cudaStream_t st)
+            float scale, float2 *d_y, unsigned long long n, unsigned int n_streams, cudaStream_t st,
+            unsigned int *d_tile_counter)
 {
     // short filters on 16-byte aligned, even-length streams: register-blocked packed kernel
     // (tile ids are 32-bit inside the kernel: streams * ceil(n / 512) must stay below 2^31)
@@ -321,8 +333,9 @@ void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps,
             const unsigned long long need = (total_rb + kRbWarps - 1) / kRbWarps;
             if (grid > need) grid = need;
             LC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+            if (d_tile_counter) LC_CUDA_CHECK(cudaMemsetAsync(d_tile_counter, 0, sizeof(unsigned int), st));
             kern<<<(unsigned int)grid, kRbThreads, C::kSmem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n,
-                                                                    (unsigned int)tiles_rb, (unsigned int)total_rb);
+                                                                    (unsigned int)tiles_rb, (unsigned int)total_rb, d_tile_counter);
         };
         if (n_taps <= 16) run(firfilt_regblock_kernel<16, 16>, RbCfg<16, 16>{});
         else if (n_taps <= 32) run(firfilt_regblock_kernel<32, 16>, RbCfg<32, 16>{});
