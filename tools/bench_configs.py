@@ -104,6 +104,19 @@ def main():
         L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
         ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
         report("c5: firpfbch2_crcf analysis M=4096 m=9, 2^29-sample segment", n, 24, ms, ln)
+    if "c3m" in args.configs:
+        # the headline kernel at other filter lengths (m = 2 is the reference's own benchmark shape,
+        # firpfbch2_crcf_benchmark.c:75): how the rate moves with the MAC work per sample
+        for m in (2, 4, 5, 7):
+            M, n = 1024, 1 << 29
+            q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+            H = q.get_state_len()
+            x = torch.zeros(2 * (H + n), dtype=torch.float32, device=dev)
+            y = torch.empty(4 * n, dtype=torch.float32, device=dev)
+            L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
+            ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
+            report("c3m: firpfbch2_crcf analysis M=1024 m=%d, 2^29 samples" % m, n, 24, ms, ln)
+            del x, y
     if "g" in args.configs:
         # shapes without a dedicated fused kernel: the one-kernel shape-generic analyzers (power-of-two M)
         for M, m, n in ((256, 4, 1 << 27), (64, 5, 1 << 27), (2048, 3, 1 << 27)):
