@@ -186,6 +186,8 @@ void  liquid_cuda_memcpy_d2h(void *_dst, const void *_src, unsigned long long _b
 void  liquid_cuda_sync(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long liquid_cuda_launch_count(void);
+/* frames each CTA / cluster walked in the most recent fused channelizer launch (0 = none yet): test aid */
+unsigned long long liquid_cuda_last_chunk_frames(void);
 /* SMs the persistent one-CTA-per-SM kernels leave free (default 0): set to 1-2 when a collective (NCCL
  * send/recv of the halo) or a side-stream launch should run beside the channelizer kernel, not after it */
 void  liquid_cuda_set_reserved_sms(int _n);

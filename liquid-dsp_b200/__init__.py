@@ -157,6 +157,7 @@ _sig("liquid_cuda_memcpy_h2d", None, _vp, _vp, _ull)
 _sig("liquid_cuda_memcpy_d2h", None, _vp, _vp, _ull)
 _sig("liquid_cuda_sync", None)
 _sig("liquid_cuda_launch_count", _ull)
+_sig("liquid_cuda_last_chunk_frames", _ull)
 _sig("liquid_cuda_set_reserved_sms", None, _i)
 _sig("liquid_cuda_get_reserved_sms", _i)
 _sig("liquid_cuda_synth_input_dev", None, _vp, _ull, _ull, _ull, _vp)

@@ -40,6 +40,9 @@ namespace lc {
 void ensure_device();
 
 extern std::atomic<unsigned long long> g_launches;
+// frames each CTA (fused M=1024 kernel) or cluster (M=4096 kernel) walked in the most recent fused
+// channelizer launch, 0 if none yet: lets a test aim its spot checks at the chunk boundaries
+extern std::atomic<unsigned long long> g_last_chunk_frames;
 // SMs the persistent one-CTA-per-SM kernels leave free (liquid_cuda_set_reserved_sms): room for a
 // collective's kernels or a small side-stream launch to run beside them instead of after them
 extern std::atomic<int> g_reserved_sms;

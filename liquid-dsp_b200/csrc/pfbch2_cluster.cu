@@ -485,6 +485,7 @@ long long run_L(ClusterArgs &a, long long n_groups, int par0, cudaStream_t st)
     cl = (n_groups + per - 1) / per;
     a.n_groups = (int)n_groups;
     a.groups_per_cluster = (int)per;
+    lc::g_last_chunk_frames.store((unsigned long long)per * kGroup);
     cfg.gridDim = dim3((unsigned int)cl * kCluster, 1, 1);
     if (par0) LC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, pfbch2_cluster_4096_kernel<L, 1>, a));
     else      LC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, pfbch2_cluster_4096_kernel<L, 0>, a));

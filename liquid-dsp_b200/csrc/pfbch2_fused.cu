@@ -318,6 +318,7 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
     a.H = H;
     a.n_groups = (int)n_groups;
     a.groups_per_cta = (int)per;
+    g_last_chunk_frames.store((unsigned long long)per * kGroup);
     switch (L) {
     case 4: launch_L<4>(a, parity0 & 1, (unsigned int)ctas, st); break;
     case 8: launch_L<8>(a, parity0 & 1, (unsigned int)ctas, st); break;

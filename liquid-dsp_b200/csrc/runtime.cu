@@ -6,6 +6,7 @@ namespace lc {
 
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_reserved_sms{0};
+std::atomic<unsigned long long> g_last_chunk_frames{0};
 static std::atomic<int> g_device_ready{0};
 
 void ensure_device()
@@ -112,6 +113,8 @@ void liquid_cuda_memcpy_d2h(void *_dst, const void *_src, unsigned long long _by
 void liquid_cuda_sync(void) { LC_CUDA_CHECK(cudaDeviceSynchronize()); }
 
 unsigned long long liquid_cuda_launch_count(void) { return lc::g_launches.load(); }
+
+unsigned long long liquid_cuda_last_chunk_frames(void) { return lc::g_last_chunk_frames.load(); }
 
 void liquid_cuda_set_reserved_sms(int _n) { lc::g_reserved_sms.store(_n < 0 ? 0 : _n); }
 int liquid_cuda_get_reserved_sms(void) { return lc::g_reserved_sms.load(); }

@@ -161,6 +161,54 @@ def test_pfbch2_segment_form_equals_stateful(L, orc):
     assert np.array_equal(got, whole[22:])
 
 
+# ------------------------------------------------------------------ BASELINE full sizes
+@pytest.mark.parametrize("M,m,log2n", [(1024, 7, 30), (4096, 9, 30)])
+def test_pfbch2_full_size_spot_checks_vs_oracle(L, orc, M, m, log2n):
+    """BASELINE configs 3 and 5 at the size one GPU runs in bench.py (2^30 input samples, 8 GiB in,
+    16 GiB out, device-resident): blocks of 48 frames at the stream start, around every kind of internal
+    boundary of the fused launch (the first chunk boundaries between CTAs / clusters, the middle one, the
+    last one), at pseudo-random places and at the very end are pulled back and checked against the oracle,
+    which is fed from 2mM samples before each block (the state is only the last 2mM - M/2 samples,
+    SURVEY.md 8c)."""
+    import ctypes as C
+    n = 1 << log2n
+    M2 = M // 2
+    n_frames = n // M2
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    H = q.get_state_len()
+    d_in = L.lib.liquid_cuda_malloc(8 * (H + n))
+    d_out = L.lib.liquid_cuda_malloc(8 * n_frames * M)
+    assert d_in and d_out
+    zeros = np.zeros(H, np.complex64)
+    L.lib.liquid_cuda_memcpy_h2d(d_in, zeros.ctypes.data_as(C.c_void_p), zeros.nbytes)
+    seed = 0x5EED0000 + M
+    L.synth_input_dev(d_in + 8 * H, n, seed=seed)
+    q.execute_segment_dev(d_in, d_in + 8 * H, 0, n_frames, d_out, 0)
+    L.lib.liquid_cuda_sync()
+    chunk = int(L.lib.liquid_cuda_last_chunk_frames())
+    assert chunk > 0, "the fused kernel did not run"
+    n_chunks = -(-n_frames // chunk)
+    nb = 48
+    starts = {0, n_frames - nb}
+    for c in (1, 2, n_chunks // 2, n_chunks - 1):
+        if 0 < c < n_chunks:
+            starts.add(c * chunk - nb // 2)              # straddles the boundary between chunks c-1 and c
+    rng = np.random.default_rng(M)
+    starts.update(int(v) & ~1 for v in rng.integers(4 * m, n_frames - nb, size=6))     # even: frame parity 0
+    oracle = orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0)
+    got = np.empty((nb, M), np.complex64)
+    for f0 in sorted(starts):
+        L.lib.liquid_cuda_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_out + 8 * f0 * M, got.nbytes)
+        assert f0 % 2 == 0 and (f0 == 0 or f0 >= 4 * m)
+        lead = min(4 * m, f0)                            # frames of run-in for the oracle (4m frames = 2mM samples)
+        x = orc.synth_input((lead + nb) * M2, seed=seed, first=(f0 - lead) * M2)
+        oracle.reset()
+        want = oracle.execute_frames(x)[lead:]
+        check_channels(got, want, x)
+    L.lib.liquid_cuda_free(d_in)
+    L.lib.liquid_cuda_free(d_out)
+
+
 # ------------------------------------------------------------------ firpfbch
 @pytest.mark.parametrize("M,m,nfr", [(4, 3, 40), (16, 4, 64), (10, 2, 33), (64, 5, 40), (256, 5, 48), (1024, 2, 20)])
 def test_pfbch_analysis_and_synthesis_vs_oracle(L, orc, M, m, nfr):
