@@ -326,6 +326,37 @@ def test_firfilt_streams_dev(L, orc):
         assert np.abs(got[s] - o.execute_block(x[s])).max() < 2e-6
 
 
+def test_firfilt_full_size_spot_checks_vs_oracle(L, orc):
+    """BASELINE config 2 at full size (64-tap Kaiser low-pass, 1024 streams x 2^20 samples, 8 GiB in and
+    out, device-resident): blocks at stream starts (zero state), at warp-tile boundaries (multiples of
+    512 outputs), at pseudo-random places and at stream ends, in the first, a middle and the last stream"""
+    import ctypes as C
+    n_streams, n, nt = 1024, 1 << 20, 64
+    q = L.firfilt_crcf.create_kaiser(nt, 0.25, 60.0, 0.0)
+    d_x = L.lib.liquid_cuda_malloc(8 * n_streams * n)
+    d_y = L.lib.liquid_cuda_malloc(8 * n_streams * n)
+    assert d_x and d_y
+    seed = 0x5EED0C02
+    L.synth_input_dev(d_x, n_streams * n, seed=seed)
+    q.execute_streams_dev(d_x, n_streams, n, d_y, 0)
+    L.lib.liquid_cuda_sync()
+    o = orc.Firfilt(kaiser=(nt, 0.25, 60.0, 0.0))
+    nb = 1100                                             # spans two warp-tile boundaries
+    got = np.empty(nb, np.complex64)
+    rng = np.random.default_rng(2)
+    for s in (0, 1, 517, n_streams - 1):
+        offs = {0, 512 - 300, 4096 - 300, n - nb} | {int(v) for v in rng.integers(nt, n - nb, size=3)}
+        for o0 in sorted(offs):
+            L.lib.liquid_cuda_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_y + 8 * (s * n + o0), got.nbytes)
+            lead = min(nt - 1, o0)                        # samples of run-in: the filter's memory, zero at the stream start
+            x = orc.synth_input(lead + nb, seed=seed, first=s * n + o0 - lead)
+            o.reset()
+            want = o.execute_block(x)[lead:]
+            assert np.abs(got - want).max() < 2e-6, (s, o0)
+    L.lib.liquid_cuda_free(d_x)
+    L.lib.liquid_cuda_free(d_y)
+
+
 def test_firfilt_freqresponse_groupdelay(L):
     h = np.array([0.1, 0.5, 1.0, 0.5, 0.1], np.float32)
     q = L.firfilt_crcf.create(h)
@@ -474,6 +505,53 @@ def test_pfbch_rnyquist_kaiser_prototypes_vs_reference(L, orc, refrn):
     got = L.firfilt_crcf.create_rnyquist(L.LIQUID_FIRFILT_RKAISER, 4, 5, 0.3).execute_block(x)
     want = orc.Firfilt(h=h).execute_block(x)
     assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("M,m,n_streams,log2n", [(16, 4, 1, 28), (256, 5, 32, 22)])
+def test_pfbch_full_size_spot_checks_vs_oracle(L, orc, M, m, n_streams, log2n):
+    """BASELINE configs 1 and 4 at full size (M=16: one 2^28-sample stream; M=256: 32 streams x 2^22 -- one
+    GPU's share of config 4), device-resident, synthesis followed by analysis for M=256: blocks at stream
+    starts, at multiples of 16 and 256 frames (tile / instance granularity of the fused kernels), at
+    pseudo-random places and at stream ends against the oracle fed from p frames earlier"""
+    import ctypes as C
+    n = 1 << log2n
+    nf = n // M
+    p = 2 * m
+    seed = 0x5EED0C00 + M
+    d_x = L.lib.liquid_cuda_malloc(8 * n_streams * n)
+    d_t = L.lib.liquid_cuda_malloc(8 * n_streams * n)
+    d_y = L.lib.liquid_cuda_malloc(8 * n_streams * n)
+    L.synth_input_dev(d_x, n_streams * n, seed=seed)
+    qa = L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    qs = L.firpfbch_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+    stages = [("a", qa, d_x, d_y, orc.ANALYZER)]
+    if M == 256:      # round trip: synthesise the channel frames, then analyse the synthesised stream
+        stages = [("s", qs, d_x, d_t, orc.SYNTHESIZER), ("a", qa, d_t, d_y, orc.ANALYZER)]
+    nb = 40
+    buf_in = np.empty(((p + nb), M), np.complex64)
+    got = np.empty((nb, M), np.complex64)
+    rng = np.random.default_rng(M)
+    for key, q, d_in, d_out, otyp in stages:
+        q.execute_streams_dev(d_in, n_streams, nf, d_out, 0)
+        L.lib.liquid_cuda_sync()
+        o = orc.Firpfbch(otyp, M, kaiser=(m, 60.0))
+        for s in sorted({0, n_streams // 2, n_streams - 1}):
+            starts = {0, 16 * 7 - 20, 256 * 3 - 20, nf - nb} | {int(v) for v in rng.integers(p, nf - nb, size=3)}
+            for f0 in sorted(starts):
+                lead = min(p, f0)                         # frames of run-in: the channelizer's memory is p frames
+                # the stage's own input as it is on the device (for "a" after "s" that is the synthesised stream)
+                src = buf_in[: lead + nb]
+                L.lib.liquid_cuda_memcpy_d2h(src.ctypes.data_as(C.c_void_p), d_in + 8 * (s * n + (f0 - lead) * M), src.nbytes)
+                L.lib.liquid_cuda_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_out + 8 * (s * n + f0 * M), got.nbytes)
+                o.reset()
+                want = o.execute_frames(src.reshape(-1))[lead:]
+                if lead < p and f0 > 0:
+                    continue
+                assert np.abs(got - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), (key, s, f0)
+                if otyp == orc.ANALYZER:
+                    check_channels(got, want, src.reshape(-1))
+    for d in (d_x, d_t, d_y):
+        L.lib.liquid_cuda_free(d)
 
 
 # ------------------------------------------------------------------ one-kernel shape-generic analyzers
