@@ -75,6 +75,22 @@ void  liquid_firdes_arkaiser(unsigned int _k, unsigned int _m, float _beta, floa
 void  liquid_firdes_rkaiser(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
 void  liquid_firdes_prototype(int _type, unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
 
+/* ---- spgramcf (windowed-FFT spectral periodogram): liquid.h:1230-1316 -> src/fft/src/spgramcf.c -> spgram.c:57-398.
+ *      SURVEY.md 8(f) item 2. */
+typedef struct spgramcf_s * spgramcf;
+spgramcf spgramcf_create(unsigned int _nfft, float *_window, unsigned int _window_len);
+spgramcf spgramcf_create_kaiser(unsigned int _nfft, unsigned int _window_len, float _beta);
+spgramcf spgramcf_create_default(unsigned int _nfft);
+void spgramcf_destroy(spgramcf _q);
+void spgramcf_reset(spgramcf _q);
+void spgramcf_push(spgramcf _q, liquid_float_complex _x);
+void spgramcf_write(spgramcf _q, liquid_float_complex *_x, unsigned int _n);
+void spgramcf_execute(spgramcf _q, liquid_float_complex *_X);
+void spgramcf_execute_psd(spgramcf _q, float *_X);
+void spgramcf_accumulate_psd(spgramcf _q, liquid_float_complex *_x, float _alpha, unsigned int _n);
+void spgramcf_write_accumulation(spgramcf _q, float *_x);
+void spgramcf_estimate_psd(spgramcf _q, liquid_float_complex *_x, unsigned int _n, float *_psd);
+
 /* ---- firpfbch2_crcf: liquid.h:5754-5793 -> src/multichannel/src/firpfbch2.c:66-358 */
 typedef struct firpfbch2_crcf_s * firpfbch2_crcf;
 firpfbch2_crcf firpfbch2_crcf_create(int _type, unsigned int _M, unsigned int _m, float *_h);
@@ -232,6 +248,11 @@ void firpfbch_crcf_execute_streams_dev(firpfbch_crcf _q, const void *_d_x, unsig
 unsigned int firpfbch_crcf_get_state_len(firpfbch_crcf _q);
 void firpfbch_crcf_get_state(firpfbch_crcf _q, liquid_float_complex *_hist);
 void firpfbch_crcf_set_state(firpfbch_crcf _q, const liquid_float_complex *_hist);
+
+/* ---- spgramcf: device-pointer forms (the whole block becomes one batch of overlapping transforms) ---- */
+void spgramcf_accumulate_psd_dev(spgramcf _q, const void *_d_x, float _alpha, unsigned long long _n, void *_stream);
+void spgramcf_estimate_psd_dev(spgramcf _q, const void *_d_x, unsigned long long _n, float *_psd, void *_stream);
+unsigned int spgramcf_get_num_transforms(spgramcf _q);
 
 /* ---- firpfbch_cccf ---- */
 void firpfbch_cccf_analyzer_execute_block(firpfbch_cccf _q, liquid_float_complex *_x,

@@ -89,6 +89,21 @@ _sig("firpfbch_crcf_execute_streams_dev", None, _vp, _vp, _u, _ull, _vp, _vp)
 _sig("firpfbch_crcf_get_state_len", _u, _vp)
 _sig("firpfbch_crcf_get_state", None, _vp, _cf_p)
 _sig("firpfbch_crcf_set_state", None, _vp, _cf_p)
+_sig("spgramcf_create", _vp, _u, _f_p, _u)
+_sig("spgramcf_create_kaiser", _vp, _u, _u, _fl)
+_sig("spgramcf_create_default", _vp, _u)
+_sig("spgramcf_destroy", None, _vp)
+_sig("spgramcf_reset", None, _vp)
+_sig("spgramcf_push", None, _vp, _cf)
+_sig("spgramcf_write", None, _vp, _cf_p, _u)
+_sig("spgramcf_execute", None, _vp, _cf_p)
+_sig("spgramcf_execute_psd", None, _vp, _f_p)
+_sig("spgramcf_accumulate_psd", None, _vp, _cf_p, _fl, _u)
+_sig("spgramcf_write_accumulation", None, _vp, _f_p)
+_sig("spgramcf_estimate_psd", None, _vp, _cf_p, _u, _f_p)
+_sig("spgramcf_accumulate_psd_dev", None, _vp, _vp, _fl, _ull, _vp)
+_sig("spgramcf_estimate_psd_dev", None, _vp, _vp, _ull, _f_p, _vp)
+_sig("spgramcf_get_num_transforms", _u, _vp)
 _sig("firpfbch_cccf_create", _vp, _i, _u, _u, _cf_p)
 _sig("firpfbch_cccf_create_kaiser", _vp, _i, _u, _u, _fl)
 _sig("firpfbch_cccf_create_rnyquist", _vp, _i, _u, _u, _fl, _i)
@@ -418,6 +433,81 @@ class firpfbch_crcf(_Handle):
     def set_state(self, hist):
         lib.firpfbch_crcf_set_state(self._h, _c64(hist))
 
+
+
+class spgramcf(_Handle):
+    """liquid.h:1230-1316: windowed-FFT spectral periodogram (src/fft/src/spgram.c)."""
+    _destroy = "spgramcf_destroy"
+
+    def __init__(self, nfft, window):
+        self.nfft = nfft
+        w = _f32(window)
+        super().__init__(lib.spgramcf_create(nfft, w, len(w)))
+
+    @classmethod
+    def create(cls, nfft, window):
+        return cls(nfft, window)
+
+    @classmethod
+    def create_kaiser(cls, nfft, window_len, beta):
+        q = cls.__new__(cls)
+        q.nfft = nfft
+        _Handle.__init__(q, lib.spgramcf_create_kaiser(nfft, window_len, beta))
+        return q
+
+    @classmethod
+    def create_default(cls, nfft):
+        q = cls.__new__(cls)
+        q.nfft = nfft
+        _Handle.__init__(q, lib.spgramcf_create_default(nfft))
+        return q
+
+    def reset(self):
+        lib.spgramcf_reset(self._h)
+
+    def push(self, v):
+        v = complex(v)
+        lib.spgramcf_push(self._h, _cf(v.real, v.imag))
+
+    def write(self, x):
+        x = _c64(x)
+        lib.spgramcf_write(self._h, x, len(x))
+
+    def execute(self):
+        X = np.empty(self.nfft, np.complex64)
+        lib.spgramcf_execute(self._h, X)
+        return X
+
+    def execute_psd(self):
+        out = np.empty(self.nfft, np.float32)
+        lib.spgramcf_execute_psd(self._h, out)
+        return out
+
+    def accumulate_psd(self, x, alpha):
+        x = _c64(x)
+        lib.spgramcf_accumulate_psd(self._h, x, alpha, len(x))
+
+    def accumulate_psd_dev(self, d_x, alpha, n, stream=0):
+        lib.spgramcf_accumulate_psd_dev(self._h, d_x, alpha, n, stream)
+
+    def write_accumulation(self):
+        out = np.empty(self.nfft, np.float32)
+        lib.spgramcf_write_accumulation(self._h, out)
+        return out
+
+    def estimate_psd(self, x):
+        x = _c64(x)
+        out = np.empty(self.nfft, np.float32)
+        lib.spgramcf_estimate_psd(self._h, x, len(x), out)
+        return out
+
+    def estimate_psd_dev(self, d_x, n, stream=0):
+        out = np.empty(self.nfft, np.float32)
+        lib.spgramcf_estimate_psd_dev(self._h, d_x, n, out, stream)
+        return out
+
+    def num_transforms(self):
+        return lib.spgramcf_get_num_transforms(self._h)
 
 
 class firpfbch_cccf(_Handle):

@@ -62,6 +62,8 @@ float kaiser_(unsigned int n, unsigned int N, float beta, float mu)
 
 namespace lc {
 
+float kaiser_window(unsigned int n, unsigned int N, float beta, float mu) { return kaiser_(n, N, beta, mu); }
+
 float kaiser_beta_As(float As)
 {
     As = fabsf(As);

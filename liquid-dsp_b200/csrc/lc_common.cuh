@@ -93,6 +93,7 @@ inline unsigned int ilog2(unsigned int n)
 
 // ---- host-side prototype design (float32, reference formulas) : design.cu ----
 float kaiser_beta_As(float As);
+float kaiser_window(unsigned int n, unsigned int N, float beta, float mu);   // kaiser(), src/math/src/math.c:289-310
 int firdes_kaiser(unsigned int n, float fc, float As, float mu, float *h);   // 0 ok, else message id
 int firdes_rrcos(unsigned int k, unsigned int m, float beta, float dt, float *h);
 float estimate_req_filter_As(float df, unsigned int N);

@@ -1,0 +1,452 @@
+// spgram.cu -- spgramcf: windowed-FFT spectral periodogram, the usual consumer right after a channelizer.
+//
+// Replaces src/fft/src/spgramcf.c -> src/fft/src/spgram.c (create :57-107, create_kaiser :113-147,
+// create_default :150-162, reset :180-199, push/write :202-219, execute :226-244, execute_psd :250-264,
+// accumulate_psd :271-311, write_accumulation :318-334, estimate_psd :341-398).  SURVEY.md 8(f) item 2.
+//
+// The reference takes one transform at a time inside a per-sample loop; here a whole block of samples
+// becomes a batch of T overlapping transforms:
+//   spgram_transform_pow2_kernel   (power-of-two nfft that fits shared memory) tapers the segments of a few
+//                                  transforms straight into shared memory (zero-padded to nfft), runs the
+//                                  Stockham FFT of fft_device.cuh there and stores |X|^2 (or X) -- the
+//                                  tapered segments never visit HBM; any other nfft: gather kernel + the
+//                                  batched DFT of fft.cu + a |X|^2 kernel
+//   spgram_fold_kernel             folds the T spectra of a chunk into one partial per frequency bin with the
+//                                  reference's recurrence  psd <- (1-alpha) psd + alpha |X|^2  (or a plain sum
+//                                  for estimate_psd); chunk 0 starts from the object's psd, so a block of up to
+//                                  64 transforms is folded in exactly the reference's order
+//   spgram_combine_kernel          psd <- decay_c psd + partial_c over the chunks, in order
+// Same state as the reference: the last window_len samples, psd[nfft] (1 after reset), sample_counter,
+// num_transforms -- including the quirk that the first transform after a reset forces alpha = 1 for the
+// rest of that accumulate_psd call (alpha is the function's own parameter, spgram.c:291-292).
+#include <cmath>
+#include <cstdint>
+
+#include "lc_common.cuh"
+#include "fft_device.cuh"
+#include "../../include/liquid_cuda.h"
+#include "host_pipeline.cuh"
+
+struct spgramcf_s {
+    unsigned int nfft, window_len;
+    std::vector<float> w;           // scaled tapering window (host copy)
+    float *d_w = nullptr;
+    float2 *d_buf = nullptr;        // last window_len samples, oldest first
+    float *d_psd = nullptr;         // [nfft] accumulation
+    unsigned int sample_counter = 0, num_transforms = 0;
+    lc::FftPlanDev fft;             // forward, nfft points
+    lc::DevBuf spectra, partials, stage, hist_tmp, one, xout;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned int kFoldChunk = 64;                    // transforms folded sequentially by one thread
+constexpr size_t kScratchBytes = (size_t)256 << 20;        // spectra of one pass
+
+// sample `idx` of the stream whose samples [-H, 0) live in hist and [0, n) in x (x may be null when n = 0)
+__device__ __forceinline__ float2 ld_sample(const float2 *__restrict__ hist, const float2 *__restrict__ x,
+                                            long long idx, int H)
+{
+    return idx >= 0 ? __ldg(x + idx) : __ldg(hist + (H + idx));
+}
+
+// transform t of the pass ends (newest sample) at stream index min(e0 + t*hop, e_max)
+struct Segs {
+    long long e0, hop, e_max;
+    __device__ __forceinline__ long long end_of(unsigned long long t) const
+    {
+        const long long e = e0 + (long long)t * hop;
+        return e < e_max ? e : e_max;
+    }
+};
+
+// power-of-two nfft: taper, transform and |X|^2 (MODE 0 -> float out) or X (MODE 1 -> float2 out) in one kernel
+template <int MODE>
+__global__ void __launch_bounds__(lcfft::kFftThreads)
+spgram_transform_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                             const float *__restrict__ w, unsigned int window_len, const float2 *__restrict__ tw,
+                             unsigned int nfft, unsigned int log2n, unsigned int per_cta, unsigned long long T,
+                             Segs segs, void *__restrict__ out)
+{
+    extern __shared__ float2 smem_f2[];
+    float2 *buf0 = smem_f2, *buf1 = smem_f2 + (size_t)per_cta * nfft;
+    const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
+    const unsigned int total = per_cta * nfft;
+    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
+        const unsigned long long t = first + i / nfft;
+        const unsigned int k = i % nfft;
+        float2 v = make_float2(0.f, 0.f);
+        if (t < T && k < window_len) {
+            const float2 s = ld_sample(hist, x, segs.end_of(t) - (long long)(window_len - 1) + k, H);
+            const float c = __ldg(w + k);
+            v = make_float2(s.x * c, s.y * c);                       // rc[i] * w[i]   (spgram.c:236-237)
+        }
+        buf0[i] = v;
+    }
+    __syncthreads();
+    const float2 *res = lcfft::stockham_pow2(buf0, buf1, tw, nfft, log2n, per_cta, -1.0f);
+    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
+        const unsigned long long t = first + i / nfft;
+        if (t >= T) continue;
+        const float2 X = res[i];
+        if (MODE == 0) reinterpret_cast<float *>(out)[t * nfft + (i % nfft)] = X.x * X.x + X.y * X.y;
+        else           reinterpret_cast<float2 *>(out)[t * nfft + (i % nfft)] = X;
+    }
+}
+
+// any nfft: tapered, zero-padded segments [T][nfft] for the batched DFT
+__global__ void __launch_bounds__(kThreads)
+spgram_gather_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ w,
+                     unsigned int window_len, unsigned int nfft, unsigned long long T, Segs segs, float2 *__restrict__ out)
+{
+    const unsigned long long total = T * nfft;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long t = i / nfft;
+        const unsigned int k = (unsigned int)(i % nfft);
+        float2 v = make_float2(0.f, 0.f);
+        if (k < window_len) {
+            const float2 s = ld_sample(hist, x, segs.end_of(t) - (long long)(window_len - 1) + k, H);
+            const float c = __ldg(w + k);
+            v = make_float2(s.x * c, s.y * c);
+        }
+        out[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+spgram_magsq_kernel(const float2 *__restrict__ X, float *__restrict__ P, unsigned long long total)
+{
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float2 v = X[i];
+        P[i] = v.x * v.x + v.y * v.y;
+    }
+}
+
+// fold chunk c (transforms [c*chunk, min((c+1)*chunk, T))) of P[T][nfft] per bin k:
+//   s = (seed_psd && c == 0) ? psd[k] : 0;   for t: s = (1-alpha) s + alpha P[t][k]   (alpha < 0: s += P[t][k])
+__global__ void __launch_bounds__(kThreads)
+spgram_fold_kernel(const float *__restrict__ P, const float *__restrict__ psd, float *__restrict__ partial,
+                   unsigned int nfft, unsigned long long T, unsigned int chunk, float alpha, int seed_psd)
+{
+    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int c = blockIdx.y;
+    if (k >= nfft) return;
+    const unsigned long long t0 = (unsigned long long)c * chunk;
+    unsigned long long t1 = t0 + chunk;
+    if (t1 > T) t1 = T;
+    float s = (seed_psd && c == 0) ? psd[k] : 0.0f;
+    if (alpha < 0.0f) {
+        for (unsigned long long t = t0; t < t1; t++) s += __ldg(P + t * nfft + k);
+    } else {
+        const float keep = 1.0f - alpha;
+        for (unsigned long long t = t0; t < t1; t++) s = keep * s + alpha * __ldg(P + t * nfft + k);
+    }
+    partial[(size_t)c * nfft + k] = s;
+}
+
+// psd[k] = partial[0][k]; for c >= 1: psd[k] = decay(c) psd[k] + partial[c][k], decay(c) = (1-alpha)^(transforms in
+// chunk c), or 1 for the plain sum
+__global__ void __launch_bounds__(kThreads)
+spgram_combine_kernel(const float *__restrict__ partial, float *__restrict__ psd, unsigned int nfft,
+                      unsigned int n_chunks, unsigned int chunk, unsigned long long T, float alpha)
+{
+    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nfft) return;
+    float s = partial[k];
+    for (unsigned int c = 1; c < n_chunks; c++) {
+        float decay = 1.0f;
+        if (alpha >= 0.0f) {
+            unsigned long long cnt = T - (unsigned long long)c * chunk;
+            if (cnt > chunk) cnt = chunk;
+            decay = powf(1.0f - alpha, (float)cnt);
+        }
+        s = decay * s + partial[(size_t)c * nfft + k];
+    }
+    psd[k] = s;
+}
+
+inline unsigned int grid_for(unsigned long long total)
+{
+    unsigned long long b = (total + kThreads - 1) / kThreads;
+    const unsigned long long cap = 148ull * 8 * 16;
+    return (unsigned int)(b < cap ? (b ? b : 1) : cap);
+}
+
+// T transforms of the (hist | x) stream -> d_out: |X|^2 [T][nfft] floats (mode 0) or X [T][nfft] (mode 1)
+void run_transforms(spgramcf q, const float2 *d_x, unsigned long long T, Segs segs, int mode, void *d_out, cudaStream_t st)
+{
+    if (T == 0) return;
+    const unsigned int nfft = q->nfft;
+    if (lcfft::pow2_in_smem(nfft)) {
+        static bool once = false;
+        if (!once) {
+            LC_CUDA_CHECK(cudaFuncSetAttribute(spgram_transform_pow2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LC_CUDA_CHECK(cudaFuncSetAttribute(spgram_transform_pow2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            once = true;
+        }
+        const unsigned int per_cta = lcfft::per_cta_for(nfft, T);
+        const unsigned long long ctas = (T + per_cta - 1) / per_cta;
+        const size_t smem = lcfft::smem_for(nfft, per_cta);
+        if (mode == 0)
+            spgram_transform_pow2_kernel<0><<<(unsigned int)ctas, lcfft::kFftThreads, smem, st>>>(
+                q->d_buf, d_x, (int)q->window_len, q->d_w, q->window_len, q->fft.d_tw, nfft, lc::ilog2(nfft), per_cta, T, segs, d_out);
+        else
+            spgram_transform_pow2_kernel<1><<<(unsigned int)ctas, lcfft::kFftThreads, smem, st>>>(
+                q->d_buf, d_x, (int)q->window_len, q->d_w, q->window_len, q->fft.d_tw, nfft, lc::ilog2(nfft), per_cta, T, segs, d_out);
+        LC_LAUNCH_CHECK();
+        return;
+    }
+    // any other size: tapered segments -> batched DFT (in place) -> |X|^2
+    float2 *d_X = (mode == 1) ? (float2 *)d_out : (float2 *)q->xout.get(sizeof(float2) * T * nfft);
+    spgram_gather_kernel<<<grid_for(T * nfft), kThreads, 0, st>>>(q->d_buf, d_x, (int)q->window_len, q->d_w, q->window_len,
+                                                                 nfft, T, segs, d_X);
+    LC_LAUNCH_CHECK();
+    q->fft.run(d_X, d_X, T, st);
+    if (mode == 0) {
+        spgram_magsq_kernel<<<grid_for(T * nfft), kThreads, 0, st>>>(d_X, (float *)d_out, T * nfft);
+        LC_LAUNCH_CHECK();
+    }
+}
+
+// fold T spectra-in-time into q->d_psd: alpha in [0,1] -> the reference's recurrence seeded with psd;
+// alpha < 0 -> plain sum (psd is overwritten by the sum, the caller zeroed nothing: seed off)
+void fold_into_psd(spgramcf q, const float *d_P, unsigned long long T, float alpha, int seed_psd, cudaStream_t st)
+{
+    const unsigned int nfft = q->nfft;
+    unsigned int chunk = kFoldChunk;
+    if ((T + chunk - 1) / chunk > 2048) chunk = (unsigned int)((T + 2047) / 2048);
+    const unsigned int n_chunks = (unsigned int)((T + chunk - 1) / chunk);
+    float *d_part = (float *)q->partials.get(sizeof(float) * (size_t)n_chunks * nfft);
+    dim3 grid((nfft + kThreads - 1) / kThreads, n_chunks);
+    spgram_fold_kernel<<<grid, kThreads, 0, st>>>(d_P, q->d_psd, d_part, nfft, T, chunk, alpha, seed_psd);
+    LC_LAUNCH_CHECK();
+    spgram_combine_kernel<<<(nfft + kThreads - 1) / kThreads, kThreads, 0, st>>>(d_part, q->d_psd, nfft, n_chunks, chunk, T, alpha);
+    LC_LAUNCH_CHECK();
+}
+
+// transforms of one pass are cut so that their spectra fit the scratch budget
+unsigned long long pass_limit(unsigned int nfft)
+{
+    unsigned long long lim = kScratchBytes / ((unsigned long long)nfft * sizeof(float));
+    return lim ? lim : 1;
+}
+
+void set_psd_ones(spgramcf q)
+{
+    std::vector<float> ones(q->nfft, 1.0f);
+    LC_CUDA_CHECK(cudaMemcpyAsync(q->d_psd, ones.data(), sizeof(float) * q->nfft, cudaMemcpyHostToDevice, q->stream));
+    LC_CUDA_CHECK(cudaStreamSynchronize(q->stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+spgramcf spgramcf_create(unsigned int _nfft, float *_window, unsigned int _window_len)
+{
+    if (_nfft < 2) lc::fatal("spgramcf_create", "fft size must be at least 2");
+    if (_window_len > _nfft) lc::fatal("spgramcf_create", "window size cannot exceed fft size");
+    if (_window_len == 0) lc::fatal("spgramcf_create", "window size must be greater than zero");
+    lc::ensure_device();
+    spgramcf q = new spgramcf_s();
+    q->nfft = _nfft;
+    q->window_len = _window_len;
+    // scale by window magnitude and FFT size: g = sqrt(2) / (rms(window) sqrt(nfft))      spgram.c:92-100
+    float g = 0.0f;
+    for (unsigned int i = 0; i < _window_len; i++) g += _window[i] * _window[i];
+    g = (float)(1.41421356237309504880 / (double)(sqrtf(g / (float)_window_len) * sqrtf((float)_nfft)));
+    q->w.resize(_window_len);
+    for (unsigned int i = 0; i < _window_len; i++) q->w[i] = g * _window[i];
+    LC_CUDA_CHECK(cudaMalloc(&q->d_w, sizeof(float) * _window_len));
+    LC_CUDA_CHECK(cudaMemcpy(q->d_w, q->w.data(), sizeof(float) * _window_len, cudaMemcpyHostToDevice));
+    LC_CUDA_CHECK(cudaMalloc(&q->d_buf, sizeof(float2) * _window_len));
+    LC_CUDA_CHECK(cudaMalloc(&q->d_psd, sizeof(float) * _nfft));
+    q->fft.init(_nfft, -1);
+    LC_CUDA_CHECK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+    spgramcf_reset(q);
+    return q;
+}
+
+spgramcf spgramcf_create_kaiser(unsigned int _nfft, unsigned int _window_len, float _beta)
+{
+    if (_nfft < 2) lc::fatal("spgramcf_create_kaiser", "fft size must be at least 2");
+    if (_window_len > _nfft) lc::fatal("spgramcf_create_kaiser", "window size cannot exceed fft size");
+    if (_window_len == 0) lc::fatal("spgramcf_create_kaiser", "window size must be greater than zero");
+    if (_beta <= 0.0f) lc::fatal("spgramcf_create_kaiser", "beta must be greater than zero");
+    std::vector<float> w(_window_len);
+    for (unsigned int i = 0; i < _window_len; i++) w[i] = lc::kaiser_window(i, _window_len, _beta, 0.0f);
+    return spgramcf_create(_nfft, w.data(), _window_len);
+}
+
+spgramcf spgramcf_create_default(unsigned int _nfft)
+{
+    if (_nfft < 2) lc::fatal("spgramcf_create_default", "fft size must be at least 2");
+    return spgramcf_create_kaiser(_nfft, _nfft / 2, 10.0f);       // spgram.c:158-161
+}
+
+void spgramcf_destroy(spgramcf _q)
+{
+    if (!_q) return;
+    cudaStreamSynchronize(_q->stream);
+    cudaFree(_q->d_w);
+    cudaFree(_q->d_buf);
+    cudaFree(_q->d_psd);
+    _q->fft.destroy();
+    _q->spectra.release();
+    _q->partials.release();
+    _q->stage.release();
+    _q->hist_tmp.release();
+    _q->one.release();
+    _q->xout.release();
+    cudaStreamDestroy(_q->stream);
+    delete _q;
+}
+
+void spgramcf_reset(spgramcf _q)
+{
+    LC_CUDA_CHECK(cudaMemsetAsync(_q->d_buf, 0, sizeof(float2) * _q->window_len, _q->stream));
+    _q->num_transforms = 0;
+    _q->sample_counter = 0;
+    set_psd_ones(_q);                    // unity = 0 dB (spgram.c:196-198)
+}
+
+void spgramcf_write(spgramcf _q, liquid_float_complex *_x, unsigned int _n)
+{
+    if (_n == 0) return;
+    // only the last window_len samples can matter
+    const unsigned int keep = _n < _q->window_len ? _n : _q->window_len;
+    float2 *d = (float2 *)_q->stage.get(sizeof(float2) * keep);
+    LC_CUDA_CHECK(cudaMemcpyAsync(d, reinterpret_cast<const lc_cf *>(_x) + (_n - keep), sizeof(float2) * keep,
+                                  cudaMemcpyHostToDevice, _q->stream));
+    lc::roll_history(_q->d_buf, _q->window_len, _q->hist_tmp, d, keep, _q->stream);
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+}
+
+void spgramcf_push(spgramcf _q, liquid_float_complex _x) { spgramcf_write(_q, &_x, 1); }
+
+void spgramcf_execute(spgramcf _q, liquid_float_complex *_X)
+{
+    // one transform of the buffer as it stands: the segment ends at stream index -1
+    float2 *d_X = (float2 *)_q->spectra.get(sizeof(float2) * _q->nfft);
+    Segs segs{-1, 0, -1};
+    run_transforms(_q, nullptr, 1, segs, 1, d_X, _q->stream);
+    if (_X) LC_CUDA_CHECK(cudaMemcpyAsync(_X, d_X, sizeof(float2) * _q->nfft, cudaMemcpyDeviceToHost, _q->stream));
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+}
+
+void spgramcf_execute_psd(spgramcf _q, float *_X)
+{
+    std::vector<lc_cf> X(_q->nfft);
+    spgramcf_execute(_q, reinterpret_cast<liquid_float_complex *>(X.data()));
+    const unsigned int h = _q->nfft / 2;
+    for (unsigned int i = 0; i < _q->nfft; i++)
+        _X[(i + h) % _q->nfft] = 10 * log10f(X[i].re * X[i].re + X[i].im * X[i].im + 1e-16f);     // spgram.c:259-263
+}
+
+// device-pointer form: _d_x holds _n new samples; state (buffer, psd, counters) advances as in the reference
+void spgramcf_accumulate_psd_dev(spgramcf _q, const void *_d_x, float _alpha, unsigned long long _n, void *_stream)
+{
+    if (_alpha < 0.0f || _alpha > 1.0f) lc::fatal("spgramcf_accumulate_psd", "alpha must be in (0,1)");
+    if (_n == 0) return;
+    cudaStream_t st = lc::as_stream(_stream);
+    const float2 *d_x = (const float2 *)_d_x;
+    const unsigned int hop = _q->window_len / 2;                 // a transform every window_len/2 pushes
+    unsigned long long T = 0;
+    long long e0 = 0;
+    if (hop > 0) {
+        T = (_n + _q->sample_counter) / hop;
+        e0 = (long long)hop - (long long)_q->sample_counter - 1;  // index in x of the push that triggers the first one
+    }
+    // the first transform after a reset forces alpha = 1 for the rest of this call (spgram.c:291-292)
+    const float alpha = (_q->num_transforms == 0 && T > 0) ? 1.0f : _alpha;
+    const unsigned long long lim = pass_limit(_q->nfft);
+    for (unsigned long long done = 0; done < T;) {
+        const unsigned long long nt = (T - done < lim) ? T - done : lim;
+        float *d_P = (float *)_q->spectra.get(sizeof(float) * nt * _q->nfft);
+        Segs segs{e0 + (long long)done * hop, (long long)hop, (long long)_n - 1};
+        run_transforms(_q, d_x, nt, segs, 0, d_P, st);
+        fold_into_psd(_q, d_P, nt, alpha, 1, st);
+        done += nt;
+    }
+    lc::roll_history(_q->d_buf, _q->window_len, _q->hist_tmp, d_x, _n, st);
+    if (hop > 0) {
+        _q->sample_counter = (unsigned int)((_n + _q->sample_counter) % hop);
+        _q->num_transforms += (unsigned int)T;
+    } else {
+        _q->sample_counter += (unsigned int)_n;                  // window_len = 1: the counter never meets 0
+    }
+}
+
+void spgramcf_accumulate_psd(spgramcf _q, liquid_float_complex *_x, float _alpha, unsigned int _n)
+{
+    if (_alpha < 0.0f || _alpha > 1.0f) lc::fatal("spgramcf_accumulate_psd", "alpha must be in (0,1)");
+    if (_n == 0) return;
+    float2 *d = (float2 *)_q->stage.get(sizeof(float2) * (size_t)_n);
+    LC_CUDA_CHECK(cudaMemcpyAsync(d, _x, sizeof(float2) * (size_t)_n, cudaMemcpyHostToDevice, _q->stream));
+    spgramcf_accumulate_psd_dev(_q, d, _alpha, _n, _q->stream);
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+}
+
+void spgramcf_write_accumulation(spgramcf _q, float *_x)
+{
+    std::vector<float> psd(_q->nfft);
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+    LC_CUDA_CHECK(cudaMemcpy(psd.data(), _q->d_psd, sizeof(float) * _q->nfft, cudaMemcpyDeviceToHost));
+    const unsigned int h = _q->nfft / 2;
+    for (unsigned int i = 0; i < _q->nfft; i++) _x[(i + h) % _q->nfft] = 10 * log10f(psd[i]);      // spgram.c:332-333
+}
+
+// device-pointer form of estimate_psd: _psd (host, nfft floats) receives the fft-shifted average in dB
+void spgramcf_estimate_psd_dev(spgramcf _q, const void *_d_x, unsigned long long _n, float *_psd, void *_stream)
+{
+    if (_n == 0) {
+        fprintf(stderr, "warning: spgram%s_estimate_psd(), input size is zero\n", "cf");
+        return;
+    }
+    cudaStream_t st = lc::as_stream(_stream);
+    const float2 *d_x = (const float2 *)_d_x;
+    spgramcf_reset(_q);
+    LC_CUDA_CHECK(cudaStreamSynchronize(st));
+    unsigned int delay = _q->nfft / 4;
+    if (delay == 0) delay = 1;
+    // a transform after every `delay` samples and after the last one            spgram.c:373-388
+    const unsigned long long T = (_n + delay - 1) / delay;
+    const unsigned int nfft = _q->nfft;
+    // the sum is kept in d_psd while the passes run, then the reset state is restored
+    LC_CUDA_CHECK(cudaMemsetAsync(_q->d_psd, 0, sizeof(float) * nfft, st));
+    const unsigned long long lim = pass_limit(nfft);
+    for (unsigned long long done = 0; done < T;) {
+        const unsigned long long nt = (T - done < lim) ? T - done : lim;
+        float *d_P = (float *)_q->spectra.get(sizeof(float) * nt * nfft);
+        Segs segs{(long long)(done + 1) * delay - 1, (long long)delay, (long long)_n - 1};
+        run_transforms(_q, d_x, nt, segs, 0, d_P, st);
+        fold_into_psd(_q, d_P, nt, -1.0f, 1, st);               // plain sum on top of what is there
+        done += nt;
+    }
+    std::vector<float> sum(nfft);
+    LC_CUDA_CHECK(cudaMemcpyAsync(sum.data(), _q->d_psd, sizeof(float) * nfft, cudaMemcpyDeviceToHost, st));
+    lc::roll_history(_q->d_buf, _q->window_len, _q->hist_tmp, d_x, _n, st);
+    LC_CUDA_CHECK(cudaStreamSynchronize(st));
+    set_psd_ones(_q);                                           // estimate_psd leaves psd as reset left it
+    for (unsigned int k = 0; k < nfft; k++)
+        _psd[(k + nfft / 2) % nfft] = 10 * log10f(sum[k] / (float)T);
+}
+
+void spgramcf_estimate_psd(spgramcf _q, liquid_float_complex *_x, unsigned int _n, float *_psd)
+{
+    if (_n == 0) {
+        fprintf(stderr, "warning: spgram%s_estimate_psd(), input size is zero\n", "cf");
+        return;
+    }
+    float2 *d = (float2 *)_q->stage.get(sizeof(float2) * (size_t)_n);
+    LC_CUDA_CHECK(cudaMemcpyAsync(d, _x, sizeof(float2) * (size_t)_n, cudaMemcpyHostToDevice, _q->stream));
+    spgramcf_estimate_psd_dev(_q, d, _n, _psd, _q->stream);
+}
+
+unsigned int spgramcf_get_num_transforms(spgramcf _q) { return _q->num_transforms; }
+
+}  // extern "C"

@@ -13,6 +13,9 @@ the record of how the fixture was made.
              5th digit, which moves every tap by ~1e-5: fine for a filter, useless as a pin)
   scalars    estimate_req_filter_As, rkaiser_approximate_rho, liquid_filter_isi points
   cccf_*     firpfbch_cccf_create with seeded complex taps: analysis and synthesis outputs
+  spgram_*   spgramcf (8f item 2): execute / execute_psd after a write, accumulate_psd in two calls
+             (alpha 0.3: the first call runs with alpha = 1 by the reference's quirk) + write_accumulation,
+             and estimate_psd, on a tone-plus-noise input
 """
 import ctypes as C
 import os
@@ -79,6 +82,27 @@ for M, p in [(8, 6), (16, 8), (12, 5), (64, 4)]:
     out["cccf_M%d_p%d_x" % (M, p)] = x
     out["cccf_M%d_p%d_a_y" % (M, p)] = O.ref_firpfbch_cccf_frames(O.ANALYZER, M, p, h, x)
     out["cccf_M%d_p%d_s_y" % (M, p)] = O.ref_firpfbch_cccf_frames(O.SYNTHESIZER, M, p, h, x)
+
+# spgramcf
+for nfft, wl, beta in [(64, 32, 10.0), (256, 200, 6.0), (1024, 512, 10.0), (100, 60, 8.0), (16, 16, 3.0)]:
+    n = 6 * nfft + 37
+    t = np.arange(n)
+    x = (O.synth_input(n, seed=0x5EED9000 + nfft) * np.float32(0.1)
+         + np.exp(2j * np.pi * 0.17 * t).astype(np.complex64)).astype(np.complex64)
+    tag = "spgram_n%d_w%d" % (nfft, wl)
+    out[tag + "_args"] = np.array([nfft, wl, beta], np.float64)
+    out[tag + "_x"] = x
+    q = O.RefSpgramcf(nfft, window_len=wl, beta=beta)
+    q.write(x[: wl + 5])
+    out[tag + "_X"] = q.execute()
+    out[tag + "_psd"] = q.execute_psd()
+    q.reset()
+    q.accumulate_psd(x[: 2 * nfft + 3], 0.3)
+    out[tag + "_acc1"] = q.write_accumulation()
+    q.accumulate_psd(x[2 * nfft + 3:], 0.3)
+    out[tag + "_acc2"] = q.write_accumulation()
+    out[tag + "_est"] = q.estimate_psd(x)
+    del q
 
 path = os.path.join(HERE, "..", "tests", "golden", "ref_outputs_next.npz")
 np.savez_compressed(path, **out)

@@ -817,6 +817,151 @@ void orc_firpfbch_cccf_execute_frames(orc_firpfbch_cccf q, const orc_cf *x, unsi
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* spgramcf: windowed-FFT spectral periodogram                      */
+/* src/fft/src/spgramcf.c:27-51 instantiating src/fft/src/spgram.c                        */
+/* ------------------------------------------------------------------------------------ */
+
+struct orc_spgramcf_s {
+    unsigned int nfft, window_len;
+    orc_cf *buf;                /* last window_len samples, oldest first */
+    float *w;                   /* scaled tapering window */
+    orc_cf *x, *X;              /* transform in / out */
+    float *psd;                 /* accumulation */
+    unsigned int sample_counter, num_transforms;
+};
+
+/* spgram.c:180-199 */
+void orc_spgramcf_reset(orc_spgramcf q)
+{
+    memset(q->buf, 0, q->window_len * sizeof *q->buf);
+    memset(q->x, 0, q->nfft * sizeof *q->x);
+    q->num_transforms = 0;
+    q->sample_counter = 0;
+    for (unsigned int i = 0; i < q->nfft; i++) q->psd[i] = 1;
+}
+
+/* spgram.c:57-107: the window is scaled by sqrt(2) / (rms(window) sqrt(nfft)) */
+orc_spgramcf orc_spgramcf_create(unsigned int nfft, const float *window, unsigned int window_len)
+{
+    if (nfft < 2 || window_len > nfft || window_len == 0) return NULL;
+    orc_spgramcf q = xmalloc(sizeof *q);
+    q->nfft = nfft;
+    q->window_len = window_len;
+    q->x = xmalloc(nfft * sizeof *q->x);
+    q->X = xmalloc(nfft * sizeof *q->X);
+    q->psd = xmalloc(nfft * sizeof *q->psd);
+    q->buf = xmalloc(window_len * sizeof *q->buf);
+    q->w = xmalloc(window_len * sizeof *q->w);
+    float g = 0.0f;
+    for (unsigned int i = 0; i < window_len; i++) g += window[i] * window[i];
+    g = M_SQRT2 / (sqrtf(g / window_len) * sqrtf((float)nfft));
+    for (unsigned int i = 0; i < window_len; i++) q->w[i] = g * window[i];
+    orc_spgramcf_reset(q);
+    return q;
+}
+
+/* spgram.c:113-147: Kaiser-Bessel taper kaiser(i, window_len, beta, 0) */
+orc_spgramcf orc_spgramcf_create_kaiser(unsigned int nfft, unsigned int window_len, float beta)
+{
+    if (nfft < 2 || window_len > nfft || window_len == 0 || beta <= 0.0f) return NULL;
+    float *w = xmalloc(window_len * sizeof *w);
+    for (unsigned int i = 0; i < window_len; i++) w[i] = orc_kaiser(i, window_len, beta, 0.0f);
+    orc_spgramcf q = orc_spgramcf_create(nfft, w, window_len);
+    free(w);
+    return q;
+}
+
+/* spgram.c:150-162: window nfft/2, beta 10 */
+orc_spgramcf orc_spgramcf_create_default(unsigned int nfft)
+{
+    if (nfft < 2) return NULL;
+    return orc_spgramcf_create_kaiser(nfft, nfft / 2, 10.0f);
+}
+
+void orc_spgramcf_destroy(orc_spgramcf q)
+{
+    if (q) { free(q->x); free(q->X); free(q->psd); free(q->buf); free(q->w); free(q); }
+}
+
+void orc_spgramcf_push(orc_spgramcf q, orc_cf v) { win_push(q->buf, q->window_len, v); }   /* spgram.c:202-207 */
+
+void orc_spgramcf_write(orc_spgramcf q, const orc_cf *x, unsigned int n)                    /* spgram.c:213-219 */
+{
+    for (unsigned int i = 0; i < n; i++) win_push(q->buf, q->window_len, x[i]);
+}
+
+/* spgram.c:226-244: taper the buffer into the first window_len transform inputs (the rest stay
+ * zero), forward transform */
+void orc_spgramcf_execute(orc_spgramcf q, orc_cf *X)
+{
+    for (unsigned int i = 0; i < q->window_len; i++)
+        q->x[i] = cf(q->buf[i].re * q->w[i], q->buf[i].im * q->w[i]);
+    orc_fft_run(q->nfft, q->x, q->X, ORC_FFT_FORWARD);
+    if (X) memmove(X, q->X, q->nfft * sizeof *X);
+}
+
+static float magsq(orc_cf v) { return v.re * v.re + v.im * v.im; }   /* crealf(X * conjf(X)) */
+
+/* spgram.c:250-264: fft-shifted dB */
+void orc_spgramcf_execute_psd(orc_spgramcf q, float *out)
+{
+    orc_spgramcf_execute(q, NULL);
+    unsigned int h = q->nfft / 2;
+    for (unsigned int i = 0; i < q->nfft; i++) out[(i + h) % q->nfft] = 10 * log10f(magsq(q->X[i]) + 1e-16f);
+}
+
+/* spgram.c:271-311: a transform every window_len/2 pushes, psd <- (1-alpha) psd + alpha |X|^2; the
+ * first transform after a reset overrides alpha with 1 -- and, alpha being the function's own
+ * parameter, it stays 1 for the rest of THAT call */
+int orc_spgramcf_accumulate_psd(orc_spgramcf q, const orc_cf *x, float alpha, unsigned int n)
+{
+    if (alpha < 0.0f || alpha > 1.0f) return -1;
+    for (unsigned int i = 0; i < n; i++) {
+        win_push(q->buf, q->window_len, x[i]);
+        q->sample_counter++;
+        if (q->sample_counter == q->window_len / 2) {
+            if (q->num_transforms == 0) alpha = 1.0f;
+            orc_spgramcf_execute(q, NULL);
+            for (unsigned int k = 0; k < q->nfft; k++)
+                q->psd[k] = (1.0f - alpha) * q->psd[k] + alpha * magsq(q->X[k]);
+            q->sample_counter = 0;
+            q->num_transforms++;
+        }
+    }
+    return 0;
+}
+
+/* spgram.c:318-334 */
+void orc_spgramcf_write_accumulation(orc_spgramcf q, float *out)
+{
+    unsigned int h = q->nfft / 2;
+    for (unsigned int i = 0; i < q->nfft; i++) out[(i + h) % q->nfft] = 10 * log10f(q->psd[i]);
+}
+
+/* spgram.c:341-398: reset, a transform every nfft/4 samples (and after the last sample), plain
+ * average of |X|^2, fft-shifted dB */
+void orc_spgramcf_estimate_psd(orc_spgramcf q, const orc_cf *x, unsigned int n, float *psd)
+{
+    if (n == 0) return;
+    orc_spgramcf_reset(q);
+    unsigned int delay = q->nfft / 4;
+    if (delay == 0) delay = 1;
+    for (unsigned int i = 0; i < q->nfft; i++) psd[i] = 0.0f;
+    unsigned int num = 0;
+    for (unsigned int i = 0; i < n; i++) {
+        win_push(q->buf, q->window_len, x[i]);
+        if (((i + 1) % delay) == 0 || i == n - 1) {
+            orc_spgramcf_execute(q, NULL);
+            for (unsigned int k = 0; k < q->nfft; k++) psd[(k + q->nfft / 2) % q->nfft] += magsq(q->X[k]);
+            num++;
+        }
+    }
+    for (unsigned int i = 0; i < q->nfft; i++) psd[i] = 10 * log10f(psd[i] / (float)num);
+}
+
+unsigned int orc_spgramcf_num_transforms(orc_spgramcf q) { return q->num_transforms; }
+
+/* ------------------------------------------------------------------------------------ */
 /* firpfbch2_crcf: channelizer with output rate 2 Fs / M                                 */
 /* ------------------------------------------------------------------------------------ */
 

@@ -109,6 +109,24 @@ def lib():
         L.orc_firpfbch_cccf_destroy.argtypes = [C.c_void_p]
         L.orc_firpfbch_cccf_execute_frames.restype = None
         L.orc_firpfbch_cccf_execute_frames.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
+        L.orc_spgramcf_create.restype = C.c_void_p
+        L.orc_spgramcf_create.argtypes = [C.c_uint, c_f_p, C.c_uint]
+        L.orc_spgramcf_create_kaiser.restype = C.c_void_p
+        L.orc_spgramcf_create_kaiser.argtypes = [C.c_uint, C.c_uint, C.c_float]
+        L.orc_spgramcf_create_default.restype = C.c_void_p
+        L.orc_spgramcf_create_default.argtypes = [C.c_uint]
+        for fn in ("destroy", "reset"):
+            getattr(L, "orc_spgramcf_" + fn).argtypes = [C.c_void_p]
+        L.orc_spgramcf_push.argtypes = [C.c_void_p, c_cf]
+        L.orc_spgramcf_write.argtypes = [C.c_void_p, c_cf_p, C.c_uint]
+        L.orc_spgramcf_execute.argtypes = [C.c_void_p, c_cf_p]
+        L.orc_spgramcf_execute_psd.argtypes = [C.c_void_p, c_f_p]
+        L.orc_spgramcf_accumulate_psd.restype = C.c_int
+        L.orc_spgramcf_accumulate_psd.argtypes = [C.c_void_p, c_cf_p, C.c_float, C.c_uint]
+        L.orc_spgramcf_write_accumulation.argtypes = [C.c_void_p, c_f_p]
+        L.orc_spgramcf_estimate_psd.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_f_p]
+        L.orc_spgramcf_num_transforms.restype = C.c_uint
+        L.orc_spgramcf_num_transforms.argtypes = [C.c_void_p]
         L.orc_firpfbch_destroy.argtypes = [C.c_void_p]; L.orc_firpfbch_reset.argtypes = [C.c_void_p]
         L.orc_firpfbch_execute_frames.restype = None
         L.orc_firpfbch_execute_frames.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
@@ -273,6 +291,61 @@ class Firpfbch(_Obj):
         y = np.empty_like(x)
         lib().orc_firpfbch_execute_frames(self.h, x, x.shape[0], y)
         return y
+
+
+class Spgramcf(_Obj):
+    """spgramcf: windowed-FFT periodogram; create(nfft, window=...) | (nfft, window_len=, beta=) | (nfft)"""
+    _destroy = "orc_spgramcf_destroy"
+
+    def __init__(self, nfft, window=None, window_len=None, beta=None):
+        self.nfft = nfft
+        if window is not None:
+            hd = lib().orc_spgramcf_create(nfft, _f(window), len(window))
+        elif window_len is not None:
+            hd = lib().orc_spgramcf_create_kaiser(nfft, window_len, beta)
+        else:
+            hd = lib().orc_spgramcf_create_default(nfft)
+        super().__init__(hd)
+
+    def reset(self):
+        lib().orc_spgramcf_reset(self.h)
+
+    def push(self, v):
+        v = complex(v)
+        lib().orc_spgramcf_push(self.h, c_cf(v.real, v.imag))
+
+    def write(self, x):
+        x = _cf(x)
+        lib().orc_spgramcf_write(self.h, x, len(x))
+
+    def execute(self):
+        X = np.empty(self.nfft, np.complex64)
+        lib().orc_spgramcf_execute(self.h, X)
+        return X
+
+    def execute_psd(self):
+        out = np.empty(self.nfft, np.float32)
+        lib().orc_spgramcf_execute_psd(self.h, out)
+        return out
+
+    def accumulate_psd(self, x, alpha):
+        x = _cf(x)
+        if lib().orc_spgramcf_accumulate_psd(self.h, x, alpha, len(x)):
+            raise ValueError("spgramcf_accumulate_psd: alpha must be in [0,1]")
+
+    def write_accumulation(self):
+        out = np.empty(self.nfft, np.float32)
+        lib().orc_spgramcf_write_accumulation(self.h, out)
+        return out
+
+    def estimate_psd(self, x):
+        x = _cf(x)
+        out = np.empty(self.nfft, np.float32)
+        lib().orc_spgramcf_estimate_psd(self.h, x, len(x), out)
+        return out
+
+    def num_transforms(self):
+        return lib().orc_spgramcf_num_transforms(self.h)
 
 
 class FirpfbchCccf(_Obj):
@@ -459,6 +532,68 @@ def ref_firpfbch_cccf_frames(type, M, p, h, x):
         fn(q, x[t], y[t])
     R.firpfbch_cccf_destroy(q)
     return y
+
+
+class RefSpgramcf:
+    """the compiled reference's spgramcf behind the same methods as Spgramcf"""
+
+    def __init__(self, nfft, window=None, window_len=None, beta=None):
+        R = ref()
+        R.spgramcf_create.restype = C.c_void_p; R.spgramcf_create.argtypes = [C.c_uint, c_f_p, C.c_uint]
+        R.spgramcf_create_kaiser.restype = C.c_void_p; R.spgramcf_create_kaiser.argtypes = [C.c_uint, C.c_uint, C.c_float]
+        R.spgramcf_create_default.restype = C.c_void_p; R.spgramcf_create_default.argtypes = [C.c_uint]
+        for fn in ("destroy", "reset"):
+            getattr(R, "spgramcf_" + fn).argtypes = [C.c_void_p]
+        R.spgramcf_write.argtypes = [C.c_void_p, c_cf_p, C.c_uint]
+        R.spgramcf_execute.argtypes = [C.c_void_p, c_cf_p]
+        R.spgramcf_execute_psd.argtypes = [C.c_void_p, c_f_p]
+        R.spgramcf_accumulate_psd.argtypes = [C.c_void_p, c_cf_p, C.c_float, C.c_uint]
+        R.spgramcf_write_accumulation.argtypes = [C.c_void_p, c_f_p]
+        R.spgramcf_estimate_psd.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_f_p]
+        self.R, self.nfft = R, nfft
+        if window is not None:
+            self.q = C.c_void_p(R.spgramcf_create(nfft, _f(window), len(window)))
+        elif window_len is not None:
+            self.q = C.c_void_p(R.spgramcf_create_kaiser(nfft, window_len, beta))
+        else:
+            self.q = C.c_void_p(R.spgramcf_create_default(nfft))
+
+    def __del__(self):
+        if getattr(self, "q", None):
+            self.R.spgramcf_destroy(self.q)
+            self.q = None
+
+    def reset(self):
+        self.R.spgramcf_reset(self.q)
+
+    def write(self, x):
+        x = _cf(x)
+        self.R.spgramcf_write(self.q, x, len(x))
+
+    def execute(self):
+        X = np.empty(self.nfft, np.complex64)
+        self.R.spgramcf_execute(self.q, X)
+        return X
+
+    def execute_psd(self):
+        out = np.empty(self.nfft, np.float32)
+        self.R.spgramcf_execute_psd(self.q, out)
+        return out
+
+    def accumulate_psd(self, x, alpha):
+        x = _cf(x)
+        self.R.spgramcf_accumulate_psd(self.q, x, alpha, len(x))
+
+    def write_accumulation(self):
+        out = np.empty(self.nfft, np.float32)
+        self.R.spgramcf_write_accumulation(self.q, out)
+        return out
+
+    def estimate_psd(self, x):
+        x = _cf(x)
+        out = np.empty(self.nfft, np.float32)
+        self.R.spgramcf_estimate_psd(self.q, x, len(x), out)
+        return out
 
 
 def ref_firfilt_block(x, h=None, kaiser=None, scale=None):

@@ -630,6 +630,32 @@ def test_pfbch_cccf_real_taps_take_the_crcf_path(L, orc, monkeypatch):
         assert np.array_equal(q.analyzer_run(0), want[t])
 
 
+# ------------------------------------------------------------------ spgramcf
+def test_spgramcf_vs_reference_fixture_and_oracle(L, orc, refrn):
+    """every entry point against the compiled reference's outputs (power-of-two and other nfft), plus a
+    long block against the oracle: many transforms per call, several fold chunks, alpha < 1"""
+    from test_oracle import _spgram_cases, _spgram_run, lin_close, spgram_check
+    for tag, nfft, wl, beta in _spgram_cases(refrn):
+        q = L.spgramcf.create_kaiser(nfft, wl, beta)
+        spgram_check(_spgram_run(q, refrn[tag + "_x"], nfft, wl), refrn, tag)
+    nfft, wl = 256, 160
+    x = (orc.synth_input(3000 * nfft, seed=0x59) * np.float32(0.2)
+         + np.exp(2j * np.pi * 0.11 * np.arange(3000 * nfft)).astype(np.complex64)).astype(np.complex64)
+    q, o = L.spgramcf.create_kaiser(nfft, wl, 8.0), orc.Spgramcf(nfft, window_len=wl, beta=8.0)
+    for part, alpha in ((x[:1000], 0.5), (x[1000:400000], 0.02), (x[400000:400077], 0.02), (x[400077:], 0.001)):
+        q.accumulate_psd(part, alpha)
+        o.accumulate_psd(part, alpha)
+        assert q.num_transforms() == o.num_transforms()
+        assert lin_close(q.write_accumulation(), o.write_accumulation(), rel=1e-5)
+    assert lin_close(q.estimate_psd(x), o.estimate_psd(x), rel=1e-5)
+    # push one sample at a time == write
+    q.reset(); o.reset()
+    for v in x[:wl + 3]:
+        q.push(v)
+    o.write(x[:wl + 3])
+    assert np.abs(q.execute() - o.execute()).max() < 2e-6 * np.abs(o.execute()).max()
+
+
 # ------------------------------------------------------------------ cluster-of-8 M=4096 kernel specifics
 @pytest.mark.parametrize("m", [4, 7, 9])
 def test_pfbch2_cluster_4096_vs_oracle_odd_splits(L, orc, m):

@@ -360,3 +360,62 @@ def test_pfbch_cccf_real_taps_equal_crcf(orc):
         a = orc.FirpfbchCccf(typ, M, 2 * m, h.astype(np.complex64)).execute_frames(x)
         b = orc.Firpfbch(typ, M, p=2 * m, h=h).execute_frames(x)
         assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
+
+
+# ------------------------------------------------------------------ spgramcf
+def _spgram_cases(refrn):
+    for name in sorted(k for k in refrn if k.startswith("spgram_") and k.endswith("_args")):
+        nfft, wl, beta = refrn[name]
+        yield name[:-5], int(nfft), int(wl), np.float32(beta)
+
+
+def _spgram_run(q, x, nfft, wl):
+    q.write(x[: wl + 5])
+    X, psd = q.execute(), q.execute_psd()
+    q.reset()
+    q.accumulate_psd(x[: 2 * nfft + 3], 0.3)
+    acc1 = q.write_accumulation()
+    q.accumulate_psd(x[2 * nfft + 3:], 0.3)
+    acc2 = q.write_accumulation()
+    est = q.estimate_psd(x)
+    return X, psd, acc1, acc2, est
+
+
+def lin_close(got_db, want_db, rel=2e-6):
+    """dB spectra compared as linear power relative to the strongest bin: a float32 FFT is accurate to
+    ~1e-7 of the LARGEST component, so a bin 50 dB down is only good to ~1e-4 dB while its absolute error
+    in power stays far below rel * peak"""
+    g, w = 10.0 ** (np.asarray(got_db, np.float64) / 10), 10.0 ** (np.asarray(want_db, np.float64) / 10)
+    return np.abs(g - w).max() <= rel * w.max()
+
+
+def spgram_check(res, refrn, tag):
+    X, psd, acc1, acc2, est = res
+    assert np.abs(X - refrn[tag + "_X"]).max() <= 2e-6 * np.abs(refrn[tag + "_X"]).max()
+    for got, key in ((psd, "_psd"), (acc1, "_acc1"), (acc2, "_acc2"), (est, "_est")):
+        assert lin_close(got, refrn[tag + key]), (tag, key)
+
+
+def test_fixture_spgramcf(orc, refrn):
+    for tag, nfft, wl, beta in _spgram_cases(refrn):
+        q = orc.Spgramcf(nfft, window_len=wl, beta=beta)
+        spgram_check(_spgram_run(q, refrn[tag + "_x"], nfft, wl), refrn, tag)
+
+
+def test_spgramcf_properties(orc):
+    """default object = Kaiser(nfft/2, beta 10); the window scaling sqrt(2) / (rms(w) sqrt(nfft)) puts white
+    input of power P at 2 P window_len / nfft per bin on average (= P for the default window); the first
+    accumulate_psd call after a reset runs with alpha = 1 whatever was asked (spgram.c:291-292), so it
+    leaves the LAST periodogram"""
+    nfft = 128
+    x = orc.synth_input(40 * nfft, seed=77)                   # uniform +-0.5 per component: power 1/6
+    q = orc.Spgramcf(nfft)
+    est = q.estimate_psd(x)
+    mean_lin = np.mean(10 ** (est / 10))
+    assert abs(mean_lin - 1.0 / 6.0) < 0.02
+    q.reset()
+    q.accumulate_psd(x[:5 * nfft], 0.1)
+    first = q.write_accumulation()
+    q2 = orc.Spgramcf(nfft)
+    q2.write(x[:5 * nfft])                                    # same buffer contents as after the last transform
+    assert np.abs(first - q2.execute_psd()).max() < 1e-3

@@ -3,7 +3,7 @@
 measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
 events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
 
-  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
+  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
 """
 import argparse
 import json
@@ -145,6 +145,19 @@ def main():
         ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
         report("f1b: firpfbch_cccf analysis M=256 p=10, complex taps (shape-generic MAC + FFT kernels), 2^27 samples", n, 16, ms, ln)
         del x, y
+    if "f2" in args.configs:
+        # spgramcf_accumulate_psd on a device-resident block: default object (Kaiser window
+        # nfft/2, a transform every nfft/4 samples ... window_len/2), 2^28 samples
+        for nfft in (256, 1024, 4096):
+            n = 1 << 28
+            x = torch.empty(2 * n, dtype=torch.float32, device=dev)
+            L.synth_input_dev(x.data_ptr(), n, stream=st.cuda_stream)
+            q = L.spgramcf.create_default(nfft)
+            ms, ln = timed(lambda: q.accumulate_psd_dev(x.data_ptr(), 0.01, n, st.cuda_stream))
+            report("f2: spgramcf_accumulate_psd nfft=%d window=%d (one transform per %d samples), 2^28 samples"
+                   % (nfft, nfft // 2, nfft // 4), n, 8, ms, ln,
+                   {"transforms_per_step": n // (nfft // 4), "note": "algorithmic bytes: the input, read once"})
+            del x
 
 
 if __name__ == "__main__":
