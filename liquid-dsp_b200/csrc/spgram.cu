@@ -6,16 +6,17 @@
 //
 // The reference takes one transform at a time inside a per-sample loop; here a whole block of samples
 // becomes a batch of T overlapping transforms:
-//   spgram_transform_pow2_kernel   (power-of-two nfft that fits shared memory) tapers the segments of a few
-//                                  transforms straight into shared memory (zero-padded to nfft), runs the
-//                                  Stockham FFT of fft_device.cuh there and stores |X|^2 (or X) -- the
-//                                  tapered segments never visit HBM; any other nfft: gather kernel + the
-//                                  batched DFT of fft.cu + a |X|^2 kernel
-//   spgram_fold_kernel             folds the T spectra of a chunk into one partial per frequency bin with the
-//                                  reference's recurrence  psd <- (1-alpha) psd + alpha |X|^2  (or a plain sum
-//                                  for estimate_psd); chunk 0 starts from the object's psd, so a block of up to
-//                                  64 transforms is folded in exactly the reference's order
+//   spgram_accumulate_pow2_kernel  (power-of-two nfft that fits shared memory: the throughput path) CTA c walks a
+//                                  run of consecutive transforms: taper straight into shared memory (zero-padded
+//                                  to nfft), Stockham FFT of fft_device.cuh there, and |X|^2 folded into register
+//                                  accumulators with the reference's recurrence
+//                                      psd <- (1-alpha) psd + alpha |X|^2      (plain sum for estimate_psd)
+//                                  in transform order; it leaves one partial spectrum.  Neither the tapered
+//                                  segments nor the T spectra visit HBM.  Chunk 0 starts from the object's psd, so
+//                                  a block of up to 64 transforms is folded in exactly the reference's order.
 //   spgram_combine_kernel          psd <- decay_c psd + partial_c over the chunks, in order
+//   spgram_transform_pow2_kernel   one transform's X (spgramcf_execute)
+//   any other nfft                 gather kernel -> batched DFT of fft.cu -> |X|^2 -> spgram_fold_kernel -> combine
 // Same state as the reference: the last window_len samples, psd[nfft] (1 after reset), sample_counter,
 // num_transforms -- including the quirk that the first transform after a reset forces alpha = 1 for the
 // rest of that accumulate_psd call (alpha is the function's own parameter, spgram.c:291-292).
@@ -96,6 +97,66 @@ spgram_transform_pow2_kernel(const float2 *__restrict__ hist, const float2 *__re
     }
 }
 
+// power-of-two nfft, the throughput path of accumulate_psd / estimate_psd: CTA c walks the `tpc` consecutive
+// transforms [c tpc, (c+1) tpc) -- taper into shared memory, Stockham FFT, and the fold of |X|^2 into per-thread
+// register accumulators (bins tid, tid+256, ...) in transform order -- and leaves ONE partial spectrum; neither
+// the tapered segments nor the T spectra ever visit HBM.  Consecutive transforms overlap by 50-75 % of their
+// input, which L1/L2 serve.
+__global__ void __launch_bounds__(lcfft::kFftThreads)
+spgram_accumulate_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                              const float *__restrict__ w, unsigned int window_len, const float2 *__restrict__ tw,
+                              unsigned int nfft, unsigned int log2n, unsigned int per_cta, unsigned long long T,
+                              unsigned int tpc, Segs segs, const float *__restrict__ psd, float *__restrict__ partial,
+                              float alpha, int seed_psd)
+{
+    extern __shared__ float2 smem_f2[];
+    float2 *buf0 = smem_f2, *buf1 = smem_f2 + (size_t)per_cta * nfft;
+    const unsigned long long t_begin = (unsigned long long)blockIdx.x * tpc;
+    unsigned long long t_end = t_begin + tpc;
+    if (t_end > T) t_end = T;
+    constexpr int kMaxBins = 4096 / lcfft::kFftThreads;                // bins per thread at nfft = 4096
+    float acc[kMaxBins];
+#pragma unroll
+    for (int b = 0; b < kMaxBins; b++) {
+        const unsigned int k = threadIdx.x + b * lcfft::kFftThreads;
+        acc[b] = (seed_psd && blockIdx.x == 0 && k < nfft) ? psd[k] : 0.0f;
+    }
+    const float keep = 1.0f - alpha;
+    const unsigned int total = per_cta * nfft;
+    for (unsigned long long g0 = t_begin; g0 < t_end; g0 += per_cta) {
+        for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
+            const unsigned long long t = g0 + i / nfft;
+            const unsigned int k = i % nfft;
+            float2 v = make_float2(0.f, 0.f);
+            if (t < t_end && k < window_len) {
+                const float2 sv = ld_sample(hist, x, segs.end_of(t) - (long long)(window_len - 1) + k, H);
+                const float c = __ldg(w + k);
+                v = make_float2(sv.x * c, sv.y * c);
+            }
+            buf0[i] = v;
+        }
+        __syncthreads();
+        const float2 *res = lcfft::stockham_pow2(buf0, buf1, tw, nfft, log2n, per_cta, -1.0f);
+        for (unsigned int tt = 0; tt < per_cta && g0 + tt < t_end; tt++) {
+#pragma unroll
+            for (int b = 0; b < kMaxBins; b++) {
+                const unsigned int k = threadIdx.x + b * lcfft::kFftThreads;
+                if (k < nfft) {
+                    const float2 X = res[tt * nfft + k];
+                    const float P = X.x * X.x + X.y * X.y;
+                    acc[b] = (alpha < 0.0f) ? acc[b] + P : keep * acc[b] + alpha * P;
+                }
+            }
+        }
+        __syncthreads();                                               // the buffers are refilled next
+    }
+#pragma unroll
+    for (int b = 0; b < kMaxBins; b++) {
+        const unsigned int k = threadIdx.x + b * lcfft::kFftThreads;
+        if (k < nfft) partial[(size_t)blockIdx.x * nfft + k] = acc[b];
+    }
+}
+
 // any nfft: tapered, zero-padded segments [T][nfft] for the batched DFT
 __global__ void __launch_bounds__(kThreads)
 spgram_gather_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ w,
@@ -149,23 +210,21 @@ spgram_fold_kernel(const float *__restrict__ P, const float *__restrict__ psd, f
 }
 
 // psd[k] = partial[0][k]; for c >= 1: psd[k] = decay(c) psd[k] + partial[c][k], decay(c) = (1-alpha)^(transforms in
-// chunk c), or 1 for the plain sum
+// chunk c) (all chunks but the last hold `chunk` transforms), or 1 for the plain sum
 __global__ void __launch_bounds__(kThreads)
 spgram_combine_kernel(const float *__restrict__ partial, float *__restrict__ psd, unsigned int nfft,
                       unsigned int n_chunks, unsigned int chunk, unsigned long long T, float alpha)
 {
     const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nfft) return;
-    float s = partial[k];
-    for (unsigned int c = 1; c < n_chunks; c++) {
-        float decay = 1.0f;
-        if (alpha >= 0.0f) {
-            unsigned long long cnt = T - (unsigned long long)c * chunk;
-            if (cnt > chunk) cnt = chunk;
-            decay = powf(1.0f - alpha, (float)cnt);
-        }
-        s = decay * s + partial[(size_t)c * nfft + k];
+    float d_full = 1.0f, d_last = 1.0f;
+    if (alpha >= 0.0f) {
+        d_full = powf(1.0f - alpha, (float)chunk);
+        d_last = powf(1.0f - alpha, (float)(T - (unsigned long long)(n_chunks - 1) * chunk));
     }
+    float s = partial[k];
+    for (unsigned int c = 1; c < n_chunks; c++)
+        s = ((c + 1 == n_chunks) ? d_last : d_full) * s + __ldg(partial + (size_t)c * nfft + k);
     psd[k] = s;
 }
 
@@ -213,12 +272,12 @@ void run_transforms(spgramcf q, const float2 *d_x, unsigned long long T, Segs se
 }
 
 // fold T spectra-in-time into q->d_psd: alpha in [0,1] -> the reference's recurrence seeded with psd;
-// alpha < 0 -> plain sum (psd is overwritten by the sum, the caller zeroed nothing: seed off)
+// alpha < 0 -> plain sum on top of psd
 void fold_into_psd(spgramcf q, const float *d_P, unsigned long long T, float alpha, int seed_psd, cudaStream_t st)
 {
     const unsigned int nfft = q->nfft;
     unsigned int chunk = kFoldChunk;
-    if ((T + chunk - 1) / chunk > 2048) chunk = (unsigned int)((T + 2047) / 2048);
+    if ((T + chunk - 1) / chunk > 256) chunk = (unsigned int)((T + 255) / 256);
     const unsigned int n_chunks = (unsigned int)((T + chunk - 1) / chunk);
     float *d_part = (float *)q->partials.get(sizeof(float) * (size_t)n_chunks * nfft);
     dim3 grid((nfft + kThreads - 1) / kThreads, n_chunks);
@@ -228,11 +287,46 @@ void fold_into_psd(spgramcf q, const float *d_P, unsigned long long T, float alp
     LC_LAUNCH_CHECK();
 }
 
-// transforms of one pass are cut so that their spectra fit the scratch budget
-unsigned long long pass_limit(unsigned int nfft)
+// all T transforms of the (hist | x) stream folded into q->d_psd (alpha < 0: plain sum on top of it)
+void accumulate_transforms(spgramcf q, const float2 *d_x, unsigned long long T, Segs segs, float alpha, cudaStream_t st)
 {
-    unsigned long long lim = kScratchBytes / ((unsigned long long)nfft * sizeof(float));
-    return lim ? lim : 1;
+    if (T == 0) return;
+    const unsigned int nfft = q->nfft;
+    if (lcfft::pow2_in_smem(nfft)) {
+        static bool once = false;
+        if (!once) {
+            LC_CUDA_CHECK(cudaFuncSetAttribute(spgram_accumulate_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            once = true;
+        }
+        // transforms per CTA: a block of up to 64 transforms is one chunk (folded in exactly the reference's
+        // order); beyond that aim at ~8 CTAs per SM, at most 2048 chunks for the combine pass
+        unsigned long long tpc = kFoldChunk;
+        if (T > tpc * 148 * 8) tpc = (T + 148 * 8 - 1) / (148 * 8);
+        if ((T + tpc - 1) / tpc > 2048) tpc = (T + 2047) / 2048;
+        const unsigned int per_cta = lcfft::per_cta_for(nfft, tpc);
+        tpc = (tpc + per_cta - 1) / per_cta * per_cta;
+        const unsigned int n_chunks = (unsigned int)((T + tpc - 1) / tpc);
+        float *d_part = (float *)q->partials.get(sizeof(float) * (size_t)n_chunks * nfft);
+        spgram_accumulate_pow2_kernel<<<n_chunks, lcfft::kFftThreads, lcfft::smem_for(nfft, per_cta), st>>>(
+            q->d_buf, d_x, (int)q->window_len, q->d_w, q->window_len, q->fft.d_tw, nfft, lc::ilog2(nfft), per_cta, T,
+            (unsigned int)tpc, segs, q->d_psd, d_part, alpha, 1);
+        LC_LAUNCH_CHECK();
+        spgram_combine_kernel<<<(nfft + kThreads - 1) / kThreads, kThreads, 0, st>>>(d_part, q->d_psd, nfft, n_chunks,
+                                                                                  (unsigned int)tpc, T, alpha);
+        LC_LAUNCH_CHECK();
+        return;
+    }
+    // any other nfft: passes of gather -> batched DFT -> |X|^2 -> fold, cut so that the spectra fit the scratch budget
+    unsigned long long lim = kScratchBytes / ((unsigned long long)nfft * sizeof(float2));
+    if (lim == 0) lim = 1;
+    for (unsigned long long done = 0; done < T;) {
+        const unsigned long long nt = (T - done < lim) ? T - done : lim;
+        float *d_P = (float *)q->spectra.get(sizeof(float) * nt * nfft);
+        Segs sub{segs.e0 + (long long)done * segs.hop, segs.hop, segs.e_max};
+        run_transforms(q, d_x, nt, sub, 0, d_P, st);
+        fold_into_psd(q, d_P, nt, alpha, 1, st);
+        done += nt;
+    }
 }
 
 void set_psd_ones(spgramcf q)
@@ -363,15 +457,7 @@ void spgramcf_accumulate_psd_dev(spgramcf _q, const void *_d_x, float _alpha, un
     }
     // the first transform after a reset forces alpha = 1 for the rest of this call (spgram.c:291-292)
     const float alpha = (_q->num_transforms == 0 && T > 0) ? 1.0f : _alpha;
-    const unsigned long long lim = pass_limit(_q->nfft);
-    for (unsigned long long done = 0; done < T;) {
-        const unsigned long long nt = (T - done < lim) ? T - done : lim;
-        float *d_P = (float *)_q->spectra.get(sizeof(float) * nt * _q->nfft);
-        Segs segs{e0 + (long long)done * hop, (long long)hop, (long long)_n - 1};
-        run_transforms(_q, d_x, nt, segs, 0, d_P, st);
-        fold_into_psd(_q, d_P, nt, alpha, 1, st);
-        done += nt;
-    }
+    accumulate_transforms(_q, d_x, T, Segs{e0, (long long)hop, (long long)_n - 1}, alpha, st);
     lc::roll_history(_q->d_buf, _q->window_len, _q->hist_tmp, d_x, _n, st);
     if (hop > 0) {
         _q->sample_counter = (unsigned int)((_n + _q->sample_counter) % hop);
@@ -418,15 +504,7 @@ void spgramcf_estimate_psd_dev(spgramcf _q, const void *_d_x, unsigned long long
     const unsigned int nfft = _q->nfft;
     // the sum is kept in d_psd while the passes run, then the reset state is restored
     LC_CUDA_CHECK(cudaMemsetAsync(_q->d_psd, 0, sizeof(float) * nfft, st));
-    const unsigned long long lim = pass_limit(nfft);
-    for (unsigned long long done = 0; done < T;) {
-        const unsigned long long nt = (T - done < lim) ? T - done : lim;
-        float *d_P = (float *)_q->spectra.get(sizeof(float) * nt * nfft);
-        Segs segs{(long long)(done + 1) * delay - 1, (long long)delay, (long long)_n - 1};
-        run_transforms(_q, d_x, nt, segs, 0, d_P, st);
-        fold_into_psd(_q, d_P, nt, -1.0f, 1, st);               // plain sum on top of what is there
-        done += nt;
-    }
+    accumulate_transforms(_q, d_x, T, Segs{(long long)delay - 1, (long long)delay, (long long)_n - 1}, -1.0f, st);
     std::vector<float> sum(nfft);
     LC_CUDA_CHECK(cudaMemcpyAsync(sum.data(), _q->d_psd, sizeof(float) * nfft, cudaMemcpyDeviceToHost, st));
     lc::roll_history(_q->d_buf, _q->window_len, _q->hist_tmp, d_x, _n, st);
