@@ -19,30 +19,29 @@ namespace {
 using lcfft::fft_post;
 using lcfft::kFftThreads;
 
-// Stockham autosort FFT of n = 2^log2n points per transform, `per_cta` transforms per CTA.
-// smem: 2 * per_cta * n float2.
+// Stockham autosort FFT of n = 2^log2n points per transform, `per_cta` transforms per CTA (fft_device.cuh).
 __global__ void __launch_bounds__(kFftThreads)
 fft_pow2_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const float2 *__restrict__ tw,
                 unsigned int n, unsigned int log2n, unsigned int per_cta, unsigned long long batch,
                 float sgn, int post_mode, float pa, float pb)
 {
     extern __shared__ float2 smem[];
-    float2 *buf0 = smem;
-    float2 *buf1 = smem + (size_t)per_cta * n;
+    const lcfft::Smem sm = lcfft::carve(smem, n, per_cta);
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
     const unsigned int total = per_cta * n;
 
+    lcfft::stage_twiddles(sm, tw, n);
     for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
         unsigned long long b = first + i / n;
-        buf0[i] = (b < batch) ? x[b * n + (i % n)] : make_float2(0.f, 0.f);
+        sm.buf0[lcfft::pidx(i)] = (b < batch) ? x[b * n + (i % n)] : make_float2(0.f, 0.f);
     }
     __syncthreads();
 
-    float2 *in = lcfft::stockham_pow2(buf0, buf1, tw, n, log2n, per_cta, sgn);
+    const float2 *in = lcfft::stockham_pow2(sm, n, log2n, per_cta, sgn);
 
     for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
         unsigned long long b = first + i / n;
-        if (b < batch) y[b * n + (i % n)] = fft_post(in[i], post_mode, pa, pb);
+        if (b < batch) y[b * n + (i % n)] = fft_post(in[lcfft::pidx(i)], post_mode, pa, pb);
     }
 }
 

@@ -1,7 +1,16 @@
-// fft_device.cuh -- the shared-memory Stockham FFT used by the batched FFT kernel (fft.cu) and by the
-// shape-generic fused analyzers (pfb_kernels.cu), and the post-scaling of a transform's output.
+// fft_device.cuh -- the shared-memory FFT used by the batched FFT kernel (fft.cu), by the shape-generic
+// one-kernel analyzers (pfb_kernels.cu) and by the periodogram (spgram.cu), and the post-scaling of a
+// transform's output.
+//
+// Power-of-two n, `per_cta` transforms side by side in shared memory.  Stockham autosort passes of radix 16
+// (then one pass of radix 8 / 4 / 2 for what is left: 1024 = 16 * 16 * 4, three passes instead of five
+// radix-4 ones): a thread takes R points at stride n/R (consecutive threads read consecutive addresses),
+// multiplies by W_{R Ns}^(k m) from a table staged in shared memory, does the R-point DFT in registers
+// (RegDft, packed FP32x2) and writes them to their autosort positions.  Both buffers are stored with one
+// pad element per 16 (pidx), which makes the stride-R writes of the first pass bank-conflict-free as well.
 #pragma once
 #include "lc_common.cuh"
+#include "fused_common.cuh"
 
 namespace lcfft {
 
@@ -15,68 +24,97 @@ __device__ __forceinline__ float2 fft_post(float2 v, int mode, float a, float b)
     return v;
 }
 
-// multiply by s*j  (s = +1 or -1)
-__device__ __forceinline__ float2 mul_sj(float2 v, float s) { return make_float2(-s * v.y, s * v.x); }
+// physical position of logical element i of a buffer (i counts across the per_cta transforms)
+__host__ __device__ __forceinline__ unsigned int pidx(unsigned int i) { return i + (i >> 4); }
 
-// Stockham autosort FFT of `per_cta` transforms of n = 2^log2n points each, in shared memory: reads
-// buf0, ping-pongs with buf1, returns the buffer that holds the result (natural order).  The caller
-// has filled buf0 and synchronised; every thread of the CTA must call this.
-__device__ __forceinline__ float2 *stockham_pow2(float2 *buf0, float2 *buf1, const float2 *__restrict__ tw,
-                                                 unsigned int n, unsigned int log2n, unsigned int per_cta, float sgn)
+// the two ping-pong buffers and the twiddle table, carved out of the kernel's dynamic shared memory
+struct Smem {
+    float2 *buf0, *buf1, *tw;
+};
+__host__ __device__ __forceinline__ unsigned int padded_len(unsigned int n, unsigned int per_cta)
 {
-    float2 *in = buf0, *out = buf1;
-    unsigned int Ns = 1;
-    unsigned int stages4 = log2n / 2;
-    for (unsigned int s = 0; s < stages4; s++, Ns <<= 2) {
-        const unsigned int q = n >> 2;                 // butterflies per transform
-        for (unsigned int i = threadIdx.x; i < per_cta * q; i += blockDim.x) {
-            unsigned int f = i / q, j = i % q;
-            const float2 *src = in + (size_t)f * n;
-            float2 *dst = out + (size_t)f * n;
-            unsigned int k = j & (Ns - 1);
-            unsigned int tstep = k * (n / (Ns << 2)); // index of W_n^(k n/(4Ns)) = W_{4Ns}^k
-            float2 v0 = src[j];
-            float2 v1 = lcd::cmul(src[j + q], tw[tstep]);
-            float2 v2 = lcd::cmul(src[j + 2 * q], tw[2 * tstep]);
-            float2 v3 = lcd::cmul(src[j + 3 * q], tw[3 * tstep]);
-            float2 a02 = lcd::cadd(v0, v2), s02 = lcd::csub(v0, v2);
-            float2 a13 = lcd::cadd(v1, v3), s13 = mul_sj(lcd::csub(v1, v3), sgn);
-            unsigned int d = ((j - k) << 2) + k;
-            dst[d]          = lcd::cadd(a02, a13);
-            dst[d + Ns]     = lcd::cadd(s02, s13);
-            dst[d + 2 * Ns] = lcd::csub(a02, a13);
-            dst[d + 3 * Ns] = lcd::csub(s02, s13);
+    return (pidx(per_cta * n - 1) + 2) & ~1u;               // even: keeps the next region 16-byte aligned
+}
+__device__ __forceinline__ Smem carve(float2 *base, unsigned int n, unsigned int per_cta)
+{
+    const unsigned int p = padded_len(n, per_cta);
+    return Smem{base, base + p, base + 2 * p};
+}
+// cooperative copy of the plan's table tw[i] = e^{sign j 2 pi i / n}; a barrier must follow before the FFT
+// (the callers' own barrier after filling buf0 serves)
+__device__ __forceinline__ void stage_twiddles(const Smem &s, const float2 *__restrict__ tw, unsigned int n)
+{
+    for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) s.tw[i] = __ldg(tw + i);
+}
+
+template <int R, int SIGN>
+__device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, float2 *__restrict__ dst,
+                                              const float2 *__restrict__ tw, unsigned int n, unsigned int log2n,
+                                              unsigned int Ns, unsigned int per_cta)
+{
+    constexpr unsigned int kLog2R = (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1;
+    const unsigned int log2q = log2n - kLog2R;
+    const unsigned int q = 1u << log2q;                        // butterflies per transform
+    const unsigned int tstride = (n >> kLog2R) / Ns;           // table step of W_{R Ns}
+    for (unsigned int i = threadIdx.x; i < (per_cta << log2q); i += blockDim.x) {
+        const unsigned int f = i >> log2q, j = i & (q - 1);
+        const unsigned int k = j & (Ns - 1);
+        const unsigned int base = f << log2n;
+        float2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; m++) v[m] = src[pidx(base + j + m * q)];
+        if (Ns > 1) {
+#pragma unroll
+            for (int m = 1; m < R; m++) v[m] = lcf::cmul2(v[m], tw[k * m * tstride]);
         }
-        __syncthreads();
+        lcf::RegDft<R, SIGN>::run(v);
+        const unsigned int d = base + (j - k) * R + k;
+#pragma unroll
+        for (int m = 0; m < R; m++) dst[pidx(d + m * Ns)] = v[m];
+    }
+    __syncthreads();
+}
+
+template <int SIGN>
+__device__ __forceinline__ float2 *stockham_all(const Smem &s, unsigned int n, unsigned int log2n, unsigned int per_cta)
+{
+    float2 *in = s.buf0, *out = s.buf1;
+    unsigned int Ns = 1, left = log2n;
+    while (left >= 4) {
+        stockham_pass<16, SIGN>(in, out, s.tw, n, log2n, Ns, per_cta);
+        Ns <<= 4;
+        left -= 4;
         float2 *t = in; in = out; out = t;
     }
-    if (log2n & 1) {
-        const unsigned int q = n >> 1;
-        for (unsigned int i = threadIdx.x; i < per_cta * q; i += blockDim.x) {
-            unsigned int f = i / q, j = i % q;
-            const float2 *src = in + (size_t)f * n;
-            float2 *dst = out + (size_t)f * n;
-            unsigned int k = j & (Ns - 1);
-            float2 v0 = src[j];
-            float2 v1 = lcd::cmul(src[j + q], tw[k * (n / (Ns << 1))]);
-            unsigned int d = ((j - k) << 1) + k;
-            dst[d]      = lcd::cadd(v0, v1);
-            dst[d + Ns] = lcd::csub(v0, v1);
-        }
-        __syncthreads();
-        float2 *t = in; in = out; out = t;
-    }
+    if (left == 3)      stockham_pass<8, SIGN>(in, out, s.tw, n, log2n, Ns, per_cta);
+    else if (left == 2) stockham_pass<4, SIGN>(in, out, s.tw, n, log2n, Ns, per_cta);
+    else if (left == 1) stockham_pass<2, SIGN>(in, out, s.tw, n, log2n, Ns, per_cta);
+    if (left) { float2 *t = in; in = out; out = t; }
     return in;
 }
 
-// transforms per CTA for n-point transforms (aim at 2048 points per CTA) and the shared memory they need
-inline unsigned int per_cta_for(unsigned int n, unsigned long long batch)
+// FFT of the per_cta transforms in s.buf0 (logical element i at s.buf0[pidx(i)]); the twiddle table must have
+// been staged and the CTA synchronised.  Returns the buffer that holds the result, natural order, same layout.
+// sgn: +1 backward (e^{+j}), -1 forward; it must match the staged table.
+__device__ __forceinline__ float2 *stockham_pow2(const Smem &s, unsigned int n, unsigned int log2n,
+                                                 unsigned int per_cta, float sgn)
+{
+    return sgn > 0.0f ? stockham_all<+1>(s, n, log2n, per_cta) : stockham_all<-1>(s, n, log2n, per_cta);
+}
+
+// transforms per CTA for n-point transforms and the shared memory they need.  2048 points per CTA keeps four
+// CTAs per SM (what the analyzers, whose fill phase is load-latency bound, want); 4096 gives every one of the 256
+// threads a butterfly in a radix-16 pass (what the periodogram's long FFT-only loop wants)
+inline unsigned int per_cta_for(unsigned int n, unsigned long long batch, unsigned int target_points = 2048)
 {
     unsigned int per_cta = 1;
-    while (per_cta * n < 2048 && per_cta < batch) per_cta <<= 1;
+    while (per_cta * n < target_points && per_cta < batch) per_cta <<= 1;
     return per_cta;
 }
-inline size_t smem_for(unsigned int n, unsigned int per_cta) { return (size_t)2 * per_cta * n * sizeof(float2); }
+inline size_t smem_for(unsigned int n, unsigned int per_cta)
+{
+    return ((size_t)2 * padded_len(n, per_cta) + n) * sizeof(float2);
+}
 inline bool pow2_in_smem(unsigned int n) { return lc::is_pow2(n) && n >= 2 && (size_t)n * 16 <= 200 * 1024; }
 
 }  // namespace lcfft

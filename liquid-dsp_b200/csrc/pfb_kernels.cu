@@ -68,7 +68,8 @@ pfbch2_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__rest
                            unsigned long long n_frames, int parity0, long long t_first)
 {
     extern __shared__ float2 smem_f2[];
-    float2 *buf0 = smem_f2, *buf1 = smem_f2 + (size_t)per_cta * M;
+    const lcfft::Smem sm = lcfft::carve(smem_f2, M, per_cta);
+    lcfft::stage_twiddles(sm, tw, M);
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
     const unsigned int total = per_cta * M;
     {
@@ -107,15 +108,15 @@ pfbch2_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__rest
                         }
                     }
                 }
-                buf0[fi * M + w] = make_float2(re, im);
+                sm.buf0[lcfft::pidx(fi * M + w)] = make_float2(re, im);
             }
         }
     }
     __syncthreads();
-    const float2 *res = lcfft::stockham_pow2(buf0, buf1, tw, M, log2M, per_cta, +1.0f);
+    const float2 *res = lcfft::stockham_pow2(sm, M, log2M, per_cta, +1.0f);
     for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
         const unsigned long long f = first + i / M;
-        if (f < n_frames) y[f * M + (i % M)] = lcfft::fft_post(res[i], 1, (float)M, 1.0f);
+        if (f < n_frames) y[f * M + (i % M)] = lcfft::fft_post(res[lcfft::pidx(i)], 1, (float)M, 1.0f);
     }
 }
 
@@ -193,7 +194,8 @@ pfbch_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restr
                           unsigned long long n_frames, unsigned int phase, unsigned int first_in, unsigned int k)
 {
     extern __shared__ float2 smem_f2[];
-    float2 *buf0 = smem_f2, *buf1 = smem_f2 + (size_t)per_cta * M;
+    const lcfft::Smem sm = lcfft::carve(smem_f2, M, per_cta);
+    lcfft::stage_twiddles(sm, tw, M);
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
     const unsigned int total = per_cta * M;
     {
@@ -225,15 +227,15 @@ pfbch_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restr
                             tap_mac(__ldg(tp), lcd::ld_stream(hist, x, last - (long long)n * M, H), re, im);
                     }
                 }
-                buf0[fi * M + u] = make_float2(re, im);
+                sm.buf0[lcfft::pidx(fi * M + u)] = make_float2(re, im);
             }
         }
     }
     __syncthreads();
-    const float2 *res = lcfft::stockham_pow2(buf0, buf1, tw, M, log2M, per_cta, -1.0f);
+    const float2 *res = lcfft::stockham_pow2(sm, M, log2M, per_cta, -1.0f);
     for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
         const unsigned long long f = first + i / M;
-        if (f < n_frames) y[f * M + (i % M)] = res[i];
+        if (f < n_frames) y[f * M + (i % M)] = res[lcfft::pidx(i)];
     }
 }
 

@@ -72,7 +72,8 @@ spgram_transform_pow2_kernel(const float2 *__restrict__ hist, const float2 *__re
                              Segs segs, void *__restrict__ out)
 {
     extern __shared__ float2 smem_f2[];
-    float2 *buf0 = smem_f2, *buf1 = smem_f2 + (size_t)per_cta * nfft;
+    const lcfft::Smem sm = lcfft::carve(smem_f2, nfft, per_cta);
+    lcfft::stage_twiddles(sm, tw, nfft);
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
     const unsigned int total = per_cta * nfft;
     for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -84,14 +85,14 @@ spgram_transform_pow2_kernel(const float2 *__restrict__ hist, const float2 *__re
             const float c = __ldg(w + k);
             v = make_float2(s.x * c, s.y * c);                       // rc[i] * w[i]   (spgram.c:236-237)
         }
-        buf0[i] = v;
+        sm.buf0[lcfft::pidx(i)] = v;
     }
     __syncthreads();
-    const float2 *res = lcfft::stockham_pow2(buf0, buf1, tw, nfft, log2n, per_cta, -1.0f);
+    const float2 *res = lcfft::stockham_pow2(sm, nfft, log2n, per_cta, -1.0f);
     for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
         const unsigned long long t = first + i / nfft;
         if (t >= T) continue;
-        const float2 X = res[i];
+        const float2 X = res[lcfft::pidx(i)];
         if (MODE == 0) reinterpret_cast<float *>(out)[t * nfft + (i % nfft)] = X.x * X.x + X.y * X.y;
         else           reinterpret_cast<float2 *>(out)[t * nfft + (i % nfft)] = X;
     }
@@ -110,7 +111,8 @@ spgram_accumulate_pow2_kernel(const float2 *__restrict__ hist, const float2 *__r
                               float alpha, int seed_psd)
 {
     extern __shared__ float2 smem_f2[];
-    float2 *buf0 = smem_f2, *buf1 = smem_f2 + (size_t)per_cta * nfft;
+    const lcfft::Smem sm = lcfft::carve(smem_f2, nfft, per_cta);
+    lcfft::stage_twiddles(sm, tw, nfft);
     const unsigned long long t_begin = (unsigned long long)blockIdx.x * tpc;
     unsigned long long t_end = t_begin + tpc;
     if (t_end > T) t_end = T;
@@ -133,16 +135,16 @@ spgram_accumulate_pow2_kernel(const float2 *__restrict__ hist, const float2 *__r
                 const float c = __ldg(w + k);
                 v = make_float2(sv.x * c, sv.y * c);
             }
-            buf0[i] = v;
+            sm.buf0[lcfft::pidx(i)] = v;
         }
         __syncthreads();
-        const float2 *res = lcfft::stockham_pow2(buf0, buf1, tw, nfft, log2n, per_cta, -1.0f);
+        const float2 *res = lcfft::stockham_pow2(sm, nfft, log2n, per_cta, -1.0f);
         for (unsigned int tt = 0; tt < per_cta && g0 + tt < t_end; tt++) {
 #pragma unroll
             for (int b = 0; b < kMaxBins; b++) {
                 const unsigned int k = threadIdx.x + b * lcfft::kFftThreads;
                 if (k < nfft) {
-                    const float2 X = res[tt * nfft + k];
+                    const float2 X = res[lcfft::pidx(tt * nfft + k)];
                     const float P = X.x * X.x + X.y * X.y;
                     acc[b] = (alpha < 0.0f) ? acc[b] + P : keep * acc[b] + alpha * P;
                 }
@@ -303,7 +305,7 @@ void accumulate_transforms(spgramcf q, const float2 *d_x, unsigned long long T, 
         unsigned long long tpc = kFoldChunk;
         if (T > tpc * 148 * 8) tpc = (T + 148 * 8 - 1) / (148 * 8);
         if ((T + tpc - 1) / tpc > 2048) tpc = (T + 2047) / 2048;
-        const unsigned int per_cta = lcfft::per_cta_for(nfft, tpc);
+        const unsigned int per_cta = lcfft::per_cta_for(nfft, tpc, 4096);
         tpc = (tpc + per_cta - 1) / per_cta * per_cta;
         const unsigned int n_chunks = (unsigned int)((T + tpc - 1) / tpc);
         float *d_part = (float *)q->partials.get(sizeof(float) * (size_t)n_chunks * nfft);
