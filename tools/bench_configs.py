@@ -3,7 +3,7 @@
 measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
 events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
 
-  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
+  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
 """
 import argparse
 import json
@@ -145,6 +145,19 @@ def main():
         ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
         report("f1b: firpfbch_cccf analysis M=256 p=10, complex taps (shape-generic MAC + FFT kernels), 2^27 samples", n, 16, ms, ln)
         del x, y
+    if "fft" in args.configs:
+        # a11: the batched complex FFT on its own (fft_execute_batch_dev), 2^28 points per step, out of place
+        import numpy as np
+        for nn in (16, 256, 1024, 4096):
+            n = 1 << 28
+            x = torch.empty(2 * n, dtype=torch.float32, device=dev)
+            y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+            L.synth_input_dev(x.data_ptr(), n, stream=st.cuda_stream)
+            hx, hy = np.zeros(nn, np.complex64), np.zeros(nn, np.complex64)
+            p = L.fftplan(nn, hx, hy, L.LIQUID_FFT_FORWARD)
+            ms, ln = timed(lambda: p.execute_batch_dev(x.data_ptr(), y.data_ptr(), n // nn, st.cuda_stream))
+            report("fft: fft_execute_batch_dev n=%d, 2^28 points" % nn, n, 16, ms, ln)
+            del x, y
     if "f2" in args.configs:
         # spgramcf_accumulate_psd on a device-resident block: default object (Kaiser window
         # nfft/2, a transform every nfft/4 samples ... window_len/2), 2^28 samples
