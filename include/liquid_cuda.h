@@ -75,6 +75,27 @@ void  liquid_firdes_arkaiser(unsigned int _k, unsigned int _m, float _beta, floa
 void  liquid_firdes_rkaiser(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
 void  liquid_firdes_prototype(int _type, unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
 
+/* ---- firdecim_crcf / firinterp_crcf: liquid.h:2665-2722, :2498-2556 -> src/filter/src/firdecim.c:46-223,
+ *      firinterp.c:43-217 (instantiated by filter_crcf.c).  SURVEY.md 8(f) item 3. */
+typedef struct firdecim_crcf_s * firdecim_crcf;
+firdecim_crcf firdecim_crcf_create(unsigned int _M, float *_h, unsigned int _h_len);
+firdecim_crcf firdecim_crcf_create_kaiser(unsigned int _M, unsigned int _m, float _As);
+firdecim_crcf firdecim_crcf_create_prototype(int _type, unsigned int _M, unsigned int _m, float _beta, float _dt);
+void firdecim_crcf_destroy(firdecim_crcf _q);
+void firdecim_crcf_print(firdecim_crcf _q);
+void firdecim_crcf_clear(firdecim_crcf _q);
+void firdecim_crcf_execute(firdecim_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+void firdecim_crcf_execute_block(firdecim_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+typedef struct firinterp_crcf_s * firinterp_crcf;
+firinterp_crcf firinterp_crcf_create(unsigned int _M, float *_h, unsigned int _h_len);
+firinterp_crcf firinterp_crcf_create_kaiser(unsigned int _M, unsigned int _m, float _As);
+firinterp_crcf firinterp_crcf_create_prototype(int _type, unsigned int _k, unsigned int _m, float _beta, float _dt);
+void firinterp_crcf_destroy(firinterp_crcf _q);
+void firinterp_crcf_print(firinterp_crcf _q);
+void firinterp_crcf_reset(firinterp_crcf _q);
+void firinterp_crcf_execute(firinterp_crcf _q, liquid_float_complex _x, liquid_float_complex *_y);
+void firinterp_crcf_execute_block(firinterp_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+
 /* ---- spgramcf (windowed-FFT spectral periodogram): liquid.h:1230-1316 -> src/fft/src/spgramcf.c -> spgram.c:57-398.
  *      SURVEY.md 8(f) item 2. */
 typedef struct spgramcf_s * spgramcf;
@@ -248,6 +269,10 @@ void firpfbch_crcf_execute_streams_dev(firpfbch_crcf _q, const void *_d_x, unsig
 unsigned int firpfbch_crcf_get_state_len(firpfbch_crcf _q);
 void firpfbch_crcf_get_state(firpfbch_crcf _q, liquid_float_complex *_hist);
 void firpfbch_crcf_set_state(firpfbch_crcf _q, const liquid_float_complex *_hist);
+
+/* ---- firdecim_crcf / firinterp_crcf: device-pointer forms (_n = outputs for firdecim, inputs for firinterp) ---- */
+void firdecim_crcf_execute_block_dev(firdecim_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
+void firinterp_crcf_execute_block_dev(firinterp_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
 
 /* ---- spgramcf: device-pointer forms (the whole block becomes one batch of overlapping transforms) ---- */
 void spgramcf_accumulate_psd_dev(spgramcf _q, const void *_d_x, float _alpha, unsigned long long _n, void *_stream);

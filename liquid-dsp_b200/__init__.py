@@ -89,6 +89,24 @@ _sig("firpfbch_crcf_execute_streams_dev", None, _vp, _vp, _u, _ull, _vp, _vp)
 _sig("firpfbch_crcf_get_state_len", _u, _vp)
 _sig("firpfbch_crcf_get_state", None, _vp, _cf_p)
 _sig("firpfbch_crcf_set_state", None, _vp, _cf_p)
+_sig("firdecim_crcf_create", _vp, _u, _f_p, _u)
+_sig("firdecim_crcf_create_kaiser", _vp, _u, _u, _fl)
+_sig("firdecim_crcf_create_prototype", _vp, _i, _u, _u, _fl, _fl)
+_sig("firdecim_crcf_destroy", None, _vp)
+_sig("firdecim_crcf_print", None, _vp)
+_sig("firdecim_crcf_clear", None, _vp)
+_sig("firdecim_crcf_execute", None, _vp, _cf_p, _cf_p)
+_sig("firdecim_crcf_execute_block", None, _vp, _vp, _u, _vp)
+_sig("firdecim_crcf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
+_sig("firinterp_crcf_create", _vp, _u, _f_p, _u)
+_sig("firinterp_crcf_create_kaiser", _vp, _u, _u, _fl)
+_sig("firinterp_crcf_create_prototype", _vp, _i, _u, _u, _fl, _fl)
+_sig("firinterp_crcf_destroy", None, _vp)
+_sig("firinterp_crcf_print", None, _vp)
+_sig("firinterp_crcf_reset", None, _vp)
+_sig("firinterp_crcf_execute", None, _vp, _cf, _cf_p)
+_sig("firinterp_crcf_execute_block", None, _vp, _vp, _u, _vp)
+_sig("firinterp_crcf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
 _sig("spgramcf_create", _vp, _u, _f_p, _u)
 _sig("spgramcf_create_kaiser", _vp, _u, _u, _fl)
 _sig("spgramcf_create_default", _vp, _u)
@@ -433,6 +451,98 @@ class firpfbch_crcf(_Handle):
     def set_state(self, hist):
         lib.firpfbch_crcf_set_state(self._h, _c64(hist))
 
+
+
+class firdecim_crcf(_Handle):
+    """liquid.h:2665-2722 (src/filter/src/firdecim.c): n outputs from n*M inputs."""
+    _destroy = "firdecim_crcf_destroy"
+
+    def __init__(self, M, h):
+        self.M = M
+        hh = _f32(h)
+        super().__init__(lib.firdecim_crcf_create(M, hh, len(hh)))
+
+    @classmethod
+    def create(cls, M, h):
+        return cls(M, h)
+
+    @classmethod
+    def create_kaiser(cls, M, m, As):
+        q = cls.__new__(cls)
+        q.M = M
+        _Handle.__init__(q, lib.firdecim_crcf_create_kaiser(M, m, As))
+        return q
+
+    @classmethod
+    def create_prototype(cls, ftype, M, m, beta, dt=0.0):
+        q = cls.__new__(cls)
+        q.M = M
+        _Handle.__init__(q, lib.firdecim_crcf_create_prototype(ftype, M, m, beta, dt))
+        return q
+
+    def clear(self):
+        lib.firdecim_crcf_clear(self._h)
+
+    def execute(self, x):
+        y = np.empty(1, np.complex64)
+        lib.firdecim_crcf_execute(self._h, _c64(x), y)
+        return y[0]
+
+    def execute_block(self, x):
+        x = _c64(x)
+        n = x.size // self.M
+        y = np.empty(n, np.complex64)
+        lib.firdecim_crcf_execute_block(self._h, _ptr(x), n, _ptr(y))
+        return y
+
+    def execute_block_dev(self, d_x, n, d_y, stream=0):
+        lib.firdecim_crcf_execute_block_dev(self._h, d_x, n, d_y, stream)
+
+
+class firinterp_crcf(_Handle):
+    """liquid.h:2498-2556 (src/filter/src/firinterp.c): n*M outputs from n inputs."""
+    _destroy = "firinterp_crcf_destroy"
+
+    def __init__(self, M, h):
+        self.M = M
+        hh = _f32(h)
+        super().__init__(lib.firinterp_crcf_create(M, hh, len(hh)))
+
+    @classmethod
+    def create(cls, M, h):
+        return cls(M, h)
+
+    @classmethod
+    def create_kaiser(cls, M, m, As):
+        q = cls.__new__(cls)
+        q.M = M
+        _Handle.__init__(q, lib.firinterp_crcf_create_kaiser(M, m, As))
+        return q
+
+    @classmethod
+    def create_prototype(cls, ftype, M, m, beta, dt=0.0):
+        q = cls.__new__(cls)
+        q.M = M
+        _Handle.__init__(q, lib.firinterp_crcf_create_prototype(ftype, M, m, beta, dt))
+        return q
+
+    def reset(self):
+        lib.firinterp_crcf_reset(self._h)
+
+    def execute(self, v):
+        v = complex(v)
+        y = np.empty(self.M, np.complex64)
+        lib.firinterp_crcf_execute(self._h, _cf(v.real, v.imag), y)
+        return y
+
+    def execute_block(self, x):
+        x = _c64(x)
+        y = np.empty(x.size * self.M, np.complex64)
+        lib.firinterp_crcf_execute_block(self._h, _ptr(x), x.size, _ptr(y))
+        return y
+
+    def execute_block_dev(self, d_x, n, d_y, stream=0):
+        lib.firinterp_crcf_execute_block_dev(self._h, d_x, n, d_y, stream)
 
 
 class spgramcf(_Handle):

@@ -1,0 +1,318 @@
+// firmultirate.cu -- firdecim_crcf and firinterp_crcf: the polyphase FIR pattern without a transform
+// (the natural pre-decimation / post-interpolation stages around a channelizer).  SURVEY.md 8(f) item 3.
+//
+// Replaces src/filter/src/firdecim.c (create :46-82, create_kaiser :88-118, create_prototype :126-163,
+// clear :179-182, execute :189-206, execute_block :213-223) and src/filter/src/firinterp.c (create :43-80,
+// create_kaiser :86-116, create_prototype :124-158, reset :178-181, execute :187-199, execute_block :205-217),
+// both instantiated for crcf by src/filter/src/filter_crcf.c.
+//
+//   firdecim   y[i] = sum_k h[k] x[i M - k]: the reference pushes M samples per output and takes the dot
+//              product right after the FIRST push.  Kernel: a CTA stages tile*M + h_len - 1 input samples in
+//              shared memory with coalesced loads (every input sample is read from HBM once), the taps sit in
+//              shared memory too (broadcast reads), each thread produces one output; the staged samples are
+//              padded by one element per 16 so that the stride-M reads do not pile onto a few banks.
+//   firinterp  y[i M + j] = sum_n h[j + n M] x[i - n] (a firpfb: one push, then the M branch outputs).  Kernel:
+//              one thread per output; the M outputs of one input share their samples (broadcast within the
+//              warp), taps are read coalesced.  The path is bound by its 8 M bytes of output per input sample.
+// State, as in the reference: the last h_len (firdecim) / ceil(h_len / M) (firinterp) input samples.
+#include <cmath>
+#include <cstdint>
+
+#include "lc_common.cuh"
+#include "../../include/liquid_cuda.h"
+#include "host_pipeline.cuh"
+
+struct firdecim_crcf_s {
+    unsigned int M, h_len;
+    std::vector<float> h;
+    float *d_h = nullptr;
+    float2 *d_hist = nullptr;        // last h_len samples, oldest first
+    lc::DevBuf stage_in, stage_out, hist_tmp;
+    cudaStream_t stream = nullptr;
+};
+
+struct firinterp_crcf_s {
+    unsigned int M, h_len, sub_len;  // h_len = M * sub_len (zero-padded prototype)
+    std::vector<float> h;
+    float *d_h = nullptr;
+    float2 *d_hist = nullptr;        // last sub_len samples, oldest first
+    lc::DevBuf stage_in, stage_out, hist_tmp;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ unsigned int pad16(unsigned int i) { return i + (i >> 4); }
+
+// outputs [blockIdx.x * tile, ...): smem = taps[h_len] floats, then the staged samples
+__global__ void __launch_bounds__(kThreads)
+firdecim_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ h,
+                unsigned int h_len, unsigned int M, unsigned int tile, float2 *__restrict__ y, unsigned long long n_out)
+{
+    extern __shared__ float smem_f[];
+    float *h_s = smem_f;
+    float2 *xs = reinterpret_cast<float2 *>(smem_f + ((h_len + 1) & ~1u));
+    const unsigned long long o0 = (unsigned long long)blockIdx.x * tile;
+    unsigned int nt = tile;
+    if (o0 + nt > n_out) nt = (unsigned int)(n_out - o0);
+    for (unsigned int k = threadIdx.x; k < h_len; k += blockDim.x) h_s[k] = __ldg(h + k);
+    // staged sample q is stream sample o0*M - (h_len-1) + q, q < (nt-1)*M + h_len
+    const long long first = (long long)(o0 * M) - (long long)(h_len - 1);
+    const unsigned int n_samp = (nt - 1) * M + h_len;
+    for (unsigned int q = threadIdx.x; q < n_samp; q += blockDim.x) xs[pad16(q)] = lcd::ld_stream(hist, x, first + q, H);
+    __syncthreads();
+    for (unsigned int t = threadIdx.x; t < nt; t += blockDim.x) {
+        // oldest sample first, as the reference's dot product over its window (firdecim.c:64-67, :200-203)
+        float re = 0.f, im = 0.f;
+        const unsigned int base = t * M;
+        for (unsigned int i = 0; i < h_len; i++) {
+            const float2 s = xs[pad16(base + i)];
+            const float c = h_s[h_len - 1 - i];
+            re = fmaf(c, s.x, re);
+            im = fmaf(c, s.y, im);
+        }
+        y[o0 + t] = make_float2(re, im);
+    }
+}
+
+// output o = i M + j:  sum_n h[j + n M] x[i - n], oldest sample first (firpfb.c:71-84 stores branches reversed)
+__global__ void __launch_bounds__(kThreads)
+firinterp_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ h,
+                 unsigned int sub_len, unsigned int M, float2 *__restrict__ y, unsigned long long n_out)
+{
+    for (unsigned long long o = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; o < n_out;
+         o += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long i = (long long)(o / M);
+        const unsigned int j = (unsigned int)(o % M);
+        float re = 0.f, im = 0.f;
+        for (unsigned int k = 0; k < sub_len; k++) {
+            const unsigned int n = sub_len - 1 - k;                   // tap index: n-th newest sample
+            const float2 s = lcd::ld_stream(hist, x, i - (long long)n, H);
+            const float c = __ldg(h + j + (size_t)n * M);
+            re = fmaf(c, s.x, re);
+            im = fmaf(c, s.y, im);
+        }
+        y[o] = make_float2(re, im);
+    }
+}
+
+inline unsigned int grid_for(unsigned long long total)
+{
+    unsigned long long b = (total + kThreads - 1) / kThreads;
+    const unsigned long long cap = 148ull * 8 * 16;
+    return (unsigned int)(b < cap ? (b ? b : 1) : cap);
+}
+
+void decim_dev(firdecim_crcf q, const float2 *d_x, unsigned long long n_out, float2 *d_y, cudaStream_t st)
+{
+    if (n_out == 0) return;
+    // outputs per CTA: as many as fit ~96 KB of staged samples, at most 256
+    const size_t budget = 96 * 1024;
+    const size_t taps_bytes = sizeof(float) * ((q->h_len + 1) & ~1u);
+    unsigned int tile = kThreads;
+    auto bytes_for = [&](unsigned int t) {
+        const size_t n_samp = (size_t)(t - 1) * q->M + q->h_len;
+        return taps_bytes + sizeof(float2) * (n_samp + n_samp / 16 + 2);
+    };
+    while (tile > 1 && bytes_for(tile) > budget) tile >>= 1;
+    const size_t smem = bytes_for(tile);
+    if (smem > 200 * 1024) lc::fatal("firdecim_crcf_execute_block", "filter too long for this build");
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        LC_CUDA_CHECK(cudaFuncSetAttribute(firdecim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        smem_set = 200 * 1024;
+    }
+    const unsigned long long ctas = (n_out + tile - 1) / tile;
+    if (ctas >= (1ull << 31)) lc::fatal("firdecim_crcf_execute_block", "too many outputs for one launch");
+    firdecim_kernel<<<(unsigned int)ctas, kThreads, smem, st>>>(q->d_hist, d_x, (int)q->h_len, q->d_h, q->h_len, q->M, tile, d_y, n_out);
+    LC_LAUNCH_CHECK();
+    lc::roll_history(q->d_hist, q->h_len, q->hist_tmp, d_x, n_out * q->M, st);
+}
+
+void interp_dev(firinterp_crcf q, const float2 *d_x, unsigned long long n_in, float2 *d_y, cudaStream_t st)
+{
+    if (n_in == 0) return;
+    firinterp_kernel<<<grid_for(n_in * q->M), kThreads, 0, st>>>(q->d_hist, d_x, (int)q->sub_len, q->d_h, q->sub_len, q->M, d_y, n_in * q->M);
+    LC_LAUNCH_CHECK();
+    lc::roll_history(q->d_hist, q->sub_len, q->hist_tmp, d_x, n_in, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------ firdecim_crcf
+firdecim_crcf firdecim_crcf_create(unsigned int _M, float *_h, unsigned int _h_len)
+{
+    if (_h_len == 0) lc::fatal("decim_crcf_create", "filter length must be greater than zero");
+    if (_M == 0) lc::fatal("decim_crcf_create", "decimation factor must be greater than zero");
+    lc::ensure_device();
+    firdecim_crcf q = new firdecim_crcf_s();
+    q->M = _M;
+    q->h_len = _h_len;
+    q->h.assign(_h, _h + _h_len);
+    LC_CUDA_CHECK(cudaMalloc(&q->d_h, sizeof(float) * _h_len));
+    LC_CUDA_CHECK(cudaMemcpy(q->d_h, q->h.data(), sizeof(float) * _h_len, cudaMemcpyHostToDevice));
+    LC_CUDA_CHECK(cudaMalloc(&q->d_hist, sizeof(float2) * _h_len));
+    LC_CUDA_CHECK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+    firdecim_crcf_clear(q);
+    return q;
+}
+
+firdecim_crcf firdecim_crcf_create_kaiser(unsigned int _M, unsigned int _m, float _As)
+{
+    if (_M < 2) lc::fatal("decim_crcf_create_kaiser", "decim factor must be greater than 1");
+    if (_m == 0) lc::fatal("decim_crcf_create_kaiser", "filter delay must be greater than 0");
+    if (_As < 0.0f) lc::fatal("decim_crcf_create_kaiser", "stop-band attenuation must be positive");
+    // 2Mm+1 Kaiser taps at fc = 0.5/M; the first 2Mm are used                      firdecim.c:106-117
+    const unsigned int h_len = 2 * _M * _m + 1;
+    std::vector<float> hf(h_len);
+    liquid_firdes_kaiser(h_len, 0.5f / (float)_M, _As, 0.0f, hf.data());
+    return firdecim_crcf_create(_M, hf.data(), 2 * _M * _m);
+}
+
+firdecim_crcf firdecim_crcf_create_prototype(int _type, unsigned int _M, unsigned int _m, float _beta, float _dt)
+{
+    if (_M < 2) lc::fatal("decim_crcf_create_prototype", "decimation factor must be greater than 1");
+    if (_m == 0) lc::fatal("decim_crcf_create_prototype", "filter delay must be greater than 0");
+    if (_beta < 0.0f || _beta > 1.0f) lc::fatal("decim_crcf_create_prototype", "filter excess bandwidth factor must be in [0,1]");
+    if (_dt < -1.0f || _dt > 1.0f) lc::fatal("decim_crcf_create_prototype", "filter fractional sample delay must be in [-1,1]");
+    const unsigned int h_len = 2 * _M * _m + 1;                    // all 2Mm+1 taps here (firdecim.c:150-162)
+    std::vector<float> h(h_len);
+    liquid_firdes_prototype(_type, _M, _m, _beta, _dt, h.data());
+    return firdecim_crcf_create(_M, h.data(), h_len);
+}
+
+void firdecim_crcf_destroy(firdecim_crcf _q)
+{
+    if (!_q) return;
+    cudaStreamSynchronize(_q->stream);
+    cudaFree(_q->d_h);
+    cudaFree(_q->d_hist);
+    _q->stage_in.release();
+    _q->stage_out.release();
+    _q->hist_tmp.release();
+    cudaStreamDestroy(_q->stream);
+    delete _q;
+}
+
+void firdecim_crcf_print(firdecim_crcf _q)
+{
+    printf("firdecim_crcf [%u] : %u taps (cuda)\n", _q->M, _q->h_len);
+}
+
+void firdecim_crcf_clear(firdecim_crcf _q)
+{
+    LC_CUDA_CHECK(cudaMemsetAsync(_q->d_hist, 0, sizeof(float2) * _q->h_len, _q->stream));
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+}
+
+// _n outputs from _n * M device-resident inputs; state carried in stream order
+void firdecim_crcf_execute_block_dev(firdecim_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream)
+{
+    decim_dev(_q, (const float2 *)_d_x, _n, (float2 *)_d_y, lc::as_stream(_stream));
+}
+
+void firdecim_crcf_execute_block(firdecim_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y)
+{
+    lc::host_block(_q->stream, _q->stage_in, _q->stage_out, reinterpret_cast<const lc_cf *>(_x),
+                   reinterpret_cast<lc_cf *>(_y), _n, _q->M, 1,
+                   [&](float2 *di, size_t nu, float2 *dob, cudaStream_t st) { decim_dev(_q, di, nu, dob, st); });
+}
+
+void firdecim_crcf_execute(firdecim_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y)
+{
+    firdecim_crcf_execute_block(_q, _x, 1, _y);
+}
+
+// ------------------------------------------------------------------------------------------ firinterp_crcf
+firinterp_crcf firinterp_crcf_create(unsigned int _M, float *_h, unsigned int _h_len)
+{
+    if (_M < 2) lc::fatal("firinterp_crcf_create", "interp factor must be greater than 1");
+    if (_h_len < _M) lc::fatal("firinterp_crcf_create", "filter length cannot be less than interp factor");
+    lc::ensure_device();
+    firinterp_crcf q = new firinterp_crcf_s();
+    q->M = _M;
+    q->sub_len = 0;
+    while (q->M * q->sub_len < _h_len) q->sub_len++;
+    q->h_len = q->M * q->sub_len;                                  // prototype padded with zeros (firinterp.c:63-72)
+    q->h.assign(q->h_len, 0.0f);
+    for (unsigned int i = 0; i < _h_len; i++) q->h[i] = _h[i];
+    LC_CUDA_CHECK(cudaMalloc(&q->d_h, sizeof(float) * q->h_len));
+    LC_CUDA_CHECK(cudaMemcpy(q->d_h, q->h.data(), sizeof(float) * q->h_len, cudaMemcpyHostToDevice));
+    LC_CUDA_CHECK(cudaMalloc(&q->d_hist, sizeof(float2) * q->sub_len));
+    LC_CUDA_CHECK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+    firinterp_crcf_reset(q);
+    return q;
+}
+
+firinterp_crcf firinterp_crcf_create_kaiser(unsigned int _M, unsigned int _m, float _As)
+{
+    if (_M < 2) lc::fatal("firinterp_crcf_create_kaiser", "interp factor must be greater than 1");
+    if (_m == 0) lc::fatal("firinterp_crcf_create_kaiser", "filter delay must be greater than 0");
+    if (_As < 0.0f) lc::fatal("firinterp_crcf_create_kaiser", "stop-band attenuation must be positive");
+    const unsigned int h_len = 2 * _M * _m + 1;
+    std::vector<float> hf(h_len);
+    liquid_firdes_kaiser(h_len, 0.5f / (float)_M, _As, 0.0f, hf.data());
+    return firinterp_crcf_create(_M, hf.data(), 2 * _M * _m);       // firinterp.c:115
+}
+
+firinterp_crcf firinterp_crcf_create_prototype(int _type, unsigned int _k, unsigned int _m, float _beta, float _dt)
+{
+    if (_k < 2) lc::fatal("firinterp_crcf_create_prototype", "interp factor must be greater than 1");
+    if (_m == 0) lc::fatal("firinterp_crcf_create_prototype", "filter delay must be greater than 0");
+    if (_beta < 0.0f || _beta > 1.0f) lc::fatal("firinterp_crcf_create_prototype", "filter excess bandwidth factor must be in [0,1]");
+    if (_dt < -1.0f || _dt > 1.0f) lc::fatal("firinterp_crcf_create_prototype", "filter fractional sample delay must be in [-1,1]");
+    const unsigned int h_len = 2 * _k * _m + 1;
+    std::vector<float> h(h_len);
+    liquid_firdes_prototype(_type, _k, _m, _beta, _dt, h.data());
+    return firinterp_crcf_create(_k, h.data(), h_len);
+}
+
+void firinterp_crcf_destroy(firinterp_crcf _q)
+{
+    if (!_q) return;
+    cudaStreamSynchronize(_q->stream);
+    cudaFree(_q->d_h);
+    cudaFree(_q->d_hist);
+    _q->stage_in.release();
+    _q->stage_out.release();
+    _q->hist_tmp.release();
+    cudaStreamDestroy(_q->stream);
+    delete _q;
+}
+
+void firinterp_crcf_print(firinterp_crcf _q)
+{
+    printf("interp():\n");
+    printf("    interp  :   %u\n", _q->M);
+    printf("    h_len   :   %u\n", _q->h_len);
+}
+
+void firinterp_crcf_reset(firinterp_crcf _q)
+{
+    LC_CUDA_CHECK(cudaMemsetAsync(_q->d_hist, 0, sizeof(float2) * _q->sub_len, _q->stream));
+    LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+}
+
+// _n * M outputs from _n device-resident inputs; state carried in stream order
+void firinterp_crcf_execute_block_dev(firinterp_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream)
+{
+    interp_dev(_q, (const float2 *)_d_x, _n, (float2 *)_d_y, lc::as_stream(_stream));
+}
+
+void firinterp_crcf_execute_block(firinterp_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y)
+{
+    lc::host_block(_q->stream, _q->stage_in, _q->stage_out, reinterpret_cast<const lc_cf *>(_x),
+                   reinterpret_cast<lc_cf *>(_y), _n, 1, _q->M,
+                   [&](float2 *di, size_t nu, float2 *dob, cudaStream_t st) { interp_dev(_q, di, nu, dob, st); });
+}
+
+void firinterp_crcf_execute(firinterp_crcf _q, liquid_float_complex _x, liquid_float_complex *_y)
+{
+    firinterp_crcf_execute_block(_q, &_x, 1, _y);
+}
+
+}  // extern "C"

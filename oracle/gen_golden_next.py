@@ -13,6 +13,7 @@ the record of how the fixture was made.
              5th digit, which moves every tap by ~1e-5: fine for a filter, useless as a pin)
   scalars    estimate_req_filter_As, rkaiser_approximate_rho, liquid_filter_isi points
   cccf_*     firpfbch_cccf_create with seeded complex taps: analysis and synthesis outputs
+  mr_*       firdecim_crcf / firinterp_crcf (8f item 3): Kaiser objects and seeded random taps
   spgram_*   spgramcf (8f item 2): execute / execute_psd after a write, accumulate_psd in two calls
              (alpha 0.3: the first call runs with alpha = 1 by the reference's quirk) + write_accumulation,
              and estimate_psd, on a tone-plus-noise input
@@ -82,6 +83,19 @@ for M, p in [(8, 6), (16, 8), (12, 5), (64, 4)]:
     out["cccf_M%d_p%d_x" % (M, p)] = x
     out["cccf_M%d_p%d_a_y" % (M, p)] = O.ref_firpfbch_cccf_frames(O.ANALYZER, M, p, h, x)
     out["cccf_M%d_p%d_s_y" % (M, p)] = O.ref_firpfbch_cccf_frames(O.SYNTHESIZER, M, p, h, x)
+
+# firdecim_crcf / firinterp_crcf (8f item 3)
+rng3 = np.random.default_rng(20261019)
+for M, m in [(2, 4), (4, 5), (8, 3), (5, 2), (16, 6)]:
+    x = O.synth_input(M * 300, seed=0x5EEDA000 + M)
+    h = rng3.standard_normal(2 * M * m + 3).astype(np.float32)
+    tag = "mr_M%d_m%d" % (M, m)
+    out[tag + "_x"] = x
+    out[tag + "_h"] = h
+    out[tag + "_decim_kaiser"] = O.ref_firdecim_block(M, x, kaiser=(m, 60.0))
+    out[tag + "_decim_h"] = O.ref_firdecim_block(M, x, h=h)
+    out[tag + "_interp_kaiser"] = O.ref_firinterp_block(M, x[:300], kaiser=(m, 60.0))
+    out[tag + "_interp_h"] = O.ref_firinterp_block(M, x[:300], h=h)
 
 # spgramcf
 for nfft, wl, beta in [(64, 32, 10.0), (256, 200, 6.0), (1024, 512, 10.0), (100, 60, 8.0), (16, 16, 3.0)]:

@@ -817,6 +817,104 @@ void orc_firpfbch_cccf_execute_frames(orc_firpfbch_cccf q, const orc_cf *x, unsi
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* firdecim_crcf / firinterp_crcf: the polyphase pattern without a   */
+/* transform.  src/filter/src/firdecim.c, firinterp.c                                      */
+/* ------------------------------------------------------------------------------------ */
+
+struct orc_firdecim_s {
+    unsigned int M, h_len;
+    float *hr;                  /* taps reversed: lines up with an oldest-first window (firdecim.c:64-67) */
+    orc_cf *w;                  /* window of h_len samples */
+};
+
+/* firdecim.c:46-82 */
+orc_firdecim orc_firdecim_create(unsigned int M, const float *h, unsigned int h_len)
+{
+    if (h_len == 0 || M == 0) return NULL;
+    orc_firdecim q = xmalloc(sizeof *q);
+    q->M = M; q->h_len = h_len;
+    q->hr = xmalloc(h_len * sizeof *q->hr);
+    for (unsigned int i = 0; i < h_len; i++) q->hr[i] = h[h_len - i - 1];
+    q->w = xmalloc(h_len * sizeof *q->w);
+    memset(q->w, 0, h_len * sizeof *q->w);
+    return q;
+}
+
+/* firdecim.c:88-118: 2Mm+1 Kaiser taps at fc = 0.5/M, the first 2Mm used */
+orc_firdecim orc_firdecim_create_kaiser(unsigned int M, unsigned int m, float As)
+{
+    if (M < 2 || m == 0 || As < 0.0f) return NULL;
+    unsigned int h_len = 2 * M * m + 1;
+    float *h = xmalloc(h_len * sizeof *h);
+    orc_firdes_kaiser(h_len, 0.5f / (float)M, As, 0.0f, h);
+    orc_firdecim q = orc_firdecim_create(M, h, 2 * M * m);
+    free(h);
+    return q;
+}
+
+void orc_firdecim_destroy(orc_firdecim q) { if (q) { free(q->hr); free(q->w); free(q); } }
+void orc_firdecim_clear(orc_firdecim q) { memset(q->w, 0, q->h_len * sizeof *q->w); }   /* firdecim.c:179-182 */
+
+/* firdecim.c:189-223: M pushes per output, the dot product is taken right after the FIRST push */
+void orc_firdecim_execute_block(orc_firdecim q, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    for (unsigned int i = 0; i < n; i++)
+        for (unsigned int j = 0; j < q->M; j++) {
+            win_push(q->w, q->h_len, x[(size_t)i * q->M + j]);
+            if (j == 0) y[i] = dot_crcf(q->hr, q->w, q->h_len);
+        }
+}
+
+struct orc_firinterp_s {
+    unsigned int M, sub_len;
+    float *sub;                 /* [M][sub_len], newest tap last (the firpfb layout, firpfb.c:71-84) */
+    orc_cf *w;                  /* window of sub_len samples */
+};
+
+/* firinterp.c:43-80: prototype zero-padded to M * ceil(h_len / M), split into the M branches of a firpfb */
+orc_firinterp orc_firinterp_create(unsigned int M, const float *h, unsigned int h_len)
+{
+    if (M < 2 || h_len < M) return NULL;
+    orc_firinterp q = xmalloc(sizeof *q);
+    q->M = M;
+    q->sub_len = 0;
+    while (M * q->sub_len < h_len) q->sub_len++;
+    unsigned int H = M * q->sub_len;
+    float *hp = xmalloc(H * sizeof *hp);
+    for (unsigned int i = 0; i < H; i++) hp[i] = i < h_len ? h[i] : 0.0f;
+    q->sub = polyphase_split(hp, M, q->sub_len);
+    free(hp);
+    q->w = xmalloc(q->sub_len * sizeof *q->w);
+    memset(q->w, 0, q->sub_len * sizeof *q->w);
+    return q;
+}
+
+/* firinterp.c:86-116 */
+orc_firinterp orc_firinterp_create_kaiser(unsigned int M, unsigned int m, float As)
+{
+    if (M < 2 || m == 0 || As < 0.0f) return NULL;
+    unsigned int h_len = 2 * M * m + 1;
+    float *h = xmalloc(h_len * sizeof *h);
+    orc_firdes_kaiser(h_len, 0.5f / (float)M, As, 0.0f, h);
+    orc_firinterp q = orc_firinterp_create(M, h, 2 * M * m);
+    free(h);
+    return q;
+}
+
+void orc_firinterp_destroy(orc_firinterp q) { if (q) { free(q->sub); free(q->w); free(q); } }
+void orc_firinterp_reset(orc_firinterp q) { memset(q->w, 0, q->sub_len * sizeof *q->w); }   /* firinterp.c:178-181 */
+
+/* firinterp.c:187-217: one push, then the M branch outputs */
+void orc_firinterp_execute_block(orc_firinterp q, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    for (unsigned int i = 0; i < n; i++) {
+        win_push(q->w, q->sub_len, x[i]);
+        for (unsigned int j = 0; j < q->M; j++)
+            y[(size_t)i * q->M + j] = dot_crcf(q->sub + (size_t)j * q->sub_len, q->w, q->sub_len);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* spgramcf: windowed-FFT spectral periodogram                      */
 /* src/fft/src/spgramcf.c:27-51 instantiating src/fft/src/spgram.c                        */
 /* ------------------------------------------------------------------------------------ */

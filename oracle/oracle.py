@@ -109,6 +109,16 @@ def lib():
         L.orc_firpfbch_cccf_destroy.argtypes = [C.c_void_p]
         L.orc_firpfbch_cccf_execute_frames.restype = None
         L.orc_firpfbch_cccf_execute_frames.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
+        for nm in ("firdecim", "firinterp"):
+            getattr(L, "orc_%s_create" % nm).restype = C.c_void_p
+            getattr(L, "orc_%s_create" % nm).argtypes = [C.c_uint, c_f_p, C.c_uint]
+            getattr(L, "orc_%s_create_kaiser" % nm).restype = C.c_void_p
+            getattr(L, "orc_%s_create_kaiser" % nm).argtypes = [C.c_uint, C.c_uint, C.c_float]
+            getattr(L, "orc_%s_destroy" % nm).argtypes = [C.c_void_p]
+            getattr(L, "orc_%s_execute_block" % nm).restype = None
+            getattr(L, "orc_%s_execute_block" % nm).argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
+        L.orc_firdecim_clear.argtypes = [C.c_void_p]
+        L.orc_firinterp_reset.argtypes = [C.c_void_p]
         L.orc_spgramcf_create.restype = C.c_void_p
         L.orc_spgramcf_create.argtypes = [C.c_uint, c_f_p, C.c_uint]
         L.orc_spgramcf_create_kaiser.restype = C.c_void_p
@@ -290,6 +300,45 @@ class Firpfbch(_Obj):
         x = _cf(x).reshape(-1, self.M)
         y = np.empty_like(x)
         lib().orc_firpfbch_execute_frames(self.h, x, x.shape[0], y)
+        return y
+
+
+class Firdecim(_Obj):
+    """firdecim_crcf: n outputs from n*M inputs"""
+    _destroy = "orc_firdecim_destroy"
+
+    def __init__(self, M, h=None, kaiser=None):
+        self.M = M
+        super().__init__(lib().orc_firdecim_create(M, _f(h), len(h)) if kaiser is None
+                         else lib().orc_firdecim_create_kaiser(M, *kaiser))
+
+    def clear(self):
+        lib().orc_firdecim_clear(self.h)
+
+    def execute_block(self, x):
+        x = _cf(x)
+        n = len(x) // self.M
+        y = np.empty(n, np.complex64)
+        lib().orc_firdecim_execute_block(self.h, x, n, y)
+        return y
+
+
+class Firinterp(_Obj):
+    """firinterp_crcf: n*M outputs from n inputs"""
+    _destroy = "orc_firinterp_destroy"
+
+    def __init__(self, M, h=None, kaiser=None):
+        self.M = M
+        super().__init__(lib().orc_firinterp_create(M, _f(h), len(h)) if kaiser is None
+                         else lib().orc_firinterp_create_kaiser(M, *kaiser))
+
+    def reset(self):
+        lib().orc_firinterp_reset(self.h)
+
+    def execute_block(self, x):
+        x = _cf(x)
+        y = np.empty(len(x) * self.M, np.complex64)
+        lib().orc_firinterp_execute_block(self.h, x, len(x), y)
         return y
 
 
@@ -531,6 +580,34 @@ def ref_firpfbch_cccf_frames(type, M, p, h, x):
     for t in range(x.shape[0]):
         fn(q, x[t], y[t])
     R.firpfbch_cccf_destroy(q)
+    return y
+
+
+def ref_firdecim_block(M, x, h=None, kaiser=None):
+    R = ref()
+    R.firdecim_crcf_create.restype = C.c_void_p; R.firdecim_crcf_create.argtypes = [C.c_uint, c_f_p, C.c_uint]
+    R.firdecim_crcf_create_kaiser.restype = C.c_void_p; R.firdecim_crcf_create_kaiser.argtypes = [C.c_uint, C.c_uint, C.c_float]
+    R.firdecim_crcf_execute_block.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
+    R.firdecim_crcf_destroy.argtypes = [C.c_void_p]
+    q = C.c_void_p(R.firdecim_crcf_create(M, _f(h), len(h)) if kaiser is None else R.firdecim_crcf_create_kaiser(M, *kaiser))
+    x = _cf(x)
+    y = np.empty(len(x) // M, np.complex64)
+    R.firdecim_crcf_execute_block(q, x, len(y), y)
+    R.firdecim_crcf_destroy(q)
+    return y
+
+
+def ref_firinterp_block(M, x, h=None, kaiser=None):
+    R = ref()
+    R.firinterp_crcf_create.restype = C.c_void_p; R.firinterp_crcf_create.argtypes = [C.c_uint, c_f_p, C.c_uint]
+    R.firinterp_crcf_create_kaiser.restype = C.c_void_p; R.firinterp_crcf_create_kaiser.argtypes = [C.c_uint, C.c_uint, C.c_float]
+    R.firinterp_crcf_execute_block.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
+    R.firinterp_crcf_destroy.argtypes = [C.c_void_p]
+    q = C.c_void_p(R.firinterp_crcf_create(M, _f(h), len(h)) if kaiser is None else R.firinterp_crcf_create_kaiser(M, *kaiser))
+    x = _cf(x)
+    y = np.empty(len(x) * M, np.complex64)
+    R.firinterp_crcf_execute_block(q, x, len(x), y)
+    R.firinterp_crcf_destroy(q)
     return y
 
 

@@ -630,6 +630,41 @@ def test_pfbch_cccf_real_taps_take_the_crcf_path(L, orc, monkeypatch):
         assert np.array_equal(q.analyzer_run(0), want[t])
 
 
+# ------------------------------------------------------------------ firdecim / firinterp
+def test_firdecim_firinterp_vs_reference_fixture_and_oracle(L, orc, refrn):
+    """Kaiser objects and random taps against the compiled reference's outputs; state carried across calls
+    of awkward sizes; a long block against the oracle"""
+    from test_oracle import _mr_cases
+    for tag, M, m in _mr_cases(refrn):
+        x, h = refrn[tag + "_x"], refrn[tag + "_h"]
+        for make_l, key in ((lambda: L.firdecim_crcf.create_kaiser(M, m, 60.0), "_decim_kaiser"),
+                            (lambda: L.firdecim_crcf.create(M, h), "_decim_h")):
+            want = refrn[tag + key]
+            q = make_l()
+            got = np.concatenate([q.execute_block(x[:7 * M]), q.execute_block(x[7 * M:8 * M]), q.execute_block(x[8 * M:])])
+            assert np.abs(got - want).max() < 4e-6 * max(1.0, np.abs(want).max()), (tag, key)
+            q.clear()
+            assert np.abs(q.execute(x[:M]) - want[0]) < 4e-6 * max(1.0, np.abs(want).max())
+        xi = x[:300]
+        for make_l, key in ((lambda: L.firinterp_crcf.create_kaiser(M, m, 60.0), "_interp_kaiser"),
+                            (lambda: L.firinterp_crcf.create(M, h), "_interp_h")):
+            want = refrn[tag + key]
+            q = make_l()
+            got = np.concatenate([q.execute_block(xi[:5]), q.execute_block(xi[5:6]), q.execute_block(xi[6:])])
+            assert np.abs(got - want).max() < 4e-6 * max(1.0, np.abs(want).max()), (tag, key)
+            q.reset()
+            assert np.abs(q.execute(xi[0]) - want[:M]).max() < 4e-6 * max(1.0, np.abs(want).max())
+    M, m = 8, 6
+    x = orc.synth_input(M * 40000 + 3 * M, seed=0x3A)
+    assert np.abs(L.firdecim_crcf.create_kaiser(M, m, 60.0).execute_block(x) - orc.Firdecim(M, kaiser=(m, 60.0)).execute_block(x)).max() < 4e-6
+    assert np.abs(L.firinterp_crcf.create_kaiser(M, m, 60.0).execute_block(x[:50000])
+                  - orc.Firinterp(M, kaiser=(m, 60.0)).execute_block(x[:50000])).max() < 4e-6
+    # root-Nyquist prototype path
+    got = L.firdecim_crcf.create_prototype(L.LIQUID_FIRFILT_ARKAISER, 4, 5, 0.3).execute_block(x[:4000])
+    want = orc.Firdecim(4, h=orc.firdes_arkaiser(4, 5, np.float32(0.3))).execute_block(x[:4000])
+    assert np.abs(got - want).max() < 4e-6 * np.abs(want).max()
+
+
 # ------------------------------------------------------------------ spgramcf (SURVEY 8f item 2)
 def test_spgramcf_vs_reference_fixture_and_oracle(L, orc, refrn):
     """every entry point against the compiled reference's outputs (power-of-two and other nfft), plus a

@@ -419,3 +419,34 @@ def test_spgramcf_properties(orc):
     q2 = orc.Spgramcf(nfft)
     q2.write(x[:5 * nfft])                                    # same buffer contents as after the last transform
     assert np.abs(first - q2.execute_psd()).max() < 1e-3
+
+
+# ------------------------------------------------------------------ firdecim / firinterp
+def _mr_cases(refrn):
+    for name in sorted(k for k in refrn if k.startswith("mr_") and k.endswith("_x")):
+        M, m = (int(v[1:]) for v in name.split("_")[1:3])
+        yield name[:-2], M, m
+
+
+def test_fixture_firdecim_firinterp(orc, refrn):
+    for tag, M, m in _mr_cases(refrn):
+        x, h = refrn[tag + "_x"], refrn[tag + "_h"]
+        assert np.abs(orc.Firdecim(M, kaiser=(m, 60.0)).execute_block(x) - refrn[tag + "_decim_kaiser"]).max() < 2e-6
+        got = orc.Firdecim(M, h=h).execute_block(x)
+        assert np.abs(got - refrn[tag + "_decim_h"]).max() < 2e-6 * np.abs(refrn[tag + "_decim_h"]).max()
+        assert np.abs(orc.Firinterp(M, kaiser=(m, 60.0)).execute_block(x[:300]) - refrn[tag + "_interp_kaiser"]).max() < 2e-6
+        got = orc.Firinterp(M, h=h).execute_block(x[:300])
+        assert np.abs(got - refrn[tag + "_interp_h"]).max() < 2e-6 * np.abs(refrn[tag + "_interp_h"]).max()
+
+
+def test_firdecim_is_subsampled_firfilt_and_firinterp_is_filtered_upsampling(orc):
+    """the identities the two objects stand for: decimation = every M-th output of the full-rate filter;
+    interpolation = the full-rate filter over the zero-stuffed input"""
+    M, m = 4, 3
+    h = orc.firdes_kaiser(2 * M * m + 1, 0.5 / M, 60.0)[: 2 * M * m]
+    x = orc.synth_input(M * 100, seed=5)
+    full = orc.Firfilt(h=h).execute_block(x)
+    assert np.abs(orc.Firdecim(M, h=h).execute_block(x) - full[::M]).max() < 1e-6
+    up = np.zeros(100 * M, np.complex64)
+    up[::M] = x[:100]
+    assert np.abs(orc.Firinterp(M, h=h).execute_block(x[:100]) - orc.Firfilt(h=h).execute_block(up)).max() < 1e-6

@@ -3,7 +3,7 @@
 measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
 events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
 
-  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
+  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
 """
 import argparse
 import json
@@ -117,6 +117,18 @@ def main():
             ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
             report("c3m: firpfbch2_crcf analysis M=1024 m=%d, 2^29 samples" % m, n, 24, ms, ln)
             del x, y
+    if "c5m" in args.configs:
+        # the cluster kernel (M=4096) at the filter lengths it is instantiated for
+        for m in (4, 7, 9):
+            M, n = 4096, 1 << 29
+            q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+            H = q.get_state_len()
+            x = torch.zeros(2 * (H + n), dtype=torch.float32, device=dev)
+            y = torch.empty(4 * n, dtype=torch.float32, device=dev)
+            L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
+            ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
+            report("c5m: firpfbch2_crcf analysis M=4096 m=%d, 2^29 samples" % m, n, 24, ms, ln)
+            del x, y
     if "g" in args.configs:
         # shapes without a dedicated fused kernel: the one-kernel shape-generic analyzers (power-of-two M)
         for M, m, n in ((256, 4, 1 << 27), (64, 5, 1 << 27), (2048, 3, 1 << 27)):
@@ -144,6 +156,22 @@ def main():
         q = L.firpfbch_cccf.create(L.LIQUID_ANALYZER, M, 2 * m, h)
         ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
         report("f1b: firpfbch_cccf analysis M=256 p=10, complex taps (shape-generic MAC + FFT kernels), 2^27 samples", n, 16, ms, ln)
+        del x, y
+    if "f3" in args.configs:
+        # firdecim_crcf (M=8, m=6: 96 taps, 2^28 inputs) and firinterp_crcf (M=8, m=6, 2^25 inputs)
+        M, m = 8, 6
+        n = 1 << 28
+        x = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr(), n, stream=st.cuda_stream)
+        q = L.firdecim_crcf.create_kaiser(M, m, 60.0)
+        ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
+        report("f3a: firdecim_crcf M=8 m=6 (96 taps), 2^28 input samples", n, 8 + 8 / M, ms, ln)
+        ni = n // M
+        qi = L.firinterp_crcf.create_kaiser(M, m, 60.0)
+        ms, ln = timed(lambda: qi.execute_block_dev(x.data_ptr(), ni, y.data_ptr(), st.cuda_stream))
+        report("f3b: firinterp_crcf M=8 m=6, 2^25 input samples (2^28 outputs)", ni, 8 + 8 * M, ms, ln,
+               {"note": "throughput in INPUT samples/s; algorithmic bytes 8 in + 8 M out per input sample"})
         del x, y
     if "fft" in args.configs:
         # a11: the batched complex FFT on its own (fft_execute_batch_dev), 2^28 points per step, out of place
