@@ -84,11 +84,9 @@ void FftPlanDev::init(unsigned int n_, int sign_)
     LC_CUDA_CHECK(cudaMemcpy(d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
     if (is_pow2(n) && n >= 2) {
         // transforms above 3072 points need more than the default 48 KB of dynamic smem
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<unsigned long long> configured{0};
+        if (first_time_on_device(configured))
             LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
     }
 }
 

@@ -348,11 +348,9 @@ void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps,
     const unsigned int row = (n_samp + kOpt - 1) / kOpt + 1;
     const size_t smem = sizeof(float) * ((n_taps + 1) & ~1u) + sizeof(float2) * (size_t)row * kOpt;
     if (smem > 200 * 1024) fatal("firfilt_crcf_execute_block", "filter too long for this build (more than ~20000 taps)");
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
+    static std::atomic<unsigned long long> configured{0};
+    if (smem > 48 * 1024 && first_time_on_device(configured))
         LC_CUDA_CHECK(cudaFuncSetAttribute(firfilt_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        smem_set = 200 * 1024;
-    }
     unsigned long long total = tiles * n_streams;
     const unsigned long long max_grid = 1ull << 30;
     if (total > max_grid) fatal("firfilt_crcf_execute_streams_dev", "too many tiles for one launch");

@@ -119,11 +119,9 @@ void decim_dev(firdecim_crcf q, const float2 *d_x, unsigned long long n_out, flo
     while (tile > 1 && bytes_for(tile) > budget) tile >>= 1;
     const size_t smem = bytes_for(tile);
     if (smem > 200 * 1024) lc::fatal("firdecim_crcf_execute_block", "filter too long for this build");
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
+    static std::atomic<unsigned long long> configured{0};
+    if (smem > 48 * 1024 && lc::first_time_on_device(configured))
         LC_CUDA_CHECK(cudaFuncSetAttribute(firdecim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        smem_set = 200 * 1024;
-    }
     const unsigned long long ctas = (n_out + tile - 1) / tile;
     if (ctas >= (1ull << 31)) lc::fatal("firdecim_crcf_execute_block", "too many outputs for one launch");
     firdecim_kernel<<<(unsigned int)ctas, kThreads, smem, st>>>(q->d_hist, d_x, (int)q->h_len, q->d_h, q->h_len, q->M, tile, d_y, n_out);

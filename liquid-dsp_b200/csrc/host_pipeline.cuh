@@ -22,11 +22,16 @@ struct CopyStreams {
     }
 };
 
+// the calling thread's copy streams on the CURRENT device (streams belong to a device; a process may drive
+// several through liquid_cuda_set_device)
 inline CopyStreams &copy_streams()
 {
-    static thread_local CopyStreams cs;
-    cs.ensure();
-    return cs;
+    static thread_local CopyStreams cs[64];
+    int dev = 0;
+    LC_CUDA_CHECK(cudaGetDevice(&dev));
+    CopyStreams &c = cs[dev & 63];
+    c.ensure();
+    return c;
 }
 
 // n_units units of work; unit u reads in_per complex samples at x + u*in_per and writes out_per at

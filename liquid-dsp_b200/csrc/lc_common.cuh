@@ -81,6 +81,17 @@ struct DevBuf {
     }
 };
 
+// Function attributes (opt-in dynamic shared memory) belong to a device: a process that drives several GPUs
+// through liquid_cuda_set_device must configure each kernel once per device.  `mask` is a function-local
+// static of the caller; returns true the first time it is asked on the current device.
+inline bool first_time_on_device(std::atomic<unsigned long long> &mask)
+{
+    int dev = 0;
+    LC_CUDA_CHECK(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+}
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline bool is_pow2(unsigned int n) { return n && !(n & (n - 1)); }

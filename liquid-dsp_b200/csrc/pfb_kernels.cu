@@ -334,8 +334,8 @@ void launch_pfbch2_analyze_pow2(const float2 *d_hist, const float2 *d_x, int H, 
                                 float2 *d_y, unsigned int M, unsigned int L, unsigned long long n_frames, int parity0,
                                 cudaStream_t st, long long t_first)
 {
-    static bool once = (ensure_big_smem(pfbch2_analyze_pow2_kernel), true);
-    (void)once;
+    static std::atomic<unsigned long long> configured{0};
+    if (first_time_on_device(configured)) ensure_big_smem(pfbch2_analyze_pow2_kernel);
     const unsigned int per_cta = lcfft::per_cta_for(M, n_frames);
     const unsigned long long ctas = (n_frames + per_cta - 1) / per_cta;
     if (ctas >= (1ull << 31)) fatal("firpfbch2_crcf_execute_block", "too many frames for one launch");
@@ -350,8 +350,8 @@ static void launch_pfbch_analyze_pow2_t(const float2 *d_hist, const float2 *d_x,
                                         unsigned long long n_frames, unsigned int phase, unsigned int first,
                                         unsigned int k, cudaStream_t st)
 {
-    static bool once = (ensure_big_smem(pfbch_analyze_pow2_kernel<TapT>), true);
-    (void)once;
+    static std::atomic<unsigned long long> configured{0};
+    if (first_time_on_device(configured)) ensure_big_smem(pfbch_analyze_pow2_kernel<TapT>);
     const unsigned int per_cta = lcfft::per_cta_for(M, n_frames);
     const unsigned long long ctas = (n_frames + per_cta - 1) / per_cta;
     if (ctas >= (1ull << 31)) fatal("firpfbch_analyzer_execute_block", "too many frames for one launch");

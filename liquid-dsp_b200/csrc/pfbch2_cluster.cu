@@ -437,17 +437,19 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_cluster_4096_kernel(const 
     cluster_sync_all();
 }
 
-int g_max_clusters = -1;         // co-resident clusters of 8 on this device (measured on first use)
+int g_max_clusters_dev[64];      // co-resident clusters of 8 per device, stored as n + 1 (0 = not measured yet)
 
 template <int L>
 long long run_L(ClusterArgs &a, long long n_groups, int par0, cudaStream_t st)
 {
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured)) {
         LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_cluster_4096_kernel<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<L>::kBytes));
         LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_cluster_4096_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<L>::kBytes));
-        configured = true;
     }
+    int cur_dev = 0;
+    LC_CUDA_CHECK(cudaGetDevice(&cur_dev));
+    int &max_slot = g_max_clusters_dev[cur_dev & 63];
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = Smem<L>::kBytes;
@@ -459,10 +461,9 @@ long long run_L(ClusterArgs &a, long long n_groups, int par0, cudaStream_t st)
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (g_max_clusters < 0) {
-        int dev = 0, sms = 148, n = 0;
-        LC_CUDA_CHECK(cudaGetDevice(&dev));
-        LC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (max_slot == 0) {
+        int sms = 148, n = 0;
+        LC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev));
         cfg.gridDim = dim3((unsigned int)(sms / kCluster) * kCluster, 1, 1);
         cudaError_t e = cudaOccupancyMaxActiveClusters(&n, pfbch2_cluster_4096_kernel<L, 0>, &cfg);
         if (e != cudaSuccess) {
@@ -473,10 +474,11 @@ long long run_L(ClusterArgs &a, long long n_groups, int par0, cudaStream_t st)
             int lim = atoi(env);
             if (lim >= 0 && lim < n) n = lim;
         }
-        g_max_clusters = n;
+        max_slot = n + 1;
         if (getenv("LIQUID_CUDA_VERBOSE"))
             fprintf(stderr, "liquid_cuda: pfbch2 cluster kernel: %d co-resident clusters of %d CTAs on %d SMs\n", n, kCluster, sms);
     }
+    const int g_max_clusters = max_slot - 1;
     if (g_max_clusters == 0) return 0;                     // clusters of 8 cannot be scheduled here
     // at least 4 groups (16 frames) per cluster so the history prologue and the pipeline fill amortise
     long long cl = (n_groups + 3) / 4;
@@ -519,7 +521,12 @@ void cluster_pfbch2_make_twiddles(std::vector<float2> &tw)
         }
 }
 
-int cluster_pfbch2_max_clusters() { return g_max_clusters; }
+int cluster_pfbch2_max_clusters()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    return g_max_clusters_dev[dev & 63] - 1;
+}
 
 long long launch_pfbch2_cluster(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps_scaled,
                                 const float2 *d_tw, float2 *d_y, unsigned int M, unsigned int L,

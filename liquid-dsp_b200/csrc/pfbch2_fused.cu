@@ -255,11 +255,10 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
 template <int L>
 void launch_L(const FusedArgs &a, int par0, unsigned int grid, cudaStream_t st)
 {
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured)) {
         LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_fused_1024_kernel<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_fused_1024_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
     }
     if (par0) pfbch2_fused_1024_kernel<L, 1><<<grid, kThreads, kSmemBytes, st>>>(a);
     else      pfbch2_fused_1024_kernel<L, 0><<<grid, kThreads, kSmemBytes, st>>>(a);

@@ -243,11 +243,10 @@ void run_transforms(spgramcf q, const float2 *d_x, unsigned long long T, Segs se
     if (T == 0) return;
     const unsigned int nfft = q->nfft;
     if (lcfft::pow2_in_smem(nfft)) {
-        static bool once = false;
-        if (!once) {
+        static std::atomic<unsigned long long> configured{0};
+        if (lc::first_time_on_device(configured)) {
             LC_CUDA_CHECK(cudaFuncSetAttribute(spgram_transform_pow2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             LC_CUDA_CHECK(cudaFuncSetAttribute(spgram_transform_pow2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            once = true;
         }
         const unsigned int per_cta = lcfft::per_cta_for(nfft, T);
         const unsigned long long ctas = (T + per_cta - 1) / per_cta;
@@ -295,11 +294,9 @@ void accumulate_transforms(spgramcf q, const float2 *d_x, unsigned long long T, 
     if (T == 0) return;
     const unsigned int nfft = q->nfft;
     if (lcfft::pow2_in_smem(nfft)) {
-        static bool once = false;
-        if (!once) {
+        static std::atomic<unsigned long long> configured{0};
+        if (lc::first_time_on_device(configured))
             LC_CUDA_CHECK(cudaFuncSetAttribute(spgram_accumulate_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            once = true;
-        }
         // transforms per CTA: a block of up to 64 transforms is one chunk (folded in exactly the reference's
         // order); beyond that aim at ~8 CTAs per SM, at most 2048 chunks for the combine pass
         unsigned long long tpc = kFoldChunk;
