@@ -69,6 +69,7 @@ class ClockSampler:
     def __init__(self, index, period=0.002):
         self.samples, self.reasons, self.stop_flag = [], set(), False
         self.period = period
+        self.armed = False              # the thread is started before the timed region, samples count from arm()
         self.max_mhz = None
         self.thread = None
         try:
@@ -95,7 +96,11 @@ class ClockSampler:
         }
         while not self.stop_flag:
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                if not self.armed:
+                    time.sleep(self.period)
+                    continue
+                self.samples.append(mhz)
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:   # noqa: BLE001
@@ -111,6 +116,9 @@ class ClockSampler:
         if self.nv:
             self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
+
+    def arm(self):
+        self.armed = True
 
     def stop(self):
         self.stop_flag = True
@@ -291,8 +299,13 @@ def main():
     sampler = ClockSampler(local_rank, period=0.002 if world == 1 else 0.010) if rank == 0 else None
     launches0 = L.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # the sampler thread's start-up and first NVML call happen before the barrier, not inside the timed region
     if sampler:
         sampler.start()
+    time.sleep(0.05)
+    sync_all()                                           # every rank: barrier + device synchronize
+    if sampler:
+        sampler.arm()
     ev[0].record(stream)
     for i in range(args.steps):
         step()
