@@ -20,86 +20,35 @@ namespace {
 using lcfft::fft_post;
 using lcfft::kFftThreads;
 
-// One Stockham pass of radix R (as lcfft::stockham_pass) whose source and / or destination is global memory:
-// the first pass of a transform reads x directly (consecutive threads read consecutive addresses), the last
-// pass writes y directly (runs of Ns >= 16 consecutive outputs) with the post-scaling applied -- the transform
-// makes no extra trip through shared memory at either end, and transforms of up to 16 points never touch it.
-template <int R, int SIGN, bool SRC_GLOBAL, bool DST_GLOBAL>
-__device__ __forceinline__ void fft_pass_io(const float2 *__restrict__ src_s, float2 *__restrict__ dst_s,
-                                            const float2 *__restrict__ tw_s, unsigned int n, unsigned int log2n,
-                                            unsigned int Ns, unsigned int per_cta, const float2 *__restrict__ x,
-                                            float2 *__restrict__ y, unsigned long long first, unsigned long long batch,
-                                            int post_mode, float pa, float pb)
-{
-    constexpr unsigned int kLog2R = (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1;
-    const unsigned int log2q = log2n - kLog2R;
-    const unsigned int q = 1u << log2q;
-    const unsigned int tstride = (n >> kLog2R) / Ns;
-    for (unsigned int i = threadIdx.x; i < (per_cta << log2q); i += blockDim.x) {
-        const unsigned int f = i >> log2q, j = i & (q - 1);
-        const unsigned int k = j & (Ns - 1);
-        const unsigned int base = f << log2n;
+// first-pass source / last-pass destination of the batched FFT: global memory, directly (consecutive threads
+// read consecutive addresses; the last pass writes runs of Ns >= 16 consecutive outputs, post-scaled)
+struct GlobalSrc {
+    const float2 *x;
+    unsigned int n;
+    unsigned long long first, batch;
+    __device__ __forceinline__ float2 operator()(unsigned int f, unsigned int idx) const
+    {
         const unsigned long long b = first + f;
-        float2 v[R];
-        if (SRC_GLOBAL) {
-            const float2 *xp = x + b * n + j;
-#pragma unroll
-            for (int m = 0; m < R; m++) v[m] = (b < batch) ? __ldg(xp + m * q) : make_float2(0.f, 0.f);
-        } else {
-#pragma unroll
-            for (int m = 0; m < R; m++) v[m] = src_s[lcfft::pidx(base + j + m * q)];
-        }
-        if (Ns > 1) {
-#pragma unroll
-            for (int m = 1; m < R; m++) v[m] = lcf::cmul2(v[m], tw_s[k * m * tstride]);
-        }
-        lcf::RegDft<R, SIGN>::run(v);
-        const unsigned int d = (j - k) * R + k;
-        if (DST_GLOBAL) {
-            if (b < batch) {
-                float2 *yp = y + b * n + d;
-#pragma unroll
-                for (int m = 0; m < R; m++) yp[m * Ns] = fft_post(v[m], post_mode, pa, pb);
-            }
-        } else {
-#pragma unroll
-            for (int m = 0; m < R; m++) dst_s[lcfft::pidx(base + d + m * Ns)] = v[m];
-        }
+        return b < batch ? __ldg(x + b * n + idx) : make_float2(0.f, 0.f);
     }
-    if (!DST_GLOBAL) __syncthreads();
-}
-
-template <int SIGN>
-__device__ __forceinline__ void fft_pow2_body(const lcfft::Smem &sm, const float2 *__restrict__ x, float2 *__restrict__ y,
-                                              unsigned int n, unsigned int log2n, unsigned int per_cta,
-                                              unsigned long long first, unsigned long long batch,
-                                              int post_mode, float pa, float pb)
-{
-#define LC_FFT_PASS(R, SRCG, DSTG) \
-    fft_pass_io<R, SIGN, SRCG, DSTG>(in, out, sm.tw, n, log2n, Ns, per_cta, x, y, first, batch, post_mode, pa, pb)
-    float2 *in = sm.buf0, *out = sm.buf1;
-    unsigned int Ns = 1, left = log2n;
-    bool first_pass = true;
-    while (left >= 4) {
-        const bool last = (left == 4);
-        if (first_pass && last)  LC_FFT_PASS(16, true, true);
-        else if (first_pass)     LC_FFT_PASS(16, true, false);
-        else if (last)           LC_FFT_PASS(16, false, true);
-        else                     LC_FFT_PASS(16, false, false);
-        Ns <<= 4;
-        left -= 4;
-        first_pass = false;
-        float2 *t = in; in = out; out = t;
+};
+struct GlobalDst {
+    float2 *y;
+    unsigned int n;
+    unsigned long long first, batch;
+    int post_mode;
+    float pa, pb;
+    __device__ __forceinline__ void operator()(unsigned int f, unsigned int idx, float2 v) const
+    {
+        const unsigned long long b = first + f;
+        if (b < batch) y[b * n + idx] = fft_post(v, post_mode, pa, pb);
     }
-    if (left == 3)      { if (first_pass) LC_FFT_PASS(8, true, true); else LC_FFT_PASS(8, false, true); }
-    else if (left == 2) { if (first_pass) LC_FFT_PASS(4, true, true); else LC_FFT_PASS(4, false, true); }
-    else if (left == 1) { if (first_pass) LC_FFT_PASS(2, true, true); else LC_FFT_PASS(2, false, true); }
-#undef LC_FFT_PASS
-}
+};
 
 // Stockham autosort FFT of n = 2^log2n points per transform, `per_cta` transforms per CTA (fft_device.cuh),
-// first pass from global memory, last pass to global memory.  In place (x == y) is fine: a CTA has read all the
-// inputs of its transforms before it writes any of their outputs.
+// first pass from global memory, last pass to global memory: a transform makes no extra trip through shared
+// memory at either end, and transforms of up to 16 points never touch it.  In place (x == y) is fine: a CTA
+// has read all the inputs of its transforms before it writes any of their outputs.
 __global__ void __launch_bounds__(kFftThreads)
 fft_pow2_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const float2 *__restrict__ tw,
                 unsigned int n, unsigned int log2n, unsigned int per_cta, unsigned long long batch,
@@ -108,13 +57,11 @@ fft_pow2_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const floa
     extern __shared__ float2 smem[];
     const lcfft::Smem sm = lcfft::carve(smem, n, per_cta);
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
-    if (log2n > 4) {
-        // more than one pass: the later ones need the twiddle table; the barrier at the end of the first pass
-        // (which needs no twiddles, Ns = 1) publishes it
-        lcfft::stage_twiddles(sm, tw, n);
-    }
-    if (sgn > 0.0f) fft_pow2_body<+1>(sm, x, y, n, log2n, per_cta, first, batch, post_mode, pa, pb);
-    else            fft_pow2_body<-1>(sm, x, y, n, log2n, per_cta, first, batch, post_mode, pa, pb);
+    if (log2n > 4) lcfft::stage_twiddles(sm, tw, n);          // published by the barrier after the first pass
+    const GlobalSrc src{x, n, first, batch};
+    const GlobalDst dst{y, n, first, batch, post_mode, pa, pb};
+    if (sgn > 0.0f) lcfft::stockham_run<+1>(sm, n, log2n, per_cta, src, dst);
+    else            lcfft::stockham_run<-1>(sm, n, log2n, per_cta, src, dst);
 }
 
 // table-driven DFT, one CTA per transform; smem: n float2

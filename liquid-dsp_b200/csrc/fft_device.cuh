@@ -47,10 +47,27 @@ __device__ __forceinline__ void stage_twiddles(const Smem &s, const float2 *__re
     for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) s.tw[i] = __ldg(tw + i);
 }
 
-template <int R, int SIGN>
-__device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, float2 *__restrict__ dst,
-                                              const float2 *__restrict__ tw, unsigned int n, unsigned int log2n,
-                                              unsigned int Ns, unsigned int per_cta)
+// element accessors of a pass: Src()(f, idx) returns logical element idx of transform f of this CTA,
+// Dst()(f, idx, v) stores it.  The shared-memory ones address the padded buffers; callers supply their own for
+// the first pass (read global memory, taper a segment, compute a polyphase dot product ...) and the last pass
+// (write global memory with a scale ...), so a transform makes no extra trip through shared memory at its ends.
+struct SmemSrc {
+    const float2 *p;
+    unsigned int log2n;
+    __device__ __forceinline__ float2 operator()(unsigned int f, unsigned int idx) const { return p[pidx((f << log2n) + idx)]; }
+};
+struct SmemDst {
+    float2 *p;
+    unsigned int log2n;
+    __device__ __forceinline__ void operator()(unsigned int f, unsigned int idx, float2 v) const { p[pidx((f << log2n) + idx)] = v; }
+};
+
+// one Stockham autosort pass of radix R over the per_cta transforms: butterfly j of transform f reads elements
+// j + m q (q = n / R), multiplies by W_{R Ns}^(k m) (k = j mod Ns), does the R-point DFT in registers and writes
+// elements (j - k) R + k + m Ns
+template <int R, int SIGN, class Src, class Dst>
+__device__ __forceinline__ void stockham_pass(const Src &src, const Dst &dst, const float2 *__restrict__ tw,
+                                              unsigned int n, unsigned int log2n, unsigned int Ns, unsigned int per_cta)
 {
     constexpr unsigned int kLog2R = (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1;
     const unsigned int log2q = log2n - kLog2R;
@@ -59,47 +76,67 @@ __device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, fl
     for (unsigned int i = threadIdx.x; i < (per_cta << log2q); i += blockDim.x) {
         const unsigned int f = i >> log2q, j = i & (q - 1);
         const unsigned int k = j & (Ns - 1);
-        const unsigned int base = f << log2n;
         float2 v[R];
 #pragma unroll
-        for (int m = 0; m < R; m++) v[m] = src[pidx(base + j + m * q)];
+        for (int m = 0; m < R; m++) v[m] = src(f, j + m * q);
         if (Ns > 1) {
 #pragma unroll
             for (int m = 1; m < R; m++) v[m] = lcf::cmul2(v[m], tw[k * m * tstride]);
         }
         lcf::RegDft<R, SIGN>::run(v);
-        const unsigned int d = base + (j - k) * R + k;
+        const unsigned int d = (j - k) * R + k;
 #pragma unroll
-        for (int m = 0; m < R; m++) dst[pidx(d + m * Ns)] = v[m];
+        for (int m = 0; m < R; m++) dst(f, d + m * Ns, v[m]);
     }
-    __syncthreads();
 }
 
-template <int SIGN>
-__device__ __forceinline__ float2 *stockham_all(const Smem &s, unsigned int n, unsigned int log2n, unsigned int per_cta)
+// all passes of the per_cta transforms: radix 16 while at least 16 points are left, then one pass of radix
+// 8 / 4 / 2.  The first pass reads through `first`, the last pass writes through `last`; passes in between
+// ping-pong in shared memory with a block barrier after each.  When the transform has more than one pass the
+// twiddle table must have been staged (stage_twiddles) -- the barrier after the first pass publishes it.
+template <int SIGN, class Src, class Dst>
+__device__ __forceinline__ void stockham_run(const Smem &s, unsigned int n, unsigned int log2n, unsigned int per_cta,
+                                             const Src &first, const Dst &last)
 {
     float2 *in = s.buf0, *out = s.buf1;
     unsigned int Ns = 1, left = log2n;
+    bool is_first = true;
+#define LC_PASS(R)                                                                                               \
+    do {                                                                                                         \
+        const bool is_last = (left == ((R == 16) ? 4u : (R == 8) ? 3u : (R == 4) ? 2u : 1u));                    \
+        const SmemSrc ssrc{in, log2n};                                                                           \
+        const SmemDst sdst{out, log2n};                                                                          \
+        if (is_first && is_last)  stockham_pass<R, SIGN>(first, last, s.tw, n, log2n, Ns, per_cta);              \
+        else if (is_first)        stockham_pass<R, SIGN>(first, sdst, s.tw, n, log2n, Ns, per_cta);              \
+        else if (is_last)         stockham_pass<R, SIGN>(ssrc, last, s.tw, n, log2n, Ns, per_cta);               \
+        else                      stockham_pass<R, SIGN>(ssrc, sdst, s.tw, n, log2n, Ns, per_cta);               \
+        if (!is_last) __syncthreads();                                                                           \
+    } while (0)
     while (left >= 4) {
-        stockham_pass<16, SIGN>(in, out, s.tw, n, log2n, Ns, per_cta);
+        LC_PASS(16);
         Ns <<= 4;
         left -= 4;
+        is_first = false;
         float2 *t = in; in = out; out = t;
     }
-    if (left == 3)      stockham_pass<8, SIGN>(in, out, s.tw, n, log2n, Ns, per_cta);
-    else if (left == 2) stockham_pass<4, SIGN>(in, out, s.tw, n, log2n, Ns, per_cta);
-    else if (left == 1) stockham_pass<2, SIGN>(in, out, s.tw, n, log2n, Ns, per_cta);
-    if (left) { float2 *t = in; in = out; out = t; }
-    return in;
+    if (left == 3)      LC_PASS(8);
+    else if (left == 2) LC_PASS(4);
+    else if (left == 1) LC_PASS(2);
+#undef LC_PASS
 }
 
-// FFT of the per_cta transforms in s.buf0 (logical element i at s.buf0[pidx(i)]); the twiddle table must have
-// been staged and the CTA synchronised.  Returns the buffer that holds the result, natural order, same layout.
-// sgn: +1 backward (e^{+j}), -1 forward; it must match the staged table.
-__device__ __forceinline__ float2 *stockham_pow2(const Smem &s, unsigned int n, unsigned int log2n,
-                                                 unsigned int per_cta, float sgn)
+// the same with the result left in shared memory (padded layout, natural order): returns the buffer that
+// holds it; a block barrier has been passed when it returns
+template <int SIGN, class Src>
+__device__ __forceinline__ const float2 *stockham_run_to_smem(const Smem &s, unsigned int n, unsigned int log2n,
+                                                              unsigned int per_cta, const Src &first)
 {
-    return sgn > 0.0f ? stockham_all<+1>(s, n, log2n, per_cta) : stockham_all<-1>(s, n, log2n, per_cta);
+    // the buffer the last pass writes: passes alternate buf1, buf0, buf1, ...
+    const unsigned int n_passes = (log2n + 3) / 4;
+    float2 *res = (n_passes & 1) ? s.buf1 : s.buf0;
+    stockham_run<SIGN>(s, n, log2n, per_cta, first, SmemDst{res, log2n});
+    __syncthreads();
+    return res;
 }
 
 // transforms per CTA for n-point transforms and the shared memory they need.  2048 points per CTA keeps four

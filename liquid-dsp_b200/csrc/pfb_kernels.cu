@@ -58,9 +58,24 @@ pfbch2_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x,
         X[gid] = pfbch2_mac_elem(hist, x, H, taps, M, L, parity0, t_first + (long long)(gid / M), (unsigned int)(gid % M));
 }
 
+// last-pass destination of the one-kernel analyzers: global memory, scaled
+struct FrameDst {
+    float2 *y;
+    unsigned int M;
+    unsigned long long first, n_frames;
+    int post_mode;
+    float pa;
+    __device__ __forceinline__ void operator()(unsigned int f, unsigned int k, float2 v) const
+    {
+        if (first + f < n_frames) y[(first + f) * M + k] = lcfft::fft_post(v, post_mode, pa, 1.0f);
+    }
+};
+
 // firpfbch2 analyzer for power-of-two M in ONE kernel: the polyphase MACs of `per_cta` frames are written
-// straight into shared memory, transformed there (Stockham, backward) and stored divided by M -- the
-// transform input never visits HBM.  Samples are re-read through L1/L2 (2m uses each).
+// straight into shared memory (all threads busy with independent dot products: computing them inside the
+// first FFT pass instead serialises 16 of them per thread and halved the rate), transformed there (Stockham,
+// backward), and the last pass writes global memory divided by M -- the transform input never visits HBM.
+// Samples are re-read through L1/L2 (2m uses each).
 __global__ void __launch_bounds__(lcfft::kFftThreads)
 pfbch2_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
                            const float *__restrict__ taps, const float2 *__restrict__ tw, float2 *__restrict__ y,
@@ -71,7 +86,6 @@ pfbch2_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__rest
     const lcfft::Smem sm = lcfft::carve(smem_f2, M, per_cta);
     lcfft::stage_twiddles(sm, tw, M);
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
-    const unsigned int total = per_cta * M;
     {
         // fill: thread = (window, frame lane); everything that depends on the window alone is hoisted out of
         // the frame loop and the taps walk by pointer -- the same fmaf sequence as pfbch2_mac_elem, bit for bit
@@ -113,11 +127,8 @@ pfbch2_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__rest
         }
     }
     __syncthreads();
-    const float2 *res = lcfft::stockham_pow2(sm, M, log2M, per_cta, +1.0f);
-    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
-        const unsigned long long f = first + i / M;
-        if (f < n_frames) y[f * M + (i % M)] = lcfft::fft_post(res[lcfft::pidx(i)], 1, (float)M, 1.0f);
-    }
+    const FrameDst dst{y, M, first, n_frames, 1, (float)M};
+    lcfft::stockham_run<+1>(sm, M, log2M, per_cta, lcfft::SmemSrc{sm.buf0, log2M}, dst);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -184,8 +195,8 @@ pfbch_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, 
         X[gid] = pfbch_mac_elem<TapT>(hist, x, H, taps, M, p, phase, first, k, (long long)(gid / M), (unsigned int)(gid % M));
 }
 
-// firpfbch analyzer for power-of-two M in ONE kernel (see pfbch2_analyze_pow2_kernel): MAC into shared
-// memory, forward Stockham FFT there, unscaled store
+// firpfbch analyzer for power-of-two M in ONE kernel (see pfbch2_analyze_pow2_kernel): MAC into shared memory,
+// forward Stockham FFT there, unscaled store by the last pass
 template <typename TapT>
 __global__ void __launch_bounds__(lcfft::kFftThreads)
 pfbch_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
@@ -197,7 +208,6 @@ pfbch_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restr
     const lcfft::Smem sm = lcfft::carve(smem_f2, M, per_cta);
     lcfft::stage_twiddles(sm, tw, M);
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
-    const unsigned int total = per_cta * M;
     {
         // fill: thread = (transform input u, frame lane).  The window branch M-1-u reads and the offset d of its
         // newest sample do not depend on the run index (C = phase + first + s M is congruent mod M for all s),
@@ -232,11 +242,8 @@ pfbch_analyze_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restr
         }
     }
     __syncthreads();
-    const float2 *res = lcfft::stockham_pow2(sm, M, log2M, per_cta, -1.0f);
-    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
-        const unsigned long long f = first + i / M;
-        if (f < n_frames) y[f * M + (i % M)] = res[lcfft::pidx(i)];
-    }
+    const FrameDst dst{y, M, first, n_frames, 0, 1.0f};
+    lcfft::stockham_run<-1>(sm, M, log2M, per_cta, lcfft::SmemSrc{sm.buf0, log2M}, dst);
 }
 
 template <typename TapT>

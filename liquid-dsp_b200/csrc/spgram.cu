@@ -63,6 +63,40 @@ struct Segs {
     }
 };
 
+// first-pass source of the periodogram transforms: element k of transform t is the tapered sample (zero beyond
+// the window), read straight into the butterfly's registers                              spgram.c:233-237
+struct TaperSrc {
+    const float2 *hist, *x;
+    const float *w;
+    int H;
+    unsigned int window_len;
+    Segs segs;
+    unsigned long long t0, t_end;          // transform t0 + f, valid below t_end
+    __device__ __forceinline__ float2 operator()(unsigned int f, unsigned int k) const
+    {
+        const unsigned long long t = t0 + f;
+        if (t >= t_end || k >= window_len) return make_float2(0.f, 0.f);
+        const float2 s = ld_sample(hist, x, segs.end_of(t) - (long long)(window_len - 1) + k, H);
+        const float c = __ldg(w + k);
+        return make_float2(s.x * c, s.y * c);
+    }
+};
+
+// last-pass destination of spgram_transform_pow2_kernel: |X|^2 (MODE 0) or X (MODE 1) to global memory
+template <int MODE>
+struct SpectrumDst {
+    void *out;
+    unsigned int nfft;
+    unsigned long long t0, t_end;
+    __device__ __forceinline__ void operator()(unsigned int f, unsigned int k, float2 X) const
+    {
+        const unsigned long long t = t0 + f;
+        if (t >= t_end) return;
+        if (MODE == 0) reinterpret_cast<float *>(out)[t * nfft + k] = X.x * X.x + X.y * X.y;
+        else           reinterpret_cast<float2 *>(out)[t * nfft + k] = X;
+    }
+};
+
 // power-of-two nfft: taper, transform and |X|^2 (MODE 0 -> float out) or X (MODE 1 -> float2 out) in one kernel
 template <int MODE>
 __global__ void __launch_bounds__(lcfft::kFftThreads)
@@ -73,36 +107,18 @@ spgram_transform_pow2_kernel(const float2 *__restrict__ hist, const float2 *__re
 {
     extern __shared__ float2 smem_f2[];
     const lcfft::Smem sm = lcfft::carve(smem_f2, nfft, per_cta);
-    lcfft::stage_twiddles(sm, tw, nfft);
+    if (log2n > 4) lcfft::stage_twiddles(sm, tw, nfft);
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
-    const unsigned int total = per_cta * nfft;
-    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
-        const unsigned long long t = first + i / nfft;
-        const unsigned int k = i % nfft;
-        float2 v = make_float2(0.f, 0.f);
-        if (t < T && k < window_len) {
-            const float2 s = ld_sample(hist, x, segs.end_of(t) - (long long)(window_len - 1) + k, H);
-            const float c = __ldg(w + k);
-            v = make_float2(s.x * c, s.y * c);                       // rc[i] * w[i]   (spgram.c:236-237)
-        }
-        sm.buf0[lcfft::pidx(i)] = v;
-    }
-    __syncthreads();
-    const float2 *res = lcfft::stockham_pow2(sm, nfft, log2n, per_cta, -1.0f);
-    for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
-        const unsigned long long t = first + i / nfft;
-        if (t >= T) continue;
-        const float2 X = res[lcfft::pidx(i)];
-        if (MODE == 0) reinterpret_cast<float *>(out)[t * nfft + (i % nfft)] = X.x * X.x + X.y * X.y;
-        else           reinterpret_cast<float2 *>(out)[t * nfft + (i % nfft)] = X;
-    }
+    const TaperSrc src{hist, x, w, H, window_len, segs, first, T};
+    const SpectrumDst<MODE> dst{out, nfft, first, T};
+    lcfft::stockham_run<-1>(sm, nfft, log2n, per_cta, src, dst);
 }
 
 // power-of-two nfft, the throughput path of accumulate_psd / estimate_psd: CTA c walks the `tpc` consecutive
-// transforms [c tpc, (c+1) tpc) -- taper into shared memory, Stockham FFT, and the fold of |X|^2 into per-thread
-// register accumulators (bins tid, tid+256, ...) in transform order -- and leaves ONE partial spectrum; neither
-// the tapered segments nor the T spectra ever visit HBM.  Consecutive transforms overlap by 50-75 % of their
-// input, which L1/L2 serve.
+// transforms [c tpc, (c+1) tpc) -- tapered samples straight into the first FFT pass's registers, Stockham passes
+// in shared memory, and the fold of |X|^2 into per-thread register accumulators (bins tid, tid+256, ...) in
+// transform order -- and leaves ONE partial spectrum; neither the tapered segments nor the T spectra ever visit
+// HBM.  Consecutive transforms overlap by 50-75 % of their input, which L1/L2 serve.
 __global__ void __launch_bounds__(lcfft::kFftThreads)
 spgram_accumulate_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
                               const float *__restrict__ w, unsigned int window_len, const float2 *__restrict__ tw,
@@ -124,21 +140,10 @@ spgram_accumulate_pow2_kernel(const float2 *__restrict__ hist, const float2 *__r
         acc[b] = (seed_psd && blockIdx.x == 0 && k < nfft) ? psd[k] : 0.0f;
     }
     const float keep = 1.0f - alpha;
-    const unsigned int total = per_cta * nfft;
+    __syncthreads();                                                   // twiddle table staged
     for (unsigned long long g0 = t_begin; g0 < t_end; g0 += per_cta) {
-        for (unsigned int i = threadIdx.x; i < total; i += blockDim.x) {
-            const unsigned long long t = g0 + i / nfft;
-            const unsigned int k = i % nfft;
-            float2 v = make_float2(0.f, 0.f);
-            if (t < t_end && k < window_len) {
-                const float2 sv = ld_sample(hist, x, segs.end_of(t) - (long long)(window_len - 1) + k, H);
-                const float c = __ldg(w + k);
-                v = make_float2(sv.x * c, sv.y * c);
-            }
-            sm.buf0[lcfft::pidx(i)] = v;
-        }
-        __syncthreads();
-        const float2 *res = lcfft::stockham_pow2(sm, nfft, log2n, per_cta, -1.0f);
+        const TaperSrc src{hist, x, w, H, window_len, segs, g0, t_end};
+        const float2 *res = lcfft::stockham_run_to_smem<-1>(sm, nfft, log2n, per_cta, src);
         for (unsigned int tt = 0; tt < per_cta && g0 + tt < t_end; tt++) {
 #pragma unroll
             for (int b = 0; b < kMaxBins; b++) {
@@ -150,7 +155,7 @@ spgram_accumulate_pow2_kernel(const float2 *__restrict__ hist, const float2 *__r
                 }
             }
         }
-        __syncthreads();                                               // the buffers are refilled next
+        __syncthreads();                                               // the buffers are rewritten next
     }
 #pragma unroll
     for (int b = 0; b < kMaxBins; b++) {
