@@ -6,6 +6,7 @@
 // pfbch2_fused.cu, which keep the sliding windows in registers.
 #include "pfb_kernels.cuh"
 #include "fft_device.cuh"
+#include "fused_common.cuh"
 
 namespace {
 
@@ -157,6 +158,78 @@ pfbch2_synth_fir_kernel(const float2 *__restrict__ hist, const float2 *__restric
     }
 }
 
+// firpfbch2 synthesis FIR with the rows of v kept in registers (power-of-two-ish shapes: M/2 a multiple of 128,
+// NT = 4m taps per output in {8, 16, 20, 28}: 4 NT registers of state + NT taps).  Thread i owns output column i: the last NT values of
+// v[.][i] and of v[.][i + M/2] live in two circular register buffers and the NT taps h[i + q M/2] beside them;
+// per frame it loads two new values (coalesced rows), does NT packed FFMA2 and stores one output.  A CTA walks
+// a chunk of frames that starts on a multiple of NT, so that -- one period of NT frames fully unrolled -- every
+// buffer slot index is a compile-time constant; the chunk's first NT-1 rows of history come from v itself (or
+// from the object's state in front of frame 0).  Each row of v is read from HBM once instead of 4m times
+// through L2.  Same summation order as pfbch2_synth_fir_kernel (even and odd taps apart), so the results are
+// bit-identical to it.
+template <int NT, int PAR0>
+__global__ void __launch_bounds__(128)
+pfbch2_synth_fir_reg_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ v, int hist_rows,
+                            const float *__restrict__ taps, float2 *__restrict__ y, unsigned int M,
+                            unsigned long long n_frames, unsigned int frames_per_chunk)
+{
+    using namespace lcf;
+    const unsigned int M2 = M >> 1;
+    const unsigned int i = blockIdx.x * 128 + threadIdx.x;            // output column, < M2 by construction
+    const long long t0 = (long long)blockIdx.y * frames_per_chunk;    // multiple of NT (hence even)
+    long long t_end = t0 + frames_per_chunk;
+    if (t_end > (long long)n_frames) t_end = (long long)n_frames;
+    float h[NT];
+#pragma unroll
+    for (int q = 0; q < NT; q++) h[q] = __ldg(taps + (size_t)q * M2 + i);
+    float2 lo[NT], hi[NT];                                             // row r sits in slot r mod NT
+    auto row = [&](long long r) -> const float2 * {
+        return r >= 0 ? v + (size_t)r * M : hist + (size_t)(hist_rows + r) * M;
+    };
+#pragma unroll
+    for (int s = 1; s < NT; s++) {                                     // rows t0 - NT + s, s = 1 .. NT-1
+        const float2 *p = row(t0 - NT + s);
+        lo[s] = __ldg(p + i);
+        hi[s] = __ldg(p + i + M2);
+    }
+    lo[0] = hi[0] = make_float2(0.f, 0.f);
+    for (long long tp = t0; tp < t_end; tp += NT) {
+#pragma unroll
+        for (int tt = 0; tt < NT; tt++) {
+            const long long t = tp + tt;
+            if (t >= t_end) break;                                     // uniform: tail of the last period
+            const float2 *p = v + (size_t)t * M;
+            lo[tt] = __ldg(p + i);
+            hi[tt] = __ldg(p + i + M2);
+            const bool odd = ((PAR0 + tt) & 1) != 0;                   // t0 and NT are even
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < NT; q++) {
+                const float2 sv = odd ? hi[(tt - q + NT) % NT] : lo[(tt - q + NT) % NT];
+                if (q & 1) a1 = __ffma2_rn(bc(h[q]), sv, a1);
+                else       a0 = __ffma2_rn(bc(h[q]), sv, a0);
+            }
+            y[(size_t)t * M2 + i] = __fadd2_rn(a0, a1);
+        }
+    }
+}
+
+template <int NT>
+bool launch_synth_fir_reg(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float *d_taps, float2 *d_y,
+                          unsigned int M, unsigned long long n_frames, int parity0, cudaStream_t st)
+{
+    const unsigned int fpc = NT * ((256 + NT - 1) / NT);               // frames per chunk: a multiple of NT near 256
+    const unsigned long long chunks = (n_frames + fpc - 1) / fpc;
+    if (chunks > 65535) return false;                                  // grid.y limit: the caller falls back
+    dim3 grid((M / 2) / 128, (unsigned int)chunks);
+    if (parity0 & 1)
+        pfbch2_synth_fir_reg_kernel<NT, 1><<<grid, 128, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, fpc);
+    else
+        pfbch2_synth_fir_reg_kernel<NT, 0><<<grid, 128, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, fpc);
+    LC_LAUNCH_CHECK();
+    return true;
+}
+
 // transform input u of run s of the firpfbch analyzer (M pushes per run, alignment index k)  firpfbch.c:369-409
 template <typename TapT>
 __device__ __forceinline__ float2 pfbch_mac_elem(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
@@ -291,6 +364,18 @@ void launch_pfbch2_synth_fir(const float2 *d_hist_rows, const float2 *d_v, int h
                              float2 *d_y, unsigned int M, unsigned int n_taps, unsigned long long n_frames,
                              int parity0, cudaStream_t st)
 {
+    // register-window kernel for the shapes it is instantiated for (needs >= n_taps - 1 rows of history)
+    if ((M / 2) % 128 == 0 && hist_rows >= (int)n_taps - 1 && n_frames >= 64 && !getenv("LIQUID_CUDA_NO_FUSED")) {
+        bool done = false;
+        switch (n_taps) {
+        case 8: done = launch_synth_fir_reg<8>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
+        case 16: done = launch_synth_fir_reg<16>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
+        case 20: done = launch_synth_fir_reg<20>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
+        case 28: done = launch_synth_fir_reg<28>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
+        default: break;
+        }
+        if (done) return;
+    }
     pfbch2_synth_fir_kernel<<<grid_for(n_frames * (M / 2)), kThreads, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y,
                                                                               M, n_taps, n_frames, parity0);
     LC_LAUNCH_CHECK();

@@ -115,6 +115,21 @@ def test_pfbch2_synthesis_vs_oracle(L, orc, M, m, nfr):
     assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
 
 
+@pytest.mark.parametrize("M,m,nfr,cut", [(256, 2, 333, 65), (256, 4, 700, 128), (1024, 5, 301, 77),
+                                          (1024, 7, 520, 260), (1024, 9, 200, 100)])
+def test_pfbch2_synthesis_register_window_vs_oracle(L, orc, M, m, nfr, cut):
+    """long blocks take the register-window synthesis FIR (pfb_kernels.cu, 4m in {8,16,20,28}; m=9 stays on
+    the generic kernel): odd and even starting parity, state carried across blocks, ragged chunk tail"""
+    X = orc.synth_input(nfr * M, seed=0xC0 + M + m)
+    want = orc.Firpfbch2(orc.SYNTHESIZER, M, m, As=60.0).execute_frames(X)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+    got = np.concatenate([q.execute_block(X[:cut * M]), q.execute_block(X[cut * M:])])
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+    q.reset()
+    one = q.execute_block(X)
+    assert np.abs(one - got).max() / np.abs(want).max() < 2e-6
+
+
 def test_pfbch2_large_block_linearity_and_time_invariance(L, orc):
     """size-independent properties at a large size (2^22 samples, M=1024, m=7): linearity, and
     invariance to a shift by a whole number of frame pairs once the history is flushed"""

@@ -129,6 +129,26 @@ def main():
             ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
             report("c5m: firpfbch2_crcf analysis M=4096 m=%d, 2^29 samples" % m, n, 24, ms, ln)
             del x, y
+    if "s" in args.configs:
+        # synthesizers (a4, a6): firpfbch2 M=1024 m=7 (2^27 output samples) and firpfbch M=1024 m=2 / M=256 m=5
+        M, m, n = 1024, 7, 1 << 27                      # n = output samples; input = 2 n channel samples
+        q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+        X = torch.empty(4 * n, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        L.synth_input_dev(X.data_ptr(), 2 * n, stream=st.cuda_stream)
+        ms, ln = timed(lambda: q.execute_block_dev(X.data_ptr(), n // (M // 2), y.data_ptr(), st.cuda_stream))
+        report("s: firpfbch2_crcf synthesis M=1024 m=7, 2^27 output samples", n, 24, ms, ln,
+               {"note": "throughput in OUTPUT samples/s; algorithmic bytes 16 in + 8 out per output sample"})
+        del X, y
+        for M, m in ((1024, 2), (256, 5)):
+            n = 1 << 27
+            q = L.firpfbch_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+            X = torch.empty(2 * n, dtype=torch.float32, device=dev)
+            y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+            L.synth_input_dev(X.data_ptr(), n, stream=st.cuda_stream)
+            ms, ln = timed(lambda: q.execute_block_dev(X.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
+            report("s: firpfbch_crcf synthesis M=%d m=%d, 2^27 samples (one stream, stateful)" % (M, m), n, 16, ms, ln)
+            del X, y
     if "g" in args.configs:
         # shapes without a dedicated fused kernel: the one-kernel shape-generic analyzers (power-of-two M)
         for M, m, n in ((256, 4, 1 << 27), (64, 5, 1 << 27), (2048, 3, 1 << 27)):
