@@ -168,7 +168,7 @@ pfbch2_synth_fir_kernel(const float2 *__restrict__ hist, const float2 *__restric
 // through L2.  Same summation order as pfbch2_synth_fir_kernel (even and odd taps apart), so the results are
 // bit-identical to it.
 template <int NT, int PAR0>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, NT > 16 ? 2 : 3)
 pfbch2_synth_fir_reg_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ v, int hist_rows,
                             const float *__restrict__ taps, float2 *__restrict__ y, unsigned int M,
                             unsigned long long n_frames, unsigned int frames_per_chunk)
@@ -186,6 +186,22 @@ pfbch2_synth_fir_reg_kernel(const float2 *__restrict__ hist, const float2 *__res
     auto row = [&](long long r) -> const float2 * {
         return r >= 0 ? v + (size_t)r * M : hist + (size_t)(hist_rows + r) * M;
     };
+    // thread-private prefetch ring in shared memory: slot tt holds the (lo, hi) pair of frame tp + tt for this
+    // thread's column, fetched kAhead frames early by cp.async; only the owning thread touches its slots, so
+    // cp.async.wait_group is the only synchronisation
+    extern __shared__ float2 s_ring[];                                  // [NT][2][128]
+    constexpr int kAhead = NT - 2;
+    const unsigned int ring = (unsigned int)__cvta_generic_to_shared(s_ring) + threadIdx.x * 8u;
+    auto fetch = [&](long long t, int slot) {
+        if (t < t_end) {
+            const float2 *p = v + (size_t)t * M + i;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ring + (unsigned int)slot * 2048u), "l"(p) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ring + (unsigned int)slot * 2048u + 1024u), "l"(p + M2) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < kAhead; s++) fetch(t0 + s, s);
 #pragma unroll
     for (int s = 1; s < NT; s++) {                                     // rows t0 - NT + s, s = 1 .. NT-1
         const float2 *p = row(t0 - NT + s);
@@ -198,9 +214,10 @@ pfbch2_synth_fir_reg_kernel(const float2 *__restrict__ hist, const float2 *__res
         for (int tt = 0; tt < NT; tt++) {
             const long long t = tp + tt;
             if (t >= t_end) break;                                     // uniform: tail of the last period
-            const float2 *p = v + (size_t)t * M;
-            lo[tt] = __ldg(p + i);
-            hi[tt] = __ldg(p + i + M2);
+            fetch(t + kAhead, (tt + kAhead) % NT);
+            asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");
+            lo[tt] = s_ring[tt * 256 + threadIdx.x];
+            hi[tt] = s_ring[tt * 256 + 128 + threadIdx.x];
             const bool odd = ((PAR0 + tt) & 1) != 0;                   // t0 and NT are even
             float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -212,6 +229,7 @@ pfbch2_synth_fir_reg_kernel(const float2 *__restrict__ hist, const float2 *__res
             y[(size_t)t * M2 + i] = __fadd2_rn(a0, a1);
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 template <int NT>
@@ -222,10 +240,16 @@ bool launch_synth_fir_reg(const float2 *d_hist_rows, const float2 *d_v, int hist
     const unsigned long long chunks = (n_frames + fpc - 1) / fpc;
     if (chunks > 65535) return false;                                  // grid.y limit: the caller falls back
     dim3 grid((M / 2) / 128, (unsigned int)chunks);
+    constexpr size_t smem = (size_t)NT * 2048;                         // the prefetch ring
+    static std::atomic<unsigned long long> configured{0};
+    if (smem > 48 * 1024 && lc::first_time_on_device(configured)) {
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_synth_fir_reg_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_synth_fir_reg_kernel<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (parity0 & 1)
-        pfbch2_synth_fir_reg_kernel<NT, 1><<<grid, 128, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, fpc);
+        pfbch2_synth_fir_reg_kernel<NT, 1><<<grid, 128, smem, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, fpc);
     else
-        pfbch2_synth_fir_reg_kernel<NT, 0><<<grid, 128, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, fpc);
+        pfbch2_synth_fir_reg_kernel<NT, 0><<<grid, 128, smem, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, fpc);
     LC_LAUNCH_CHECK();
     return true;
 }
