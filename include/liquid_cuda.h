@@ -96,6 +96,32 @@ void firinterp_crcf_reset(firinterp_crcf _q);
 void firinterp_crcf_execute(firinterp_crcf _q, liquid_float_complex _x, liquid_float_complex *_y);
 void firinterp_crcf_execute_block(firinterp_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
 
+/* ---- resamp2_crcf (half-band filter / 2:1 resamplers): liquid.h:2840-2925 -> src/filter/src/resamp2.c:65-359;
+ *      msresamp2_crcf (2^S cascades): liquid.h:3022-3080 -> src/filter/src/msresamp2.c:82-354;
+ *      estimate_req_filter_len: liquid.h:1500 -> src/filter/src/firdes.c:52-75.  SURVEY.md 8(f) item 3. */
+#define LIQUID_RESAMP_INTERP 0      /* enum liquid_resamp_type, liquid.h:3022-3025 */
+#define LIQUID_RESAMP_DECIM  1
+unsigned int estimate_req_filter_len(float _df, float _As);
+typedef struct resamp2_crcf_s * resamp2_crcf;
+resamp2_crcf resamp2_crcf_create(unsigned int _m, float _f0, float _As);
+resamp2_crcf resamp2_crcf_recreate(resamp2_crcf _q, unsigned int _m, float _f0, float _As);
+void resamp2_crcf_destroy(resamp2_crcf _q);
+void resamp2_crcf_print(resamp2_crcf _q);
+void resamp2_crcf_clear(resamp2_crcf _q);
+unsigned int resamp2_crcf_get_delay(resamp2_crcf _q);
+void resamp2_crcf_filter_execute(resamp2_crcf _q, liquid_float_complex _x, liquid_float_complex *_y0, liquid_float_complex *_y1);
+void resamp2_crcf_analyzer_execute(resamp2_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+void resamp2_crcf_synthesizer_execute(resamp2_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+void resamp2_crcf_decim_execute(resamp2_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+void resamp2_crcf_interp_execute(resamp2_crcf _q, liquid_float_complex _x, liquid_float_complex *_y);
+typedef struct msresamp2_crcf_s * msresamp2_crcf;
+msresamp2_crcf msresamp2_crcf_create(int _type, unsigned int _num_stages, float _fc, float _f0, float _As);
+void msresamp2_crcf_destroy(msresamp2_crcf _q);
+void msresamp2_crcf_print(msresamp2_crcf _q);
+void msresamp2_crcf_reset(msresamp2_crcf _q);
+float msresamp2_crcf_get_delay(msresamp2_crcf _q);
+void msresamp2_crcf_execute(msresamp2_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+
 /* ---- spgramcf (windowed-FFT spectral periodogram): liquid.h:1230-1316 -> src/fft/src/spgramcf.c -> spgram.c:57-398.
  *      SURVEY.md 8(f) item 2. */
 typedef struct spgramcf_s * spgramcf;
@@ -273,6 +299,27 @@ void firpfbch_crcf_set_state(firpfbch_crcf _q, const liquid_float_complex *_hist
 /* ---- firdecim_crcf / firinterp_crcf: device-pointer forms (_n = outputs for firdecim, inputs for firinterp) ---- */
 void firdecim_crcf_execute_block_dev(firdecim_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
 void firinterp_crcf_execute_block_dev(firinterp_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
+
+/* ---- resamp2_crcf / msresamp2_crcf: block forms over _n units (filter: samples; analyzer / synthesizer: pairs in,
+ *      pairs out; decim: outputs from 2 _n inputs; interp: inputs giving 2 _n outputs; msresamp2: _n inputs giving
+ *      _n 2^S outputs, or _n outputs from _n 2^S inputs), host and device pointers; get_taps copies the 4m+1 tap
+ *      prototype and / or the 2m filter-branch taps (either pointer may be NULL) ---- */
+void resamp2_crcf_get_taps(resamp2_crcf _q, float *_h, float *_h1);
+void resamp2_crcf_filter_execute_block(resamp2_crcf _q, liquid_float_complex *_x, unsigned int _n,
+                                       liquid_float_complex *_y0, liquid_float_complex *_y1);
+void resamp2_crcf_analyzer_execute_block(resamp2_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+void resamp2_crcf_synthesizer_execute_block(resamp2_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+void resamp2_crcf_decim_execute_block(resamp2_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+void resamp2_crcf_interp_execute_block(resamp2_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+void resamp2_crcf_filter_execute_block_dev(resamp2_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y0,
+                                           void *_d_y1, void *_stream);
+void resamp2_crcf_analyzer_execute_block_dev(resamp2_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
+void resamp2_crcf_synthesizer_execute_block_dev(resamp2_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
+void resamp2_crcf_decim_execute_block_dev(resamp2_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
+void resamp2_crcf_interp_execute_block_dev(resamp2_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
+unsigned int msresamp2_crcf_get_stage_semilength(msresamp2_crcf _q, unsigned int _i);
+void msresamp2_crcf_execute_block(msresamp2_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+void msresamp2_crcf_execute_block_dev(msresamp2_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
 
 /* ---- spgramcf: device-pointer forms (the whole block becomes one batch of overlapping transforms) ---- */
 void spgramcf_accumulate_psd_dev(spgramcf _q, const void *_d_x, float _alpha, unsigned long long _n, void *_stream);

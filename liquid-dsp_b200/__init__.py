@@ -105,6 +105,33 @@ _sig("firinterp_crcf_destroy", None, _vp)
 _sig("firinterp_crcf_print", None, _vp)
 _sig("firinterp_crcf_reset", None, _vp)
 _sig("firinterp_crcf_execute", None, _vp, _cf, _cf_p)
+_sig("estimate_req_filter_len", _u, _fl, _fl)
+_sig("resamp2_crcf_create", _vp, _u, _fl, _fl)
+_sig("resamp2_crcf_recreate", _vp, _vp, _u, _fl, _fl)
+_sig("resamp2_crcf_destroy", None, _vp)
+_sig("resamp2_crcf_print", None, _vp)
+_sig("resamp2_crcf_clear", None, _vp)
+_sig("resamp2_crcf_get_delay", _u, _vp)
+_sig("resamp2_crcf_get_taps", None, _vp, _vp, _vp)
+_sig("resamp2_crcf_filter_execute", None, _vp, _cf, _cf_p, _cf_p)
+_sig("resamp2_crcf_analyzer_execute", None, _vp, _cf_p, _cf_p)
+_sig("resamp2_crcf_synthesizer_execute", None, _vp, _cf_p, _cf_p)
+_sig("resamp2_crcf_decim_execute", None, _vp, _cf_p, _cf_p)
+_sig("resamp2_crcf_interp_execute", None, _vp, _cf, _cf_p)
+_sig("resamp2_crcf_filter_execute_block", None, _vp, _vp, _u, _vp, _vp)
+_sig("resamp2_crcf_filter_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp, _vp)
+for _nm in ("analyzer", "synthesizer", "decim", "interp"):
+    _sig("resamp2_crcf_%s_execute_block" % _nm, None, _vp, _vp, _u, _vp)
+    _sig("resamp2_crcf_%s_execute_block_dev" % _nm, None, _vp, _vp, _ull, _vp, _vp)
+_sig("msresamp2_crcf_create", _vp, _i, _u, _fl, _fl, _fl)
+_sig("msresamp2_crcf_destroy", None, _vp)
+_sig("msresamp2_crcf_print", None, _vp)
+_sig("msresamp2_crcf_reset", None, _vp)
+_sig("msresamp2_crcf_get_delay", _fl, _vp)
+_sig("msresamp2_crcf_get_stage_semilength", _u, _vp, _u)
+_sig("msresamp2_crcf_execute", None, _vp, _cf_p, _cf_p)
+_sig("msresamp2_crcf_execute_block", None, _vp, _vp, _u, _vp)
+_sig("msresamp2_crcf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
 _sig("firinterp_crcf_execute_block", None, _vp, _vp, _u, _vp)
 _sig("firinterp_crcf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
 _sig("spgramcf_create", _vp, _u, _f_p, _u)
@@ -497,6 +524,138 @@ class firdecim_crcf(_Handle):
 
     def execute_block_dev(self, d_x, n, d_y, stream=0):
         lib.firdecim_crcf_execute_block_dev(self._h, d_x, n, d_y, stream)
+
+
+LIQUID_RESAMP_INTERP, LIQUID_RESAMP_DECIM = 0, 1
+
+
+class resamp2_crcf(_Handle):
+    """liquid.h:2840-2925 (src/filter/src/resamp2.c): half-band filter, analysis / synthesis pair, 2:1 decimator,
+    1:2 interpolator.  The *_block methods run n units in one kernel."""
+    _destroy = "resamp2_crcf_destroy"
+
+    def __init__(self, m, f0=0.0, As=60.0):
+        self.m = m
+        super().__init__(lib.resamp2_crcf_create(m, f0, As))
+
+    @classmethod
+    def create(cls, m, f0, As):
+        return cls(m, f0, As)
+
+    def recreate(self, m, f0, As):
+        self._h = lib.resamp2_crcf_recreate(self._h, m, f0, As)
+        self.m = m
+        return self
+
+    def clear(self):
+        lib.resamp2_crcf_clear(self._h)
+
+    def get_delay(self):
+        return lib.resamp2_crcf_get_delay(self._h)
+
+    def get_taps(self):
+        h = np.empty(4 * self.m + 1, np.float32)
+        h1 = np.empty(2 * self.m, np.float32)
+        lib.resamp2_crcf_get_taps(self._h, _ptr(h), _ptr(h1))
+        return h, h1
+
+    def filter_execute(self, v):
+        v = complex(v)
+        y0 = np.empty(1, np.complex64); y1 = np.empty(1, np.complex64)
+        lib.resamp2_crcf_filter_execute(self._h, _cf(v.real, v.imag), y0, y1)
+        return y0[0], y1[0]
+
+    def analyzer_execute(self, x):
+        y = np.empty(2, np.complex64)
+        lib.resamp2_crcf_analyzer_execute(self._h, _c64(x), y)
+        return y
+
+    def synthesizer_execute(self, x):
+        y = np.empty(2, np.complex64)
+        lib.resamp2_crcf_synthesizer_execute(self._h, _c64(x), y)
+        return y
+
+    def decim_execute(self, x):
+        y = np.empty(1, np.complex64)
+        lib.resamp2_crcf_decim_execute(self._h, _c64(x), y)
+        return y[0]
+
+    def interp_execute(self, v):
+        v = complex(v)
+        y = np.empty(2, np.complex64)
+        lib.resamp2_crcf_interp_execute(self._h, _cf(v.real, v.imag), y)
+        return y
+
+    def filter_execute_block(self, x):
+        x = _c64(x)
+        y0 = np.empty(x.size, np.complex64); y1 = np.empty(x.size, np.complex64)
+        lib.resamp2_crcf_filter_execute_block(self._h, _ptr(x), x.size, _ptr(y0), _ptr(y1))
+        return y0, y1
+
+    def _block(self, name, x, n, n_out):
+        y = np.empty(n_out, np.complex64)
+        getattr(lib, "resamp2_crcf_%s_execute_block" % name)(self._h, _ptr(x), n, _ptr(y))
+        return y
+
+    def analyzer_execute_block(self, x):
+        x = _c64(x)
+        return self._block("analyzer", x, x.size // 2, x.size // 2 * 2)
+
+    def synthesizer_execute_block(self, x):
+        x = _c64(x)
+        return self._block("synthesizer", x, x.size // 2, x.size // 2 * 2)
+
+    def decim_execute_block(self, x):
+        x = _c64(x)
+        return self._block("decim", x, x.size // 2, x.size // 2)
+
+    def interp_execute_block(self, x):
+        x = _c64(x)
+        return self._block("interp", x, x.size, 2 * x.size)
+
+    def execute_block_dev(self, mode, d_x, n, d_y, stream=0, d_y1=None):
+        if mode == "filter":
+            lib.resamp2_crcf_filter_execute_block_dev(self._h, d_x, n, d_y, d_y1, stream)
+        else:
+            getattr(lib, "resamp2_crcf_%s_execute_block_dev" % mode)(self._h, d_x, n, d_y, stream)
+
+
+class msresamp2_crcf(_Handle):
+    """liquid.h:3027-3080 (src/filter/src/msresamp2.c): cascade of half-band stages, rate 2^num_stages."""
+    _destroy = "msresamp2_crcf_destroy"
+
+    def __init__(self, type, num_stages, fc, f0, As):
+        self.type, self.num_stages, self.M = type, num_stages, 1 << num_stages
+        super().__init__(lib.msresamp2_crcf_create(type, num_stages, fc, f0, As))
+
+    @classmethod
+    def create(cls, type, num_stages, fc, f0, As):
+        return cls(type, num_stages, fc, f0, As)
+
+    def reset(self):
+        lib.msresamp2_crcf_reset(self._h)
+
+    def get_delay(self):
+        return lib.msresamp2_crcf_get_delay(self._h)
+
+    def stage_semilengths(self):
+        return [lib.msresamp2_crcf_get_stage_semilength(self._h, i) for i in range(self.num_stages)]
+
+    def execute(self, x):
+        y = np.empty(self.M if self.type == LIQUID_RESAMP_INTERP else 1, np.complex64)
+        lib.msresamp2_crcf_execute(self._h, _c64(x), y)
+        return y
+
+    def execute_block(self, x):
+        x = _c64(x)
+        interp = self.type == LIQUID_RESAMP_INTERP
+        n = x.size if interp else x.size // self.M
+        y = np.empty(n * self.M if interp else n, np.complex64)
+        lib.msresamp2_crcf_execute_block(self._h, _ptr(x), n, _ptr(y))
+        return y
+
+    def execute_block_dev(self, d_x, n, d_y, stream=0):
+        lib.msresamp2_crcf_execute_block_dev(self._h, d_x, n, d_y, stream)
 
 
 class firinterp_crcf(_Handle):

@@ -63,6 +63,10 @@ float kaiser_(unsigned int n, unsigned int N, float beta, float mu)
 namespace lc {
 
 float kaiser_window(unsigned int n, unsigned int N, float beta, float mu) { return kaiser_(n, N, beta, mu); }
+float sinc_value(float x) { return sincf_(x); }
+
+// Kaiser's length estimate (the reference build's method 0)                           firdes.c:52-75, :163-176
+unsigned int estimate_req_filter_len(float df, float As) { return (unsigned int)((As - 7.95f) / (14.26f * df)); }
 
 float kaiser_beta_As(float As)
 {
@@ -317,6 +321,13 @@ void rnyquist_fatal(const char *fn, int rc)
 
 // ---- C ABI: liquid.h:1463, :1583, :1586, :1664 ----
 extern "C" float estimate_req_filter_As(float _df, unsigned int _N) { return lc::estimate_req_filter_As(_df, _N); }
+
+extern "C" unsigned int estimate_req_filter_len(float _df, float _As)
+{
+    if (_df > 0.5f || _df <= 0.0f) lc::fatal("estimate_req_filter_len", "invalid bandwidth");
+    if (_As <= 0.0f) lc::fatal("estimate_req_filter_len", "invalid stopband level");
+    return lc::estimate_req_filter_len(_df, _As);
+}
 
 extern "C" void liquid_filter_isi(float *_h, unsigned int _k, unsigned int _m, float *_rms, float *_max)
 {

@@ -108,6 +108,8 @@ float kaiser_window(unsigned int n, unsigned int N, float beta, float mu);   // 
 int firdes_kaiser(unsigned int n, float fc, float As, float mu, float *h);   // 0 ok, else message id
 int firdes_rrcos(unsigned int k, unsigned int m, float beta, float dt, float *h);
 float estimate_req_filter_As(float df, unsigned int N);
+unsigned int estimate_req_filter_len(float df, float As);                   // firdes.c:52-75
+float sinc_value(float x);                                                   // sincf(), src/math/src/math.c:128-139
 void filter_isi(const float *h, unsigned int k, unsigned int m, float *rms, float *peak);
 float rkaiser_approximate_rho(unsigned int m, float beta);
 int firdes_arkaiser(unsigned int k, unsigned int m, float beta, float dt, float *h);          // 0 ok, else message id

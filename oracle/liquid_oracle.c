@@ -915,6 +915,211 @@ void orc_firinterp_execute_block(orc_firinterp q, const orc_cf *x, unsigned int 
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* resamp2_crcf / msresamp2_crcf: half-band filter, 2:1 resamplers    */
+/* and their 2^S cascades.  src/filter/src/resamp2.c, msresamp2.c                           */
+/* ------------------------------------------------------------------------------------ */
+
+struct orc_resamp2_s {
+    unsigned int m, len;        /* len = 2m taps on the filter branch */
+    float *hb;                  /* filter-branch taps, lined up with an oldest-first window */
+    orc_cf *w0, *w1;            /* delay-branch and filter-branch windows, len samples each */
+    unsigned int toggle;
+};
+
+/* firdes.c:52-75 (Kaiser's estimate, the build's method 0) */
+unsigned int orc_estimate_req_filter_len(float df, float As)
+{
+    return (unsigned int)((As - 7.95f) / (14.26f * df));
+}
+
+/* resamp2.c:65-123: 4m+1 tap prototype sinc(t/2) * kaiser * cos(2 pi f0 t); the filter branch keeps the
+ * odd-indexed taps, reversed */
+orc_resamp2 orc_resamp2_create(unsigned int m, float f0, float As)
+{
+    if (m < 2 || f0 < -0.5f || f0 > 0.5f) return NULL;
+    orc_resamp2 q = xmalloc(sizeof *q);
+    q->m = m; q->len = 2 * m;
+    unsigned int n = 4 * m + 1;
+    float *h = xmalloc(n * sizeof *h);
+    float beta = orc_kaiser_beta_As(As);
+    for (unsigned int i = 0; i < n; i++) {
+        float t = (float)i - (float)(n - 1) / 2.0f;
+        float a = orc_sincf(t / 2.0f);
+        float b = orc_kaiser(i, n, beta, 0);
+        float c = cosf(2.0f * M_PI * t * f0);
+        h[i] = a * b * c;
+    }
+    q->hb = xmalloc(q->len * sizeof *q->hb);
+    for (unsigned int j = 0, i = 1; i < n; i += 2) q->hb[j++] = h[n - i - 1];
+    free(h);
+    q->w0 = xmalloc(q->len * sizeof *q->w0);
+    q->w1 = xmalloc(q->len * sizeof *q->w1);
+    orc_resamp2_clear(q);
+    return q;
+}
+
+void orc_resamp2_destroy(orc_resamp2 q) { if (q) { free(q->hb); free(q->w0); free(q->w1); free(q); } }
+
+/* resamp2.c:209-215 */
+void orc_resamp2_clear(orc_resamp2 q)
+{
+    memset(q->w0, 0, q->len * sizeof *q->w0);
+    memset(q->w1, 0, q->len * sizeof *q->w1);
+    q->toggle = 0;
+}
+
+void orc_resamp2_get_taps(orc_resamp2 q, float *hb) { memcpy(hb, q->hb, q->len * sizeof *hb); }
+
+static orc_cf cf_add(orc_cf a, orc_cf b) { return cf(a.re + b.re, a.im + b.im); }
+static orc_cf cf_sub(orc_cf a, orc_cf b) { return cf(a.re - b.re, a.im - b.im); }
+static orc_cf cf_half(orc_cf a) { return cf(0.5f * a.re, 0.5f * a.im); }
+
+/* resamp2.c:228-264: n samples through the half-band filter -> low band y0[n], high band y1[n] */
+void orc_resamp2_filter_execute(orc_resamp2 q, const orc_cf *x, unsigned int n, orc_cf *y0, orc_cf *y1)
+{
+    for (unsigned int i = 0; i < n; i++) {
+        orc_cf *wp = q->toggle ? q->w1 : q->w0;     /* the window this sample joins; the other one is filtered */
+        orc_cf *wf = q->toggle ? q->w0 : q->w1;
+        win_push(wp, q->len, x[i]);
+        orc_cf d = wp[q->m - 1];
+        orc_cf f = dot_crcf(q->hb, wf, q->len);
+        q->toggle = 1 - q->toggle;
+        y0[i] = cf_half(cf_add(d, f));
+        y1[i] = cf_half(cf_sub(d, f));
+    }
+}
+
+/* resamp2.c:271-290: n input pairs -> n (low, high) pairs at half rate */
+void orc_resamp2_analyzer_execute(orc_resamp2 q, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    for (unsigned int i = 0; i < n; i++) {
+        win_push(q->w1, q->len, cf_half(x[2 * i]));
+        orc_cf f = dot_crcf(q->hb, q->w1, q->len);
+        win_push(q->w0, q->len, cf_half(x[2 * i + 1]));
+        orc_cf d = q->w0[q->m - 1];
+        y[2 * i] = cf_add(f, d);
+        y[2 * i + 1] = cf_sub(f, d);
+    }
+}
+
+/* resamp2.c:297-313 */
+void orc_resamp2_synthesizer_execute(orc_resamp2 q, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    for (unsigned int i = 0; i < n; i++) {
+        win_push(q->w0, q->len, cf_add(x[2 * i], x[2 * i + 1]));
+        y[2 * i] = q->w0[q->m - 1];
+        win_push(q->w1, q->len, cf_sub(x[2 * i], x[2 * i + 1]));
+        y[2 * i + 1] = dot_crcf(q->hb, q->w1, q->len);
+    }
+}
+
+/* resamp2.c:320-338: n outputs from 2n inputs */
+void orc_resamp2_decim_execute(orc_resamp2 q, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    for (unsigned int i = 0; i < n; i++) {
+        win_push(q->w1, q->len, x[2 * i]);
+        orc_cf f = dot_crcf(q->hb, q->w1, q->len);
+        win_push(q->w0, q->len, x[2 * i + 1]);
+        y[i] = cf_add(q->w0[q->m - 1], f);
+    }
+}
+
+/* resamp2.c:345-359: 2n outputs from n inputs */
+void orc_resamp2_interp_execute(orc_resamp2 q, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    for (unsigned int i = 0; i < n; i++) {
+        win_push(q->w0, q->len, x[i]);
+        y[2 * i] = q->w0[q->m - 1];
+        win_push(q->w1, q->len, x[i]);
+        y[2 * i + 1] = dot_crcf(q->hb, q->w1, q->len);
+    }
+}
+
+struct orc_msresamp2_s {
+    int interp;
+    unsigned int S;             /* stages; rate 2^S */
+    unsigned int *m;            /* semi-length of each stage */
+    orc_resamp2 *hb;
+};
+
+/* msresamp2.c:82-170: stage i has cut-off fc/2^(i+1), transition (0.5 - fc_i)/2, semi-length from
+ * Kaiser's length estimate (at least 3) */
+orc_msresamp2 orc_msresamp2_create(int type, unsigned int S, float fc, float f0, float As)
+{
+    if (S > 16 || fc <= 0.0f || fc >= 0.5f) return NULL;
+    if (fc > 0.45f) fc = 0.45f;
+    f0 = 0.0f;                                   /* msresamp2.c:108-111: centre frequency unsupported */
+    orc_msresamp2 q = xmalloc(sizeof *q);
+    q->interp = (type == 0);                     /* LIQUID_RESAMP_INTERP = 0 */
+    q->S = S;
+    q->m = xmalloc((S ? S : 1) * sizeof *q->m);
+    q->hb = xmalloc((S ? S : 1) * sizeof *q->hb);
+    for (unsigned int i = 0; i < S; i++) {
+        f0 = 0.5f * f0;
+        fc = 0.5f * fc;
+        float ft = (0.5f - fc) / 2.0f;
+        unsigned int h_len = orc_estimate_req_filter_len(ft, As);
+        unsigned int m = (unsigned int)ceilf((float)(h_len - 1) / 4.0f);
+        q->m[i] = m < 3 ? 3 : m;
+        q->hb[i] = orc_resamp2_create(q->m[i], f0, As);
+    }
+    return q;
+}
+
+void orc_msresamp2_destroy(orc_msresamp2 q)
+{
+    if (!q) return;
+    for (unsigned int i = 0; i < q->S; i++) orc_resamp2_destroy(q->hb[i]);
+    free(q->hb); free(q->m); free(q);
+}
+
+void orc_msresamp2_reset(orc_msresamp2 q) { for (unsigned int i = 0; i < q->S; i++) orc_resamp2_clear(q->hb[i]); }
+unsigned int orc_msresamp2_stage_m(orc_msresamp2 q, unsigned int i) { return q->m[i]; }
+
+/* msresamp2.c:231-258 */
+float orc_msresamp2_get_delay(orc_msresamp2 q)
+{
+    float delay = 0;
+    for (unsigned int i = 0; i < q->S; i++) {
+        if (q->interp) { delay *= 0.5f; delay += q->m[i]; }
+        else           { delay *= 2; delay += 2 * q->m[q->S - i - 1] - 1; }
+    }
+    return delay;
+}
+
+/* msresamp2.c:264-354 over a block of n units (interp: n inputs -> n 2^S outputs, stages last to first;
+ * decim: n 2^S inputs -> n outputs scaled by 2^-S, stages first to last).  The stages only see their own
+ * sample streams, so running each stage over the whole block equals the reference's unit-by-unit order. */
+void orc_msresamp2_execute_block(orc_msresamp2 q, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    unsigned int M = 1u << q->S;
+    if (q->S == 0) { memcpy(y, x, n * sizeof *y); return; }
+    size_t cap = (size_t)n * M;
+    orc_cf *a = xmalloc(cap * sizeof *a), *b = xmalloc(cap * sizeof *b);
+    if (q->interp) {
+        memcpy(a, x, n * sizeof *a);
+        size_t cnt = n;
+        for (unsigned int s = 0; s < q->S; s++) {
+            orc_resamp2_interp_execute(q->hb[q->S - s - 1], a, (unsigned int)cnt, b);
+            cnt *= 2;
+            orc_cf *t = a; a = b; b = t;
+        }
+        memcpy(y, a, cnt * sizeof *y);
+    } else {
+        memcpy(a, x, cap * sizeof *a);
+        size_t cnt = cap;
+        for (unsigned int s = 0; s < q->S; s++) {
+            cnt /= 2;
+            orc_resamp2_decim_execute(q->hb[s], a, (unsigned int)cnt, b);
+            orc_cf *t = a; a = b; b = t;
+        }
+        float zeta = 1.0f / (float)M;
+        for (unsigned int i = 0; i < n; i++) y[i] = cf(a[i].re * zeta, a[i].im * zeta);
+    }
+    free(a); free(b);
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* spgramcf: windowed-FFT spectral periodogram                      */
 /* src/fft/src/spgramcf.c:27-51 instantiating src/fft/src/spgram.c                        */
 /* ------------------------------------------------------------------------------------ */

@@ -118,6 +118,28 @@ def lib():
             getattr(L, "orc_%s_execute_block" % nm).restype = None
             getattr(L, "orc_%s_execute_block" % nm).argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
         L.orc_firdecim_clear.argtypes = [C.c_void_p]
+        L.orc_estimate_req_filter_len.restype = C.c_uint
+        L.orc_estimate_req_filter_len.argtypes = [C.c_float, C.c_float]
+        L.orc_resamp2_create.restype = C.c_void_p
+        L.orc_resamp2_create.argtypes = [C.c_uint, C.c_float, C.c_float]
+        L.orc_resamp2_destroy.argtypes = [C.c_void_p]
+        L.orc_resamp2_clear.argtypes = [C.c_void_p]
+        L.orc_resamp2_get_taps.argtypes = [C.c_void_p, c_f_p]
+        L.orc_resamp2_filter_execute.restype = None
+        L.orc_resamp2_filter_execute.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p, c_cf_p]
+        for nm in ("analyzer", "synthesizer", "decim", "interp"):
+            getattr(L, "orc_resamp2_%s_execute" % nm).restype = None
+            getattr(L, "orc_resamp2_%s_execute" % nm).argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
+        L.orc_msresamp2_create.restype = C.c_void_p
+        L.orc_msresamp2_create.argtypes = [C.c_int, C.c_uint, C.c_float, C.c_float, C.c_float]
+        L.orc_msresamp2_destroy.argtypes = [C.c_void_p]
+        L.orc_msresamp2_reset.argtypes = [C.c_void_p]
+        L.orc_msresamp2_stage_m.restype = C.c_uint
+        L.orc_msresamp2_stage_m.argtypes = [C.c_void_p, C.c_uint]
+        L.orc_msresamp2_get_delay.restype = C.c_float
+        L.orc_msresamp2_get_delay.argtypes = [C.c_void_p]
+        L.orc_msresamp2_execute_block.restype = None
+        L.orc_msresamp2_execute_block.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
         L.orc_firinterp_reset.argtypes = [C.c_void_p]
         L.orc_spgramcf_create.restype = C.c_void_p
         L.orc_spgramcf_create.argtypes = [C.c_uint, c_f_p, C.c_uint]
@@ -339,6 +361,76 @@ class Firinterp(_Obj):
         x = _cf(x)
         y = np.empty(len(x) * self.M, np.complex64)
         lib().orc_firinterp_execute_block(self.h, x, len(x), y)
+        return y
+
+
+RESAMP_INTERP, RESAMP_DECIM = 0, 1      # liquid.h:3023-3024
+
+
+class Resamp2(_Obj):
+    """resamp2_crcf: half-band filter / analyzer / synthesizer / decimator / interpolator, block forms"""
+    _destroy = "orc_resamp2_destroy"
+
+    def __init__(self, m, f0=0.0, As=60.0):
+        self.m = m
+        super().__init__(lib().orc_resamp2_create(m, f0, As))
+
+    def clear(self):
+        lib().orc_resamp2_clear(self.h)
+
+    def taps(self):
+        hb = np.empty(2 * self.m, np.float32)
+        lib().orc_resamp2_get_taps(self.h, hb)
+        return hb
+
+    def filter_execute(self, x):
+        x = _cf(x)
+        y0 = np.empty(len(x), np.complex64); y1 = np.empty(len(x), np.complex64)
+        lib().orc_resamp2_filter_execute(self.h, x, len(x), y0, y1)
+        return y0, y1
+
+    def _run(self, name, x, n, n_out):
+        x = _cf(x)
+        y = np.empty(n_out, np.complex64)
+        getattr(lib(), "orc_resamp2_%s_execute" % name)(self.h, x, n, y)
+        return y
+
+    def analyzer_execute(self, x):
+        return self._run("analyzer", x, len(x) // 2, len(x) // 2 * 2)
+
+    def synthesizer_execute(self, x):
+        return self._run("synthesizer", x, len(x) // 2, len(x) // 2 * 2)
+
+    def decim_execute(self, x):
+        return self._run("decim", x, len(x) // 2, len(x) // 2)
+
+    def interp_execute(self, x):
+        return self._run("interp", x, len(x), 2 * len(x))
+
+
+class Msresamp2(_Obj):
+    """msresamp2_crcf: cascade of S half-band stages, rate 2^S"""
+    _destroy = "orc_msresamp2_destroy"
+
+    def __init__(self, type, S, fc, f0, As):
+        self.type, self.S = type, S
+        super().__init__(lib().orc_msresamp2_create(type, S, fc, f0, As))
+
+    def reset(self):
+        lib().orc_msresamp2_reset(self.h)
+
+    def stage_m(self):
+        return [lib().orc_msresamp2_stage_m(self.h, i) for i in range(self.S)]
+
+    def get_delay(self):
+        return lib().orc_msresamp2_get_delay(self.h)
+
+    def execute_block(self, x):
+        x = _cf(x)
+        M = 1 << self.S
+        n = len(x) if self.type == RESAMP_INTERP else len(x) // M
+        y = np.empty(n * M if self.type == RESAMP_INTERP else n, np.complex64)
+        lib().orc_msresamp2_execute_block(self.h, x, n, y)
         return y
 
 
@@ -609,6 +701,131 @@ def ref_firinterp_block(M, x, h=None, kaiser=None):
     R.firinterp_crcf_execute_block(q, x, len(x), y)
     R.firinterp_crcf_destroy(q)
     return y
+
+
+def _c_by_value(v):
+    """a C `float complex` argument passed by value: on x86-64 SysV it travels in the low 8 bytes of one XMM
+    register, exactly like a double with the same bits (ctypes has no complex type before 3.14)"""
+    return C.c_double(np.array([v], np.complex64).view(np.float64)[0])
+
+
+def ref_resamp2(mode, m, f0, As, x):
+    """the compiled reference's resamp2_crcf run sample by sample (it has no block form)"""
+    R = ref()
+    R.resamp2_crcf_create.restype = C.c_void_p; R.resamp2_crcf_create.argtypes = [C.c_uint, C.c_float, C.c_float]
+    R.resamp2_crcf_destroy.argtypes = [C.c_void_p]
+    q = C.c_void_p(R.resamp2_crcf_create(m, f0, As))
+    x = _cf(x)
+    if mode == "filter":
+        R.resamp2_crcf_filter_execute.argtypes = [C.c_void_p, C.c_double, c_cf_p, c_cf_p]
+        y0 = np.empty(len(x), np.complex64); y1 = np.empty(len(x), np.complex64)
+        for i in range(len(x)):
+            R.resamp2_crcf_filter_execute(q, _c_by_value(x[i]), y0[i:i + 1], y1[i:i + 1])
+        out = (y0, y1)
+    elif mode == "interp":
+        R.resamp2_crcf_interp_execute.argtypes = [C.c_void_p, C.c_double, c_cf_p]
+        out = np.empty(2 * len(x), np.complex64)
+        for i in range(len(x)):
+            R.resamp2_crcf_interp_execute(q, _c_by_value(x[i]), out[2 * i:2 * i + 2])
+    else:
+        fn = getattr(R, "resamp2_crcf_%s_execute" % mode)
+        fn.argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+        n = len(x) // 2
+        per = 1 if mode == "decim" else 2
+        out = np.empty(n * per, np.complex64)
+        for i in range(n):
+            fn(q, x[2 * i:2 * i + 2], out[per * i:per * i + per])
+    R.resamp2_crcf_destroy(q)
+    return out
+
+
+MIXED_MODES = ("decim", "filter", "interp", "analyzer", "synthesizer", "filter")
+
+
+def mixed_segments(n):
+    """(mode, first sample, samples) of the mixed-mode run over n input samples: segments of 36 + 2 k samples,
+    the modes of MIXED_MODES in turn (the odd number of filter calls in some segments leaves the toggle set)"""
+    segs, pos, k = [], 0, 0
+    while pos < n:
+        mode = MIXED_MODES[k % len(MIXED_MODES)]
+        ln = min(36 + 2 * k + (1 if mode == "filter" else 0), n - pos)
+        if mode not in ("filter", "interp"):
+            ln -= ln % 2
+        if ln == 0:
+            break
+        segs.append((mode, pos, ln))
+        pos += ln
+        k += 1
+    return segs
+
+
+def ref_resamp2_mixed(m, f0, As, x):
+    """one reference object driven through all five modes in turn; outputs concatenated (filter: y0 then y1)"""
+    R = ref()
+    R.resamp2_crcf_create.restype = C.c_void_p; R.resamp2_crcf_create.argtypes = [C.c_uint, C.c_float, C.c_float]
+    R.resamp2_crcf_destroy.argtypes = [C.c_void_p]
+    R.resamp2_crcf_filter_execute.argtypes = [C.c_void_p, C.c_double, c_cf_p, c_cf_p]
+    R.resamp2_crcf_interp_execute.argtypes = [C.c_void_p, C.c_double, c_cf_p]
+    for nm in ("analyzer", "synthesizer", "decim"):
+        getattr(R, "resamp2_crcf_%s_execute" % nm).argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+    q = C.c_void_p(R.resamp2_crcf_create(m, f0, As))
+    x = _cf(x)
+    parts = []
+    for mode, pos, ln in mixed_segments(len(x)):
+        seg = x[pos:pos + ln]
+        if mode == "filter":
+            y0 = np.empty(ln, np.complex64); y1 = np.empty(ln, np.complex64)
+            for i in range(ln):
+                R.resamp2_crcf_filter_execute(q, _c_by_value(seg[i]), y0[i:i + 1], y1[i:i + 1])
+            parts += [y0, y1]
+        elif mode == "interp":
+            y = np.empty(2 * ln, np.complex64)
+            for i in range(ln):
+                R.resamp2_crcf_interp_execute(q, _c_by_value(seg[i]), y[2 * i:2 * i + 2])
+            parts.append(y)
+        else:
+            per = 1 if mode == "decim" else 2
+            y = np.empty(ln // 2 * per, np.complex64)
+            fn = getattr(R, "resamp2_crcf_%s_execute" % mode)
+            for i in range(ln // 2):
+                fn(q, seg[2 * i:2 * i + 2], y[per * i:per * i + per])
+            parts.append(y)
+    R.resamp2_crcf_destroy(q)
+    return np.concatenate(parts)
+
+
+def run_resamp2_mixed(q, x):
+    """the same mixed-mode run on an object with the block methods (the oracle's Resamp2 or the CUDA mirror)"""
+    x = _cf(x)
+    parts = []
+    for mode, pos, ln in mixed_segments(len(x)):
+        fn = getattr(q, mode + "_execute_block", None) or getattr(q, mode + "_execute")
+        r = fn(x[pos:pos + ln])
+        parts += list(r) if mode == "filter" else [r]
+    return np.concatenate(parts)
+
+
+def ref_msresamp2_block(type, S, fc, f0, As, x):
+    R = ref()
+    R.msresamp2_crcf_create.restype = C.c_void_p
+    R.msresamp2_crcf_create.argtypes = [C.c_int, C.c_uint, C.c_float, C.c_float, C.c_float]
+    R.msresamp2_crcf_execute.argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+    R.msresamp2_crcf_get_delay.restype = C.c_float; R.msresamp2_crcf_get_delay.argtypes = [C.c_void_p]
+    R.msresamp2_crcf_destroy.argtypes = [C.c_void_p]
+    q = C.c_void_p(R.msresamp2_crcf_create(type, S, fc, f0, As))
+    x = _cf(x)
+    M = 1 << S
+    if type == RESAMP_INTERP:
+        y = np.empty(len(x) * M, np.complex64)
+        for i in range(len(x)):
+            R.msresamp2_crcf_execute(q, x[i:i + 1], y[i * M:(i + 1) * M])
+    else:
+        y = np.empty(len(x) // M, np.complex64)
+        for i in range(len(y)):
+            R.msresamp2_crcf_execute(q, x[i * M:(i + 1) * M], y[i:i + 1])
+    delay = R.msresamp2_crcf_get_delay(q)
+    R.msresamp2_crcf_destroy(q)
+    return y, delay
 
 
 class RefSpgramcf:

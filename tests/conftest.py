@@ -37,6 +37,12 @@ def refrn():
 
 
 @pytest.fixture(scope="session")
+def refrn2():
+    """resamp2_crcf / msresamp2_crcf outputs of the compiled reference (oracle/gen_golden_next2.py)"""
+    return dict(np.load(os.path.join(GOLDEN, "ref_outputs_next2.npz")))
+
+
+@pytest.fixture(scope="session")
 def orc():
     """the CPU oracle (checker only)"""
     from oracle import oracle as O

@@ -680,6 +680,88 @@ def test_firdecim_firinterp_vs_reference_fixture_and_oracle(L, orc, refrn):
     assert np.abs(got - want).max() < 4e-6 * np.abs(want).max()
 
 
+# ------------------------------------------------------------------ resamp2 / msresamp2
+def test_resamp2_vs_reference_fixture(L, orc, refrn2):
+    """all five modes and the mixed-mode run (shared windows, toggle) against the compiled reference's outputs;
+    the prototype bit for bit against the oracle; the per-call entry points; recreate"""
+    from test_oracle import _hb_cases, hb_check
+    for tag, m, f0, As in _hb_cases(refrn2):
+        q = L.resamp2_crcf(m, f0, As)
+        assert np.array_equal(q.get_taps()[1], orc.Resamp2(m, f0, As).taps()), tag
+        assert q.get_delay() == 2 * m - 1
+        hb_check(q, orc.run_resamp2_mixed, refrn2, tag, 1e-6)
+        # per-call API on a fresh state, continuing with blocks
+        q.clear()
+        x = refrn2[tag + "_x"]
+        want = refrn2[tag + "_decim"]
+        got = [q.decim_execute(x[0:2]), q.decim_execute(x[2:4])]
+        got = np.concatenate([np.array(got, np.complex64), q.decim_execute_block(x[4:9 * 2]), q.decim_execute_block(x[18:])])
+        assert np.abs(got - want).max() < 1e-6, tag
+        q.clear()
+        y = np.concatenate([q.interp_execute(x[0]), q.interp_execute(x[1]), q.interp_execute_block(x[2:])])
+        assert np.abs(y - refrn2[tag + "_interp"]).max() < 1e-6, tag
+        q.clear()
+        pairs = [q.filter_execute(v) for v in x[:5]]
+        y0, y1 = q.filter_execute_block(x[5:])
+        got = np.concatenate([np.array([p[0] for p in pairs], np.complex64), y0, np.array([p[1] for p in pairs], np.complex64), y1])
+        assert np.abs(got - refrn2[tag + "_filter"]).max() < 1e-6, tag
+        q.clear()
+        y = np.concatenate([q.analyzer_execute(x[0:2]), q.analyzer_execute_block(x[2:])])
+        assert np.abs(y - refrn2[tag + "_analyzer"]).max() < 1e-6, tag
+        q.clear()
+        y = np.concatenate([q.synthesizer_execute(x[0:2]), q.synthesizer_execute_block(x[2:])])
+        assert np.abs(y - refrn2[tag + "_synthesizer"]).max() < 1e-6, tag
+    q = L.resamp2_crcf(4, 0.0, 60.0)
+    q.recreate(4, 0.1, 70.0)
+    assert np.array_equal(q.get_taps()[1], orc.Resamp2(4, 0.1, 70.0).taps())
+    q.recreate(7, 0.1, 70.0)
+    assert np.abs(q.decim_execute_block(refrn2["hb_m7_f+010_x"]) - refrn2["hb_m7_f+010_decim"]).max() < 1e-6
+
+
+def test_msresamp2_vs_reference_fixture_and_oracle(L, orc, refrn2):
+    from test_oracle import _ms_cases
+    for tag, typ, S, fc, As, delay in _ms_cases(refrn2):
+        q = L.msresamp2_crcf(typ, S, fc, 0.0, As)
+        assert q.get_delay() == delay, tag
+        assert q.stage_semilengths() == orc.Msresamp2(typ, S, fc, 0.0, As).stage_m(), tag
+        x, want = refrn2[tag + "_x"], refrn2[tag + "_y"]
+        M = 1 << S
+        unit = 1 if typ == L.LIQUID_RESAMP_INTERP else M
+        cut = 7 * unit
+        got = np.concatenate([q.execute(x[:unit]), q.execute_block(x[unit:cut]), q.execute_block(x[cut:])])
+        assert np.abs(got - want).max() < 2e-6 * max(1.0, np.abs(want).max()), tag
+        q.reset()
+        assert np.abs(q.execute_block(x) - want).max() < 2e-6 * max(1.0, np.abs(want).max()), tag
+    # long blocks against the oracle, state carried
+    x = orc.synth_input(1 << 20, seed=0x77)
+    for typ, S, n in ((L.LIQUID_RESAMP_DECIM, 4, 1 << 20), (L.LIQUID_RESAMP_INTERP, 3, 1 << 16)):
+        q = L.msresamp2_crcf(typ, S, 0.4, 0.0, 60.0)
+        o = orc.Msresamp2(typ, S, 0.4, 0.0, 60.0)
+        cut = (n // 3) & ~15
+        got = np.concatenate([q.execute_block(x[:cut]), q.execute_block(x[cut:n])])
+        want = o.execute_block(x[:n])
+        assert np.abs(got - want).max() < 4e-6 * max(1.0, np.abs(want).max())
+
+
+def test_resamp2_long_blocks_vs_oracle(L, orc):
+    """2^21 samples through each mode, two blocks with an odd split for the filter mode"""
+    x = orc.synth_input(1 << 21, seed=0x99)
+    m = 9
+    for mode in ("analyzer", "synthesizer", "decim", "interp"):
+        q, o = L.resamp2_crcf(m, 0.05, 60.0), orc.Resamp2(m, 0.05, 60.0)
+        n = len(x) if mode != "interp" else len(x) // 2
+        cut = 333334
+        fn = getattr(q, mode + "_execute_block")
+        got = np.concatenate([fn(x[:cut]), fn(x[cut:n])])
+        assert np.abs(got - getattr(o, mode + "_execute")(x[:n])).max() < 2e-6, mode
+    q, o = L.resamp2_crcf(m, 0.05, 60.0), orc.Resamp2(m, 0.05, 60.0)
+    a0, a1 = q.filter_execute_block(x[:777777])
+    b0, b1 = q.filter_execute_block(x[777777:])
+    w0, w1 = o.filter_execute(x)
+    assert np.abs(np.concatenate([a0, b0]) - w0).max() < 2e-6
+    assert np.abs(np.concatenate([a1, b1]) - w1).max() < 2e-6
+
+
 # ------------------------------------------------------------------ spgramcf (SURVEY 8f item 2)
 def test_spgramcf_vs_reference_fixture_and_oracle(L, orc, refrn):
     """every entry point against the compiled reference's outputs (power-of-two and other nfft), plus a

@@ -115,3 +115,9 @@ def test_host_design_rnyquist_kaiser(L, orc, refrn):
         assert np.allclose([rms, peak], refrn["isi_rkaiser_" + tag], rtol=1e-6)
     for df, N, want in refrn["req_As"]:
         assert L.lib.estimate_req_filter_As(df, int(N)) == np.float32(want)
+
+
+def test_estimate_req_filter_len(L, refrn2):
+    """Kaiser's length estimate (host code) at the fixture's points from the compiled reference"""
+    for (df, As), want in zip(refrn2["len_points"], refrn2["len_values"]):
+        assert L.lib.estimate_req_filter_len(float(df), float(As)) == want

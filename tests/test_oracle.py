@@ -450,3 +450,68 @@ def test_firdecim_is_subsampled_firfilt_and_firinterp_is_filtered_upsampling(orc
     up = np.zeros(100 * M, np.complex64)
     up[::M] = x[:100]
     assert np.abs(orc.Firinterp(M, h=h).execute_block(x[:100]) - orc.Firfilt(h=h).execute_block(up)).max() < 1e-6
+
+
+# ------------------------------------------------------------------ resamp2 / msresamp2
+HB_MODES = ("analyzer", "synthesizer", "decim", "interp")
+
+
+def _hb_cases(fx):
+    for name in sorted(k for k in fx if k.startswith("hb_") and k.endswith("_args")):
+        m, f0, As = fx[name]
+        yield name[:-5], int(m), float(f0), float(As)
+
+
+def _ms_cases(fx):
+    for name in sorted(k for k in fx if k.startswith("ms_") and k.endswith("_args")):
+        typ, S, fc, As, delay = fx[name]
+        yield name[:-5], int(typ), int(S), float(fc), float(As), float(delay)
+
+
+def hb_check(q, run_mixed, fx, tag, tol):
+    """every mode of a half-band object (fresh state each) and the mixed-mode run against the fixture"""
+    x = fx[tag + "_x"]
+    y0, y1 = q.filter_execute_block(x) if hasattr(q, "filter_execute_block") else q.filter_execute(x)
+    assert np.abs(np.concatenate([y0, y1]) - fx[tag + "_filter"]).max() < tol, (tag, "filter")
+    for mode in HB_MODES:
+        q.clear()
+        fn = getattr(q, mode + "_execute_block", None) or getattr(q, mode + "_execute")
+        assert np.abs(fn(x) - fx[tag + "_" + mode]).max() < tol, (tag, mode)
+    q.clear()
+    assert np.abs(run_mixed(q, x) - fx[tag + "_mixed"]).max() < tol, (tag, "mixed")
+
+
+def test_fixture_resamp2(orc, refrn2):
+    for tag, m, f0, As in _hb_cases(refrn2):
+        hb_check(orc.Resamp2(m, f0, As), orc.run_resamp2_mixed, refrn2, tag, 3e-7)
+
+
+def test_fixture_msresamp2_and_filter_len(orc, refrn2):
+    for (df, As), want in zip(refrn2["len_points"], refrn2["len_values"]):
+        assert orc.lib().orc_estimate_req_filter_len(float(df), float(As)) == want
+    for tag, typ, S, fc, As, delay in _ms_cases(refrn2):
+        q = orc.Msresamp2(typ, S, fc, 0.0, As)
+        assert q.get_delay() == delay
+        want = refrn2[tag + "_y"]
+        assert np.abs(q.execute_block(refrn2[tag + "_x"]) - want).max() < 1e-6 * max(1.0, np.abs(want).max()), tag
+
+
+def test_resamp2_properties(orc):
+    """what the object stands for: the two bands of the filter mode add up to the delayed input; the decimator is
+    every second (odd) output of the low band, times two; the interpolator is the low band of the zero-stuffed
+    input, times two"""
+    m = 6
+    x = orc.synth_input(800, seed=77)
+    q = orc.Resamp2(m, 0.0, 60.0)
+    y0, y1 = q.filter_execute(x)
+    assert np.abs((y0 + y1)[2 * m:] - x[:-2 * m]).max() < 1e-6
+    q.clear()
+    d = q.decim_execute(x)
+    assert np.abs(d - 2 * y0[1::2]).max() < 2e-6
+    q.clear()
+    up = q.interp_execute(x[:300])               # interpolation = half-band filtering of the zero-stuffed input (x2)
+    z = np.zeros(600, np.complex64)
+    z[::2] = x[:300]
+    q.clear()
+    z0, _ = q.filter_execute(z)
+    assert np.abs(up - 2 * z0).max() < 2e-6

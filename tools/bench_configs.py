@@ -3,7 +3,7 @@
 measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
 events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
 
-  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
+  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [f4] [s] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
 """
 import argparse
 import json
@@ -192,6 +192,27 @@ def main():
         ms, ln = timed(lambda: qi.execute_block_dev(x.data_ptr(), ni, y.data_ptr(), st.cuda_stream))
         report("f3b: firinterp_crcf M=8 m=6, 2^25 input samples (2^28 outputs)", ni, 8 + 8 * M, ms, ln,
                {"note": "throughput in INPUT samples/s; algorithmic bytes 8 in + 8 M out per input sample"})
+        del x, y
+    if "f4" in args.configs:
+        # SURVEY 8(f) item 3, second part: resamp2_crcf decimator / interpolator (m=7: 14 taps on the filter branch)
+        # and msresamp2_crcf decimating by 2^4, 2^28 input samples (interpolator: 2^27 in)
+        n = 1 << 28
+        x = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr(), n, stream=st.cuda_stream)
+        q = L.resamp2_crcf(7, 0.0, 60.0)
+        ms, ln = timed(lambda: q.execute_block_dev("decim", x.data_ptr(), n // 2, y.data_ptr(), st.cuda_stream))
+        report("f4a: resamp2_crcf decimator m=7, 2^28 input samples", n, 8 + 4, ms, ln)
+        ms, ln = timed(lambda: q.execute_block_dev("interp", x.data_ptr(), n // 2, y.data_ptr(), st.cuda_stream))
+        report("f4b: resamp2_crcf interpolator m=7, 2^27 input samples (2^28 outputs)", n // 2, 8 + 16, ms, ln,
+               {"note": "throughput in INPUT samples/s; algorithmic bytes 8 in + 16 out per input sample"})
+        ms, ln = timed(lambda: q.execute_block_dev("analyzer", x.data_ptr(), n // 2, y.data_ptr(), st.cuda_stream))
+        report("f4c: resamp2_crcf analyzer m=7, 2^28 input samples", n, 16, ms, ln)
+        qm = L.msresamp2_crcf(L.LIQUID_RESAMP_DECIM, 4, 0.4, 0.0, 60.0)
+        ms, ln = timed(lambda: qm.execute_block_dev(x.data_ptr(), n // 16, y.data_ptr(), st.cuda_stream))
+        report("f4d: msresamp2_crcf decimator 4 stages (m=%s), 2^28 input samples" % qm.stage_semilengths(), n,
+               8 + 8 / 16, ms, ln, {"note": "algorithmic bytes: input read once, output written once; the "
+                                            "intermediate streams of the stage-by-stage form are extra traffic"})
         del x, y
     if "fft" in args.configs:
         # a11: the batched complex FFT on its own (fft_execute_batch_dev), 2^28 points per step, out of place
