@@ -124,6 +124,106 @@ resamp2_units_kernel(Windows w, const float *__restrict__ hb, unsigned int m, co
     }
 }
 
+// two adjacent units (t, t + 1), t even, from a staged filter-branch sequence: unit t's taps start at element t.
+// Packed FFMA2 on (re, im): the same two IEEE fused multiply-adds per tap as the scalar chains, in the same order.
+__device__ __forceinline__ void pair_fir(const float4 *__restrict__ sb4, unsigned int t2, const float *__restrict__ hs,
+                                         unsigned int len, float2 &acc0, float2 &acc1)
+{
+    const float2 *hs2 = reinterpret_cast<const float2 *>(hs);
+    acc0 = make_float2(0.f, 0.f);
+    acc1 = make_float2(0.f, 0.f);
+    float4 cur = sb4[t2];                                                // elements t, t + 1
+    for (unsigned int k2 = 0; k2 < len / 2; k2++) {
+        const float4 nxt = sb4[t2 + k2 + 1];
+        const float2 h = hs2[k2];                                        // taps 2 k2, 2 k2 + 1
+        const float2 h0 = make_float2(h.x, h.x), h1 = make_float2(h.y, h.y);
+        acc0 = __ffma2_rn(h0, make_float2(cur.x, cur.y), acc0);
+        acc0 = __ffma2_rn(h1, make_float2(cur.z, cur.w), acc0);
+        acc1 = __ffma2_rn(h0, make_float2(cur.z, cur.w), acc1);
+        acc1 = __ffma2_rn(h1, make_float2(nxt.x, nxt.y), acc1);
+        cur = nxt;
+    }
+}
+
+__device__ __forceinline__ void cp_async8(float2 *dst_smem, const float2 *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned int)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// The throughput form of the above (16-byte aligned x and y): a CTA stages the two branch sequences of kTile units
+// plus 2m - 1 units of history in shared memory -- one coalesced 16-byte load per input pair, every input byte
+// read from HBM once -- and each thread then produces two adjacent units from 16-byte shared-memory reads
+// (consecutive lanes, consecutive addresses).  Same fmaf chain per output as resamp2_units_kernel: identical bits.
+constexpr unsigned int kTile = 2048;
+
+__host__ __device__ inline unsigned int tile_hs_f2(unsigned int len) { return (len / 2 + 1) & ~1u; }   // taps, in float2, even
+__host__ __device__ inline unsigned int tile_sb_f2(unsigned int len) { return (kTile + len + 2 + 1) & ~1u; }
+inline size_t tile_smem(unsigned int len) { return sizeof(float2) * (tile_hs_f2(len) + 2 * tile_sb_f2(len)); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+resamp2_tile_kernel(Windows w, const float *__restrict__ hb, unsigned int m, const float2 *__restrict__ x,
+                    float2 *__restrict__ y, unsigned long long n, float scale)
+{
+    extern __shared__ float4 smem_f4[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_f4);
+    float *hs = reinterpret_cast<float *>(sm);
+    float2 *sb = sm + tile_hs_f2(w.len);
+    float2 *sa = sb + tile_sb_f2(w.len);
+    const unsigned int halo = w.len - 1;
+    const unsigned long long u0 = (unsigned long long)blockIdx.x * kTile;
+    const unsigned int nt = (n - u0 < kTile) ? (unsigned int)(n - u0) : kTile;
+    for (unsigned int k = threadIdx.x; k < w.len; k += blockDim.x) hs[k] = __ldg(hb + k);
+    // staged element q holds unit u0 - halo + q
+    for (unsigned int q = threadIdx.x; q < halo + nt; q += blockDim.x) {
+        const long long idx = (long long)u0 - (long long)halo + q;
+        if (idx < 0) {
+            sb[q] = __ldg(w.w1 + ((long long)w.len + idx));
+            sa[q] = __ldg(w.w0 + ((long long)w.len + idx));
+        } else if (MODE == kInterp) {
+            cp_async8(sb + q, x + idx);
+            cp_async8(sa + q, x + idx);
+        } else if (MODE == kDecim) {
+            cp_async8(sb + q, x + 2 * idx);
+            cp_async8(sa + q, x + 2 * idx + 1);
+        } else {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + idx);      // (x[2 idx], x[2 idx + 1])
+            const float2 e = make_float2(v.x, v.y), o = make_float2(v.z, v.w);
+            if (MODE == kAnalyzer) { sb[q] = half2(e); sa[q] = half2(o); }
+            if (MODE == kSynth) { sa[q] = add2(e, o); sb[q] = sub2(e, o); }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const float4 *sb4 = reinterpret_cast<const float4 *>(sb);
+    for (unsigned int t2 = threadIdx.x; 2 * t2 < nt; t2 += blockDim.x) {
+        const unsigned int t = 2 * t2;                                   // units u0 + t and u0 + t + 1
+        float2 f0, f1;
+        pair_fir(sb4, t2, hs, w.len, f0, f1);
+        const float re0 = f0.x, im0 = f0.y, re1 = f1.x, im1 = f1.y;
+        const float2 d0 = sa[halo + t - m], d1 = sa[halo + t + 1 - m];
+        const bool second = (t + 1 < nt);
+        const unsigned long long u = u0 + t;
+        if (MODE == kDecim) {
+            const float2 v0 = make_float2((d0.x + re0) * scale, (d0.y + im0) * scale);
+            const float2 v1 = make_float2((d1.x + re1) * scale, (d1.y + im1) * scale);
+            if (second) *reinterpret_cast<float4 *>(y + u) = make_float4(v0.x, v0.y, v1.x, v1.y);
+            else        y[u] = v0;
+        } else if (MODE == kAnalyzer) {
+            reinterpret_cast<float4 *>(y)[u] = make_float4(re0 + d0.x, im0 + d0.y, re0 - d0.x, im0 - d0.y);
+            if (second) reinterpret_cast<float4 *>(y)[u + 1] = make_float4(re1 + d1.x, im1 + d1.y, re1 - d1.x, im1 - d1.y);
+        } else {
+            reinterpret_cast<float4 *>(y)[u] = make_float4(d0.x, d0.y, re0, im0);
+            if (second) reinterpret_cast<float4 *>(y)[u + 1] = make_float4(d1.x, d1.y, re1, im1);
+        }
+    }
+}
+
 // the windows after n units, written to the other half of the ping-pong pair
 template <int MODE>
 __global__ void resamp2_units_roll_kernel(Windows w, const float2 *__restrict__ x, unsigned long long n, float2 *__restrict__ next)
@@ -178,6 +278,221 @@ __global__ void resamp2_filter_roll_kernel(Windows w, unsigned int g, const floa
     next[j] = filt_val(w, x, newest - 2ll * (w.len - 1 - pos), g);
 }
 
+// ---- msresamp2 decimator, all stages in ONE kernel -------------------------------------------------------------
+// A CTA produces kT final outputs.  Working backwards, stage s must compute the units [lo_s, hi_s) with
+// lo_{s-1} = 2 (lo_s - (len_s - 1)), hi_{s-1} = 2 hi_s: each stage recomputes the 2m - 1 units of history the next one
+// needs (a few percent of extra arithmetic) instead of reading them back from HBM, so the input is read once and only
+// the final stream is written.  A stage's two branch sequences live de-interleaved in shared memory (the pair of
+// outputs (u, u+1), u even, is the next stage's (b, a) pair at unit u/2), units below zero come from that stage's
+// windows, and the last CTA leaves every stage's windows as they stand after the block.
+// The inner loop is register-blocked: a thread owns 8 adjacent units, the filter length is a template parameter and
+// the tap loop is fully unrolled, so each staged element is read from shared memory once per thread (16-byte reads;
+// the arrays are padded by 16 bytes per 64 so that the 64-byte lane stride is conflict-free) and feeds up to 8 packed
+// FFMA2.  Same fused multiply-add chains and the same d + f, * 2^-S roundings as the stage-by-stage form: identical bits.
+constexpr int kMaxFusedStages = 8;
+constexpr unsigned int kMaxFusedLen = 32;
+constexpr unsigned int kBlockUnits = 8;
+
+struct CascadeStage {
+    const float2 *w0, *w1;        // current windows (oldest first)
+    float2 *next;                 // the other half of the ping-pong pair: (w0 | w1) after the block
+    const float *hb;
+    unsigned int len, m;
+};
+
+struct CascadeArgs {
+    CascadeStage st[kMaxFusedStages];
+    unsigned int S, T;            // stages, final outputs per CTA (a multiple of 8)
+    unsigned int cap[2];          // float2 capacity (padded layout) of one staged array in region 0 / 1
+    unsigned int back[kMaxFusedStages];   // stage s computes the units [(o_lo << (S-1-s)) - back[s], o_hi << (S-1-s))
+    float zeta;
+};
+
+// padded position of staged element q: 2 elements (16 bytes) of padding after every 8
+__host__ __device__ inline unsigned int phys(unsigned int q) { return q + 2 * (q >> 3); }
+
+// units of stage s the tile whose final outputs are [o_lo, o_hi) must compute
+__host__ __device__ inline void cascade_range(const CascadeArgs &a, unsigned int s, long long o_lo, long long o_hi,
+                                              long long &lo, long long &hi)
+{
+    lo = o_lo;
+    hi = o_hi;
+    for (unsigned int j = a.S - 1; j > s; j--) {
+        lo = 2 * (lo - (long long)(a.st[j].len - 1));
+        hi = 2 * hi;
+    }
+}
+
+// One stage over the units [lo, hi) of a tile.  Staged element q of sb / sa is unit lo - (LEN - 1) + q of the
+// filter / delay branch.  Units below zero (start of the stream) are skipped: the next stage reads its windows there.
+template <int LEN, bool FINAL>
+__device__ __forceinline__ void cascade_stage(const float2 *__restrict__ sb, const float2 *__restrict__ sa,
+                                              const float *__restrict__ hs, unsigned int m, long long lo, unsigned int cnt,
+                                              float2 *__restrict__ nb, float2 *__restrict__ na, float2 *__restrict__ y,
+                                              float zeta)
+{
+    constexpr int R = kBlockUnits;
+    constexpr int NE = R + LEN;                                       // elements a thread reads (one spare: LEN + R - 1 used)
+    const unsigned int first = lo < 0 ? (unsigned int)(-lo) : 0;      // first unit (relative to lo) that exists
+    for (unsigned int t = (first & ~(R - 1u)) + R * threadIdx.x; t < cnt; t += R * blockDim.x) {
+        float2 e[NE];
+        const float4 *p = reinterpret_cast<const float4 *>(sb + phys(t));   // t is a multiple of 8: 16-byte aligned
+#pragma unroll
+        for (int j = 0; j < NE / 2; j++) {
+            // elements t + 2j, t + 2j + 1: pairs never straddle the padding
+            const float4 v = p[(2 * j + 2 * ((2 * j) >> 3)) / 2];
+            e[2 * j] = make_float2(v.x, v.y);
+            e[2 * j + 1] = make_float2(v.z, v.w);
+        }
+        float2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < LEN; k++) {
+            const float2 h = make_float2(hs[k], hs[k]);
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = __ffma2_rn(h, e[k + r], acc[r]);
+        }
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = add2(sa[phys(LEN - 1 + t + r - m)], acc[r]);
+        const bool whole = (t >= first) && (t + R <= cnt);
+        if (!FINAL) {
+            // outputs (t + 2j, t + 2j + 1) are the next stage's (b, a) pair at element t/2 + j
+            const unsigned int q = phys(t / 2);                       // t/2 is a multiple of 4: 16-byte aligned, no padding inside
+            if (whole) {
+                *reinterpret_cast<float4 *>(nb + q) = make_float4(v[0].x, v[0].y, v[2].x, v[2].y);
+                *reinterpret_cast<float4 *>(nb + q + 2) = make_float4(v[4].x, v[4].y, v[6].x, v[6].y);
+                *reinterpret_cast<float4 *>(na + q) = make_float4(v[1].x, v[1].y, v[3].x, v[3].y);
+                *reinterpret_cast<float4 *>(na + q + 2) = make_float4(v[5].x, v[5].y, v[7].x, v[7].y);
+            } else {
+#pragma unroll
+                for (int j = 0; j < R / 2; j++)
+                    if (t + 2 * j >= first && t + 2 * j < cnt) {      // first and cnt are even here
+                        nb[q + j] = v[2 * j];
+                        na[q + j] = v[2 * j + 1];
+                    }
+            }
+        } else {
+            float2 *yo = y + lo + t;                                  // lo >= 0 on the final stage, a multiple of 8
+            if (whole) {
+#pragma unroll
+                for (int j = 0; j < R / 2; j++)
+                    reinterpret_cast<float4 *>(yo)[j] = make_float4(v[2 * j].x * zeta, v[2 * j].y * zeta,
+                                                                    v[2 * j + 1].x * zeta, v[2 * j + 1].y * zeta);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (t + r < cnt) yo[r] = make_float2(v[r].x * zeta, v[r].y * zeta);
+            }
+        }
+    }
+}
+
+template <bool FINAL>
+__device__ __forceinline__ void cascade_stage_any(unsigned int len, const float2 *sb, const float2 *sa, const float *hs,
+                                                  unsigned int m, long long lo, unsigned int cnt, float2 *nb, float2 *na,
+                                                  float2 *y, float zeta)
+{
+    switch (len) {
+#define LC_STAGE(L) case L: cascade_stage<L, FINAL>(sb, sa, hs, m, lo, cnt, nb, na, y, zeta); break;
+        LC_STAGE(4) LC_STAGE(6) LC_STAGE(8) LC_STAGE(10) LC_STAGE(12) LC_STAGE(14) LC_STAGE(16) LC_STAGE(18)
+        LC_STAGE(20) LC_STAGE(22) LC_STAGE(24) LC_STAGE(26) LC_STAGE(28) LC_STAGE(30) LC_STAGE(32)
+#undef LC_STAGE
+    default: break;                                                   // the host only launches supported lengths
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+msresamp2_decim_fused_kernel(CascadeArgs a, const float2 *__restrict__ x, float2 *__restrict__ y, unsigned long long n_out)
+{
+    extern __shared__ float4 smem_f4[];
+    float *hs = reinterpret_cast<float *>(smem_f4);                        // kMaxFusedLen taps of the running stage
+    float2 *sm = reinterpret_cast<float2 *>(smem_f4) + kMaxFusedLen / 2;   // region 0 = [0, 2 cap0), region 1 after it
+    const long long o_lo = (long long)blockIdx.x * a.T;
+    const long long o_hi = (o_lo + a.T < (long long)n_out) ? o_lo + a.T : (long long)n_out;
+    const bool last_cta = (blockIdx.x == gridDim.x - 1);
+
+    // stage 0's sequences from the input: pair idx = (x[2 idx], x[2 idx + 1]) = (b, a); every load of a thread is in
+    // flight at once (cp.async), nothing passes through registers
+    {
+        const long long lo = (o_lo << (a.S - 1)) - (long long)a.back[0], hi = o_hi << (a.S - 1);
+        const CascadeStage &g = a.st[0];
+        const long long org = lo - (long long)(g.len - 1);
+        float2 *sb = sm, *sa = sm + a.cap[0];
+        const unsigned int cnt = (unsigned int)(hi - org);
+        if (org >= 0) {
+            // 32-bit shared addresses, one 64-bit pointer bump per pair
+            const float2 *src = x + 2 * org + 2 * threadIdx.x;
+            const unsigned int sb_addr = (unsigned int)__cvta_generic_to_shared(sb);
+            const unsigned int a_off = a.cap[0] * (unsigned int)sizeof(float2);
+#pragma unroll 4
+            for (unsigned int q = threadIdx.x; q < cnt; q += kThreads, src += 2 * kThreads) {
+                const unsigned int dst = sb_addr + phys(q) * (unsigned int)sizeof(float2);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + a_off), "l"(src + 1) : "memory");
+            }
+        } else {
+            for (unsigned int q = threadIdx.x; q < cnt; q += blockDim.x) {
+                const long long idx = org + q;
+                if (idx >= 0) {
+                    cp_async8(sb + phys(q), x + 2 * idx);
+                    cp_async8(sa + phys(q), x + 2 * idx + 1);
+                } else if (idx >= -(long long)g.len) {
+                    // (the staged range reaches below the window near the start of the stream; those elements
+                    // are never used: the first unit computed is unit 0)
+                    sb[phys(q)] = __ldg(g.w1 + ((long long)g.len + idx));
+                    sa[phys(q)] = __ldg(g.w0 + ((long long)g.len + idx));
+                }
+            }
+        }
+        cp_async_wait_all();
+    }
+    for (unsigned int s = 0; s < a.S; s++) {
+        const CascadeStage &g = a.st[s];
+        const long long lo = (o_lo << (a.S - 1 - s)) - (long long)a.back[s], hi = o_hi << (a.S - 1 - s);
+        const unsigned int r = s & 1;
+        const unsigned int cur_off = r ? 2 * a.cap[0] : 0, nxt_off = r ? 0 : 2 * a.cap[0];
+        const float2 *sb = sm + cur_off, *sa = sm + cur_off + a.cap[r];
+        float2 *nb = sm + nxt_off, *na = sm + nxt_off + a.cap[r ^ 1];
+        const bool final_stage = (s == a.S - 1);
+        for (unsigned int k = threadIdx.x; k < g.len; k += blockDim.x) hs[k] = __ldg(g.hb + k);
+        if (!final_stage && lo < 0) {
+            // the next stage's units below zero: its windows (unit org' + q with org' = lo / 2)
+            const CascadeStage &gn = a.st[s + 1];
+            const long long orgn = lo / 2;
+            for (long long q = threadIdx.x; orgn + q < 0; q += blockDim.x) {
+                if (orgn + q < -(long long)gn.len) continue;
+                nb[phys((unsigned int)q)] = __ldg(gn.w1 + ((long long)gn.len + orgn + q));
+                na[phys((unsigned int)q)] = __ldg(gn.w0 + ((long long)gn.len + orgn + q));
+            }
+        }
+        __syncthreads();                                                   // this stage's sequences and taps are in place
+        if (last_cta) {
+            // the windows after the block: the last len units of this stage's sequences
+            const long long org = lo - (long long)(g.len - 1);
+            for (unsigned int j = threadIdx.x; j < g.len; j += blockDim.x) {
+                const unsigned int q = phys((unsigned int)(hi - (long long)g.len + j - org));
+                g.next[j] = sa[q];
+                g.next[g.len + j] = sb[q];
+            }
+        }
+        const unsigned int cnt = (unsigned int)(hi - lo);
+        if (final_stage) cascade_stage_any<true>(g.len, sb, sa, hs, g.m, lo, cnt, nb, na, y, a.zeta);
+        else             cascade_stage_any<false>(g.len, sb, sa, hs, g.m, lo, cnt, nb, na, y, a.zeta);
+        __syncthreads();                                                   // hs and this stage's region are free again
+    }
+}
+
+// padded float2 capacity one array of stage s needs for a full tile (with the slack of the blocked reads)
+inline unsigned int cascade_capacity(const CascadeArgs &a, unsigned int s)
+{
+    long long lo, hi;
+    cascade_range(a, s, 0, a.T, lo, hi);
+    const unsigned int elems = (unsigned int)(hi - lo) + 2 * kBlockUnits + a.st[s].len + 2;
+    return (phys(elems) + 3) & ~3u;
+}
+
 inline unsigned int grid_for(unsigned long long total)
 {
     unsigned long long b = (total + kThreads - 1) / kThreads;
@@ -198,8 +513,15 @@ void units_dev(resamp2_crcf q, const float2 *d_x, unsigned long long n, float2 *
 {
     if (n == 0) return;
     const Windows w = windows_of(q);
-    resamp2_units_kernel<MODE><<<grid_for(n), kThreads, sizeof(float) * q->len, st>>>(
-        w, q->d_hb, q->m, d_x, d_y, n, scale, (reinterpret_cast<uintptr_t>(d_y) & 15) == 0);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_y)) & 15) == 0;
+    const size_t smem = tile_smem(q->len);
+    const unsigned long long tiles = (n + kTile - 1) / kTile;
+    if (aligned && n >= 4 * kTile && smem <= 48 * 1024 && tiles < (1ull << 31) && !getenv("LIQUID_CUDA_RESAMP2_SIMPLE")) {
+        resamp2_tile_kernel<MODE><<<(unsigned int)tiles, kThreads, smem, st>>>(w, q->d_hb, q->m, d_x, d_y, n, scale);
+    } else {
+        resamp2_units_kernel<MODE><<<grid_for(n), kThreads, sizeof(float) * q->len, st>>>(
+            w, q->d_hb, q->m, d_x, d_y, n, scale, (reinterpret_cast<uintptr_t>(d_y) & 15) == 0);
+    }
     LC_LAUNCH_CHECK();
     resamp2_units_roll_kernel<MODE><<<1, (q->len + 31) / 32 * 32, 0, st>>>(w, d_x, n, next_windows(q));
     LC_LAUNCH_CHECK();
@@ -260,6 +582,61 @@ void host_small(resamp2_crcf q, const liquid_float_complex *x, size_t n_in, liqu
     run(din, dout, q->stream);
     LC_CUDA_CHECK(cudaMemcpyAsync(y, dout, sizeof(float2) * n_out, cudaMemcpyDeviceToHost, q->stream));
     LC_CUDA_CHECK(cudaStreamSynchronize(q->stream));
+}
+
+// the whole decimating cascade in one launch; false when the shape is left to the stage-by-stage form
+bool decim_fused_dev(msresamp2_crcf q, const float2 *d_x, unsigned long long n_out, float2 *d_y, cudaStream_t st)
+{
+    if (q->S < 2 || q->S > (unsigned int)kMaxFusedStages || getenv("LIQUID_CUDA_MSRESAMP2_STAGED")) return false;
+    if (((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_y)) & 15) != 0) return false;
+    CascadeArgs a;
+    a.S = q->S;
+    a.zeta = q->zeta;
+    for (unsigned int s = 0; s < q->S; s++) {
+        resamp2_crcf h = q->hb[s];
+        if (h->len > kMaxFusedLen || h->len < 4) return false;
+        const Windows w = windows_of(h);
+        a.st[s] = CascadeStage{w.w0, w.w1, next_windows(h), h->d_hb, h->len, h->m};
+    }
+    for (unsigned int s = 0; s < q->S; s++) {
+        long long lo, hi;
+        cascade_range(a, s, 0, 0, lo, hi);
+        a.back[s] = (unsigned int)(-lo);
+    }
+    // final outputs per CTA: a multiple of 8, the largest for which stage 0 (the widest) is at most one 8-unit task
+    // per thread and the staged sequences fit ~72 KB (three CTAs per SM)
+    size_t smem = 0;
+    unsigned int best = 0;
+    for (unsigned int T = 8; T <= 2048; T += 8) {
+        a.T = T;
+        long long lo, hi;
+        cascade_range(a, 0, 0, T, lo, hi);
+        if ((unsigned long long)(hi - lo) > (unsigned long long)kBlockUnits * kThreads) break;
+        a.cap[0] = a.cap[1] = 0;
+        for (unsigned int s = 0; s < q->S; s++) a.cap[s & 1] = std::max(a.cap[s & 1], cascade_capacity(a, s));
+        if (sizeof(float) * kMaxFusedLen + sizeof(float2) * 2 * ((size_t)a.cap[0] + a.cap[1]) > 72 * 1024) break;
+        best = T;
+    }
+    if (best == 0) return false;
+    a.T = best;
+    a.cap[0] = a.cap[1] = 0;
+    for (unsigned int s = 0; s < q->S; s++) a.cap[s & 1] = std::max(a.cap[s & 1], cascade_capacity(a, s));
+    smem = sizeof(float) * kMaxFusedLen + sizeof(float2) * 2 * ((size_t)a.cap[0] + a.cap[1]);
+    if (n_out < 8ull * a.T) return false;
+    const unsigned long long tiles = (n_out + a.T - 1) / a.T;
+    if (tiles >= (1ull << 31)) return false;
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+    {
+        LC_CUDA_CHECK(cudaFuncSetAttribute(msresamp2_decim_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        // several CTAs per SM hide each other's load and barrier phases: ask for the full shared-memory carve-out
+        LC_CUDA_CHECK(cudaFuncSetAttribute(msresamp2_decim_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
+    }
+    msresamp2_decim_fused_kernel<<<(unsigned int)tiles, kThreads, smem, st>>>(a, d_x, d_y, n_out);
+    LC_LAUNCH_CHECK();
+    for (unsigned int s = 0; s < q->S; s++) q->hb[s]->cur ^= 1;
+    return true;
 }
 
 }  // namespace
@@ -541,6 +918,7 @@ void msresamp2_crcf_execute_block_dev(msresamp2_crcf _q, const void *_d_x, unsig
         LC_CUDA_CHECK(cudaMemcpyAsync(_d_y, _d_x, sizeof(float2) * _n, cudaMemcpyDeviceToDevice, st));
         return;
     }
+    if (!_q->interp && decim_fused_dev(_q, (const float2 *)_d_x, _n, (float2 *)_d_y, st)) return;
     const size_t half = (size_t)_n * (_q->M / 2);                  // the largest intermediate stream
     float2 *buf[2] = {nullptr, nullptr};
     if (_q->S > 1) {

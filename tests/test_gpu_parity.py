@@ -743,6 +743,29 @@ def test_msresamp2_vs_reference_fixture_and_oracle(L, orc, refrn2):
         assert np.abs(got - want).max() < 4e-6 * max(1.0, np.abs(want).max())
 
 
+def test_msresamp2_fused_cascade_equals_stage_by_stage(L, orc, monkeypatch):
+    """the one-kernel decimating cascade against the stage-by-stage form of the same library, bit for bit: several
+    stage counts, blocks of awkward sizes (state carried through every stage's windows), and against the oracle"""
+    x = orc.synth_input(3 << 20, seed=0x51)
+    for S, fc, As in ((2, 0.3, 60.0), (3, 0.45, 80.0), (4, 0.4, 60.0), (6, 0.2, 70.0), (8, 0.1, 60.0)):
+        M = 1 << S
+        cuts = [0, 40000 * M // 16 * 16 // M * M, (40000 * M // 16 * 16 // M + 9001) * M, len(x) // M * M]
+        cuts = [min(c, len(x) // M * M) for c in cuts]
+        outs = {}
+        for staged in (False, True):
+            if staged:
+                monkeypatch.setenv("LIQUID_CUDA_MSRESAMP2_STAGED", "1")
+            else:
+                monkeypatch.delenv("LIQUID_CUDA_MSRESAMP2_STAGED", raising=False)
+            q = L.msresamp2_crcf(L.LIQUID_RESAMP_DECIM, S, fc, 0.0, As)
+            outs[staged] = np.concatenate([q.execute_block(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:]) if b > a])
+        monkeypatch.delenv("LIQUID_CUDA_MSRESAMP2_STAGED", raising=False)
+        assert np.array_equal(outs[False].view(np.uint32), outs[True].view(np.uint32)), S
+        if S <= 4:
+            want = orc.Msresamp2(orc.RESAMP_DECIM, S, fc, 0.0, As).execute_block(x[:cuts[-1]])
+            assert np.abs(outs[False] - want).max() < 4e-6 * max(1.0, np.abs(want).max()), S
+
+
 def test_resamp2_long_blocks_vs_oracle(L, orc):
     """2^21 samples through each mode, two blocks with an odd split for the filter mode"""
     x = orc.synth_input(1 << 21, seed=0x99)
@@ -754,6 +777,14 @@ def test_resamp2_long_blocks_vs_oracle(L, orc):
         fn = getattr(q, mode + "_execute_block")
         got = np.concatenate([fn(x[:cut]), fn(x[cut:n])])
         assert np.abs(got - getattr(o, mode + "_execute")(x[:n])).max() < 2e-6, mode
+    # the modes in turn on ONE object, long blocks (the windows each mode leaves are the next one's history)
+    q, o = L.resamp2_crcf(m, 0.05, 60.0), orc.Resamp2(m, 0.05, 60.0)
+    pos = 0
+    for mode, ln in (("decim", 100000), ("interp", 50001), ("analyzer", 70002), ("interp", 40000), ("synthesizer", 60000),
+                     ("decim", 40000)):
+        seg = x[pos:pos + ln]
+        pos += ln
+        assert np.abs(getattr(q, mode + "_execute_block")(seg) - getattr(o, mode + "_execute")(seg)).max() < 2e-6, mode
     q, o = L.resamp2_crcf(m, 0.05, 60.0), orc.Resamp2(m, 0.05, 60.0)
     a0, a1 = q.filter_execute_block(x[:777777])
     b0, b1 = q.filter_execute_block(x[777777:])
