@@ -122,6 +122,17 @@ void msresamp2_crcf_reset(msresamp2_crcf _q);
 float msresamp2_crcf_get_delay(msresamp2_crcf _q);
 void msresamp2_crcf_execute(msresamp2_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
 
+/* ---- fftfilt_crcf (FIR filtering through 2n-point transforms): liquid.h:2192-2232 -> src/filter/src/fftfilt.c:68-266.
+ *      SURVEY.md 8(f) item 3.  x and y must not overlap in the device-pointer form. */
+typedef struct fftfilt_crcf_s * fftfilt_crcf;
+fftfilt_crcf fftfilt_crcf_create(float *_h, unsigned int _h_len, unsigned int _n);
+void fftfilt_crcf_destroy(fftfilt_crcf _q);
+void fftfilt_crcf_reset(fftfilt_crcf _q);
+void fftfilt_crcf_print(fftfilt_crcf _q);
+void fftfilt_crcf_set_scale(fftfilt_crcf _q, float _scale);
+void fftfilt_crcf_execute(fftfilt_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
+unsigned int fftfilt_crcf_get_length(fftfilt_crcf _q);
+
 /* ---- spgramcf (windowed-FFT spectral periodogram): liquid.h:1230-1316 -> src/fft/src/spgramcf.c -> spgram.c:57-398.
  *      SURVEY.md 8(f) item 2. */
 typedef struct spgramcf_s * spgramcf;
@@ -320,6 +331,10 @@ void resamp2_crcf_interp_execute_block_dev(resamp2_crcf _q, const void *_d_x, un
 unsigned int msresamp2_crcf_get_stage_semilength(msresamp2_crcf _q, unsigned int _i);
 void msresamp2_crcf_execute_block(msresamp2_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
 void msresamp2_crcf_execute_block_dev(msresamp2_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
+
+/* ---- fftfilt_crcf: _n_blocks blocks of n samples in one call (all blocks run in parallel), host / device pointers ---- */
+void fftfilt_crcf_execute_block(fftfilt_crcf _q, liquid_float_complex *_x, unsigned int _n_blocks, liquid_float_complex *_y);
+void fftfilt_crcf_execute_block_dev(fftfilt_crcf _q, const void *_d_x, unsigned long long _n_blocks, void *_d_y, void *_stream);
 
 /* ---- spgramcf: device-pointer forms (the whole block becomes one batch of overlapping transforms) ---- */
 void spgramcf_accumulate_psd_dev(spgramcf _q, const void *_d_x, float _alpha, unsigned long long _n, void *_stream);

@@ -123,6 +123,15 @@ _sig("resamp2_crcf_filter_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp, _v
 for _nm in ("analyzer", "synthesizer", "decim", "interp"):
     _sig("resamp2_crcf_%s_execute_block" % _nm, None, _vp, _vp, _u, _vp)
     _sig("resamp2_crcf_%s_execute_block_dev" % _nm, None, _vp, _vp, _ull, _vp, _vp)
+_sig("fftfilt_crcf_create", _vp, _f_p, _u, _u)
+_sig("fftfilt_crcf_destroy", None, _vp)
+_sig("fftfilt_crcf_reset", None, _vp)
+_sig("fftfilt_crcf_print", None, _vp)
+_sig("fftfilt_crcf_set_scale", None, _vp, _fl)
+_sig("fftfilt_crcf_get_length", _u, _vp)
+_sig("fftfilt_crcf_execute", None, _vp, _cf_p, _cf_p)
+_sig("fftfilt_crcf_execute_block", None, _vp, _vp, _u, _vp)
+_sig("fftfilt_crcf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
 _sig("msresamp2_crcf_create", _vp, _i, _u, _fl, _fl, _fl)
 _sig("msresamp2_crcf_destroy", None, _vp)
 _sig("msresamp2_crcf_print", None, _vp)
@@ -656,6 +665,44 @@ class msresamp2_crcf(_Handle):
 
     def execute_block_dev(self, d_x, n, d_y, stream=0):
         lib.msresamp2_crcf_execute_block_dev(self._h, d_x, n, d_y, stream)
+
+
+class fftfilt_crcf(_Handle):
+    """liquid.h:2192-2232 (src/filter/src/fftfilt.c): FIR filtering of blocks of n samples through 2n-point FFTs."""
+    _destroy = "fftfilt_crcf_destroy"
+
+    def __init__(self, h, n):
+        hh = _f32(h)
+        self.n = n
+        super().__init__(lib.fftfilt_crcf_create(hh, len(hh), n))
+
+    @classmethod
+    def create(cls, h, n):
+        return cls(h, n)
+
+    def reset(self):
+        lib.fftfilt_crcf_reset(self._h)
+
+    def set_scale(self, scale):
+        lib.fftfilt_crcf_set_scale(self._h, scale)
+
+    def get_length(self):
+        return lib.fftfilt_crcf_get_length(self._h)
+
+    def execute(self, x):
+        y = np.empty(self.n, np.complex64)
+        lib.fftfilt_crcf_execute(self._h, _c64(x), y)
+        return y
+
+    def execute_block(self, x):
+        x = _c64(x)
+        nb = x.size // self.n
+        y = np.empty(nb * self.n, np.complex64)
+        lib.fftfilt_crcf_execute_block(self._h, _ptr(x), nb, _ptr(y))
+        return y
+
+    def execute_block_dev(self, d_x, n_blocks, d_y, stream=0):
+        lib.fftfilt_crcf_execute_block_dev(self._h, d_x, n_blocks, d_y, stream)
 
 
 class firinterp_crcf(_Handle):

@@ -10,6 +10,7 @@ the record of how the fixture was made.
   ms_*     msresamp2_crcf(type, stages, fc, 0, As): outputs, get_delay and the stage semi-lengths implied by
            estimate_req_filter_len
   len_*    estimate_req_filter_len points
+  ff_*     fftfilt_crcf(h, n) over several blocks (random taps / a Kaiser low-pass, with and without set_scale)
 """
 import ctypes as C
 import os
@@ -43,6 +44,18 @@ for typ, S, fc, As in [(0, 1, 0.25, 60.0), (0, 3, 0.4, 60.0), (0, 5, 0.1, 80.0),
     out[tag + "_args"] = np.array([typ, S, fc, As, delay], np.float64)
     out[tag + "_x"] = x
     out[tag + "_y"] = y
+
+# fftfilt_crcf: seeded random taps and a Kaiser low-pass; power-of-two and other block sizes; a set_scale case
+rng = np.random.default_rng(20261020)
+for h_len, n, scale in [(5, 8, None), (21, 32, None), (64, 64, 0.5), (33, 100, None), (129, 128, 2.0), (200, 512, None),
+                        (17, 30, None)]:
+    tag = "ff_h%d_n%d" % (h_len, n)
+    h = rng.standard_normal(h_len).astype(np.float32) if h_len != 129 else O.firdes_kaiser(129, 0.2, 60.0)
+    x = O.synth_input(n * (9 if n < 200 else 4), seed=0x5EEDD000 + n)
+    out[tag + "_args"] = np.array([h_len, n, -1.0 if scale is None else scale], np.float64)
+    out[tag + "_h"] = h
+    out[tag + "_x"] = x
+    out[tag + "_y"] = O.ref_fftfilt_blocks(h, n, x, scale)
 
 R = O.ref()
 R.estimate_req_filter_len.restype = C.c_uint

@@ -1120,6 +1120,58 @@ void orc_msresamp2_execute_block(orc_msresamp2 q, const orc_cf *x, unsigned int 
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* fftfilt_crcf: FIR filtering by overlap-add with 2n-point transforms  */
+/* src/filter/src/fftfilt.c                                                                  */
+/* ------------------------------------------------------------------------------------ */
+
+struct orc_fftfilt_s {
+    unsigned int h_len, n;
+    orc_cf *H;                  /* transform of the zero-padded taps, 2n bins */
+    orc_cf *tail;               /* second half of the previous block's result */
+    orc_cf *tb, *fb;            /* time / frequency work arrays, 2n each */
+    float scale;
+};
+
+/* fftfilt.c:68-129 */
+orc_fftfilt orc_fftfilt_create(const float *h, unsigned int h_len, unsigned int n)
+{
+    if (h_len == 0 || n < h_len - 1) return NULL;
+    orc_fftfilt q = xmalloc(sizeof *q);
+    q->h_len = h_len; q->n = n;
+    unsigned int N = 2 * n;
+    q->H = xmalloc(N * sizeof *q->H);
+    q->tb = xmalloc(N * sizeof *q->tb);
+    q->fb = xmalloc(N * sizeof *q->fb);
+    q->tail = xmalloc(n * sizeof *q->tail);
+    for (unsigned int i = 0; i < N; i++) q->tb[i] = cf(i < h_len ? h[i] : 0.0f, 0.0f);
+    orc_fft_run(N, q->tb, q->H, ORC_FFT_FORWARD);
+    orc_fftfilt_set_scale(q, 1.0f);
+    orc_fftfilt_reset(q);
+    return q;
+}
+
+void orc_fftfilt_destroy(orc_fftfilt q) { if (q) { free(q->H); free(q->tb); free(q->fb); free(q->tail); free(q); } }
+void orc_fftfilt_reset(orc_fftfilt q) { memset(q->tail, 0, q->n * sizeof *q->tail); }            /* fftfilt.c:155-161 */
+void orc_fftfilt_set_scale(orc_fftfilt q, float scale) { q->scale = scale / (float)(2 * q->n); }  /* fftfilt.c:184-189 */
+
+/* fftfilt.c:195-260 over n_blocks blocks of n samples */
+void orc_fftfilt_execute_blocks(orc_fftfilt q, const orc_cf *x, unsigned int n_blocks, orc_cf *y)
+{
+    unsigned int n = q->n, N = 2 * q->n;
+    for (unsigned int b = 0; b < n_blocks; b++) {
+        for (unsigned int i = 0; i < n; i++) { q->tb[i] = x[(size_t)b * n + i]; q->tb[n + i] = cf(0.0f, 0.0f); }
+        orc_fft_run(N, q->tb, q->fb, ORC_FFT_FORWARD);
+        for (unsigned int i = 0; i < N; i++) q->fb[i] = cf_mul(q->fb[i], q->H[i]);
+        orc_fft_run(N, q->fb, q->tb, ORC_FFT_BACKWARD);
+        for (unsigned int i = 0; i < n; i++) {
+            orc_cf v = cf(q->tb[i].re + q->tail[i].re, q->tb[i].im + q->tail[i].im);
+            y[(size_t)b * n + i] = cf(v.re * q->scale, v.im * q->scale);
+        }
+        memcpy(q->tail, q->tb + n, n * sizeof *q->tail);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* spgramcf: windowed-FFT spectral periodogram                      */
 /* src/fft/src/spgramcf.c:27-51 instantiating src/fft/src/spgram.c                        */
 /* ------------------------------------------------------------------------------------ */

@@ -138,6 +138,13 @@ def lib():
         L.orc_msresamp2_stage_m.argtypes = [C.c_void_p, C.c_uint]
         L.orc_msresamp2_get_delay.restype = C.c_float
         L.orc_msresamp2_get_delay.argtypes = [C.c_void_p]
+        L.orc_fftfilt_create.restype = C.c_void_p
+        L.orc_fftfilt_create.argtypes = [c_f_p, C.c_uint, C.c_uint]
+        L.orc_fftfilt_destroy.argtypes = [C.c_void_p]
+        L.orc_fftfilt_reset.argtypes = [C.c_void_p]
+        L.orc_fftfilt_set_scale.argtypes = [C.c_void_p, C.c_float]
+        L.orc_fftfilt_execute_blocks.restype = None
+        L.orc_fftfilt_execute_blocks.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
         L.orc_msresamp2_execute_block.restype = None
         L.orc_msresamp2_execute_block.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
         L.orc_firinterp_reset.argtypes = [C.c_void_p]
@@ -431,6 +438,28 @@ class Msresamp2(_Obj):
         n = len(x) if self.type == RESAMP_INTERP else len(x) // M
         y = np.empty(n * M if self.type == RESAMP_INTERP else n, np.complex64)
         lib().orc_msresamp2_execute_block(self.h, x, n, y)
+        return y
+
+
+class Fftfilt(_Obj):
+    """fftfilt_crcf: overlap-add FIR on blocks of n samples"""
+    _destroy = "orc_fftfilt_destroy"
+
+    def __init__(self, h, n):
+        self.n = n
+        super().__init__(lib().orc_fftfilt_create(_f(h), len(h), n))
+
+    def reset(self):
+        lib().orc_fftfilt_reset(self.h)
+
+    def set_scale(self, scale):
+        lib().orc_fftfilt_set_scale(self.h, scale)
+
+    def execute_blocks(self, x):
+        x = _cf(x)
+        nb = len(x) // self.n
+        y = np.empty(nb * self.n, np.complex64)
+        lib().orc_fftfilt_execute_blocks(self.h, x, nb, y)
         return y
 
 
@@ -826,6 +855,23 @@ def ref_msresamp2_block(type, S, fc, f0, As, x):
     delay = R.msresamp2_crcf_get_delay(q)
     R.msresamp2_crcf_destroy(q)
     return y, delay
+
+
+def ref_fftfilt_blocks(h, n, x, scale=None):
+    R = ref()
+    R.fftfilt_crcf_create.restype = C.c_void_p; R.fftfilt_crcf_create.argtypes = [c_f_p, C.c_uint, C.c_uint]
+    R.fftfilt_crcf_set_scale.argtypes = [C.c_void_p, C.c_float]
+    R.fftfilt_crcf_execute.argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+    R.fftfilt_crcf_destroy.argtypes = [C.c_void_p]
+    q = C.c_void_p(R.fftfilt_crcf_create(_f(h), len(h), n))
+    if scale is not None:
+        R.fftfilt_crcf_set_scale(q, scale)
+    x = _cf(x)
+    y = np.empty(len(x) // n * n, np.complex64)
+    for b in range(len(x) // n):
+        R.fftfilt_crcf_execute(q, x[b * n:(b + 1) * n], y[b * n:(b + 1) * n])
+    R.fftfilt_crcf_destroy(q)
+    return y
 
 
 class RefSpgramcf:

@@ -793,6 +793,42 @@ def test_resamp2_long_blocks_vs_oracle(L, orc):
     assert np.abs(np.concatenate([a1, b1]) - w1).max() < 2e-6
 
 
+# ------------------------------------------------------------------ fftfilt
+def test_fftfilt_vs_reference_fixture_and_oracle(L, orc, refrn2, monkeypatch):
+    """the compiled reference's outputs (power-of-two and other block sizes, set_scale), state carried over calls of
+    one and of several blocks, the shared-memory kernel against the scratch-buffer path, long inputs against the
+    oracle's overlap-add and against firfilt"""
+    from test_oracle import _ff_cases
+    for tag, n, scale in _ff_cases(refrn2):
+        x, h, want = refrn2[tag + "_x"], refrn2[tag + "_h"], refrn2[tag + "_y"]
+        for generic in (False, True):
+            if generic:
+                monkeypatch.setenv("LIQUID_CUDA_FFTFILT_GENERIC", "1")
+            else:
+                monkeypatch.delenv("LIQUID_CUDA_FFTFILT_GENERIC", raising=False)
+            q = L.fftfilt_crcf(h, n)
+            assert q.get_length() == len(h)
+            if scale is not None:
+                q.set_scale(scale)
+            got = np.concatenate([q.execute(x[:n]), q.execute_block(x[n:3 * n]), q.execute_block(x[3 * n:])])
+            assert np.abs(got - want).max() < 2e-6 * np.abs(want).max(), (tag, generic)
+            q.reset()
+            assert np.abs(q.execute_block(x) - want).max() < 2e-6 * np.abs(want).max(), (tag, generic)
+        monkeypatch.delenv("LIQUID_CUDA_FFTFILT_GENERIC", raising=False)
+    x = orc.synth_input(1 << 20, seed=0x41)
+    for h_len, n in ((129, 128), (1025, 1024), (300, 2048), (2049, 2048), (200, 500)):
+        h = orc.firdes_kaiser(h_len, 0.15, 60.0)
+        q = L.fftfilt_crcf(h, n)
+        nb = len(x) // n
+        cut = (nb // 3) * n
+        got = np.concatenate([q.execute_block(x[:cut]), q.execute_block(x[cut:nb * n])])
+        want = orc.Fftfilt(h, n).execute_blocks(x[:nb * n])
+        assert np.abs(got - want).max() < 4e-6 * np.abs(want).max(), (h_len, n)
+        if h_len <= 300:
+            ff = L.firfilt_crcf.create(h).execute_block(x[:nb * n])
+            assert np.abs(got - ff).max() < 4e-6 * np.abs(want).max(), (h_len, n)
+
+
 # ------------------------------------------------------------------ spgramcf (SURVEY 8f item 2)
 def test_spgramcf_vs_reference_fixture_and_oracle(L, orc, refrn):
     """every entry point against the compiled reference's outputs (power-of-two and other nfft), plus a

@@ -515,3 +515,29 @@ def test_resamp2_properties(orc):
     q.clear()
     z0, _ = q.filter_execute(z)
     assert np.abs(up - 2 * z0).max() < 2e-6
+
+
+# ------------------------------------------------------------------ fftfilt
+def _ff_cases(fx):
+    for name in sorted(k for k in fx if k.startswith("ff_") and k.endswith("_args")):
+        h_len, n, scale = fx[name]
+        yield name[:-5], int(n), (None if scale < 0 else float(scale))
+
+
+def test_fixture_fftfilt(orc, refrn2):
+    for tag, n, scale in _ff_cases(refrn2):
+        q = orc.Fftfilt(refrn2[tag + "_h"], n)
+        if scale is not None:
+            q.set_scale(scale)
+        want = refrn2[tag + "_y"]
+        assert np.abs(q.execute_blocks(refrn2[tag + "_x"]) - want).max() < 1e-6 * np.abs(want).max(), tag
+
+
+def test_fftfilt_is_firfilt(orc):
+    """what the object stands for: the causal linear convolution, however the blocks are cut"""
+    h = orc.firdes_kaiser(57, 0.2, 60.0)
+    x = orc.synth_input(64 * 20, seed=31)
+    want = orc.Firfilt(h=h).execute_block(x)
+    for n in (56, 64, 80):
+        got = orc.Fftfilt(h, n).execute_blocks(x[: len(x) // n * n])
+        assert np.abs(got - want[: len(got)]).max() < 2e-6

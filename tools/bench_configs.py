@@ -3,7 +3,7 @@
 measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
 events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
 
-  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [f4] [s] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
+  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [f4] [f5] [s] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
 """
 import argparse
 import json
@@ -213,6 +213,20 @@ def main():
         report("f4d: msresamp2_crcf decimator 4 stages (m=%s), 2^28 input samples" % qm.stage_semilengths(), n,
                8 + 8 / 16, ms, ln, {"note": "algorithmic bytes: input read once, output written once; the "
                                             "intermediate streams of the stage-by-stage form are extra traffic"})
+        del x, y
+    if "f5" in args.configs:
+        # fftfilt_crcf, 2^28 samples: 1025 taps in blocks of 1024, 257 taps in blocks of 256
+        import numpy as np
+        n_s = 1 << 28
+        x = torch.empty(2 * n_s, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * n_s, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr(), n_s, stream=st.cuda_stream)
+        for h_len, n in ((1025, 1024), (257, 256), (2049, 2048)):
+            h = L.liquid_firdes_kaiser(h_len, 0.2, 60.0, 0.0)
+            q = L.fftfilt_crcf(h, n)
+            ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n_s // n, y.data_ptr(), st.cuda_stream))
+            report("f5: fftfilt_crcf %d taps, blocks of %d (2n = %d point transforms), 2^28 samples" % (h_len, n, 2 * n),
+                   n_s, 16, ms, ln)
         del x, y
     if "fft" in args.configs:
         # a11: the batched complex FFT on its own (fft_execute_batch_dev), 2^28 points per step, out of place
