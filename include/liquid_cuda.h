@@ -149,6 +149,18 @@ void spgramcf_accumulate_psd(spgramcf _q, liquid_float_complex *_x, float _alpha
 void spgramcf_write_accumulation(spgramcf _q, float *_x);
 void spgramcf_estimate_psd(spgramcf _q, liquid_float_complex *_x, unsigned int _n, float *_psd);
 
+/* ---- asgramcf (ASCII spectrogram over spgramcf): liquid.h:1333-1395 -> src/fft/src/asgram.c:48-213.
+ *      _ascii holds nfft characters (no terminator is written, as in the reference). */
+typedef struct asgramcf_s * asgramcf;
+asgramcf asgramcf_create(unsigned int _nfft);
+void asgramcf_destroy(asgramcf _q);
+void asgramcf_reset(asgramcf _q);
+void asgramcf_set_scale(asgramcf _q, float _offset, float _scale);
+void asgramcf_push(asgramcf _q, liquid_float_complex _x);
+void asgramcf_write(asgramcf _q, liquid_float_complex *_x, unsigned int _n);
+void asgramcf_execute(asgramcf _q, char *_ascii, float *_peakval, float *_peakfreq);
+void asgramcf_print(asgramcf _q);
+
 /* ---- firpfbch2_crcf: liquid.h:5754-5793 -> src/multichannel/src/firpfbch2.c:66-358 */
 typedef struct firpfbch2_crcf_s * firpfbch2_crcf;
 firpfbch2_crcf firpfbch2_crcf_create(int _type, unsigned int _M, unsigned int _m, float *_h);

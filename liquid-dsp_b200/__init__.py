@@ -123,6 +123,14 @@ _sig("resamp2_crcf_filter_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp, _v
 for _nm in ("analyzer", "synthesizer", "decim", "interp"):
     _sig("resamp2_crcf_%s_execute_block" % _nm, None, _vp, _vp, _u, _vp)
     _sig("resamp2_crcf_%s_execute_block_dev" % _nm, None, _vp, _vp, _ull, _vp, _vp)
+_sig("asgramcf_create", _vp, _u)
+_sig("asgramcf_destroy", None, _vp)
+_sig("asgramcf_reset", None, _vp)
+_sig("asgramcf_set_scale", None, _vp, _fl, _fl)
+_sig("asgramcf_push", None, _vp, _cf)
+_sig("asgramcf_write", None, _vp, _cf_p, _u)
+_sig("asgramcf_execute", None, _vp, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_float))
+_sig("asgramcf_print", None, _vp)
 _sig("fftfilt_crcf_create", _vp, _f_p, _u, _u)
 _sig("fftfilt_crcf_destroy", None, _vp)
 _sig("fftfilt_crcf_reset", None, _vp)
@@ -665,6 +673,42 @@ class msresamp2_crcf(_Handle):
 
     def execute_block_dev(self, d_x, n, d_y, stream=0):
         lib.msresamp2_crcf_execute_block_dev(self._h, d_x, n, d_y, stream)
+
+
+class asgramcf(_Handle):
+    """liquid.h:1333-1395 (src/fft/src/asgram.c): ASCII spectrogram; execute() -> (string, peak dB, peak frequency)."""
+    _destroy = "asgramcf_destroy"
+
+    def __init__(self, nfft):
+        self.nfft = nfft
+        super().__init__(lib.asgramcf_create(nfft))
+
+    @classmethod
+    def create(cls, nfft):
+        return cls(nfft)
+
+    def reset(self):
+        lib.asgramcf_reset(self._h)
+
+    def set_scale(self, offset, scale):
+        lib.asgramcf_set_scale(self._h, offset, scale)
+
+    def push(self, v):
+        v = complex(v)
+        lib.asgramcf_push(self._h, _cf(v.real, v.imag))
+
+    def write(self, x):
+        x = _c64(x)
+        lib.asgramcf_write(self._h, x, x.size)
+
+    def execute(self):
+        buf = C.create_string_buffer(self.nfft + 1)
+        pv, pf = C.c_float(), C.c_float()
+        lib.asgramcf_execute(self._h, buf, C.byref(pv), C.byref(pf))
+        return buf.raw[:self.nfft].decode("ascii"), pv.value, pf.value
+
+    def print(self):
+        lib.asgramcf_print(self._h)
 
 
 class fftfilt_crcf(_Handle):

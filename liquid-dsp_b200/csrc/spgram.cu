@@ -532,3 +532,113 @@ void spgramcf_estimate_psd(spgramcf _q, liquid_float_complex *_x, unsigned int _
 unsigned int spgramcf_get_num_transforms(spgramcf _q) { return _q->num_transforms; }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ asgramcf
+// ASCII spectrogram on top of spgramcf: liquid.h:1333-1395 -> src/fft/src/asgram.c (create :48-87, set_scale :113-128,
+// execute :157-195, print :199-213).  The transform of the buffer is spgramcf's; one more tiny kernel shifts the
+// spectrum, takes 10 log10 |X| (the reference's quantity: the magnitude, not its square), maps it to the ten level
+// characters and finds the first maximum.
+struct asgramcf_s {
+    unsigned int nfft = 0;
+    spgramcf periodogram = nullptr;
+    float levels[10];
+    char levelchar[10];
+    float scale = 10.0f, offset = 0.0f;
+    lc::DevBuf out;                 // [nfft] chars, then (peak value, peak frequency) floats
+};
+
+namespace {
+struct AsgramLevels {
+    float levels[10];
+    char levelchar[10];
+};
+
+__global__ void asgram_levels_kernel(const float2 *__restrict__ X, unsigned int nfft, AsgramLevels lv, char *__restrict__ ascii,
+                                     float *__restrict__ psd, float *__restrict__ peak)
+{
+    for (unsigned int i = threadIdx.x; i < nfft; i += blockDim.x) {
+        const float2 v = X[(i + nfft / 2) % nfft];
+        const float p = 10 * log10f(hypotf(v.x, v.y));
+        psd[i] = p;
+        char c = lv.levelchar[0];
+        for (int j = 0; j < 10; j++)
+            if (p > lv.levels[j]) c = lv.levelchar[j];
+        ascii[i] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float best = psd[0];
+        unsigned int arg = 0;
+        for (unsigned int i = 1; i < nfft; i++)
+            if (psd[i] > best) { best = psd[i]; arg = i; }
+        peak[0] = best;
+        peak[1] = (float)arg / (float)nfft - 0.5f;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+asgramcf asgramcf_create(unsigned int _nfft)
+{
+    if (_nfft < 2) lc::fatal("asgramcf_create", "fft size must be at least 2");
+    asgramcf q = new asgramcf_s();
+    q->nfft = _nfft;
+    q->periodogram = spgramcf_create_kaiser(_nfft, _nfft, 10.0f);
+    const char chars[10] = {' ', '.', ',', '-', '+', '*', '&', 'N', 'M', '#'};
+    for (int i = 0; i < 10; i++) q->levelchar[i] = chars[i];
+    asgramcf_set_scale(q, 0.0f, 10.0f);
+    return q;
+}
+
+void asgramcf_destroy(asgramcf _q)
+{
+    if (!_q) return;
+    spgramcf_destroy(_q->periodogram);
+    _q->out.release();
+    delete _q;
+}
+
+void asgramcf_reset(asgramcf _q) { spgramcf_reset(_q->periodogram); }
+
+void asgramcf_set_scale(asgramcf _q, float _offset, float _scale)
+{
+    if (_scale <= 0.0f) lc::fatal("asgramcf_set_scale", "scale must be greater than zero");
+    _q->offset = _offset;
+    _q->scale = _scale;
+    for (unsigned int i = 0; i < 10; i++) _q->levels[i] = _q->offset + i * _q->scale;
+}
+
+void asgramcf_push(asgramcf _q, liquid_float_complex _x) { spgramcf_push(_q->periodogram, _x); }
+void asgramcf_write(asgramcf _q, liquid_float_complex *_x, unsigned int _n) { spgramcf_write(_q->periodogram, _x, _n); }
+
+void asgramcf_execute(asgramcf _q, char *_ascii, float *_peakval, float *_peakfreq)
+{
+    spgramcf sp = _q->periodogram;
+    spgramcf_execute(sp, nullptr);                                  // the spectrum stays on the device
+    const float2 *d_X = (const float2 *)sp->spectra.get(sizeof(float2) * _q->nfft);
+    const size_t chars = ((size_t)_q->nfft + 15) & ~(size_t)15;
+    char *d_out = (char *)_q->out.get(chars + sizeof(float) * ((size_t)_q->nfft + 2));
+    float *d_psd = (float *)(d_out + chars);
+    float *d_peak = d_psd + _q->nfft;
+    AsgramLevels lv;
+    for (int i = 0; i < 10; i++) { lv.levels[i] = _q->levels[i]; lv.levelchar[i] = _q->levelchar[i]; }
+    asgram_levels_kernel<<<1, 256, 0, sp->stream>>>(d_X, _q->nfft, lv, d_out, d_psd, d_peak);
+    LC_LAUNCH_CHECK();
+    float peak[2];
+    LC_CUDA_CHECK(cudaMemcpyAsync(_ascii, d_out, _q->nfft, cudaMemcpyDeviceToHost, sp->stream));
+    LC_CUDA_CHECK(cudaMemcpyAsync(peak, d_peak, sizeof(peak), cudaMemcpyDeviceToHost, sp->stream));
+    LC_CUDA_CHECK(cudaStreamSynchronize(sp->stream));
+    *_peakval = peak[0];
+    *_peakfreq = peak[1];
+}
+
+void asgramcf_print(asgramcf _q)
+{
+    std::vector<char> ascii(_q->nfft + 1, '\0');
+    float maxval, maxfreq;
+    asgramcf_execute(_q, ascii.data(), &maxval, &maxfreq);
+    printf(" > %s < pk%5.1f dB [%5.2f]\n", ascii.data(), maxval, maxfreq);
+}
+
+}  // extern "C"

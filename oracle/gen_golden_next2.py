@@ -10,6 +10,7 @@ the record of how the fixture was made.
   ms_*     msresamp2_crcf(type, stages, fc, 0, As): outputs, get_delay and the stage semi-lengths implied by
            estimate_req_filter_len
   len_*    estimate_req_filter_len points
+  asg_*    asgramcf(nfft) after a write of a tone plus noise: the character string and the peak (default and custom scale)
   ff_*     fftfilt_crcf(h, n) over several blocks (random taps / a Kaiser low-pass, with and without set_scale)
 """
 import ctypes as C
@@ -56,6 +57,18 @@ for h_len, n, scale in [(5, 8, None), (21, 32, None), (64, 64, 0.5), (33, 100, N
     out[tag + "_h"] = h
     out[tag + "_x"] = x
     out[tag + "_y"] = O.ref_fftfilt_blocks(h, n, x, scale)
+
+# asgramcf: a tone plus noise, default and custom scale
+for nfft, offset, scale in [(64, None, None), (72, -20.0, 5.0), (256, -30.0, 4.0)]:
+    tag = "asg_n%d" % nfft
+    t = np.arange(3 * nfft + 5)
+    x = (O.synth_input(len(t), seed=0x5EEDE000 + nfft) * np.float32(0.05)
+         + np.exp(2j * np.pi * 0.21 * t).astype(np.complex64)).astype(np.complex64)
+    ascii_, pv, pf = O.ref_asgramcf(nfft, x, offset, scale)
+    out[tag + "_args"] = np.array([nfft, np.nan if offset is None else offset, np.nan if scale is None else scale], np.float64)
+    out[tag + "_x"] = x
+    out[tag + "_ascii"] = np.frombuffer(ascii_.encode("ascii"), np.uint8).copy()
+    out[tag + "_peak"] = np.array([pv, pf], np.float32)
 
 R = O.ref()
 R.estimate_req_filter_len.restype = C.c_uint

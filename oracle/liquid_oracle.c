@@ -1316,6 +1316,48 @@ void orc_spgramcf_estimate_psd(orc_spgramcf q, const orc_cf *x, unsigned int n, 
 
 unsigned int orc_spgramcf_num_transforms(orc_spgramcf q) { return q->num_transforms; }
 
+/* asgramcf: ASCII spectrogram over spgramcf.  src/fft/src/asgram.c:48-195 */
+struct orc_asgramcf_s {
+    unsigned int nfft;
+    orc_spgramcf sp;
+    float levels[10];
+};
+
+orc_asgramcf orc_asgramcf_create(unsigned int nfft)
+{
+    if (nfft < 2) return NULL;
+    orc_asgramcf q = xmalloc(sizeof *q);
+    q->nfft = nfft;
+    q->sp = orc_spgramcf_create_kaiser(nfft, nfft, 10.0f);          /* asgram.c:66-69 */
+    orc_asgramcf_set_scale(q, 0.0f, 10.0f);
+    return q;
+}
+
+void orc_asgramcf_destroy(orc_asgramcf q) { if (q) { orc_spgramcf_destroy(q->sp); free(q); } }
+void orc_asgramcf_reset(orc_asgramcf q) { orc_spgramcf_reset(q->sp); }
+void orc_asgramcf_set_scale(orc_asgramcf q, float offset, float scale)       /* asgram.c:113-128 */
+{
+    for (unsigned int i = 0; i < 10; i++) q->levels[i] = offset + i * scale;
+}
+void orc_asgramcf_write(orc_asgramcf q, const orc_cf *x, unsigned int n) { orc_spgramcf_write(q->sp, x, n); }
+
+/* asgram.c:157-195: shifted 10 log10 |X| (the magnitude), level characters, first maximum */
+void orc_asgramcf_execute(orc_asgramcf q, char *ascii, float *peakval, float *peakfreq)
+{
+    static const char lc[10] = {' ', '.', ',', '-', '+', '*', '&', 'N', 'M', '#'};
+    orc_cf *X = xmalloc(q->nfft * sizeof *X);
+    orc_spgramcf_execute(q->sp, X);
+    for (unsigned int i = 0; i < q->nfft; i++) {
+        orc_cf v = X[(i + q->nfft / 2) % q->nfft];
+        float p = 10 * log10f(hypotf(v.re, v.im));
+        if (i == 0 || p > *peakval) { *peakval = p; *peakfreq = (float)i / (float)q->nfft - 0.5f; }
+        ascii[i] = lc[0];
+        for (unsigned int j = 0; j < 10; j++)
+            if (p > q->levels[j]) ascii[i] = lc[j];
+    }
+    free(X);
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* firpfbch2_crcf: channelizer with output rate 2 Fs / M                                 */
 /* ------------------------------------------------------------------------------------ */

@@ -138,6 +138,13 @@ def lib():
         L.orc_msresamp2_stage_m.argtypes = [C.c_void_p, C.c_uint]
         L.orc_msresamp2_get_delay.restype = C.c_float
         L.orc_msresamp2_get_delay.argtypes = [C.c_void_p]
+        L.orc_asgramcf_create.restype = C.c_void_p
+        L.orc_asgramcf_create.argtypes = [C.c_uint]
+        L.orc_asgramcf_destroy.argtypes = [C.c_void_p]
+        L.orc_asgramcf_reset.argtypes = [C.c_void_p]
+        L.orc_asgramcf_set_scale.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.orc_asgramcf_write.argtypes = [C.c_void_p, c_cf_p, C.c_uint]
+        L.orc_asgramcf_execute.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_fftfilt_create.restype = C.c_void_p
         L.orc_fftfilt_create.argtypes = [c_f_p, C.c_uint, C.c_uint]
         L.orc_fftfilt_destroy.argtypes = [C.c_void_p]
@@ -439,6 +446,31 @@ class Msresamp2(_Obj):
         y = np.empty(n * M if self.type == RESAMP_INTERP else n, np.complex64)
         lib().orc_msresamp2_execute_block(self.h, x, n, y)
         return y
+
+
+class Asgramcf(_Obj):
+    """asgramcf: ASCII spectrogram; execute() -> (string, peak dB, peak frequency)"""
+    _destroy = "orc_asgramcf_destroy"
+
+    def __init__(self, nfft):
+        self.nfft = nfft
+        super().__init__(lib().orc_asgramcf_create(nfft))
+
+    def reset(self):
+        lib().orc_asgramcf_reset(self.h)
+
+    def set_scale(self, offset, scale):
+        lib().orc_asgramcf_set_scale(self.h, offset, scale)
+
+    def write(self, x):
+        x = _cf(x)
+        lib().orc_asgramcf_write(self.h, x, len(x))
+
+    def execute(self):
+        buf = C.create_string_buffer(self.nfft + 1)
+        pv, pf = C.c_float(), C.c_float()
+        lib().orc_asgramcf_execute(self.h, buf, C.byref(pv), C.byref(pf))
+        return buf.raw[:self.nfft].decode("ascii"), pv.value, pf.value
 
 
 class Fftfilt(_Obj):
@@ -855,6 +887,26 @@ def ref_msresamp2_block(type, S, fc, f0, As, x):
     delay = R.msresamp2_crcf_get_delay(q)
     R.msresamp2_crcf_destroy(q)
     return y, delay
+
+
+def ref_asgramcf(nfft, x, offset=None, scale=None):
+    """the compiled reference's asgramcf after writing x: (ascii, peak dB, peak frequency)"""
+    R = ref()
+    R.asgramcf_create.restype = C.c_void_p; R.asgramcf_create.argtypes = [C.c_uint]
+    R.asgramcf_set_scale.argtypes = [C.c_void_p, C.c_float, C.c_float]
+    R.asgramcf_write.argtypes = [C.c_void_p, c_cf_p, C.c_uint]
+    R.asgramcf_execute.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    R.asgramcf_destroy.argtypes = [C.c_void_p]
+    q = C.c_void_p(R.asgramcf_create(nfft))
+    if offset is not None:
+        R.asgramcf_set_scale(q, offset, scale)
+    x = _cf(x)
+    R.asgramcf_write(q, x, len(x))
+    buf = C.create_string_buffer(nfft + 1)
+    pv, pf = C.c_float(), C.c_float()
+    R.asgramcf_execute(q, buf, C.byref(pv), C.byref(pf))
+    R.asgramcf_destroy(q)
+    return buf.raw[:nfft].decode("ascii"), pv.value, pf.value
 
 
 def ref_fftfilt_blocks(h, n, x, scale=None):

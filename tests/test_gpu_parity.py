@@ -793,6 +793,29 @@ def test_resamp2_long_blocks_vs_oracle(L, orc):
     assert np.abs(np.concatenate([a1, b1]) - w1).max() < 2e-6
 
 
+# ------------------------------------------------------------------ asgramcf
+def test_asgramcf_vs_reference_fixture(L, orc, refrn2):
+    from test_oracle import _asg_cases, asgram_check
+    for tag, nfft, offset, scale in _asg_cases(refrn2):
+        asgram_check(L.asgramcf(nfft), refrn2, tag, offset, scale)
+    # push / reset / a second spectrum on the same object against the oracle
+    q, o = L.asgramcf(64), orc.Asgramcf(64)
+    x = (orc.synth_input(200, seed=3) * np.float32(0.2) + np.exp(-2j * np.pi * 0.3 * np.arange(200))).astype(np.complex64)
+    for v in x[:70]:
+        q.push(v)
+    o.write(x[:70])
+    q.write(x[70:])
+    o.write(x[70:])
+    (ga, gv, gf), (wa, wv, wf) = q.execute(), o.execute()
+    assert sum(a != b for a, b in zip(ga, wa)) <= 1 and abs(gv - wv) < 1e-3 and gf == wf
+    q.reset()
+    o.reset()
+    q.write(x[:64])
+    o.write(x[:64])
+    (ga, gv, gf), (wa, wv, wf) = q.execute(), o.execute()
+    assert sum(a != b for a, b in zip(ga, wa)) <= 1 and abs(gv - wv) < 1e-3 and gf == wf
+
+
 # ------------------------------------------------------------------ fftfilt
 def test_fftfilt_vs_reference_fixture_and_oracle(L, orc, refrn2, monkeypatch):
     """the compiled reference's outputs (power-of-two and other block sizes, set_scale), state carried over calls of

@@ -541,3 +541,31 @@ def test_fftfilt_is_firfilt(orc):
     for n in (56, 64, 80):
         got = orc.Fftfilt(h, n).execute_blocks(x[: len(x) // n * n])
         assert np.abs(got - want[: len(got)]).max() < 2e-6
+
+
+# ------------------------------------------------------------------ asgramcf
+def _asg_cases(fx):
+    for name in sorted(k for k in fx if k.startswith("asg_") and k.endswith("_args")):
+        nfft, offset, scale = fx[name]
+        yield name[:-5], int(nfft), (None if np.isnan(offset) else float(offset)), (None if np.isnan(scale) else float(scale))
+
+
+def asgram_check(q, fx, tag, offset, scale):
+    """characters and peak of an asgramcf object against the fixture; a character may move by one level where
+    the bin sits within float rounding of a threshold (at most 2 % of the bins)"""
+    levels = " .,-+*&NM#"
+    if offset is not None:
+        q.set_scale(offset, scale)
+    q.write(fx[tag + "_x"])
+    got, pv, pf = q.execute()
+    want = bytes(fx[tag + "_ascii"]).decode("ascii")
+    assert len(got) == len(want)
+    diff = [(a, b) for a, b in zip(got, want) if a != b]
+    assert len(diff) <= max(1, len(want) // 50), (tag, got, want)
+    assert all(abs(levels.index(a) - levels.index(b)) == 1 for a, b in diff), (tag, diff)
+    assert abs(pv - fx[tag + "_peak"][0]) < 1e-3 and pf == fx[tag + "_peak"][1], tag
+
+
+def test_fixture_asgramcf(orc, refrn2):
+    for tag, nfft, offset, scale in _asg_cases(refrn2):
+        asgram_check(orc.Asgramcf(nfft), refrn2, tag, offset, scale)
