@@ -98,6 +98,68 @@ firinterp_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, 
     }
 }
 
+// The throughput form of firinterp: a CTA stages the inputs of its tile (+ sub_len - 1 of history) and the whole
+// prototype in shared memory; a work item is (block of 8 consecutive inputs, branch j) and keeps a sliding window
+// of 8 samples in registers, so each staged sample is read once per item and feeds 8 packed FFMA2 per tap.  Items
+// are laid out branch-fastest: the M outputs of one input are written by adjacent lanes (full sectors).  Oldest
+// sample first, as firinterp_kernel.
+constexpr int kIR = 8;                                                // inputs per work item
+
+__global__ void __launch_bounds__(kThreads)
+firinterp_tile_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ h,
+                      unsigned int sub_len, unsigned int M, unsigned int n_ib, float2 *__restrict__ y, unsigned long long n_in)
+{
+    extern __shared__ float2 smem_i[];
+    const unsigned int T = n_ib * kIR;                                // inputs per CTA
+    const unsigned int halo = sub_len - 1;
+    float2 *xs = smem_i;                                              // staged sample q = input i0 - halo + q
+    float *hs = reinterpret_cast<float *>(xs + ((T + halo + 1) & ~1u));
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * T;
+    const unsigned int nt = (n_in - i0 < T) ? (unsigned int)(n_in - i0) : T;
+    for (unsigned int k = threadIdx.x; k < M * sub_len; k += blockDim.x) hs[k] = __ldg(h + k);
+    for (unsigned int q = threadIdx.x; q < nt + halo; q += blockDim.x) {
+        const long long idx = (long long)i0 - (long long)halo + q;
+        if (idx >= 0) {
+            const unsigned int dst = (unsigned int)__cvta_generic_to_shared(xs + q);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(x + idx) : "memory");
+        } else {
+            xs[q] = __ldg(hist + (H + idx));
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (unsigned int w = threadIdx.x; w < n_ib * M; w += blockDim.x) {
+        const unsigned int j = w % M, ib = w / M;
+        const unsigned int t0 = ib * kIR;                             // first input of the item, relative to i0
+        if (t0 >= nt) continue;
+        // at step k (tap n = sub_len-1-k) input t0 + r needs sample t0 + r - n = staged element t0 + r + k
+        float2 win[kIR];
+#pragma unroll
+        for (int r = 0; r < kIR - 1; r++) win[r] = xs[t0 + r];
+        float2 acc[kIR];
+#pragma unroll
+        for (int r = 0; r < kIR; r++) acc[r] = make_float2(0.f, 0.f);
+        for (unsigned int k0 = 0; k0 < sub_len; k0 += kIR) {
+#pragma unroll
+            for (int u = 0; u < kIR; u++) {
+                const unsigned int k = k0 + u;
+                if (k < sub_len) {
+                    win[(u + kIR - 1) % kIR] = xs[t0 + kIR - 1 + k];   // the slot freed by the previous step
+                    const float c = hs[j + (sub_len - 1 - k) * M];
+                    const float2 cc = make_float2(c, c);
+#pragma unroll
+                    for (int r = 0; r < kIR; r++) acc[r] = __ffma2_rn(cc, win[(r + u) % kIR], acc[r]);
+                }
+            }
+        }
+        float2 *yo = y + (i0 + t0) * M + j;
+#pragma unroll
+        for (int r = 0; r < kIR; r++)
+            if (t0 + r < nt) yo[(size_t)r * M] = acc[r];
+    }
+}
+
 inline unsigned int grid_for(unsigned long long total)
 {
     unsigned long long b = (total + kThreads - 1) / kThreads;
@@ -132,7 +194,18 @@ void decim_dev(firdecim_crcf q, const float2 *d_x, unsigned long long n_out, flo
 void interp_dev(firinterp_crcf q, const float2 *d_x, unsigned long long n_in, float2 *d_y, cudaStream_t st)
 {
     if (n_in == 0) return;
-    firinterp_kernel<<<grid_for(n_in * q->M), kThreads, 0, st>>>(q->d_hist, d_x, (int)q->sub_len, q->d_h, q->sub_len, q->M, d_y, n_in * q->M);
+    // items per CTA: at least one per thread, at least 4 input blocks
+    unsigned int n_ib = (kThreads + q->M - 1) / q->M;
+    if (n_ib < 4) n_ib = 4;
+    const unsigned int T = n_ib * kIR;
+    const size_t smem = sizeof(float2) * ((T + q->sub_len) & ~1u) + sizeof(float) * (size_t)q->M * q->sub_len;
+    const unsigned long long tiles = (n_in + T - 1) / T;
+    if (smem <= 48 * 1024 && n_in >= 4ull * T && tiles < (1ull << 31) && !getenv("LIQUID_CUDA_FIRINTERP_SIMPLE")) {
+        firinterp_tile_kernel<<<(unsigned int)tiles, kThreads, smem, st>>>(q->d_hist, d_x, (int)q->sub_len, q->d_h, q->sub_len,
+                                                                          q->M, n_ib, d_y, n_in);
+    } else {
+        firinterp_kernel<<<grid_for(n_in * q->M), kThreads, 0, st>>>(q->d_hist, d_x, (int)q->sub_len, q->d_h, q->sub_len, q->M, d_y, n_in * q->M);
+    }
     LC_LAUNCH_CHECK();
     lc::roll_history(q->d_hist, q->sub_len, q->hist_tmp, d_x, n_in, st);
 }

@@ -680,6 +680,26 @@ def test_firdecim_firinterp_vs_reference_fixture_and_oracle(L, orc, refrn):
     assert np.abs(got - want).max() < 4e-6 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("M,m", [(2, 9), (3, 4), (4, 5), (5, 3), (8, 6), (16, 7), (64, 3), (300, 2)])
+def test_firinterp_firdecim_long_blocks_vs_oracle(L, orc, M, m):
+    """the shared-memory tiled kernels (long blocks) for several rates and lengths incl. odd ones, state carried
+    over an awkward cut, against the oracle"""
+    n_in = 60000 if M <= 16 else 6000
+    x = orc.synth_input(n_in * max(M, 1), seed=0x600 + M)
+    rng = np.random.default_rng(M)
+    h = rng.standard_normal(2 * M * m + 1).astype(np.float32)
+    q, o = L.firinterp_crcf.create(M, h), orc.Firinterp(M, h=h)
+    cut = n_in // 3 + 1
+    got = np.concatenate([q.execute_block(x[:cut]), q.execute_block(x[cut:n_in])])
+    want = o.execute_block(x[:n_in])
+    assert np.abs(got - want).max() < 4e-6 * max(1.0, np.abs(want).max())
+    qd, od = L.firdecim_crcf.create(M, h), orc.Firdecim(M, h=h)
+    cutd = (n_in // 3 + 1) * M
+    got = np.concatenate([qd.execute_block(x[:cutd]), qd.execute_block(x[cutd:])])
+    want = od.execute_block(x)
+    assert np.abs(got - want).max() < 4e-6 * max(1.0, np.abs(want).max())
+
+
 # ------------------------------------------------------------------ resamp2 / msresamp2 (SURVEY 8f item 3)
 def test_resamp2_vs_reference_fixture(L, orc, refrn2):
     """all five modes and the mixed-mode run (shared windows, toggle) against the compiled reference's outputs;
