@@ -160,6 +160,88 @@ firinterp_tile_kernel(const float2 *__restrict__ hist, const float2 *__restrict_
     }
 }
 
+// The throughput form of firdecim: the filter is split into its M branches h_j[n] = h[n M + j] (zero-padded to
+// sub_len M taps), y[o] = sum_j sum_n h_j[n] x[(o - n) M - j].  A CTA stages the inputs of kDR * n_ob outputs (+ the
+// sub_len M - 1 samples of history) once; a work item is (block of 8 consecutive outputs, branch j) and slides an
+// 8-sample register window over its branch's decimated sequence -- every staged sample is read once per item and
+// feeds up to 8 packed FFMA2 per tap -- then the M partial sums of each output are added in branch order through
+// shared memory.  The staged array is padded by M elements per 8 M so that the item groups of a warp spread over
+// the banks.  (Summation order differs from the oldest-first dot product of firdecim_kernel: float32 rounding.)
+constexpr int kDR = 8;                                                // outputs per work item
+
+__global__ void __launch_bounds__(kThreads)
+firdecim_tile_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ h,
+                     unsigned int h_len, unsigned int sub_len, unsigned int M, unsigned int n_ob, float2 *__restrict__ y,
+                     unsigned long long n_out)
+{
+    extern __shared__ float2 smem_d[];
+    const unsigned int T = n_ob * kDR;                                // outputs per CTA
+    const unsigned int rows = n_ob + (sub_len + kDR - 1) / kDR + 1;    // rows of 8 M staged samples (padded to 9 M)
+    float2 *xs = smem_d;
+    float2 *part = xs + (size_t)rows * (kDR + 1) * M;                  // [T][M + 1] partial sums
+    float *hs = reinterpret_cast<float *>(part + (size_t)T * (M + 1)); // [sub_len M] taps, zero beyond h_len
+    const unsigned long long o0 = (unsigned long long)blockIdx.x * T;
+    const unsigned int nt = (n_out - o0 < T) ? (unsigned int)(n_out - o0) : T;
+    for (unsigned int k = threadIdx.x; k < M * sub_len; k += blockDim.x) hs[k] = k < h_len ? __ldg(h + k) : 0.0f;
+    // staged sample q is stream sample o0 M - sub_len M + 1 + q, q < (nt - 1 + sub_len) M
+    const long long first = (long long)(o0 * M) - (long long)(sub_len * M) + 1;
+    const unsigned int n_samp = (nt - 1 + sub_len) * M;
+    const unsigned int row_rcp = 0xFFFFFFFFu / (kDR * M) + 1;          // q / (8 M) = umulhi(q, row_rcp) for the small q here
+    for (unsigned int q = threadIdx.x; q < n_samp; q += blockDim.x) {
+        const unsigned int pq = q + M * __umulhi(q, row_rcp);
+        const long long idx = first + q;
+        if (idx >= 0) {
+            const unsigned int dst = (unsigned int)__cvta_generic_to_shared(xs + pq);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(x + idx) : "memory");
+        } else {
+            xs[pq] = (idx >= -(long long)H) ? __ldg(hist + (H + idx)) : make_float2(0.f, 0.f);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (unsigned int w = threadIdx.x; w < n_ob * M; w += blockDim.x) {
+        const unsigned int j = w % M, ob = w / M;
+        const unsigned int t0 = ob * kDR;
+        if (t0 >= nt) continue;
+        // element u of the branch's decimated sequence (u = 0 is output o0's oldest tap) sits at staged
+        // u M + (M - 1 - j), padded row u / 8
+        // (t0 is a multiple of 8: the first 7 elements share a row, every 8th step crosses into the next one)
+        const float2 *px = xs + (size_t)t0 * M + (M - 1 - j) + (size_t)M * ob;      // element t0
+        float2 win[kDR];
+#pragma unroll
+        for (int r = 0; r < kDR - 1; r++) win[r] = px[(size_t)r * M];
+        px += (size_t)(kDR - 1) * M;                                                  // element t0 + 7 (same row)
+        const float *ph = hs + (size_t)(sub_len - 1) * M + j;                         // tap sub_len - 1 of the branch
+        float2 acc[kDR];
+#pragma unroll
+        for (int r = 0; r < kDR; r++) acc[r] = make_float2(0.f, 0.f);
+        for (unsigned int k0 = 0; k0 < sub_len; k0 += kDR) {
+#pragma unroll
+            for (int u = 0; u < kDR; u++) {
+                if (k0 + u < sub_len) {                               // step k = k0 + u: tap n = sub_len - 1 - k
+                    win[(u + kDR - 1) % kDR] = *px;                   // element t0 + 7 + k
+                    px += (u == 0) ? 2 * M : M;                       // element t0 + 8 + k0 starts the next row (one pad)
+                    const float c = *ph;
+                    ph -= M;
+                    const float2 cc = make_float2(c, c);
+#pragma unroll
+                    for (int r = 0; r < kDR; r++) acc[r] = __ffma2_rn(cc, win[(r + u) % kDR], acc[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kDR; r++) part[(size_t)(t0 + r) * (M + 1) + j] = acc[r];
+    }
+    __syncthreads();
+    for (unsigned int t = threadIdx.x; t < nt; t += blockDim.x) {
+        const float2 *p = part + (size_t)t * (M + 1);
+        float2 sum = p[0];
+        for (unsigned int j = 1; j < M; j++) sum = __fadd2_rn(sum, p[j]);
+        y[o0 + t] = sum;
+    }
+}
+
 inline unsigned int grid_for(unsigned long long total)
 {
     unsigned long long b = (total + kThreads - 1) / kThreads;
@@ -170,6 +252,26 @@ inline unsigned int grid_for(unsigned long long total)
 void decim_dev(firdecim_crcf q, const float2 *d_x, unsigned long long n_out, float2 *d_y, cudaStream_t st)
 {
     if (n_out == 0) return;
+    {
+        // branch-decomposed tiled kernel when its staging fits ~96 KB
+        const unsigned int sub_len = (q->h_len + q->M - 1) / q->M;
+        unsigned int n_ob = (kThreads + q->M - 1) / q->M;
+        if (n_ob < 4) n_ob = 4;
+        const unsigned int T = n_ob * kDR;
+        const size_t rows = n_ob + (sub_len + kDR - 1) / kDR + 1;
+        const size_t smem_t = sizeof(float2) * (rows * (kDR + 1) * q->M + (size_t)T * (q->M + 1)) + sizeof(float) * (size_t)q->M * sub_len;
+        const unsigned long long tiles = (n_out + T - 1) / T;
+        if (smem_t <= 96 * 1024 && n_out >= 4ull * T && tiles < (1ull << 31) && !getenv("LIQUID_CUDA_FIRDECIM_SIMPLE")) {
+            static std::atomic<unsigned long long> configured_t{0};
+            if (lc::first_time_on_device(configured_t))
+                LC_CUDA_CHECK(cudaFuncSetAttribute(firdecim_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            firdecim_tile_kernel<<<(unsigned int)tiles, kThreads, smem_t, st>>>(q->d_hist, d_x, (int)q->h_len, q->d_h, q->h_len,
+                                                                             sub_len, q->M, n_ob, d_y, n_out);
+            LC_LAUNCH_CHECK();
+            lc::roll_history(q->d_hist, q->h_len, q->hist_tmp, d_x, n_out * q->M, st);
+            return;
+        }
+    }
     // outputs per CTA: as many as fit ~96 KB of staged samples, at most 256
     const size_t budget = 96 * 1024;
     const size_t taps_bytes = sizeof(float) * ((q->h_len + 1) & ~1u);
