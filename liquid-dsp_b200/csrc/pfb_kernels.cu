@@ -292,6 +292,84 @@ pfbch_mac_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, 
         X[gid] = pfbch_mac_elem<TapT>(hist, x, H, taps, M, p, phase, first, k, (long long)(gid / M), (unsigned int)(gid % M));
 }
 
+// The same kernel with the window of a thread kept in registers while it walks its frames (LW = 2m taps, a
+// compile-time constant): a window takes a new sample every other frame, so a lane that owns a contiguous run of
+// frames loads LW + (run / 2) samples instead of LW per frame, and its two tap sets (by parity) once.  Same fmaf
+// sequence per output as above: identical bits.
+template <int LW>
+__global__ void __launch_bounds__(lcfft::kFftThreads)
+pfbch2_analyze_pow2_win_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                               const float *__restrict__ taps, const float2 *__restrict__ tw, float2 *__restrict__ y,
+                               unsigned int M, unsigned int log2M, unsigned int per_cta,
+                               unsigned long long n_frames, int parity0, long long t_first)
+{
+    extern __shared__ float2 smem_f2[];
+    const lcfft::Smem sm = lcfft::carve(smem_f2, M, per_cta);
+    lcfft::stage_twiddles(sm, tw, M);
+    const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
+    {
+        const unsigned int M2 = M >> 1;
+        const unsigned int nw = M < blockDim.x ? M : blockDim.x;       // windows covered per pass (power of two)
+        const unsigned int fl = blockDim.x / nw;                        // frame lanes
+        const unsigned int w0 = threadIdx.x % nw, f0 = threadIdx.x / nw;
+        const unsigned int run = (per_cta + fl - 1) / fl;               // contiguous frames per lane
+        const unsigned int fa = f0 * run;
+        const unsigned int fb = (fa + run < per_cta) ? fa + run : per_cta;
+        for (unsigned int w = w0; w < M; w += nw) {
+            const bool lower = w < M2;
+            const long long off = lower ? (long long)(M2 - 1 - w) : (long long)(M - 1 - w);
+            float2 win[LW];                                             // win[n] = sample (tu - 2n) M2 + off
+            float c0[LW], c1[LW];                                       // both tap sets of the window (by parity)
+#pragma unroll
+            for (int n = 0; n < LW; n++) {
+                c0[n] = __ldg(taps + w + (size_t)n * M);
+                c1[n] = __ldg(taps + (size_t)LW * M + w + (size_t)n * M);
+            }
+            long long cur_tu = 0;
+            bool have = false;
+            for (unsigned int fi = fa; fi < fb; fi++) {
+                const unsigned long long f = first + fi;
+                float re = 0.f, im = 0.f;
+                if (f < n_frames) {
+                    const long long t = t_first + (long long)f;
+                    const int par = (parity0 + (int)(t & 1)) & 1;
+                    const long long tu = (par == (lower ? 0 : 1)) ? t : t - 1;
+                    if (!have || tu != cur_tu) {
+                        if (have && tu == cur_tu + 2) {
+#pragma unroll
+                            for (int n = LW - 1; n > 0; n--) win[n] = win[n - 1];
+                            win[0] = lcd::ld_stream(hist, x, tu * (long long)M2 + off, H);
+                        } else {
+#pragma unroll
+                            for (int n = 0; n < LW; n++)
+                                win[n] = lcd::ld_stream(hist, x, (tu - 2 * (long long)n) * (long long)M2 + off, H);
+                        }
+                        cur_tu = tu;
+                        have = true;
+                    }
+                    if (par) {
+#pragma unroll
+                        for (int n = 0; n < LW; n++) {
+                            re = fmaf(c1[n], win[n].x, re);
+                            im = fmaf(c1[n], win[n].y, im);
+                        }
+                    } else {
+#pragma unroll
+                        for (int n = 0; n < LW; n++) {
+                            re = fmaf(c0[n], win[n].x, re);
+                            im = fmaf(c0[n], win[n].y, im);
+                        }
+                    }
+                }
+                sm.buf0[lcfft::pidx(fi * M + w)] = make_float2(re, im);
+            }
+        }
+    }
+    __syncthreads();
+    const FrameDst dst{y, M, first, n_frames, 1, (float)M};
+    lcfft::stockham_run<+1>(sm, M, log2M, per_cta, lcfft::SmemSrc{sm.buf0, log2M}, dst);
+}
+
 // firpfbch analyzer for power-of-two M in ONE kernel (see pfbch2_analyze_pow2_kernel): MAC into shared memory,
 // forward Stockham FFT there, unscaled store by the last pass
 template <typename TapT>
@@ -436,6 +514,65 @@ void launch_pfbch_synth_fir_cc(const float2 *d_hist_rows, const float2 *d_v, int
 }
 
 namespace {
+// firpfbch analyzer with the window and the taps of a thread in registers (P taps, compile time): the window of a
+// branch takes one new sample per frame, so a lane that owns a contiguous run of frames loads P + run samples and
+// its P taps once, instead of 2 P loads per output.  Same tap_mac sequence as pfbch_analyze_pow2_kernel: identical bits.
+template <typename TapT, int P>
+__global__ void __launch_bounds__(lcfft::kFftThreads)
+pfbch_analyze_pow2_win_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                              const TapT *__restrict__ taps, const float2 *__restrict__ tw, float2 *__restrict__ y,
+                              unsigned int M, unsigned int log2M, unsigned int per_cta,
+                              unsigned long long n_frames, unsigned int phase, unsigned int first_in, unsigned int k)
+{
+    extern __shared__ float2 smem_f2[];
+    const lcfft::Smem sm = lcfft::carve(smem_f2, M, per_cta);
+    lcfft::stage_twiddles(sm, tw, M);
+    const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
+    {
+        const unsigned int nw = M < blockDim.x ? M : blockDim.x;
+        const unsigned int fl = blockDim.x / nw;
+        const unsigned int u0 = threadIdx.x % nw, f0 = threadIdx.x / nw;
+        const unsigned int run = (per_cta + fl - 1) / fl;               // contiguous frames per lane
+        const unsigned int fa = f0 * run;
+        const unsigned int fb = (fa + run < per_cta) ? fa + run : per_cta;
+        for (unsigned int u = u0; u < M; u += nw) {
+            const unsigned int i = M - 1 - u;                           // branch
+            const unsigned int win_i = (i + k) % M;                     // window it reads (firpfbch.c:395)
+            const long long rr = (long long)(M - 1 - win_i);
+            long long d = ((long long)phase + (long long)first_in - 1 - rr) % (long long)M;
+            if (d < 0) d += M;
+            const long long last0 = (long long)first_in - 1 - d;        // newest sample of run 0 (index into x)
+            TapT c[P];
+#pragma unroll
+            for (int n = 0; n < P; n++) c[n] = __ldg(taps + i + (size_t)n * M);
+            float2 win[P];                                              // win[n] = sample last - n M
+            bool have = false;
+            for (unsigned int fi = fa; fi < fb; fi++) {
+                const unsigned long long f = first + fi;
+                float re = 0.f, im = 0.f;
+                if (f < n_frames) {
+                    const long long last = last0 + (long long)f * M;
+                    if (have) {
+#pragma unroll
+                        for (int n = P - 1; n > 0; n--) win[n] = win[n - 1];
+                        win[0] = lcd::ld_stream(hist, x, last, H);
+                    } else {
+#pragma unroll
+                        for (int n = 0; n < P; n++) win[n] = lcd::ld_stream(hist, x, last - (long long)n * M, H);
+                        have = true;
+                    }
+#pragma unroll
+                    for (int n = 0; n < P; n++) tap_mac(c[n], win[n], re, im);
+                }
+                sm.buf0[lcfft::pidx(fi * M + u)] = make_float2(re, im);
+            }
+        }
+    }
+    __syncthreads();
+    const FrameDst dst{y, M, first, n_frames, 0, 1.0f};
+    lcfft::stockham_run<-1>(sm, M, log2M, per_cta, lcfft::SmemSrc{sm.buf0, log2M}, dst);
+}
+
 template <typename Kern>
 void ensure_big_smem(Kern kern)
 {
@@ -451,12 +588,31 @@ void launch_pfbch2_analyze_pow2(const float2 *d_hist, const float2 *d_x, int H, 
                                 cudaStream_t st, long long t_first)
 {
     static std::atomic<unsigned long long> configured{0};
-    if (first_time_on_device(configured)) ensure_big_smem(pfbch2_analyze_pow2_kernel);
+    if (first_time_on_device(configured)) {
+        ensure_big_smem(pfbch2_analyze_pow2_kernel);
+#define LC_WIN(LW) ensure_big_smem(pfbch2_analyze_pow2_win_kernel<LW>);
+        LC_WIN(4) LC_WIN(6) LC_WIN(8) LC_WIN(10) LC_WIN(12) LC_WIN(14) LC_WIN(16) LC_WIN(18) LC_WIN(20)
+#undef LC_WIN
+    }
     const unsigned int per_cta = lcfft::per_cta_for(M, n_frames);
     const unsigned long long ctas = (n_frames + per_cta - 1) / per_cta;
     if (ctas >= (1ull << 31)) fatal("firpfbch2_crcf_execute_block", "too many frames for one launch");
-    pfbch2_analyze_pow2_kernel<<<(unsigned int)ctas, lcfft::kFftThreads, lcfft::smem_for(M, per_cta), st>>>(
-        d_hist, d_x, H, d_taps, d_tw, d_y, M, ilog2(M), L, per_cta, n_frames, parity0, t_first);
+    const size_t smem = lcfft::smem_for(M, per_cta);
+    // a lane that owns at least 4 consecutive frames keeps its window in registers
+    const unsigned int lanes = lcfft::kFftThreads / (M < (unsigned int)lcfft::kFftThreads ? M : (unsigned int)lcfft::kFftThreads);
+    const bool sliding = per_cta / lanes >= 4 && !getenv("LIQUID_CUDA_ANALYZE_NO_WINDOW");
+    switch (sliding ? L : 0u) {
+#define LC_WIN(LW)                                                                                             \
+    case LW:                                                                                                   \
+        pfbch2_analyze_pow2_win_kernel<LW><<<(unsigned int)ctas, lcfft::kFftThreads, smem, st>>>(              \
+            d_hist, d_x, H, d_taps, d_tw, d_y, M, ilog2(M), per_cta, n_frames, parity0, t_first);              \
+        break;
+        LC_WIN(4) LC_WIN(6) LC_WIN(8) LC_WIN(10) LC_WIN(12) LC_WIN(14) LC_WIN(16) LC_WIN(18) LC_WIN(20)
+#undef LC_WIN
+    default:
+        pfbch2_analyze_pow2_kernel<<<(unsigned int)ctas, lcfft::kFftThreads, smem, st>>>(
+            d_hist, d_x, H, d_taps, d_tw, d_y, M, ilog2(M), L, per_cta, n_frames, parity0, t_first);
+    }
     LC_LAUNCH_CHECK();
 }
 
@@ -467,12 +623,33 @@ static void launch_pfbch_analyze_pow2_t(const float2 *d_hist, const float2 *d_x,
                                         unsigned int k, cudaStream_t st)
 {
     static std::atomic<unsigned long long> configured{0};
-    if (first_time_on_device(configured)) ensure_big_smem(pfbch_analyze_pow2_kernel<TapT>);
+#define LC_WIN_ALL LC_WIN(2) LC_WIN(3) LC_WIN(4) LC_WIN(5) LC_WIN(6) LC_WIN(7) LC_WIN(8) LC_WIN(10) LC_WIN(12) LC_WIN(14) LC_WIN(16)
+    if (first_time_on_device(configured)) {
+        ensure_big_smem(pfbch_analyze_pow2_kernel<TapT>);
+#define LC_WIN(PP) ensure_big_smem(pfbch_analyze_pow2_win_kernel<TapT, PP>);
+        LC_WIN_ALL
+#undef LC_WIN
+    }
     const unsigned int per_cta = lcfft::per_cta_for(M, n_frames);
     const unsigned long long ctas = (n_frames + per_cta - 1) / per_cta;
     if (ctas >= (1ull << 31)) fatal("firpfbch_analyzer_execute_block", "too many frames for one launch");
-    pfbch_analyze_pow2_kernel<TapT><<<(unsigned int)ctas, lcfft::kFftThreads, lcfft::smem_for(M, per_cta), st>>>(
-        d_hist, d_x, H, d_taps, d_tw, d_y, M, ilog2(M), p, per_cta, n_frames, phase, first, k);
+    const size_t smem = lcfft::smem_for(M, per_cta);
+    // a lane that owns at least 4 consecutive frames keeps its window and taps in registers
+    const unsigned int lanes = lcfft::kFftThreads / (M < (unsigned int)lcfft::kFftThreads ? M : (unsigned int)lcfft::kFftThreads);
+    const bool sliding = per_cta / lanes >= 4 && !getenv("LIQUID_CUDA_ANALYZE_NO_WINDOW");
+    switch (sliding ? p : 0u) {
+#define LC_WIN(PP)                                                                                              \
+    case PP:                                                                                                    \
+        pfbch_analyze_pow2_win_kernel<TapT, PP><<<(unsigned int)ctas, lcfft::kFftThreads, smem, st>>>(          \
+            d_hist, d_x, H, d_taps, d_tw, d_y, M, ilog2(M), per_cta, n_frames, phase, first, k);                \
+        break;
+        LC_WIN_ALL
+#undef LC_WIN
+    default:
+        pfbch_analyze_pow2_kernel<TapT><<<(unsigned int)ctas, lcfft::kFftThreads, smem, st>>>(
+            d_hist, d_x, H, d_taps, d_tw, d_y, M, ilog2(M), p, per_cta, n_frames, phase, first, k);
+    }
+#undef LC_WIN_ALL
     LC_LAUNCH_CHECK();
 }
 
