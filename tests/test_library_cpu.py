@@ -4,6 +4,7 @@ No compute calls that need a GPU."""
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -121,3 +122,32 @@ def test_estimate_req_filter_len(L, refrn2):
     """Kaiser's length estimate (host code) at the fixture's points from the compiled reference"""
     for (df, As), want in zip(refrn2["len_points"], refrn2["len_values"]):
         assert L.lib.estimate_req_filter_len(float(df), float(As)) == want
+
+
+BAD_CALLS = [
+    # (python expression on the ctypes mirror `L`, function named in the message)   reference file:line of the check
+    ("L.lib.firpfbch2_crcf_create_kaiser(0, 7, 3, 60.0)", "firpfbch2_crcf_create_kaiser"),        # firpfbch2.c:140-146 (odd M)
+    ("L.lib.firpfbch2_crcf_create_kaiser(0, 8, 0, 60.0)", "firpfbch2_crcf_create_kaiser"),        # :147-150 (m = 0)
+    ("L.lib.firpfbch_crcf_create_kaiser(0, 0, 3, 60.0)", "firpfbch_crcf_create_kaiser"),          # firpfbch.c:156-159
+    ("L.lib.firdecim_crcf_create_kaiser(1, 3, 60.0)", "decim_crcf_create_kaiser"),                # firdecim.c:93-96
+    ("L.lib.firinterp_crcf_create_kaiser(1, 3, 60.0)", "firinterp_crcf_create_kaiser"),           # firinterp.c:91-94
+    ("L.lib.resamp2_crcf_create(1, 0.0, 60.0)", "resamp2_crcf_create"),                           # resamp2.c:70-73
+    ("L.lib.resamp2_crcf_create(4, 0.75, 60.0)", "resamp2_crcf_create"),                          # resamp2.c:79-82
+    ("L.lib.msresamp2_crcf_create(1, 17, 0.25, 0.0, 60.0)", "msresamp2_crcf_create"),             # msresamp2.c:89-92
+    ("L.lib.msresamp2_crcf_create(1, 3, 0.5, 0.0, 60.0)", "msresamp2_crcf_create"),               # msresamp2.c:95-98
+    ("L.lib.fftfilt_crcf_create(np.ones(9, np.float32), 9, 4)", "fftfilt_crcf_create"),           # fftfilt.c:77-83
+    ("L.lib.asgramcf_create(1)", "asgramcf_create"),                                              # asgram.c:51-54
+    ("L.lib.estimate_req_filter_len(0.7, 60.0)", "estimate_req_filter_len"),                      # firdes.c:55-58
+    ("L.lib.spgramcf_create_kaiser(1, 1, 3.0)", "spgramcf_create"),                               # spgram.c:63-66
+]
+
+
+@pytest.mark.parametrize("expr,fn", BAD_CALLS)
+def test_invalid_arguments_follow_the_reference_error_convention(expr, fn):
+    """the reference prints `error: <fn>(), <message>` to stderr and exits with status 1 (e.g. firpfbch2.c:72-81);
+    the argument checks come before any device work, so this runs without a GPU"""
+    code = ("import sys, importlib, numpy as np; sys.path.insert(0, %r); "
+            "L = importlib.import_module('liquid-dsp_b200'); %s" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), expr))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1, (expr, r.returncode, r.stderr[-300:])
+    assert ("error: %s" % fn) in r.stderr, (expr, r.stderr[-300:])
