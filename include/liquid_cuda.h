@@ -122,6 +122,26 @@ void msresamp2_crcf_reset(msresamp2_crcf _q);
 float msresamp2_crcf_get_delay(msresamp2_crcf _q);
 void msresamp2_crcf_execute(msresamp2_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y);
 
+/* ---- ofdmframegen (OFDM symbol generator) and the subcarrier-allocation helpers: liquid.h:5803-5876 ->
+ *      src/multichannel/src/ofdmframegen.c:85-361, ofdmframe.common.c:176-282.  SURVEY.md 8(f) item 4. */
+#define OFDMFRAME_SCTYPE_NULL   0
+#define OFDMFRAME_SCTYPE_PILOT  1
+#define OFDMFRAME_SCTYPE_DATA   2
+void ofdmframe_init_default_sctype(unsigned int _M, unsigned char *_p);
+void ofdmframe_validate_sctype(unsigned char *_p, unsigned int _M, unsigned int *_M_null, unsigned int *_M_pilot,
+                               unsigned int *_M_data);
+void ofdmframe_print_sctype(unsigned char *_p, unsigned int _M);
+typedef struct ofdmframegen_s * ofdmframegen;
+ofdmframegen ofdmframegen_create(unsigned int _M, unsigned int _cp_len, unsigned int _taper_len, unsigned char *_p);
+void ofdmframegen_destroy(ofdmframegen _q);
+void ofdmframegen_print(ofdmframegen _q);
+void ofdmframegen_reset(ofdmframegen _q);
+void ofdmframegen_write_S0a(ofdmframegen _q, liquid_float_complex *_y);
+void ofdmframegen_write_S0b(ofdmframegen _q, liquid_float_complex *_y);
+void ofdmframegen_write_S1(ofdmframegen _q, liquid_float_complex *_y);
+void ofdmframegen_writesymbol(ofdmframegen _q, liquid_float_complex *_x, liquid_float_complex *_y);
+void ofdmframegen_writetail(ofdmframegen _q, liquid_float_complex *_x);
+
 /* ---- fftfilt_crcf (FIR filtering through 2n-point transforms): liquid.h:2192-2232 -> src/filter/src/fftfilt.c:68-266.
  *      SURVEY.md 8(f) item 3.  x and y must not overlap in the device-pointer form. */
 typedef struct fftfilt_crcf_s * fftfilt_crcf;
@@ -343,6 +363,11 @@ void resamp2_crcf_interp_execute_block_dev(resamp2_crcf _q, const void *_d_x, un
 unsigned int msresamp2_crcf_get_stage_semilength(msresamp2_crcf _q, unsigned int _i);
 void msresamp2_crcf_execute_block(msresamp2_crcf _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
 void msresamp2_crcf_execute_block_dev(msresamp2_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
+
+/* ---- ofdmframegen: _n data symbols in one call (_x [n][M] -> _y [n][M + cp_len]), host / device pointers ---- */
+void ofdmframegen_get_sctype(ofdmframegen _q, unsigned char *_p);
+void ofdmframegen_writesymbols(ofdmframegen _q, liquid_float_complex *_x, unsigned int _n, liquid_float_complex *_y);
+void ofdmframegen_writesymbols_dev(ofdmframegen _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);
 
 /* ---- fftfilt_crcf: _n_blocks blocks of n samples in one call (all blocks run in parallel), host / device pointers ---- */
 void fftfilt_crcf_execute_block(fftfilt_crcf _q, liquid_float_complex *_x, unsigned int _n_blocks, liquid_float_complex *_y);

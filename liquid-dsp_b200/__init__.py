@@ -131,6 +131,22 @@ _sig("asgramcf_push", None, _vp, _cf)
 _sig("asgramcf_write", None, _vp, _cf_p, _u)
 _sig("asgramcf_execute", None, _vp, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_float))
 _sig("asgramcf_print", None, _vp)
+_u8_p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_sig("ofdmframe_init_default_sctype", None, _u, _u8_p)
+_sig("ofdmframe_validate_sctype", None, _u8_p, _u, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint))
+_sig("ofdmframe_print_sctype", None, _u8_p, _u)
+_sig("ofdmframegen_create", _vp, _u, _u, _u, _vp)
+_sig("ofdmframegen_destroy", None, _vp)
+_sig("ofdmframegen_print", None, _vp)
+_sig("ofdmframegen_reset", None, _vp)
+_sig("ofdmframegen_get_sctype", None, _vp, _u8_p)
+_sig("ofdmframegen_write_S0a", None, _vp, _cf_p)
+_sig("ofdmframegen_write_S0b", None, _vp, _cf_p)
+_sig("ofdmframegen_write_S1", None, _vp, _cf_p)
+_sig("ofdmframegen_writesymbol", None, _vp, _cf_p, _cf_p)
+_sig("ofdmframegen_writesymbols", None, _vp, _vp, _u, _vp)
+_sig("ofdmframegen_writesymbols_dev", None, _vp, _vp, _ull, _vp, _vp)
+_sig("ofdmframegen_writetail", None, _vp, _cf_p)
 _sig("fftfilt_crcf_create", _vp, _f_p, _u, _u)
 _sig("fftfilt_crcf_destroy", None, _vp)
 _sig("fftfilt_crcf_reset", None, _vp)
@@ -709,6 +725,75 @@ class asgramcf(_Handle):
 
     def print(self):
         lib.asgramcf_print(self._h)
+
+
+OFDMFRAME_SCTYPE_NULL, OFDMFRAME_SCTYPE_PILOT, OFDMFRAME_SCTYPE_DATA = 0, 1, 2
+
+
+def ofdmframe_init_default_sctype(M):
+    p = np.empty(M, np.uint8)
+    lib.ofdmframe_init_default_sctype(M, p)
+    return p
+
+
+class ofdmframegen(_Handle):
+    """liquid.h:5836-5876 (src/multichannel/src/ofdmframegen.c): OFDM symbol generator; p = subcarrier allocation
+    (uint8 array) or None for the default one.  writesymbols() runs n data symbols in one call."""
+    _destroy = "ofdmframegen_destroy"
+
+    def __init__(self, M, cp_len, taper_len, p=None):
+        self.M, self.cp, self.tl = M, cp_len, taper_len
+        self._p = None if p is None else np.ascontiguousarray(p, np.uint8)
+        super().__init__(lib.ofdmframegen_create(M, cp_len, taper_len, None if self._p is None else self._p.ctypes.data))
+
+    @classmethod
+    def create(cls, M, cp_len, taper_len, p=None):
+        return cls(M, cp_len, taper_len, p)
+
+    def reset(self):
+        lib.ofdmframegen_reset(self._h)
+
+    def print(self):
+        lib.ofdmframegen_print(self._h)
+
+    def sctype(self):
+        p = np.empty(self.M, np.uint8)
+        lib.ofdmframegen_get_sctype(self._h, p)
+        return p
+
+    def _sym(self, fn):
+        y = np.empty(self.M + self.cp, np.complex64)
+        fn(self._h, y)
+        return y
+
+    def write_S0a(self):
+        return self._sym(lib.ofdmframegen_write_S0a)
+
+    def write_S0b(self):
+        return self._sym(lib.ofdmframegen_write_S0b)
+
+    def write_S1(self):
+        return self._sym(lib.ofdmframegen_write_S1)
+
+    def writesymbol(self, x):
+        y = np.empty(self.M + self.cp, np.complex64)
+        lib.ofdmframegen_writesymbol(self._h, _c64(x), y)
+        return y
+
+    def writesymbols(self, x):
+        x = _c64(x)
+        n = x.size // self.M
+        y = np.empty(n * (self.M + self.cp), np.complex64)
+        lib.ofdmframegen_writesymbols(self._h, _ptr(x), n, _ptr(y))
+        return y
+
+    def writesymbols_dev(self, d_x, n, d_y, stream=0):
+        lib.ofdmframegen_writesymbols_dev(self._h, d_x, n, d_y, stream)
+
+    def writetail(self):
+        y = np.empty(max(self.tl, 1), np.complex64)
+        lib.ofdmframegen_writetail(self._h, y)
+        return y[:self.tl]
 
 
 class fftfilt_crcf(_Handle):

@@ -102,6 +102,9 @@ void FftPlanDev::init(unsigned int n_, int sign_)
     LC_CUDA_CHECK(cudaMalloc(&d_tw, sizeof(float2) * n));
     LC_CUDA_CHECK(cudaMemcpy(d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
     if (is_pow2(n) && n >= 2) {
+        const std::vector<float2> twp = lcfft::pass_ordered_twiddles(tw, n);
+        LC_CUDA_CHECK(cudaMalloc(&d_twp, sizeof(float2) * n));
+        LC_CUDA_CHECK(cudaMemcpy(d_twp, twp.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
         // transforms above 3072 points need more than the default 48 KB of dynamic smem
         static std::atomic<unsigned long long> configured{0};
         if (first_time_on_device(configured))
@@ -112,7 +115,9 @@ void FftPlanDev::init(unsigned int n_, int sign_)
 void FftPlanDev::destroy()
 {
     if (d_tw) cudaFree(d_tw);
+    if (d_twp) cudaFree(d_twp);
     d_tw = nullptr;
+    d_twp = nullptr;
 }
 
 void FftPlanDev::run(const float2 *d_x, float2 *d_y, unsigned long long batch, cudaStream_t st,
@@ -135,7 +140,7 @@ void FftPlanDev::run(const float2 *d_x, float2 *d_y, unsigned long long batch, c
             unsigned long long ctas = (nb + per_cta - 1) / per_cta;
             if (ctas > max_grid) { ctas = max_grid; nb = ctas * per_cta; }
             fft_pow2_kernel<<<(unsigned int)ctas, kFftThreads, smem, st>>>(
-                d_x + done * n, d_y + done * n, d_tw, n, ilog2(n), per_cta, nb,
+                d_x + done * n, d_y + done * n, d_twp, n, ilog2(n), per_cta, nb,
                 (float)sign, post_mode, a, b);
             LC_LAUNCH_CHECK();
             done += nb;

@@ -9,6 +9,7 @@
 // (RegDft, packed FP32x2) and writes them to their autosort positions.  Both buffers are stored with one
 // pad element per 16 (pidx), which makes the stride-R writes of the first pass bank-conflict-free as well.
 #pragma once
+#include <vector>
 #include "lc_common.cuh"
 #include "fused_common.cuh"
 
@@ -40,7 +41,8 @@ __device__ __forceinline__ Smem carve(float2 *base, unsigned int n, unsigned int
     const unsigned int p = padded_len(n, per_cta);
     return Smem{base, base + p, base + 2 * p};
 }
-// cooperative copy of the plan's table tw[i] = e^{sign j 2 pi i / n}; a barrier must follow before the FFT
+// cooperative copy of the plan's PASS-ORDERED table (FftPlanDev::d_twp, n entries: for every pass after the first,
+// in order, the R-1 rows W_{R Ns}^(k m), k < Ns, of that pass; zero padded); a barrier must follow before the FFT
 // (the callers' own barrier after filling buf0 serves)
 __device__ __forceinline__ void stage_twiddles(const Smem &s, const float2 *__restrict__ tw, unsigned int n)
 {
@@ -66,13 +68,12 @@ struct SmemDst {
 // j + m q (q = n / R), multiplies by W_{R Ns}^(k m) (k = j mod Ns), does the R-point DFT in registers and writes
 // elements (j - k) R + k + m Ns
 template <int R, int SIGN, class Src, class Dst>
-__device__ __forceinline__ void stockham_pass(const Src &src, const Dst &dst, const float2 *__restrict__ tw,
+__device__ __forceinline__ void stockham_pass(const Src &src, const Dst &dst, const float2 *__restrict__ twp,
                                               unsigned int n, unsigned int log2n, unsigned int Ns, unsigned int per_cta)
 {
     constexpr unsigned int kLog2R = (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1;
     const unsigned int log2q = log2n - kLog2R;
     const unsigned int q = 1u << log2q;                        // butterflies per transform
-    const unsigned int tstride = (n >> kLog2R) / Ns;           // table step of W_{R Ns}
     for (unsigned int i = threadIdx.x; i < (per_cta << log2q); i += blockDim.x) {
         const unsigned int f = i >> log2q, j = i & (q - 1);
         const unsigned int k = j & (Ns - 1);
@@ -80,8 +81,10 @@ __device__ __forceinline__ void stockham_pass(const Src &src, const Dst &dst, co
 #pragma unroll
         for (int m = 0; m < R; m++) v[m] = src(f, j + m * q);
         if (Ns > 1) {
+            // this pass's table holds W_{R Ns}^(k m) at [(m-1) Ns + k]: the lanes of a warp (consecutive k) read
+            // consecutive entries
 #pragma unroll
-            for (int m = 1; m < R; m++) v[m] = lcf::cmul2(v[m], tw[k * m * tstride]);
+            for (int m = 1; m < R; m++) v[m] = lcf::cmul2(v[m], twp[(m - 1) * Ns + k]);
         }
         lcf::RegDft<R, SIGN>::run(v);
         const unsigned int d = (j - k) * R + k;
@@ -101,19 +104,21 @@ __device__ __forceinline__ void stockham_run(const Smem &s, unsigned int n, unsi
     float2 *in = s.buf0, *out = s.buf1;
     unsigned int Ns = 1, left = log2n;
     bool is_first = true;
+    const float2 *twp = s.tw;                                  // table of the running pass (pass-ordered layout)
 #define LC_PASS(R)                                                                                               \
     do {                                                                                                         \
         const bool is_last = (left == ((R == 16) ? 4u : (R == 8) ? 3u : (R == 4) ? 2u : 1u));                    \
         const SmemSrc ssrc{in, log2n};                                                                           \
         const SmemDst sdst{out, log2n};                                                                          \
-        if (is_first && is_last)  stockham_pass<R, SIGN>(first, last, s.tw, n, log2n, Ns, per_cta);              \
-        else if (is_first)        stockham_pass<R, SIGN>(first, sdst, s.tw, n, log2n, Ns, per_cta);              \
-        else if (is_last)         stockham_pass<R, SIGN>(ssrc, last, s.tw, n, log2n, Ns, per_cta);               \
-        else                      stockham_pass<R, SIGN>(ssrc, sdst, s.tw, n, log2n, Ns, per_cta);               \
+        if (is_first && is_last)  stockham_pass<R, SIGN>(first, last, twp, n, log2n, Ns, per_cta);               \
+        else if (is_first)        stockham_pass<R, SIGN>(first, sdst, twp, n, log2n, Ns, per_cta);               \
+        else if (is_last)         stockham_pass<R, SIGN>(ssrc, last, twp, n, log2n, Ns, per_cta);                \
+        else                      stockham_pass<R, SIGN>(ssrc, sdst, twp, n, log2n, Ns, per_cta);                \
         if (!is_last) __syncthreads();                                                                           \
     } while (0)
     while (left >= 4) {
         LC_PASS(16);
+        if (Ns > 1) twp += 15 * Ns;
         Ns <<= 4;
         left -= 4;
         is_first = false;
@@ -137,6 +142,29 @@ __device__ __forceinline__ const float2 *stockham_run_to_smem(const Smem &s, uns
     stockham_run<SIGN>(s, n, log2n, per_cta, first, SmemDst{res, log2n});
     __syncthreads();
     return res;
+}
+
+// host: the pass-ordered table from the flat one tw[i] = e^{sign j 2 pi i / n} (same values, so results do not change;
+// the flat table read at k m tstride made the lanes of a warp hit one bank in the middle passes of long transforms)
+inline std::vector<float2> pass_ordered_twiddles(const std::vector<float2> &flat, unsigned int n)
+{
+    std::vector<float2> t;
+    unsigned int left = 0;
+    while ((1u << left) < n) left++;
+    unsigned int Ns = 1;
+    auto emit = [&](unsigned int R) {
+        if (Ns > 1) {
+            const unsigned int tstride = (n / R) / Ns;
+            for (unsigned int m = 1; m < R; m++)
+                for (unsigned int k = 0; k < Ns; k++) t.push_back(flat[(size_t)k * m * tstride]);
+        }
+    };
+    while (left >= 4) { emit(16); Ns <<= 4; left -= 4; }
+    if (left == 3) emit(8);
+    else if (left == 2) emit(4);
+    else if (left == 1) emit(2);
+    t.resize(n, make_float2(0.f, 0.f));
+    return t;
 }
 
 // transforms per CTA for n-point transforms and the shared memory they need.  2048 points per CTA keeps four

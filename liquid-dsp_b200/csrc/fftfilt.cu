@@ -156,7 +156,7 @@ void blocks_dev(fftfilt_crcf q, const float2 *d_x, unsigned long long n_blocks, 
         const unsigned long long ctas = (n_blocks + per_cta - 1) / per_cta;
         if (ctas >= (1ull << 31)) lc::fatal("fftfilt_crcf_execute_block", "too many blocks for one launch");
         fftfilt_pow2_kernel<<<(unsigned int)ctas, lcfft::kFftThreads, pow2_smem(N, per_cta), st>>>(
-            q->d_hist, d_x, q->d_H, q->fwd.d_tw, q->bwd.d_tw, d_y, n, lc::ilog2(N), per_cta, n_blocks, q->scale);
+            q->d_hist, d_x, q->d_H, q->fwd.d_twp, q->bwd.d_twp, d_y, n, lc::ilog2(N), per_cta, n_blocks, q->scale);
         LC_LAUNCH_CHECK();
     } else {
         // pieces of at most ~256 MB of scratch per buffer

@@ -41,7 +41,7 @@ void analyze_generic(firpfbch_crcf q, const float2 *d_hist, const float2 *d_x, f
                      unsigned int phase, unsigned int first, unsigned int k, cudaStream_t st)
 {
     if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL")) {
-        lc::pfb::launch_pfbch_analyze_pow2(d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_tw, d_y, q->M, q->p, n, phase, first, k, st);
+        lc::pfb::launch_pfbch_analyze_pow2(d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_twp, d_y, q->M, q->p, n, phase, first, k, st);
         return;
     }
     lc::pfb::launch_pfbch_mac(d_hist, d_x, (int)q->H, q->d_taps, d_y, q->M, q->p, n, phase, first, k, st);

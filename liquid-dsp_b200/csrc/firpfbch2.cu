@@ -55,7 +55,7 @@ void analyze_dev(firpfbch2_crcf q, const float2 *d_hist, const float2 *d_x, int 
     float2 *d_yr = d_y + done * q->M;
     if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL")) {
         // power-of-two M: polyphase MAC, backward FFT and /M in one kernel (shared memory)
-        lc::pfb::launch_pfbch2_analyze_pow2(d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_tw, d_yr, q->M, q->L,
+        lc::pfb::launch_pfbch2_analyze_pow2(d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_twp, d_yr, q->M, q->L,
                                             n_frames - done, parity0, st, (long long)done);
         return;
     }

@@ -43,7 +43,7 @@ void analyze_generic_cc(firpfbch_cccf q, const float2 *d_x, float2 *d_y, unsigne
                         unsigned int k, cudaStream_t st)
 {
     if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL")) {
-        lc::pfb::launch_pfbch_analyze_pow2_cc(q->d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_tw, d_y, q->M, q->p, n,
+        lc::pfb::launch_pfbch_analyze_pow2_cc(q->d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_twp, d_y, q->M, q->p, n,
                                               q->phase, first, k, st);
         return;
     }

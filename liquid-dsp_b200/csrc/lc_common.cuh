@@ -121,6 +121,7 @@ struct FftPlanDev {
     unsigned int n = 0;
     int sign = 0;              // -1 forward (e^{-j}), +1 backward (e^{+j})
     float2 *d_tw = nullptr;    // [n], device
+    float2 *d_twp = nullptr;   // [n], device: the same values in the pass order of the shared-memory FFT (power-of-two n)
     void init(unsigned int n_, int sign_);
     void destroy();
     // y[b][k] = post( sum_i x[b][i] e^{sign j 2 pi i k / n} ); post = identity (mode 0),

@@ -258,10 +258,10 @@ void run_transforms(spgramcf q, const float2 *d_x, unsigned long long T, Segs se
         const size_t smem = lcfft::smem_for(nfft, per_cta);
         if (mode == 0)
             spgram_transform_pow2_kernel<0><<<(unsigned int)ctas, lcfft::kFftThreads, smem, st>>>(
-                q->d_buf, d_x, (int)q->window_len, q->d_w, q->window_len, q->fft.d_tw, nfft, lc::ilog2(nfft), per_cta, T, segs, d_out);
+                q->d_buf, d_x, (int)q->window_len, q->d_w, q->window_len, q->fft.d_twp, nfft, lc::ilog2(nfft), per_cta, T, segs, d_out);
         else
             spgram_transform_pow2_kernel<1><<<(unsigned int)ctas, lcfft::kFftThreads, smem, st>>>(
-                q->d_buf, d_x, (int)q->window_len, q->d_w, q->window_len, q->fft.d_tw, nfft, lc::ilog2(nfft), per_cta, T, segs, d_out);
+                q->d_buf, d_x, (int)q->window_len, q->d_w, q->window_len, q->fft.d_twp, nfft, lc::ilog2(nfft), per_cta, T, segs, d_out);
         LC_LAUNCH_CHECK();
         return;
     }
@@ -312,7 +312,7 @@ void accumulate_transforms(spgramcf q, const float2 *d_x, unsigned long long T, 
         const unsigned int n_chunks = (unsigned int)((T + tpc - 1) / tpc);
         float *d_part = (float *)q->partials.get(sizeof(float) * (size_t)n_chunks * nfft);
         spgram_accumulate_pow2_kernel<<<n_chunks, lcfft::kFftThreads, lcfft::smem_for(nfft, per_cta), st>>>(
-            q->d_buf, d_x, (int)q->window_len, q->d_w, q->window_len, q->fft.d_tw, nfft, lc::ilog2(nfft), per_cta, T,
+            q->d_buf, d_x, (int)q->window_len, q->d_w, q->window_len, q->fft.d_twp, nfft, lc::ilog2(nfft), per_cta, T,
             (unsigned int)tpc, segs, q->d_psd, d_part, alpha, 1);
         LC_LAUNCH_CHECK();
         spgram_combine_kernel<<<(nfft + kThreads - 1) / kThreads, kThreads, 0, st>>>(d_part, q->d_psd, nfft, n_chunks,

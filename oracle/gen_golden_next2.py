@@ -11,6 +11,7 @@ the record of how the fixture was made.
            estimate_req_filter_len
   len_*    estimate_req_filter_len points
   asg_*    asgramcf(nfft) after a write of a tone plus noise: the character string and the peak (default and custom scale)
+  ofdm_*   ofdmframegen(M, cp_len, taper_len, allocation): a whole frame S0a | S0b | S1 | data symbols | tail
   ff_*     fftfilt_crcf(h, n) over several blocks (random taps / a Kaiser low-pass, with and without set_scale)
 """
 import ctypes as C
@@ -69,6 +70,24 @@ for nfft, offset, scale in [(64, None, None), (72, -20.0, 5.0), (256, -30.0, 4.0
     out[tag + "_x"] = x
     out[tag + "_ascii"] = np.frombuffer(ascii_.encode("ascii"), np.uint8).copy()
     out[tag + "_peak"] = np.array([pv, pf], np.float32)
+
+# ofdmframegen: whole frames (S0a | S0b | S1 | data symbols | tail), default and custom allocations, power-of-two
+# and other subcarrier counts, with and without taper
+def custom_alloc(M):
+    p = np.full(M, 2, np.uint8)
+    p[0] = p[M // 2] = 0
+    p[1] = p[M - 1] = p[3] = 1
+    return p
+
+
+for M, cp, tl, custom, nsym in [(64, 16, 4, False, 9), (64, 16, 0, False, 3), (120, 20, 8, False, 5), (256, 32, 32, False, 40),
+                                (32, 8, 2, True, 70), (1024, 128, 16, False, 3), (10, 2, 1, True, 4)]:
+    tag = "ofdm_M%d_cp%d_t%d" % (M, cp, tl)
+    p = custom_alloc(M) if custom else None
+    x = O.synth_input(M * nsym, seed=0x5EEDF000 + M)
+    out[tag + "_args"] = np.array([M, cp, tl, int(custom)], np.int64)
+    out[tag + "_x"] = x
+    out[tag + "_frame"] = O.ofdm_frame(O.RefOfdmframegen(M, cp, tl, p), x)
 
 R = O.ref()
 R.estimate_req_filter_len.restype = C.c_uint

@@ -1359,6 +1359,188 @@ void orc_asgramcf_execute(orc_asgramcf q, char *ascii, float *peakval, float *pe
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* ofdmframegen: OFDM symbol generator -- subcarrier allocation,    */
+/* PLCP sequences, IFFT, cyclic prefix and tapered overlap.                               */
+/* src/multichannel/src/ofdmframe.common.c, ofdmframegen.c, src/sequence/src/msequence.c  */
+/* ------------------------------------------------------------------------------------ */
+
+/* default m-sequence of register length m (msequence.c:41-58: generator polynomial shifted right by one, initial
+ * state 1 << (m-1)); advance (:166-177): output bit = parity(v & g), pushed into the register */
+struct mseq { unsigned int m, g, n, v; };
+static const unsigned int mseq_poly[16] = {0, 0, 0x0003, 0x0005, 0x0009, 0x0012, 0x0021, 0x0044, 0x008E,
+                                           0x0108, 0x0204, 0x0402, 0x0829, 0x100d, 0x2015, 0x4001};
+static struct mseq mseq_default(unsigned int m)
+{
+    struct mseq s = {m, mseq_poly[m], (1u << m) - 1, 1u << (m - 1)};
+    return s;
+}
+static unsigned int mseq_advance(struct mseq *s)
+{
+    unsigned int b = (unsigned int)__builtin_parity(s->v & s->g);
+    s->v = ((s->v << 1) | b) & s->n;
+    return b;
+}
+static unsigned int mseq_symbol(struct mseq *s, unsigned int bps)
+{
+    unsigned int v = 0;
+    for (unsigned int i = 0; i < bps; i++) v = (v << 1) | mseq_advance(s);
+    return v;
+}
+
+static unsigned int nextpow2(unsigned int x)          /* math.c:143-157 */
+{
+    unsigned int n = 0;
+    x--;
+    while (x > 0) { x >>= 1; n++; }
+    return n;
+}
+
+/* ofdmframe.common.c:176-214 */
+void orc_ofdmframe_init_default_sctype(unsigned int M, unsigned char *p)
+{
+    unsigned int M2 = M / 2, G = M / 10;
+    if (G < 2) G = 2;
+    unsigned int P = (M > 34) ? 8 : 4, P2 = P / 2;
+    for (unsigned int i = 0; i < M; i++) p[i] = 0;
+    for (unsigned int i = 1; i + G < M2; i++) {
+        unsigned char t = (((i + P2) % P) == 0) ? 1 : 2;
+        p[i] = t;
+        p[M - i] = t;
+    }
+}
+
+/* ofdmframe.common.c:41-101 (which = 0: short sequence, even enabled subcarriers only) and :109-167 (which = 1: long
+ * sequence, register one longer): +-1 from bit 0 of 3-bit symbols, backward transform, scaled by 1/sqrt(enabled) */
+static unsigned int ofdm_plcp(const unsigned char *p, unsigned int M, int which, orc_cf *S, orc_cf *s)
+{
+    unsigned int m = nextpow2(M);
+    if (m < 4) m = 4; else if (m > 8) m = 8;
+    if (which) m++;
+    struct mseq ms = mseq_default(m);
+    unsigned int enabled = 0;
+    for (unsigned int i = 0; i < M; i++) {
+        unsigned int b = mseq_symbol(&ms, 3) & 1;
+        if (p[i] == 0 || (!which && (i % 2))) S[i] = cf(0.0f, 0.0f);
+        else { S[i] = cf(b ? 1.0f : -1.0f, 0.0f); enabled++; }
+    }
+    orc_fft_run(M, S, s, ORC_FFT_BACKWARD);
+    float g = 1.0f / sqrtf(enabled);
+    for (unsigned int i = 0; i < M; i++) s[i] = cf(s[i].re * g, s[i].im * g);
+    return enabled;
+}
+
+struct orc_ofdmframegen_s {
+    unsigned int M, cp, tl, n_pilot, n_data;
+    unsigned char *p;
+    float *taper, g_data;
+    orc_cf *postfix, *X, *x, *S0, *s0, *S1, *s1;
+    struct mseq pilot;
+};
+
+/* ofdmframegen.c:85-171 */
+orc_ofdmframegen orc_ofdmframegen_create(unsigned int M, unsigned int cp, unsigned int tl, const unsigned char *p)
+{
+    if (M < 2 || (M % 2) || cp > M || tl > cp) return NULL;
+    orc_ofdmframegen q = xmalloc(sizeof *q);
+    q->M = M; q->cp = cp; q->tl = tl;
+    q->p = xmalloc(M);
+    if (p) memcpy(q->p, p, M); else orc_ofdmframe_init_default_sctype(M, q->p);
+    q->n_pilot = q->n_data = 0;
+    for (unsigned int i = 0; i < M; i++) { q->n_pilot += q->p[i] == 1; q->n_data += q->p[i] == 2; }
+    if (q->n_data == 0 || q->n_pilot < 2) { free(q->p); free(q); return NULL; }
+    q->X = xmalloc(M * sizeof(orc_cf)); q->x = xmalloc(M * sizeof(orc_cf));
+    q->S0 = xmalloc(M * sizeof(orc_cf)); q->s0 = xmalloc(M * sizeof(orc_cf));
+    q->S1 = xmalloc(M * sizeof(orc_cf)); q->s1 = xmalloc(M * sizeof(orc_cf));
+    ofdm_plcp(q->p, M, 0, q->S0, q->s0);
+    ofdm_plcp(q->p, M, 1, q->S1, q->s1);
+    q->taper = xmalloc((tl ? tl : 1) * sizeof(float));
+    q->postfix = xmalloc((tl ? tl : 1) * sizeof(orc_cf));
+    for (unsigned int i = 0; i < tl; i++) {
+        float t = ((float)i + 0.5f) / (float)tl;
+        float g = sinf(M_PI_2 * t);
+        q->taper[i] = g * g;
+    }
+    q->g_data = 1.0f / sqrtf(q->n_pilot + q->n_data);
+    orc_ofdmframegen_reset(q);
+    return q;
+}
+
+void orc_ofdmframegen_destroy(orc_ofdmframegen q)
+{
+    if (!q) return;
+    free(q->p); free(q->taper); free(q->postfix); free(q->X); free(q->x);
+    free(q->S0); free(q->s0); free(q->S1); free(q->s1); free(q);
+}
+
+/* ofdmframegen.c:214-222 */
+void orc_ofdmframegen_reset(orc_ofdmframegen q)
+{
+    q->pilot = mseq_default(8);
+    memset(q->postfix, 0, q->tl * sizeof(orc_cf));
+}
+
+void orc_ofdmframegen_get_sctype(orc_ofdmframegen q, unsigned char *p) { memcpy(p, q->p, q->M); }
+
+/* ofdmframegen.c:345-361: cyclic prefix, taper against the previous symbol's postfix, keep the new postfix */
+static void ofdm_gensymbol(orc_ofdmframegen q, orc_cf *y)
+{
+    memcpy(y, q->x + (q->M - q->cp), q->cp * sizeof(orc_cf));
+    memcpy(y + q->cp, q->x, q->M * sizeof(orc_cf));
+    for (unsigned int i = 0; i < q->tl; i++) {
+        float a = q->taper[i], b = q->taper[q->tl - i - 1];
+        y[i] = cf(y[i].re * a, y[i].im * a);
+        y[i] = cf(y[i].re + q->postfix[i].re * b, y[i].im + q->postfix[i].im * b);
+    }
+    memcpy(q->postfix, q->x, q->tl * sizeof(orc_cf));
+}
+
+/* ofdmframegen.c:237-250 */
+void orc_ofdmframegen_write_S0a(orc_ofdmframegen q, orc_cf *y)
+{
+    for (unsigned int i = 0; i < q->M + q->cp; i++) y[i] = q->s0[(i + q->M - 2 * q->cp) % q->M];
+    for (unsigned int i = 0; i < q->tl; i++) y[i] = cf(y[i].re * q->taper[i], y[i].im * q->taper[i]);
+}
+
+/* ofdmframegen.c:252-264 */
+void orc_ofdmframegen_write_S0b(orc_ofdmframegen q, orc_cf *y)
+{
+    for (unsigned int i = 0; i < q->M + q->cp; i++) y[i] = q->s0[(i + q->M - q->cp) % q->M];
+    memcpy(q->postfix, q->s0, q->tl * sizeof(orc_cf));
+}
+
+/* ofdmframegen.c:266-272 */
+void orc_ofdmframegen_write_S1(orc_ofdmframegen q, orc_cf *y)
+{
+    memcpy(q->x, q->s1, q->M * sizeof(orc_cf));
+    ofdm_gensymbol(q, y);
+}
+
+/* ofdmframegen.c:279-311 over n symbols: x [n][M] -> y [n][M + cp] */
+void orc_ofdmframegen_writesymbols(orc_ofdmframegen q, const orc_cf *x, unsigned int n, orc_cf *y)
+{
+    for (unsigned int s = 0; s < n; s++) {
+        const orc_cf *xs = x + (size_t)s * q->M;
+        for (unsigned int i = 0; i < q->M; i++) {
+            unsigned int k = (i + q->M / 2) % q->M;
+            if (q->p[k] == 0) q->X[k] = cf(0.0f, 0.0f);
+            else if (q->p[k] == 1) q->X[k] = cf((mseq_advance(&q->pilot) ? 1.0f : -1.0f) * q->g_data, 0.0f);
+            else q->X[k] = cf(xs[k].re * q->g_data, xs[k].im * q->g_data);
+        }
+        orc_fft_run(q->M, q->X, q->x, ORC_FFT_BACKWARD);
+        ofdm_gensymbol(q, y + (size_t)s * (q->M + q->cp));
+    }
+}
+
+/* ofdmframegen.c:314-322 */
+void orc_ofdmframegen_writetail(orc_ofdmframegen q, orc_cf *y)
+{
+    for (unsigned int i = 0; i < q->tl; i++) {
+        float b = q->taper[q->tl - i - 1];
+        y[i] = cf(q->postfix[i].re * b, q->postfix[i].im * b);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* firpfbch2_crcf: channelizer with output rate 2 Fs / M                                 */
 /* ------------------------------------------------------------------------------------ */
 

@@ -145,6 +145,16 @@ def lib():
         L.orc_asgramcf_set_scale.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.orc_asgramcf_write.argtypes = [C.c_void_p, c_cf_p, C.c_uint]
         L.orc_asgramcf_execute.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        c_u8_p = np.ctypeslib.ndpointer(np.uint8, flags="C")
+        L.orc_ofdmframe_init_default_sctype.argtypes = [C.c_uint, c_u8_p]
+        L.orc_ofdmframegen_create.restype = C.c_void_p
+        L.orc_ofdmframegen_create.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_void_p]
+        L.orc_ofdmframegen_destroy.argtypes = [C.c_void_p]
+        L.orc_ofdmframegen_reset.argtypes = [C.c_void_p]
+        L.orc_ofdmframegen_get_sctype.argtypes = [C.c_void_p, c_u8_p]
+        for nm in ("write_S0a", "write_S0b", "write_S1", "writetail"):
+            getattr(L, "orc_ofdmframegen_" + nm).argtypes = [C.c_void_p, c_cf_p]
+        L.orc_ofdmframegen_writesymbols.argtypes = [C.c_void_p, c_cf_p, C.c_uint, c_cf_p]
         L.orc_fftfilt_create.restype = C.c_void_p
         L.orc_fftfilt_create.argtypes = [c_f_p, C.c_uint, C.c_uint]
         L.orc_fftfilt_destroy.argtypes = [C.c_void_p]
@@ -471,6 +481,56 @@ class Asgramcf(_Obj):
         pv, pf = C.c_float(), C.c_float()
         lib().orc_asgramcf_execute(self.h, buf, C.byref(pv), C.byref(pf))
         return buf.raw[:self.nfft].decode("ascii"), pv.value, pf.value
+
+
+class Ofdmframegen(_Obj):
+    """ofdmframegen: S0a / S0b / S1 / n data symbols / tail; p = subcarrier allocation (uint8) or None (default)"""
+    _destroy = "orc_ofdmframegen_destroy"
+
+    def __init__(self, M, cp_len, taper_len, p=None):
+        self.M, self.cp, self.tl = M, cp_len, taper_len
+        self._p = None if p is None else np.ascontiguousarray(p, np.uint8)
+        super().__init__(lib().orc_ofdmframegen_create(M, cp_len, taper_len,
+                                                       None if self._p is None else self._p.ctypes.data))
+
+    def reset(self):
+        lib().orc_ofdmframegen_reset(self.h)
+
+    def sctype(self):
+        p = np.empty(self.M, np.uint8)
+        lib().orc_ofdmframegen_get_sctype(self.h, p)
+        return p
+
+    def _sym(self, name):
+        y = np.empty(self.M + self.cp, np.complex64)
+        getattr(lib(), "orc_ofdmframegen_" + name)(self.h, y)
+        return y
+
+    def write_S0a(self):
+        return self._sym("write_S0a")
+
+    def write_S0b(self):
+        return self._sym("write_S0b")
+
+    def write_S1(self):
+        return self._sym("write_S1")
+
+    def writesymbols(self, x):
+        x = _cf(x)
+        n = len(x) // self.M
+        y = np.empty(n * (self.M + self.cp), np.complex64)
+        lib().orc_ofdmframegen_writesymbols(self.h, x, n, y)
+        return y
+
+    def writetail(self):
+        y = np.empty(max(self.tl, 1), np.complex64)
+        lib().orc_ofdmframegen_writetail(self.h, y)
+        return y[:self.tl]
+
+
+def ofdm_frame(q, x):
+    """a whole frame from an object with the methods above: S0a | S0b | S1 | data symbols | tail"""
+    return np.concatenate([q.write_S0a(), q.write_S0b(), q.write_S1(), q.writesymbols(x), q.writetail()])
 
 
 class Fftfilt(_Obj):
@@ -907,6 +967,58 @@ def ref_asgramcf(nfft, x, offset=None, scale=None):
     R.asgramcf_execute(q, buf, C.byref(pv), C.byref(pf))
     R.asgramcf_destroy(q)
     return buf.raw[:nfft].decode("ascii"), pv.value, pf.value
+
+
+class RefOfdmframegen:
+    """the compiled reference's ofdmframegen behind the same methods as Ofdmframegen"""
+
+    def __init__(self, M, cp_len, taper_len, p=None):
+        R = ref()
+        R.ofdmframegen_create.restype = C.c_void_p
+        R.ofdmframegen_create.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_void_p]
+        R.ofdmframegen_destroy.argtypes = [C.c_void_p]
+        R.ofdmframegen_reset.argtypes = [C.c_void_p]
+        for nm in ("write_S0a", "write_S0b", "write_S1", "writetail"):
+            getattr(R, "ofdmframegen_" + nm).argtypes = [C.c_void_p, c_cf_p]
+        R.ofdmframegen_writesymbol.argtypes = [C.c_void_p, c_cf_p, c_cf_p]
+        self.R, self.M, self.cp, self.tl = R, M, cp_len, taper_len
+        self._p = None if p is None else np.ascontiguousarray(p, np.uint8)
+        self.q = C.c_void_p(R.ofdmframegen_create(M, cp_len, taper_len, None if self._p is None else self._p.ctypes.data))
+
+    def __del__(self):
+        if getattr(self, "q", None):
+            self.R.ofdmframegen_destroy(self.q)
+            self.q = None
+
+    def reset(self):
+        self.R.ofdmframegen_reset(self.q)
+
+    def _sym(self, name):
+        y = np.empty(self.M + self.cp, np.complex64)
+        getattr(self.R, "ofdmframegen_" + name)(self.q, y)
+        return y
+
+    def write_S0a(self):
+        return self._sym("write_S0a")
+
+    def write_S0b(self):
+        return self._sym("write_S0b")
+
+    def write_S1(self):
+        return self._sym("write_S1")
+
+    def writesymbols(self, x):
+        x = _cf(x)
+        n = len(x) // self.M
+        y = np.empty(n * (self.M + self.cp), np.complex64)
+        for s in range(n):
+            self.R.ofdmframegen_writesymbol(self.q, x[s * self.M:(s + 1) * self.M], y[s * (self.M + self.cp):(s + 1) * (self.M + self.cp)])
+        return y
+
+    def writetail(self):
+        y = np.empty(max(self.tl, 1), np.complex64)
+        self.R.ofdmframegen_writetail(self.q, y)
+        return y[:self.tl]
 
 
 def ref_fftfilt_blocks(h, n, x, scale=None):

@@ -836,6 +836,37 @@ def test_asgramcf_vs_reference_fixture(L, orc, refrn2):
     assert sum(a != b for a, b in zip(ga, wa)) <= 1 and abs(gv - wv) < 1e-3 and gf == wf
 
 
+# ------------------------------------------------------------------ ofdmframegen
+def test_ofdmframegen_vs_reference_fixture_and_oracle(L, orc, refrn2, monkeypatch):
+    """whole frames against the compiled reference (default / custom allocation, power-of-two and other M, no
+    taper), symbol-by-symbol and block calls mixed on one object (pilot sequence and overlap carried), the
+    one-kernel path against the scratch path, and long blocks against the oracle"""
+    from test_oracle import _ofdm_cases
+    for tag, M, cp, tl, p in _ofdm_cases(refrn2):
+        x, want = refrn2[tag + "_x"], refrn2[tag + "_frame"]
+        for generic in (False, True):
+            if generic:
+                monkeypatch.setenv("LIQUID_CUDA_OFDM_GENERIC", "1")
+            else:
+                monkeypatch.delenv("LIQUID_CUDA_OFDM_GENERIC", raising=False)
+            q = L.ofdmframegen(M, cp, tl, p)
+            assert np.array_equal(q.sctype(), orc.Ofdmframegen(M, cp, tl, p).sctype())
+            got = np.concatenate([q.write_S0a(), q.write_S0b(), q.write_S1(), q.writesymbol(x[:M]), q.writesymbols(x[M:3 * M]),
+                                  q.writesymbols(x[3 * M:]), q.writetail()])
+            assert got.shape == want.shape and np.abs(got - want).max() < 3e-6 * np.abs(want).max(), (tag, generic)
+            q.reset()
+            assert np.abs(orc.ofdm_frame(q, x) - want).max() < 3e-6 * np.abs(want).max(), (tag, generic)
+        monkeypatch.delenv("LIQUID_CUDA_OFDM_GENERIC", raising=False)
+    assert np.array_equal(L.ofdmframe_init_default_sctype(120), orc.Ofdmframegen(120, 8, 2).sctype())
+    for M, cp, tl, nsym in ((64, 16, 4, 5000), (256, 64, 16, 3000), (2048, 512, 64, 300), (200, 40, 10, 700)):
+        x = orc.synth_input(M * nsym, seed=0xF0 + M)
+        q, o = L.ofdmframegen(M, cp, tl), orc.Ofdmframegen(M, cp, tl)
+        cut = (nsym // 3 + 1) * M
+        got = np.concatenate([q.writesymbols(x[:cut]), q.writesymbols(x[cut:]), q.writetail()])
+        want = np.concatenate([o.writesymbols(x), o.writetail()])
+        assert np.abs(got - want).max() < 4e-6 * np.abs(want).max(), M
+
+
 # ------------------------------------------------------------------ fftfilt (SURVEY 8f item 3)
 def test_fftfilt_vs_reference_fixture_and_oracle(L, orc, refrn2, monkeypatch):
     """the compiled reference's outputs (power-of-two and other block sizes, set_scale), state carried over calls of

@@ -139,6 +139,9 @@ BAD_CALLS = [
     ("L.lib.asgramcf_create(1)", "asgramcf_create"),                                              # asgram.c:51-54
     ("L.lib.estimate_req_filter_len(0.7, 60.0)", "estimate_req_filter_len"),                      # firdes.c:55-58
     ("L.lib.spgramcf_create_kaiser(1, 1, 3.0)", "spgramcf_create"),                               # spgram.c:63-66
+    ("L.lib.ofdmframegen_create(63, 8, 2, None)", "ofdmframegen_create"),                         # ofdmframegen.c:94-96
+    ("L.lib.ofdmframegen_create(64, 8, 9, None)", "ofdmframegen_create"),                         # ofdmframegen.c:100-102
+    ("L.lib.ofdmframegen_create(8, 2, 1, np.zeros(8, np.uint8).ctypes.data)", "ofdmframegen_create"),   # :121-123
 ]
 
 

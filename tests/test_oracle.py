@@ -569,3 +569,45 @@ def asgram_check(q, fx, tag, offset, scale):
 def test_fixture_asgramcf(orc, refrn2):
     for tag, nfft, offset, scale in _asg_cases(refrn2):
         asgram_check(orc.Asgramcf(nfft), refrn2, tag, offset, scale)
+
+
+# ------------------------------------------------------------------ ofdmframegen
+def ofdm_custom_alloc(M):
+    p = np.full(M, 2, np.uint8)
+    p[0] = p[M // 2] = 0
+    p[1] = p[M - 1] = p[3] = 1
+    return p
+
+
+def _ofdm_cases(fx):
+    for name in sorted(k for k in fx if k.startswith("ofdm_") and k.endswith("_args")):
+        M, cp, tl, custom = (int(v) for v in fx[name])
+        yield name[:-5], M, cp, tl, (ofdm_custom_alloc(M) if custom else None)
+
+
+def test_fixture_ofdmframegen(orc, refrn2):
+    for tag, M, cp, tl, p in _ofdm_cases(refrn2):
+        want = refrn2[tag + "_frame"]
+        got = orc.ofdm_frame(orc.Ofdmframegen(M, cp, tl, p), refrn2[tag + "_x"])
+        assert got.shape == want.shape and np.abs(got - want).max() < 2e-6 * np.abs(want).max(), tag
+
+
+def test_ofdmframegen_properties(orc):
+    """what the generator stands for: the default allocation (guard band, DC null, pilot spacing); the body of a
+    data symbol is the scaled IDFT of the mapped subcarriers with BPSK pilots; the cyclic prefix repeats the end of
+    the body; consecutive symbols overlap-add to a constant-envelope taper (taper[i] + taper[tl-1-i] = 1)"""
+    M, cp, tl = 64, 16, 8
+    q = orc.Ofdmframegen(M, cp, tl)
+    p = q.sctype()
+    assert p[0] == 0 and np.all(p[M // 2 - 6:M // 2 + 7] == 0) and (p == 1).sum() == 6 and (p == 2).sum() == 44
+    x = orc.synth_input(M * 3, seed=11)
+    y = q.writesymbols(x).reshape(3, M + cp)
+    g = 1.0 / np.sqrt((p != 0).sum())
+    for s in range(3):
+        X = np.fft.fft(y[s, cp:]) / M                      # the reference transform is unscaled
+        assert np.abs(X[p == 2] - x[s * M:(s + 1) * M][p == 2] * g).max() < 1e-5
+        assert np.allclose(np.abs(X[p == 1]), g, atol=1e-5) and np.abs(X[p == 1].imag).max() < 1e-5
+        assert np.abs(X[p == 0]).max() < 1e-5
+        assert np.abs(y[s, tl:cp] - y[s, M + tl:M + cp]).max() < 1e-6
+    t = np.sin(np.pi / 2 * (np.arange(tl) + 0.5) / tl) ** 2
+    assert np.abs(y[1, :tl] - (y[1, M:M + tl] * t + y[0, cp:cp + tl] * t[::-1])).max() < 1e-6

@@ -3,7 +3,7 @@
 measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
 events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
 
-  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [f4] [f5] [s] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
+  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [f4] [f5] [f6] [s] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
 """
 import argparse
 import json
@@ -228,6 +228,20 @@ def main():
             report("f5: fftfilt_crcf %d taps, blocks of %d (2n = %d point transforms), 2^28 samples" % (h_len, n, 2 * n),
                    n_s, 16, ms, ln)
         del x, y
+    if "f6" in args.configs:
+        # ofdmframegen data symbols, default allocation, 2^27 subcarrier values per step
+        n_s = 1 << 27
+        x = torch.empty(2 * n_s, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr(), n_s, stream=st.cuda_stream)
+        for M, cp, tl in ((64, 16, 4), (1024, 128, 16), (4096, 512, 64)):
+            y = torch.empty(2 * (n_s // M) * (M + cp), dtype=torch.float32, device=dev)
+            q = L.ofdmframegen(M, cp, tl)
+            ms, ln = timed(lambda: q.writesymbols_dev(x.data_ptr(), n_s // M, y.data_ptr(), st.cuda_stream))
+            report("f6: ofdmframegen M=%d cp=%d taper=%d, 2^27 subcarrier values (%d symbols)" % (M, cp, tl, n_s // M),
+                   n_s, 8 + 8 * (M + cp) / M, ms, ln,
+                   {"note": "throughput in subcarrier values/s; algorithmic bytes 8 in + 8 (M + cp)/M out each"})
+            del y
+        del x
     if "fft" in args.configs:
         # a11: the batched complex FFT on its own (fft_execute_batch_dev), 2^28 points per step, out of place
         import numpy as np
