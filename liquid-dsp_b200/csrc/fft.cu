@@ -49,19 +49,21 @@ struct GlobalDst {
 // first pass from global memory, last pass to global memory: a transform makes no extra trip through shared
 // memory at either end, and transforms of up to 16 points never touch it.  In place (x == y) is fine: a CTA
 // has read all the inputs of its transforms before it writes any of their outputs.
+template <bool TWG>
 __global__ void __launch_bounds__(kFftThreads)
 fft_pow2_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const float2 *__restrict__ tw,
                 unsigned int n, unsigned int log2n, unsigned int per_cta, unsigned long long batch,
                 float sgn, int post_mode, float pa, float pb)
 {
     extern __shared__ float2 smem[];
-    const lcfft::Smem sm = lcfft::carve(smem, n, per_cta);
+    lcfft::Smem sm = lcfft::carve(smem, n, per_cta);
     const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
-    if (log2n > 4) lcfft::stage_twiddles(sm, tw, n);          // published by the barrier after the first pass
+    if (TWG) sm.tw = const_cast<float2 *>(tw);                // long transforms: the plan's table itself, through L1
+    else if (log2n > 4) lcfft::stage_twiddles(sm, tw, n);     // published by the barrier after the first pass
     const GlobalSrc src{x, n, first, batch};
     const GlobalDst dst{y, n, first, batch, post_mode, pa, pb};
-    if (sgn > 0.0f) lcfft::stockham_run<+1>(sm, n, log2n, per_cta, src, dst);
-    else            lcfft::stockham_run<-1>(sm, n, log2n, per_cta, src, dst);
+    if (sgn > 0.0f) lcfft::stockham_run<+1, TWG>(sm, n, log2n, per_cta, src, dst);
+    else            lcfft::stockham_run<-1, TWG>(sm, n, log2n, per_cta, src, dst);
 }
 
 // table-driven DFT, one CTA per transform; smem: n float2
@@ -108,7 +110,10 @@ void FftPlanDev::init(unsigned int n_, int sign_)
         // transforms above 3072 points need more than the default 48 KB of dynamic smem
         static std::atomic<unsigned long long> configured{0};
         if (first_time_on_device(configured))
-            LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        {
+            LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        }
     }
 }
 
@@ -131,17 +136,22 @@ void FftPlanDev::run(const float2 *d_x, float2 *d_y, unsigned long long batch, c
         return;
     }
     if (lcfft::pow2_in_smem(n)) {
-        const unsigned int per_cta = lcfft::per_cta_for(n, batch);     // aim at 2048 points per CTA
-        const size_t smem = lcfft::smem_for(n, per_cta);
+        // aim at 2048 points per CTA
+        const unsigned int per_cta = lcfft::per_cta_for(n, batch);
+        const bool twg = n >= lcfft::kTwGlobalFrom;
+        const size_t smem = lcfft::smem_for(n, per_cta, !twg);
         const unsigned long long max_grid = 1ull << 30;
         unsigned long long done = 0;
         while (done < batch) {      // grid.x limit is 2^31-1; keep launches below 2^30 CTAs
             unsigned long long nb = batch - done;
             unsigned long long ctas = (nb + per_cta - 1) / per_cta;
             if (ctas > max_grid) { ctas = max_grid; nb = ctas * per_cta; }
-            fft_pow2_kernel<<<(unsigned int)ctas, kFftThreads, smem, st>>>(
-                d_x + done * n, d_y + done * n, d_twp, n, ilog2(n), per_cta, nb,
-                (float)sign, post_mode, a, b);
+            if (twg)
+                fft_pow2_kernel<true><<<(unsigned int)ctas, kFftThreads, smem, st>>>(
+                    d_x + done * n, d_y + done * n, d_twp, n, ilog2(n), per_cta, nb, (float)sign, post_mode, a, b);
+            else
+                fft_pow2_kernel<false><<<(unsigned int)ctas, kFftThreads, smem, st>>>(
+                    d_x + done * n, d_y + done * n, d_twp, n, ilog2(n), per_cta, nb, (float)sign, post_mode, a, b);
             LC_LAUNCH_CHECK();
             done += nb;
         }

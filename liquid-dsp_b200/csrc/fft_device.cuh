@@ -44,6 +44,12 @@ __device__ __forceinline__ Smem carve(float2 *base, unsigned int n, unsigned int
 // cooperative copy of the plan's PASS-ORDERED table (FftPlanDev::d_twp, n entries: for every pass after the first,
 // in order, the R-1 rows W_{R Ns}^(k m), k < Ns, of that pass; zero padded); a barrier must follow before the FFT
 // (the callers' own barrier after filling buf0 serves)
+// From kTwGlobalFrom points on the FFT-only kernels (fft.cu, fftfilt.cu, ofdmframe.cu; kernel template parameter TWG)
+// do NOT stage the table: a CTA holds one or two such transforms, so its table would be as large as its data; the
+// passes then read the plan's table in global memory through L1 (stockham_run<SIGN, true>: coalesced, because of
+// the pass order) and the shared memory saved goes into occupancy.  The analyzers and the periodogram, whose fill
+// phases live on L1 themselves, keep the staged copy (measured: slower without it).
+constexpr unsigned int kTwGlobalFrom = 1024;
 __device__ __forceinline__ void stage_twiddles(const Smem &s, const float2 *__restrict__ tw, unsigned int n)
 {
     for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) s.tw[i] = __ldg(tw + i);
@@ -67,7 +73,7 @@ struct SmemDst {
 // one Stockham autosort pass of radix R over the per_cta transforms: butterfly j of transform f reads elements
 // j + m q (q = n / R), multiplies by W_{R Ns}^(k m) (k = j mod Ns), does the R-point DFT in registers and writes
 // elements (j - k) R + k + m Ns
-template <int R, int SIGN, class Src, class Dst>
+template <int R, int SIGN, bool TWG, class Src, class Dst>
 __device__ __forceinline__ void stockham_pass(const Src &src, const Dst &dst, const float2 *__restrict__ twp,
                                               unsigned int n, unsigned int log2n, unsigned int Ns, unsigned int per_cta)
 {
@@ -84,7 +90,7 @@ __device__ __forceinline__ void stockham_pass(const Src &src, const Dst &dst, co
             // this pass's table holds W_{R Ns}^(k m) at [(m-1) Ns + k]: the lanes of a warp (consecutive k) read
             // consecutive entries
 #pragma unroll
-            for (int m = 1; m < R; m++) v[m] = lcf::cmul2(v[m], twp[(m - 1) * Ns + k]);
+            for (int m = 1; m < R; m++) v[m] = lcf::cmul2(v[m], TWG ? __ldg(twp + (m - 1) * Ns + k) : twp[(m - 1) * Ns + k]);
         }
         lcf::RegDft<R, SIGN>::run(v);
         const unsigned int d = (j - k) * R + k;
@@ -97,7 +103,9 @@ __device__ __forceinline__ void stockham_pass(const Src &src, const Dst &dst, co
 // 8 / 4 / 2.  The first pass reads through `first`, the last pass writes through `last`; passes in between
 // ping-pong in shared memory with a block barrier after each.  When the transform has more than one pass the
 // twiddle table must have been staged (stage_twiddles) -- the barrier after the first pass publishes it.
-template <int SIGN, class Src, class Dst>
+// TWG: the table pointer s.tw is the plan's table in GLOBAL memory (read through L1, coalesced thanks to the pass
+// order) instead of a staged copy -- for long transforms, where a CTA's table would be as large as its data
+template <int SIGN, bool TWG = false, class Src, class Dst>
 __device__ __forceinline__ void stockham_run(const Smem &s, unsigned int n, unsigned int log2n, unsigned int per_cta,
                                              const Src &first, const Dst &last)
 {
@@ -110,10 +118,10 @@ __device__ __forceinline__ void stockham_run(const Smem &s, unsigned int n, unsi
         const bool is_last = (left == ((R == 16) ? 4u : (R == 8) ? 3u : (R == 4) ? 2u : 1u));                    \
         const SmemSrc ssrc{in, log2n};                                                                           \
         const SmemDst sdst{out, log2n};                                                                          \
-        if (is_first && is_last)  stockham_pass<R, SIGN>(first, last, twp, n, log2n, Ns, per_cta);               \
-        else if (is_first)        stockham_pass<R, SIGN>(first, sdst, twp, n, log2n, Ns, per_cta);               \
-        else if (is_last)         stockham_pass<R, SIGN>(ssrc, last, twp, n, log2n, Ns, per_cta);                \
-        else                      stockham_pass<R, SIGN>(ssrc, sdst, twp, n, log2n, Ns, per_cta);                \
+        if (is_first && is_last)  stockham_pass<R, SIGN, TWG>(first, last, twp, n, log2n, Ns, per_cta);               \
+        else if (is_first)        stockham_pass<R, SIGN, TWG>(first, sdst, twp, n, log2n, Ns, per_cta);               \
+        else if (is_last)         stockham_pass<R, SIGN, TWG>(ssrc, last, twp, n, log2n, Ns, per_cta);                \
+        else                      stockham_pass<R, SIGN, TWG>(ssrc, sdst, twp, n, log2n, Ns, per_cta);                \
         if (!is_last) __syncthreads();                                                                           \
     } while (0)
     while (left >= 4) {
@@ -132,14 +140,14 @@ __device__ __forceinline__ void stockham_run(const Smem &s, unsigned int n, unsi
 
 // the same with the result left in shared memory (padded layout, natural order): returns the buffer that
 // holds it; a block barrier has been passed when it returns
-template <int SIGN, class Src>
+template <int SIGN, bool TWG = false, class Src>
 __device__ __forceinline__ const float2 *stockham_run_to_smem(const Smem &s, unsigned int n, unsigned int log2n,
                                                               unsigned int per_cta, const Src &first)
 {
     // the buffer the last pass writes: passes alternate buf1, buf0, buf1, ...
     const unsigned int n_passes = (log2n + 3) / 4;
     float2 *res = (n_passes & 1) ? s.buf1 : s.buf0;
-    stockham_run<SIGN>(s, n, log2n, per_cta, first, SmemDst{res, log2n});
+    stockham_run<SIGN, TWG>(s, n, log2n, per_cta, first, SmemDst{res, log2n});
     __syncthreads();
     return res;
 }
@@ -176,9 +184,9 @@ inline unsigned int per_cta_for(unsigned int n, unsigned long long batch, unsign
     while (per_cta * n < target_points && per_cta < batch) per_cta <<= 1;
     return per_cta;
 }
-inline size_t smem_for(unsigned int n, unsigned int per_cta)
+inline size_t smem_for(unsigned int n, unsigned int per_cta, bool staged_table = true)
 {
-    return ((size_t)2 * padded_len(n, per_cta) + n) * sizeof(float2);
+    return ((size_t)2 * padded_len(n, per_cta) + (staged_table ? n : 0)) * sizeof(float2);
 }
 inline bool pow2_in_smem(unsigned int n) { return lc::is_pow2(n) && n >= 2 && (size_t)n * 16 <= 200 * 1024; }
 

@@ -79,6 +79,7 @@ struct KeepDst {
     }
 };
 
+template <bool TWG>
 __global__ void __launch_bounds__(lcfft::kFftThreads)
 fftfilt_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, const float2 *__restrict__ Hf,
                     const float2 *__restrict__ tw_f, const float2 *__restrict__ tw_b, float2 *__restrict__ y,
@@ -86,19 +87,24 @@ fftfilt_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ 
 {
     extern __shared__ float2 smem_f2[];
     const unsigned int N = 2 * n;
-    const lcfft::Smem sf = lcfft::carve(smem_f2, N, per_cta);          // buf0, buf1, forward table
+    lcfft::Smem sf = lcfft::carve(smem_f2, N, per_cta);                // buf0, buf1, forward table
     float2 *twb = sf.tw + N;                                           // backward table behind it
-    for (unsigned int i = threadIdx.x; i < N; i += blockDim.x) {
-        sf.tw[i] = __ldg(tw_f + i);
-        twb[i] = __ldg(tw_b + i);
+    if (TWG) {                                                         // long transforms: the plans' tables, through L1
+        sf.tw = const_cast<float2 *>(tw_f);
+        twb = const_cast<float2 *>(tw_b);
     }
+    if (!TWG)
+        for (unsigned int i = threadIdx.x; i < N; i += blockDim.x) {
+            sf.tw[i] = __ldg(tw_f + i);
+            twb[i] = __ldg(tw_b + i);
+        }
     const unsigned long long b0 = (unsigned long long)blockIdx.x * per_cta;
     const SegmentSrc src{hist, x, (int)n, n, b0, n_blocks};
-    const float2 *X = lcfft::stockham_run_to_smem<-1>(sf, N, log2N, per_cta, src);
+    const float2 *X = lcfft::stockham_run_to_smem<-1, TWG>(sf, N, log2N, per_cta, src);
     // the backward transform starts from the buffer that holds X
     float2 *other = (X == sf.buf0) ? sf.buf1 : sf.buf0;
     const lcfft::Smem sb{const_cast<float2 *>(X), other, twb};
-    lcfft::stockham_run<+1>(sb, N, log2N, per_cta, ProductSrc{X, Hf, log2N}, KeepDst{y, n, scale, b0, n_blocks});
+    lcfft::stockham_run<+1, TWG>(sb, N, log2N, per_cta, ProductSrc{X, Hf, log2N}, KeepDst{y, n, scale, b0, n_blocks});
 }
 
 // ---- any other n: through scratch ---------------------------------------------------------------------------
@@ -142,7 +148,11 @@ inline unsigned int grid_for(unsigned long long total)
     return (unsigned int)(b < cap ? (b ? b : 1) : cap);
 }
 
-size_t pow2_smem(unsigned int N, unsigned int per_cta) { return lcfft::smem_for(N, per_cta) + sizeof(float2) * N; }
+size_t pow2_smem(unsigned int N, unsigned int per_cta)
+{
+    const bool staged = N < lcfft::kTwGlobalFrom;                      // forward and backward tables
+    return lcfft::smem_for(N, per_cta, staged) + (staged ? sizeof(float2) * N : 0);
+}
 
 void blocks_dev(fftfilt_crcf q, const float2 *d_x, unsigned long long n_blocks, float2 *d_y, cudaStream_t st)
 {
@@ -150,13 +160,19 @@ void blocks_dev(fftfilt_crcf q, const float2 *d_x, unsigned long long n_blocks, 
     const unsigned int n = q->n, N = 2 * n;
     if (lcfft::pow2_in_smem(N) && pow2_smem(N, 1) <= 200 * 1024 && !getenv("LIQUID_CUDA_FFTFILT_GENERIC")) {
         static std::atomic<unsigned long long> configured{0};
-        if (lc::first_time_on_device(configured))
-            LC_CUDA_CHECK(cudaFuncSetAttribute(fftfilt_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (lc::first_time_on_device(configured)) {
+            LC_CUDA_CHECK(cudaFuncSetAttribute(fftfilt_pow2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LC_CUDA_CHECK(cudaFuncSetAttribute(fftfilt_pow2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        }
         const unsigned int per_cta = lcfft::per_cta_for(N, n_blocks, 4096);
         const unsigned long long ctas = (n_blocks + per_cta - 1) / per_cta;
         if (ctas >= (1ull << 31)) lc::fatal("fftfilt_crcf_execute_block", "too many blocks for one launch");
-        fftfilt_pow2_kernel<<<(unsigned int)ctas, lcfft::kFftThreads, pow2_smem(N, per_cta), st>>>(
-            q->d_hist, d_x, q->d_H, q->fwd.d_twp, q->bwd.d_twp, d_y, n, lc::ilog2(N), per_cta, n_blocks, q->scale);
+        if (N >= lcfft::kTwGlobalFrom)
+            fftfilt_pow2_kernel<true><<<(unsigned int)ctas, lcfft::kFftThreads, pow2_smem(N, per_cta), st>>>(
+                q->d_hist, d_x, q->d_H, q->fwd.d_twp, q->bwd.d_twp, d_y, n, lc::ilog2(N), per_cta, n_blocks, q->scale);
+        else
+            fftfilt_pow2_kernel<false><<<(unsigned int)ctas, lcfft::kFftThreads, pow2_smem(N, per_cta), st>>>(
+                q->d_hist, d_x, q->d_H, q->fwd.d_twp, q->bwd.d_twp, d_y, n, lc::ilog2(N), per_cta, n_blocks, q->scale);
         LC_LAUNCH_CHECK();
     } else {
         // pieces of at most ~256 MB of scratch per buffer

@@ -135,16 +135,18 @@ struct PrefixDst {
     }
 };
 
+template <bool TWG>
 __global__ void __launch_bounds__(lcfft::kFftThreads, 3)
 ofdm_symbols_pow2_kernel(MapArgs a, const float2 *__restrict__ x, const float2 *__restrict__ tw, const float *__restrict__ taper,
                          float2 *__restrict__ y, unsigned int log2M, unsigned int per_cta, unsigned int cp, unsigned int tl,
                          unsigned long long n_sym)
 {
     extern __shared__ float2 smem_f2[];
-    const lcfft::Smem sm = lcfft::carve(smem_f2, a.M, per_cta);
-    if (log2M > 4) lcfft::stage_twiddles(sm, tw, a.M);
+    lcfft::Smem sm = lcfft::carve(smem_f2, a.M, per_cta);
+    if (TWG) sm.tw = const_cast<float2 *>(tw);
+    else if (log2M > 4) lcfft::stage_twiddles(sm, tw, a.M);
     const unsigned long long s0 = (unsigned long long)blockIdx.x * per_cta;
-    lcfft::stockham_run<+1>(sm, a.M, log2M, per_cta, SymbolSrc{a, x, s0, n_sym, (unsigned int)(s0 % kPilotPeriod)},
+    lcfft::stockham_run<+1, TWG>(sm, a.M, log2M, per_cta, SymbolSrc{a, x, s0, n_sym, (unsigned int)(s0 % kPilotPeriod)},
                             PrefixDst{y, taper, a.M, cp, tl, s0, n_sym});
 }
 
@@ -226,13 +228,21 @@ void symbols_dev(ofdmframegen q, const float2 *d_x, unsigned long long n, float2
     const unsigned int M = q->M;
     if (lcfft::pow2_in_smem(M) && !getenv("LIQUID_CUDA_OFDM_GENERIC")) {
         static std::atomic<unsigned long long> configured{0};
-        if (lc::first_time_on_device(configured))
-            LC_CUDA_CHECK(cudaFuncSetAttribute(ofdm_symbols_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (lc::first_time_on_device(configured)) {
+            LC_CUDA_CHECK(cudaFuncSetAttribute(ofdm_symbols_pow2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LC_CUDA_CHECK(cudaFuncSetAttribute(ofdm_symbols_pow2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        }
         const unsigned int per_cta = lcfft::per_cta_for(M, n);
         const unsigned long long ctas = (n + per_cta - 1) / per_cta;
         if (ctas >= (1ull << 31)) lc::fatal("ofdmframegen_writesymbols", "too many symbols for one launch");
-        ofdm_symbols_pow2_kernel<<<(unsigned int)ctas, lcfft::kFftThreads, lcfft::smem_for(M, per_cta), st>>>(
-            a, d_x, q->ifft.d_twp, q->d_taper, d_y, lc::ilog2(M), per_cta, q->cp_len, q->taper_len, n);
+        const bool twg = M >= lcfft::kTwGlobalFrom;
+        const size_t smem = lcfft::smem_for(M, per_cta, !twg);
+        if (twg)
+            ofdm_symbols_pow2_kernel<true><<<(unsigned int)ctas, lcfft::kFftThreads, smem, st>>>(
+                a, d_x, q->ifft.d_twp, q->d_taper, d_y, lc::ilog2(M), per_cta, q->cp_len, q->taper_len, n);
+        else
+            ofdm_symbols_pow2_kernel<false><<<(unsigned int)ctas, lcfft::kFftThreads, smem, st>>>(
+                a, d_x, q->ifft.d_twp, q->d_taper, d_y, lc::ilog2(M), per_cta, q->cp_len, q->taper_len, n);
         LC_LAUNCH_CHECK();
         if (q->taper_len) {
             ofdm_overlap_kernel<<<grid_for(n * q->taper_len), kThreads, 0, st>>>(d_y, q->d_postfix, q->d_taper, M, q->cp_len, q->taper_len, n);
