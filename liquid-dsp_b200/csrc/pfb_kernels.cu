@@ -499,9 +499,75 @@ void launch_pfbch_mac_cc(const float2 *d_hist, const float2 *d_x, int H, const f
     LC_LAUNCH_CHECK();
 }
 
+namespace {
+// firpfbch synthesis FIR with a column's window and taps in registers (P taps, compile time): thread i owns output
+// column i of a chunk of frames, loads each row of v once (8 rows in flight) and slides its window by one per frame,
+// instead of P loads per output through L2.  Same tap_mac sequence as pfbch_synth_fir_kernel: identical bits.
+constexpr unsigned int kSynthChunk = 256;                  // frames per CTA
+template <typename TapT, int P>
+__global__ void __launch_bounds__(128)
+pfbch_synth_fir_win_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ v, int hist_rows,
+                           const TapT *__restrict__ taps, float2 *__restrict__ y, unsigned int M, unsigned long long n_frames)
+{
+    const unsigned int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= M) return;
+    const long long s0 = (long long)blockIdx.y * kSynthChunk;
+    long long s_end = s0 + kSynthChunk;
+    if (s_end > (long long)n_frames) s_end = (long long)n_frames;
+    TapT c[P];
+#pragma unroll
+    for (int n = 0; n < P; n++) c[n] = __ldg(taps + (size_t)n * M + i);
+    float2 win[P];                                         // win[n] = row s - n
+#pragma unroll
+    for (int n = 1; n < P; n++) {                          // rows s0 - 1 ... s0 - (P-1), shifted in by the first frame
+        const long long r = s0 - n;
+        win[n - 1] = (r >= 0) ? __ldg(v + (size_t)r * M + i) : __ldg(hist + (size_t)(hist_rows + r) * M + i);
+    }
+    constexpr int U = 8;
+    for (long long s = s0; s < s_end; s += U) {
+        float2 rows[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) rows[u] = (s + u < s_end) ? __ldg(v + (size_t)(s + u) * M + i) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (s + u < s_end) {
+#pragma unroll
+                for (int n = P - 1; n > 0; n--) win[n] = win[n - 1];
+                win[0] = rows[u];
+                float re = 0.f, im = 0.f;
+#pragma unroll
+                for (int n = 0; n < P; n++) tap_mac(c[n], win[n], re, im);
+                y[(size_t)(s + u) * M + i] = make_float2(re, im);
+            }
+        }
+    }
+}
+
+template <typename TapT>
+bool launch_synth_fir_win(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const TapT *d_taps, float2 *d_y,
+                          unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st)
+{
+    const unsigned long long chunks = (n_frames + kSynthChunk - 1) / kSynthChunk;
+    if (n_frames < 2 * kSynthChunk || chunks > 65535 || hist_rows + 1 < (int)p || getenv("LIQUID_CUDA_SYNTH_NO_WINDOW")) return false;
+    const dim3 grid((M + 127) / 128, (unsigned int)chunks);
+    switch (p) {
+#define LC_WIN(PP)                                                                                                   \
+    case PP:                                                                                                         \
+        pfbch_synth_fir_win_kernel<TapT, PP><<<grid, 128, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames); \
+        break;
+        LC_WIN(2) LC_WIN(3) LC_WIN(4) LC_WIN(5) LC_WIN(6) LC_WIN(7) LC_WIN(8) LC_WIN(10) LC_WIN(12) LC_WIN(14) LC_WIN(16)
+#undef LC_WIN
+    default: return false;
+    }
+    LC_LAUNCH_CHECK();
+    return true;
+}
+}  // namespace
+
 void launch_pfbch_synth_fir(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float *d_taps,
                             float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st)
 {
+    if (launch_synth_fir_win<float>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, p, n_frames, st)) return;
     pfbch_synth_fir_kernel<float><<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, p, n_frames);
     LC_LAUNCH_CHECK();
 }
@@ -509,6 +575,7 @@ void launch_pfbch_synth_fir(const float2 *d_hist_rows, const float2 *d_v, int hi
 void launch_pfbch_synth_fir_cc(const float2 *d_hist_rows, const float2 *d_v, int hist_rows, const float2 *d_taps,
                                float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st)
 {
+    if (launch_synth_fir_win<float2>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, p, n_frames, st)) return;
     pfbch_synth_fir_kernel<float2><<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, p, n_frames);
     LC_LAUNCH_CHECK();
 }

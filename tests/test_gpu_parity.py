@@ -237,6 +237,32 @@ def test_pfbch_analysis_and_synthesis_vs_oracle(L, orc, M, m, nfr):
             assert rel_rms_per_channel(got, want).max() < TOL_REL_RMS
 
 
+@pytest.mark.parametrize("M,m,nfr", [(64, 2, 1500), (100, 3, 900), (1024, 2, 700), (512, 5, 600), (2048, 4, 530)])
+def test_pfbch_synthesis_register_window_vs_oracle(L, orc, monkeypatch, M, m, nfr):
+    """long blocks take the register-window synthesis FIR (pfb_kernels.cu, p = 2m taps in registers): against the
+    oracle, state carried over an awkward cut, and bit for bit against the plain FIR kernel; complex taps too"""
+    X = orc.synth_input(nfr * M, seed=0xD0 + M)
+    want = orc.Firpfbch(orc.SYNTHESIZER, M, kaiser=(m, 60.0)).execute_frames(X)
+    outs = {}
+    for plain in (False, True):
+        if plain:
+            monkeypatch.setenv("LIQUID_CUDA_SYNTH_NO_WINDOW", "1")
+        else:
+            monkeypatch.delenv("LIQUID_CUDA_SYNTH_NO_WINDOW", raising=False)
+        q = L.firpfbch_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+        cut = (nfr // 2 + 7) * M
+        outs[plain] = np.concatenate([q.execute_block(X[:cut]), q.execute_block(X[cut:])])
+    monkeypatch.delenv("LIQUID_CUDA_SYNTH_NO_WINDOW", raising=False)
+    assert np.abs(outs[False] - want).max() / np.abs(want).max() < 1e-5
+    assert np.array_equal(outs[False].view(np.uint32), outs[True].view(np.uint32))
+    if M <= 512:
+        rng = np.random.default_rng(M)
+        h = ((rng.standard_normal(M * 2 * m) + 1j * rng.standard_normal(M * 2 * m)) / (2 * m)).astype(np.complex64)
+        got = L.firpfbch_cccf.create(L.LIQUID_SYNTHESIZER, M, 2 * m, h).execute_block(X)
+        o = orc.FirpfbchCccf(orc.SYNTHESIZER, M, 2 * m, h).execute_frames(X)
+        assert np.abs(got - o).max() / np.abs(o).max() < 1e-5
+
+
 @pytest.mark.parametrize("M,m", [(4, 3), (16, 4), (10, 2), (64, 5)])
 def test_pfbch_vs_reference_fixtures(L, refout, M, m):
     x = refout["pfbch_a_M%d_m%d_x" % (M, m)]
