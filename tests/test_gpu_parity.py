@@ -1052,3 +1052,75 @@ def test_pfbch_synthesis_fused_and_streams(L, orc, M, m, nfr):
     for s in range(n_streams):
         w = orc.Firpfbch(orc.SYNTHESIZER, M, kaiser=(m, 60.0)).execute_frames(xs[s])
         assert np.abs(out[s].reshape(nfr, M) - w).max() / np.abs(w).max() < 1e-5
+
+
+# ------------------------------------------------------------------ randomized shapes (the 8f objects)
+def test_randomized_shapes_vs_oracle(L, orc):
+    """seeded random shapes and block cuts for the rate changers, fftfilt and ofdmframegen against the oracle: sizes
+    around the thresholds where the tiled / fused kernels take over, odd lengths, one-unit blocks"""
+    rng = np.random.default_rng(20261023)
+
+    def cuts(n_units, k=3):
+        c = sorted(set([0, n_units] + [int(v) for v in rng.integers(0, n_units + 1, k)]))
+        return list(zip(c[:-1], c[1:]))
+
+    for _ in range(12):
+        M, m = int(rng.integers(2, 40)), int(rng.integers(1, 8))
+        n = int(rng.choice([1, 7, 250, 1100, 9000]))
+        h = rng.standard_normal(int(rng.integers(M, 2 * M * m + 2))).astype(np.float32)
+        x = orc.synth_input(n * M, seed=int(rng.integers(1 << 30)))
+        q, o = L.firdecim_crcf.create(M, h), orc.Firdecim(M, h=h)
+        got = np.concatenate([q.execute_block(x[a * M:b * M]) for a, b in cuts(n)])
+        want = o.execute_block(x)
+        assert np.abs(got - want).max() < 5e-6 * max(1.0, np.abs(want).max()), ("firdecim", M, len(h), n)
+        q, o = L.firinterp_crcf.create(M, h), orc.Firinterp(M, h=h)
+        got = np.concatenate([q.execute_block(x[a:b]) for a, b in cuts(n)])
+        want = o.execute_block(x[:n])
+        assert np.abs(got - want).max() < 5e-6 * max(1.0, np.abs(want).max()), ("firinterp", M, len(h), n)
+    for _ in range(8):
+        m, f0 = int(rng.integers(2, 20)), float(rng.uniform(-0.5, 0.5))
+        n = int(rng.choice([2, 30, 8190, 8194, 40000]))
+        x = orc.synth_input(2 * n, seed=int(rng.integers(1 << 30)))
+        for mode in ("decim", "interp", "analyzer", "synthesizer"):
+            q, o = L.resamp2_crcf(m, f0, 60.0), orc.Resamp2(m, f0, 60.0)
+            per = 1 if mode == "interp" else 2
+            got = np.concatenate([getattr(q, mode + "_execute_block")(x[a * per:b * per]) for a, b in cuts(n)])
+            want = getattr(o, mode + "_execute")(x[:n * per])
+            assert np.abs(got - want).max() < 3e-6, ("resamp2", mode, m, n)
+    for _ in range(6):
+        S, typ = int(rng.integers(1, 7)), int(rng.integers(0, 2))
+        fc, As = float(rng.uniform(0.05, 0.45)), float(rng.choice([40.0, 60.0, 90.0]))
+        n = int(rng.choice([1, 5, 300, 5000]))
+        q, o = L.msresamp2_crcf(typ, S, fc, 0.0, As), orc.Msresamp2(typ, S, fc, 0.0, As)
+        unit = 1 if typ == L.LIQUID_RESAMP_INTERP else (1 << S)
+        x = orc.synth_input(n * unit, seed=int(rng.integers(1 << 30)))
+        got = np.concatenate([q.execute_block(x[a * unit:b * unit]) for a, b in cuts(n)])
+        want = o.execute_block(x)
+        assert np.abs(got - want).max() < 5e-6 * max(1.0, np.abs(want).max()), ("msresamp2", typ, S, n)
+    for _ in range(8):
+        n = int(rng.choice([1, 2, 5, 64, 100, 512, 1000, 4096]))
+        h_len = int(rng.integers(1, n + 2))
+        nb = int(rng.choice([1, 3, 40]))
+        h = rng.standard_normal(h_len).astype(np.float32)
+        x = orc.synth_input(n * nb, seed=int(rng.integers(1 << 30)))
+        q, o = L.fftfilt_crcf(h, n), orc.Fftfilt(h, n)
+        got = np.concatenate([q.execute_block(x[a * n:b * n]) for a, b in cuts(nb, 2)])
+        want = o.execute_blocks(x)
+        assert np.abs(got - want).max() < 6e-6 * max(1.0, np.abs(want).max()), ("fftfilt", h_len, n, nb)
+    for _ in range(8):
+        M = int(rng.choice([8, 12, 16, 50, 64, 128, 2048]))
+        cp = int(rng.integers(0, M // 2 + 1))
+        tl = int(rng.integers(0, cp + 1))
+        nsym = int(rng.choice([1, 2, 17, 300]))
+        try:
+            o = orc.Ofdmframegen(M, cp, tl)
+        except Exception:       # (an allocation with fewer than two pilots: the reference rejects it too)
+            continue
+        if not o.h:
+            continue
+        x = orc.synth_input(M * nsym, seed=int(rng.integers(1 << 30)))
+        q = L.ofdmframegen(M, cp, tl)
+        got = np.concatenate([q.write_S0a(), q.write_S0b(), q.write_S1()] + [q.writesymbols(x[a * M:b * M]) for a, b in cuts(nsym, 2)]
+                             + [q.writetail()])
+        want = orc.ofdm_frame(o, x)
+        assert np.abs(got - want).max() < 4e-6 * max(1.0, np.abs(want).max()), ("ofdm", M, cp, tl, nsym)
