@@ -399,6 +399,8 @@ void firfilt_crcf_execute_block_dev(firfilt_crcf _q, const void *_d_x, unsigned 
 /* for i < _n: push _x[i], then _y[i] = execute(_idx[i]) */
 void firpfb_crcf_execute_block(firpfb_crcf _q, liquid_float_complex *_x, const unsigned int *_idx,
                                unsigned int _n, liquid_float_complex *_y);
+void firpfb_crcf_execute_block_dev(firpfb_crcf _q, const void *_d_x, const unsigned int *_d_idx, unsigned long long _n,
+                                   void *_d_y, void *_stream);
 
 /* ---- dotprod_crcf ---- */
 /* _n_vec dot products: vector v starts at _d_x + v*_stride (complex samples) */

@@ -223,6 +223,7 @@ _sig("firpfb_crcf_reset", None, _vp)
 _sig("firpfb_crcf_push", None, _vp, _cf)
 _sig("firpfb_crcf_execute", None, _vp, _u, _cf_p)
 _sig("firpfb_crcf_execute_block", None, _vp, _cf_p, _u_p, _u, _cf_p)
+_sig("firpfb_crcf_execute_block_dev", None, _vp, _vp, _vp, _ull, _vp, _vp)
 _sig("dotprod_crcf_run", None, _f_p, _cf_p, _u, _cf_p)
 _sig("dotprod_crcf_run4", None, _f_p, _cf_p, _u, _cf_p)
 _sig("dotprod_crcf_create", _vp, _f_p, _u)
@@ -1123,6 +1124,9 @@ class firpfb_crcf(_Handle):
         y = np.empty(1, np.complex64)
         lib.firpfb_crcf_execute(self._h, i, y)
         return y[0]
+
+    def execute_block_dev(self, d_x, d_idx, n, d_y, stream=0):
+        lib.firpfb_crcf_execute_block_dev(self._h, d_x, d_idx, n, d_y, stream)
 
     def execute_block(self, x, idx):
         x = _c64(x)

@@ -374,10 +374,60 @@ void launch_dotprod_batch(const float *d_h, unsigned int n, const float2 *d_x, u
     LC_LAUNCH_CHECK();
 }
 
-void launch_firpfb_block(const float2 *d_hist, const float2 *d_x, int H, const float *d_sub, unsigned int sub_len,
-                         const unsigned int *d_idx, float scale, float2 *d_y, unsigned long long n, cudaStream_t st)
+// The throughput form: a CTA stages the samples of 2048 outputs (+ sub_len - 1 of history; 8-byte cp.async) and the
+// whole bank (rows padded to an odd length: the gather by filter index spreads over the banks) in shared memory; one
+// thread per output, same fmaf chain as firpfb_block_kernel (oldest sample first): identical bits.
+constexpr unsigned int kPfbTile = 2048;
+__global__ void __launch_bounds__(kThreads)
+firpfb_tile_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ sub,
+                   unsigned int sub_len, unsigned int n_filters, const unsigned int *__restrict__ idx, float scale,
+                   float2 *__restrict__ y, unsigned long long n)
 {
-    firpfb_block_kernel<<<grid_cap((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(d_hist, d_x, H, d_sub, sub_len, d_idx, scale, d_y, n);
+    extern __shared__ float2 smem_p[];
+    const unsigned int halo = sub_len - 1;
+    const unsigned int row = sub_len | 1;                                // padded row length of the bank
+    float2 *xs = smem_p;                                                 // staged sample q = sample i0 - halo + q
+    float *bank = reinterpret_cast<float *>(xs + ((kPfbTile + halo + 1) & ~1u));
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * kPfbTile;
+    const unsigned int nt = (n - i0 < kPfbTile) ? (unsigned int)(n - i0) : kPfbTile;
+    for (unsigned int e = threadIdx.x; e < n_filters * sub_len; e += blockDim.x)
+        bank[(e / sub_len) * row + e % sub_len] = __ldg(sub + e);
+    for (unsigned int q = threadIdx.x; q < nt + halo; q += blockDim.x) {
+        const long long s = (long long)i0 - (long long)halo + q;
+        if (s >= 0) {
+            const unsigned int dst = (unsigned int)__cvta_generic_to_shared(xs + q);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(x + s) : "memory");
+        } else {
+            xs[q] = __ldg(hist + (H + s));
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (unsigned int t = threadIdx.x; t < nt; t += blockDim.x) {
+        const float *hf = bank + __ldg(idx + i0 + t) * row;
+        float re = 0.f, im = 0.f;
+        for (unsigned int k = 0; k < sub_len; k++) {
+            const float2 s = xs[t + k];
+            const float c = hf[k];
+            re = fmaf(c, s.x, re);
+            im = fmaf(c, s.y, im);
+        }
+        y[i0 + t] = make_float2(re * scale, im * scale);
+    }
+}
+
+void launch_firpfb_block(const float2 *d_hist, const float2 *d_x, int H, const float *d_sub, unsigned int sub_len,
+                         const unsigned int *d_idx, float scale, float2 *d_y, unsigned long long n, cudaStream_t st,
+                         unsigned int n_filters)
+{
+    const size_t smem = sizeof(float2) * ((kPfbTile + sub_len) & ~1u) + sizeof(float) * (size_t)n_filters * (sub_len | 1);
+    const unsigned long long tiles = (n + kPfbTile - 1) / kPfbTile;
+    if (n_filters && smem <= 48 * 1024 && n >= 4ull * kPfbTile && tiles < (1ull << 31) && !getenv("LIQUID_CUDA_FIRPFB_SIMPLE")) {
+        firpfb_tile_kernel<<<(unsigned int)tiles, kThreads, smem, st>>>(d_hist, d_x, H, d_sub, sub_len, n_filters, d_idx, scale, d_y, n);
+    } else {
+        firpfb_block_kernel<<<grid_cap((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(d_hist, d_x, H, d_sub, sub_len, d_idx, scale, d_y, n);
+    }
     LC_LAUNCH_CHECK();
 }
 

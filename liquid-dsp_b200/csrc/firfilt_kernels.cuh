@@ -23,8 +23,10 @@ void launch_dotprod_batch(const float *d_h, unsigned int n, const float2 *d_x, u
                           unsigned long long stride, float2 *d_y, cudaStream_t st);
 
 // firpfb: for i < n: window <- x[i]; y[i] = scale * sum_k sub[idx[i]][k] * window[k]
+// n_filters: rows of d_sub (0 = unknown: the bank is not staged in shared memory)
 void launch_firpfb_block(const float2 *d_hist, const float2 *d_x, int H, const float *d_sub, unsigned int sub_len,
-                         const unsigned int *d_idx, float scale, float2 *d_y, unsigned long long n, cudaStream_t st);
+                         const unsigned int *d_idx, float scale, float2 *d_y, unsigned long long n, cudaStream_t st,
+                         unsigned int n_filters = 0);
 
 }  // namespace firfilt
 }  // namespace lc

@@ -133,10 +133,22 @@ void firpfb_crcf_execute_block(firpfb_crcf _q, liquid_float_complex *_x, const u
     unsigned int *di = (unsigned int *)_q->didx.get(sizeof(unsigned int) * _n);
     LC_CUDA_CHECK(cudaMemcpyAsync(dx, _x, sizeof(float2) * _n, cudaMemcpyHostToDevice, _q->stream));
     LC_CUDA_CHECK(cudaMemcpyAsync(di, _idx, sizeof(unsigned int) * _n, cudaMemcpyHostToDevice, _q->stream));
-    lc::firfilt::launch_firpfb_block(_q->d_hist, dx, (int)_q->sub_len, _q->d_sub, _q->sub_len, di, _q->scale, dy, _n, _q->stream);
+    lc::firfilt::launch_firpfb_block(_q->d_hist, dx, (int)_q->sub_len, _q->d_sub, _q->sub_len, di, _q->scale, dy, _n, _q->stream, _q->M);
     lc::roll_history(_q->d_hist, _q->sub_len, _q->hist_tmp, dx, _n, _q->stream);
     LC_CUDA_CHECK(cudaMemcpyAsync(_y, dy, sizeof(float2) * _n, cudaMemcpyDeviceToHost, _q->stream));
     LC_CUDA_CHECK(cudaStreamSynchronize(_q->stream));
+}
+
+// device-pointer form: _d_x [n] samples, _d_idx [n] filter indices (each < M: not checked here), _d_y [n] outputs;
+// the window is carried in stream order
+void firpfb_crcf_execute_block_dev(firpfb_crcf _q, const void *_d_x, const unsigned int *_d_idx, unsigned long long _n,
+                                   void *_d_y, void *_stream)
+{
+    if (_n == 0) return;
+    cudaStream_t st = lc::as_stream(_stream);
+    lc::firfilt::launch_firpfb_block(_q->d_hist, (const float2 *)_d_x, (int)_q->sub_len, _q->d_sub, _q->sub_len, _d_idx, _q->scale,
+                                     (float2 *)_d_y, _n, st, _q->M);
+    lc::roll_history(_q->d_hist, _q->sub_len, _q->hist_tmp, (const float2 *)_d_x, _n, st);
 }
 
 void firpfb_crcf_push(firpfb_crcf _q, liquid_float_complex _x)

@@ -447,6 +447,29 @@ def test_firpfb_reference_kat_and_oracle(L, orc, kat):
     assert np.abs(got - want).max() < 2e-6
 
 
+@pytest.mark.parametrize("M,m", [(8, 4), (32, 6), (33, 3), (64, 11)])
+def test_firpfb_long_blocks_tiled_kernel(L, orc, monkeypatch, M, m):
+    """long blocks take the shared-memory tiled kernel: bit for bit against the plain kernel (arbitrary filter index per
+    sample, state carried over an awkward cut), and the head of the stream against the oracle run sample by sample"""
+    n = 40000
+    x = orc.synth_input(n, seed=0xE0 + M)
+    idx = (np.random.default_rng(M).integers(0, M, n)).astype(np.uint32)
+    outs = {}
+    for plain in (False, True):
+        if plain:
+            monkeypatch.setenv("LIQUID_CUDA_FIRPFB_SIMPLE", "1")
+        else:
+            monkeypatch.delenv("LIQUID_CUDA_FIRPFB_SIMPLE", raising=False)
+        q = L.firpfb_crcf.create_kaiser(M, m, 0.4, 60.0)
+        outs[plain] = np.concatenate([q.execute_block(x[:17001], idx[:17001]), q.execute_block(x[17001:], idx[17001:])])
+    monkeypatch.delenv("LIQUID_CUDA_FIRPFB_SIMPLE", raising=False)
+    assert np.array_equal(outs[False].view(np.uint32), outs[True].view(np.uint32))
+    qo = orc.Firpfb(M, kaiser=(m, 0.4, 60.0))
+    for i in range(1500):
+        qo.push(x[i])
+        assert abs(outs[False][i] - qo.execute(int(idx[i]))) < 2e-6
+
+
 def test_fft_reference_golden_vectors(L, kat):
     """fft_runtest.c:30-66: forward vs golden, inverse round trip, every size the reference ships"""
     for n, case in kat["fft"]["cases"].items():

@@ -3,7 +3,7 @@
 measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
 events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
 
-  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [f4] [f5] [f6] [s] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
+  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [f4] [f5] [f6] [s] [p] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
 """
 import argparse
 import json
@@ -242,6 +242,19 @@ def main():
                    {"note": "throughput in subcarrier values/s; algorithmic bytes 8 in + 8 (M + cp)/M out each"})
             del y
         del x
+    if "p" in args.configs:
+        # a13: firpfb_crcf (M = 32 filters, m = 6: 12 taps each), a new sample and an arbitrary filter index per output
+        # (the symbol-timing use), 2^28 samples
+        n_s = 1 << 28
+        x = torch.empty(2 * n_s, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * n_s, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr(), n_s, stream=st.cuda_stream)
+        idx = (torch.arange(n_s, device=dev, dtype=torch.int64) * 7 % 32).to(torch.int32)
+        q = L.firpfb_crcf.create_kaiser(32, 6, 0.5, 60.0)
+        ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), idx.data_ptr(), n_s, y.data_ptr(), st.cuda_stream))
+        report("p: firpfb_crcf M=32 m=6 (12 taps per output, filter index per sample), 2^28 samples", n_s, 20, ms, ln,
+               {"note": "algorithmic bytes 8 in + 4 index + 8 out per sample"})
+        del x, y, idx
     if "fft" in args.configs:
         # a11: the batched complex FFT on its own (fft_execute_batch_dev), 2^28 points per step, out of place
         import numpy as np
