@@ -3,7 +3,7 @@
 measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
 events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
 
-  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [f4] [f5] [f6] [s] [p] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
+  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [f4] [f5] [f6] [s] [p] [d] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
 """
 import argparse
 import json
@@ -255,6 +255,19 @@ def main():
         report("p: firpfb_crcf M=32 m=6 (12 taps per output, filter index per sample), 2^28 samples", n_s, 20, ms, ln,
                {"note": "algorithmic bytes 8 in + 4 index + 8 out per sample"})
         del x, y, idx
+    if "d" in args.configs:
+        # a8: dotprod_crcf as an object: 2^22 / 2^18 independent dot products of 64 / 1024 taps over disjoint vectors
+        import numpy as np
+        n_s = 1 << 28
+        x = torch.empty(2 * n_s, dtype=torch.float32, device=dev)
+        L.synth_input_dev(x.data_ptr(), n_s, stream=st.cuda_stream)
+        for nt in (64, 1024):
+            y = torch.empty(2 * (n_s // nt), dtype=torch.float32, device=dev)
+            q = L.dotprod_crcf(L.liquid_firdes_kaiser(nt, 0.2, 60.0, 0.0))
+            ms, ln = timed(lambda: q.execute_batch_dev(x.data_ptr(), n_s // nt, nt, y.data_ptr(), st.cuda_stream))
+            report("d: dotprod_crcf_execute_batch_dev %d taps, %d vectors (2^28 samples)" % (nt, n_s // nt), n_s, 8 + 8 / nt, ms, ln)
+            del y
+        del x
     if "fft" in args.configs:
         # a11: the batched complex FFT on its own (fft_execute_batch_dev), 2^28 points per step, out of place
         import numpy as np
