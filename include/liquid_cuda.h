@@ -48,7 +48,7 @@ typedef struct { float real; float imag; } liquid_float_complex;
 /* enum liquid_firfilt_type, liquid.h:1414-1435 (values only; prototypes marked * are designed here) */
 #define LIQUID_FIRFILT_UNKNOWN   0
 #define LIQUID_FIRFILT_KAISER    1  /* * */
-#define LIQUID_FIRFILT_PM        2
+#define LIQUID_FIRFILT_PM        2  /* * */
 #define LIQUID_FIRFILT_RCOS      3
 #define LIQUID_FIRFILT_FEXP      4
 #define LIQUID_FIRFILT_FSECH     5
@@ -56,7 +56,7 @@ typedef struct { float real; float imag; } liquid_float_complex;
 #define LIQUID_FIRFILT_ARKAISER  7  /* * */
 #define LIQUID_FIRFILT_RKAISER   8  /* * */
 #define LIQUID_FIRFILT_RRC       9  /* * */
-#define LIQUID_FIRFILT_hM3       10
+#define LIQUID_FIRFILT_hM3       10 /* * */
 #define LIQUID_FIRFILT_GMSKTX    11
 #define LIQUID_FIRFILT_GMSKRX    12
 #define LIQUID_FIRFILT_RFEXP     13
@@ -74,6 +74,17 @@ void  liquid_filter_isi(float *_h, unsigned int _k, unsigned int _m, float *_rms
 void  liquid_firdes_arkaiser(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
 void  liquid_firdes_rkaiser(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
 void  liquid_firdes_prototype(int _type, unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+/* Parks-McClellan equiripple design (band-pass / even-symmetric filters) and the harris-Moerder root-Nyquist
+ * prototype built on it: liquid.h:1482-1512, :1592 -> src/filter/src/firdespm.c:115-748, hM3.c:49-126 (host code) */
+#define LIQUID_FIRDESPM_BANDPASS        0   /* liquid_firdespm_btype */
+#define LIQUID_FIRDESPM_DIFFERENTIATOR  1
+#define LIQUID_FIRDESPM_HILBERT         2
+#define LIQUID_FIRDESPM_FLATWEIGHT      0   /* liquid_firdespm_wtype */
+#define LIQUID_FIRDESPM_EXPWEIGHT       1
+#define LIQUID_FIRDESPM_LINWEIGHT       2
+void  firdespm_run(unsigned int _h_len, unsigned int _num_bands, float *_bands, float *_des, float *_weights,
+                   int *_wtype, int _btype, float *_h);
+void  liquid_firdes_hM3(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
 
 /* ---- firdecim_crcf / firinterp_crcf: liquid.h:2665-2722, :2498-2556 -> src/filter/src/firdecim.c:46-223,
  *      firinterp.c:43-217 (instantiated by filter_crcf.c).  SURVEY.md 8(f) item 3. */

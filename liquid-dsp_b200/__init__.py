@@ -59,6 +59,8 @@ _sig("estimate_req_filter_As", _fl, _fl, _u)
 _sig("liquid_filter_isi", None, _f_p, _u, _u, C.POINTER(C.c_float), C.POINTER(C.c_float))
 _sig("liquid_firdes_arkaiser", None, _u, _u, _fl, _fl, _f_p)
 _sig("liquid_firdes_rkaiser", None, _u, _u, _fl, _fl, _f_p)
+_sig("liquid_firdes_hM3", None, _u, _u, _fl, _fl, _f_p)
+_sig("firdespm_run", None, _u, _u, _f_p, _f_p, _f_p, C.POINTER(C.c_int), _i, _f_p)
 _sig("liquid_firdes_prototype", None, _i, _u, _u, _fl, _fl, _f_p)
 _sig("firpfbch2_crcf_create", _vp, _i, _u, _u, _f_p)
 _sig("firpfbch2_crcf_create_kaiser", _vp, _i, _u, _u, _fl)
@@ -314,6 +316,28 @@ def liquid_firdes_arkaiser(k, m, beta, dt=0.0):
 def liquid_firdes_rkaiser(k, m, beta, dt=0.0):
     h = np.empty(2 * k * m + 1, np.float32)
     lib.liquid_firdes_rkaiser(k, m, beta, dt, h)
+    return h
+
+
+def liquid_firdes_hM3(k, m, beta, dt=0.0):
+    h = np.empty(2 * k * m + 1, np.float32)
+    lib.liquid_firdes_hM3(k, m, beta, dt, h)
+    return h
+
+
+LIQUID_FIRDESPM_BANDPASS, LIQUID_FIRDESPM_DIFFERENTIATOR, LIQUID_FIRDESPM_HILBERT = 0, 1, 2
+LIQUID_FIRDESPM_FLATWEIGHT, LIQUID_FIRDESPM_EXPWEIGHT, LIQUID_FIRDESPM_LINWEIGHT = 0, 1, 2
+LIQUID_FIRFILT_PM = 2
+
+
+def firdespm_run(h_len, bands, des, weights=None, wtype=None, btype=LIQUID_FIRDESPM_BANDPASS):
+    """Parks-McClellan design (liquid.h:1504): bands = [f0, f1] per band in [0, 0.5], des / weights / wtype per band"""
+    bands, des = _f32(bands), _f32(des)
+    nb = des.size
+    w = np.ones(nb, np.float32) if weights is None else _f32(weights)
+    wt = np.zeros(nb, np.int32) if wtype is None else np.ascontiguousarray(wtype, np.int32)
+    h = np.empty(h_len, np.float32)
+    lib.firdespm_run(h_len, nb, bands, des, w, wt.ctypes.data_as(C.POINTER(C.c_int)), btype, h)
     return h
 
 

@@ -306,6 +306,231 @@ extern "C" void liquid_firdes_rrcos(unsigned int _k, unsigned int _m, float _bet
     }
 }
 
+namespace lc {
+
+// ---- Parks-McClellan equiripple design (firdespm.c) and the harris-Moerder prototype built on it (hM3.c) ---------
+// Band-pass (even-symmetric) filters, the only kind firdespm_compute_taps() of the reference produces.  All of it in
+// double precision with the reference's operation order: frequency grid of 20 points per approximating function on
+// the bands (firdespm.c:214-223, :346-455), Remez exchange with a barycentric Lagrange interpolant on the r + 1
+// extremal points (:456-497, poly.lagrange.c:104-151), extremal search keeping alternating signs and dropping the
+// smallest surplus extrema (:518-659), at most 40 rounds or until the extremal errors agree to 1e-3 (:663-686), then
+// the taps from the interpolant sampled on h_len points (:689-748).
+namespace {
+struct PmDesign {
+    unsigned int h_len, s, n, r, grid = 0;
+    std::vector<double> F, D, W, E, x, alpha, c;
+    std::vector<unsigned int> iext;
+    double rho = 0.0;
+    unsigned int exchanges = 0;
+
+    static double lagrange_val(const std::vector<double> &x, const std::vector<double> &y, const std::vector<double> &w, double x0)
+    {
+        double t0 = 0.0, t1 = 0.0;
+        const float tol = 1e-6f;
+        for (size_t j = 0; j < x.size(); j++) {
+            const double g = x0 - x[j];
+            if (fabs(g) < tol) return y[j];
+            t0 += w[j] * y[j] / g;
+            t1 += w[j] / g;
+        }
+        return t0 / t1;
+    }
+
+    void interpolant()
+    {
+        for (unsigned int i = 0; i <= r; i++) x[i] = cos(2 * M_PI * F[iext[i]]);
+        for (unsigned int j = 0; j <= r; j++) {               // barycentric weights, normalised by the first
+            double w = 1.;
+            for (unsigned int k = 0; k <= r; k++)
+                if (j != k) w *= (x[j] - x[k]);
+            alpha[j] = 1. / w;
+        }
+        const double w0 = alpha[0];
+        for (unsigned int j = 0; j <= r; j++) alpha[j] /= w0;
+        double t0 = 0.0, t1 = 0.0;
+        for (unsigned int i = 0; i <= r; i++) {
+            t0 += alpha[i] * D[iext[i]];
+            t1 += alpha[i] / W[iext[i]] * (i % 2 ? -1.0 : 1.0);
+        }
+        rho = t0 / t1;
+        for (unsigned int i = 0; i <= r; i++) c[i] = D[iext[i]] - (i % 2 ? -1 : 1) * rho / W[iext[i]];
+    }
+
+    void errors()
+    {
+        for (unsigned int i = 0; i < grid; i++) {
+            const double xf = cos(2 * M_PI * F[i]);
+            E[i] = W[i] * (D[i] - lagrange_val(x, c, alpha, xf));
+        }
+    }
+
+    void exchange(unsigned int num_bands)
+    {
+        std::vector<unsigned int> found;
+        found.reserve(2 * r + 2 * num_bands);
+        found.push_back(0);                                    // both ends are always candidates
+        for (unsigned int i = 1; i + 1 < grid; i++)
+            if ((E[i] >= 0.0 && E[i - 1] <= E[i] && E[i + 1] <= E[i]) || (E[i] < 0.0 && E[i - 1] >= E[i] && E[i + 1] >= E[i]))
+                found.push_back(i);
+        found.push_back(grid - 1);
+        if (found.size() < r + 1) {
+            fprintf(stderr, "warning: firdespm_iext_search(), too few extrema found (expected %u, found %u); exiting prematurely\n",
+                    r + 1, (unsigned int)found.size());
+            exchanges = 0;
+            return;
+        }
+        size_t extra = found.size() - r - 1;
+        while (extra) {
+            unsigned int sign = E[found[0]] > 0.0;
+            size_t imin = 0;
+            bool alternating = true;
+            for (size_t i = 1; i < found.size(); i++) {
+                if (fabs(E[found[i]]) < fabs(E[found[imin]])) imin = i;
+                if (sign && E[found[i]] < 0.0) sign = 0;
+                else if (!sign && E[found[i]] >= 0.0) sign = 1;
+                else {                                         // two neighbours of one sign: drop the smaller
+                    imin = fabs(E[found[i]]) < fabs(E[found[i - 1]]) ? i : i - 1;
+                    alternating = false;
+                    break;
+                }
+            }
+            if (alternating && extra == 1) imin = fabs(E[found.front()]) < fabs(E[found.back()]) ? 0 : found.size() - 1;
+            found.erase(found.begin() + (long)imin);
+            extra--;
+        }
+        exchanges = 0;
+        for (unsigned int i = 0; i <= r; i++) exchanges += iext[i] == found[i] ? 0 : 1;
+        for (unsigned int i = 0; i <= r; i++) iext[i] = found[i];
+    }
+
+    bool converged() const
+    {
+        if (exchanges == 0) return true;
+        const double tol = 1e-3f;
+        double emin = 0.0, emax = 0.0;
+        for (unsigned int i = 0; i <= r; i++) {
+            const double e = fabs(E[iext[i]]);
+            if (i == 0 || e < emin) emin = e;
+            if (i == 0 || e > emax) emax = e;
+        }
+        return (emax - emin) / emax < tol;
+    }
+};
+}  // namespace
+
+// 0 ok; 1 invalid bands; 2 invalid weights; 3 no bands; 4 invalid weight type; 5 band type without a tap formula
+int firdespm_bandpass(unsigned int h_len, unsigned int num_bands, const float *bands, const float *des, const float *weights,
+                      const int *wtype, float *h)
+{
+    bool bands_ok = true, weights_ok = true;
+    for (unsigned int i = 0; i < 2 * num_bands; i++) bands_ok &= bands[i] >= 0.0 && bands[i] <= 0.5;
+    for (unsigned int i = 1; i < 2 * num_bands; i++) bands_ok &= bands[i] >= bands[i - 1];
+    for (unsigned int i = 0; i < num_bands; i++) weights_ok &= (weights == nullptr || weights[i] > 0);
+    if (!bands_ok) return 1;
+    if (!weights_ok) return 2;
+    if (num_bands == 0) return 3;
+    PmDesign q;
+    q.h_len = h_len;
+    q.s = h_len % 2;
+    q.n = (h_len - q.s) / 2;
+    q.r = q.n + q.s;
+    const unsigned int density = 20;
+    const double df = 0.5 / (density * q.r);
+    // the grid: every band sampled at df, its last point forced onto the upper edge
+    for (unsigned int b = 0; b < num_bands; b++) {
+        const double f0 = bands[2 * b], f1 = bands[2 * b + 1];
+        unsigned int pts = (unsigned int)((f1 - f0) / df + 0.5);
+        if (pts < 1) pts = 1;
+        for (unsigned int j = 0; j < pts; j++) {
+            double fw = 1.0f;                                  // (a double in the reference too: firdespm.c:381)
+            const int wt = wtype ? wtype[b] : LIQUID_FIRDESPM_FLATWEIGHT;
+            if (wt == LIQUID_FIRDESPM_FLATWEIGHT) fw = 1.0f;
+            else if (wt == LIQUID_FIRDESPM_EXPWEIGHT) fw = expf((float)(2.0f * j * df));
+            else if (wt == LIQUID_FIRDESPM_LINWEIGHT) fw = 1.0f + 2.7f * j * df;
+            else return 4;
+            q.F.push_back(f0 + j * df);
+            q.D.push_back((double)des[b]);
+            q.W.push_back((double)(weights ? weights[b] : 1.0f) * fw);
+        }
+        q.F.back() = f1;
+    }
+    q.grid = (unsigned int)q.F.size();
+    if (q.s == 0)                                               // even length: the cos(pi f) factor moves into D and W
+        for (unsigned int i = 0; i < q.grid; i++) {
+            q.D[i] /= cos(M_PI * q.F[i]);
+            q.W[i] *= cos(M_PI * q.F[i]);
+        }
+    q.E.assign(q.grid, 0.0);
+    q.x.assign(q.r + 1, 0.0);
+    q.alpha.assign(q.r + 1, 0.0);
+    q.c.assign(q.r + 1, 0.0);
+    q.iext.resize(q.r + 1);
+    for (unsigned int i = 0; i <= q.r; i++) q.iext[i] = (i * (q.grid - 1)) / q.r;
+    for (unsigned int it = 0; it < 40; it++) {
+        q.interpolant();
+        q.errors();
+        q.exchange(num_bands);
+        if (q.converged()) break;
+    }
+    q.interpolant();
+    const unsigned int p = q.r - q.s + 1;
+    std::vector<double> G(p);
+    for (unsigned int i = 0; i < p; i++) {
+        const double f = (double)i / (double)h_len;
+        const double cf = PmDesign::lagrange_val(q.x, q.c, q.alpha, cos(2 * M_PI * f));
+        const double g = q.s == 1 ? 1.0 : cos(M_PI * i / h_len);
+        G[i] = cf * g;
+    }
+    for (unsigned int i = 0; i < h_len; i++) {
+        double v = G[0];
+        const double f = ((double)i - (double)(p - 1) + 0.5 * (1 - q.s)) / (double)h_len;
+        for (unsigned int j = 1; j < q.r; j++) v += 2.0 * G[j] * cos(2 * M_PI * f * j);
+        h[i] = (float)(v / (double)h_len);
+    }
+    return 0;
+}
+
+// hM3.c:49-126: three-band equiripple design (pass band to fc(1-beta), 1/sqrt(2) at fc, stop band from fc(1+beta)
+// with exponential weight), the pass-band edge walked towards fc in 100 steps while the inter-symbol interference
+// keeps falling; unit energy per symbol.  0 ok, else message id
+int firdes_hM3(unsigned int k, unsigned int m, float beta, float dt, float *h_out)
+{
+    (void)dt;
+    if (k < 2) return 1;
+    if (m < 1) return 2;
+    if (beta < 0.0f || beta > 1.0f) return 3;
+    const unsigned int n = 2 * k * m + 1;
+    const float fc = (float)(1.0 / (float)(2 * k));
+    float fp = (float)(fc * (1.0 - beta));
+    const float fs = (float)(fc * (1.0 + beta));
+    float bands[6] = {0.0f, fp, fc, fc, fs, 0.5f};
+    const float des[3] = {1.0f, 1.0f / sqrtf(2.0f), 0.0f};
+    const float weights[3] = {1.0f, 1.0f, 1.0f};
+    const int wtype[3] = {LIQUID_FIRDESPM_FLATWEIGHT, LIQUID_FIRDESPM_FLATWEIGHT, LIQUID_FIRDESPM_EXPWEIGHT};
+    std::vector<float> h(n);
+    firdespm_bandpass(n, 3, bands, des, weights, wtype, h.data());
+    std::copy(h.begin(), h.end(), h_out);
+    float isi_rms, isi_max;
+    filter_isi(h.data(), k, m, &isi_rms, &isi_max);
+    float isi_rms_min = isi_rms;
+    const unsigned int pmax = 100;
+    for (unsigned int p = 0; p < pmax; p++) {
+        fp = (float)(fc * (1.0 - beta * p / (float)pmax));
+        bands[1] = fp;
+        firdespm_bandpass(n, 3, bands, des, weights, wtype, h.data());
+        filter_isi(h.data(), k, m, &isi_rms, &isi_max);
+        if (isi_rms > isi_rms_min) break;
+        isi_rms_min = isi_rms;
+        std::copy(h.begin(), h.end(), h_out);
+    }
+    float e2 = 0.0f;
+    for (unsigned int i = 0; i < n; i++) e2 += h_out[i] * h_out[i];
+    for (unsigned int i = 0; i < n; i++) h_out[i] *= sqrtf(k / e2);
+    return 0;
+}
+
+}  // namespace lc
+
 namespace {
 void rnyquist_fatal(const char *fn, int rc)
 {
@@ -347,6 +572,33 @@ extern "C" void liquid_firdes_rkaiser(unsigned int _k, unsigned int _m, float _b
 // (root-)Nyquist prototype of 2km+1 taps by liquid_firfilt_type           liquid.h:1444, firdes.c:290-370
 // Provided: KAISER, ARKAISER, RKAISER, RRC.  The Parks-McClellan based ones (PM, hM3: firdespm.c) and the
 // rcos / fexp / fsech / farcsech / GMSK families belong to filter-design subsystems outside this library.
+extern "C" void firdespm_run(unsigned int _h_len, unsigned int _num_bands, float *_bands, float *_des, float *_weights,
+                             int *_wtype, int _btype, float *_h)
+{
+    if (_btype != LIQUID_FIRDESPM_BANDPASS) {
+        // (the reference only warns and leaves _h untouched for these: firdespm.c:737-743)
+        fprintf(stderr, "warning: firdespm_compute_taps(), filter configuration not yet supported\n");
+        return;
+    }
+    switch (lc::firdespm_bandpass(_h_len, _num_bands, _bands, _des, _weights, _wtype, _h)) {
+    case 0: return;
+    case 1: lc::fatal("firdespm_create", "invalid bands");
+    case 2: lc::fatal("firdespm_create", "invalid weights (must be positive)");
+    case 3: lc::fatal("firdespm_create", "number of bands must be > 0");
+    default: lc::fatal("firdespm_init_grid", "invalid weighting specifyer");
+    }
+}
+
+extern "C" void liquid_firdes_hM3(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h)
+{
+    switch (lc::firdes_hM3(_k, _m, _beta, _dt, _h)) {
+    case 0: return;
+    case 1: lc::fatal("liquid_firdes_hM3", "k must be greater than 1");
+    case 2: lc::fatal("liquid_firdes_hM3", "m must be greater than 0");
+    default: lc::fatal("liquid_firdes_hM3", "beta must be in [0,1]");
+    }
+}
+
 extern "C" void liquid_firdes_prototype(int _type, unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h)
 {
     const unsigned int h_len = 2 * _k * _m + 1;
@@ -360,19 +612,28 @@ extern "C" void liquid_firdes_prototype(int _type, unsigned int _k, unsigned int
     case LIQUID_FIRFILT_ARKAISER: liquid_firdes_arkaiser(_k, _m, _beta, _dt, _h); return;
     case LIQUID_FIRFILT_RKAISER: liquid_firdes_rkaiser(_k, _m, _beta, _dt, _h); return;
     case LIQUID_FIRFILT_RRC: liquid_firdes_rrcos(_k, _m, _beta, _dt, _h); return;
-    case LIQUID_FIRFILT_PM:
+    case LIQUID_FIRFILT_hM3: liquid_firdes_hM3(_k, _m, _beta, _dt, _h); return;
+    case LIQUID_FIRFILT_PM: {
+        // firdes.c:303-323: three bands around the cut-off, k / k/2 / 0, flat weights (the timing offset is ignored)
+        const float fc = 0.5f / (float)_k, df = _beta / (float)_k;
+        float bands[6] = {0.0f, fc - 0.5f * df, fc, fc, fc + 0.5f * df, 0.5f};
+        float des[3] = {(float)_k, 0.5f * _k, 0.0f};
+        float weights[3] = {1.0f, 1.0f, 1.0f};
+        int wtype[3] = {LIQUID_FIRDESPM_FLATWEIGHT, LIQUID_FIRDESPM_FLATWEIGHT, LIQUID_FIRDESPM_FLATWEIGHT};
+        firdespm_run(h_len, 3, bands, des, weights, wtype, LIQUID_FIRDESPM_BANDPASS, _h);
+        return;
+    }
     case LIQUID_FIRFILT_RCOS:
     case LIQUID_FIRFILT_FEXP:
     case LIQUID_FIRFILT_FSECH:
     case LIQUID_FIRFILT_FARCSECH:
-    case LIQUID_FIRFILT_hM3:
     case LIQUID_FIRFILT_GMSKTX:
     case LIQUID_FIRFILT_GMSKRX:
     case LIQUID_FIRFILT_RFEXP:
     case LIQUID_FIRFILT_RFSECH:
     case LIQUID_FIRFILT_RFARCSECH:
         fprintf(stderr, "error: liquid_firdes_prototype(), filter type '%d' is not provided by liquid_cuda "
-                        "(KAISER, ARKAISER, RKAISER and RRC are; pass external taps to the create() form)\n", _type);
+                        "(KAISER, PM, ARKAISER, RKAISER, RRC and hM3 are; pass external taps to the create() form)\n", _type);
         exit(1);
     default:
         fprintf(stderr, "error: liquid_firdes_prototype(), invalid root-Nyquist filter type '%d'\n", _type);

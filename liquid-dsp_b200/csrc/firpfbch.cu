@@ -118,12 +118,9 @@ firpfbch_crcf firpfbch_crcf_create_rnyquist(int _type, unsigned int _M, unsigned
     case LIQUID_FIRFILT_ARKAISER:
     case LIQUID_FIRFILT_RKAISER:
     case LIQUID_FIRFILT_RRC:
+    case LIQUID_FIRFILT_hM3:
         liquid_firdes_prototype(_ftype, _M, _m, _beta, 0.0f, h.data());
         break;
-    case LIQUID_FIRFILT_hM3:
-        lc::fatal("firpfbch_crcf_create_rnyquist",
-                  "the hM3 prototype needs the Parks-McClellan designer, which liquid_cuda does not carry "
-                  "(use ARKAISER, RKAISER or RRC, or firpfbch_crcf_create with external taps)");
     default:
         fprintf(stderr, "error: firpfbch_%s_create_rnyquist(), unknown/invalid prototype (%d)\n", "crcf", _ftype);
         exit(1);

@@ -115,10 +115,8 @@ firpfbch_cccf firpfbch_cccf_create_rnyquist(int _type, unsigned int _M, unsigned
     } else if (_m == 0) {
         lc::fatal("firpfbch_cccf_create_rnyquist", "invalid filter size (must be greater than 0)");
     }
-    if (_ftype != LIQUID_FIRFILT_ARKAISER && _ftype != LIQUID_FIRFILT_RKAISER && _ftype != LIQUID_FIRFILT_RRC) {
-        if (_ftype == LIQUID_FIRFILT_hM3)
-            lc::fatal("firpfbch_cccf_create_rnyquist",
-                      "the hM3 prototype needs the Parks-McClellan designer, which liquid_cuda does not carry");
+    if (_ftype != LIQUID_FIRFILT_ARKAISER && _ftype != LIQUID_FIRFILT_RKAISER && _ftype != LIQUID_FIRFILT_RRC &&
+        _ftype != LIQUID_FIRFILT_hM3) {
         fprintf(stderr, "error: firpfbch_%s_create_rnyquist(), unknown/invalid prototype (%d)\n", "cccf", _ftype);
         exit(1);
     }

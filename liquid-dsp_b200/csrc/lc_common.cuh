@@ -114,6 +114,9 @@ void filter_isi(const float *h, unsigned int k, unsigned int m, float *rms, floa
 float rkaiser_approximate_rho(unsigned int m, float beta);
 int firdes_arkaiser(unsigned int k, unsigned int m, float beta, float dt, float *h);          // 0 ok, else message id
 int firdes_rkaiser(unsigned int k, unsigned int m, float beta, float dt, float *h, float *rho_out);
+int firdespm_bandpass(unsigned int h_len, unsigned int num_bands, const float *bands, const float *des, const float *weights,
+                      const int *wtype, float *h);                           // firdespm.c (band-pass type); 0 ok
+int firdes_hM3(unsigned int k, unsigned int m, float beta, float dt, float *h);  // hM3.c:49-126; 0 ok, else message id
 
 // ---- batched FFT building block shared by the channelizers and the fft_* API : fft.cu ----
 // d_tw: twiddle table of n entries e^{sign j 2 pi i/n} (only used for non power-of-two n)

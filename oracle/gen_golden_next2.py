@@ -12,6 +12,8 @@ the record of how the fixture was made.
   len_*    estimate_req_filter_len points
   asg_*    asgramcf(nfft) after a write of a tone plus noise: the character string and the peak (default and custom scale)
   ofdm_*   ofdmframegen(M, cp_len, taper_len, allocation): a whole frame S0a | S0b | S1 | data symbols | tail
+  taps_hM3_* / taps_pm_* / pmrun_* / pfbch_hM3_*   liquid_firdes_hM3, liquid_firdes_prototype(PM), firdespm_run and
+           firpfbch_crcf_create_rnyquist(hM3) outputs
   ff_*     fftfilt_crcf(h, n) over several blocks (random taps / a Kaiser low-pass, with and without set_scale)
 """
 import ctypes as C
@@ -88,6 +90,47 @@ for M, cp, tl, custom, nsym in [(64, 16, 4, False, 9), (64, 16, 0, False, 3), (1
     out[tag + "_args"] = np.array([M, cp, tl, int(custom)], np.int64)
     out[tag + "_x"] = x
     out[tag + "_frame"] = O.ofdm_frame(O.RefOfdmframegen(M, cp, tl, p), x)
+
+# Parks-McClellan designs and the harris-Moerder prototype (8f item 1, the last prototype of create_rnyquist): taps from
+# the reference (both builds agree bit for bit: the designer runs in double precision), and firpfbch_crcf outputs
+# with the hM3 prototype.  (k=3, m=7, beta=0.9 and its like trip an assert inside the reference's own extremal search
+# -- firdespm.c:544 -- and are left out.)
+Rr = O.ref()
+c_f_p2 = np.ctypeslib.ndpointer(np.float32, flags="C")
+Rr.liquid_firdes_hM3.argtypes = [C.c_uint, C.c_uint, C.c_float, C.c_float, c_f_p2]
+Rr.liquid_firdes_prototype.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_float, c_f_p2]
+Rr.firdespm_run.argtypes = [C.c_uint, C.c_uint, c_f_p2, c_f_p2, c_f_p2, C.POINTER(C.c_int), C.c_int, c_f_p2]
+pm_cases = []
+for k, m, beta in [(2, 3, 0.3), (4, 5, 0.5), (8, 3, 0.4), (2, 12, 0.2), (16, 4, 0.35), (3, 7, 0.5), (5, 9, 0.25), (64, 2, 0.5)]:
+    n = 2 * k * m + 1
+    h = np.empty(n, np.float32)
+    Rr.liquid_firdes_hM3(k, m, beta, 0.0, h)
+    out["taps_hM3_k%d_m%d_b%03d" % (k, m, round(beta * 100))] = h.copy()
+    Rr.liquid_firdes_prototype(2, k, m, beta, 0.0, h)                 # LIQUID_FIRFILT_PM
+    out["taps_pm_k%d_m%d_b%03d" % (k, m, round(beta * 100))] = h.copy()
+    pm_cases.append((k, m, beta))
+out["pm_cases"] = np.array(pm_cases, np.float64)
+# firdespm_run on its own: low-pass with weights, even length, exponential / linear weights, four bands
+for tag, h_len, bands, des, wts, wtype in [
+        ("lp51", 51, [0.0, 0.2, 0.25, 0.5], [1.0, 0.0], [1.0, 10.0], [0, 0]),
+        ("lp40", 40, [0.0, 0.1, 0.15, 0.5], [1.0, 0.0], [1.0, 1.0], [0, 1]),
+        ("bp77", 77, [0.0, 0.1, 0.15, 0.3, 0.35, 0.5], [0.0, 1.0, 0.0], [4.0, 1.0, 4.0], [0, 0, 2]),
+        ("mb64", 64, [0.0, 0.08, 0.12, 0.2, 0.25, 0.33, 0.38, 0.5], [1.0, 0.0, 0.5, 0.0], [1.0, 2.0, 1.0, 3.0], [0, 0, 0, 0])]:
+    h = np.empty(h_len, np.float32)
+    wt = np.array(wtype, np.int32)
+    Rr.firdespm_run(h_len, len(des), np.array(bands, np.float32), np.array(des, np.float32), np.array(wts, np.float32),
+                    wt.ctypes.data_as(C.POINTER(C.c_int)), 0, h)
+    out["pmrun_%s_bands" % tag] = np.array(bands, np.float32)
+    out["pmrun_%s_des" % tag] = np.array(des, np.float32)
+    out["pmrun_%s_weights" % tag] = np.array(wts, np.float32)
+    out["pmrun_%s_wtype" % tag] = wt
+    out["pmrun_%s_h" % tag] = h
+for M, m, beta in [(8, 3, 0.4), (64, 2, 0.5)]:
+    x = O.synth_input(M * 60, seed=0x5EEDAA00 + M)
+    out["pfbch_hM3_M%d_m%d_x" % (M, m)] = x
+    out["pfbch_hM3_M%d_m%d_args" % (M, m)] = np.array([M, m, beta], np.float64)
+    out["pfbch_hM3_a_M%d_m%d_y" % (M, m)] = O.ref_firpfbch_frames(O.ANALYZER, M, x, rnyquist=(m, beta, 10))
+    out["pfbch_hM3_s_M%d_m%d_y" % (M, m)] = O.ref_firpfbch_frames(O.SYNTHESIZER, M, x, rnyquist=(m, beta, 10))
 
 R = O.ref()
 R.estimate_req_filter_len.restype = C.c_uint

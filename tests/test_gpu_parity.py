@@ -263,6 +263,21 @@ def test_pfbch_synthesis_register_window_vs_oracle(L, orc, monkeypatch, M, m, nf
         assert np.abs(got - o).max() / np.abs(o).max() < 1e-5
 
 
+def test_pfbch_hM3_prototype_vs_reference_fixture(L, refrn2):
+    """firpfbch_crcf / firpfbch_cccf create_rnyquist with the harris-Moerder prototype (Parks-McClellan designs on the
+    host) against the compiled reference's channelizer outputs"""
+    for name in sorted(k for k in refrn2 if k.startswith("pfbch_hM3_") and k.endswith("_args")):
+        M, m, beta = refrn2[name]
+        M, m = int(M), int(m)
+        x = refrn2["pfbch_hM3_M%d_m%d_x" % (M, m)]
+        for kind, typ in (("a", L.LIQUID_ANALYZER), ("s", L.LIQUID_SYNTHESIZER)):
+            want = refrn2["pfbch_hM3_%s_M%d_m%d_y" % (kind, M, m)]
+            got = L.firpfbch_crcf.create_rnyquist(typ, M, m, np.float32(beta), L.LIQUID_FIRFILT_hM3).execute_block(x)
+            assert np.abs(got - want).max() / np.abs(want).max() < 1e-5, (M, kind)
+            got = L.firpfbch_cccf.create_rnyquist(typ, M, m, np.float32(beta), L.LIQUID_FIRFILT_hM3).execute_block(x)
+            assert np.abs(got - want).max() / np.abs(want).max() < 1e-5, (M, kind, "cccf")
+
+
 @pytest.mark.parametrize("M,m", [(4, 3), (16, 4), (10, 2), (64, 5)])
 def test_pfbch_vs_reference_fixtures(L, refout, M, m):
     x = refout["pfbch_a_M%d_m%d_x" % (M, m)]

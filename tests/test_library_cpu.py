@@ -154,3 +154,26 @@ def test_invalid_arguments_follow_the_reference_error_convention(expr, fn):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1, (expr, r.returncode, r.stderr[-300:])
     assert ("error: %s" % fn) in r.stderr, (expr, r.stderr[-300:])
+
+
+def test_host_design_parks_mcclellan_and_hM3_equal_the_reference_bit_for_bit(L, refrn2):
+    """firdespm_run (band-pass type: low-pass with weights, even length, exponential / linear weights, several bands),
+    liquid_firdes_prototype(PM) and liquid_firdes_hM3 (up to 101 equiripple designs each, picked by inter-symbol
+    interference) against taps of the compiled reference: the designer runs in double precision with the reference's
+    operation order, so the float32 taps are identical"""
+    for k, m, beta in refrn2["pm_cases"]:
+        k, m = int(k), int(m)
+        tag = "k%d_m%d_b%03d" % (k, m, round(beta * 100))
+        assert np.array_equal(L.liquid_firdes_hM3(k, m, np.float32(beta)), refrn2["taps_hM3_" + tag]), tag
+        assert np.array_equal(L.liquid_firdes_prototype(L.LIQUID_FIRFILT_hM3, k, m, np.float32(beta)), refrn2["taps_hM3_" + tag]), tag
+        assert np.array_equal(L.liquid_firdes_prototype(L.LIQUID_FIRFILT_PM, k, m, np.float32(beta)), refrn2["taps_pm_" + tag]), tag
+    for name in sorted(k for k in refrn2 if k.startswith("pmrun_") and k.endswith("_h")):
+        tag = name[:-2]
+        want = refrn2[name]
+        got = L.firdespm_run(len(want), refrn2[tag + "_bands"], refrn2[tag + "_des"], refrn2[tag + "_weights"], refrn2[tag + "_wtype"])
+        assert np.array_equal(got, want), tag
+    # what an equiripple low-pass is: pass band near 1, stop band small
+    h = L.firdespm_run(51, [0.0, 0.2, 0.25, 0.5], [1.0, 0.0], [1.0, 10.0])
+    H = np.abs(np.fft.fft(h, 1024))[:513]
+    f = np.arange(513) / 1024.0
+    assert np.abs(H[f <= 0.2] - 1).max() < 0.1 and H[f >= 0.25].max() < 0.01
