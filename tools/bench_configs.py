@@ -213,6 +213,10 @@ def main():
         report("f4d: msresamp2_crcf decimator 4 stages (m=%s), 2^28 input samples" % qm.stage_semilengths(), n,
                8 + 8 / 16, ms, ln, {"note": "algorithmic bytes: input read once, output written once; the "
                                             "intermediate streams of the stage-by-stage form are extra traffic"})
+        qi = L.msresamp2_crcf(L.LIQUID_RESAMP_INTERP, 4, 0.4, 0.0, 60.0)
+        ms, ln = timed(lambda: qi.execute_block_dev(x.data_ptr(), n // 16, y.data_ptr(), st.cuda_stream))
+        report("f4e: msresamp2_crcf interpolator 4 stages, 2^24 input samples (2^28 outputs)", n // 16, 8 + 8 * 16, ms, ln,
+               {"note": "throughput in INPUT samples/s; algorithmic bytes 8 in + 128 out per input sample"})
         del x, y
     if "f5" in args.configs:
         # fftfilt_crcf, 2^28 samples: 1025 taps in blocks of 1024, 257 taps in blocks of 256
