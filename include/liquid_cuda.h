@@ -49,19 +49,19 @@ typedef struct { float real; float imag; } liquid_float_complex;
 #define LIQUID_FIRFILT_UNKNOWN   0
 #define LIQUID_FIRFILT_KAISER    1  /* * */
 #define LIQUID_FIRFILT_PM        2  /* * */
-#define LIQUID_FIRFILT_RCOS      3
-#define LIQUID_FIRFILT_FEXP      4
-#define LIQUID_FIRFILT_FSECH     5
-#define LIQUID_FIRFILT_FARCSECH  6
+#define LIQUID_FIRFILT_RCOS      3  /* * */
+#define LIQUID_FIRFILT_FEXP      4  /* * */
+#define LIQUID_FIRFILT_FSECH     5  /* * */
+#define LIQUID_FIRFILT_FARCSECH  6  /* * */
 #define LIQUID_FIRFILT_ARKAISER  7  /* * */
 #define LIQUID_FIRFILT_RKAISER   8  /* * */
 #define LIQUID_FIRFILT_RRC       9  /* * */
 #define LIQUID_FIRFILT_hM3       10 /* * */
-#define LIQUID_FIRFILT_GMSKTX    11
-#define LIQUID_FIRFILT_GMSKRX    12
-#define LIQUID_FIRFILT_RFEXP     13
-#define LIQUID_FIRFILT_RFSECH    14
-#define LIQUID_FIRFILT_RFARCSECH 15
+#define LIQUID_FIRFILT_GMSKTX    11 /* * */
+#define LIQUID_FIRFILT_GMSKRX    12 /* * */
+#define LIQUID_FIRFILT_RFEXP     13 /* * */
+#define LIQUID_FIRFILT_RFSECH    14 /* * */
+#define LIQUID_FIRFILT_RFARCSECH 15 /* * */
 
 /* ---- prototype design: liquid.h:1476, :1548, :1580 -> src/filter/src/firdes.c:224-280, rrcos.c:37-95 */
 float kaiser_beta_As(float _As);
@@ -85,6 +85,18 @@ void  liquid_firdes_prototype(int _type, unsigned int _k, unsigned int _m, float
 void  firdespm_run(unsigned int _h_len, unsigned int _num_bands, float *_bands, float *_des, float *_weights,
                    int *_wtype, int _btype, float *_h);
 void  liquid_firdes_hM3(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+/* the remaining families of liquid_firdes_prototype (host code): raised cosine, flipped exponential / sech / arcsech
+ * Nyquist and root-Nyquist filters, GMSK transmit / receive: liquid.h:1573-1605 -> src/filter/src/rcos.c:39-80,
+ * fnyquist.c:47-318, gmsk.c:39-193 */
+void  liquid_firdes_rcos(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+void  liquid_firdes_fexp(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+void  liquid_firdes_rfexp(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+void  liquid_firdes_fsech(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+void  liquid_firdes_rfsech(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+void  liquid_firdes_farcsech(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+void  liquid_firdes_rfarcsech(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+void  liquid_firdes_gmsktx(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
+void  liquid_firdes_gmskrx(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
 
 /* ---- firdecim_crcf / firinterp_crcf: liquid.h:2665-2722, :2498-2556 -> src/filter/src/firdecim.c:46-223,
  *      firinterp.c:43-217 (instantiated by filter_crcf.c).  SURVEY.md 8(f) item 3. */

@@ -60,6 +60,8 @@ _sig("liquid_filter_isi", None, _f_p, _u, _u, C.POINTER(C.c_float), C.POINTER(C.
 _sig("liquid_firdes_arkaiser", None, _u, _u, _fl, _fl, _f_p)
 _sig("liquid_firdes_rkaiser", None, _u, _u, _fl, _fl, _f_p)
 _sig("liquid_firdes_hM3", None, _u, _u, _fl, _fl, _f_p)
+for _nm in ("rcos", "fexp", "rfexp", "fsech", "rfsech", "farcsech", "rfarcsech", "gmsktx", "gmskrx"):
+    _sig("liquid_firdes_" + _nm, None, _u, _u, _fl, _fl, _f_p)
 _sig("firdespm_run", None, _u, _u, _f_p, _f_p, _f_p, C.POINTER(C.c_int), _i, _f_p)
 _sig("liquid_firdes_prototype", None, _i, _u, _u, _fl, _fl, _f_p)
 _sig("firpfbch2_crcf_create", _vp, _i, _u, _u, _f_p)
@@ -328,6 +330,8 @@ def liquid_firdes_hM3(k, m, beta, dt=0.0):
 LIQUID_FIRDESPM_BANDPASS, LIQUID_FIRDESPM_DIFFERENTIATOR, LIQUID_FIRDESPM_HILBERT = 0, 1, 2
 LIQUID_FIRDESPM_FLATWEIGHT, LIQUID_FIRDESPM_EXPWEIGHT, LIQUID_FIRDESPM_LINWEIGHT = 0, 1, 2
 LIQUID_FIRFILT_PM = 2
+LIQUID_FIRFILT_RCOS, LIQUID_FIRFILT_FEXP, LIQUID_FIRFILT_FSECH, LIQUID_FIRFILT_FARCSECH = 3, 4, 5, 6
+LIQUID_FIRFILT_GMSKTX, LIQUID_FIRFILT_GMSKRX, LIQUID_FIRFILT_RFEXP, LIQUID_FIRFILT_RFSECH, LIQUID_FIRFILT_RFARCSECH = 11, 12, 13, 14, 15
 
 
 def firdespm_run(h_len, bands, des, weights=None, wtype=None, btype=LIQUID_FIRDESPM_BANDPASS):

@@ -572,6 +572,189 @@ extern "C" void liquid_firdes_rkaiser(unsigned int _k, unsigned int _m, float _b
 // (root-)Nyquist prototype of 2km+1 taps by liquid_firfilt_type           liquid.h:1444, firdes.c:290-370
 // Provided: KAISER, ARKAISER, RKAISER, RRC.  The Parks-McClellan based ones (PM, hM3: firdespm.c) and the
 // rcos / fexp / fsech / farcsech / GMSK families belong to filter-design subsystems outside this library.
+namespace lc {
+namespace {
+// unscaled DFT of a short odd-length design array (the reference uses its float FFT here, fnyquist.c:86, gmsk.c:152-179;
+// a direct sum in double agrees with it to float rounding): y[k] = sum_i x[i] e^{sign j 2 pi i k / n}
+void design_dft(const std::vector<lc_cf> &x, std::vector<lc_cf> &y, int sign)
+{
+    const unsigned int n = (unsigned int)x.size();
+    y.resize(n);
+    for (unsigned int k = 0; k < n; k++) {
+        double re = 0.0, im = 0.0;
+        for (unsigned int i = 0; i < n; i++) {
+            const double a = (double)sign * 2.0 * M_PI * (double)(((unsigned long long)i * k) % n) / (double)n;
+            const double c = cos(a), sn = sin(a);
+            re += x[i].re * c - x[i].im * sn;
+            im += x[i].re * sn + x[i].im * c;
+        }
+        y[k] = lc_cf{(float)re, (float)im};
+    }
+}
+
+int nyquist_args(unsigned int k, unsigned int m, float beta)       // 0 ok, else message id
+{
+    if (k < 1) return 1;
+    if (m < 1) return 2;
+    if (beta < 0.0f || beta > 1.0f) return 3;
+    return 0;
+}
+
+float asechf_(float z)                                              // fnyquist.c:253-262
+{
+    if (z <= 0.0f || z > 1.0f) {
+        fprintf(stderr, "warning: liquid_asechf(), input out of range\n");
+        return 0.0f;
+    }
+    const float zi = 1.0f / z;
+    return logf(sqrtf(zi - 1.0f) * sqrtf(zi + 1.0f) + zi);
+}
+}  // namespace
+
+// rcos.c:39-80: raised cosine, cos(pi beta z) sinc(z) / (1 - 4 beta^2 z^2) with the removable singularity patched
+int firdes_rcos(unsigned int k, unsigned int m, float beta, float dt, float *h)
+{
+    if (int rc = nyquist_args(k, m, beta)) return rc;
+    const unsigned int h_len = 2 * k * m + 1;
+    for (unsigned int n = 0; n < h_len; n++) {
+        const float z = ((float)n + dt) / (float)k - (float)m;
+        const float t1 = cosf((float)(beta * M_PI * z));
+        const float t2 = sincf_(z);
+        const float t3 = 1 - 4.0f * beta * beta * z * z;
+        if (fabsf(t3) < 1e-3f) h[n] = (float)(sinf((float)(M_PI / (2.0 * beta))) * beta * 0.5f);
+        else h[n] = t1 * t2 / t3;
+    }
+    return 0;
+}
+
+// fnyquist.c:47-93, :121-318: flipped-exponential / -sech / -arcsech Nyquist filters designed in the frequency domain
+// (kind 0 / 1 / 2), optionally the square root of the response, inverse transform, shift and scale
+int firdes_fnyquist(int kind, int root, unsigned int k, unsigned int m, float beta, float dt, float *h)
+{
+    (void)dt;
+    if (int rc = nyquist_args(k, m, beta)) return rc;
+    const unsigned int h_len = 2 * k * m + 1;
+    const float f0 = 0.5f * (1.0f - beta) / (float)k, f1 = 0.5f * (1.0f) / (float)k, f2 = 0.5f * (1.0f + beta) / (float)k;
+    const float B = 0.5f / (float)k;
+    const float gamma = (kind == 0 ? logf(2.0f) : logf(sqrtf(3.0f) + 2.0f)) / (beta * B);
+    const float zeta = 1.0f / (2.0f * beta * B);
+    std::vector<lc_cf> H(h_len), t;
+    for (unsigned int i = 0; i < h_len; i++) {
+        float f = (float)i / (float)h_len;
+        if (f > 0.5f) f = f - 1.0f;
+        f = fabsf(f);
+        float v;
+        if (f < f0) v = 1.0f;
+        else if (f > f0 && f < f2) {
+            if (kind == 0) v = f < f1 ? expf(gamma * (B * (1 - beta) - f)) : 1.0f - expf(gamma * (f - (1 + beta) * B));
+            else if (kind == 1) v = f < f1 ? 1.0f / coshf(gamma * (f - B * (1 - beta))) : 1.0f - 1.0f / coshf(gamma * (B * (1 + beta) - f));
+            else v = f < f1 ? 1.0f - (zeta / gamma) * asechf_(zeta * (B * (1 + beta) - f)) : (zeta / gamma) * asechf_(zeta * (f - B * (1 - beta)));
+        } else v = 0.0f;
+        H[i] = lc_cf{root ? sqrtf(v) : v, 0.0f};
+    }
+    design_dft(H, t, +1);
+    for (unsigned int i = 0; i < h_len; i++) h[i] = t[(i + k * m + 1) % h_len].re * (float)k / (float)h_len;
+    return 0;
+}
+
+// gmsk.c:39-78: Gaussian pulse-shaping filter (difference of two Q functions), normalised to an integral of pi/2, times k
+int firdes_gmsktx(unsigned int k, unsigned int m, float beta, float dt, float *h)
+{
+    if (int rc = nyquist_args(k, m, beta)) return rc;
+    const unsigned int h_len = 2 * k * m + 1;
+    const float c0 = 1.0f / sqrtf(logf(2.0f));
+    auto Q = [](float z) { return 0.5f * (1.0f - erff((float)(z * M_SQRT1_2))); };
+    for (unsigned int i = 0; i < h_len; i++) {
+        const float t = (float)i / (float)k - (float)m + dt;
+        h[i] = Q((float)(2 * M_PI * beta * (t - 0.5f) * c0)) - Q((float)(2 * M_PI * beta * (t + 0.5f) * c0));
+    }
+    float e = 0.0f;
+    for (unsigned int i = 0; i < h_len; i++) e += h[i];
+    for (unsigned int i = 0; i < h_len; i++) h[i] = (float)(h[i] * (M_PI / (2.0f * e)));
+    for (unsigned int i = 0; i < h_len; i++) h[i] *= (float)k;
+    return 0;
+}
+
+// gmsk.c:91-193: receive filter that, cascaded with the transmit filter, approximates a Kaiser Nyquist prototype:
+// ratio of the two frequency responses (minima removed, small correction added), times a 60 dB Kaiser "gain" filter
+int firdes_gmskrx(unsigned int k, unsigned int m, float beta, float dt, float *h)
+{
+    (void)dt;
+    if (int rc = nyquist_args(k, m, beta)) return rc;
+    const unsigned int h_len = 2 * k * m + 1;
+    const float delta = 1e-3f;
+    std::vector<float> ht(h_len), hp(h_len), gp(h_len);
+    firdes_gmsktx(k, m, beta, 0.0f, ht.data());
+    {
+        const float fc = 0.5f / (float)k, df = beta / (float)k;       // the KAISER case of liquid_firdes_prototype
+        firdes_kaiser(h_len, fc, estimate_req_filter_As(df, h_len), 0.0f, hp.data());
+    }
+    firdes_kaiser(h_len, (float)((0.7f + 0.1 * beta) / (float)k), 60.0f, 0.0f, gp.data());
+    std::vector<lc_cf> a(h_len), b(h_len), c(h_len), Hp, Gp, Ht;
+    for (unsigned int i = 0; i < h_len; i++) {
+        a[i] = lc_cf{hp[(i + k * m) % h_len], 0.0f};
+        b[i] = lc_cf{gp[(i + k * m) % h_len], 0.0f};
+        c[i] = lc_cf{ht[(i + k * m) % h_len], 0.0f};
+    }
+    design_dft(a, Hp, -1);
+    design_dft(b, Gp, -1);
+    design_dft(c, Ht, -1);
+    float Ht_min = 0.0f, Hp_min = 0.0f, Gp_min = 0.0f;
+    for (unsigned int i = 0; i < h_len; i++) {
+        if (i == 0 || Ht[i].re < Ht_min) Ht_min = Ht[i].re;
+        if (i == 0 || Hp[i].re < Hp_min) Hp_min = Hp[i].re;
+        if (i == 0 || Gp[i].re < Gp_min) Gp_min = Gp[i].re;
+    }
+    std::vector<lc_cf> Hh(h_len), hh;
+    for (unsigned int i = 0; i < h_len; i++) {
+        float v = (Hp[i].re - Hp_min + delta) / (Ht[i].re - Ht_min + delta);
+        v *= (Gp[i].re - Gp_min) / Gp[0].re;
+        Hh[i] = lc_cf{v, 0.0f};
+    }
+    design_dft(Hh, hh, +1);
+    for (unsigned int i = 0; i < h_len; i++) {
+        const float hr = hh[(i + k * m + 1) % h_len].re / (float)(k * h_len);
+        h[i] = hr * k * k;
+    }
+    return 0;
+}
+
+}  // namespace lc
+
+namespace {
+void nyquist_fatal(const char *fn, int rc)
+{
+    if (rc == 1) lc::fatal(fn, "k must be greater than 0");
+    if (rc == 2) lc::fatal(fn, "m must be greater than 0");
+    if (rc) lc::fatal(fn, "beta must be in [0,1]");
+}
+}  // namespace
+
+extern "C" void liquid_firdes_rcos(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h)
+{
+    nyquist_fatal("liquid_firdes_rcos", lc::firdes_rcos(_k, _m, _beta, _dt, _h));
+}
+#define LC_FNYQUIST(NAME, KIND, ROOT)                                                                          \
+    extern "C" void liquid_firdes_##NAME(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h) \
+    {                                                                                                          \
+        nyquist_fatal("liquid_firdes_fnyquist", lc::firdes_fnyquist(KIND, ROOT, _k, _m, _beta, _dt, _h));      \
+    }
+LC_FNYQUIST(fexp, 0, 0)
+LC_FNYQUIST(rfexp, 0, 1)
+LC_FNYQUIST(fsech, 1, 0)
+LC_FNYQUIST(rfsech, 1, 1)
+LC_FNYQUIST(farcsech, 2, 0)
+LC_FNYQUIST(rfarcsech, 2, 1)
+#undef LC_FNYQUIST
+extern "C" void liquid_firdes_gmsktx(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h)
+{
+    nyquist_fatal("liquid_firdes_gmsktx", lc::firdes_gmsktx(_k, _m, _beta, _dt, _h));
+}
+extern "C" void liquid_firdes_gmskrx(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h)
+{
+    nyquist_fatal("liquid_firdes_gmskrx", lc::firdes_gmskrx(_k, _m, _beta, _dt, _h));
+}
+
 extern "C" void firdespm_run(unsigned int _h_len, unsigned int _num_bands, float *_bands, float *_des, float *_weights,
                              int *_wtype, int _btype, float *_h)
 {
@@ -623,18 +806,15 @@ extern "C" void liquid_firdes_prototype(int _type, unsigned int _k, unsigned int
         firdespm_run(h_len, 3, bands, des, weights, wtype, LIQUID_FIRDESPM_BANDPASS, _h);
         return;
     }
-    case LIQUID_FIRFILT_RCOS:
-    case LIQUID_FIRFILT_FEXP:
-    case LIQUID_FIRFILT_FSECH:
-    case LIQUID_FIRFILT_FARCSECH:
-    case LIQUID_FIRFILT_GMSKTX:
-    case LIQUID_FIRFILT_GMSKRX:
-    case LIQUID_FIRFILT_RFEXP:
-    case LIQUID_FIRFILT_RFSECH:
-    case LIQUID_FIRFILT_RFARCSECH:
-        fprintf(stderr, "error: liquid_firdes_prototype(), filter type '%d' is not provided by liquid_cuda "
-                        "(KAISER, PM, ARKAISER, RKAISER, RRC and hM3 are; pass external taps to the create() form)\n", _type);
-        exit(1);
+    case LIQUID_FIRFILT_RCOS: liquid_firdes_rcos(_k, _m, _beta, _dt, _h); return;
+    case LIQUID_FIRFILT_FEXP: liquid_firdes_fexp(_k, _m, _beta, _dt, _h); return;
+    case LIQUID_FIRFILT_FSECH: liquid_firdes_fsech(_k, _m, _beta, _dt, _h); return;
+    case LIQUID_FIRFILT_FARCSECH: liquid_firdes_farcsech(_k, _m, _beta, _dt, _h); return;
+    case LIQUID_FIRFILT_GMSKTX: liquid_firdes_gmsktx(_k, _m, _beta, _dt, _h); return;
+    case LIQUID_FIRFILT_GMSKRX: liquid_firdes_gmskrx(_k, _m, _beta, _dt, _h); return;
+    case LIQUID_FIRFILT_RFEXP: liquid_firdes_rfexp(_k, _m, _beta, _dt, _h); return;
+    case LIQUID_FIRFILT_RFSECH: liquid_firdes_rfsech(_k, _m, _beta, _dt, _h); return;
+    case LIQUID_FIRFILT_RFARCSECH: liquid_firdes_rfarcsech(_k, _m, _beta, _dt, _h); return;
     default:
         fprintf(stderr, "error: liquid_firdes_prototype(), invalid root-Nyquist filter type '%d'\n", _type);
         exit(1);

@@ -125,6 +125,14 @@ for tag, h_len, bands, des, wts, wtype in [
     out["pmrun_%s_weights" % tag] = np.array(wts, np.float32)
     out["pmrun_%s_wtype" % tag] = wt
     out["pmrun_%s_h" % tag] = h
+# the other families of liquid_firdes_prototype (rcos, fexp / fsech / farcsech and their roots, gmsk tx / rx)
+proto_cases = [(2, 3, 0.3, 0.0), (4, 5, 0.5, 0.0), (8, 3, 0.4, 0.25), (2, 12, 0.2, 0.0), (16, 4, 0.35, 0.0), (3, 7, 0.9, -0.5)]
+out["proto_cases"] = np.array(proto_cases, np.float64)
+for ftype in (3, 4, 5, 6, 11, 12, 13, 14, 15):
+    for k, m, beta, dt in proto_cases:
+        h = np.empty(2 * k * m + 1, np.float32)
+        Rr.liquid_firdes_prototype(ftype, k, m, beta, dt, h)
+        out["taps_proto%d_k%d_m%d" % (ftype, k, m)] = h.copy()
 for M, m, beta in [(8, 3, 0.4), (64, 2, 0.5)]:
     x = O.synth_input(M * 60, seed=0x5EEDAA00 + M)
     out["pfbch_hM3_M%d_m%d_x" % (M, m)] = x

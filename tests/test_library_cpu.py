@@ -177,3 +177,19 @@ def test_host_design_parks_mcclellan_and_hM3_equal_the_reference_bit_for_bit(L, 
     H = np.abs(np.fft.fft(h, 1024))[:513]
     f = np.arange(513) / 1024.0
     assert np.abs(H[f <= 0.2] - 1).max() < 0.1 and H[f >= 0.25].max() < 0.01
+
+
+def test_host_design_remaining_prototype_families(L, refrn2):
+    """liquid_firdes_prototype for RCOS, FEXP / FSECH / FARCSECH and their root versions, GMSKTX / GMSKRX against the
+    compiled reference's taps: the closed forms bit for bit, the frequency-sampled ones to the rounding of the
+    reference's float FFT (the receive GMSK design divides two such responses: 2e-5)"""
+    tol = {3: 0.0, 11: 0.0, 4: 2e-6, 5: 2e-6, 6: 2e-6, 13: 2e-6, 14: 2e-6, 15: 2e-6, 12: 2e-5}
+    for ftype, t in tol.items():
+        for k, m, beta, dt in refrn2["proto_cases"]:
+            k, m = int(k), int(m)
+            want = refrn2["taps_proto%d_k%d_m%d" % (ftype, k, m)]
+            got = L.liquid_firdes_prototype(ftype, k, m, np.float32(beta), np.float32(dt))
+            if t == 0.0:
+                assert np.array_equal(got, want), (ftype, k, m)
+            else:
+                assert np.abs(got - want).max() <= t * np.abs(want).max(), (ftype, k, m)
