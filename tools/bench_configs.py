@@ -3,7 +3,15 @@
 measured here for the record).  One JSON line per config, device-resident synthetic data, CUDA
 events, inputs larger than L2.  Not the driver's headline bench (that is bench.py).
 
-  python tools/bench_configs.py [c1] [c2] [c4] [c5] [g] [f1] [f2] [f3] [f4] [f5] [f6] [s] [p] [d] [fft] [--steps K]     (f1 = SURVEY 8(f) item 1: firpfbch_cccf)
+  python tools/bench_configs.py [config ...] [--steps K]
+
+  c1 c2 c4 c5   BASELINE configs 1, 2, 4, 5 (c3 is bench.py)          c3m c5m  c3 / c5 against the filter length m
+  g             shape-generic one-kernel analyzers (M = 256, 64, 2048)  s        synthesizers (firpfbch2 M=1024, firpfbch M=1024 / 256)
+  fft           fft_execute_batch_dev, n = 16 / 256 / 1024 / 4096       d        dotprod_crcf batch entry point
+  p             firpfb_crcf block form
+  f1            firpfbch_cccf (8f item 1)                                f2       spgramcf_accumulate_psd (8f item 2)
+  f3            firdecim_crcf / firinterp_crcf                           f4       resamp2_crcf modes, msresamp2_crcf cascades
+  f5            fftfilt_crcf                                             f6       ofdmframegen data symbols (8f item 4)
 """
 import argparse
 import json
