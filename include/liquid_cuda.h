@@ -84,6 +84,12 @@ void  liquid_firdes_prototype(int _type, unsigned int _k, unsigned int _m, float
 #define LIQUID_FIRDESPM_LINWEIGHT       2
 void  firdespm_run(unsigned int _h_len, unsigned int _num_bands, float *_bands, float *_des, float *_weights,
                    int *_wtype, int _btype, float *_h);
+typedef struct firdespm_s * firdespm;            /* liquid.h:1514-1540 -> firdespm.c:142-343 */
+firdespm firdespm_create(unsigned int _h_len, unsigned int _num_bands, float *_bands, float *_des, float *_weights,
+                         int *_wtype, int _btype);
+void  firdespm_destroy(firdespm _q);
+void  firdespm_print(firdespm _q);
+void  firdespm_execute(firdespm _q, float *_h);
 void  liquid_firdes_hM3(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h);
 /* the remaining families of liquid_firdes_prototype (host code): raised cosine, flipped exponential / sech / arcsech
  * Nyquist and root-Nyquist filters, GMSK transmit / receive: liquid.h:1573-1605 -> src/filter/src/rcos.c:39-80,

@@ -60,6 +60,10 @@ _sig("liquid_filter_isi", None, _f_p, _u, _u, C.POINTER(C.c_float), C.POINTER(C.
 _sig("liquid_firdes_arkaiser", None, _u, _u, _fl, _fl, _f_p)
 _sig("liquid_firdes_rkaiser", None, _u, _u, _fl, _fl, _f_p)
 _sig("liquid_firdes_hM3", None, _u, _u, _fl, _fl, _f_p)
+_sig("firdespm_create", _vp, _u, _u, _f_p, _f_p, _f_p, C.POINTER(C.c_int), _i)
+_sig("firdespm_destroy", None, _vp)
+_sig("firdespm_print", None, _vp)
+_sig("firdespm_execute", None, _vp, _f_p)
 for _nm in ("rcos", "fexp", "rfexp", "fsech", "rfsech", "farcsech", "rfarcsech", "gmsktx", "gmskrx"):
     _sig("liquid_firdes_" + _nm, None, _u, _u, _fl, _fl, _f_p)
 _sig("firdespm_run", None, _u, _u, _f_p, _f_p, _f_p, C.POINTER(C.c_int), _i, _f_p)

@@ -772,6 +772,59 @@ extern "C" void firdespm_run(unsigned int _h_len, unsigned int _num_bands, float
     }
 }
 
+// the designer as an object (liquid.h:1514-1540, firdespm.c:142-343): the specification is kept, execute() designs
+struct firdespm_s {
+    unsigned int h_len, num_bands;
+    std::vector<float> bands, des, weights;
+    std::vector<int> wtype;
+    int btype;
+};
+
+extern "C" firdespm firdespm_create(unsigned int _h_len, unsigned int _num_bands, float *_bands, float *_des, float *_weights,
+                                    int *_wtype, int _btype)
+{
+    bool bands_ok = true, weights_ok = true;
+    for (unsigned int i = 0; i < 2 * _num_bands; i++) bands_ok &= _bands[i] >= 0.0 && _bands[i] <= 0.5;
+    for (unsigned int i = 1; i < 2 * _num_bands; i++) bands_ok &= _bands[i] >= _bands[i - 1];
+    for (unsigned int i = 0; i < _num_bands; i++) weights_ok &= (_weights == nullptr || _weights[i] > 0);
+    if (!bands_ok) lc::fatal("firdespm_create", "invalid bands");
+    if (!weights_ok) lc::fatal("firdespm_create", "invalid weights (must be positive)");
+    if (_num_bands == 0) lc::fatal("firdespm_create", "number of bands must be > 0");
+    firdespm q = new firdespm_s();
+    q->h_len = _h_len;
+    q->num_bands = _num_bands;
+    q->bands.assign(_bands, _bands + 2 * _num_bands);
+    q->des.assign(_des, _des + _num_bands);
+    q->weights.assign(_num_bands, 1.0f);
+    if (_weights) q->weights.assign(_weights, _weights + _num_bands);
+    q->wtype.assign(_num_bands, LIQUID_FIRDESPM_FLATWEIGHT);
+    if (_wtype) q->wtype.assign(_wtype, _wtype + _num_bands);
+    q->btype = _btype;
+    return q;
+}
+
+extern "C" void firdespm_destroy(firdespm _q) { delete _q; }
+
+extern "C" void firdespm_print(firdespm _q)
+{
+    printf("firdespm:               ");
+    for (unsigned int i = 0; i < _q->num_bands; i++) printf("      band %-5u", i);
+    printf("\n  lower band edge       ");
+    for (unsigned int i = 0; i < _q->num_bands; i++) printf("%16.8f", _q->bands[2 * i]);
+    printf("\n  upper band edge       ");
+    for (unsigned int i = 0; i < _q->num_bands; i++) printf("%16.8f", _q->bands[2 * i + 1]);
+    printf("\n  desired value         ");
+    for (unsigned int i = 0; i < _q->num_bands; i++) printf("%16.8f", _q->des[i]);
+    printf("\n  weighting             ");
+    for (unsigned int i = 0; i < _q->num_bands; i++) printf("%16.8f", _q->weights[i]);
+    printf("\n");
+}
+
+extern "C" void firdespm_execute(firdespm _q, float *_h)
+{
+    firdespm_run(_q->h_len, _q->num_bands, _q->bands.data(), _q->des.data(), _q->weights.data(), _q->wtype.data(), _q->btype, _h);
+}
+
 extern "C" void liquid_firdes_hM3(unsigned int _k, unsigned int _m, float _beta, float _dt, float *_h)
 {
     switch (lc::firdes_hM3(_k, _m, _beta, _dt, _h)) {

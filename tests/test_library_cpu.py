@@ -172,6 +172,16 @@ def test_host_design_parks_mcclellan_and_hM3_equal_the_reference_bit_for_bit(L, 
         want = refrn2[name]
         got = L.firdespm_run(len(want), refrn2[tag + "_bands"], refrn2[tag + "_des"], refrn2[tag + "_weights"], refrn2[tag + "_wtype"])
         assert np.array_equal(got, want), tag
+    # the object form gives the same taps
+    tag = "pmrun_bp77"
+    wt = np.ascontiguousarray(refrn2[tag + "_wtype"], np.int32)
+    import ctypes as C
+    q = L.lib.firdespm_create(77, 3, refrn2[tag + "_bands"], refrn2[tag + "_des"], refrn2[tag + "_weights"],
+                              wt.ctypes.data_as(C.POINTER(C.c_int)), L.LIQUID_FIRDESPM_BANDPASS)
+    h = np.empty(77, np.float32)
+    L.lib.firdespm_execute(q, h)
+    L.lib.firdespm_destroy(q)
+    assert np.array_equal(h, refrn2[tag + "_h"])
     # what an equiripple low-pass is: pass band near 1, stop band small
     h = L.firdespm_run(51, [0.0, 0.2, 0.25, 0.5], [1.0, 0.0], [1.0, 10.0])
     H = np.abs(np.fft.fft(h, 1024))[:513]
