@@ -203,3 +203,31 @@ def test_host_design_remaining_prototype_families(L, refrn2):
                 assert np.array_equal(got, want), (ftype, k, m)
             else:
                 assert np.abs(got - want).max() <= t * np.abs(want).max(), (ftype, k, m)
+
+
+def test_c_program_builds_and_links_against_the_drop_in(L, tmp_path):
+    """the boundary is a C ABI: include/liquid_cuda.h compiles as C99 and as C++11, and a plain C program that calls
+    the reference's own function names links against libliquid_cuda.so and runs (host-side design calls: no GPU)"""
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(L.LIB_PATH)
+    src = tmp_path / "app.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <liquid_cuda.h>\n'
+        'int main(void) {\n'
+        '    float h[57];\n'
+        '    liquid_firdes_kaiser(57, 0.2f, 60.0f, 0.0f, h);\n'
+        '    float g[2 * 4 * 3 + 1];\n'
+        '    liquid_firdes_prototype(LIQUID_FIRFILT_hM3, 4, 3, 0.3f, 0.0f, g);\n'
+        '    printf("%.8e %u %.8e\\n", h[28], estimate_req_filter_len(0.1f, 60.0f), g[12]);\n'
+        '    return 0;\n}\n')
+    exe = tmp_path / "app"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe), "-L", libdir,
+                           "-lliquid_cuda", "-lm", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-300:]
+    centre, n_len, g12 = out.stdout.split()
+    assert abs(float(centre) - float(L.liquid_firdes_kaiser(57, 0.2, 60.0)[28])) < 1e-9 and int(n_len) == 36
+    assert abs(float(g12) - float(L.liquid_firdes_hM3(4, 3, 0.3)[12])) < 1e-7
+    cpp = tmp_path / "hdr.cpp"
+    cpp.write_text('#include <liquid_cuda.h>\nint main() { return 0; }\n')
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", str(cpp)])
