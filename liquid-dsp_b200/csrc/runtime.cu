@@ -37,6 +37,9 @@ void ensure_device()
                 dev, prop.name, prop.major, prop.minor);
         abort();
     }
+    if (getenv("LIQUID_CUDA_VERBOSE"))      // one line when the library takes over a process (e.g. under LD_PRELOAD)
+        fprintf(stderr, "liquid_cuda: active on device %d (%s, sm_%d%d, %d SMs)\n", dev, prop.name, prop.major, prop.minor,
+                prop.multiProcessorCount);
     g_device_ready.store(1, std::memory_order_release);
 }
 

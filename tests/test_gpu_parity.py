@@ -4,6 +4,8 @@ vectors, plus size-independent properties at larger sizes.
 
 Tolerances (BASELINE.json north_star): per-channel relative RMS error <= 1e-5 and
 max-abs error <= 1e-4 normalised to sqrt(input power), for the float32 channelizer outputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -1162,3 +1164,37 @@ def test_randomized_shapes_vs_oracle(L, orc):
                              + [q.writetail()])
         want = orc.ofdm_frame(o, x)
         assert np.abs(got - want).max() < 4e-6 * max(1.0, np.abs(want).max()), ("ofdm", M, cp, tl, nsym)
+
+
+# ------------------------------------------------------------------ the reference's own example programs on the drop-in
+REF_EXAMPLES_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "examples")
+
+
+@pytest.mark.parametrize("name", ["firpfbch2_crcf_example", "firpfbch_crcf_analysis_example", "firpfbch_crcf_synthesis_example",
+                                  "firdecim_crcf_example", "msresamp2_crcf_example", "resamp2_crcf_decim_example"])
+def test_reference_example_program_unmodified_on_the_drop_in(L, name, tmp_path):
+    """a binary of the reference's own example (built by oracle/Makefile from /root/reference/examples, unmodified,
+    linked against the compiled reference) run twice: as it is, and with libliquid_cuda.so preloaded so that the
+    hot-path symbols resolve to this library -- every number it writes to its .m file must agree"""
+    import re
+    import subprocess
+    exe = os.path.join(REF_EXAMPLES_DIR, name)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/examples not built (needs /root/reference at build time)")
+    outs = []
+    for tag, preload in (("ref", None), ("cuda", L.LIB_PATH)):
+        d = tmp_path / tag
+        d.mkdir()
+        env = dict(os.environ)
+        env["LIQUID_CUDA_VERBOSE"] = "1"                  # the library announces itself on stderr when it is in charge
+        if preload:
+            env["LD_PRELOAD"] = preload
+        r = subprocess.run([exe], cwd=str(d), env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (tag, r.stderr[-400:])
+        assert ("liquid_cuda: active on device" in r.stderr) == bool(preload), (tag, r.stderr[-400:])
+        text = (d / (name + ".m")).read_text()
+        nums = [float(v) for v in re.findall(r"[-+]?\d+\.\d+(?:[eE][-+]?\d+)?", text)]
+        outs.append(np.array(nums))
+    ref, got = outs
+    assert ref.shape == got.shape and ref.size > 50
+    assert np.abs(ref - got).max() <= 2e-5 * max(1.0, np.abs(ref).max()), name
