@@ -1171,7 +1171,9 @@ REF_EXAMPLES_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 
 
 @pytest.mark.parametrize("name", ["firpfbch2_crcf_example", "firpfbch_crcf_analysis_example", "firpfbch_crcf_synthesis_example",
-                                  "firdecim_crcf_example", "msresamp2_crcf_example", "resamp2_crcf_decim_example"])
+                                  "firdecim_crcf_example", "msresamp2_crcf_example", "resamp2_crcf_decim_example",
+                                  "firfilt_crcf_example", "firinterp_crcf_example", "resamp2_crcf_interp_example",
+                                  "resamp2_crcf_filter_example", "resamp2_crcf_example"])
 def test_reference_example_program_unmodified_on_the_drop_in(L, name, tmp_path):
     """a binary of the reference's own example (built by oracle/Makefile from /root/reference/examples, unmodified,
     linked against the compiled reference) run twice: as it is, and with libliquid_cuda.so preloaded so that the

@@ -231,3 +231,30 @@ def test_c_program_builds_and_links_against_the_drop_in(L, tmp_path):
     cpp = tmp_path / "hdr.cpp"
     cpp.write_text('#include <liquid_cuda.h>\nint main() { return 0; }\n')
     subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", str(cpp)])
+
+
+@pytest.mark.parametrize("name,symbol", [("firdes_kaiser_example", "liquid_firdes_kaiser"), ("firdespm_example", "firdespm_run")])
+def test_reference_design_example_unmodified_on_the_drop_in(L, tmp_path, name, symbol):
+    """the reference's own filter-design example programs (compiled unmodified against the compiled reference by
+    oracle/Makefile) run as they are and with libliquid_cuda.so preloaded: the dynamic linker binds the design call
+    to this library (LD_DEBUG=bindings) and the programs write the same numbers -- host code, no GPU involved"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "examples", name)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/examples not built (needs /root/reference at build time)")
+    outs = []
+    for tag, preload in (("ref", None), ("cuda", L.LIB_PATH)):
+        d = tmp_path / tag
+        d.mkdir()
+        env = dict(os.environ)
+        env["LD_DEBUG"] = "bindings"
+        if preload:
+            env["LD_PRELOAD"] = preload
+        r = subprocess.run([exe], cwd=str(d), env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (tag, r.stderr[-300:])
+        bound_here = any("libliquid_cuda.so" in ln.split(" to ")[-1] and ("`%s'" % symbol) in ln
+                         for ln in r.stderr.splitlines() if "binding file" in ln and " to " in ln)
+        assert bound_here == bool(preload), (tag, symbol)
+        text = (d / (name + ".m")).read_text()
+        outs.append(np.array([float(v) for v in re.findall(r"[-+]?\d+\.\d+(?:[eE][-+]?\d+)?", text)]))
+    ref, got = outs
+    assert ref.shape == got.shape and ref.size > 10 and np.abs(ref - got).max() <= 1e-6 * max(1.0, np.abs(ref).max())
