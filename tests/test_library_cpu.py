@@ -258,3 +258,15 @@ def test_reference_design_example_unmodified_on_the_drop_in(L, tmp_path, name, s
         outs.append(np.array([float(v) for v in re.findall(r"[-+]?\d+\.\d+(?:[eE][-+]?\d+)?", text)]))
     ref, got = outs
     assert ref.shape == got.shape and ref.size > 10 and np.abs(ref - got).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+
+
+def test_exported_prototypes_equal_the_reference_header():
+    """every function exported under a reference name takes exactly the reference's parameters: both headers are
+    preprocessed (the reference generates its API with macros) and compared type by type -- needs /root/reference,
+    so this runs in the build container only (tools/check_signatures.py)"""
+    if not os.path.isdir("/root/reference/include"):
+        pytest.skip("/root/reference is not present on this machine")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_signatures.py")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:]
+    n = int(r.stdout.split()[0])
+    assert n >= 150, r.stdout
