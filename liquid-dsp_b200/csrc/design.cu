@@ -549,8 +549,14 @@ extern "C" float estimate_req_filter_As(float _df, unsigned int _N) { return lc:
 
 extern "C" unsigned int estimate_req_filter_len(float _df, float _As)
 {
-    if (_df > 0.5f || _df <= 0.0f) lc::fatal("estimate_req_filter_len", "invalid bandwidth");
-    if (_As <= 0.0f) lc::fatal("estimate_req_filter_len", "invalid stopband level");
+    if (_df > 0.5f || _df <= 0.0f) {
+        fprintf(stderr, "error: estimate_req_filter_len(), invalid bandwidth : %f\n", _df);
+        exit(1);
+    }
+    if (_As <= 0.0f) {
+        fprintf(stderr, "error: estimate_req_filter_len(), invalid stopband level : %f\n", _As);
+        exit(1);
+    }
     return lc::estimate_req_filter_len(_df, _As);
 }
 
@@ -722,11 +728,17 @@ int firdes_gmskrx(unsigned int k, unsigned int m, float beta, float dt, float *h
 }  // namespace lc
 
 namespace {
+// (these design functions of the reference punctuate "error: <fn>(): <msg>")
+[[noreturn]] void fatal_colon(const char *fn, const char *msg)
+{
+    fprintf(stderr, "error: %s(): %s\n", fn, msg);
+    exit(1);
+}
 void nyquist_fatal(const char *fn, int rc)
 {
-    if (rc == 1) lc::fatal(fn, "k must be greater than 0");
-    if (rc == 2) lc::fatal(fn, "m must be greater than 0");
-    if (rc) lc::fatal(fn, "beta must be in [0,1]");
+    if (rc == 1) fatal_colon(fn, "k must be greater than 0");
+    if (rc == 2) fatal_colon(fn, "m must be greater than 0");
+    if (rc) fatal_colon(fn, "beta must be in [0,1]");
 }
 }  // namespace
 
@@ -829,9 +841,9 @@ extern "C" void liquid_firdes_hM3(unsigned int _k, unsigned int _m, float _beta,
 {
     switch (lc::firdes_hM3(_k, _m, _beta, _dt, _h)) {
     case 0: return;
-    case 1: lc::fatal("liquid_firdes_hM3", "k must be greater than 1");
-    case 2: lc::fatal("liquid_firdes_hM3", "m must be greater than 0");
-    default: lc::fatal("liquid_firdes_hM3", "beta must be in [0,1]");
+    case 1: fatal_colon("liquid_firdes_hM3", "k must be greater than 1");
+    case 2: fatal_colon("liquid_firdes_hM3", "m must be greater than 0");
+    default: fatal_colon("liquid_firdes_hM3", "beta must be in [0,1]");
     }
 }
 

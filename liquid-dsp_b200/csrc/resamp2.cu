@@ -562,7 +562,10 @@ void design(resamp2_crcf q)
 void check_args(const char *fn, unsigned int m, float f0)
 {
     if (m < 2) lc::fatal(fn, "filter semi-length must be at least 2");
-    if (f0 < -0.5f || f0 > 0.5f) lc::fatal(fn, "f0 must be in (-1,1)");
+    if (f0 < -0.5f || f0 > 0.5f) {
+        fprintf(stderr, "error: %s(), f0 (%12.4e) must be in (-1,1)\n", fn, f0);
+        exit(1);
+    }
 }
 
 void allocate(resamp2_crcf q)

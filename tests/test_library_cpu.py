@@ -270,3 +270,57 @@ def test_exported_prototypes_equal_the_reference_header():
     assert r.returncode == 0, r.stdout[-2000:]
     n = int(r.stdout.split()[0])
     assert n >= 150, r.stdout
+
+
+_F = "C.c_float(%r)"
+ERROR_TEXT_CALLS = [
+    ("resamp2_crcf_create", "(4, C.c_float(0.75), C.c_float(60.0))"), ("estimate_req_filter_len", "(C.c_float(0.7), C.c_float(60.0))"),
+    ("estimate_req_filter_len", "(C.c_float(0.1), C.c_float(-1.0))"), ("liquid_firdes_hM3", "(1, 3, C.c_float(0.3), C.c_float(0.0), None)"),
+    ("liquid_firdes_rcos", "(0, 3, C.c_float(0.3), C.c_float(0.0), None)"), ("liquid_firdes_fexp", "(2, 0, C.c_float(0.3), C.c_float(0.0), None)"),
+    ("liquid_firdes_gmsktx", "(2, 3, C.c_float(1.3), C.c_float(0.0), None)"), ("liquid_firdes_gmskrx", "(0, 3, C.c_float(0.3), C.c_float(0.0), None)"),
+    ("liquid_firdes_kaiser", "(0, C.c_float(0.2), C.c_float(60.0), C.c_float(0.0), None)"),
+    ("liquid_firdes_kaiser", "(11, C.c_float(0.7), C.c_float(60.0), C.c_float(0.0), None)"),
+    ("liquid_firdes_kaiser", "(11, C.c_float(0.2), C.c_float(60.0), C.c_float(0.9), None)"),
+    ("liquid_firdes_arkaiser", "(1, 3, C.c_float(0.3), C.c_float(0.0), None)"), ("liquid_firdes_rkaiser", "(2, 0, C.c_float(0.3), C.c_float(0.0), None)"),
+    ("liquid_firdes_rkaiser", "(2, 3, C.c_float(1.3), C.c_float(0.0), None)"), ("liquid_firdes_arkaiser", "(2, 3, C.c_float(0.3), C.c_float(2.0), None)"),
+    ("liquid_firdes_rrcos", "(2, 3, C.c_float(1.3), C.c_float(0.0), None)"), ("liquid_firdes_prototype", "(77, 2, 3, C.c_float(0.3), C.c_float(0.0), None)"),
+    ("firfilt_crcf_create", "(None, 0)"), ("firfilt_crcf_create_rnyquist", "(9, 1, 3, C.c_float(0.3), C.c_float(0.0))"),
+    ("firfilt_crcf_create_rect", "(0,)"), ("firfilt_crcf_create_rect", "(2000,)"), ("firfilt_crcf_create_kaiser", "(0, C.c_float(0.2), C.c_float(60.0), C.c_float(0.0))"),
+    ("firpfbch_crcf_create", "(5, 4, 3, None)"), ("firpfbch_crcf_create", "(0, 0, 3, None)"), ("firpfbch_crcf_create", "(0, 4, 0, None)"),
+    ("firpfbch_crcf_create_kaiser", "(0, 4, 0, C.c_float(60.0))"), ("firpfbch_crcf_create_kaiser", "(0, 0, 3, C.c_float(60.0))"),
+    ("firpfbch_crcf_create_rnyquist", "(0, 4, 3, C.c_float(0.3), 99)"),
+    ("firpfbch2_crcf_create", "(0, 7, 3, None)"), ("firpfbch2_crcf_create", "(0, 8, 0, None)"),
+    ("firpfbch2_crcf_create_kaiser", "(0, 7, 3, C.c_float(60.0))"), ("firpfbch2_crcf_create_kaiser", "(0, 8, 0, C.c_float(60.0))"),
+    ("firpfb_crcf_create", "(0, None, 10)"), ("firpfb_crcf_create", "(4, None, 0)"), ("firpfb_crcf_create_kaiser", "(0, 3, C.c_float(0.3), C.c_float(60.0))"),
+    ("firpfb_crcf_create_rnyquist", "(9, 0, 2, 3, C.c_float(0.3))"), ("firpfb_crcf_create_rnyquist", "(9, 4, 1, 3, C.c_float(0.3))"),
+    ("firdecim_crcf_create", "(0, None, 10)"), ("firdecim_crcf_create", "(4, None, 0)"), ("firdecim_crcf_create_kaiser", "(4, 0, C.c_float(60.0))"),
+    ("firdecim_crcf_create_kaiser", "(1, 3, C.c_float(60.0))"), ("firdecim_crcf_create_prototype", "(9, 1, 3, C.c_float(0.3), C.c_float(0.0))"),
+    ("firinterp_crcf_create", "(1, None, 10)"), ("firinterp_crcf_create", "(4, None, 2)"), ("firinterp_crcf_create_kaiser", "(4, 0, C.c_float(60.0))"),
+    ("firinterp_crcf_create_kaiser", "(1, 3, C.c_float(60.0))"), ("firinterp_crcf_create_prototype", "(9, 4, 0, C.c_float(0.3), C.c_float(0.0))"),
+    ("fftfilt_crcf_create", "(None, 0, 8)"), ("spgramcf_create", "(64, None, 65)"), ("spgramcf_create", "(64, None, 0)"),
+    ("spgramcf_create_kaiser", "(64, 65, C.c_float(3.0))"), ("spgramcf_create_kaiser", "(1, 1, C.c_float(3.0))"), ("spgramcf_create_default", "(1,)"),
+    ("ofdmframegen_create", "(1, 0, 0, None)"), ("ofdmframegen_create", "(63, 8, 2, None)"), ("ofdmframegen_create", "(64, 65, 2, None)"),
+    ("ofdmframegen_create", "(64, 8, 9, None)"), ("msresamp2_crcf_create", "(1, 3, C.c_float(0.0), C.c_float(0.0), C.c_float(60.0))"),
+    ("msresamp2_crcf_create", "(1, 17, C.c_float(0.25), C.c_float(0.0), C.c_float(60.0))"), ("resamp2_crcf_create", "(1, C.c_float(0.0), C.c_float(60.0))"),
+    ("asgramcf_create", "(0,)"),
+]
+
+
+def test_error_messages_and_exit_status_equal_the_reference(L):
+    """the same invalid call made against this library and against the compiled reference (each in its own process):
+    identical first message line on stderr and identical exit status, for some sixty bad calls across every object family"""
+    ref_lib = os.path.join(ROOT, "oracle", "_ref", "libliquid_ref_sse.so")
+    if not os.path.exists(ref_lib):
+        pytest.skip("oracle/_ref not built")
+    script = ("import ctypes as C, sys\nL = C.CDLL(sys.argv[1])\n"
+              "fn, args = sys.argv[2], eval(sys.argv[3])\ngetattr(L, fn)(*args)\n")
+    diffs = []
+    for fn, args in ERROR_TEXT_CALLS:
+        seen = []
+        for lib in (L.LIB_PATH, ref_lib):
+            r = subprocess.run([sys.executable, "-c", script, lib, fn, args], capture_output=True, text=True, timeout=60)
+            lines = [ln for ln in r.stderr.splitlines() if ln.startswith(("error", "warning"))]
+            seen.append((r.returncode, lines[0] if lines else "<none>"))
+        if seen[0] != seen[1] or seen[0][0] != 1:
+            diffs.append((fn, args, seen))
+    assert not diffs, diffs
