@@ -103,17 +103,18 @@ void FftPlanDev::init(unsigned int n_, int sign_)
     }
     LC_CUDA_CHECK(cudaMalloc(&d_tw, sizeof(float2) * n));
     LC_CUDA_CHECK(cudaMemcpy(d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    // transforms above 3072 (power of two) / 6144 (other) points need more than the default 48 KB of dynamic
+    // shared memory; every kernel a plan may launch is opted in, whatever n this particular plan has
+    static std::atomic<unsigned long long> configured{0};
+    if (first_time_on_device(configured)) {
+        LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LC_CUDA_CHECK(cudaFuncSetAttribute(dft_any_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
     if (is_pow2(n) && n >= 2) {
         const std::vector<float2> twp = lcfft::pass_ordered_twiddles(tw, n);
         LC_CUDA_CHECK(cudaMalloc(&d_twp, sizeof(float2) * n));
         LC_CUDA_CHECK(cudaMemcpy(d_twp, twp.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
-        // transforms above 3072 points need more than the default 48 KB of dynamic smem
-        static std::atomic<unsigned long long> configured{0};
-        if (first_time_on_device(configured))
-        {
-            LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        }
     }
 }
 

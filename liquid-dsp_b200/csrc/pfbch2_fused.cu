@@ -60,8 +60,9 @@ constexpr int kOffTw4 = 0;                                     // float2 tw4[3][
 constexpr int kOffTw16 = kOffTw4 + 3 * 256 * 8;                // float2 tw16[16][16]: W256^(k1 r2)
 constexpr int kOffX = kOffTw16 + 16 * 16 * 8;                  // X ring
 constexpr int kOffIn = kOffX + kRingGroups * kGroup * kSlotStride * 8;
-constexpr int kOffBar = kOffIn + kInStages * kInStageBytes;
-constexpr int kNumBars = 2 * kRingGroups + kInStages;
+constexpr int kOffTwQ = kOffIn + kInStages * kInStageBytes;    // float4 twq[16][16]: {c, c, -s, s} of tw16 (experiment 32)
+constexpr int kOffBar = kOffTwQ + 16 * 16 * 16;
+constexpr int kNumBars = 2 * kRingGroups + kInStages + kRingGroups * kGroup;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8;
 
 // ---------------------------------------------------------------------------------- the kernel
@@ -96,9 +97,13 @@ __device__ __forceinline__ void radix4_store(uint32_t slot, float2 a0, float2 a1
     sts64(slot + 3 * (kSubStride * 8), cmul2(u3, t3));
 }
 
-template <int L, int PAR0>
+template <int L, int PAR0, int X = 0>
 __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const FusedArgs a)
 {
+    // X: experiment switches (profiling only; X = 0 is the product kernel)
+    //   1 MAC warps skip the dot products   2 FFT warps skip the DFT arithmetic   4 roles swapped (FFT warps 0..7)
+    //   8 waits use a suspend-time hint   16 one "full" barrier per frame instead of per group (FFT warps of the
+    //   four frames of a group start one frame time apart)   32 FFT warps read {c, c, -s, s} twiddles (no MOVs)
     constexpr int P = L / 2;                               // groups per period
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
@@ -109,6 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
     auto bar_full = [&](int g) { return s_bar + 8u * g; };
     auto bar_empty = [&](int g) { return s_bar + 8u * (kRingGroups + g); };
     auto bar_in_full = [&](int s) { return s_bar + 8u * (2 * kRingGroups + s); };
+    auto bar_ffull = [&](int slot) { return s_bar + 8u * (2 * kRingGroups + kInStages + slot); };   // X & 16: per frame slot
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -124,6 +130,13 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
     {
         float2 *tw_s = reinterpret_cast<float2 *>(smem + kOffTw4);
         for (int i = tid; i < 3 * 256 + 16 * 16; i += kThreads) tw_s[i] = a.tw[i];
+        if (X & 32) {
+            float4 *twq = reinterpret_cast<float4 *>(smem + kOffTwQ);
+            for (int i = tid; i < 16 * 16; i += kThreads) {
+                const float2 t = a.tw[3 * 256 + i];
+                twq[i] = make_float4(t.x, t.x, -t.y, t.y);
+            }
+        }
     }
     if (tid == 0) {
         for (int g = 0; g < kRingGroups; g++) {
@@ -131,14 +144,16 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
             mbar_init(bar_empty(g), kFftWarps);
         }
         for (int s = 0; s < kInStages; s++) mbar_init(bar_in_full(s), 1);
+        for (int s = 0; s < kRingGroups * kGroup; s++) mbar_init(bar_ffull(s), kMacWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp < kMacWarps) {
+    const bool mac_role = (X & 4) ? (warp >= kFftWarps) : (warp < kMacWarps);
+    if (mac_role) {
         // =========================================================================== MAC warps
         asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-        const int j = tid;                                  // windows j, j+256, j+512, j+768
+        const int j = tid & (kMacThreads - 1);              // windows j, j+256, j+512, j+768
         PairState<L> s0, s1;                                // pairs (j, j+512) and (j+256, j+768)
         pair_load<L, kM>(s0, a.taps, a.hist, a.x, a.H, j, f_begin);
         pair_load<L, kM>(s1, a.taps, a.hist, a.x, a.H, j + 256, f_begin);
@@ -159,8 +174,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                 const int fg = (uu & 1) * 2;                // frame-in-group of this pair's even frame
                 if ((uu & 1) == 0) {
                     const uint32_t par = (uint32_t)(g >> 2) & 1u;
-                    mbar_wait(bar_in_full(gq), par);          // the group's 16 KB of input have landed
-                    mbar_wait(bar_empty(gq), par ^ 1u);       // the FFT warps are done with this X slot
+                    mbar_wait<(X & 8) != 0>(bar_in_full(gq), par);          // the group's 16 KB of input have landed
+                    mbar_wait<(X & 8) != 0>(bar_empty(gq), par ^ 1u);       // the FFT warps are done with this X slot
                 }
                 const uint32_t in_g = in_thr + (uint32_t)gq * kInStageBytes;
                 const uint32_t x_g = x_thr + (uint32_t)gq * (kGroup * kSlotStride * 8);
@@ -170,22 +185,35 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                 // ---- even local frame: the window pushed on even frames gets the new sample
                 s0.dA[uu] = lds64(in_g + fg * (kM2 * 8));
                 s1.dA[uu] = lds64(in_g + fg * (kM2 * 8) - 256 * 8);
+                if (X & 1) { o1 = s0.dA[uu]; o2 = s0.dB[(uu + 1) % L]; o3 = s1.dA[uu]; o4 = s1.dB[(uu + 1) % L]; }
+                else {
                 pair_mac<L, 0>(s0, uu, o1, o2);
                 pair_mac<L, 0>(s1, uu, o3, o4);
+                }
                 // o1/o3 belong to windows j, j+256 when the segment starts on an even frame (PAR0 = 0),
                 // to windows j+512, j+768 otherwise
                 if (PAR0 == 0) radix4_store(x_g + (uint32_t)fg * (kSlotStride * 8), o1, o3, o2, o4, t1, t2, t3);
                 else           radix4_store(x_g + (uint32_t)fg * (kSlotStride * 8), o2, o4, o1, o3, t1, t2, t3);
+                if (X & 16) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_ffull(gq * kGroup + fg));
+                }
 
                 // ---- odd local frame: the other window of each pair gets the new sample, branches swap
                 s0.dB[uu] = lds64(in_g + (fg + 1) * (kM2 * 8));
                 s1.dB[uu] = lds64(in_g + (fg + 1) * (kM2 * 8) - 256 * 8);
+                if (X & 1) { o1 = s0.dA[uu]; o2 = s0.dB[uu]; o3 = s1.dA[uu]; o4 = s1.dB[uu]; }
+                else {
                 pair_mac<L, 1>(s0, uu, o1, o2);
                 pair_mac<L, 1>(s1, uu, o3, o4);
+                }
                 if (PAR0 == 0) radix4_store(x_g + (uint32_t)(fg + 1) * (kSlotStride * 8), o1, o3, o2, o4, t1, t2, t3);
                 else           radix4_store(x_g + (uint32_t)(fg + 1) * (kSlotStride * 8), o2, o4, o1, o3, t1, t2, t3);
 
-                if (uu & 1) {
+                if (X & 16) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_ffull(gq * kGroup + fg + 1));
+                } else if (uu & 1) {
                     // group complete: publish it to the FFT warps (this also hands the input stage back:
                     // the producer refills stage gq only after full[gq] of this group has completed)
                     __syncwarp();
@@ -196,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
     } else {
         // =========================================================================== FFT warps
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        const int fwarp = warp - kMacWarps;                 // 0..7
+        const int fwarp = (X & 4) ? warp : warp - kMacWarps;   // 0..7
         const int f = fwarp >> 1;                           // frame-in-group handled by this warp pair
         const int h = fwarp & 1;                            // which half of the work
         // pass A: lane = (sub, r2): sub-problem p = 2h + sub, column r2
@@ -207,7 +235,9 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
         // pass B: lane = (k1 - 8h, p): row k1 = 8h + lane/4 of sub-problem p = lane % 4
         const int pB = lane & 3, k1B = 8 * h + (lane >> 2);
         const uint32_t offB = (uint32_t)(pB * kSubStride + k1B) * 8;           // + r2 * 17 * 8
-        const bool producer = (fwarp == 0 && lane == 0);    // streams the input, 4 groups ahead
+        // streams the input, 4 groups ahead (X & 16: a warp of the group's last frame, whose "full" barrier
+        // completes when every MAC warp has read the whole input stage)
+        const bool producer = (fwarp == ((X & 16) ? 6 : 0) && lane == 0);
         auto fetch_group = [&](int gg) {
             // 4 consecutive frames are contiguous in the stream: one 16 KB bulk copy
             const int st = gg & (kInStages - 1);
@@ -220,7 +250,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
         }
         for (int g = 0; g < n_groups; g++) {
             const int gs = g & (kRingGroups - 1);
-            mbar_wait(bar_full(gs), (uint32_t)(g >> 2) & 1u);
+            if (X & 16) mbar_wait<(X & 8) != 0>(bar_ffull(gs * kGroup + f), (uint32_t)(g >> 2) & 1u);
+            else        mbar_wait<(X & 8) != 0>(bar_full(gs), (uint32_t)(g >> 2) & 1u);
             // every MAC warp has finished group g, so input stage gs is free again
             if (producer && g + kInStages < n_groups) fetch_group(g + kInStages);
             const uint32_t slot = s_x + (uint32_t)(gs * kGroup + f) * (kSlotStride * 8);
@@ -229,9 +260,18 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
             // pass A: 16-point DFT down the column r2 of sub-problem pA, then twiddle W256^(r2 k1)
 #pragma unroll
             for (int r1 = 0; r1 < 16; r1++) v[r1] = lds64(slot + offA + (uint32_t)(r1 * 17) * 8);
+            if (!(X & 2)) {
             RegDft<16, +1>::run(v);
 #pragma unroll
-            for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul2(v[k1], lds64(tw_lane + k1 * 128));
+            for (int k1 = 1; k1 < 16; k1++) {
+                if (X & 32) {
+                    const float4 t = lds128(s_base + kOffTwQ + (uint32_t)(k1 * 16 + r2) * 16);
+                    v[k1] = __ffma2_rn(make_float2(t.z, t.w), make_float2(v[k1].y, v[k1].x), __fmul2_rn(make_float2(t.x, t.y), v[k1]));
+                } else {
+                    v[k1] = cmul2(v[k1], lds64(tw_lane + k1 * 128));
+                }
+            }
+            }
             __syncwarp();                                   // both sub-problems of this warp fully read
             // transposed store: row r2, column k1 (conflict-free: lanes are 17 units apart)
 #pragma unroll
@@ -241,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
             // pass B: row k1 of sub-problem pB: 16-point DFT over r2 -> Y[4 (k1 + 16 k2) + p]
 #pragma unroll
             for (int q = 0; q < 16; q++) v[q] = lds64(slot + offB + (uint32_t)(q * 17) * 8);
-            RegDft<16, +1>::run(v);
+            if (!(X & 2)) RegDft<16, +1>::run(v);
             // the slot has been consumed (the DFT above needed every loaded value)
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty(gs));
@@ -264,6 +304,16 @@ void launch_L(const FusedArgs &a, int par0, unsigned int grid, cudaStream_t st)
     else      pfbch2_fused_1024_kernel<L, 0><<<grid, kThreads, kSmemBytes, st>>>(a);
     LC_LAUNCH_CHECK();
 }
+
+#ifdef LC_FUSED_EXPERIMENTS
+template <int X>
+void launch_X(const FusedArgs &a, unsigned int grid, cudaStream_t st)
+{
+    LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_fused_1024_kernel<14, 0, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    pfbch2_fused_1024_kernel<14, 0, X><<<grid, kThreads, kSmemBytes, st>>>(a);
+    LC_LAUNCH_CHECK();
+}
+#endif
 
 }  // namespace
 
@@ -318,6 +368,28 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
     a.n_groups = (int)n_groups;
     a.groups_per_cta = (int)per;
     g_last_chunk_frames.store((unsigned long long)per * kGroup);
+#ifdef LC_FUSED_EXPERIMENTS
+    if (const char *env = getenv("LIQUID_CUDA_FUSED_X")) {
+        const int x = atoi(env);
+        if (x && L == 14 && !(parity0 & 1)) {
+            switch (x) {
+            case 1: launch_X<1>(a, (unsigned int)ctas, st); break;
+            case 2: launch_X<2>(a, (unsigned int)ctas, st); break;
+            case 3: launch_X<3>(a, (unsigned int)ctas, st); break;
+            case 4: launch_X<4>(a, (unsigned int)ctas, st); break;
+            case 8: launch_X<8>(a, (unsigned int)ctas, st); break;
+            case 12: launch_X<12>(a, (unsigned int)ctas, st); break;
+            case 56: launch_X<56>(a, (unsigned int)ctas, st); break;
+            case 48: launch_X<48>(a, (unsigned int)ctas, st); break;
+            case 32: launch_X<32>(a, (unsigned int)ctas, st); break;
+            case 24: launch_X<24>(a, (unsigned int)ctas, st); break;
+            case 16: launch_X<16>(a, (unsigned int)ctas, st); break;
+            default: fatal("launch_pfbch2_fused", "unknown experiment");
+            }
+            return n_groups * kGroup;
+        }
+    }
+#endif
     switch (L) {
     case 4: launch_L<4>(a, parity0 & 1, (unsigned int)ctas, st); break;
     case 8: launch_L<8>(a, parity0 & 1, (unsigned int)ctas, st); break;
