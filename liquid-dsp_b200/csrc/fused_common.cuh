@@ -23,33 +23,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
-template <bool HINT = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    if (HINT) {
-        // suspend-time hint: the warp sleeps in the barrier unit until the phase completes or ~the hint (ns) elapses
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "WAIT_LOOP:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-            "@p bra WAIT_DONE;\n\t"
-            "bra WAIT_LOOP;\n\t"
-            "WAIT_DONE:\n\t"
-            "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "WAIT_LOOP:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-            "@p bra WAIT_DONE;\n\t"
-            "bra WAIT_LOOP;\n\t"
-            "WAIT_DONE:\n\t"
-            "}" ::"r"(bar), "r"(parity)
-            : "memory");
-    }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)

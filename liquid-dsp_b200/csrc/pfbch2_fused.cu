@@ -19,13 +19,19 @@
 //                                16 points in registers, radix-2 DIT butterflies with constant twiddles
 //                                in packed FP32x2 arithmetic (3 instructions per general butterfly), one
 //                                transposition through the frame slot (rows of 16 padded to 17), inter-
-//                                pass twiddles from a shared 16x16 table, then 16 coalesced 256-byte row
-//                                stores per thread straight to HBM.
+//                                pass twiddles from a shared 16x16 table of {c, c, -s, s} (a complex
+//                                product is then two packed instructions on register pairs as they are
+//                                loaded: no register moves), then 16 coalesced 256-byte row stores per
+//                                thread straight to HBM.  Each FRAME slot of the X ring has its own
+//                                "full" barrier, so the warp pairs of the four frames of a group start
+//                                one frame time apart and the two FFT warps of a sub-partition run half a
+//                                group period out of phase (one in its arithmetic while the other waits
+//                                for shared memory).
 //   input                        one lane of the first FFT warp streams the input with cp.async.bulk
 //                                (TMA engine): one 16 KB copy per group of 4 frames, four groups
 //                                ahead, into a 4-stage ring; completion is counted in bytes on an
 //                                mbarrier.  A stage is refilled once every MAC warp has published the
-//                                group that read it, so no second barrier is needed.
+//                                last frame of the group that read it, so no second barrier is needed.
 //
 // FP32 pipe and shared-memory pipe work of the two roles overlap by construction (the warp
 // scheduler interleaves them); per input sample the kernel reads 8 B and writes 16 B of HBM.
@@ -57,13 +63,16 @@ constexpr int kInStageBytes = kGroup * kM2 * 8;                // 4 frames x 512
 
 // shared memory carve-up (bytes)
 constexpr int kOffTw4 = 0;                                     // float2 tw4[3][256]: W1024^(j p), p = 1..3
-constexpr int kOffTw16 = kOffTw4 + 3 * 256 * 8;                // float2 tw16[16][16]: W256^(k1 r2)
-constexpr int kOffX = kOffTw16 + 16 * 16 * 8;                  // X ring
+constexpr int kOffX = kOffTw4 + 3 * 256 * 8;                   // X ring
 constexpr int kOffIn = kOffX + kRingGroups * kGroup * kSlotStride * 8;
-constexpr int kOffTwQ = kOffIn + kInStages * kInStageBytes;    // float4 twq[16][16]: {c, c, -s, s} of tw16 (experiment 32)
-constexpr int kOffBar = kOffTwQ + 16 * 16 * 16;
-constexpr int kNumBars = 2 * kRingGroups + kInStages + kRingGroups * kGroup;
+// (the 16x16 table sits behind the rings: placed directly behind tw4 the kernel measured 3 % slower, the position of
+// the rings themselves makes no difference -- profiles/r02_fused_smem_layout_search.log)
+constexpr int kOffTw16 = kOffIn + kInStages * kInStageBytes;   // float4 tw16[16][16]: {c, c, -s, s} of W256^(k1 r2)
+constexpr int kOffBar = kOffTw16 + 16 * 16 * 16;
+constexpr int kSlots = kRingGroups * kGroup;                   // frame slots of the X ring
+constexpr int kNumBars = kSlots + kRingGroups + kInStages;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 // ---------------------------------------------------------------------------------- the kernel
 struct FusedArgs {
@@ -71,7 +80,7 @@ struct FusedArgs {
     const float2 *x;           // segment input
     float2 *y;                 // [n_frames][1024]
     const float *taps;         // [2][L][1024] as in firpfbch2.cu, pre-scaled by 1/M
-    const float2 *tw;          // tw4[3][256] followed by tw16[16][16]
+    const float2 *tw;          // tw4[3][256] (float2) followed by tw16[16][16] as {c, c, -s, s} (float4)
     int H;
     int n_groups;              // groups of 4 frames in the segment
     int groups_per_cta;
@@ -97,24 +106,27 @@ __device__ __forceinline__ void radix4_store(uint32_t slot, float2 a0, float2 a1
     sts64(slot + 3 * (kSubStride * 8), cmul2(u3, t3));
 }
 
+// a * t with t given as {c, c, -s, s}: two packed instructions on the register pairs as loaded
+__device__ __forceinline__ float2 cmulq(float2 a, float4 t)
+{
+    return __ffma2_rn(make_float2(t.z, t.w), make_float2(a.y, a.x), __fmul2_rn(make_float2(t.x, t.y), a));
+}
+
 template <int L, int PAR0, int X = 0>
 __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const FusedArgs a)
 {
-    // X: experiment switches (profiling only; X = 0 is the product kernel)
-    //   1 MAC warps skip the dot products   2 FFT warps skip the DFT arithmetic   4 roles swapped (FFT warps 0..7)
-    //   8 waits use a suspend-time hint   16 one "full" barrier per frame instead of per group (FFT warps of the
-    //   four frames of a group start one frame time apart)   32 FFT warps read {c, c, -s, s} twiddles (no MOVs)
+    // X: profiling switches, compiled with -DLC_FUSED_EXPERIMENTS only (X = 0 is the product kernel):
+    //   1 the MAC warps skip the dot products, 2 the FFT warps skip the DFT arithmetic -- what each role costs alone
     constexpr int P = L / 2;                               // groups per period
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_x = s_base + kOffX;
     const uint32_t s_in = s_base + kOffIn;
     const uint32_t s_bar = s_base + kOffBar;
-    // barriers: X ring full[g] / empty[g], input ring in_full[s]
-    auto bar_full = [&](int g) { return s_bar + 8u * g; };
-    auto bar_empty = [&](int g) { return s_bar + 8u * (kRingGroups + g); };
-    auto bar_in_full = [&](int s) { return s_bar + 8u * (2 * kRingGroups + s); };
-    auto bar_ffull = [&](int slot) { return s_bar + 8u * (2 * kRingGroups + kInStages + slot); };   // X & 16: per frame slot
+    // barriers: X ring full[frame slot] / empty[group], input ring in_full[stage]
+    auto bar_full = [&](int slot) { return s_bar + 8u * slot; };
+    auto bar_empty = [&](int g) { return s_bar + 8u * (kSlots + g); };
+    auto bar_in_full = [&](int s) { return s_bar + 8u * (kSlots + kRingGroups + s); };
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -128,32 +140,22 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
 
     // ---- one-time setup
     {
-        float2 *tw_s = reinterpret_cast<float2 *>(smem + kOffTw4);
-        for (int i = tid; i < 3 * 256 + 16 * 16; i += kThreads) tw_s[i] = a.tw[i];
-        if (X & 32) {
-            float4 *twq = reinterpret_cast<float4 *>(smem + kOffTwQ);
-            for (int i = tid; i < 16 * 16; i += kThreads) {
-                const float2 t = a.tw[3 * 256 + i];
-                twq[i] = make_float4(t.x, t.x, -t.y, t.y);
-            }
-        }
+        float2 *tw_s = reinterpret_cast<float2 *>(smem + kOffTw4), *twq_s = reinterpret_cast<float2 *>(smem + kOffTw16);
+        for (int i = tid; i < 3 * 256; i += kThreads) tw_s[i] = a.tw[i];
+        for (int i = tid; i < 2 * 16 * 16; i += kThreads) twq_s[i] = a.tw[3 * 256 + i];
     }
     if (tid == 0) {
-        for (int g = 0; g < kRingGroups; g++) {
-            mbar_init(bar_full(g), kMacWarps);
-            mbar_init(bar_empty(g), kFftWarps);
-        }
+        for (int sl = 0; sl < kSlots; sl++) mbar_init(bar_full(sl), kMacWarps);
+        for (int g = 0; g < kRingGroups; g++) mbar_init(bar_empty(g), kFftWarps);
         for (int s = 0; s < kInStages; s++) mbar_init(bar_in_full(s), 1);
-        for (int s = 0; s < kRingGroups * kGroup; s++) mbar_init(bar_ffull(s), kMacWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    const bool mac_role = (X & 4) ? (warp >= kFftWarps) : (warp < kMacWarps);
-    if (mac_role) {
+    if (warp < kMacWarps) {
         // =========================================================================== MAC warps
         asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-        const int j = tid & (kMacThreads - 1);              // windows j, j+256, j+512, j+768
+        const int j = tid;                                  // windows j, j+256, j+512, j+768
         PairState<L> s0, s1;                                // pairs (j, j+512) and (j+256, j+768)
         pair_load<L, kM>(s0, a.taps, a.hist, a.x, a.H, j, f_begin);
         pair_load<L, kM>(s1, a.taps, a.hist, a.x, a.H, j + 256, f_begin);
@@ -174,8 +176,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                 const int fg = (uu & 1) * 2;                // frame-in-group of this pair's even frame
                 if ((uu & 1) == 0) {
                     const uint32_t par = (uint32_t)(g >> 2) & 1u;
-                    mbar_wait<(X & 8) != 0>(bar_in_full(gq), par);          // the group's 16 KB of input have landed
-                    mbar_wait<(X & 8) != 0>(bar_empty(gq), par ^ 1u);       // the FFT warps are done with this X slot
+                    mbar_wait(bar_in_full(gq), par);          // the group's 16 KB of input have landed
+                    mbar_wait(bar_empty(gq), par ^ 1u);       // the FFT warps are done with this group of X slots
                 }
                 const uint32_t in_g = in_thr + (uint32_t)gq * kInStageBytes;
                 const uint32_t x_g = x_thr + (uint32_t)gq * (kGroup * kSlotStride * 8);
@@ -194,10 +196,9 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                 // to windows j+512, j+768 otherwise
                 if (PAR0 == 0) radix4_store(x_g + (uint32_t)fg * (kSlotStride * 8), o1, o3, o2, o4, t1, t2, t3);
                 else           radix4_store(x_g + (uint32_t)fg * (kSlotStride * 8), o2, o4, o1, o3, t1, t2, t3);
-                if (X & 16) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_ffull(gq * kGroup + fg));
-                }
+                // frame complete: publish it to its two FFT warps
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full(gq * kGroup + fg));
 
                 // ---- odd local frame: the other window of each pair gets the new sample, branches swap
                 s0.dB[uu] = lds64(in_g + (fg + 1) * (kM2 * 8));
@@ -210,34 +211,29 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
                 if (PAR0 == 0) radix4_store(x_g + (uint32_t)(fg + 1) * (kSlotStride * 8), o1, o3, o2, o4, t1, t2, t3);
                 else           radix4_store(x_g + (uint32_t)(fg + 1) * (kSlotStride * 8), o2, o4, o1, o3, t1, t2, t3);
 
-                if (X & 16) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_ffull(gq * kGroup + fg + 1));
-                } else if (uu & 1) {
-                    // group complete: publish it to the FFT warps (this also hands the input stage back:
-                    // the producer refills stage gq only after full[gq] of this group has completed)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_full(gq));
-                }
+                // (the last frame of a group also hands the input stage back: the producer refills stage gq
+                // only after this barrier has completed)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full(gq * kGroup + fg + 1));
             }
         }
     } else {
         // =========================================================================== FFT warps
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        const int fwarp = (X & 4) ? warp : warp - kMacWarps;   // 0..7
+        const int fwarp = warp - kMacWarps;                 // 0..7
         const int f = fwarp >> 1;                           // frame-in-group handled by this warp pair
         const int h = fwarp & 1;                            // which half of the work
         // pass A: lane = (sub, r2): sub-problem p = 2h + sub, column r2
         const int pA = 2 * h + (lane >> 4), r2 = lane & 15;
         const uint32_t offA = (uint32_t)(pA * kSubStride + r2) * 8;           // + r1 * 17 * 8 (loads)
         const uint32_t offAt = (uint32_t)(pA * kSubStride + r2 * 17) * 8;      // + k1 * 8 (transposed stores)
-        const uint32_t tw_lane = s_base + kOffTw16 + (uint32_t)r2 * 8;         // tw16[k1][r2] at + k1 * 128
+        const uint32_t tw_lane = s_base + kOffTw16 + (uint32_t)r2 * 16;        // tw16[k1][r2] at + k1 * 256
         // pass B: lane = (k1 - 8h, p): row k1 = 8h + lane/4 of sub-problem p = lane % 4
         const int pB = lane & 3, k1B = 8 * h + (lane >> 2);
         const uint32_t offB = (uint32_t)(pB * kSubStride + k1B) * 8;           // + r2 * 17 * 8
-        // streams the input, 4 groups ahead (X & 16: a warp of the group's last frame, whose "full" barrier
-        // completes when every MAC warp has read the whole input stage)
-        const bool producer = (fwarp == ((X & 16) ? 6 : 0) && lane == 0);
+        // one lane of the LAST frame's warp pair streams the input, 4 groups ahead: that frame's "full" barrier
+        // completes when every MAC warp has finished the group, i.e. has read the whole input stage
+        const bool producer = (fwarp == 2 * (kGroup - 1) && lane == 0);
         auto fetch_group = [&](int gg) {
             // 4 consecutive frames are contiguous in the stream: one 16 KB bulk copy
             const int st = gg & (kInStages - 1);
@@ -250,9 +246,8 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
         }
         for (int g = 0; g < n_groups; g++) {
             const int gs = g & (kRingGroups - 1);
-            if (X & 16) mbar_wait<(X & 8) != 0>(bar_ffull(gs * kGroup + f), (uint32_t)(g >> 2) & 1u);
-            else        mbar_wait<(X & 8) != 0>(bar_full(gs), (uint32_t)(g >> 2) & 1u);
-            // every MAC warp has finished group g, so input stage gs is free again
+            mbar_wait(bar_full(gs * kGroup + f), (uint32_t)(g >> 2) & 1u);
+            // (producer: every MAC warp has finished group g, so input stage gs is free again)
             if (producer && g + kInStages < n_groups) fetch_group(g + kInStages);
             const uint32_t slot = s_x + (uint32_t)(gs * kGroup + f) * (kSlotStride * 8);
 
@@ -263,14 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) pfbch2_fused_1024_kernel(const Fu
             if (!(X & 2)) {
             RegDft<16, +1>::run(v);
 #pragma unroll
-            for (int k1 = 1; k1 < 16; k1++) {
-                if (X & 32) {
-                    const float4 t = lds128(s_base + kOffTwQ + (uint32_t)(k1 * 16 + r2) * 16);
-                    v[k1] = __ffma2_rn(make_float2(t.z, t.w), make_float2(v[k1].y, v[k1].x), __fmul2_rn(make_float2(t.x, t.y), v[k1]));
-                } else {
-                    v[k1] = cmul2(v[k1], lds64(tw_lane + k1 * 128));
-                }
-            }
+            for (int k1 = 1; k1 < 16; k1++) v[k1] = cmulq(v[k1], lds128(tw_lane + k1 * 256));
             }
             __syncwarp();                                   // both sub-problems of this warp fully read
             // transposed store: row r2, column k1 (conflict-free: lanes are 17 units apart)
@@ -327,8 +315,9 @@ bool fused_pfbch2_supported(unsigned int M, unsigned int L)
 
 void fused_pfbch2_make_twiddles(std::vector<float2> &tw)
 {
-    // tw4[p-1][j] = e^{+j 2 pi j p / 1024}, p = 1..3, j < 256; then tw16[k1][r2] = e^{+j 2 pi k1 r2 / 256}
-    tw.resize(3 * 256 + 16 * 16);
+    // tw4[p-1][j] = e^{+j 2 pi j p / 1024}, p = 1..3, j < 256; then tw16[k1][r2] = e^{+j 2 pi k1 r2 / 256} = c + j s
+    // stored as the four floats {c, c, -s, s}: (c, c) * a + (-s, s) * swap(a) is the complex product
+    tw.resize(3 * 256 + 2 * 16 * 16);
     for (int p = 1; p <= 3; p++)
         for (int j = 0; j < 256; j++) {
             double ang = 2.0 * M_PI * (double)(j * p) / 1024.0;
@@ -337,7 +326,9 @@ void fused_pfbch2_make_twiddles(std::vector<float2> &tw)
     for (int k1 = 0; k1 < 16; k1++)
         for (int r2 = 0; r2 < 16; r2++) {
             double ang = 2.0 * M_PI * (double)(k1 * r2) / 256.0;
-            tw[3 * 256 + k1 * 16 + r2] = make_float2((float)cos(ang), (float)sin(ang));
+            const float c = (float)cos(ang), sn = (float)sin(ang);
+            tw[3 * 256 + 2 * (k1 * 16 + r2)] = make_float2(c, c);
+            tw[3 * 256 + 2 * (k1 * 16 + r2) + 1] = make_float2(-sn, sn);
         }
 }
 
@@ -376,14 +367,6 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
             case 1: launch_X<1>(a, (unsigned int)ctas, st); break;
             case 2: launch_X<2>(a, (unsigned int)ctas, st); break;
             case 3: launch_X<3>(a, (unsigned int)ctas, st); break;
-            case 4: launch_X<4>(a, (unsigned int)ctas, st); break;
-            case 8: launch_X<8>(a, (unsigned int)ctas, st); break;
-            case 12: launch_X<12>(a, (unsigned int)ctas, st); break;
-            case 56: launch_X<56>(a, (unsigned int)ctas, st); break;
-            case 48: launch_X<48>(a, (unsigned int)ctas, st); break;
-            case 32: launch_X<32>(a, (unsigned int)ctas, st); break;
-            case 24: launch_X<24>(a, (unsigned int)ctas, st); break;
-            case 16: launch_X<16>(a, (unsigned int)ctas, st); break;
             default: fatal("launch_pfbch2_fused", "unknown experiment");
             }
             return n_groups * kGroup;
