@@ -10,7 +10,14 @@ A step is one pass of firpfbch2_crcf analysis (M=1024, m=7, As=60 dB Kaiser prot
 already resident in HBM for `value`.  With N>1 the N segments are consecutive time segments of ONE
 long stream: every step each rank sends the last 2mM input samples of its segment to its right
 neighbour with NCCL send/recv (the filter-history halo), the interior frames run while the halo is in
-flight.  Weak scaling: per-GPU work is fixed.
+flight -- all inside the C entry point firpfbch2_crcf_execute_sharded_dev (csrc/multi.cu); torch.distributed
+only carries the rendezvous (the NCCL unique id), the barrier and the max-over-ranks of the timing.  Weak
+scaling: per-GPU work is fixed.  After the timed region every rank > 0 checks its halo and its halo-dependent
+frames bit for bit ("halo_parity"); a mismatch fails the run.
+
+--workload c2 / c4 run BASELINE.json configs[1] / configs[3] instead, sharded by STREAM across the ranks (no
+collective); at N=1 the default run also measures configs 1, 2, 4, 5 briefly after the timed region and
+reports them under "other_configs" (same code as tools/bench_configs.py).
 
 `e2e` is the same metric through the host-pointer C ABI call firpfbch2_crcf_execute_block with
 pinned host buffers: H2D of the input and D2H of the channelised output inside the timed region.
@@ -33,9 +40,9 @@ if ROOT not in sys.path:
 M, SEMI, AS = 1024, 7, 60.0
 BYTES_PER_SAMPLE = 24            # algorithmic: 8 B read + 16 B written per input sample
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel from one `ncu --set full` capture
-# (profiles/r01_ncu_fused_v7_summary.txt: 1.090287 GB + 2.090002 GB for 2^27 samples) -> bytes per sample
-NCU_DRAM_BYTES_PER_SAMPLE = (1.090287e9 + 2.090002e9) / (1 << 27)
-NCU_SOURCE = "profiles/r01_ncu_fused_v7_summary.txt"
+# (profiles/r02_ncu_fused_v9_summary.txt: 1.090297 GB + 2.088802 GB for 2^27 samples) -> bytes per sample
+NCU_DRAM_BYTES_PER_SAMPLE = (1.090297e9 + 2.088802e9) / (1 << 27)
+NCU_SOURCE = "profiles/r02_ncu_fused_v9_summary.txt"
 NCU_LOG2 = 27
 KERNEL = "pfbch2_fused_1024_kernel<14,0> (fused polyphase MAC + 1024-point IFFT)"
 METRIC = "firpfbch2_crcf analysis M=1024 m=7 input throughput"
@@ -190,6 +197,113 @@ def impl_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
+# stream-sharded workloads (BASELINE.json configs[1] and configs[3]): no collective on the data path
+# --------------------------------------------------------------------------------------------
+def main_streams(args):
+    import torch
+    import torch.distributed as dist
+    import liquid_dsp_b200 as L
+    import liquid_dsp_b200.multi as multi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    L.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    st = torch.cuda.current_stream()
+    if args.workload == "c2":
+        total_streams, n, bytes_per_sample = 1024, 1 << 20, 16
+        metric = "firfilt_crcf_execute_block 64-tap Kaiser low-pass input throughput"
+        lo, hi = multi.streams_of_rank(total_streams, rank, world)
+        ns = hi - lo
+        q = L.firfilt_crcf.create_kaiser(64, 0.25, 60.0, 0.0)
+        x = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+        for s_i in range(ns):       # stream s of the job has its own seed
+            L.synth_input_dev(x.data_ptr() + 8 * s_i * n, n, seed=0x5EED0000 + lo + s_i, stream=st.cuda_stream)
+
+        def step():
+            q.execute_streams_dev(x.data_ptr(), ns, n, y.data_ptr(), st.cuda_stream)
+        workload = ("firfilt_crcf 64 taps (Kaiser, fc=0.25, As=60), %d independent streams x 2^20 samples, sharded by stream over "
+                    "%d GPU(s): %d streams on rank 0" % (total_streams, world, ns))
+        kernel = "firfilt_regblock_kernel<64,16>"
+    else:
+        total_streams, n, bytes_per_sample = 256, 1 << 22, 32
+        Mc, mc = 256, 5
+        metric = "firpfbch_crcf synthesis+analysis round trip M=256 m=5 input throughput"
+        lo, hi = multi.streams_of_rank(total_streams, rank, world)
+        ns = hi - lo
+        qs = L.firpfbch_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, Mc, mc, 60.0)
+        qa = L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, Mc, mc, 60.0)
+        x = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+        t = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+        y = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+        for s_i in range(ns):
+            L.synth_input_dev(x.data_ptr() + 8 * s_i * n, n, seed=0x5EED0000 + lo + s_i, stream=st.cuda_stream)
+
+        def step():
+            qs.execute_streams_dev(x.data_ptr(), ns, n // Mc, t.data_ptr(), st.cuda_stream)
+            qa.execute_streams_dev(t.data_ptr(), ns, n // Mc, y.data_ptr(), st.cuda_stream)
+        workload = ("firpfbch_crcf synthesis then analysis, M=256 m=5 As=60, %d independent streams x 2^22 samples, sharded by "
+                    "stream over %d GPU(s): %d streams on rank 0" % (total_streams, world, ns))
+        kernel = "pfbch_synth_fused_256_kernel<10> + pfbch_fused_256_kernel<10> (two API calls per step)"
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 0)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank, period=0.002 if world == 1 else 0.010) if rank == 0 else None
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.start()
+    time.sleep(0.05)
+    sync_all()
+    if sampler:
+        sampler.arm()
+    e0.record(st)
+    for _ in range(args.steps):
+        step()
+    e1.record(st)
+    sync_all()
+    clocks = sampler.stop() if sampler else None
+    launches = L.launch_count() - launches0
+    local_ms = e0.elapsed_time(e1)
+    total_ms = local_ms
+    if world > 1:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    value = total_streams * n * args.steps / (total_ms * 1e-3) / 1e6
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    achieved = bytes_per_sample * ns * n * args.steps / (local_ms * 1e-3) / 1e9
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "l2": "inputs larger than L2 per GPU per step, no flush needed",
+                           "timing": "CUDA events on the launching stream, max over ranks",
+                           "sharding": "by stream, contiguous blocks per rank (liquid_dsp_b200.multi.streams_of_rank), no collective"},
+                "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": kernel, "algorithmic_bytes_per_sample": bytes_per_sample,
+                             "note": "rank 0's share of the job / rank 0's event time"},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
 def main():
@@ -208,9 +322,19 @@ def main():
     ap.add_argument("--debug-steps", action="store_true", help="N>1: print every rank's per-step times to stderr")
     ap.add_argument("--reserve-sms", type=int, default=2,
                     help="N>1 only: SMs the persistent kernel leaves to the NCCL kernels and the halo launch")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
-                    help="c3 = headline (M=1024, m=7); c5 = BASELINE.json configs[4] (M=4096, m=9)")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5", "c2", "c4"],
+                    help="c3 = headline (M=1024, m=7); c5 = BASELINE.json configs[4] (M=4096, m=9), both time-sharded; "
+                         "c2 / c4 = configs[1] / configs[3], sharded by stream")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the brief runs of configs 1, 2, 4, 5 (N=1 only)")
+    ap.add_argument("--other-steps", type=int, default=3)
+    ap.add_argument("--python-exchange", action="store_true",
+                    help="N>1: the round-1 path (torch.distributed send/recv driven from Python) instead of the C driver")
     args = ap.parse_args()
+    if args.workload in ("c2", "c4"):
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm times the headline workload only"}))
+            return 0
+        return main_streams(args)
     select_workload(args.workload)
     if args.impl == "reference":
         return impl_reference(args)
@@ -265,11 +389,21 @@ def main():
     # channelizer kernel leaves two SMs free (--reserve-sms), so that the NCCL send/recv kernels and the
     # small halo launch run BESIDE the interior frames instead of queueing behind a kernel that owns every SM
     side = torch.cuda.Stream(device=dev) if world > 1 else None
-    if world > 1:
+    comm = None
+    if world > 1 and args.python_exchange:
         L.set_reserved_sms(args.reserve_sms)
+    elif world > 1:
+        # the C multi-GPU driver: rank 0 makes the NCCL unique id, torch.distributed carries it to the others
+        ids = [L.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = L.Comm(rank, world, ids[0])
+        if args.reserve_sms != 2:
+            L.set_reserved_sms(args.reserve_sms)
 
     def step():
-        if world > 1:
+        if comm is not None:
+            q.execute_sharded_dev(comm, d_halo, first_frame, n_frames, d_y, stream.cuda_stream)
+        elif world > 1:
             with torch.cuda.stream(side):
                 reqs = multi.exchange_halo(dist, head, tail, rank, world)      # NCCL send/recv of 2mM samples
             # interior frames do not see the halo: run them while it is in flight
@@ -323,6 +457,36 @@ def main():
         total_ms = float(t.item())
     value = world * n * args.steps / (total_ms * 1e-3) / 1e6          # MS/s, whole job
 
+    # multi-GPU parity, checked on the buffers the timed steps left behind: (1) the head-room holds the left
+    # neighbour's last 2mM samples bit for bit (the input is counter-based, so the rank regenerates them);
+    # (2) the 4m halo-dependent frames equal, bit for bit, the same launch over the regenerated halo; (3) the
+    # first 8m frames agree with ONE single-GPU segment that starts 4m frames inside the left neighbour's range
+    # (different kernels take part -- the fused kernel there, the shape-generic one for the short halo launch --
+    # so this last comparison is to 2e-6 of the output scale, not bitwise)
+    halo_parity = None
+    if world > 1:
+        ok = True
+        if rank > 0:
+            z = torch.empty(2 * 4 * H, dtype=torch.float32, device=dev)          # stream[rank*n - 2H, rank*n + 2H)
+            L.synth_input_dev(z.data_ptr(), 4 * H, seed=0x5EED0000, first=rank * n - 2 * H, stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            ok &= bool(torch.equal(z[2 * H: 4 * H].view(torch.int32), xbuf[: 2 * H].view(torch.int32)))
+            yh = torch.empty(2 * halo_frames * M, dtype=torch.float32, device=dev)
+            q.execute_segment_dev(z.data_ptr() + 8 * H, d_x, first_frame, halo_frames, yh.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            ok &= bool(torch.equal(yh.view(torch.int32), ybuf[: 2 * halo_frames * M].view(torch.int32)))
+            ym = torch.empty(2 * 3 * halo_frames * M, dtype=torch.float32, device=dev)
+            q.execute_segment_dev(z.data_ptr(), z.data_ptr() + 8 * H, first_frame - halo_frames, 3 * halo_frames,
+                                  ym.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            ref = ym[2 * halo_frames * M:]
+            got = ybuf[: 2 * 2 * halo_frames * M]
+            ok &= bool((ref - got).abs().max().item() <= 2e-6 * max(ref.abs().max().item(), 1e-30))
+            del z, yh, ym
+        t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        halo_parity = bool(t.item() > 0.5)
+
     # roofline of the dominant kernel: algorithmic bytes per launch / average launch duration.
     # One step on one GPU is one pass of the fused channelizer kernel(s) over n samples; the
     # duration is the CUDA-event time of the step on the launching stream (this rank).
@@ -347,34 +511,102 @@ def main():
     # end to end through the host-pointer C ABI (pinned host buffers, copies inside the timed region)
     e2e = None
     if not args.no_e2e:
+        import ctypes as C
+        import numpy as np
         ne = 1 << args.e2e_log2_samples
         nfe = ne // (M // 2)
         hx = L.pinned_empty(ne)
         hy = L.pinned_empty(nfe * M)
-        # fill the pinned input with the same synthetic stream (generated on the device, copied back)
-        import ctypes as C
-        L.synth_input_dev(d_x, min(ne, n), seed=0x5EED0000, first=rank * n, stream=stream.cuda_stream)
+        # fill the pinned input with this rank's part of the synthetic stream (generated on the device, copied back)
+        L.synth_input_dev(d_x, min(ne, n), seed=0x5EED0000, first=rank * ne, stream=stream.cuda_stream)
         torch.cuda.synchronize()
         L.lib.liquid_cuda_memcpy_d2h(hx.ctypes.data_as(C.c_void_p), d_x, min(ne, n) * 8)
         qe = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, SEMI, AS)
-        qe.execute_block(hx, out=hy)                        # warm-up (allocates staging buffers)
+
+        def e2e_step(x, y):
+            # N > 1: the ranks' host arrays are consecutive segments of one stream; the C driver moves the halo
+            if comm is not None:
+                qe.execute_sharded(comm, x, rank * nfe, out=y)
+            else:
+                qe.reset()
+                qe.execute_block(x, out=y)
+
+        def e2e_time(x, y, steps):
+            e2e_step(x, y)                                   # warm-up (allocates staging buffers)
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_step(x, y)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return world * ne * steps / dt / 1e6
+
+        v_pinned = e2e_time(hx, hy, args.e2e_steps)
+        # what the link gives on its own: one pinned D2H copy of the output / H2D copy of the input, nothing else running
+        def copy_rate(nbytes, d2h):
+            torch.cuda.synchronize()
+            best = 0.0
+            for _ in range(3):
+                t0 = time.perf_counter()
+                if d2h:
+                    L.lib.liquid_cuda_memcpy_d2h(hy.ctypes.data_as(C.c_void_p), d_y, nbytes)
+                else:
+                    L.lib.liquid_cuda_memcpy_h2d(d_x, hx.ctypes.data_as(C.c_void_p), nbytes)
+                best = max(best, nbytes / (time.perf_counter() - t0) / 1e9)
+            return best
+        probe_bytes = min(ne * 8, 1 << 30)
         sync_all()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            qe.execute_block(hx, out=hy)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * ne * args.e2e_steps / dt / 1e6, "unit": UNIT,
+        d2h_alone, h2d_alone = copy_rate(probe_bytes, True), copy_rate(probe_bytes, False)
+        d2h_rate = (v_pinned / world) * 1e6 * 16 / 1e9       # GB/s of channelised output per GPU
+        e2e = {"value": v_pinned, "unit": UNIT,
                "h2d_bytes_per_step": ne * 8, "d2h_bytes_per_step": nfe * M * 8,
                "samples_per_step_per_gpu": ne, "steps": args.e2e_steps,
-               "api": "firpfbch2_crcf_execute_block (host pointers, pinned, chunked H2D/compute/D2H pipeline)"}
+               "api": ("firpfbch2_crcf_execute_sharded (host pointers, pinned; NCCL halo, then the chunked pipeline)"
+                       if comm is not None else
+                       "firpfbch2_crcf_execute_block (host pointers, pinned, chunked H2D/compute/D2H pipeline)"),
+               "link": {"d2h_alone_GBps": d2h_alone, "h2d_alone_GBps": h2d_alone, "d2h_achieved_GBps_per_gpu": d2h_rate,
+                        "note": "all ranks probe at the same time" if world > 1 else "single copy, idle machine"},
+               "link_frac": d2h_rate / d2h_alone if d2h_alone > 0 else None}
+        if world == 1:
+            # a caller's malloc'd arrays: page-locked for the duration of each call (default) or plain pageable copies
+            px, py = np.empty(ne, np.complex64), np.empty(nfe * M, np.complex64)
+            px[:] = hx
+            py[:] = 0
+            pageable = {}
+            for mode in ("register", "direct"):
+                os.environ["LIQUID_CUDA_PAGEABLE"] = mode
+                pageable[mode] = e2e_time(px, py, max(1, args.e2e_steps - 1))
+            os.environ.pop("LIQUID_CUDA_PAGEABLE", None)
+            e2e["pageable_host_arrays"] = {"unit": UNIT, "page_locked_per_call": pageable["register"],
+                                           "plain_pageable_copies": pageable["direct"]}
+            del px, py
         qe.destroy()
         L.pinned_free(hx)
         L.pinned_free(hy)
+
+    # the other BASELINE configs, briefly (N = 1): same code as tools/bench_configs.py
+    other = None
+    if world == 1 and not args.no_other_configs and args.workload == "c3":
+        del xbuf, ybuf
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        other = {}
+
+        def keep(line):
+            other[line["config"].split(":")[0]] = {"config": line["config"], "value": line["value"], "unit": line["unit"],
+                                                   "ms_per_step": line["ms_per_step"], "roofline_frac": line["roofline"]["frac"],
+                                                   "bytes_per_sample": line["roofline"]["algorithmic_bytes_per_sample"]}
+        for cfg in ("c1", "c2", "c4", "c5"):
+            try:
+                bench_configs.run([cfg], args.other_steps, 2, keep, device_index=local_rank)
+            except Exception as e:          # noqa: BLE001
+                other[cfg] = {"error": str(e)}
+            torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -394,9 +626,20 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+        if halo_parity is not None:
+            line["halo_parity"] = halo_parity
+            line["config"]["exchange"] = ("torch.distributed batch_isend_irecv (Python)" if comm is None else
+                                          "firpfbch2_crcf_execute_sharded_dev: ncclSend/ncclRecv of 2mM samples inside the C driver")
+        if other is not None:
+            line["other_configs"] = other
         print(json.dumps(line))
+    if comm is not None:
+        comm.destroy()
     if world > 1:
         dist.destroy_process_group()
+    if halo_parity is False:
+        print("bench.py: halo parity check FAILED", file=sys.stderr)
+        return 3
     return 0
 
 

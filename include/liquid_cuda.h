@@ -316,6 +316,11 @@ void *liquid_cuda_malloc(unsigned long long _bytes);  /* device memory */
 void  liquid_cuda_free(void *_dptr);
 void *liquid_cuda_host_alloc(unsigned long long _bytes);   /* pinned host memory */
 void  liquid_cuda_host_free(void *_hptr);
+/* page-lock an array the caller allocated itself (malloc, a file mapping) for as long as it is handed to the
+ * *_execute_block entry points; returns 0 on success.  Without it a pageable array of 8 MB or more is page-locked
+ * for the duration of each call (env LIQUID_CUDA_PAGEABLE=direct: never, plain cudaMemcpyAsync from pageable memory) */
+int   liquid_cuda_host_register(void *_hptr, unsigned long long _bytes);
+void  liquid_cuda_host_unregister(void *_hptr);
 void  liquid_cuda_memcpy_h2d(void *_dst, const void *_src, unsigned long long _bytes);
 void  liquid_cuda_memcpy_d2h(void *_dst, const void *_src, unsigned long long _bytes);
 void  liquid_cuda_sync(void);
@@ -351,6 +356,41 @@ void firpfbch2_crcf_execute_segment_dev(firpfbch2_crcf _q, const void *_d_halo, 
 unsigned int firpfbch2_crcf_get_state_len(firpfbch2_crcf _q);
 void firpfbch2_crcf_get_state(firpfbch2_crcf _q, liquid_float_complex *_hist, int *_flag);
 void firpfbch2_crcf_set_state(firpfbch2_crcf _q, const liquid_float_complex *_hist, int _flag);
+unsigned int firpfbch2_crcf_get_num_channels(firpfbch2_crcf _q);
+
+/* ---- multi-GPU driver: one long stream time-sharded over `world` processes, one GPU each ----
+ * Rank r owns the frames [first_frame, first_frame + n_frames) of the stream, first_frame even (every segment
+ * starts with the reference's flag = 0, firpfbch2.c:57).  The communicator wraps an NCCL communicator (NCCL is
+ * loaded at run time, so single-GPU programs never need it): rank 0 calls liquid_cuda_comm_get_unique_id and
+ * hands the liquid_cuda_comm_unique_id_bytes() bytes to the other ranks by any means (MPI_Bcast, a file, a
+ * socket), then every rank calls liquid_cuda_comm_create.  Creating a communicator with world > 1 sets
+ * NCCL_MAX/MIN_P2P_NCHANNELS=1 unless already set and reserves two SMs (liquid_cuda_set_reserved_sms) so that
+ * the exchange runs beside the persistent channelizer kernel; destroy restores the reservation. */
+typedef struct liquid_cuda_comm_s *liquid_cuda_comm;
+int  liquid_cuda_comm_unique_id_bytes(void);
+void liquid_cuda_comm_get_unique_id(void *_id);
+liquid_cuda_comm liquid_cuda_comm_create(int _rank, int _world, const void *_id);    /* _id may be NULL when world == 1 */
+void liquid_cuda_comm_destroy(liquid_cuda_comm _c);
+int  liquid_cuda_comm_rank(liquid_cuda_comm _c);
+int  liquid_cuda_comm_world(liquid_cuda_comm _c);
+/* the exchange step on its own: _n_samples complex samples from _d_tail go to rank + 1, the left neighbour's
+ * arrive in _d_head (rank 0 receives nothing), one ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd on _stream */
+void liquid_cuda_comm_exchange_halo_dev(liquid_cuda_comm _c, void *_d_head, const void *_d_tail,
+                                        unsigned long long _n_samples, void *_stream);
+/* one pass of the sharded analyzer.  _d_x_with_headroom: get_state_len() samples of head-room followed by this
+ * rank's n_frames * M/2 input samples; the left neighbour's last get_state_len() samples land in the head-room
+ * (rank 0's head-room is read as it is: zeros = the reference's reset state).  The interior frames run on
+ * _stream while the halo is in flight, the 4m halo-dependent frames follow on the communicator's side stream,
+ * and _stream waits for them: on return everything is ordered on _stream.  Object state is not touched. */
+void firpfbch2_crcf_execute_sharded_dev(firpfbch2_crcf _q, liquid_cuda_comm _c, void *_d_x_with_headroom,
+                                        unsigned long long _first_frame, unsigned long long _n_frames,
+                                        void *_d_y, void *_stream);
+/* the same pass on host pointers: _x[_n_frames*M/2] is this rank's segment, _y[_n_frames*M] its output.  The last
+ * get_state_len() samples go to the right neighbour, the left neighbour's become the object's history (rank 0: the
+ * reset state), then the segment runs through the chunked H2D / compute / D2H pipeline of execute_block.  On return
+ * the object holds the state after the segment, as after execute_block. */
+void firpfbch2_crcf_execute_sharded(firpfbch2_crcf _q, liquid_cuda_comm _c, liquid_float_complex *_x,
+                                    unsigned long long _first_frame, unsigned int _n_frames, liquid_float_complex *_y);
 
 /* ---- firpfbch_crcf ---- */
 void firpfbch_crcf_analyzer_execute_block(firpfbch_crcf _q, liquid_float_complex *_x,

@@ -78,6 +78,18 @@ _sig("firpfbch2_crcf_execute_block", None, _vp, _vp, _u, _vp)
 _sig("firpfbch2_crcf_execute_block_dev", None, _vp, _vp, _ull, _vp, _vp)
 _sig("firpfbch2_crcf_execute_segment_dev", None, _vp, _vp, _vp, _ull, _ull, _vp, _vp)
 _sig("firpfbch2_crcf_get_state_len", _u, _vp)
+_sig("firpfbch2_crcf_get_num_channels", _u, _vp)
+_sig("liquid_cuda_comm_unique_id_bytes", _i)
+_sig("liquid_cuda_comm_get_unique_id", None, _vp)
+_sig("liquid_cuda_comm_create", _vp, _i, _i, _vp)
+_sig("liquid_cuda_comm_destroy", None, _vp)
+_sig("liquid_cuda_comm_rank", _i, _vp)
+_sig("liquid_cuda_comm_world", _i, _vp)
+_sig("liquid_cuda_comm_exchange_halo_dev", None, _vp, _vp, _vp, _ull, _vp)
+_sig("firpfbch2_crcf_execute_sharded_dev", None, _vp, _vp, _vp, _ull, _ull, _vp, _vp)
+_sig("firpfbch2_crcf_execute_sharded", None, _vp, _vp, _vp, _ull, _u, _vp)
+_sig("liquid_cuda_host_register", _i, _vp, _ull)
+_sig("liquid_cuda_host_unregister", None, _vp)
 _sig("firpfbch2_crcf_get_state", None, _vp, _cf_p, C.POINTER(C.c_int))
 _sig("firpfbch2_crcf_set_state", None, _vp, _cf_p, _i)
 _sig("firpfbch_crcf_create", _vp, _i, _u, _u, _f_p)
@@ -289,6 +301,30 @@ def launch_count():
     return int(lib.liquid_cuda_launch_count())
 
 
+class Comm:
+    """liquid_cuda_comm: the C multi-GPU driver's communicator (NCCL underneath).  `id_bytes` comes from
+    Comm.unique_id() on rank 0 and travels to the other ranks by whatever the launcher offers."""
+
+    def __init__(self, rank, world, id_bytes=None):
+        buf = C.create_string_buffer(bytes(id_bytes), len(id_bytes)) if id_bytes is not None else None
+        self._h = lib.liquid_cuda_comm_create(rank, world, C.cast(buf, C.c_void_p) if buf is not None else None)
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(lib.liquid_cuda_comm_unique_id_bytes())
+        lib.liquid_cuda_comm_get_unique_id(C.cast(buf, C.c_void_p))
+        return buf.raw
+
+    def exchange_halo_dev(self, d_head, d_tail, n_samples, stream=0):
+        lib.liquid_cuda_comm_exchange_halo_dev(self._h, d_head, d_tail, n_samples, stream)
+
+    def destroy(self):
+        if self._h:
+            lib.liquid_cuda_comm_destroy(self._h)
+            self._h = None
+
+
 def _c64(a):
     return np.ascontiguousarray(a, dtype=np.complex64)
 
@@ -455,6 +491,18 @@ class firpfbch2_crcf(_Handle):
 
     def execute_segment_dev(self, d_halo, d_x, first_frame, n_frames, d_y, stream=0):
         lib.firpfbch2_crcf_execute_segment_dev(self._h, d_halo, d_x, first_frame, n_frames, d_y, stream)
+
+    def execute_sharded_dev(self, comm, d_x_with_headroom, first_frame, n_frames, d_y, stream=0):
+        """one pass of the time-sharded analyzer through the C multi-GPU driver (csrc/multi.cu)"""
+        lib.firpfbch2_crcf_execute_sharded_dev(self._h, comm._h, d_x_with_headroom, first_frame, n_frames, d_y, stream)
+
+    def execute_sharded(self, comm, x, first_frame, out=None):
+        """this rank's segment of a time-sharded stream, host arrays (csrc/firpfbch2.cu)"""
+        x = _c64(x)
+        n_frames = x.size // self.n_in
+        y = out if out is not None else np.empty(n_frames * self.n_out, np.complex64)
+        lib.firpfbch2_crcf_execute_sharded(self._h, comm._h, _ptr(x), first_frame, n_frames, _ptr(y))
+        return y.reshape(n_frames, self.n_out) if out is None else y
 
     def get_state_len(self):
         return lib.firpfbch2_crcf_get_state_len(self._h)

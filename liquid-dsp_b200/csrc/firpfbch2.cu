@@ -206,6 +206,7 @@ void firpfbch2_crcf_print(firpfbch2_crcf _q)
 }
 
 unsigned int firpfbch2_crcf_get_state_len(firpfbch2_crcf _q) { return _q->H; }
+unsigned int firpfbch2_crcf_get_num_channels(firpfbch2_crcf _q) { return _q->M; }
 
 void firpfbch2_crcf_get_state(firpfbch2_crcf _q, liquid_float_complex *_hist, int *_flag)
 {
@@ -257,6 +258,28 @@ void firpfbch2_crcf_execute_block(firpfbch2_crcf _q, liquid_float_complex *_x, u
                    [&](float2 *di, size_t nf, float2 *dob, cudaStream_t st) {
                        firpfbch2_crcf_execute_block_dev(_q, di, nf, dob, st);
                    });
+}
+
+void firpfbch2_crcf_execute_sharded(firpfbch2_crcf _q, liquid_cuda_comm _c, liquid_float_complex *_x,
+                                    unsigned long long _first_frame, unsigned int _n_frames, liquid_float_complex *_y)
+{
+    if (_q->type != LIQUID_ANALYZER)
+        lc::fatal("firpfbch2_crcf_execute_sharded", "the sharded form is provided for the analyzer only");
+    if (_first_frame & 1) lc::fatal("firpfbch2_crcf_execute_sharded", "a segment must start on an even frame");
+    const size_t H = _q->H, n = (size_t)_n_frames * _q->M2;
+    if (liquid_cuda_comm_world(_c) > 1 && n < H)
+        lc::fatal("firpfbch2_crcf_execute_sharded", "a segment must hold at least the 2mM samples its right neighbour needs");
+    // the object's history becomes the left neighbour's tail (rank 0: the reset state), then the segment runs
+    // through the ordinary chunked H2D / compute / D2H pipeline
+    LC_CUDA_CHECK(cudaMemsetAsync(_q->d_hist, 0, sizeof(float2) * H, _q->stream));
+    if (liquid_cuda_comm_world(_c) > 1) {
+        float2 *d_tail = (float2 *)_q->hist_tmp.get(sizeof(float2) * H);
+        LC_CUDA_CHECK(cudaMemcpyAsync(d_tail, reinterpret_cast<const float2 *>(_x) + (n - H), sizeof(float2) * H,
+                                      cudaMemcpyHostToDevice, _q->stream));
+        liquid_cuda_comm_exchange_halo_dev(_c, _q->d_hist, d_tail, H, _q->stream);
+    }
+    _q->flag = 0;
+    firpfbch2_crcf_execute_block(_q, _x, _n_frames, _y);
 }
 
 void firpfbch2_crcf_execute(firpfbch2_crcf _q, liquid_float_complex *_x, liquid_float_complex *_y)

@@ -116,6 +116,13 @@ __device__ __forceinline__ float2 cmul2(float2 a, float2 t)
     return __ffma2_rn(ms_s, make_float2(a.y, a.x), __fmul2_rn(bc(t.x), a));
 }
 
+// the same product as t.x * a + t.y * (j a): the negation inside j a = {-a.y, a.x} costs one scalar FADD on the FMA
+// pipe, but no register moves (the form above builds its {-t.y, t.y} pair with two MOVs on the half-rate ALU pipe)
+__device__ __forceinline__ float2 cmul2_rot(float2 a, float2 t)
+{
+    return __ffma2_rn(bc(t.y), rot90(a), __fmul2_rn(bc(t.x), a));
+}
+
 // N-point DFT of v[] in registers, natural order in and out, e^{SIGN j 2 pi nk/N}.
 // Decimation in time; every index is a compile-time constant, so the even/odd split is renaming.
 template <int N, int SIGN>

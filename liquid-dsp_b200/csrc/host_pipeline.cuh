@@ -11,16 +11,62 @@
 
 namespace lc {
 
+constexpr int kPipeEvents = 4;                 // ring of per-chunk events (two chunks are in flight at most)
 struct CopyStreams {
     cudaStream_t in = nullptr, out = nullptr;
+    // created once per thread and device, reused by every call: a chunk takes the three events of slot c % 4
+    // (a stream wait captures the record that precedes it, so re-recording a slot later is harmless)
+    cudaEvent_t ev_in[kPipeEvents] = {}, ev_k[kPipeEvents] = {}, ev_out[kPipeEvents] = {};
     void ensure()
     {
         if (!in) {
             LC_CUDA_CHECK(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
             LC_CUDA_CHECK(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+            for (int i = 0; i < kPipeEvents; i++) {
+                LC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+                LC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+                LC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+            }
         }
     }
 };
+
+// A caller's malloc'd (pageable) array makes cudaMemcpyAsync synchronous and staged through the driver's
+// bounce buffer: no overlap and roughly half the link rate.  For the duration of a large call the array is
+// page-locked in place instead (cudaHostRegister); arrays that are already pinned (liquid_cuda_host_alloc,
+// liquid_cuda_host_register, cudaHostAlloc) are left alone.  LIQUID_CUDA_PAGEABLE=direct switches this off.
+struct ScopedPin {
+    void *p = nullptr;
+    ScopedPin(const void *ptr, size_t bytes)
+    {
+        const char *e = getenv("LIQUID_CUDA_PAGEABLE");
+        if ((e && !strcmp(e, "direct")) || bytes < (8u << 20)) return;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return;
+        }
+        if (at.type != cudaMemoryTypeUnregistered) return;
+        if (cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess) p = const_cast<void *>(ptr);
+        else (void)cudaGetLastError();              // e.g. read-only mapping: fall back to the pageable path
+    }
+    ~ScopedPin()
+    {
+        if (p) cudaHostUnregister(p);
+    }
+    ScopedPin(const ScopedPin &) = delete;
+    ScopedPin &operator=(const ScopedPin &) = delete;
+};
+
+inline size_t pipeline_chunk_bytes()
+{
+    static const size_t v = [] {
+        const char *e = getenv("LIQUID_CUDA_CHUNK_MB");
+        long mb = e ? atol(e) : 0;
+        return (size_t)(mb >= 1 && mb <= 4096 ? mb : 32) << 20;
+    }();
+    return v;
+}
 
 // the calling thread's copy streams on the CURRENT device (streams belong to a device; a process may drive
 // several through liquid_cuda_set_device)
@@ -38,9 +84,13 @@ inline CopyStreams &copy_streams()
 // y + u*out_per.  run(d_in, n_units_in_chunk, d_out, stream) enqueues the device work of one chunk.
 template <typename Run>
 void host_block(cudaStream_t compute, DevBuf &stage_in, DevBuf &stage_out, const lc_cf *x, lc_cf *y,
-                size_t n_units, size_t in_per, size_t out_per, Run run, size_t chunk_bytes = (32u << 20))
+                size_t n_units, size_t in_per, size_t out_per, Run run, size_t chunk_bytes = 0)
 {
     if (n_units == 0) return;
+    if (chunk_bytes == 0) chunk_bytes = pipeline_chunk_bytes();
+    const bool alias = (const void *)x == (const void *)y;         // firfilt allows in-place blocks
+    ScopedPin pin_x(x, n_units * in_per * sizeof(float2));
+    ScopedPin pin_y(alias ? nullptr : y, alias ? 0 : n_units * out_per * sizeof(float2));
     const size_t per = std::max(in_per, out_per) * sizeof(float2);
     const size_t chunk_units = std::max<size_t>(1, chunk_bytes / per);
     const size_t n_chunks = (n_units + chunk_units - 1) / chunk_units;
@@ -49,36 +99,26 @@ void host_block(cudaStream_t compute, DevBuf &stage_in, DevBuf &stage_out, const
     float2 *din = (float2 *)stage_in.get(bufs * cu * in_per * sizeof(float2));
     float2 *dout = (float2 *)stage_out.get(bufs * cu * out_per * sizeof(float2));
     CopyStreams &cs = copy_streams();
-    std::vector<cudaEvent_t> ev_in(n_chunks), ev_k(n_chunks), ev_out(n_chunks);
     for (size_t c = 0; c < n_chunks; c++) {
-        LC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
-        LC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming));
-        LC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_out[c], cudaEventDisableTiming));
-    }
-    for (size_t c = 0; c < n_chunks; c++) {
+        const int e = (int)(c % kPipeEvents), e_old = (int)((c + kPipeEvents - bufs) % kPipeEvents);
         const size_t u0 = c * chunk_units, nu = std::min(chunk_units, n_units - u0);
         float2 *di = din + (c % bufs) * cu * in_per;
         float2 *dob = dout + (c % bufs) * cu * out_per;
         if (c >= bufs) {                               // buffer reuse: wait for its last consumers
-            LC_CUDA_CHECK(cudaStreamWaitEvent(cs.in, ev_k[c - bufs], 0));
-            LC_CUDA_CHECK(cudaStreamWaitEvent(compute, ev_out[c - bufs], 0));
+            LC_CUDA_CHECK(cudaStreamWaitEvent(cs.in, cs.ev_k[e_old], 0));
+            LC_CUDA_CHECK(cudaStreamWaitEvent(compute, cs.ev_out[e_old], 0));
         }
         LC_CUDA_CHECK(cudaMemcpyAsync(di, x + u0 * in_per, nu * in_per * sizeof(float2), cudaMemcpyHostToDevice, cs.in));
-        LC_CUDA_CHECK(cudaEventRecord(ev_in[c], cs.in));
-        LC_CUDA_CHECK(cudaStreamWaitEvent(compute, ev_in[c], 0));
+        LC_CUDA_CHECK(cudaEventRecord(cs.ev_in[e], cs.in));
+        LC_CUDA_CHECK(cudaStreamWaitEvent(compute, cs.ev_in[e], 0));
         run(di, nu, dob, compute);
-        LC_CUDA_CHECK(cudaEventRecord(ev_k[c], compute));
-        LC_CUDA_CHECK(cudaStreamWaitEvent(cs.out, ev_k[c], 0));
+        LC_CUDA_CHECK(cudaEventRecord(cs.ev_k[e], compute));
+        LC_CUDA_CHECK(cudaStreamWaitEvent(cs.out, cs.ev_k[e], 0));
         LC_CUDA_CHECK(cudaMemcpyAsync(y + u0 * out_per, dob, nu * out_per * sizeof(float2), cudaMemcpyDeviceToHost, cs.out));
-        LC_CUDA_CHECK(cudaEventRecord(ev_out[c], cs.out));
+        LC_CUDA_CHECK(cudaEventRecord(cs.ev_out[e], cs.out));
     }
     LC_CUDA_CHECK(cudaStreamSynchronize(cs.out));
     LC_CUDA_CHECK(cudaStreamSynchronize(compute));
-    for (size_t c = 0; c < n_chunks; c++) {
-        cudaEventDestroy(ev_in[c]);
-        cudaEventDestroy(ev_k[c]);
-        cudaEventDestroy(ev_out[c]);
-    }
 }
 
 // new state = last H samples of [hist | x(n samples)], all on the device, in stream order

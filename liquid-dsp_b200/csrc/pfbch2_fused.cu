@@ -101,9 +101,9 @@ __device__ __forceinline__ void radix4_store(uint32_t slot, float2 a0, float2 a1
     const float2 u1 = __fadd2_rn(d02, rot90(d13));      // W4 = +j (backward transform)
     const float2 u3 = __fadd2_rn(d02, rot270(d13));
     sts64(slot, u0);
-    sts64(slot + 1 * (kSubStride * 8), cmul2(u1, t1));
-    sts64(slot + 2 * (kSubStride * 8), cmul2(u2, t2));
-    sts64(slot + 3 * (kSubStride * 8), cmul2(u3, t3));
+    sts64(slot + 1 * (kSubStride * 8), cmul2_rot(u1, t1));
+    sts64(slot + 2 * (kSubStride * 8), cmul2_rot(u2, t2));
+    sts64(slot + 3 * (kSubStride * 8), cmul2_rot(u3, t3));
 }
 
 // a * t with t given as {c, c, -s, s}: two packed instructions on the register pairs as loaded

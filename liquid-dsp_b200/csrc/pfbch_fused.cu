@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreads) pfbch_fused_256_kernel(const PfbArgs
         for (int r1 = 0; r1 < 16; r1++) v[r1] = fr[r1 * 17 + r2];
         RegDft<16, -1>::run(v);
 #pragma unroll
-        for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul2(v[k1], __ldg(twp + 16 * k1));
+        for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul2_rot(v[k1], __ldg(twp + 16 * k1));
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 16; k1++) fr[r2 * 17 + k1] = v[k1];
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kThreads) pfbch_synth_fused_256_kernel(const S
         for (int r1 = 0; r1 < 16; r1++) v[r1] = __ldg(xf + 16 * r1);
         RegDft<16, +1>::run(v);
 #pragma unroll
-        for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul2(v[k1], __ldg(twp + 16 * k1));
+        for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul2_rot(v[k1], __ldg(twp + 16 * k1));
 #pragma unroll
         for (int k1 = 0; k1 < 16; k1++) fr[r2 * 17 + k1] = v[k1];
         __syncwarp();

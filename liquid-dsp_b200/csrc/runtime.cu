@@ -103,6 +103,19 @@ void *liquid_cuda_host_alloc(unsigned long long _bytes)
 
 void liquid_cuda_host_free(void *_hptr) { if (_hptr) LC_CUDA_CHECK(cudaFreeHost(_hptr)); }
 
+int liquid_cuda_host_register(void *_hptr, unsigned long long _bytes)
+{
+    lc::ensure_device();
+    if (cudaHostRegister(_hptr, _bytes, cudaHostRegisterDefault) == cudaSuccess) return 0;
+    (void)cudaGetLastError();
+    return -1;
+}
+
+void liquid_cuda_host_unregister(void *_hptr)
+{
+    if (_hptr && cudaHostUnregister(_hptr) != cudaSuccess) (void)cudaGetLastError();
+}
+
 void liquid_cuda_memcpy_h2d(void *_dst, const void *_src, unsigned long long _bytes)
 {
     LC_CUDA_CHECK(cudaMemcpy(_dst, _src, _bytes, cudaMemcpyHostToDevice));

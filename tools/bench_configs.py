@@ -28,10 +28,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     args = ap.parse_args()
+    run(args.configs, args.steps, args.warmup, lambda line: print(json.dumps(line), flush=True))
+
+
+def run(configs, steps, warmup, sink, device_index=0):
+    """measure `configs` (names as in the module docstring) on the current process's GPU; every result line (a dict)
+    goes to `sink` -- bench.py collects the BASELINE configs this way for its `other_configs` entry"""
+    import types
+    args = types.SimpleNamespace(configs=list(configs), steps=steps, warmup=warmup)
     import torch
     import liquid_dsp_b200 as L
-    L.set_device(0)
-    dev = torch.device("cuda", 0)
+    L.set_device(device_index)
+    dev = torch.device("cuda", device_index)
     st = torch.cuda.current_stream()
     peak = 6531.6
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -59,7 +67,7 @@ def main():
                              "algorithmic_bytes_per_sample": bytes_per_sample}}
         if extra:
             line.update(extra)
-        print(json.dumps(line), flush=True)
+        sink(line)
 
     if "c1" in args.configs:
         # firpfbch_crcf analysis M=16, m=4 (p=8), one long stream (BASELINE configs[0] shape, GPU-sized)
