@@ -317,8 +317,9 @@ void  liquid_cuda_free(void *_dptr);
 void *liquid_cuda_host_alloc(unsigned long long _bytes);   /* pinned host memory */
 void  liquid_cuda_host_free(void *_hptr);
 /* page-lock an array the caller allocated itself (malloc, a file mapping) for as long as it is handed to the
- * *_execute_block entry points; returns 0 on success.  Without it a pageable array of 8 MB or more is page-locked
- * for the duration of each call (env LIQUID_CUDA_PAGEABLE=direct: never, plain cudaMemcpyAsync from pageable memory) */
+ * *_execute_block entry points; returns 0 on success.  Pageable arrays work without it, at the rate of the driver's
+ * staged copies (about a fifth of the pinned rate, bench.py e2e.pageable_host_arrays); env LIQUID_CUDA_PAGEABLE=register
+ * page-locks arrays of 8 MB or more for the duration of each call instead (slower unless calls are very long). */
 int   liquid_cuda_host_register(void *_hptr, unsigned long long _bytes);
 void  liquid_cuda_host_unregister(void *_hptr);
 void  liquid_cuda_memcpy_h2d(void *_dst, const void *_src, unsigned long long _bytes);

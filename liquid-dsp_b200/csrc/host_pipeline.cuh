@@ -31,16 +31,17 @@ struct CopyStreams {
     }
 };
 
-// A caller's malloc'd (pageable) array makes cudaMemcpyAsync synchronous and staged through the driver's
-// bounce buffer: no overlap and roughly half the link rate.  For the duration of a large call the array is
-// page-locked in place instead (cudaHostRegister); arrays that are already pinned (liquid_cuda_host_alloc,
-// liquid_cuda_host_register, cudaHostAlloc) are left alone.  LIQUID_CUDA_PAGEABLE=direct switches this off.
+// A caller's malloc'd (pageable) array makes cudaMemcpyAsync synchronous and staged through the driver's bounce
+// buffer: measured 0.64 GS/s end to end against 3.2 GS/s from pinned arrays (firpfbch2 M=1024, bench.py e2e).
+// Page-locking the arrays for the duration of each call (cudaHostRegister, LIQUID_CUDA_PAGEABLE=register) is
+// worse still -- 0.12 GS/s, registering 6 GB costs seconds -- so the default leaves pageable arrays to the driver;
+// a caller that reuses its arrays pins them once with liquid_cuda_host_register and gets the pinned rate.
 struct ScopedPin {
     void *p = nullptr;
     ScopedPin(const void *ptr, size_t bytes)
     {
         const char *e = getenv("LIQUID_CUDA_PAGEABLE");
-        if ((e && !strcmp(e, "direct")) || bytes < (8u << 20)) return;
+        if (!e || strcmp(e, "register") || bytes < (8u << 20)) return;
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
             (void)cudaGetLastError();
