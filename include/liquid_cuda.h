@@ -19,6 +19,16 @@
  *
  * All pointers are plain host pointers unless the name ends in _dev (device pointers, asynchronous
  * on the given cudaStream_t passed as void*; NULL = the legacy default stream).
+ *
+ * Stream contract: a *_dev call updates the object's state (history, frame parity) in stream order on the
+ * CALLER's stream.  Every other entry point of the same object (execute, execute_block, reset, get_state,
+ * set_state, push ...) works on the object's own private stream and synchronises only that one.  Between a
+ * *_dev call on stream S and any non-_dev call on the same object the caller must synchronise S
+ * (cudaStreamSynchronize / liquid_cuda_sync); consecutive *_dev calls need nothing as long as they are issued
+ * on the same stream (or on streams the caller has ordered with events).  Distinct objects never interact.
+ *
+ * Device selection: liquid_cuda_set_device(d) (or env LIQUID_CUDA_DEVICE when it is never called) selects the
+ * device for every thread of the process; each thread is switched to it on its first call into the library.
  */
 #ifndef LIQUID_CUDA_H
 #define LIQUID_CUDA_H
@@ -269,6 +279,7 @@ typedef struct firpfb_crcf_s * firpfb_crcf;
 firpfb_crcf firpfb_crcf_create(unsigned int _M, float *_h, unsigned int _h_len);
 firpfb_crcf firpfb_crcf_create_kaiser(unsigned int _M, unsigned int _m, float _fc, float _As);
 firpfb_crcf firpfb_crcf_create_rnyquist(int _type, unsigned int _M, unsigned int _k, unsigned int _m, float _beta);
+firpfb_crcf firpfb_crcf_create_drnyquist(int _type, unsigned int _M, unsigned int _k, unsigned int _m, float _beta);   /* liquid.h:2432 */
 firpfb_crcf firpfb_crcf_recreate(firpfb_crcf _q, unsigned int _M, float *_h, unsigned int _h_len);
 void firpfb_crcf_destroy(firpfb_crcf _q);
 void firpfb_crcf_print(firpfb_crcf _q);

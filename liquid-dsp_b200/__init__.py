@@ -10,6 +10,7 @@ Host arrays are numpy ``complex64`` / ``float32``; the ``*_dev`` methods take ra
 (``tensor.data_ptr()``) and a CUDA stream handle, so torch is plumbing only and never imported here.
 """
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -235,6 +236,7 @@ _sig("firfilt_crcf_groupdelay", _fl, _vp, _fl)
 _sig("firpfb_crcf_create", _vp, _u, _f_p, _u)
 _sig("firpfb_crcf_create_kaiser", _vp, _u, _u, _fl, _fl)
 _sig("firpfb_crcf_create_rnyquist", _vp, _i, _u, _u, _u, _fl)
+_sig("firpfb_crcf_create_drnyquist", _vp, _i, _u, _u, _u, _fl)
 _sig("firpfb_crcf_recreate", _vp, _vp, _u, _f_p, _u)
 _sig("firpfb_crcf_destroy", None, _vp)
 _sig("firpfb_crcf_print", None, _vp)
@@ -401,13 +403,27 @@ def kaiser_beta_As(As):
     return lib.kaiser_beta_As(As)
 
 
+class _PinnedBlock:
+    """owner of one cudaHostAlloc'd block: freed by pinned_free or, failing that, when the last array over it goes"""
+
+    def __init__(self, nbytes):
+        self.ptr = lib.liquid_cuda_host_alloc(nbytes)
+        self.buf = (C.c_char * nbytes).from_address(self.ptr)
+        self._fin = weakref.finalize(self, lib.liquid_cuda_host_free, self.ptr)
+
+    def free(self):
+        self._fin()                      # idempotent: runs liquid_cuda_host_free at most once
+
+
 def pinned_empty(n, dtype=np.complex64):
-    """numpy array over cudaHostAlloc'd (pinned) memory; keeps the allocation alive with the array"""
+    """numpy array over cudaHostAlloc'd (pinned) memory.  The block lives as long as the array (or any view of it)
+    does: the array's base chain holds the owner object, whose finalizer frees the block; pinned_free(arr) frees it
+    at once -- the array must not be used afterwards."""
     nbytes = int(n) * np.dtype(dtype).itemsize
-    p = lib.liquid_cuda_host_alloc(nbytes)
-    buf = (C.c_char * nbytes).from_address(p)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(n))
-    _PINNED[arr.ctypes.data] = p
+    blk = _PinnedBlock(max(nbytes, 1))
+    arr = np.frombuffer(blk.buf, dtype=dtype, count=int(n))      # arr.base -> blk.buf (a ctypes array)
+    blk.buf._owner = blk                                           # ... which keeps the owner (and the block) alive
+    _PINNED[arr.ctypes.data] = weakref.ref(blk)
     return arr
 
 
@@ -415,9 +431,10 @@ _PINNED = {}
 
 
 def pinned_free(arr):
-    p = _PINNED.pop(arr.ctypes.data, None)
-    if p:
-        lib.liquid_cuda_host_free(p)
+    ref = _PINNED.pop(arr.ctypes.data, None)
+    blk = ref() if ref is not None else None
+    if blk is not None:
+        blk.free()
 
 
 class _Handle:
@@ -1188,6 +1205,20 @@ class firpfb_crcf(_Handle):
         q = cls.__new__(cls)
         q.M = M
         _Handle.__init__(q, lib.firpfb_crcf_create_kaiser(M, m, fc, As))
+        return q
+
+    @classmethod
+    def create_rnyquist(cls, type, M, k, m, beta):
+        q = cls.__new__(cls)
+        q.M = M
+        _Handle.__init__(q, lib.firpfb_crcf_create_rnyquist(type, M, k, m, beta))
+        return q
+
+    @classmethod
+    def create_drnyquist(cls, type, M, k, m, beta):
+        q = cls.__new__(cls)
+        q.M = M
+        _Handle.__init__(q, lib.firpfb_crcf_create_drnyquist(type, M, k, m, beta))
         return q
 
     def reset(self):

@@ -5,6 +5,8 @@
 // State = the last sub_len samples pushed.  Not used by the channelizers (they own one window per
 // branch); listed by north_star as a changed subsystem, provided for completeness with a batched
 // push+execute entry point.
+#include <cmath>
+
 #include "lc_common.cuh"
 #include "../../include/liquid_cuda.h"
 #include "host_pipeline.cuh"
@@ -74,6 +76,29 @@ firpfb_crcf firpfb_crcf_create_rnyquist(int _type, unsigned int _M, unsigned int
     std::vector<float> Hf(H_len);
     liquid_firdes_prototype(_type, _M * _k, _m, _beta, 0.0f, Hf.data());   // firpfb.c:170
     return firpfb_crcf_create(_M, Hf.data(), H_len);
+}
+
+// derivative square-root Nyquist bank (firpfb.c:188-239): central differences of the prototype (circular at the two
+// ends), scaled by 0.06 / max|h dh| -- the matched-filter derivative bank of a symbol timing loop
+firpfb_crcf firpfb_crcf_create_drnyquist(int _type, unsigned int _M, unsigned int _k, unsigned int _m, float _beta)
+{
+    if (_M == 0) lc::fatal("firpfb_crcf_create_drnyquist", "number of filters must be greater than zero");
+    if (_k < 2) lc::fatal("firpfb_crcf_create_drnyquist", "filter samples/symbol must be greater than 1");
+    if (_m == 0) lc::fatal("firpfb_crcf_create_drnyquist", "filter delay must be greater than 0");
+    if (_beta < 0.0f || _beta > 1.0f) lc::fatal("firpfb_crcf_create_drnyquist", "filter excess bandwidth factor must be in [0,1]");
+    const unsigned int H_len = 2 * _M * _k * _m + 1;
+    std::vector<float> Hf(H_len), dHf(H_len);
+    liquid_firdes_prototype(_type, _M * _k, _m, _beta, 0.0f, Hf.data());   // firpfb.c:211
+    float HdH_max = 0.0f;
+    for (unsigned int i = 0; i < H_len; i++) {
+        if (i == 0)              dHf[i] = Hf[i + 1] - Hf[H_len - 1];
+        else if (i == H_len - 1) dHf[i] = Hf[0] - Hf[i - 1];
+        else                     dHf[i] = Hf[i + 1] - Hf[i - 1];
+        const float v = fabsf(Hf[i] * dHf[i]);
+        if (v > HdH_max) HdH_max = v;
+    }
+    for (unsigned int i = 0; i < H_len; i++) dHf[i] = dHf[i] * 0.06f / HdH_max;
+    return firpfb_crcf_create(_M, dHf.data(), H_len);
 }
 
 firpfb_crcf firpfb_crcf_recreate(firpfb_crcf _q, unsigned int _M, float *_h, unsigned int _h_len)

@@ -38,6 +38,7 @@ namespace lc {
 // selects the device once (env LIQUID_CUDA_DEVICE or the current one) and aborts loudly when
 // there is no usable sm_100 GPU: this library has no CPU path.
 void ensure_device();
+void choose_device(int dev);       // liquid_cuda_set_device: takes precedence over LIQUID_CUDA_DEVICE, applies to every thread
 
 extern std::atomic<unsigned long long> g_launches;
 // frames each CTA (fused M=1024 kernel) or cluster (M=4096 kernel) walked in the most recent fused

@@ -7,29 +7,17 @@ namespace lc {
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_reserved_sms{0};
 std::atomic<unsigned long long> g_last_chunk_frames{0};
-static std::atomic<int> g_device_ready{0};
+// The device this library works on: LIQUID_CUDA_DEVICE unless liquid_cuda_set_device was called (an explicit call
+// wins), else whatever the calling thread's current device is.  The CUDA current device is per-thread state, so a
+// thread that has not been here yet is switched to the chosen device on its first call; the sm_100 check runs once
+// per device.
+static std::atomic<int> g_chosen_device{-1};          // -1: none chosen (follow the thread's current device)
+static std::atomic<unsigned long long> g_device_checked{0};
 
-void ensure_device()
+static void check_device(int dev)
 {
-    if (g_device_ready.load(std::memory_order_acquire)) return;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        fprintf(stderr, "liquid_cuda: no CUDA device available (%s); this library has no CPU fallback\n",
-                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-        abort();
-    }
-    const char *env = getenv("LIQUID_CUDA_DEVICE");
-    if (env) {
-        int dev = atoi(env);
-        if (dev < 0 || dev >= count) {
-            fprintf(stderr, "liquid_cuda: LIQUID_CUDA_DEVICE=%s out of range (have %d devices)\n", env, count);
-            abort();
-        }
-        LC_CUDA_CHECK(cudaSetDevice(dev));
-    }
-    int dev = 0;
-    LC_CUDA_CHECK(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (g_device_checked.load(std::memory_order_acquire) & bit) return;
     cudaDeviceProp prop;
     LC_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) {
@@ -37,10 +25,55 @@ void ensure_device()
                 dev, prop.name, prop.major, prop.minor);
         abort();
     }
-    if (getenv("LIQUID_CUDA_VERBOSE"))      // one line when the library takes over a process (e.g. under LD_PRELOAD)
+    if (getenv("LIQUID_CUDA_VERBOSE"))      // one line when the library takes over a device (e.g. under LD_PRELOAD)
         fprintf(stderr, "liquid_cuda: active on device %d (%s, sm_%d%d, %d SMs)\n", dev, prop.name, prop.major, prop.minor,
                 prop.multiProcessorCount);
-    g_device_ready.store(1, std::memory_order_release);
+    g_device_checked.fetch_or(bit, std::memory_order_acq_rel);
+}
+
+void ensure_device()
+{
+    static thread_local int t_ready_for = -2;          // the chosen device this thread was last aligned with
+    const int chosen = g_chosen_device.load(std::memory_order_acquire);
+    if (t_ready_for == chosen && chosen != -1) return;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        fprintf(stderr, "liquid_cuda: no CUDA device available (%s); this library has no CPU fallback\n",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        abort();
+    }
+    int dev = chosen;
+    if (dev == -1) {
+        if (const char *env = getenv("LIQUID_CUDA_DEVICE")) {
+            dev = atoi(env);
+            if (dev < 0 || dev >= count) {
+                fprintf(stderr, "liquid_cuda: LIQUID_CUDA_DEVICE=%s out of range (have %d devices)\n", env, count);
+                abort();
+            }
+            int expected = -1;
+            g_chosen_device.compare_exchange_strong(expected, dev);
+            dev = g_chosen_device.load();
+        }
+    }
+    if (dev >= 0) {
+        LC_CUDA_CHECK(cudaSetDevice(dev));
+        t_ready_for = dev;
+    } else {
+        LC_CUDA_CHECK(cudaGetDevice(&dev));            // no choice made: the thread's own current device
+    }
+    check_device(dev);
+}
+
+void choose_device(int dev)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || dev < 0 || dev >= count) {
+        fprintf(stderr, "liquid_cuda: liquid_cuda_set_device(%d): no such device (have %d)\n", dev, count);
+        abort();
+    }
+    g_chosen_device.store(dev, std::memory_order_release);
+    ensure_device();
 }
 
 }  // namespace lc
@@ -77,11 +110,7 @@ int liquid_cuda_device_count(void)
     return count;
 }
 
-void liquid_cuda_set_device(int _device)
-{
-    LC_CUDA_CHECK(cudaSetDevice(_device));
-    lc::ensure_device();
-}
+void liquid_cuda_set_device(int _device) { lc::choose_device(_device); }
 
 void *liquid_cuda_malloc(unsigned long long _bytes)
 {

@@ -43,6 +43,12 @@ def refrn2():
 
 
 @pytest.fixture(scope="session")
+def refr2():
+    """fixtures added in round 2 from the compiled reference (oracle/gen_golden_r2.py)"""
+    return dict(np.load(os.path.join(GOLDEN, "ref_outputs_r2.npz")))
+
+
+@pytest.fixture(scope="session")
 def orc():
     """the CPU oracle (checker only)"""
     from oracle import oracle as O

@@ -464,6 +464,27 @@ def test_firpfb_reference_kat_and_oracle(L, orc, kat):
     assert np.abs(got - want).max() < 2e-6
 
 
+def test_firpfb_rnyquist_and_drnyquist_vs_reference_fixture(L, refr2):
+    """firpfb_crcf_create_rnyquist / _create_drnyquist (firpfb.c:146-239): push + execute against the compiled
+    reference's outputs on the same input, sample by sample and as one block"""
+    tags = sorted(k[:-5] for k in refr2 if k.startswith("pfbd_") and k.endswith("_args"))
+    assert len(tags) == 8
+    for tag in tags:
+        ftype, M, k, m, beta = refr2[tag + "_args"]
+        x, want = refr2[tag + "_x"], refr2[tag + "_y"]
+        make = L.firpfb_crcf.create_drnyquist if "_drnyquist_" in tag else L.firpfb_crcf.create_rnyquist
+        q = make(int(ftype), int(M), int(k), int(m), np.float32(beta))
+        idx = (7 * np.arange(x.size) + 3) % int(M)
+        got = q.execute_block(x, idx)
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() < 3e-6 * scale, tag
+        q.reset()
+        for n in range(40):
+            q.push(x[n])
+            assert abs(q.execute(int(idx[n])) - want[n]) < 3e-6 * scale, (tag, n)
+        q.destroy()
+
+
 @pytest.mark.parametrize("M,m", [(8, 4), (32, 6), (33, 3), (64, 11)])
 def test_firpfb_long_blocks_tiled_kernel(L, orc, monkeypatch, M, m):
     """long blocks take the shared-memory tiled kernel: bit for bit against the plain kernel (arbitrary filter index per
