@@ -181,6 +181,24 @@ void ofdmframegen_write_S1(ofdmframegen _q, liquid_float_complex *_y);
 void ofdmframegen_writesymbol(ofdmframegen _q, liquid_float_complex *_x, liquid_float_complex *_y);
 void ofdmframegen_writetail(ofdmframegen _q, liquid_float_complex *_x);
 
+/* ---- ofdmframesync: liquid.h:5878-5911 -> src/multichannel/src/ofdmframesync.c.  Acquisition (the PLCP search and the
+ *      equalizer fit) runs on the host as in the reference; the payload state -- NCO mix, M-point transform, equalizer
+ *      product, pilot phase fit, de-rotation, NCO feedback, for every symbol left in an execute() call -- is one
+ *      device launch, and the callbacks are made in order afterwards (csrc/ofdmframesync.cu). */
+typedef int (*ofdmframesync_callback)(liquid_float_complex *_y, unsigned char *_p, unsigned int _M, void *_userdata);
+typedef struct ofdmframesync_s * ofdmframesync;
+ofdmframesync ofdmframesync_create(unsigned int _M, unsigned int _cp_len, unsigned int _taper_len, unsigned char *_p,
+                                   ofdmframesync_callback _callback, void *_userdata);
+void ofdmframesync_destroy(ofdmframesync _q);
+void ofdmframesync_print(ofdmframesync _q);
+void ofdmframesync_reset(ofdmframesync _q);
+void ofdmframesync_execute(ofdmframesync _q, liquid_float_complex *_x, unsigned int _n);
+float ofdmframesync_get_rssi(ofdmframesync _q);
+float ofdmframesync_get_cfo(ofdmframesync _q);
+void ofdmframesync_debug_enable(ofdmframesync _q);
+void ofdmframesync_debug_disable(ofdmframesync _q);
+void ofdmframesync_debug_print(ofdmframesync _q, const char *_filename);
+
 /* ---- fftfilt_crcf (FIR filtering through 2n-point transforms): liquid.h:2192-2232 -> src/filter/src/fftfilt.c:68-266.
  *      SURVEY.md 8(f) item 3.  x and y must not overlap in the device-pointer form. */
 typedef struct fftfilt_crcf_s * fftfilt_crcf;
@@ -419,6 +437,10 @@ void firpfbch_crcf_execute_streams_dev(firpfbch_crcf _q, const void *_d_x, unsig
 unsigned int firpfbch_crcf_get_state_len(firpfbch_crcf _q);
 void firpfbch_crcf_get_state(firpfbch_crcf _q, liquid_float_complex *_hist);
 void firpfbch_crcf_set_state(firpfbch_crcf _q, const liquid_float_complex *_hist);
+
+/* ---- ofdmframesync: 1 while the object is in the payload state (between the long training symbol and the callback
+ *      that ends the frame) ---- */
+int ofdmframesync_is_frame_open(ofdmframesync _q);
 
 /* ---- firdecim_crcf / firinterp_crcf: device-pointer forms (_n = outputs for firdecim, inputs for firinterp) ---- */
 void firdecim_crcf_execute_block_dev(firdecim_crcf _q, const void *_d_x, unsigned long long _n, void *_d_y, void *_stream);

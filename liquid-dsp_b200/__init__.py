@@ -168,6 +168,18 @@ _sig("ofdmframegen_writesymbol", None, _vp, _cf_p, _cf_p)
 _sig("ofdmframegen_writesymbols", None, _vp, _vp, _u, _vp)
 _sig("ofdmframegen_writesymbols_dev", None, _vp, _vp, _ull, _vp, _vp)
 _sig("ofdmframegen_writetail", None, _vp, _cf_p)
+OFDMFRAMESYNC_CALLBACK = C.CFUNCTYPE(C.c_int, C.POINTER(_cf), C.POINTER(C.c_ubyte), C.c_uint, C.c_void_p)
+_sig("ofdmframesync_create", _vp, _u, _u, _u, _vp, OFDMFRAMESYNC_CALLBACK, _vp)
+_sig("ofdmframesync_destroy", None, _vp)
+_sig("ofdmframesync_print", None, _vp)
+_sig("ofdmframesync_reset", None, _vp)
+_sig("ofdmframesync_execute", None, _vp, _vp, _u)
+_sig("ofdmframesync_get_rssi", _fl, _vp)
+_sig("ofdmframesync_get_cfo", _fl, _vp)
+_sig("ofdmframesync_debug_enable", None, _vp)
+_sig("ofdmframesync_debug_disable", None, _vp)
+_sig("ofdmframesync_debug_print", None, _vp, C.c_char_p)
+_sig("ofdmframesync_is_frame_open", _i, _vp)
 _sig("fftfilt_crcf_create", _vp, _f_p, _u, _u)
 _sig("fftfilt_crcf_destroy", None, _vp)
 _sig("fftfilt_crcf_reset", None, _vp)
@@ -832,6 +844,43 @@ def ofdmframe_init_default_sctype(M):
     p = np.empty(M, np.uint8)
     lib.ofdmframe_init_default_sctype(M, p)
     return p
+
+
+class ofdmframesync(_Handle):
+    """liquid.h:5878-5911 (src/multichannel/src/ofdmframesync.c).  callback(row, p) -> int receives every equalised
+    symbol as a complex64 array of M subcarriers (a copy) and the allocation; a non-zero return ends the frame."""
+    _destroy = "ofdmframesync_destroy"
+
+    def __init__(self, M, cp_len, taper_len, p=None, callback=None):
+        self.M, self.cp, self.tl = M, cp_len, taper_len
+        self._p = None if p is None else np.ascontiguousarray(p, np.uint8)
+        self._user_cb = callback
+
+        def _cb(yp, pp, m, ud):
+            if self._user_cb is None:
+                return 0
+            row = np.ctypeslib.as_array(C.cast(yp, C.POINTER(C.c_float)), shape=(2 * m,)).view(np.complex64).copy()
+            alloc = np.ctypeslib.as_array(pp, shape=(m,)).copy()
+            return int(self._user_cb(row, alloc) or 0)
+        self._cb = OFDMFRAMESYNC_CALLBACK(_cb)         # kept alive with the object
+        super().__init__(lib.ofdmframesync_create(M, cp_len, taper_len, None if self._p is None else self._p.ctypes.data,
+                                                  self._cb, None))
+
+    def reset(self):
+        lib.ofdmframesync_reset(self._h)
+
+    def execute(self, x):
+        x = _c64(x)
+        lib.ofdmframesync_execute(self._h, _ptr(x), x.size)
+
+    def get_cfo(self):
+        return lib.ofdmframesync_get_cfo(self._h)
+
+    def get_rssi(self):
+        return lib.ofdmframesync_get_rssi(self._h)
+
+    def is_frame_open(self):
+        return bool(lib.ofdmframesync_is_frame_open(self._h))
 
 
 class ofdmframegen(_Handle):

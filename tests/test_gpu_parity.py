@@ -1221,3 +1221,54 @@ def test_reference_example_program_unmodified_on_the_drop_in(L, name, tmp_path):
     ref, got = outs
     assert ref.shape == got.shape and ref.size > 50
     assert np.abs(ref - got).max() <= 2e-5 * max(1.0, np.abs(ref).max()), name
+
+
+# ------------------------------------------------------------------ ofdmframesync (receive side)
+@pytest.mark.parametrize("tag", ["osync_M64", "osync_M256", "osync_M48", "osync_M1024"])
+def test_ofdmframesync_rows_vs_reference_fixture(L, refr2, tag):
+    """ofdmframegen -> channel (delay, gain, carrier offset, noise) -> ofdmframesync: every row the callback receives
+    against the rows the compiled reference's callback received on the same samples, fed in the same uneven chunks
+    (acquisition on the host, the payload symbols in one device launch per execute() call)"""
+    M, cp, taper, nsym, cfo_ref = refr2[tag + "_args"]
+    M, cp, taper, nsym = int(M), int(cp), int(taper), int(nsym)
+    y, chunks, want = refr2[tag + "_y"], [int(c) for c in refr2[tag + "_chunks"]], refr2[tag + "_rows"]
+    rows = []
+    q = L.ofdmframesync(M, cp, taper, None, lambda row, p: rows.append(row) or 0)
+    pos = k = 0
+    while pos < y.size:
+        c = chunks[k % len(chunks)]
+        k += 1
+        q.execute(y[pos: pos + c])
+        pos += c
+    assert len(rows) >= nsym, (len(rows), nsym)
+    got = np.array(rows[:nsym])
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() < 2e-4 * scale, float(np.abs(got - want).max() / scale)
+    # (the fixture's carrier offset is read after the three all-noise symbols that follow the frame, whose pilot
+    # phases are arbitrary: only its neighbourhood is comparable)
+    assert abs(q.get_cfo() - cfo_ref) < 1e-2
+    q.destroy()
+
+
+def test_ofdmframesync_callback_ends_frames(L, refr2):
+    """two frames in one stream; the callback returns 1 after the last data symbol of each: the rows after it are dropped,
+    the object goes back to acquisition inside the same execute() call and finds the second frame"""
+    M, cp, taper, nsym, _ = [int(v) for v in refr2["osync_two_args"]]
+    y, chunks, want = refr2["osync_two_y"], [int(c) for c in refr2["osync_two_chunks"]], refr2["osync_two_rows"]
+    rows = []
+
+    def cb(row, p):
+        rows.append(row)
+        return 1 if len(rows) % nsym == 0 else 0
+    q = L.ofdmframesync(M, cp, taper, None, cb)
+    pos = k = 0
+    while pos < y.size:
+        c = chunks[k % len(chunks)]
+        k += 1
+        q.execute(y[pos: pos + c])
+        pos += c
+    assert len(rows) == len(want) == 2 * nsym
+    got = np.array(rows)
+    assert np.abs(got - want).max() < 2e-4 * np.abs(want).max()
+    assert not q.is_frame_open()
+    q.destroy()
