@@ -25,6 +25,7 @@ def _header_functions():
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"//[^\n]*", "", src)
     src = re.sub(r"^\s*#.*$", "", src, flags=re.M)            # preprocessor lines
+    src = re.sub(r"typedef\s+[^;]*\(\s*\*\s*\w+\s*\)\s*\([^;]*\)\s*;", "", src)   # function-pointer typedefs (callbacks)
     names = set()
     for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", src):
         names.add(m.group(1))
