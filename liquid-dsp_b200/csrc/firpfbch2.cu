@@ -18,6 +18,7 @@
 #include "host_pipeline.cuh"
 #include "pfbch2_fused.cuh"
 #include "pfbch2_cluster.cuh"
+#include "pfbch2_tile.cuh"
 
 struct firpfbch2_crcf_s {
     int type;
@@ -29,6 +30,7 @@ struct firpfbch2_crcf_s {
     float2 *d_tw_fused = nullptr;  // fused kernel's inter-stage twiddles
     bool fused = false;            // M = 1024: one CTA per frame (pfbch2_fused.cu)
     bool clustered = false;        // M = 4096: one frame per cluster of 8 CTAs (pfbch2_cluster.cu)
+    bool tiled = false;            // M = 64 ... 512: register windows + shared-memory tile of 8 frames (pfbch2_tile.cu)
     float2 *d_hist = nullptr;      // last H samples (analyzer: inputs; synthesizer: scaled IDFT rows)
     int flag = 0;                  // frame parity (firpfbch2.c:57)
     lc::FftPlanDev fft;            // M-point backward transform
@@ -50,6 +52,9 @@ void analyze_dev(firpfbch2_crcf q, const float2 *d_hist, const float2 *d_x, int 
     else if (q->clustered && n_frames >= 32 && !getenv("LIQUID_CUDA_NO_FUSED"))
         done = (unsigned long long)lc::pfb::launch_pfbch2_cluster(d_hist, d_x, (int)q->H, q->d_taps_scaled, q->d_tw_fused,
                                                                   d_y, q->M, q->L, n_frames, parity0, st);
+    else if (q->tiled && !getenv("LIQUID_CUDA_NO_FUSED"))
+        done = (unsigned long long)lc::pfb::launch_pfbch2_tile(d_hist, d_x, (int)q->H, q->d_taps_scaled, q->d_tw_fused,
+                                                               d_y, q->M, q->L, n_frames, parity0, st);
     if (done == n_frames) return;
     // shape-generic path (and the few frames the fused kernels leave)
     float2 *d_yr = d_y + done * q->M;
@@ -124,19 +129,22 @@ firpfbch2_crcf firpfbch2_crcf_create(int _type, unsigned int _M, unsigned int _m
     LC_CUDA_CHECK(cudaMemcpy(q->d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
     const bool want_fused = _type == LIQUID_ANALYZER && lc::pfb::fused_pfbch2_supported(M, L);
     const bool want_cluster = _type == LIQUID_ANALYZER && lc::pfb::cluster_pfbch2_supported(M, L);
-    if (want_fused || want_cluster) {
+    const bool want_tile = _type == LIQUID_ANALYZER && lc::pfb::tile_pfbch2_supported(M, L);
+    if (want_fused || want_cluster || want_tile) {
         // the fused kernels fold the 1/M output scale into the taps (exact: M is a power of two)
         std::vector<float> ts(taps);
         for (float &v : ts) v *= 1.0f / (float)M;
         LC_CUDA_CHECK(cudaMalloc(&q->d_taps_scaled, ts.size() * sizeof(float)));
         LC_CUDA_CHECK(cudaMemcpy(q->d_taps_scaled, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice));
         std::vector<float2> tw;
-        if (want_fused) lc::pfb::fused_pfbch2_make_twiddles(tw);
-        else            lc::pfb::cluster_pfbch2_make_twiddles(tw);
+        if (want_fused)        lc::pfb::fused_pfbch2_make_twiddles(tw);
+        else if (want_cluster) lc::pfb::cluster_pfbch2_make_twiddles(tw);
+        else                   lc::pfb::tile_pfbch2_make_twiddles(tw, M);
         LC_CUDA_CHECK(cudaMalloc(&q->d_tw_fused, tw.size() * sizeof(float2)));
         LC_CUDA_CHECK(cudaMemcpy(q->d_tw_fused, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
         q->fused = want_fused;
         q->clustered = want_cluster;
+        q->tiled = want_tile;
     }
     LC_CUDA_CHECK(cudaMalloc(&q->d_hist, sizeof(float2) * q->H));
     q->fft.init(M, +1);                            // backward, unscaled (firpfbch2.c:115)

@@ -1,0 +1,308 @@
+// pfbch2_tile.cu -- fused firpfbch2_crcf analysis kernels for M = 64, 128, 256, 512 (sm_100a): the shapes of the
+// reference's own benchmark (src/multichannel/bench/firpfbch2_crcf_benchmark.c:70-82) below the M = 1024 kernel.
+//
+// These sizes are HBM-bound (24 B per input sample against 16m + 10 log2 M flops), so the kernel reads every
+// sample once, writes every output once and keeps the transform input in shared memory:
+//
+//   phase 1  thread u (< M/2) owns the window pair (u, u + M/2).  The pair receives ONE stream sample per frame,
+//            s_T = x[T M/2 + M/2-1-u], alternately into its two windows, so with the 2m taps of the two branches
+//            (hA = branch u, hB = branch u + M/2) and a register window of the last 4m-1 + 8 samples
+//                d1 = sum_n hA[n] s_{T-2n},   d2 = sum_n hB[n] s_{T-1-2n}
+//            are the pair's two dot products of frame T -- (X[u], X[u+M/2]) = (d1, d2) on even frames, (d2, d1) on
+//            odd ones (firpfbch2.c:253-271).  The thread also does the first radix-2 decimation-in-frequency stage
+//            of the M-point backward transform on its own two values (z0 = X[u] + X[u+M/2], z1 = (X[u] - X[u+M/2])
+//            W_M^u), which leaves two independent M/2-point problems per frame in the shared tile (8 frames).
+//   phase 2  M/16 threads per frame (all M/2 threads busy on a tile of 8 frames): each M/2-point problem is
+//            16 x R2 (R2 = M/32): a 16-point register DFT down a column, the inter-pass twiddle, an in-place
+//            transposition (rows padded to R2 + 1: every access conflict-free), R2-point register DFTs along the
+//            rows, and the outputs Y[2 (k1 + 16 k2) + p] leave as 32-byte (M = 64) to 256-byte (M = 512) runs.
+//   An instance (M/2 threads; 256 / (M/2) instances per CTA) walks consecutive tiles carrying its window in registers;
+//   the 1/M output scale is folded into the taps (exact: M is a power of two).
+//
+// Reference semantics: src/multichannel/src/firpfbch2.c:244-282 (see firpfbch2.cu).
+#include "pfbch2_tile.cuh"
+#include "fused_common.cuh"
+
+#include <cmath>
+
+namespace {
+
+using namespace lcf;
+
+constexpr int kThreads = 256;
+constexpr int kFr = 8;                          // frames per tile
+constexpr int kStages = 2;                      // input ring: the next tile is in flight while this one is computed
+
+// Tile layout (8-byte units): address = f*FS + p*SS + row*PR + col for frame f, sub-problem p, row < 16, col < R2.
+// (PR, SS, FS) come from tools/tile_layout_search.py: with them every shared-memory access pattern of the kernel
+// (phase-1 stores, pass-A column reads / writes, pass-B row reads) costs the minimum number of wavefronts, or
+// 4 % more (M <= 256); rows padded to R2 + 1 alone leave the sub-problems and frames a multiple of 16 units
+// apart, which put the lanes of a warp on 2 - 8 banks (776 instead of 100 wavefronts per tile at M = 64).
+// WIDE: pass B takes its rows in the order (frame, row, sub-problem) across the whole instance, so that a warp
+// store covers 256 contiguous bytes of one output frame whatever M is (grouped order: 16 R2 bytes).
+template <int M> struct TileLayout;
+template <> struct TileLayout<64>  { static constexpr int PR = 3,  SS = 56,  FS = 106, WIDE = 1; };
+template <> struct TileLayout<128> { static constexpr int PR = 5,  SS = 88,  FS = 172, WIDE = 1; };
+template <> struct TileLayout<256> { static constexpr int PR = 9,  SS = 152, FS = 295, WIDE = 0; };
+template <> struct TileLayout<512> { static constexpr int PR = 17, SS = 280, FS = 551, WIDE = 0; };
+
+struct TileArgs {
+    const float2 *hist;        // H samples preceding x[0], or null = zero state
+    const float2 *x;
+    float2 *y;                 // [n_frames][M]
+    const float *taps;         // [2][L][M] analyzer table (firpfbch2.cu), pre-scaled by 1/M; parity 0 half is used
+    const float2 *tw;          // tw2[u] = e^{+j 2 pi u / M}, u < M/2; then twp[k1][r2] = e^{+j 2 pi k1 r2 / (M/2)}
+    long long n_frames;
+    int H;
+    int par0;                  // parity of the first frame
+    int n_tiles;               // ceil(n_frames / 8): the last tile may be ragged
+    int tiles_per_inst;
+};
+
+__device__ __forceinline__ float2 ld_hist0(const float2 *__restrict__ hist, const float2 *__restrict__ x, long long idx, int H)
+{
+    if (idx >= 0) return __ldg(x + idx);
+    if (hist != nullptr && H + idx >= 0) return __ldg(hist + (H + idx));
+    return make_float2(0.f, 0.f);
+}
+
+// 8-byte asynchronous copy global -> shared; n = 0 writes zeros without touching src
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src, uint32_t n)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int M>
+constexpr size_t tile_smem_bytes()
+{
+    return sizeof(float2) * ((size_t)kStages * kFr * kThreads + (size_t)(kThreads / (M / 2)) * kFr * TileLayout<M>::FS);
+}
+
+template <int M, int L>
+__global__ void __launch_bounds__(kThreads, ((L <= 4 && M >= 128) ? 3 : (L <= 10 ? 2 : 1))) pfbch2_tile_kernel(const TileArgs a)
+{
+    using LY = TileLayout<M>;
+    constexpr int M2 = M / 2;                   // threads per instance = window pairs = sub-problem size
+    constexpr int R2 = M2 / 16;                 // second factor of the M/2-point transform
+    constexpr int PR = LY::PR, SS = LY::SS, FS = LY::FS;
+    constexpr int HL = 2 * L - 1;               // frames of history a frame looks back at
+    static_assert(R2 >= 2 && R2 <= 16, "M must be 64, 128, 256 or 512");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *ring = reinterpret_cast<float2 *>(smem_raw);          // [kStages][kFr][kThreads]: a thread's own samples
+
+    const int inst_l = threadIdx.x / M2, u = threadIdx.x % M2;
+    float2 *tile = ring + kStages * kFr * kThreads + inst_l * (kFr * FS);
+    const long long inst = (long long)blockIdx.x * (kThreads / M2) + inst_l;
+    const long long t0 = inst * a.tiles_per_inst;
+    long long ntl = (long long)a.n_tiles - t0;
+    if (ntl > a.tiles_per_inst) ntl = a.tiles_per_inst;
+    const int nt = ntl > 0 ? (int)ntl : 0;                        // uniform within an instance (a set of whole warps)
+    if (nt == 0) return;
+
+    auto inst_barrier = [&]() {
+        if (M2 == kThreads) __syncthreads();
+        else if (M2 == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + inst_l), "n"(M2) : "memory");
+    };
+    // tile `it` of this instance -> ring stage it % kStages (8 bytes per frame and thread; frames past the end of
+    // the block, and tiles past the instance's range, arrive as zeros)
+    const uint32_t ring_u32 = smem_u32(ring + threadIdx.x);
+    const float2 *xs = a.x + (M2 - 1 - u);
+    auto fetch = [&](int it) {
+        const long long f0 = (t0 + it) * kFr;
+        const uint32_t dst = ring_u32 + (uint32_t)((it % kStages) * kFr * kThreads * sizeof(float2));
+#pragma unroll
+        for (int f = 0; f < kFr; f++) {
+            const bool ok = it < nt && f0 + f < a.n_frames;
+            cp_async8(dst + f * kThreads * (int)sizeof(float2), ok ? (const void *)(xs + (f0 + f) * M2) : (const void *)a.x, ok ? 8u : 0u);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < kStages - 1; s++) fetch(s);
+
+    float hA[L], hB[L];
+#pragma unroll
+    for (int n = 0; n < L; n++) {
+        hA[n] = __ldg(a.taps + n * M + u);
+        hB[n] = __ldg(a.taps + n * M + u + M2);
+    }
+    const float2 w2 = __ldg(a.tw + u);                            // W_M^u
+    float2 win[HL + kFr];
+    {
+        const long long f0 = t0 * kFr;
+#pragma unroll
+        for (int i = 0; i < HL; i++) win[i] = ld_hist0(a.hist, a.x, (f0 - HL + i) * M2 + (M2 - 1 - u), a.H);
+    }
+    // pass-A role inside the instance: frame f2, sub-problem p2 (fastest), column t2
+    const int f2 = u / (2 * R2), p2 = u & 1, t2 = (u % (2 * R2)) >> 1;
+    const float2 *twp = a.tw + M2 + t2;                           // twp[k1][r2 = t2] at + R2 k1
+    float2 *mac_dst = tile + (u / R2) * PR + (u % R2);            // where z_p[u] lives: row u / R2, column u % R2
+    float2 *sp = tile + f2 * FS + p2 * SS;
+
+    for (int it = 0; it < nt; it++) {
+        const long long f0 = (t0 + it) * kFr;                     // first (local) frame of the tile: even
+        fetch(it + kStages - 1);
+        cp_async_wait<kStages - 1>();
+        // ---- phase 1
+        {
+            const float2 *src = ring + (it % kStages) * kFr * kThreads + threadIdx.x;
+#pragma unroll
+            for (int f = 0; f < kFr; f++) win[HL + f] = src[f * kThreads];
+        }
+#pragma unroll
+        for (int f = 0; f < kFr; f++) {
+            float2 d1 = make_float2(0.f, 0.f), d2 = d1;
+#pragma unroll
+            for (int n = L - 1; n >= 0; n--) {
+                d1 = __ffma2_rn(bc(hA[n]), win[HL + f - 2 * n], d1);
+                d2 = __ffma2_rn(bc(hB[n]), win[HL + f - 1 - 2 * n], d2);
+            }
+            // radix-2 DIF stage: z0 = X[u] + X[u+M/2] = d1 + d2 on every frame; z1 = +-(d1 - d2) W_M^u (+ on even frames)
+            const float2 z0 = __fadd2_rn(d1, d2);
+            const bool odd = ((a.par0 + f) & 1) != 0;             // f0 is even
+            const float2 df = odd ? __fadd2_rn(d2, neg2(d1)) : __fadd2_rn(d1, neg2(d2));
+            mac_dst[f * FS] = z0;
+            mac_dst[f * FS + SS] = cmul2_rot(df, w2);
+        }
+#pragma unroll
+        for (int i = 0; i < HL; i++) win[i] = win[kFr + i];
+        inst_barrier();
+        // ---- phase 2: sub-problem p2 of frame f2; pass A down column t2 (in place: a thread reads and writes its own column)
+        float2 v[16];
+#pragma unroll
+        for (int r1 = 0; r1 < 16; r1++) v[r1] = sp[r1 * PR + t2];
+        RegDft<16, +1>::run(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul2_rot(v[k1], __ldg(twp + R2 * k1));
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) sp[k1 * PR + t2] = v[k1];
+        if (LY::WIDE) {
+            // pass B over the whole instance: item j = (frame, row k1, sub-problem), sub-problem fastest
+            inst_barrier();
+#pragma unroll
+            for (int i = 0; i < 32 * kFr / M2; i++) {
+                const int j = u + M2 * i;
+                const int f = j >> 5, k1 = (j & 31) >> 1;
+                const float2 *row = tile + f * FS + (j & 1) * SS + k1 * PR;
+                float2 r[R2];
+#pragma unroll
+                for (int c = 0; c < R2; c++) r[c] = row[c];
+                RegDft<R2, +1>::run(r);
+                if (f0 + f < a.n_frames) {
+                    float2 *yf = a.y + (f0 + f) * M + (j & 31);
+#pragma unroll
+                    for (int k2 = 0; k2 < R2; k2++) __stcs(yf + 32 * k2, r[k2]);
+                }
+            }
+        } else {
+            // pass B inside the 2 R2 lanes of the sub-problem: rows k1 = t2 + R2 i
+            __syncwarp();
+            float2 *yf = a.y + (f0 + f2) * M + p2;
+            const bool live = f0 + f2 < a.n_frames;
+#pragma unroll
+            for (int i = 0; i < 16 / R2; i++) {
+                const int k1 = t2 + R2 * i;
+                float2 r[R2];
+#pragma unroll
+                for (int c = 0; c < R2; c++) r[c] = sp[k1 * PR + c];
+                RegDft<R2, +1>::run(r);
+                if (live) {
+#pragma unroll
+                    for (int k2 = 0; k2 < R2; k2++) __stcs(yf + 2 * (k1 + 16 * k2), r[k2]);
+                }
+            }
+        }
+        inst_barrier();
+    }
+    cp_async_wait<0>();
+}
+
+template <int M, int L>
+void launch_ML(const TileArgs &a, unsigned int grid, cudaStream_t st)
+{
+    constexpr size_t smem = tile_smem_bytes<M>();
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_tile_kernel<M, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pfbch2_tile_kernel<M, L><<<grid, kThreads, smem, st>>>(a);
+}
+
+template <int M>
+void launch_M(const TileArgs &a, unsigned int L, unsigned int grid, cudaStream_t st)
+{
+    switch (L) {
+    case 4: launch_ML<M, 4>(a, grid, st); break;
+    case 8: launch_ML<M, 8>(a, grid, st); break;
+    case 10: launch_ML<M, 10>(a, grid, st); break;
+    case 14: launch_ML<M, 14>(a, grid, st); break;
+    default: lc::fatal("launch_pfbch2_tile", "unsupported tap count");
+    }
+}
+
+}  // namespace
+
+namespace lc {
+namespace pfb {
+
+bool tile_pfbch2_supported(unsigned int M, unsigned int L)
+{
+    return (M == 64 || M == 128 || M == 256 || M == 512) && (L == 4 || L == 8 || L == 10 || L == 14);
+}
+
+void tile_pfbch2_make_twiddles(std::vector<float2> &tw, unsigned int M)
+{
+    // tw2[u] = e^{+j 2 pi u / M}, u < M/2; then twp[k1][r2] = e^{+j 2 pi k1 r2 / (M/2)}, k1 < 16, r2 < M/32
+    const unsigned int M2 = M / 2, R2 = M2 / 16;
+    tw.resize(M2 + 16 * R2);
+    for (unsigned int u = 0; u < M2; u++) {
+        const double ang = 2.0 * M_PI * (double)u / (double)M;
+        tw[u] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    for (unsigned int k1 = 0; k1 < 16; k1++)
+        for (unsigned int r2 = 0; r2 < R2; r2++) {
+            const double ang = 2.0 * M_PI * (double)(k1 * r2) / (double)M2;
+            tw[M2 + k1 * R2 + r2] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+}
+
+long long launch_pfbch2_tile(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps_scaled, const float2 *d_tw,
+                             float2 *d_y, unsigned int M, unsigned int L, unsigned long long n_frames, int parity0,
+                             cudaStream_t st)
+{
+    const long long n_tiles = (long long)((n_frames + kFr - 1) / kFr);
+    if (n_tiles == 0 || n_tiles > (1ll << 30)) return 0;
+    TileArgs a;
+    a.hist = d_hist;
+    a.x = d_x;
+    a.y = d_y;
+    a.taps = d_taps_scaled;
+    a.tw = d_tw;
+    a.H = H;
+    a.n_frames = (long long)n_frames;
+    a.par0 = parity0 & 1;
+    a.n_tiles = (int)n_tiles;
+    // ~64 tiles (512 frames) per instance keeps the re-read of the 4m-1 history frames below 4 %, while leaving
+    // enough instances to fill the GPU; shrink for short blocks
+    const long long inst_per_cta = kThreads / (M / 2);
+    long long tpi = 64;
+    while (tpi > 1 && (n_tiles / tpi) < 148ll * 4 * inst_per_cta) tpi >>= 1;
+    a.tiles_per_inst = (int)tpi;
+    const long long n_inst = (n_tiles + tpi - 1) / tpi;
+    const unsigned int grid = (unsigned int)((n_inst + inst_per_cta - 1) / inst_per_cta);
+    switch (M) {
+    case 64: launch_M<64>(a, L, grid, st); break;
+    case 128: launch_M<128>(a, L, grid, st); break;
+    case 256: launch_M<256>(a, L, grid, st); break;
+    case 512: launch_M<512>(a, L, grid, st); break;
+    default: fatal("launch_pfbch2_tile", "unsupported channel count");
+    }
+    LC_LAUNCH_CHECK();
+    return (long long)n_frames;
+}
+
+}  // namespace pfb
+}  // namespace lc

@@ -1,0 +1,22 @@
+// pfbch2_tile.cuh -- launcher of the fused firpfbch2 analysis kernels for M = 64 ... 512 (pfbch2_tile.cu).
+#pragma once
+#include "lc_common.cuh"
+
+namespace lc {
+namespace pfb {
+
+// shapes the tile kernel is instantiated for (M = 64 / 128 / 256 / 512, L = 2m = 4 / 8 / 10 / 14)
+bool tile_pfbch2_supported(unsigned int M, unsigned int L);
+
+// twiddle table the kernel expects (uploaded once per object)
+void tile_pfbch2_make_twiddles(std::vector<float2> &tw, unsigned int M);
+
+// Runs the kernel over the largest multiple of 8 frames <= n_frames and returns how many frames it covered
+// (the caller finishes the remaining 0..7 frames with the generic kernels).
+// d_taps_scaled: analyzer tap table [2][L][M] already multiplied by 1/M.
+long long launch_pfbch2_tile(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps_scaled,
+                             const float2 *d_tw, float2 *d_y, unsigned int M, unsigned int L,
+                             unsigned long long n_frames, int parity0, cudaStream_t st);
+
+}  // namespace pfb
+}  // namespace lc

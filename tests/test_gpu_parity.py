@@ -586,6 +586,33 @@ def test_pfbch2_fused_matches_generic_path(L, orc, monkeypatch):
     assert np.abs(fused - generic).max() < 1e-6
 
 
+# ------------------------------------------------------------------ tile kernels, M = 64 ... 512 (pfbch2_tile.cu)
+@pytest.mark.parametrize("M,m", [(64, 2), (64, 4), (64, 5), (64, 7), (128, 2), (128, 5), (256, 2), (256, 4), (256, 7),
+                                 (512, 2), (512, 5), (512, 7)])
+def test_pfbch2_tile_vs_oracle_odd_splits_and_generic(L, orc, monkeypatch, M, m):
+    """the reference's own benchmark shapes (firpfbch2_crcf_benchmark.c:70-82) and longer filters on the tile kernel:
+    odd start parity, frame counts that are not a multiple of the 8-frame tile, several instances with ragged
+    tile counts, state carried between calls; and against the shape-generic path"""
+    nfr = 65 + 200 + 1283
+    x = orc.synth_input(nfr * M // 2, seed=0x71 + M + m)
+    want = orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0).execute_frames(x)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    l0 = L.launch_count()
+    got = np.concatenate([q.execute_block(x[:65 * M // 2]), q.execute_block(x[65 * M // 2:265 * M // 2]),
+                          q.execute_block(x[265 * M // 2:])])
+    check_channels(got, want, x)
+    q.reset()
+    whole = q.execute_block(x)
+    check_channels(whole, want, x)
+    assert np.abs(whole - got).max() < 1e-6
+    monkeypatch.setenv("LIQUID_CUDA_NO_FUSED", "1")
+    q.reset()
+    generic = q.execute_block(x)
+    monkeypatch.delenv("LIQUID_CUDA_NO_FUSED")
+    assert rel_rms_per_channel(whole, generic).max() < 2e-6
+    assert np.abs(whole - generic).max() < 1e-6
+
+
 # ------------------------------------------------------------------ root-Nyquist Kaiser prototypes (SURVEY 8f item 1)
 def test_pfbch_rnyquist_kaiser_prototypes_vs_reference(L, orc, refrn):
     """firpfbch_crcf_create_rnyquist with ARKAISER / RKAISER against the compiled reference's outputs and

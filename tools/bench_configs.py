@@ -7,6 +7,7 @@ events, inputs larger than L2.  Not the driver's headline bench (that is bench.p
 
   c1 c2 c4 c5   BASELINE configs 1, 2, 4, 5 (c3 is bench.py)          c3m c5m  c3 / c5 against the filter length m
   g             shape-generic one-kernel analyzers (M = 256, 64, 2048)  s        synthesizers (firpfbch2 M=1024, firpfbch M=1024 / 256)
+  t             firpfbch2 tile kernels, M = 64 ... 512, m = 2 / 5 / 7
   fft           fft_execute_batch_dev, n = 16 / 256 / 1024 / 4096       d        dotprod_crcf batch entry point
   p             firpfb_crcf block form
   f1            firpfbch_cccf (8f item 1)                                f2       spgramcf_accumulate_psd (8f item 2)
@@ -175,6 +176,19 @@ def run(configs, steps, warmup, sink, device_index=0):
             L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
             ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
             report("g: firpfbch2_crcf analysis M=%d m=%d (shape-generic), 2^27 samples" % (M, m), n, 24, ms, ln)
+            del x, y
+    if "t" in args.configs:
+        # the reference's own benchmark shapes below M = 1024 (firpfbch2_crcf_benchmark.c:70-82: m = 2) and m = 5 / 7:
+        # the fused tile kernels of pfbch2_tile.cu
+        for M, m in ((64, 2), (64, 5), (128, 5), (256, 2), (256, 5), (512, 2), (512, 5), (512, 7)):
+            n = 1 << 28
+            q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+            H = q.get_state_len()
+            x = torch.zeros(2 * (H + n), dtype=torch.float32, device=dev)
+            y = torch.empty(4 * n, dtype=torch.float32, device=dev)
+            L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
+            ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
+            report("t: firpfbch2_crcf analysis M=%d m=%d (tile kernel), 2^28 samples" % (M, m), n, 24, ms, ln)
             del x, y
     if "f1" in args.configs:
         # firpfbch_cccf analysis, M=256, p=10, one stream of 2^27 samples --
