@@ -31,7 +31,7 @@ using namespace lcf;
 
 constexpr int kThreads = 256;
 constexpr int kFr = 8;                          // frames per tile
-constexpr int kStages = 2;                      // input ring: the next tile is in flight while this one is computed
+constexpr int kTwPitch = 18;                    // float2 per column of the shared twiddle table (144 B: 16-byte reads, conflict-free)
 
 // Tile layout (8-byte units): address = f*FS + p*SS + row*PR + col for frame f, sub-problem p, row < 16, col < R2.
 // (PR, SS, FS) come from tools/tile_layout_search.py: with them every shared-memory access pattern of the kernel
@@ -41,10 +41,14 @@ constexpr int kStages = 2;                      // input ring: the next tile is 
 // WIDE: pass B takes its rows in the order (frame, row, sub-problem) across the whole instance, so that a warp
 // store covers 256 contiguous bytes of one output frame whatever M is (grouped order: 16 R2 bytes).
 template <int M> struct TileLayout;
-template <> struct TileLayout<64>  { static constexpr int PR = 3,  SS = 56,  FS = 106, WIDE = 1; };
-template <> struct TileLayout<128> { static constexpr int PR = 5,  SS = 88,  FS = 172, WIDE = 1; };
-template <> struct TileLayout<256> { static constexpr int PR = 9,  SS = 152, FS = 295, WIDE = 0; };
-template <> struct TileLayout<512> { static constexpr int PR = 17, SS = 280, FS = 551, WIDE = 0; };
+// NBUF: tile buffers per instance.  Two buffers leave ONE instance barrier per tile (phase 1 of the next tile writes
+// the other buffer while slower warps are still in pass B); an instance that is a single warp (M = 64) needs none.
+// STAGES: input slots per thread: 1 = the next tile's 8 samples are in flight from the end of the MAC phase on,
+// 2 = a whole tile ahead.
+template <> struct TileLayout<64>  { static constexpr int PR = 3,  SS = 56,  FS = 106, WIDE = 1, NBUF = 1, STAGES = 2; };
+template <> struct TileLayout<128> { static constexpr int PR = 5,  SS = 88,  FS = 172, WIDE = 1, NBUF = 2, STAGES = 1; };
+template <> struct TileLayout<256> { static constexpr int PR = 9,  SS = 152, FS = 295, WIDE = 0, NBUF = 2, STAGES = 1; };
+template <> struct TileLayout<512> { static constexpr int PR = 17, SS = 280, FS = 551, WIDE = 0, NBUF = 2, STAGES = 1; };
 
 struct TileArgs {
     const float2 *hist;        // H samples preceding x[0], or null = zero state
@@ -78,51 +82,53 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int M>
 constexpr size_t tile_smem_bytes()
 {
-    return sizeof(float2) * ((size_t)kStages * kFr * kThreads + (size_t)(kThreads / (M / 2)) * kFr * TileLayout<M>::FS);
+    using LY = TileLayout<M>;
+    return sizeof(float2) * ((size_t)LY::STAGES * kFr * kThreads + (size_t)(kThreads / (M / 2)) * LY::NBUF * kFr * LY::FS
+                             + (size_t)(M / 32) * kTwPitch);
 }
 
 template <int M, int L>
-__global__ void __launch_bounds__(kThreads, ((L <= 4 && M >= 128) ? 3 : (L <= 10 ? 2 : 1))) pfbch2_tile_kernel(const TileArgs a)
+__global__ void __launch_bounds__(kThreads, (L <= 10 ? 2 : 1)) pfbch2_tile_kernel(const TileArgs a)
 {
     using LY = TileLayout<M>;
     constexpr int M2 = M / 2;                   // threads per instance = window pairs = sub-problem size
     constexpr int R2 = M2 / 16;                 // second factor of the M/2-point transform
-    constexpr int PR = LY::PR, SS = LY::SS, FS = LY::FS;
+    constexpr int PR = LY::PR, SS = LY::SS, FS = LY::FS, kStages = LY::STAGES, NBUF = LY::NBUF;
     constexpr int HL = 2 * L - 1;               // frames of history a frame looks back at
     static_assert(R2 >= 2 && R2 <= 16, "M must be 64, 128, 256 or 512");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *ring = reinterpret_cast<float2 *>(smem_raw);          // [kStages][kFr][kThreads]: a thread's own samples
 
     const int inst_l = threadIdx.x / M2, u = threadIdx.x % M2;
-    float2 *tile = ring + kStages * kFr * kThreads + inst_l * (kFr * FS);
+    float2 *tile0 = ring + kStages * kFr * kThreads + inst_l * (NBUF * kFr * FS);
+    float2 *tws = ring + kStages * kFr * kThreads + (kThreads / M2) * (NBUF * kFr * FS); // [R2][kTwPitch]: column t2's 16 twiddles
     const long long inst = (long long)blockIdx.x * (kThreads / M2) + inst_l;
     const long long t0 = inst * a.tiles_per_inst;
     long long ntl = (long long)a.n_tiles - t0;
     if (ntl > a.tiles_per_inst) ntl = a.tiles_per_inst;
     const int nt = ntl > 0 ? (int)ntl : 0;                        // uniform within an instance (a set of whole warps)
-    if (nt == 0) return;
 
     auto inst_barrier = [&]() {
         if (M2 == kThreads) __syncthreads();
         else if (M2 == 32) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(1 + inst_l), "n"(M2) : "memory");
     };
-    // tile `it` of this instance -> ring stage it % kStages (8 bytes per frame and thread; frames past the end of
-    // the block, and tiles past the instance's range, arrive as zeros)
+    // tile `it` of this instance -> the thread's own input slot (8 bytes per frame; frames past the end of the
+    // block, and tiles past the instance's range, arrive as zeros)
     const uint32_t ring_u32 = smem_u32(ring + threadIdx.x);
     const float2 *xs = a.x + (M2 - 1 - u);
     auto fetch = [&](int it) {
         const long long f0 = (t0 + it) * kFr;
-        const uint32_t dst = ring_u32 + (uint32_t)((it % kStages) * kFr * kThreads * sizeof(float2));
 #pragma unroll
         for (int f = 0; f < kFr; f++) {
             const bool ok = it < nt && f0 + f < a.n_frames;
-            cp_async8(dst + f * kThreads * (int)sizeof(float2), ok ? (const void *)(xs + (f0 + f) * M2) : (const void *)a.x, ok ? 8u : 0u);
+            cp_async8(ring_u32 + ((it % kStages) * kFr + f) * kThreads * (int)sizeof(float2), ok ? (const void *)(xs + (f0 + f) * M2) : (const void *)a.x, ok ? 8u : 0u);
         }
         cp_async_commit();
     };
-#pragma unroll
-    for (int s = 0; s < kStages - 1; s++) fetch(s);
+    fetch(0);
+    // the instance's copy of the inter-pass twiddles, by column: tws[t2][k1] = e^{+j 2 pi k1 t2 / (M/2)}
+    for (int i = u; i < 16 * R2; i += M2) tws[(i % R2) * kTwPitch + i / R2] = __ldg(a.tw + M2 + i);
 
     float hA[L], hB[L];
 #pragma unroll
@@ -132,20 +138,22 @@ __global__ void __launch_bounds__(kThreads, ((L <= 4 && M >= 128) ? 3 : (L <= 10
     }
     const float2 w2 = __ldg(a.tw + u);                            // W_M^u
     float2 win[HL + kFr];
-    {
+    if (nt > 0) {
         const long long f0 = t0 * kFr;
 #pragma unroll
         for (int i = 0; i < HL; i++) win[i] = ld_hist0(a.hist, a.x, (f0 - HL + i) * M2 + (M2 - 1 - u), a.H);
     }
     // pass-A role inside the instance: frame f2, sub-problem p2 (fastest), column t2
     const int f2 = u / (2 * R2), p2 = u & 1, t2 = (u % (2 * R2)) >> 1;
-    const float2 *twp = a.tw + M2 + t2;                           // twp[k1][r2 = t2] at + R2 k1
-    float2 *mac_dst = tile + (u / R2) * PR + (u % R2);            // where z_p[u] lives: row u / R2, column u % R2
-    float2 *sp = tile + f2 * FS + p2 * SS;
+    const float4 *twc = reinterpret_cast<const float4 *>(tws + t2 * kTwPitch);
+    const int mac_off = (u / R2) * PR + (u % R2);                 // where z_p[u] lives: row u / R2, column u % R2
+    const int sp_off = f2 * FS + p2 * SS;
+    __syncthreads();                                              // the twiddle copies of all instances
 
     for (int it = 0; it < nt; it++) {
         const long long f0 = (t0 + it) * kFr;                     // first (local) frame of the tile: even
-        fetch(it + kStages - 1);
+        float2 *tile = tile0 + (it % NBUF) * (kFr * FS);
+        if (kStages == 2) fetch(it + 1);
         cp_async_wait<kStages - 1>();
         // ---- phase 1
         {
@@ -153,6 +161,7 @@ __global__ void __launch_bounds__(kThreads, ((L <= 4 && M >= 128) ? 3 : (L <= 10
 #pragma unroll
             for (int f = 0; f < kFr; f++) win[HL + f] = src[f * kThreads];
         }
+        float2 *mac_dst = tile + mac_off;
 #pragma unroll
         for (int f = 0; f < kFr; f++) {
             float2 d1 = make_float2(0.f, 0.f), d2 = d1;
@@ -168,16 +177,24 @@ __global__ void __launch_bounds__(kThreads, ((L <= 4 && M >= 128) ? 3 : (L <= 10
             mac_dst[f * FS] = z0;
             mac_dst[f * FS + SS] = cmul2_rot(df, w2);
         }
+        if (kStages == 1) fetch(it + 1);                          // the slot's values are consumed: refill it
 #pragma unroll
         for (int i = 0; i < HL; i++) win[i] = win[kFr + i];
+        // with two buffers the one barrier of a tile: the instance's phase-1 stores are visible, and every warp has
+        // left pass B of the tile before (which read the other buffer -- the one phase 1 of the next tile writes)
         inst_barrier();
         // ---- phase 2: sub-problem p2 of frame f2; pass A down column t2 (in place: a thread reads and writes its own column)
+        float2 *sp = tile + sp_off;
         float2 v[16];
 #pragma unroll
         for (int r1 = 0; r1 < 16; r1++) v[r1] = sp[r1 * PR + t2];
         RegDft<16, +1>::run(v);
 #pragma unroll
-        for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul2_rot(v[k1], __ldg(twp + R2 * k1));
+        for (int k = 0; k < 8; k++) {
+            const float4 t = twc[k];                              // twiddles k1 = 2k, 2k + 1
+            if (k > 0) v[2 * k] = cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+            v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+        }
 #pragma unroll
         for (int k1 = 0; k1 < 16; k1++) sp[k1 * PR + t2] = v[k1];
         if (LY::WIDE) {
@@ -216,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, ((L <= 4 && M >= 128) ? 3 : (L <= 10
                 }
             }
         }
-        inst_barrier();
+        if (NBUF == 1) inst_barrier();
     }
     cp_async_wait<0>();
 }
