@@ -130,6 +130,13 @@ firpfbch2_crcf firpfbch2_crcf_create(int _type, unsigned int _M, unsigned int _m
     const bool want_fused = _type == LIQUID_ANALYZER && lc::pfb::fused_pfbch2_supported(M, L);
     const bool want_cluster = _type == LIQUID_ANALYZER && lc::pfb::cluster_pfbch2_supported(M, L);
     const bool want_tile = _type == LIQUID_ANALYZER && lc::pfb::tile_pfbch2_supported(M, L);
+    if (_type == LIQUID_SYNTHESIZER && lc::pfb::tile_pfbch2_synth_supported(M, 2 * L)) {
+        std::vector<float2> tw;
+        lc::pfb::tile_pfbch2_make_twiddles(tw, M);
+        LC_CUDA_CHECK(cudaMalloc(&q->d_tw_fused, tw.size() * sizeof(float2)));
+        LC_CUDA_CHECK(cudaMemcpy(q->d_tw_fused, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        q->tiled = true;
+    }
     if (want_fused || want_cluster || want_tile) {
         // the fused kernels fold the 1/M output scale into the taps (exact: M is a power of two)
         std::vector<float> ts(taps);
@@ -238,6 +245,12 @@ void firpfbch2_crcf_execute_block_dev(firpfbch2_crcf _q, const void *_d_x, unsig
     if (_q->type == LIQUID_ANALYZER) {
         analyze_dev(_q, _q->d_hist, (const float2 *)_d_x, _q->flag, _n_frames, (float2 *)_d_y, st);
         lc::roll_history(_q->d_hist, _q->H, _q->hist_tmp, (const float2 *)_d_x, _n_frames * _q->M2, st);
+    } else if (_q->tiled && _n_frames >= 2 * _q->L && !getenv("LIQUID_CUDA_NO_FUSED")) {
+        // fused synthesizer: the rows of v stay on the chip, the kernel leaves the last 4m of them as the new state
+        float2 *d_new = (float2 *)_q->hist_tmp.get(sizeof(float2) * _q->H);
+        lc::pfb::launch_pfbch2_tile_synth(_q->d_hist, (int)(_q->H / _q->M), (const float2 *)_d_x, _q->d_taps, _q->d_tw_fused,
+                                          (float2 *)_d_y, d_new, _q->M, 2 * _q->L, _n_frames, _q->flag, st);
+        LC_CUDA_CHECK(cudaMemcpyAsync(_q->d_hist, d_new, sizeof(float2) * _q->H, cudaMemcpyDeviceToDevice, st));
     } else {
         float2 *d_v = (float2 *)_q->scratch.get(sizeof(float2) * _n_frames * _q->M);
         synthesize_dev(_q, _q->d_hist, (const float2 *)_d_x, _q->flag, _n_frames, (float2 *)_d_y, d_v, st);

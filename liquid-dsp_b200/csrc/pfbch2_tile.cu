@@ -238,6 +238,224 @@ __global__ void __launch_bounds__(kThreads, (L <= 10 ? 2 : 1)) pfbch2_tile_kerne
     cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------- synthesizer
+// The synthesizer (firpfbch2.c:287-335) is the transposed flow graph of the analyzer, and so is its kernel:
+//   pass B'  R2-point register DFTs over the rows X_p[k1 + 16 k2] (read straight from the thread's input slot),
+//   pass A'  the inter-pass twiddle (times the reference's 1/M * M/2 = 1/2, exact) and a 16-point register DFT down
+//            each column: the tile then holds E_p[u] = sum_k X[2k + p] e^{+j 2 pi u k / (M/2)} / 2,
+//   FIR      thread u does the last radix-2 stage, v[u] = E_0[u] + W_M^u E_1[u], v[u + M/2] = E_0[u] - W_M^u E_1[u],
+//            pushes the two values into register windows of the last 4m rows of v in its two columns and forms the
+//            output y[t][u] = sum_q h[u + q M/2] v[t - q][u + (t odd ? M/2 : 0)] with packed FFMA2.
+// The rows of v never reach HBM (the two-kernel path writes and re-reads 16 B per output sample).  An instance that
+// starts inside the stream first transforms the ceil((4m-1)/8) tiles before its range to rebuild its windows; the
+// last 4m rows of v of a call are written out as the object's state.
+struct SynthArgs {
+    const float2 *hist;        // hist_rows rows of v preceding frame 0, or null = zero state
+    const float2 *x;           // [n_frames][M] channel samples
+    float2 *y;                 // [n_frames][M/2]
+    float2 *hist_out;          // [NT][M]: the rows of v of the last NT frames
+    const float *taps;         // [NT][M/2]: taps[q][i] = h[i + q M/2]
+    const float2 *tw;          // as TileArgs::tw
+    long long n_frames;
+    int hist_rows;
+    int n_tiles;
+    int tiles_per_inst;
+};
+
+template <int M>
+constexpr size_t tile_synth_smem_bytes()
+{
+    using LY = TileLayout<M>;
+    return sizeof(float2) * ((size_t)16 * kThreads + (size_t)(kThreads / (M / 2)) * LY::NBUF * kFr * LY::FS
+                             + (size_t)(M / 32) * kTwPitch);
+}
+
+template <int M, int NT, int PAR0>
+__global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_tile_synth_kernel(const SynthArgs a)
+{
+    using LY = TileLayout<M>;
+    constexpr int M2 = M / 2, R2 = M2 / 16;
+    constexpr int PR = LY::PR, SS = LY::SS, FS = LY::FS, NBUF = LY::NBUF;
+    constexpr int HL = NT - 1;                  // rows of history an output looks back at
+    constexpr int WT = (HL + kFr - 1) / kFr;    // warm-up tiles of an instance that starts inside the stream
+    constexpr int RPT = 16 / R2;                // pass-B' rows per thread (grouped order)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *slot = reinterpret_cast<float2 *>(smem_raw);          // [16][kThreads]: a thread's own 16 inputs of a tile
+    const int inst_l = threadIdx.x / M2, u = threadIdx.x % M2;
+    float2 *tile0 = slot + 16 * kThreads + inst_l * (NBUF * kFr * FS);
+    float2 *tws = slot + 16 * kThreads + (kThreads / M2) * (NBUF * kFr * FS);
+    const long long inst = (long long)blockIdx.x * (kThreads / M2) + inst_l;
+    const long long t0 = inst * a.tiles_per_inst;
+    long long ntl = (long long)a.n_tiles - t0;
+    if (ntl > a.tiles_per_inst) ntl = a.tiles_per_inst;
+    const int nt = ntl > 0 ? (int)ntl : 0;
+
+    auto inst_barrier = [&]() {
+        if (M2 == kThreads) __syncthreads();
+        else if (M2 == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + inst_l), "n"(M2) : "memory");
+    };
+    // pass-A' role: frame f2, sub-problem p2 (fastest), column t2
+    const int f2 = u / (2 * R2), p2 = u & 1, t2 = (u % (2 * R2)) >> 1;
+    // the thread's 16 inputs of tile `it`: grouped order rows k1 = t2 + R2 i of (f2, p2); wide order items j = u + M2 i
+    const uint32_t slot_u32 = smem_u32(slot + threadIdx.x);
+    auto fetch = [&](int it) {
+        const long long f0 = (t0 + it) * kFr;
+#pragma unroll
+        for (int i = 0; i < (LY::WIDE ? 32 * kFr / M2 : RPT); i++) {
+            int f, off;
+            if (LY::WIDE) { const int j = u + M2 * i; f = j >> 5; off = j & 31; }
+            else          { f = f2; off = 2 * (t2 + R2 * i) + p2; }
+            const bool ok = it < nt && f0 + f < a.n_frames;
+            const float2 *src = a.x + (f0 + f) * M + off;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; k2++)
+                cp_async8(slot_u32 + (i * R2 + k2) * kThreads * (int)sizeof(float2), ok ? (const void *)(src + 32 * k2) : (const void *)a.x, ok ? 8u : 0u);
+        }
+        cp_async_commit();
+    };
+    const int it0 = (t0 > 0 && nt > 0) ? -WT : 0;
+    fetch(it0);
+    // the inter-pass twiddles by column, times 1/2: tws[t2][k1] = e^{+j 2 pi k1 t2 / (M/2)} / 2
+    for (int i = u; i < 16 * R2; i += M2) {
+        const float2 t = __ldg(a.tw + M2 + i);
+        tws[(i % R2) * kTwPitch + i / R2] = make_float2(0.5f * t.x, 0.5f * t.y);
+    }
+    float h[NT];
+#pragma unroll
+    for (int q = 0; q < NT; q++) h[q] = __ldg(a.taps + q * M2 + u);
+    const float2 w2 = __ldg(a.tw + u);                            // W_M^u
+    float2 wlo[HL + kFr], whi[HL + kFr];                          // columns u and u + M/2 of v, oldest first
+#pragma unroll
+    for (int i = 0; i < HL; i++) {
+        wlo[i] = whi[i] = make_float2(0.f, 0.f);
+        if (t0 == 0 && a.hist != nullptr) {
+            wlo[i] = __ldg(a.hist + (size_t)(a.hist_rows - HL + i) * M + u);
+            whi[i] = __ldg(a.hist + (size_t)(a.hist_rows - HL + i) * M + u + M2);
+        }
+    }
+    const float4 *twc = reinterpret_cast<const float4 *>(tws + t2 * kTwPitch);
+    const int mac_off = (u / R2) * PR + (u % R2);
+    const int sp_off = f2 * FS + p2 * SS;
+    __syncthreads();
+
+    for (int it = it0; it < nt; it++) {
+        const long long f0 = (t0 + it) * kFr;
+        float2 *tile = tile0 + ((it - it0) % NBUF) * (kFr * FS);
+        cp_async_wait<0>();
+        // ---- pass B': rows of the sub-problems, out of the input slot
+        if (LY::WIDE) {
+#pragma unroll
+            for (int i = 0; i < 32 * kFr / M2; i++) {
+                const int j = u + M2 * i;
+                float2 r[R2];
+#pragma unroll
+                for (int k2 = 0; k2 < R2; k2++) r[k2] = slot[(i * R2 + k2) * kThreads + threadIdx.x];
+                RegDft<R2, +1>::run(r);
+                float2 *row = tile + (j >> 5) * FS + (j & 1) * SS + ((j & 31) >> 1) * PR;
+#pragma unroll
+                for (int c = 0; c < R2; c++) row[c] = r[c];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < RPT; i++) {
+                float2 r[R2];
+#pragma unroll
+                for (int k2 = 0; k2 < R2; k2++) r[k2] = slot[(i * R2 + k2) * kThreads + threadIdx.x];
+                RegDft<R2, +1>::run(r);
+                float2 *row = tile + sp_off + (t2 + R2 * i) * PR;
+#pragma unroll
+                for (int c = 0; c < R2; c++) row[c] = r[c];
+            }
+        }
+        fetch(it + 1);                                            // the slot's values are consumed: refill it
+        if (LY::WIDE) inst_barrier();
+        else __syncwarp();
+        // ---- pass A': twiddle and 16-point DFT down column t2 of (f2, p2), in place
+        {
+            float2 *sp = tile + sp_off;
+            float2 v[16];
+#pragma unroll
+            for (int k1 = 0; k1 < 16; k1++) v[k1] = sp[k1 * PR + t2];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float4 t = twc[k];
+                v[2 * k] = (k == 0) ? __fmul2_rn(bc(0.5f), v[0]) : cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+                v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+            }
+            RegDft<16, +1>::run(v);
+#pragma unroll
+            for (int r1 = 0; r1 < 16; r1++) sp[r1 * PR + t2] = v[r1];
+        }
+        inst_barrier();
+        // ---- FIR: last radix-2 stage, window push, dot products
+        const float2 *src = tile + mac_off;
+#pragma unroll
+        for (int f = 0; f < kFr; f++) {
+            const float2 e0 = src[f * FS];
+            const float2 t = cmul2_rot(src[f * FS + SS], w2);
+            wlo[HL + f] = __fadd2_rn(e0, t);
+            whi[HL + f] = __fadd2_rn(e0, neg2(t));
+        }
+        if (it >= 0) {
+#pragma unroll
+            for (int f = 0; f < kFr; f++) {
+                const bool odd = ((PAR0 + f) & 1) != 0;           // f0 is even
+                float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+                for (int q = 0; q < NT; q++) {
+                    const float2 sv = odd ? whi[HL + f - q] : wlo[HL + f - q];
+                    if (q & 1) a1 = __ffma2_rn(bc(h[q]), sv, a1);
+                    else       a0 = __ffma2_rn(bc(h[q]), sv, a0);
+                }
+                if (f0 + f < a.n_frames) __stcs(a.y + (f0 + f) * M2 + u, __fadd2_rn(a0, a1));
+            }
+            if (f0 + kFr > a.n_frames - NT) {
+                // the rows of v of the last NT frames are the object's state after this call
+#pragma unroll
+                for (int f = 0; f < kFr; f++) {
+                    const long long r = f0 + f - (a.n_frames - NT);
+                    if (r >= 0 && f0 + f < a.n_frames) {
+                        a.hist_out[r * M + u] = wlo[HL + f];
+                        a.hist_out[r * M + u + M2] = whi[HL + f];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < HL; i++) {
+            wlo[i] = wlo[kFr + i];
+            whi[i] = whi[kFr + i];
+        }
+        if (NBUF == 1) inst_barrier();
+    }
+    cp_async_wait<0>();
+}
+
+template <int M, int NT>
+void launch_synth_MN(const SynthArgs &a, int par0, unsigned int grid, cudaStream_t st)
+{
+    constexpr size_t smem = tile_synth_smem_bytes<M>();
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured)) {
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_tile_synth_kernel<M, NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_tile_synth_kernel<M, NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (par0) pfbch2_tile_synth_kernel<M, NT, 1><<<grid, kThreads, smem, st>>>(a);
+    else      pfbch2_tile_synth_kernel<M, NT, 0><<<grid, kThreads, smem, st>>>(a);
+}
+
+template <int M>
+void launch_synth_M(const SynthArgs &a, unsigned int NT, int par0, unsigned int grid, cudaStream_t st)
+{
+    switch (NT) {
+    case 8: launch_synth_MN<M, 8>(a, par0, grid, st); break;
+    case 16: launch_synth_MN<M, 16>(a, par0, grid, st); break;
+    case 20: launch_synth_MN<M, 20>(a, par0, grid, st); break;
+    default: lc::fatal("launch_pfbch2_tile_synth", "unsupported tap count");
+    }
+}
+
 template <int M, int L>
 void launch_ML(const TileArgs &a, unsigned int grid, cudaStream_t st)
 {
@@ -284,6 +502,45 @@ void tile_pfbch2_make_twiddles(std::vector<float2> &tw, unsigned int M)
             const double ang = 2.0 * M_PI * (double)(k1 * r2) / (double)M2;
             tw[M2 + k1 * R2 + r2] = make_float2((float)cos(ang), (float)sin(ang));
         }
+}
+
+bool tile_pfbch2_synth_supported(unsigned int M, unsigned int n_taps)
+{
+    return (M == 64 || M == 128 || M == 256 || M == 512) && (n_taps == 8 || n_taps == 16 || n_taps == 20);
+}
+
+long long launch_pfbch2_tile_synth(const float2 *d_hist_rows, int hist_rows, const float2 *d_x, const float *d_taps,
+                                   const float2 *d_tw, float2 *d_y, float2 *d_hist_out, unsigned int M, unsigned int n_taps,
+                                   unsigned long long n_frames, int parity0, cudaStream_t st)
+{
+    const long long n_tiles = (long long)((n_frames + kFr - 1) / kFr);
+    if (n_frames < n_taps || n_tiles > (1ll << 30)) return 0;     // the state rows all come from this call
+    SynthArgs a;
+    a.hist = d_hist_rows;
+    a.hist_rows = hist_rows;
+    a.x = d_x;
+    a.y = d_y;
+    a.hist_out = d_hist_out;
+    a.taps = d_taps;
+    a.tw = d_tw;
+    a.n_frames = (long long)n_frames;
+    a.n_tiles = (int)n_tiles;
+    // 64 tiles per instance keep the warm-up tiles (1 - 3) below 5 %; never fewer than 4 (the warm-up reaches back 3)
+    const long long inst_per_cta = kThreads / (M / 2);
+    long long tpi = 64;
+    while (tpi > 4 && (n_tiles / tpi) < 148ll * 4 * inst_per_cta) tpi >>= 1;
+    a.tiles_per_inst = (int)tpi;
+    const long long n_inst = (n_tiles + tpi - 1) / tpi;
+    const unsigned int grid = (unsigned int)((n_inst + inst_per_cta - 1) / inst_per_cta);
+    switch (M) {
+    case 64: launch_synth_M<64>(a, n_taps, parity0 & 1, grid, st); break;
+    case 128: launch_synth_M<128>(a, n_taps, parity0 & 1, grid, st); break;
+    case 256: launch_synth_M<256>(a, n_taps, parity0 & 1, grid, st); break;
+    case 512: launch_synth_M<512>(a, n_taps, parity0 & 1, grid, st); break;
+    default: fatal("launch_pfbch2_tile_synth", "unsupported channel count");
+    }
+    LC_LAUNCH_CHECK();
+    return (long long)n_frames;
 }
 
 long long launch_pfbch2_tile(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps_scaled, const float2 *d_tw,

@@ -613,6 +613,36 @@ def test_pfbch2_tile_vs_oracle_odd_splits_and_generic(L, orc, monkeypatch, M, m)
     assert np.abs(whole - generic).max() < 1e-6
 
 
+@pytest.mark.parametrize("M,m", [(64, 2), (64, 4), (64, 5), (128, 2), (128, 5), (256, 2), (256, 4), (256, 5),
+                                 (512, 2), (512, 4), (512, 5)])
+def test_pfbch2_tile_synthesizer_vs_oracle_odd_splits_and_generic(L, orc, monkeypatch, M, m):
+    """the reference's synthesizer benchmark shapes (firpfbch2_crcf_benchmark.c:84-90, m = 2) and longer filters on
+    the fused tile synthesizer: odd start parity, ragged tiles, several instances (warm-up tiles rebuild the
+    windows), state handed from the fused kernel to the two-kernel path and back, get/set_state"""
+    nfr = 65 + 9 + 200 + 1283
+    X = orc.synth_input(nfr * M, seed=0x91 + M + m)
+    want = orc.Firpfbch2(orc.SYNTHESIZER, M, m, As=60.0).execute_frames(X)
+    scale = np.abs(want).max()
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+    cuts = [0, 65, 74, 274, nfr]                      # 9 frames: below 4m for m >= 4 (two-kernel path in between)
+    got = np.concatenate([q.execute_block(X[a * M:b * M]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert np.abs(got - want).max() / scale < 1e-5
+    hist, flag = q.get_state()
+    q.reset()
+    whole = q.execute_block(X)
+    assert np.abs(whole - want).max() / scale < 1e-5
+    assert np.abs(whole - got).max() / scale < 2e-6
+    hist2, flag2 = q.get_state()
+    assert flag == flag2 and np.abs(hist - hist2).max() / max(np.abs(hist).max(), 1e-30) < 2e-6
+    monkeypatch.setenv("LIQUID_CUDA_NO_FUSED", "1")
+    q.reset()
+    generic = q.execute_block(X)
+    hist3, _ = q.get_state()
+    monkeypatch.delenv("LIQUID_CUDA_NO_FUSED")
+    assert np.abs(whole - generic).max() / scale < 2e-6
+    assert np.abs(hist - hist3).max() / max(np.abs(hist).max(), 1e-30) < 2e-6
+
+
 # ------------------------------------------------------------------ root-Nyquist Kaiser prototypes (SURVEY 8f item 1)
 def test_pfbch_rnyquist_kaiser_prototypes_vs_reference(L, orc, refrn):
     """firpfbch_crcf_create_rnyquist with ARKAISER / RKAISER against the compiled reference's outputs and

@@ -7,7 +7,7 @@ events, inputs larger than L2.  Not the driver's headline bench (that is bench.p
 
   c1 c2 c4 c5   BASELINE configs 1, 2, 4, 5 (c3 is bench.py)          c3m c5m  c3 / c5 against the filter length m
   g             shape-generic one-kernel analyzers (M = 256, 64, 2048)  s        synthesizers (firpfbch2 M=1024, firpfbch M=1024 / 256)
-  t             firpfbch2 tile kernels, M = 64 ... 512, m = 2 / 5 / 7
+  t ts          firpfbch2 tile kernels (analysis / synthesis), M = 64 ... 512
   fft           fft_execute_batch_dev, n = 16 / 256 / 1024 / 4096       d        dotprod_crcf batch entry point
   p             firpfb_crcf block form
   f1            firpfbch_cccf (8f item 1)                                f2       spgramcf_accumulate_psd (8f item 2)
@@ -190,6 +190,18 @@ def run(configs, steps, warmup, sink, device_index=0):
             ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
             report("t: firpfbch2_crcf analysis M=%d m=%d (tile kernel), 2^28 samples" % (M, m), n, 24, ms, ln)
             del x, y
+    if "ts" in args.configs:
+        # the reference's synthesizer benchmark shapes (firpfbch2_crcf_benchmark.c:84-90: m = 2) and m = 4 / 5:
+        # the fused tile synthesizer of pfbch2_tile.cu; throughput in OUTPUT samples/s, 16 B in + 8 B out per output
+        for M, m in ((64, 2), (64, 5), (128, 2), (256, 2), (256, 4), (256, 5), (512, 2), (512, 5)):
+            n = 1 << 27
+            q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+            X = torch.empty(4 * n, dtype=torch.float32, device=dev)
+            y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+            L.synth_input_dev(X.data_ptr(), 2 * n, stream=st.cuda_stream)
+            ms, ln = timed(lambda: q.execute_block_dev(X.data_ptr(), n // (M // 2), y.data_ptr(), st.cuda_stream))
+            report("ts: firpfbch2_crcf synthesis M=%d m=%d (tile kernel), 2^27 output samples" % (M, m), n, 24, ms, ln)
+            del X, y
     if "f1" in args.configs:
         # firpfbch_cccf analysis, M=256, p=10, one stream of 2^27 samples --
         # (a) a real prototype (create_kaiser): rides the crcf fused kernel; (b) complex taps: generic kernels
