@@ -78,7 +78,7 @@ firpfbch_crcf firpfbch_crcf_create(int _type, unsigned int _M, unsigned int _p, 
     if ((_type == LIQUID_ANALYZER && lc::pfb::fused_pfbch_supported(_M, _p)) ||
         (_type == LIQUID_SYNTHESIZER && lc::pfb::fused_pfbch_synth_supported(_M, _p))) {
         std::vector<float2> tw;
-        lc::pfb::fused_pfbch_make_twiddles(tw, _type == LIQUID_ANALYZER ? -1 : +1);
+        lc::pfb::fused_pfbch_make_twiddles(tw, _type == LIQUID_ANALYZER ? -1 : +1, _M, _p);
         LC_CUDA_CHECK(cudaMalloc(&q->d_tw_fused, tw.size() * sizeof(float2)));
         LC_CUDA_CHECK(cudaMemcpy(q->d_tw_fused, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
         q->fused = true;

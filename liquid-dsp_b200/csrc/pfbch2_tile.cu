@@ -87,6 +87,70 @@ constexpr size_t tile_smem_bytes()
                              + (size_t)(M / 32) * kTwPitch);
 }
 
+// Phase 2 of the analyzers for one tile: the 2 x 8 sub-problems of M/2 = 16 x R2 points in `tile` (phase-1 layout) are
+// transformed (e^{SIGN j ...}) and the frames leave for y_str[(f0 + f) M + 2 (k1 + 16 k2) + p].  Called by the whole
+// instance after the barrier that follows phase 1.
+template <int M, int SIGN, class Barrier>
+__device__ __forceinline__ void tile_phase2(float2 *tile, int u, const float4 *twc, float2 *y_str, long long f0,
+                                            long long n_frames, Barrier inst_barrier)
+{
+    using LY = TileLayout<M>;
+    constexpr int M2 = M / 2, R2 = M2 / 16;
+    constexpr int PR = LY::PR, SS = LY::SS, FS = LY::FS;
+    // pass-A role inside the instance: frame f2, sub-problem p2 (fastest), column t2
+    const int f2 = u / (2 * R2), p2 = u & 1, t2 = (u % (2 * R2)) >> 1;
+    // pass A down column t2 (in place: a thread reads and writes its own column)
+    float2 *sp = tile + f2 * FS + p2 * SS;
+    float2 v[16];
+#pragma unroll
+    for (int r1 = 0; r1 < 16; r1++) v[r1] = sp[r1 * PR + t2];
+    RegDft<16, SIGN>::run(v);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float4 t = twc[k];                              // twiddles k1 = 2k, 2k + 1
+        if (k > 0) v[2 * k] = cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+        v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) sp[k1 * PR + t2] = v[k1];
+    if (LY::WIDE) {
+        // pass B over the whole instance: item j = (frame, row k1, sub-problem), sub-problem fastest
+        inst_barrier();
+#pragma unroll
+        for (int i = 0; i < 32 * kFr / M2; i++) {
+            const int j = u + M2 * i;
+            const int f = j >> 5, k1 = (j & 31) >> 1;
+            const float2 *row = tile + f * FS + (j & 1) * SS + k1 * PR;
+            float2 r[R2];
+#pragma unroll
+            for (int c = 0; c < R2; c++) r[c] = row[c];
+            RegDft<R2, SIGN>::run(r);
+            if (f0 + f < n_frames) {
+                float2 *yf = y_str + (f0 + f) * M + (j & 31);
+#pragma unroll
+                for (int k2 = 0; k2 < R2; k2++) __stcs(yf + 32 * k2, r[k2]);
+            }
+        }
+    } else {
+        // pass B inside the 2 R2 lanes of the sub-problem: rows k1 = t2 + R2 i
+        __syncwarp();
+        float2 *yf = y_str + (f0 + f2) * M + p2;
+        const bool live = f0 + f2 < n_frames;
+#pragma unroll
+        for (int i = 0; i < 16 / R2; i++) {
+            const int k1 = t2 + R2 * i;
+            float2 r[R2];
+#pragma unroll
+            for (int c = 0; c < R2; c++) r[c] = sp[k1 * PR + c];
+            RegDft<R2, SIGN>::run(r);
+            if (live) {
+#pragma unroll
+                for (int k2 = 0; k2 < R2; k2++) __stcs(yf + 2 * (k1 + 16 * k2), r[k2]);
+            }
+        }
+    }
+}
+
 template <int M, int L>
 __global__ void __launch_bounds__(kThreads, (L <= 10 ? 2 : 1)) pfbch2_tile_kernel(const TileArgs a)
 {
@@ -143,11 +207,8 @@ __global__ void __launch_bounds__(kThreads, (L <= 10 ? 2 : 1)) pfbch2_tile_kerne
 #pragma unroll
         for (int i = 0; i < HL; i++) win[i] = ld_hist0(a.hist, a.x, (f0 - HL + i) * M2 + (M2 - 1 - u), a.H);
     }
-    // pass-A role inside the instance: frame f2, sub-problem p2 (fastest), column t2
-    const int f2 = u / (2 * R2), p2 = u & 1, t2 = (u % (2 * R2)) >> 1;
-    const float4 *twc = reinterpret_cast<const float4 *>(tws + t2 * kTwPitch);
+    const float4 *twc = reinterpret_cast<const float4 *>(tws + ((u % (2 * R2)) >> 1) * kTwPitch);   // pass-A column of this thread
     const int mac_off = (u / R2) * PR + (u % R2);                 // where z_p[u] lives: row u / R2, column u % R2
-    const int sp_off = f2 * FS + p2 * SS;
     __syncthreads();                                              // the twiddle copies of all instances
 
     for (int it = 0; it < nt; it++) {
@@ -183,59 +244,156 @@ __global__ void __launch_bounds__(kThreads, (L <= 10 ? 2 : 1)) pfbch2_tile_kerne
         // with two buffers the one barrier of a tile: the instance's phase-1 stores are visible, and every warp has
         // left pass B of the tile before (which read the other buffer -- the one phase 1 of the next tile writes)
         inst_barrier();
-        // ---- phase 2: sub-problem p2 of frame f2; pass A down column t2 (in place: a thread reads and writes its own column)
-        float2 *sp = tile + sp_off;
-        float2 v[16];
-#pragma unroll
-        for (int r1 = 0; r1 < 16; r1++) v[r1] = sp[r1 * PR + t2];
-        RegDft<16, +1>::run(v);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float4 t = twc[k];                              // twiddles k1 = 2k, 2k + 1
-            if (k > 0) v[2 * k] = cmul2_rot(v[2 * k], make_float2(t.x, t.y));
-            v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
-        }
-#pragma unroll
-        for (int k1 = 0; k1 < 16; k1++) sp[k1 * PR + t2] = v[k1];
-        if (LY::WIDE) {
-            // pass B over the whole instance: item j = (frame, row k1, sub-problem), sub-problem fastest
-            inst_barrier();
-#pragma unroll
-            for (int i = 0; i < 32 * kFr / M2; i++) {
-                const int j = u + M2 * i;
-                const int f = j >> 5, k1 = (j & 31) >> 1;
-                const float2 *row = tile + f * FS + (j & 1) * SS + k1 * PR;
-                float2 r[R2];
-#pragma unroll
-                for (int c = 0; c < R2; c++) r[c] = row[c];
-                RegDft<R2, +1>::run(r);
-                if (f0 + f < a.n_frames) {
-                    float2 *yf = a.y + (f0 + f) * M + (j & 31);
-#pragma unroll
-                    for (int k2 = 0; k2 < R2; k2++) __stcs(yf + 32 * k2, r[k2]);
-                }
-            }
-        } else {
-            // pass B inside the 2 R2 lanes of the sub-problem: rows k1 = t2 + R2 i
-            __syncwarp();
-            float2 *yf = a.y + (f0 + f2) * M + p2;
-            const bool live = f0 + f2 < a.n_frames;
-#pragma unroll
-            for (int i = 0; i < 16 / R2; i++) {
-                const int k1 = t2 + R2 * i;
-                float2 r[R2];
-#pragma unroll
-                for (int c = 0; c < R2; c++) r[c] = sp[k1 * PR + c];
-                RegDft<R2, +1>::run(r);
-                if (live) {
-#pragma unroll
-                    for (int k2 = 0; k2 < R2; k2++) __stcs(yf + 2 * (k1 + 16 * k2), r[k2]);
-                }
-            }
-        }
+        // ---- phase 2
+        tile_phase2<M, +1>(tile, u, twc, a.y, f0, a.n_frames, inst_barrier);
         if (NBUF == 1) inst_barrier();
     }
     cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------- firpfbch (critically sampled) analyzer
+// firpfbch.c:369-409 (M pushes then run, alignment 0): X_s[u] = sum_n h[(M-1-u) + nM] x[(s-n)M + u], Y_s = forward
+// DFT.  Same kernel shape as above: thread u owns the windows u and u + M/2 (two samples per frame, two P-tap dot
+// products over sliding register windows), does the first radix-2 decimation-in-frequency stage on its two values,
+// and the instance finishes the two M/2-point problems per frame in the shared tile (tile_phase2 with the forward
+// sign).  grid.y = stream (independent streams from the zero state, or one stateful stream with its history).
+struct PfbTileArgs {
+    const float2 *hist;        // H samples preceding x[0] of the (single) stream, or null = zero state
+    const float2 *x;           // [n_streams][stream_stride]
+    float2 *y;
+    const float *taps;         // [P][M]: taps[n][i] = h[i + nM]
+    const float2 *tw;          // tw2[u] = e^{-j 2 pi u / M}, u < M/2; then twp[k1][r2] = e^{-j 2 pi k1 r2 / (M/2)}
+    long long n_frames;
+    long long stream_stride;
+    int H;
+    int n_tiles;
+    int tiles_per_inst;
+};
+
+template <int M>
+constexpr size_t pfb_tile_smem_bytes()
+{
+    using LY = TileLayout<M>;
+    return sizeof(float2) * ((size_t)2 * kFr * kThreads + (size_t)(kThreads / (M / 2)) * LY::NBUF * kFr * LY::FS
+                             + (size_t)(M / 32) * kTwPitch);
+}
+
+template <int M, int P>
+__global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileArgs a)
+{
+    using LY = TileLayout<M>;
+    constexpr int M2 = M / 2, R2 = M2 / 16;
+    constexpr int PR = LY::PR, SS = LY::SS, FS = LY::FS, NBUF = LY::NBUF;
+    constexpr int HL = P - 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *slot = reinterpret_cast<float2 *>(smem_raw);          // [2 kFr][kThreads]: a thread's own 16 samples of a tile
+    const int inst_l = threadIdx.x / M2, u = threadIdx.x % M2;
+    float2 *tile0 = slot + 2 * kFr * kThreads + inst_l * (NBUF * kFr * FS);
+    float2 *tws = slot + 2 * kFr * kThreads + (kThreads / M2) * (NBUF * kFr * FS);
+    const long long inst = (long long)blockIdx.x * (kThreads / M2) + inst_l;
+    const long long t0 = inst * a.tiles_per_inst;
+    long long ntl = (long long)a.n_tiles - t0;
+    if (ntl > a.tiles_per_inst) ntl = a.tiles_per_inst;
+    const int nt = ntl > 0 ? (int)ntl : 0;
+    const float2 *x = a.x + (long long)blockIdx.y * a.stream_stride;
+    float2 *y = a.y + (long long)blockIdx.y * a.stream_stride;
+
+    auto inst_barrier = [&]() {
+        if (M2 == kThreads) __syncthreads();
+        else if (M2 == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + inst_l), "n"(M2) : "memory");
+    };
+    const uint32_t slot_u32 = smem_u32(slot + threadIdx.x);
+    auto fetch = [&](int it) {
+        const long long f0 = (t0 + it) * kFr;
+#pragma unroll
+        for (int f = 0; f < kFr; f++) {
+            const bool ok = it < nt && f0 + f < a.n_frames;
+            const float2 *src = x + (f0 + f) * M + u;
+            cp_async8(slot_u32 + (2 * f) * kThreads * (int)sizeof(float2), ok ? (const void *)src : (const void *)a.x, ok ? 8u : 0u);
+            cp_async8(slot_u32 + (2 * f + 1) * kThreads * (int)sizeof(float2), ok ? (const void *)(src + M2) : (const void *)a.x, ok ? 8u : 0u);
+        }
+        cp_async_commit();
+    };
+    fetch(0);
+    for (int i = u; i < 16 * R2; i += M2) tws[(i % R2) * kTwPitch + i / R2] = __ldg(a.tw + M2 + i);
+
+    float h0[P], h1[P];
+#pragma unroll
+    for (int n = 0; n < P; n++) {
+        h0[n] = __ldg(a.taps + n * M + (M - 1 - u));              // branch M-1-u feeds input u
+        h1[n] = __ldg(a.taps + n * M + (M2 - 1 - u));             // branch M-1-(u + M/2)
+    }
+    const float2 w2 = __ldg(a.tw + u);                            // W_M^u, forward
+    float2 w0[HL + kFr], w1[HL + kFr];
+    if (nt > 0) {
+        const long long f0 = t0 * kFr;
+#pragma unroll
+        for (int i = 0; i < HL; i++) {
+            w0[i] = ld_hist0(a.hist, x, (f0 - HL + i) * M + u, a.H);
+            w1[i] = ld_hist0(a.hist, x, (f0 - HL + i) * M + u + M2, a.H);
+        }
+    }
+    const float4 *twc = reinterpret_cast<const float4 *>(tws + ((u % (2 * R2)) >> 1) * kTwPitch);
+    const int mac_off = (u / R2) * PR + (u % R2);
+    __syncthreads();
+
+    for (int it = 0; it < nt; it++) {
+        const long long f0 = (t0 + it) * kFr;
+        float2 *tile = tile0 + (it % NBUF) * (kFr * FS);
+        cp_async_wait<0>();
+        {
+            const float2 *src = slot + threadIdx.x;
+#pragma unroll
+            for (int f = 0; f < kFr; f++) {
+                w0[HL + f] = src[(2 * f) * kThreads];
+                w1[HL + f] = src[(2 * f + 1) * kThreads];
+            }
+        }
+        float2 *mac_dst = tile + mac_off;
+#pragma unroll
+        for (int f = 0; f < kFr; f++) {
+            float2 d0 = make_float2(0.f, 0.f), d1 = d0;
+#pragma unroll
+            for (int n = P - 1; n >= 0; n--) {
+                d0 = __ffma2_rn(bc(h0[n]), w0[HL + f - n], d0);
+                d1 = __ffma2_rn(bc(h1[n]), w1[HL + f - n], d1);
+            }
+            mac_dst[f * FS] = __fadd2_rn(d0, d1);
+            mac_dst[f * FS + SS] = cmul2_rot(__fadd2_rn(d0, neg2(d1)), w2);
+        }
+        fetch(it + 1);
+#pragma unroll
+        for (int i = 0; i < HL; i++) {
+            w0[i] = w0[kFr + i];
+            w1[i] = w1[kFr + i];
+        }
+        inst_barrier();
+        tile_phase2<M, -1>(tile, u, twc, y, f0, a.n_frames, inst_barrier);
+        if (NBUF == 1) inst_barrier();
+    }
+    cp_async_wait<0>();
+}
+
+template <int M, int P>
+void launch_pfb_MP(const PfbTileArgs &a, dim3 grid, cudaStream_t st)
+{
+    constexpr size_t smem = pfb_tile_smem_bytes<M>();
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch_tile_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pfbch_tile_kernel<M, P><<<grid, kThreads, smem, st>>>(a);
+}
+
+template <int M>
+void launch_pfb_M(const PfbTileArgs &a, unsigned int P, dim3 grid, cudaStream_t st)
+{
+    switch (P) {
+    case 4: launch_pfb_MP<M, 4>(a, grid, st); break;
+    case 8: launch_pfb_MP<M, 8>(a, grid, st); break;
+    case 10: launch_pfb_MP<M, 10>(a, grid, st); break;
+    default: lc::fatal("launch_pfbch_tile", "unsupported tap count");
+    }
 }
 
 // ---------------------------------------------------------------------------------- synthesizer
@@ -502,6 +660,49 @@ void tile_pfbch2_make_twiddles(std::vector<float2> &tw, unsigned int M)
             const double ang = 2.0 * M_PI * (double)(k1 * r2) / (double)M2;
             tw[M2 + k1 * R2 + r2] = make_float2((float)cos(ang), (float)sin(ang));
         }
+}
+
+bool tile_pfbch_supported(unsigned int M, unsigned int p)
+{
+    return (M == 64 || M == 128 || M == 512) && (p == 4 || p == 8 || p == 10);
+}
+
+void tile_pfbch_make_twiddles(std::vector<float2> &tw, unsigned int M)
+{
+    tile_pfbch2_make_twiddles(tw, M);
+    for (float2 &t : tw) t.y = -t.y;                              // forward transform
+}
+
+long long launch_pfbch_tile(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, const float2 *d_tw,
+                            float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
+                            unsigned int n_streams, long long stream_stride, cudaStream_t st)
+{
+    const long long n_tiles = (long long)((n_frames + kFr - 1) / kFr);
+    if (n_tiles == 0 || n_tiles > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;
+    PfbTileArgs a;
+    a.hist = d_hist;
+    a.x = d_x;
+    a.y = d_y;
+    a.taps = d_taps;
+    a.tw = d_tw;
+    a.H = H;
+    a.n_frames = (long long)n_frames;
+    a.stream_stride = stream_stride;
+    a.n_tiles = (int)n_tiles;
+    const long long inst_per_cta = kThreads / (M / 2);
+    long long tpi = 64;
+    while (tpi > 1 && (n_tiles / tpi) * n_streams < 148ll * 4 * inst_per_cta) tpi >>= 1;
+    a.tiles_per_inst = (int)tpi;
+    const long long n_inst = (n_tiles + tpi - 1) / tpi;
+    dim3 grid((unsigned int)((n_inst + inst_per_cta - 1) / inst_per_cta), n_streams, 1);
+    switch (M) {
+    case 64: launch_pfb_M<64>(a, p, grid, st); break;
+    case 128: launch_pfb_M<128>(a, p, grid, st); break;
+    case 512: launch_pfb_M<512>(a, p, grid, st); break;
+    default: fatal("launch_pfbch_tile", "unsupported channel count");
+    }
+    LC_LAUNCH_CHECK();
+    return (long long)n_frames;
 }
 
 bool tile_pfbch2_synth_supported(unsigned int M, unsigned int n_taps)

@@ -26,5 +26,13 @@ long long launch_pfbch2_tile_synth(const float2 *d_hist_rows, int hist_rows, con
                                    const float2 *d_tw, float2 *d_y, float2 *d_hist_out, unsigned int M, unsigned int n_taps,
                                    unsigned long long n_frames, int parity0, cudaStream_t st);
 
+// firpfbch (critically sampled) analyzer, M = 64 / 128 / 512, p = 2m in {4, 8, 10}: same contract as
+// launch_pfbch_fused (pfbch_fused.cuh) except that every frame is covered (ragged last tile in the kernel).
+bool tile_pfbch_supported(unsigned int M, unsigned int p);
+void tile_pfbch_make_twiddles(std::vector<float2> &tw, unsigned int M);
+long long launch_pfbch_tile(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, const float2 *d_tw,
+                            float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
+                            unsigned int n_streams, long long stream_stride, cudaStream_t st);
+
 }  // namespace pfb
 }  // namespace lc

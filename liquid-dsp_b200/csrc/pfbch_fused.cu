@@ -19,6 +19,7 @@
 // Reference semantics: src/multichannel/src/firpfbch.c:346-409 (push M samples, run with k = 0):
 //   X_s[u] = sum_n h[(M-1-u) + nM] x[(s-n)M + u],   Y_s = DFT_forward_unscaled(X_s).
 #include "pfbch_fused.cuh"
+#include "pfbch2_tile.cuh"
 #include "fused_common.cuh"
 
 #include <cmath>
@@ -290,7 +291,7 @@ namespace pfb {
 
 bool fused_pfbch_supported(unsigned int M, unsigned int p)
 {
-    return (M == 16 && (p == 4 || p == 8)) || (M == 256 && (p == 4 || p == 10));
+    return (M == 16 && (p == 4 || p == 8)) || (M == 256 && (p == 4 || p == 10)) || tile_pfbch_supported(M, p);
 }
 
 bool fused_pfbch_synth_supported(unsigned int M, unsigned int p)
@@ -298,8 +299,12 @@ bool fused_pfbch_synth_supported(unsigned int M, unsigned int p)
     return M == 256 && (p == 4 || p == 10);
 }
 
-void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign)
+void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign, unsigned int M, unsigned int p)
 {
+    if (sign < 0 && tile_pfbch_supported(M, p)) {
+        tile_pfbch_make_twiddles(tw, M);                      // analyzers for M = 64 / 128 / 512 (pfbch2_tile.cu)
+        return;
+    }
     tw.resize(16 * 16);
     for (int k1 = 0; k1 < 16; k1++)
         for (int r2 = 0; r2 < 16; r2++) {
@@ -312,6 +317,8 @@ long long launch_pfbch_fused(const float2 *d_hist, const float2 *d_x, int H, con
                              float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
                              unsigned int n_streams, long long stream_stride, cudaStream_t st)
 {
+    if (tile_pfbch_supported(M, p))
+        return launch_pfbch_tile(d_hist, d_x, H, d_taps, d_tw, d_y, M, p, n_frames, n_streams, stream_stride, st);
     const long long n_tiles = (long long)(n_frames / kTile);
     if (n_tiles == 0 || n_tiles > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;
     PfbArgs a;

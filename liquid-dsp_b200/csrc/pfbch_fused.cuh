@@ -10,7 +10,7 @@ bool fused_pfbch_supported(unsigned int M, unsigned int p);
 bool fused_pfbch_synth_supported(unsigned int M, unsigned int p);
 
 // inter-pass twiddles of the M = 256 kernels: e^{sign j 2 pi k1 r2 / 256} (-1 analyzer, +1 synthesizer)
-void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign);
+void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign, unsigned int M = 256, unsigned int p = 4);
 
 // Runs the fused analyzer over the largest multiple of 16 frames <= n_frames of each of n_streams
 // streams (stream s at d_x + s*stream_stride, output at d_y + s*stream_stride) and returns how many

@@ -7,7 +7,7 @@ events, inputs larger than L2.  Not the driver's headline bench (that is bench.p
 
   c1 c2 c4 c5   BASELINE configs 1, 2, 4, 5 (c3 is bench.py)          c3m c5m  c3 / c5 against the filter length m
   g             shape-generic one-kernel analyzers (M = 256, 64, 2048)  s        synthesizers (firpfbch2 M=1024, firpfbch M=1024 / 256)
-  t ts          firpfbch2 tile kernels (analysis / synthesis), M = 64 ... 512
+  t ts tp       firpfbch2 tile kernels (analysis / synthesis), M = 64 ... 512; firpfbch analysis M = 64 ... 1024
   fft           fft_execute_batch_dev, n = 16 / 256 / 1024 / 4096       d        dotprod_crcf batch entry point
   p             firpfb_crcf block form
   f1            firpfbch_cccf (8f item 1)                                f2       spgramcf_accumulate_psd (8f item 2)
@@ -189,6 +189,17 @@ def run(configs, steps, warmup, sink, device_index=0):
             L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
             ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
             report("t: firpfbch2_crcf analysis M=%d m=%d (tile kernel), 2^28 samples" % (M, m), n, 24, ms, ln)
+            del x, y
+    if "tp" in args.configs:
+        # firpfbch_crcf analysis at the reference's own benchmark shapes (firpfbch_crcf_benchmark.c:80-85: m = 2) and m = 5
+        for M, m in ((64, 2), (64, 5), (128, 2), (256, 2), (512, 2), (512, 5), (1024, 2)):
+            n = 1 << 28
+            q = L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+            x = torch.empty(2 * n, dtype=torch.float32, device=dev)
+            y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+            L.synth_input_dev(x.data_ptr(), n, stream=st.cuda_stream)
+            ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
+            report("tp: firpfbch_crcf analysis M=%d m=%d, 2^28 samples (one stream, stateful)" % (M, m), n, 16, ms, ln)
             del x, y
     if "ts" in args.configs:
         # the reference's synthesizer benchmark shapes (firpfbch2_crcf_benchmark.c:84-90: m = 2) and m = 4 / 5:
