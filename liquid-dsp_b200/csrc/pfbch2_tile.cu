@@ -398,7 +398,7 @@ void launch_pfb_M(const PfbTileArgs &a, unsigned int P, dim3 grid, cudaStream_t 
 
 // ---------------------------------------------------------------------------------- synthesizer
 // The synthesizer (firpfbch2.c:287-335) is the transposed flow graph of the analyzer, and so is its kernel:
-//   pass B'  R2-point register DFTs over the rows X_p[k1 + 16 k2] (read straight from the thread's input slot),
+//   pass B'  R2-point register DFTs over the rows X_p[k1 + 16 k2] (prefetched into registers one tile ahead),
 //   pass A'  the inter-pass twiddle (times the reference's 1/M * M/2 = 1/2, exact) and a 16-point register DFT down
 //            each column: the tile then holds E_p[u] = sum_k X[2k + p] e^{+j 2 pi u k / (M/2)} / 2,
 //   FIR      thread u does the last radix-2 stage, v[u] = E_0[u] + W_M^u E_1[u], v[u + M/2] = E_0[u] - W_M^u E_1[u],
@@ -424,8 +424,7 @@ template <int M>
 constexpr size_t tile_synth_smem_bytes()
 {
     using LY = TileLayout<M>;
-    return sizeof(float2) * ((size_t)16 * kThreads + (size_t)(kThreads / (M / 2)) * LY::NBUF * kFr * LY::FS
-                             + (size_t)(M / 32) * kTwPitch);
+    return sizeof(float2) * ((size_t)(kThreads / (M / 2)) * LY::NBUF * kFr * LY::FS + (size_t)(M / 32) * kTwPitch);
 }
 
 template <int M, int NT, int PAR0>
@@ -438,10 +437,9 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_tile_synth_k
     constexpr int WT = (HL + kFr - 1) / kFr;    // warm-up tiles of an instance that starts inside the stream
     constexpr int RPT = 16 / R2;                // pass-B' rows per thread (grouped order)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *slot = reinterpret_cast<float2 *>(smem_raw);          // [16][kThreads]: a thread's own 16 inputs of a tile
     const int inst_l = threadIdx.x / M2, u = threadIdx.x % M2;
-    float2 *tile0 = slot + 16 * kThreads + inst_l * (NBUF * kFr * FS);
-    float2 *tws = slot + 16 * kThreads + (kThreads / M2) * (NBUF * kFr * FS);
+    float2 *tile0 = reinterpret_cast<float2 *>(smem_raw) + inst_l * (NBUF * kFr * FS);
+    float2 *tws = reinterpret_cast<float2 *>(smem_raw) + (kThreads / M2) * (NBUF * kFr * FS);
     const long long inst = (long long)blockIdx.x * (kThreads / M2) + inst_l;
     const long long t0 = inst * a.tiles_per_inst;
     long long ntl = (long long)a.n_tiles - t0;
@@ -455,8 +453,11 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_tile_synth_k
     };
     // pass-A' role: frame f2, sub-problem p2 (fastest), column t2
     const int f2 = u / (2 * R2), p2 = u & 1, t2 = (u % (2 * R2)) >> 1;
-    // the thread's 16 inputs of tile `it`: grouped order rows k1 = t2 + R2 i of (f2, p2); wide order items j = u + M2 i
-    const uint32_t slot_u32 = smem_u32(slot + threadIdx.x);
+    // the thread's 16 inputs of tile `it`: grouped order rows k1 = t2 + R2 i of (f2, p2); wide order items j = u + M2 i.
+    // They are prefetched into REGISTERS one tile ahead (issued when pass B' has consumed the previous set, needed at
+    // the top of the next tile): staging them through a cp.async slot cost a third of the kernel's shared-memory
+    // wavefronts (ncu: mio_throttle 22 % of the stall samples, shared-memory pipe 59 % busy at 0.67 of the roofline).
+    float2 nx[16];
     auto fetch = [&](int it) {
         const long long f0 = (t0 + it) * kFr;
 #pragma unroll
@@ -467,10 +468,8 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_tile_synth_k
             const bool ok = it < nt && f0 + f < a.n_frames;
             const float2 *src = a.x + (f0 + f) * M + off;
 #pragma unroll
-            for (int k2 = 0; k2 < R2; k2++)
-                cp_async8(slot_u32 + (i * R2 + k2) * kThreads * (int)sizeof(float2), ok ? (const void *)(src + 32 * k2) : (const void *)a.x, ok ? 8u : 0u);
+            for (int k2 = 0; k2 < R2; k2++) nx[i * R2 + k2] = ok ? __ldg(src + 32 * k2) : make_float2(0.f, 0.f);
         }
-        cp_async_commit();
     };
     const int it0 = (t0 > 0 && nt > 0) ? -WT : 0;
     fetch(it0);
@@ -500,7 +499,6 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_tile_synth_k
     for (int it = it0; it < nt; it++) {
         const long long f0 = (t0 + it) * kFr;
         float2 *tile = tile0 + ((it - it0) % NBUF) * (kFr * FS);
-        cp_async_wait<0>();
         // ---- pass B': rows of the sub-problems, out of the input slot
         if (LY::WIDE) {
 #pragma unroll
@@ -508,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_tile_synth_k
                 const int j = u + M2 * i;
                 float2 r[R2];
 #pragma unroll
-                for (int k2 = 0; k2 < R2; k2++) r[k2] = slot[(i * R2 + k2) * kThreads + threadIdx.x];
+                for (int k2 = 0; k2 < R2; k2++) r[k2] = nx[i * R2 + k2];
                 RegDft<R2, +1>::run(r);
                 float2 *row = tile + (j >> 5) * FS + (j & 1) * SS + ((j & 31) >> 1) * PR;
 #pragma unroll
@@ -519,14 +517,14 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_tile_synth_k
             for (int i = 0; i < RPT; i++) {
                 float2 r[R2];
 #pragma unroll
-                for (int k2 = 0; k2 < R2; k2++) r[k2] = slot[(i * R2 + k2) * kThreads + threadIdx.x];
+                for (int k2 = 0; k2 < R2; k2++) r[k2] = nx[i * R2 + k2];
                 RegDft<R2, +1>::run(r);
                 float2 *row = tile + sp_off + (t2 + R2 * i) * PR;
 #pragma unroll
                 for (int c = 0; c < R2; c++) row[c] = r[c];
             }
         }
-        fetch(it + 1);                                            // the slot's values are consumed: refill it
+        fetch(it + 1);                                            // the values are consumed: load the next tile's
         if (LY::WIDE) inst_barrier();
         else __syncwarp();
         // ---- pass A': twiddle and 16-point DFT down column t2 of (f2, p2), in place
@@ -587,7 +585,6 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_tile_synth_k
         }
         if (NBUF == 1) inst_barrier();
     }
-    cp_async_wait<0>();
 }
 
 template <int M, int NT>
