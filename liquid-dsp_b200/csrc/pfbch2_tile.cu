@@ -79,12 +79,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int M>
+// analyzers: the next tile's samples are prefetched into registers (true) or into a cp.async slot in shared memory
+template <int L> constexpr bool kRegPrefetch = (L <= 4);           // measured: m >= 4 loses 3 - 8 % to register pressure
+
+template <int M, int L>
 constexpr size_t tile_smem_bytes()
 {
     using LY = TileLayout<M>;
-    return sizeof(float2) * ((size_t)LY::STAGES * kFr * kThreads + (size_t)(kThreads / (M / 2)) * LY::NBUF * kFr * LY::FS
-                             + (size_t)(M / 32) * kTwPitch);
+    return sizeof(float2) * ((kRegPrefetch<L> ? (size_t)0 : (size_t)LY::STAGES * kFr * kThreads)
+                             + (size_t)(kThreads / (M / 2)) * LY::NBUF * kFr * LY::FS + (size_t)(M / 32) * kTwPitch);
 }
 
 // Phase 2 of the analyzers for one tile: the 2 x 8 sub-problems of M/2 = 16 x R2 points in `tile` (phase-1 layout) are
@@ -164,8 +167,9 @@ __global__ void __launch_bounds__(kThreads, (L <= 10 ? 2 : 1)) pfbch2_tile_kerne
     float2 *ring = reinterpret_cast<float2 *>(smem_raw);          // [kStages][kFr][kThreads]: a thread's own samples
 
     const int inst_l = threadIdx.x / M2, u = threadIdx.x % M2;
-    float2 *tile0 = ring + kStages * kFr * kThreads + inst_l * (NBUF * kFr * FS);
-    float2 *tws = ring + kStages * kFr * kThreads + (kThreads / M2) * (NBUF * kFr * FS); // [R2][kTwPitch]: column t2's 16 twiddles
+    constexpr int kRingUnits = kRegPrefetch<L> ? 0 : kStages * kFr * kThreads;
+    float2 *tile0 = ring + kRingUnits + inst_l * (NBUF * kFr * FS);
+    float2 *tws = ring + kRingUnits + (kThreads / M2) * (NBUF * kFr * FS); // [R2][kTwPitch]: column t2's 16 twiddles
     const long long inst = (long long)blockIdx.x * (kThreads / M2) + inst_l;
     const long long t0 = inst * a.tiles_per_inst;
     long long ntl = (long long)a.n_tiles - t0;
@@ -181,14 +185,19 @@ __global__ void __launch_bounds__(kThreads, (L <= 10 ? 2 : 1)) pfbch2_tile_kerne
     // block, and tiles past the instance's range, arrive as zeros)
     const uint32_t ring_u32 = smem_u32(ring + threadIdx.x);
     const float2 *xs = a.x + (M2 - 1 - u);
+    // REGPF: the next tile's 8 samples are prefetched into registers instead (no shared-memory round trip); taken
+    // where the register budget allows it
+    constexpr bool REGPF = kRegPrefetch<L>;
+    float2 nx[kFr];
     auto fetch = [&](int it) {
         const long long f0 = (t0 + it) * kFr;
 #pragma unroll
         for (int f = 0; f < kFr; f++) {
             const bool ok = it < nt && f0 + f < a.n_frames;
-            cp_async8(ring_u32 + ((it % kStages) * kFr + f) * kThreads * (int)sizeof(float2), ok ? (const void *)(xs + (f0 + f) * M2) : (const void *)a.x, ok ? 8u : 0u);
+            if (REGPF) nx[f] = ok ? __ldg(xs + (f0 + f) * M2) : make_float2(0.f, 0.f);
+            else cp_async8(ring_u32 + ((it % kStages) * kFr + f) * kThreads * (int)sizeof(float2), ok ? (const void *)(xs + (f0 + f) * M2) : (const void *)a.x, ok ? 8u : 0u);
         }
-        cp_async_commit();
+        if (!REGPF) cp_async_commit();
     };
     fetch(0);
     // the instance's copy of the inter-pass twiddles, by column: tws[t2][k1] = e^{+j 2 pi k1 t2 / (M/2)}
@@ -214,14 +223,18 @@ __global__ void __launch_bounds__(kThreads, (L <= 10 ? 2 : 1)) pfbch2_tile_kerne
     for (int it = 0; it < nt; it++) {
         const long long f0 = (t0 + it) * kFr;                     // first (local) frame of the tile: even
         float2 *tile = tile0 + (it % NBUF) * (kFr * FS);
-        if (kStages == 2) fetch(it + 1);
-        cp_async_wait<kStages - 1>();
-        // ---- phase 1
-        {
+        if (REGPF) {
+#pragma unroll
+            for (int f = 0; f < kFr; f++) win[HL + f] = nx[f];
+            fetch(it + 1);
+        } else {
+            if (kStages == 2) fetch(it + 1);
+            cp_async_wait<kStages - 1>();
             const float2 *src = ring + (it % kStages) * kFr * kThreads + threadIdx.x;
 #pragma unroll
             for (int f = 0; f < kFr; f++) win[HL + f] = src[f * kThreads];
         }
+        // ---- phase 1
         float2 *mac_dst = tile + mac_off;
 #pragma unroll
         for (int f = 0; f < kFr; f++) {
@@ -238,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, (L <= 10 ? 2 : 1)) pfbch2_tile_kerne
             mac_dst[f * FS] = z0;
             mac_dst[f * FS + SS] = cmul2_rot(df, w2);
         }
-        if (kStages == 1) fetch(it + 1);                          // the slot's values are consumed: refill it
+        if (!REGPF && kStages == 1) fetch(it + 1);                // the slot's values are consumed: refill it
 #pragma unroll
         for (int i = 0; i < HL; i++) win[i] = win[kFr + i];
         // with two buffers the one barrier of a tile: the instance's phase-1 stores are visible, and every warp has
@@ -270,12 +283,16 @@ struct PfbTileArgs {
     int tiles_per_inst;
 };
 
-template <int M>
+// register prefetch of the next tile's 16 samples where it measured faster (short filters; M = 512 at every length),
+// a cp.async slot in shared memory elsewhere (M = 64, p = 10: 0.93 against 0.75 with 160 B of spills)
+template <int M, int P> constexpr bool kPfbRegPrefetch = (P <= 4) || (M >= 512);
+
+template <int M, int P>
 constexpr size_t pfb_tile_smem_bytes()
 {
     using LY = TileLayout<M>;
-    return sizeof(float2) * ((size_t)2 * kFr * kThreads + (size_t)(kThreads / (M / 2)) * LY::NBUF * kFr * LY::FS
-                             + (size_t)(M / 32) * kTwPitch);
+    return sizeof(float2) * ((kPfbRegPrefetch<M, P> ? (size_t)0 : (size_t)2 * kFr * kThreads)
+                             + (size_t)(kThreads / (M / 2)) * LY::NBUF * kFr * LY::FS + (size_t)(M / 32) * kTwPitch);
 }
 
 template <int M, int P>
@@ -286,10 +303,12 @@ __global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileAr
     constexpr int PR = LY::PR, SS = LY::SS, FS = LY::FS, NBUF = LY::NBUF;
     constexpr int HL = P - 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool REGPF = kPfbRegPrefetch<M, P>;
+    constexpr int kSlotUnits = REGPF ? 0 : 2 * kFr * kThreads;
     float2 *slot = reinterpret_cast<float2 *>(smem_raw);          // [2 kFr][kThreads]: a thread's own 16 samples of a tile
     const int inst_l = threadIdx.x / M2, u = threadIdx.x % M2;
-    float2 *tile0 = slot + 2 * kFr * kThreads + inst_l * (NBUF * kFr * FS);
-    float2 *tws = slot + 2 * kFr * kThreads + (kThreads / M2) * (NBUF * kFr * FS);
+    float2 *tile0 = slot + kSlotUnits + inst_l * (NBUF * kFr * FS);
+    float2 *tws = slot + kSlotUnits + (kThreads / M2) * (NBUF * kFr * FS);
     const long long inst = (long long)blockIdx.x * (kThreads / M2) + inst_l;
     const long long t0 = inst * a.tiles_per_inst;
     long long ntl = (long long)a.n_tiles - t0;
@@ -303,6 +322,8 @@ __global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileAr
         else if (M2 == 32) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(1 + inst_l), "n"(M2) : "memory");
     };
+    // the thread's 16 samples of the next tile: into registers, or into its cp.async slot
+    float2 nx0[kFr], nx1[kFr];
     const uint32_t slot_u32 = smem_u32(slot + threadIdx.x);
     auto fetch = [&](int it) {
         const long long f0 = (t0 + it) * kFr;
@@ -310,10 +331,15 @@ __global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileAr
         for (int f = 0; f < kFr; f++) {
             const bool ok = it < nt && f0 + f < a.n_frames;
             const float2 *src = x + (f0 + f) * M + u;
-            cp_async8(slot_u32 + (2 * f) * kThreads * (int)sizeof(float2), ok ? (const void *)src : (const void *)a.x, ok ? 8u : 0u);
-            cp_async8(slot_u32 + (2 * f + 1) * kThreads * (int)sizeof(float2), ok ? (const void *)(src + M2) : (const void *)a.x, ok ? 8u : 0u);
+            if (REGPF) {
+                nx0[f] = ok ? __ldg(src) : make_float2(0.f, 0.f);
+                nx1[f] = ok ? __ldg(src + M2) : make_float2(0.f, 0.f);
+            } else {
+                cp_async8(slot_u32 + (2 * f) * kThreads * (int)sizeof(float2), ok ? (const void *)src : (const void *)a.x, ok ? 8u : 0u);
+                cp_async8(slot_u32 + (2 * f + 1) * kThreads * (int)sizeof(float2), ok ? (const void *)(src + M2) : (const void *)a.x, ok ? 8u : 0u);
+            }
         }
-        cp_async_commit();
+        if (!REGPF) cp_async_commit();
     };
     fetch(0);
     for (int i = u; i < 16 * R2; i += M2) tws[(i % R2) * kTwPitch + i / R2] = __ldg(a.tw + M2 + i);
@@ -341,8 +367,15 @@ __global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileAr
     for (int it = 0; it < nt; it++) {
         const long long f0 = (t0 + it) * kFr;
         float2 *tile = tile0 + (it % NBUF) * (kFr * FS);
-        cp_async_wait<0>();
-        {
+        if (REGPF) {
+#pragma unroll
+            for (int f = 0; f < kFr; f++) {
+                w0[HL + f] = nx0[f];
+                w1[HL + f] = nx1[f];
+            }
+            fetch(it + 1);
+        } else {
+            cp_async_wait<0>();
             const float2 *src = slot + threadIdx.x;
 #pragma unroll
             for (int f = 0; f < kFr; f++) {
@@ -362,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileAr
             mac_dst[f * FS] = __fadd2_rn(d0, d1);
             mac_dst[f * FS + SS] = cmul2_rot(__fadd2_rn(d0, neg2(d1)), w2);
         }
-        fetch(it + 1);
+        if (!REGPF) fetch(it + 1);                                // the slot's values are consumed: refill it
 #pragma unroll
         for (int i = 0; i < HL; i++) {
             w0[i] = w0[kFr + i];
@@ -372,13 +405,13 @@ __global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileAr
         tile_phase2<M, -1>(tile, u, twc, y, f0, a.n_frames, inst_barrier);
         if (NBUF == 1) inst_barrier();
     }
-    cp_async_wait<0>();
+    if (!REGPF) cp_async_wait<0>();
 }
 
 template <int M, int P>
 void launch_pfb_MP(const PfbTileArgs &a, dim3 grid, cudaStream_t st)
 {
-    constexpr size_t smem = pfb_tile_smem_bytes<M>();
+    constexpr size_t smem = pfb_tile_smem_bytes<M, P>();
     static std::atomic<unsigned long long> configured{0};
     if (lc::first_time_on_device(configured))
         LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch_tile_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -614,7 +647,7 @@ void launch_synth_M(const SynthArgs &a, unsigned int NT, int par0, unsigned int 
 template <int M, int L>
 void launch_ML(const TileArgs &a, unsigned int grid, cudaStream_t st)
 {
-    constexpr size_t smem = tile_smem_bytes<M>();
+    constexpr size_t smem = tile_smem_bytes<M, L>();
     static std::atomic<unsigned long long> configured{0};
     if (lc::first_time_on_device(configured))
         LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_tile_kernel<M, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -661,6 +694,7 @@ void tile_pfbch2_make_twiddles(std::vector<float2> &tw, unsigned int M)
 
 bool tile_pfbch_supported(unsigned int M, unsigned int p)
 {
+    // (M = 256 stays on pfbch_fused_256_kernel: this kernel measured 0.91 against 0.90 at p = 4 but 0.74 against 0.87 at p = 10)
     return (M == 64 || M == 128 || M == 512) && (p == 4 || p == 8 || p == 10);
 }
 

@@ -291,7 +291,7 @@ namespace pfb {
 
 bool fused_pfbch_supported(unsigned int M, unsigned int p)
 {
-    return (M == 16 && (p == 4 || p == 8)) || (M == 256 && (p == 4 || p == 10)) || tile_pfbch_supported(M, p);
+    return tile_pfbch_supported(M, p) || (M == 16 && (p == 4 || p == 8)) || (M == 256 && (p == 4 || p == 10));
 }
 
 bool fused_pfbch_synth_supported(unsigned int M, unsigned int p)
