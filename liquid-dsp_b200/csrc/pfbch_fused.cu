@@ -192,6 +192,180 @@ __global__ void __launch_bounds__(kThreads) pfbch_fused_256_kernel(const PfbArgs
     }
 }
 
+// ------------------------------------------------------------------------------------------ M = 1024
+// The reference's largest benchmark shape (firpfbch_crcf_benchmark.c:85).  One instance = one CTA of 256 threads.
+//   phase 1  thread u owns the FOUR windows u + 256 q: four samples per frame, four P-tap dot products over sliding
+//            register windows, then -- the four results are exactly the inputs of one radix-4 decimation-in-frequency
+//            butterfly of the 1024-point forward DFT -- that butterfly and its three twiddles W1024^(u p): a frame
+//            leaves phase 1 as four independent 256-point problems z_p[u] in the shared tile (4 frames per tile).
+//   phase 2  64 threads per frame, lane = (p fastest, column): 256 = 16 x 16, a 16-point register DFT down the
+//            column (in place), the inter-pass twiddle from a shared copy, a 64-thread named barrier, a 16-point
+//            DFT along the row, and Y[4 (k1 + 16 k2) + p] leaves as 256-byte runs.  Sub-problems are 276 units
+//            apart (16 rows of 17, + 4), so every access pattern is bank-conflict-free (as in pfbch2_fused.cu).
+//   Two tile buffers leave one block barrier per tile; the next tile's 16 samples are prefetched into registers
+//   (P = 4) or into the thread's own cp.async slot (longer filters).
+constexpr int kQFr = 4;                                    // frames per tile
+constexpr int kQSub = 276;                                 // units per 256-point sub-problem
+constexpr int kQFrame = 4 * kQSub;                         // units per frame
+
+struct QuadArgs {
+    const float2 *hist;
+    const float2 *x;
+    float2 *y;
+    const float *taps;         // [P][1024]
+    const float2 *tw;          // tw4[p-1][u] = e^{-j 2 pi u p / 1024}, p = 1..3, u < 256; then tw256[k1][r2] = e^{-j 2 pi k1 r2 / 256}
+    long long n_frames;
+    long long stream_stride;
+    int H;
+    int n_tiles;
+    int tiles_per_inst;
+};
+
+template <int P> constexpr bool kQuadRegPrefetch = (P <= 4);
+template <int P>
+constexpr size_t quad_smem_bytes()
+{
+    return sizeof(float2) * ((kQuadRegPrefetch<P> ? (size_t)0 : (size_t)4 * kQFr * kThreads) + (size_t)2 * kQFr * kQFrame + 16 * 18);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads, P <= 4 ? 2 : 1) pfbch_quad_1024_kernel(const QuadArgs a)
+{
+    constexpr int M = 1024, HL = P - 1;
+    constexpr bool REGPF = kQuadRegPrefetch<P>;
+    constexpr int kSlotUnits = REGPF ? 0 : 4 * kQFr * kThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *slot = reinterpret_cast<float2 *>(smem_raw);              // [4 kQFr][kThreads]
+    float2 *tile0 = slot + kSlotUnits;
+    float2 *tws = tile0 + 2 * kQFr * kQFrame;                         // [r2][k1], pitch 18
+
+    const int u = threadIdx.x;
+    const long long t0 = (long long)blockIdx.x * a.tiles_per_inst;
+    long long ntl = (long long)a.n_tiles - t0;
+    if (ntl > a.tiles_per_inst) ntl = a.tiles_per_inst;
+    const int nt = ntl > 0 ? (int)ntl : 0;
+    const float2 *x = a.x + (long long)blockIdx.y * a.stream_stride;
+    float2 *y = a.y + (long long)blockIdx.y * a.stream_stride;
+
+    float2 nx[4 * kQFr];
+    const uint32_t slot_u32 = smem_u32(slot + u);
+    auto fetch = [&](int it) {
+        const long long f0 = (t0 + it) * kQFr;
+#pragma unroll
+        for (int f = 0; f < kQFr; f++) {
+            const bool ok = it < nt && f0 + f < a.n_frames;
+            const float2 *src = x + (f0 + f) * M + u;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (REGPF) nx[4 * f + q] = ok ? __ldg(src + 256 * q) : make_float2(0.f, 0.f);
+                else {
+                    const uint32_t n = ok ? 8u : 0u;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(slot_u32 + (4 * f + q) * kThreads * 8),
+                                 "l"(ok ? (const void *)(src + 256 * q) : (const void *)a.x), "r"(n) : "memory");
+                }
+            }
+        }
+        if (!REGPF) asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0);
+    tws[(u & 15) * 18 + (u >> 4)] = __ldg(a.tw + 768 + u);            // tw256[k1 = u >> 4][r2 = u & 15]
+    const float2 t1 = __ldg(a.tw + u), t2 = __ldg(a.tw + 256 + u), t3 = __ldg(a.tw + 512 + u);
+    float h[4][P];
+    float2 w[4][HL + kQFr];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#pragma unroll
+        for (int n = 0; n < P; n++) h[q][n] = __ldg(a.taps + n * M + (M - 1 - (u + 256 * q)));
+        if (nt > 0) {
+            const long long f0 = t0 * kQFr;
+#pragma unroll
+            for (int i = 0; i < HL; i++) w[q][i] = ld_hist0(a.hist, x, (f0 - HL + i) * M + u + 256 * q, a.H);
+        }
+    }
+    // phase 2 role: frame f2, sub-problem pp (fastest), column / row c
+    const int f2 = u >> 6, pp = u & 3, c = (u >> 2) & 15;
+    const float4 *twc = reinterpret_cast<const float4 *>(tws + c * 18);
+    const int z_off = (u >> 4) * 17 + (u & 15);                       // where z_p[u] lives inside its sub-problem
+    __syncthreads();
+
+    for (int it = 0; it < nt; it++) {
+        const long long f0 = (t0 + it) * kQFr;
+        float2 *tile = tile0 + (it & 1) * (kQFr * kQFrame);
+        if (REGPF) {
+#pragma unroll
+            for (int f = 0; f < kQFr; f++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) w[q][HL + f] = nx[4 * f + q];
+            fetch(it + 1);
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int f = 0; f < kQFr; f++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) w[q][HL + f] = slot[(4 * f + q) * kThreads + u];
+        }
+        // ---- phase 1
+#pragma unroll
+        for (int f = 0; f < kQFr; f++) {
+            float2 d[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                d[q] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int n = P - 1; n >= 0; n--) d[q] = __ffma2_rn(bc(h[q][n]), w[q][HL + f - n], d[q]);
+            }
+            // radix-4 DIF butterfly of the forward transform (W4 = -j) and the three twiddles
+            const float2 s02 = __fadd2_rn(d[0], d[2]), d02 = __fadd2_rn(d[0], neg2(d[2]));
+            const float2 s13 = __fadd2_rn(d[1], d[3]), d13 = __fadd2_rn(d[1], neg2(d[3]));
+            float2 *zf = tile + f * kQFrame + z_off;
+            zf[0] = __fadd2_rn(s02, s13);
+            zf[kQSub] = cmul2_rot(__fadd2_rn(d02, rot270(d13)), t1);
+            zf[2 * kQSub] = cmul2_rot(__fadd2_rn(s02, neg2(s13)), t2);
+            zf[3 * kQSub] = cmul2_rot(__fadd2_rn(d02, rot90(d13)), t3);
+        }
+        if (!REGPF) fetch(it + 1);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int i = 0; i < HL; i++) w[q][i] = w[q][kQFr + i];
+        __syncthreads();
+        // ---- phase 2
+        float2 *sp = tile + f2 * kQFrame + pp * kQSub;
+        float2 v[16];
+#pragma unroll
+        for (int r1 = 0; r1 < 16; r1++) v[r1] = sp[r1 * 17 + c];
+        RegDft<16, -1>::run(v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float4 t = twc[k];
+            if (k > 0) v[2 * k] = cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+            v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) sp[k1 * 17 + c] = v[k1];
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + f2) : "memory");
+#pragma unroll
+        for (int cc = 0; cc < 16; cc++) v[cc] = sp[c * 17 + cc];      // this thread now plays row k1 = c
+        RegDft<16, -1>::run(v);
+        if (f0 + f2 < a.n_frames) {
+            float2 *yf = y + (f0 + f2) * M + 4 * c + pp;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; k2++) __stcs(yf + 64 * k2, v[k2]);
+        }
+    }
+    if (!REGPF) asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int P>
+void launch_quad_P(const QuadArgs &a, dim3 grid, cudaStream_t st)
+{
+    constexpr size_t smem = quad_smem_bytes<P>();
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch_quad_1024_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pfbch_quad_1024_kernel<P><<<grid, kThreads, smem, st>>>(a);
+}
+
 // ------------------------------------------------------------------------------------------ M = 256 synthesis
 // firpfbch.c:314-336: v_s = unscaled backward DFT of frame s; y[sM + i] = sum_n h[i + nM] v_{s-n}[i].
 //   phase A  16 threads per frame: the 256-point backward DFT straight from global memory (two passes of
@@ -291,7 +465,8 @@ namespace pfb {
 
 bool fused_pfbch_supported(unsigned int M, unsigned int p)
 {
-    return tile_pfbch_supported(M, p) || (M == 16 && (p == 4 || p == 8)) || (M == 256 && (p == 4 || p == 10));
+    return (M == 16 && (p == 4 || p == 8)) || (M == 256 && (p == 4 || p == 10)) || tile_pfbch_supported(M, p) ||
+           (M == 1024 && (p == 4 || p == 8 || p == 10));
 }
 
 bool fused_pfbch_synth_supported(unsigned int M, unsigned int p)
@@ -303,6 +478,21 @@ void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign, unsigned int M
 {
     if (sign < 0 && tile_pfbch_supported(M, p)) {
         tile_pfbch_make_twiddles(tw, M);                      // analyzers for M = 64 / 128 / 512 (pfbch2_tile.cu)
+        return;
+    }
+    if (sign < 0 && M == 1024) {
+        // pfbch_quad_1024_kernel: tw4[p-1][u] = e^{-j 2 pi u p / 1024}, then tw256[k1][r2] = e^{-j 2 pi k1 r2 / 256}
+        tw.resize(3 * 256 + 256);
+        for (int pp = 1; pp <= 3; pp++)
+            for (int u = 0; u < 256; u++) {
+                double ang = -2.0 * M_PI * (double)(u * pp) / 1024.0;
+                tw[(pp - 1) * 256 + u] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+        for (int k1 = 0; k1 < 16; k1++)
+            for (int r2 = 0; r2 < 16; r2++) {
+                double ang = -2.0 * M_PI * (double)(k1 * r2) / 256.0;
+                tw[768 + k1 * 16 + r2] = make_float2((float)cos(ang), (float)sin(ang));
+            }
         return;
     }
     tw.resize(16 * 16);
@@ -319,6 +509,32 @@ long long launch_pfbch_fused(const float2 *d_hist, const float2 *d_x, int H, con
 {
     if (tile_pfbch_supported(M, p))
         return launch_pfbch_tile(d_hist, d_x, H, d_taps, d_tw, d_y, M, p, n_frames, n_streams, stream_stride, st);
+    if (M == 1024) {
+        const long long nq = (long long)((n_frames + kQFr - 1) / kQFr);
+        if (nq == 0 || nq > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;
+        QuadArgs q;
+        q.hist = d_hist;
+        q.x = d_x;
+        q.y = d_y;
+        q.taps = d_taps;
+        q.tw = d_tw;
+        q.H = H;
+        q.n_frames = (long long)n_frames;
+        q.stream_stride = stream_stride;
+        q.n_tiles = (int)nq;
+        long long tpi = 128;                                  // 512 frames per instance: < 2 % of history re-reads
+        while (tpi > 1 && (nq / tpi) * n_streams < 148ll * 4) tpi >>= 1;
+        q.tiles_per_inst = (int)tpi;
+        dim3 grid((unsigned int)((nq + tpi - 1) / tpi), n_streams, 1);
+        switch (p) {
+        case 4: launch_quad_P<4>(q, grid, st); break;
+        case 8: launch_quad_P<8>(q, grid, st); break;
+        case 10: launch_quad_P<10>(q, grid, st); break;
+        default: fatal("launch_pfbch_fused", "unsupported shape");
+        }
+        LC_LAUNCH_CHECK();
+        return (long long)n_frames;
+    }
     const long long n_tiles = (long long)(n_frames / kTile);
     if (n_tiles == 0 || n_tiles > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;
     PfbArgs a;
