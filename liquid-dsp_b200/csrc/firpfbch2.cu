@@ -132,7 +132,7 @@ firpfbch2_crcf firpfbch2_crcf_create(int _type, unsigned int _M, unsigned int _m
     const bool want_tile = _type == LIQUID_ANALYZER && lc::pfb::tile_pfbch2_supported(M, L);
     if (_type == LIQUID_SYNTHESIZER && lc::pfb::tile_pfbch2_synth_supported(M, 2 * L)) {
         std::vector<float2> tw;
-        lc::pfb::tile_pfbch2_make_twiddles(tw, M);
+        lc::pfb::tile_pfbch2_synth_make_twiddles(tw, M);
         LC_CUDA_CHECK(cudaMalloc(&q->d_tw_fused, tw.size() * sizeof(float2)));
         LC_CUDA_CHECK(cudaMemcpy(q->d_tw_fused, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
         q->tiled = true;

@@ -620,6 +620,164 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_tile_synth_k
     }
 }
 
+// ---------------------------------------------------------------------------------- synthesizer, M = 1024
+// Same transposed flow with a radix-4 last stage: one instance = one CTA of 256 threads, thread u owns the FOUR columns
+// u + 256 q of v.  Per frame four 256-point problems X_p[k] = X[4k + p]: 64 threads per frame, lane = (p fastest, row):
+// 16-point DFTs along the rows straight out of the thread's input slot (256-byte runs of the frame), a 64-thread
+// named barrier, twiddle (times 1/2) and 16-point DFTs down the columns; then thread u multiplies E_p[u] by W1024^(u p),
+// does the radix-4 butterfly v[u + 256 q] = sum_p (+j)^(q p) W^(u p) E_p[u], pushes the four values into register
+// windows and forms its two outputs y[t][u], y[t][u + 256] (columns u, u + 256 on even frames, u + 512, u + 768 on
+// odd ones).  4 frames per tile, two tile buffers (one block barrier per tile), sub-problems 276 units apart.
+constexpr int kQFr = 4;
+constexpr int kQSub = 276;
+constexpr int kQFrame = 4 * kQSub;
+
+template <int NT>
+constexpr size_t quad_synth_smem_bytes()
+{
+    return sizeof(float2) * ((size_t)16 * kThreads + (size_t)2 * kQFr * kQFrame + 16 * kTwPitch);
+}
+
+template <int NT, int PAR0>
+__global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_quad_synth_1024_kernel(const SynthArgs a)
+{
+    constexpr int M = 1024, M2 = 512, HL = NT - 1;
+    constexpr int WT = (HL + kQFr - 1) / kQFr;                        // warm-up tiles
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *slot = reinterpret_cast<float2 *>(smem_raw);              // [16][kThreads]: a thread's own 16 inputs of a tile
+    float2 *tile0 = slot + 16 * kThreads;
+    float2 *tws = tile0 + 2 * kQFr * kQFrame;                         // [c][k1], pitch kTwPitch, times 1/2
+    const int u = threadIdx.x;
+    const long long t0 = (long long)blockIdx.x * a.tiles_per_inst;
+    long long ntl = (long long)a.n_tiles - t0;
+    if (ntl > a.tiles_per_inst) ntl = a.tiles_per_inst;
+    const int nt = ntl > 0 ? (int)ntl : 0;
+
+    // phase-A' role: frame f2, sub-problem pp (fastest), row / column idx
+    const int f2 = u >> 6, pp = u & 3, idx = (u >> 2) & 15;
+    const uint32_t slot_u32 = smem_u32(slot + u);
+    auto fetch = [&](int it) {
+        const long long f0 = (t0 + it) * kQFr;
+        const bool ok = it < nt && f0 + f2 < a.n_frames;
+        const float2 *src = a.x + (f0 + f2) * M + 4 * idx + pp;       // X_p[k1 = idx + 16 k2] at + 64 k2
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++)
+            cp_async8(slot_u32 + k2 * kThreads * (int)sizeof(float2), ok ? (const void *)(src + 64 * k2) : (const void *)a.x, ok ? 8u : 0u);
+        cp_async_commit();
+    };
+    const int it0 = (t0 > 0 && nt > 0) ? -WT : 0;
+    fetch(it0);
+    {
+        const float2 t = __ldg(a.tw + 768 + u);                       // tw256[k1 = u >> 4][c = u & 15]
+        tws[(u & 15) * kTwPitch + (u >> 4)] = make_float2(0.5f * t.x, 0.5f * t.y);
+    }
+    const float2 t1 = __ldg(a.tw + u), t2 = __ldg(a.tw + 256 + u), t3 = __ldg(a.tw + 512 + u);   // W1024^(u p)
+    float h0[NT], h1[NT];
+#pragma unroll
+    for (int q = 0; q < NT; q++) {
+        h0[q] = __ldg(a.taps + q * M2 + u);
+        h1[q] = __ldg(a.taps + q * M2 + u + 256);
+    }
+    float2 w[4][HL + kQFr];                                           // columns u + 256 q of v, oldest first
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int i = 0; i < HL; i++) {
+            w[q][i] = make_float2(0.f, 0.f);
+            if (t0 == 0 && a.hist != nullptr) w[q][i] = __ldg(a.hist + (size_t)(a.hist_rows - HL + i) * M + u + 256 * q);
+        }
+    const float4 *twc = reinterpret_cast<const float4 *>(tws + idx * kTwPitch);
+    const int z_off = (u >> 4) * 17 + (u & 15);
+    __syncthreads();
+
+    for (int it = it0; it < nt; it++) {
+        const long long f0 = (t0 + it) * kQFr;
+        float2 *tile = tile0 + ((it - it0) & 1) * (kQFr * kQFrame);
+        float2 *sp = tile + f2 * kQFrame + pp * kQSub;
+        cp_async_wait<0>();
+        float2 v[16];
+        // ---- pass B': row k1 = idx of sub-problem pp
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) v[k2] = slot[k2 * kThreads + u];
+        RegDft<16, +1>::run(v);
+#pragma unroll
+        for (int c = 0; c < 16; c++) sp[idx * 17 + c] = v[c];
+        fetch(it + 1);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + f2) : "memory");
+        // ---- pass A': twiddle and DFT down column c = idx, in place
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) v[k1] = sp[k1 * 17 + idx];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float4 t = twc[k];
+            v[2 * k] = (k == 0) ? __fmul2_rn(bc(0.5f), v[0]) : cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+            v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+        }
+        RegDft<16, +1>::run(v);
+#pragma unroll
+        for (int r1 = 0; r1 < 16; r1++) sp[r1 * 17 + idx] = v[r1];
+        __syncthreads();
+        // ---- FIR: radix-4 last stage, window push, dot products
+#pragma unroll
+        for (int f = 0; f < kQFr; f++) {
+            const float2 *zf = tile + f * kQFrame + z_off;
+            const float2 b0 = zf[0], b1 = cmul2_rot(zf[kQSub], t1), b2 = cmul2_rot(zf[2 * kQSub], t2), b3 = cmul2_rot(zf[3 * kQSub], t3);
+            const float2 s02 = __fadd2_rn(b0, b2), d02 = __fadd2_rn(b0, neg2(b2));
+            const float2 s13 = __fadd2_rn(b1, b3), d13 = __fadd2_rn(b1, neg2(b3));
+            w[0][HL + f] = __fadd2_rn(s02, s13);
+            w[1][HL + f] = __fadd2_rn(d02, rot90(d13));               // W4 = +j (backward transform)
+            w[2][HL + f] = __fadd2_rn(s02, neg2(s13));
+            w[3][HL + f] = __fadd2_rn(d02, rot270(d13));
+        }
+        if (it >= 0) {
+#pragma unroll
+            for (int f = 0; f < kQFr; f++) {
+                const bool odd = ((PAR0 + f) & 1) != 0;               // f0 is even
+                float2 a0 = make_float2(0.f, 0.f), a1 = a0, c0 = a0, c1 = a0;
+#pragma unroll
+                for (int q = 0; q < NT; q++) {
+                    const float2 s0 = odd ? w[2][HL + f - q] : w[0][HL + f - q];
+                    const float2 s1 = odd ? w[3][HL + f - q] : w[1][HL + f - q];
+                    if (q & 1) { a1 = __ffma2_rn(bc(h0[q]), s0, a1); c1 = __ffma2_rn(bc(h1[q]), s1, c1); }
+                    else       { a0 = __ffma2_rn(bc(h0[q]), s0, a0); c0 = __ffma2_rn(bc(h1[q]), s1, c0); }
+                }
+                if (f0 + f < a.n_frames) {
+                    __stcs(a.y + (f0 + f) * M2 + u, __fadd2_rn(a0, a1));
+                    __stcs(a.y + (f0 + f) * M2 + u + 256, __fadd2_rn(c0, c1));
+                }
+            }
+            if (f0 + kQFr > a.n_frames - NT) {
+#pragma unroll
+                for (int f = 0; f < kQFr; f++) {
+                    const long long r = f0 + f - (a.n_frames - NT);
+                    if (r >= 0 && f0 + f < a.n_frames) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) a.hist_out[r * M + u + 256 * q] = w[q][HL + f];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int i = 0; i < HL; i++) w[q][i] = w[q][kQFr + i];
+    }
+    cp_async_wait<0>();
+}
+
+template <int NT>
+void launch_quad_synth_N(const SynthArgs &a, int par0, unsigned int grid, cudaStream_t st)
+{
+    constexpr size_t smem = quad_synth_smem_bytes<NT>();
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured)) {
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_quad_synth_1024_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch2_quad_synth_1024_kernel<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (par0) pfbch2_quad_synth_1024_kernel<NT, 1><<<grid, kThreads, smem, st>>>(a);
+    else      pfbch2_quad_synth_1024_kernel<NT, 0><<<grid, kThreads, smem, st>>>(a);
+}
+
 template <int M, int NT>
 void launch_synth_MN(const SynthArgs &a, int par0, unsigned int grid, cudaStream_t st)
 {
@@ -738,14 +896,36 @@ long long launch_pfbch_tile(const float2 *d_hist, const float2 *d_x, int H, cons
 
 bool tile_pfbch2_synth_supported(unsigned int M, unsigned int n_taps)
 {
-    return (M == 64 || M == 128 || M == 256 || M == 512) && (n_taps == 8 || n_taps == 16 || n_taps == 20);
+    return ((M == 64 || M == 128 || M == 256 || M == 512) && (n_taps == 8 || n_taps == 16 || n_taps == 20)) ||
+           (M == 1024 && (n_taps == 8 || n_taps == 16));
+}
+
+void tile_pfbch2_synth_make_twiddles(std::vector<float2> &tw, unsigned int M)
+{
+    if (M != 1024) {
+        tile_pfbch2_make_twiddles(tw, M);
+        return;
+    }
+    // pfbch2_quad_synth_1024_kernel: tw4[p-1][u] = e^{+j 2 pi u p / 1024}, p = 1..3, u < 256; then tw256[k1][c] = e^{+j 2 pi k1 c / 256}
+    tw.resize(3 * 256 + 256);
+    for (int pp = 1; pp <= 3; pp++)
+        for (int u = 0; u < 256; u++) {
+            const double ang = 2.0 * M_PI * (double)(u * pp) / 1024.0;
+            tw[(pp - 1) * 256 + u] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    for (int k1 = 0; k1 < 16; k1++)
+        for (int c = 0; c < 16; c++) {
+            const double ang = 2.0 * M_PI * (double)(k1 * c) / 256.0;
+            tw[768 + k1 * 16 + c] = make_float2((float)cos(ang), (float)sin(ang));
+        }
 }
 
 long long launch_pfbch2_tile_synth(const float2 *d_hist_rows, int hist_rows, const float2 *d_x, const float *d_taps,
                                    const float2 *d_tw, float2 *d_y, float2 *d_hist_out, unsigned int M, unsigned int n_taps,
                                    unsigned long long n_frames, int parity0, cudaStream_t st)
 {
-    const long long n_tiles = (long long)((n_frames + kFr - 1) / kFr);
+    const int fr_per_tile = (M == 1024) ? kQFr : kFr;
+    const long long n_tiles = (long long)((n_frames + fr_per_tile - 1) / fr_per_tile);
     if (n_frames < n_taps || n_tiles > (1ll << 30)) return 0;     // the state rows all come from this call
     SynthArgs a;
     a.hist = d_hist_rows;
@@ -758,6 +938,17 @@ long long launch_pfbch2_tile_synth(const float2 *d_hist_rows, int hist_rows, con
     a.n_frames = (long long)n_frames;
     a.n_tiles = (int)n_tiles;
     // 64 tiles per instance keep the warm-up tiles (1 - 3) below 5 %; never fewer than 4 (the warm-up reaches back 3)
+    if (M == 1024) {
+        long long tpi = 128;                                      // 512 frames per instance; never fewer than 8 tiles (warm-up: 2 - 4)
+        while (tpi > 8 && (n_tiles / tpi) < 148ll * 4) tpi >>= 1;
+        a.tiles_per_inst = (int)tpi;
+        const unsigned int grid = (unsigned int)((n_tiles + tpi - 1) / tpi);
+        if (n_taps == 8) launch_quad_synth_N<8>(a, parity0 & 1, grid, st);
+        else if (n_taps == 16) launch_quad_synth_N<16>(a, parity0 & 1, grid, st);
+        else fatal("launch_pfbch2_tile_synth", "unsupported tap count");
+        LC_LAUNCH_CHECK();
+        return (long long)n_frames;
+    }
     const long long inst_per_cta = kThreads / (M / 2);
     long long tpi = 64;
     while (tpi > 4 && (n_tiles / tpi) < 148ll * 4 * inst_per_cta) tpi >>= 1;

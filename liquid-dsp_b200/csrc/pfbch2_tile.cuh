@@ -18,10 +18,11 @@ long long launch_pfbch2_tile(const float2 *d_hist, const float2 *d_x, int H, con
                              const float2 *d_tw, float2 *d_y, unsigned int M, unsigned int L,
                              unsigned long long n_frames, int parity0, cudaStream_t st);
 
-// Synthesizer: n_taps = 4m in {8, 16, 20}.  Covers all n_frames (>= n_taps) or returns 0 (caller takes the two-kernel
+// Synthesizer: M = 64 ... 512 with n_taps = 4m in {8, 16, 20}; M = 1024 with n_taps in {8, 16}.  Covers all n_frames (>= n_taps) or returns 0 (caller takes the two-kernel
 // path).  d_hist_rows: hist_rows rows of v (scaled IDFT output) preceding frame 0; d_hist_out (may not alias it)
 // receives the rows of v of the last n_taps frames.  d_taps: [n_taps][M/2]; d_tw: the analyzer's table.
 bool tile_pfbch2_synth_supported(unsigned int M, unsigned int n_taps);
+void tile_pfbch2_synth_make_twiddles(std::vector<float2> &tw, unsigned int M);   // M = 1024 has its own table
 long long launch_pfbch2_tile_synth(const float2 *d_hist_rows, int hist_rows, const float2 *d_x, const float *d_taps,
                                    const float2 *d_tw, float2 *d_y, float2 *d_hist_out, unsigned int M, unsigned int n_taps,
                                    unsigned long long n_frames, int parity0, cudaStream_t st);

@@ -614,7 +614,7 @@ def test_pfbch2_tile_vs_oracle_odd_splits_and_generic(L, orc, monkeypatch, M, m)
 
 
 @pytest.mark.parametrize("M,m", [(64, 2), (64, 4), (64, 5), (128, 2), (128, 5), (256, 2), (256, 4), (256, 5),
-                                 (512, 2), (512, 4), (512, 5)])
+                                 (512, 2), (512, 4), (512, 5), (1024, 2), (1024, 4)])
 def test_pfbch2_tile_synthesizer_vs_oracle_odd_splits_and_generic(L, orc, monkeypatch, M, m):
     """the reference's synthesizer benchmark shapes (firpfbch2_crcf_benchmark.c:84-90, m = 2) and longer filters on
     the fused tile synthesizer: odd start parity, ragged tiles, several instances (warm-up tiles rebuild the

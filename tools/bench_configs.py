@@ -204,7 +204,7 @@ def run(configs, steps, warmup, sink, device_index=0):
     if "ts" in args.configs:
         # the reference's synthesizer benchmark shapes (firpfbch2_crcf_benchmark.c:84-90: m = 2) and m = 4 / 5:
         # the fused tile synthesizer of pfbch2_tile.cu; throughput in OUTPUT samples/s, 16 B in + 8 B out per output
-        for M, m in ((64, 2), (64, 5), (128, 2), (256, 2), (256, 4), (256, 5), (512, 2), (512, 5)):
+        for M, m in ((64, 2), (64, 5), (128, 2), (256, 2), (256, 4), (256, 5), (512, 2), (512, 5), (1024, 2), (1024, 4)):
             n = 1 << 27
             q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
             X = torch.empty(4 * n, dtype=torch.float32, device=dev)
