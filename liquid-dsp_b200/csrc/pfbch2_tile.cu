@@ -632,20 +632,21 @@ constexpr int kQFr = 4;
 constexpr int kQSub = 276;
 constexpr int kQFrame = 4 * kQSub;
 
+constexpr bool kQuadSynthRegPf = true;
 template <int NT>
 constexpr size_t quad_synth_smem_bytes()
 {
-    return sizeof(float2) * ((size_t)16 * kThreads + (size_t)2 * kQFr * kQFrame + 16 * kTwPitch);
+    return sizeof(float2) * ((kQuadSynthRegPf ? (size_t)0 : (size_t)16 * kThreads) + (size_t)2 * kQFr * kQFrame + 16 * kTwPitch);
 }
 
 template <int NT, int PAR0>
-__global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_quad_synth_1024_kernel(const SynthArgs a)
+__global__ void __launch_bounds__(kThreads, (NT <= 8 && !kQuadSynthRegPf) ? 2 : 1) pfbch2_quad_synth_1024_kernel(const SynthArgs a)
 {
     constexpr int M = 1024, M2 = 512, HL = NT - 1;
     constexpr int WT = (HL + kQFr - 1) / kQFr;                        // warm-up tiles
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *slot = reinterpret_cast<float2 *>(smem_raw);              // [16][kThreads]: a thread's own 16 inputs of a tile
-    float2 *tile0 = slot + 16 * kThreads;
+    float2 *tile0 = slot + (kQuadSynthRegPf ? 0 : 16 * kThreads);
     float2 *tws = tile0 + 2 * kQFr * kQFrame;                         // [c][k1], pitch kTwPitch, times 1/2
     const int u = threadIdx.x;
     const long long t0 = (long long)blockIdx.x * a.tiles_per_inst;
@@ -656,14 +657,17 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_quad_synth_1
     // phase-A' role: frame f2, sub-problem pp (fastest), row / column idx
     const int f2 = u >> 6, pp = u & 3, idx = (u >> 2) & 15;
     const uint32_t slot_u32 = smem_u32(slot + u);
+    float2 nx[16];
     auto fetch = [&](int it) {
         const long long f0 = (t0 + it) * kQFr;
         const bool ok = it < nt && f0 + f2 < a.n_frames;
         const float2 *src = a.x + (f0 + f2) * M + 4 * idx + pp;       // X_p[k1 = idx + 16 k2] at + 64 k2
 #pragma unroll
-        for (int k2 = 0; k2 < 16; k2++)
-            cp_async8(slot_u32 + k2 * kThreads * (int)sizeof(float2), ok ? (const void *)(src + 64 * k2) : (const void *)a.x, ok ? 8u : 0u);
-        cp_async_commit();
+        for (int k2 = 0; k2 < 16; k2++) {
+            if (kQuadSynthRegPf) nx[k2] = ok ? __ldg(src + 64 * k2) : make_float2(0.f, 0.f);
+            else cp_async8(slot_u32 + k2 * kThreads * (int)sizeof(float2), ok ? (const void *)(src + 64 * k2) : (const void *)a.x, ok ? 8u : 0u);
+        }
+        if (!kQuadSynthRegPf) cp_async_commit();
     };
     const int it0 = (t0 > 0 && nt > 0) ? -WT : 0;
     fetch(it0);
@@ -694,11 +698,11 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_quad_synth_1
         const long long f0 = (t0 + it) * kQFr;
         float2 *tile = tile0 + ((it - it0) & 1) * (kQFr * kQFrame);
         float2 *sp = tile + f2 * kQFrame + pp * kQSub;
-        cp_async_wait<0>();
+        if (!kQuadSynthRegPf) cp_async_wait<0>();
         float2 v[16];
         // ---- pass B': row k1 = idx of sub-problem pp
 #pragma unroll
-        for (int k2 = 0; k2 < 16; k2++) v[k2] = slot[k2 * kThreads + u];
+        for (int k2 = 0; k2 < 16; k2++) v[k2] = kQuadSynthRegPf ? nx[k2] : slot[k2 * kThreads + u];
         RegDft<16, +1>::run(v);
 #pragma unroll
         for (int c = 0; c < 16; c++) sp[idx * 17 + c] = v[c];
