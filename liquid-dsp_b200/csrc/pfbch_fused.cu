@@ -458,6 +458,128 @@ __global__ void __launch_bounds__(kThreads) pfbch_synth_fused_256_kernel(const S
     }
 }
 
+// ------------------------------------------------------------------------------------------ M = 1024 synthesis
+// firpfbch.c:314-336 at M = 1024: the transposed form of pfbch_quad_1024_kernel.  64 threads per frame, lane =
+// (p fastest, row): the four 256-point backward problems X_p[k] = X[4k + p] -- 16-point DFTs along the rows out of
+// register-prefetched inputs (256-byte runs of the frame), a 64-thread named barrier, twiddle and 16-point DFTs
+// down the columns; then thread u does the radix-4 last stage v[u + 256 q] = sum_p (+j)^(q p) W1024^(u p) E_p[u],
+// pushes the four values into register windows and forms its four outputs y[s][u + 256 q] = sum_n h[u + 256 q + nM]
+// v_{s-n}[u + 256 q].  An instance that starts inside the stream first transforms the ceil((P-1)/4) tiles before
+// its range; the object's state (the last P rows of v) is recomputed by the caller with the batched transform.
+template <int P>
+__global__ void __launch_bounds__(kThreads, P <= 4 ? 2 : 1) pfbch_quad_synth_1024_kernel(const SynArgs a, const long long n_frames)
+{
+    constexpr int M = 1024, HL = P - 1;
+    constexpr int WT = (HL + kQFr - 1) / kQFr;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *tile0 = reinterpret_cast<float2 *>(smem_raw);
+    float2 *tws = tile0 + 2 * kQFr * kQFrame;                         // [c][k1], pitch 18
+    const int u = threadIdx.x;
+    const long long t0 = (long long)blockIdx.x * a.tiles_per_inst;
+    long long ntl = (long long)a.n_tiles - t0;
+    if (ntl > a.tiles_per_inst) ntl = a.tiles_per_inst;
+    const int nt = ntl > 0 ? (int)ntl : 0;
+    const float2 *x = a.x + (long long)blockIdx.y * a.stream_stride;
+    float2 *y = a.y + (long long)blockIdx.y * a.stream_stride;
+
+    const int f2 = u >> 6, pp = u & 3, idx = (u >> 2) & 15;
+    float2 nx[16];
+    auto fetch = [&](int it) {
+        const long long f0 = (t0 + it) * kQFr;
+        const bool ok = it < nt && f0 + f2 < n_frames;
+        const float2 *src = x + (f0 + f2) * M + 4 * idx + pp;         // X_p[k1 = idx + 16 k2] at + 64 k2
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) nx[k2] = ok ? __ldg(src + 64 * k2) : make_float2(0.f, 0.f);
+    };
+    const int it0 = (t0 > 0 && nt > 0) ? -WT : 0;
+    fetch(it0);
+    tws[(u & 15) * 18 + (u >> 4)] = __ldg(a.tw + 768 + u);            // tw256[k1 = u >> 4][c = u & 15]
+    const float2 t1 = __ldg(a.tw + u), t2 = __ldg(a.tw + 256 + u), t3 = __ldg(a.tw + 512 + u);
+    float h[4][P];
+    float2 w[4][HL + kQFr];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#pragma unroll
+        for (int n = 0; n < P; n++) h[q][n] = __ldg(a.taps + n * M + u + 256 * q);
+#pragma unroll
+        for (int i = 0; i < HL; i++) {
+            const int r = a.n_hist_rows - HL + i;
+            w[q][i] = (t0 == 0 && a.hist_rows != nullptr && r >= 0) ? __ldg(a.hist_rows + (long long)r * M + u + 256 * q)
+                                                                   : make_float2(0.f, 0.f);
+        }
+    }
+    const float4 *twc = reinterpret_cast<const float4 *>(tws + idx * 18);
+    const int z_off = (u >> 4) * 17 + (u & 15);
+    __syncthreads();
+
+    for (int it = it0; it < nt; it++) {
+        const long long f0 = (t0 + it) * kQFr;
+        float2 *tile = tile0 + ((it - it0) & 1) * (kQFr * kQFrame);
+        float2 *sp = tile + f2 * kQFrame + pp * kQSub;
+        float2 v[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) v[k2] = nx[k2];
+        fetch(it + 1);
+        RegDft<16, +1>::run(v);
+#pragma unroll
+        for (int c = 0; c < 16; c++) sp[idx * 17 + c] = v[c];
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + f2) : "memory");
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) v[k1] = sp[k1 * 17 + idx];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float4 t = twc[k];
+            if (k > 0) v[2 * k] = cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+            v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+        }
+        RegDft<16, +1>::run(v);
+#pragma unroll
+        for (int r1 = 0; r1 < 16; r1++) sp[r1 * 17 + idx] = v[r1];
+        __syncthreads();
+#pragma unroll
+        for (int f = 0; f < kQFr; f++) {
+            const float2 *zf = tile + f * kQFrame + z_off;
+            const float2 b0 = zf[0], b1 = cmul2_rot(zf[kQSub], t1), b2 = cmul2_rot(zf[2 * kQSub], t2), b3 = cmul2_rot(zf[3 * kQSub], t3);
+            const float2 s02 = __fadd2_rn(b0, b2), d02 = __fadd2_rn(b0, neg2(b2));
+            const float2 s13 = __fadd2_rn(b1, b3), d13 = __fadd2_rn(b1, neg2(b3));
+            w[0][HL + f] = __fadd2_rn(s02, s13);
+            w[1][HL + f] = __fadd2_rn(d02, rot90(d13));               // W4 = +j (backward transform)
+            w[2][HL + f] = __fadd2_rn(s02, neg2(s13));
+            w[3][HL + f] = __fadd2_rn(d02, rot270(d13));
+        }
+        if (it >= 0) {
+#pragma unroll
+            for (int f = 0; f < kQFr; f++) {
+                float2 acc[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    acc[q] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int n = P - 1; n >= 0; n--) acc[q] = __ffma2_rn(bc(h[q][n]), w[q][HL + f - n], acc[q]);
+                }
+                if (f0 + f < n_frames) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) __stcs(y + (f0 + f) * M + u + 256 * q, acc[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int i = 0; i < HL; i++) w[q][i] = w[q][kQFr + i];
+    }
+}
+
+template <int P>
+void launch_quad_synth_P(const SynArgs &a, long long n_frames, dim3 grid, cudaStream_t st)
+{
+    constexpr size_t smem = sizeof(float2) * ((size_t)2 * kQFr * kQFrame + 16 * 18);
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch_quad_synth_1024_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pfbch_quad_synth_1024_kernel<P><<<grid, kThreads, smem, st>>>(a, n_frames);
+}
+
 }  // namespace
 
 namespace lc {
@@ -471,7 +593,7 @@ bool fused_pfbch_supported(unsigned int M, unsigned int p)
 
 bool fused_pfbch_synth_supported(unsigned int M, unsigned int p)
 {
-    return M == 256 && (p == 4 || p == 10);
+    return (M == 256 && (p == 4 || p == 10)) || (M == 1024 && (p == 4 || p == 8 || p == 10));
 }
 
 void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign, unsigned int M, unsigned int p)
@@ -480,17 +602,17 @@ void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign, unsigned int M
         tile_pfbch_make_twiddles(tw, M);                      // analyzers for M = 64 / 128 / 512 (pfbch2_tile.cu)
         return;
     }
-    if (sign < 0 && M == 1024) {
-        // pfbch_quad_1024_kernel: tw4[p-1][u] = e^{-j 2 pi u p / 1024}, then tw256[k1][r2] = e^{-j 2 pi k1 r2 / 256}
+    if (M == 1024) {
+        // pfbch_quad[_synth]_1024_kernel: tw4[p-1][u] = e^{sign j 2 pi u p / 1024}, then tw256[k1][r2] = e^{sign j 2 pi k1 r2 / 256}
         tw.resize(3 * 256 + 256);
         for (int pp = 1; pp <= 3; pp++)
             for (int u = 0; u < 256; u++) {
-                double ang = -2.0 * M_PI * (double)(u * pp) / 1024.0;
+                double ang = (double)sign * 2.0 * M_PI * (double)(u * pp) / 1024.0;
                 tw[(pp - 1) * 256 + u] = make_float2((float)cos(ang), (float)sin(ang));
             }
         for (int k1 = 0; k1 < 16; k1++)
             for (int r2 = 0; r2 < 16; r2++) {
-                double ang = -2.0 * M_PI * (double)(k1 * r2) / 256.0;
+                double ang = (double)sign * 2.0 * M_PI * (double)(k1 * r2) / 256.0;
                 tw[768 + k1 * 16 + r2] = make_float2((float)cos(ang), (float)sin(ang));
             }
         return;
@@ -568,7 +690,31 @@ long long launch_pfbch_synth_fused(const float2 *d_hist_rows, int n_hist_rows, c
                                    unsigned long long n_frames, unsigned int n_streams, long long stream_stride,
                                    cudaStream_t st)
 {
-    (void)M;
+    if (M == 1024) {
+        const long long nq = (long long)((n_frames + kQFr - 1) / kQFr);
+        if (nq == 0 || nq > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;
+        SynArgs q;
+        q.hist_rows = d_hist_rows;
+        q.n_hist_rows = n_hist_rows;
+        q.x = d_x;
+        q.y = d_y;
+        q.taps = d_taps;
+        q.tw = d_tw;
+        q.n_tiles = (int)nq;
+        q.stream_stride = stream_stride;
+        long long tpi = 128;                                  // never fewer than 8 tiles: the warm-up reaches back up to 3
+        while (tpi > 8 && (nq / tpi) * n_streams < 148ll * 4) tpi >>= 1;
+        q.tiles_per_inst = (int)tpi;
+        dim3 grid((unsigned int)((nq + tpi - 1) / tpi), n_streams, 1);
+        switch (p) {
+        case 4: launch_quad_synth_P<4>(q, (long long)n_frames, grid, st); break;
+        case 8: launch_quad_synth_P<8>(q, (long long)n_frames, grid, st); break;
+        case 10: launch_quad_synth_P<10>(q, (long long)n_frames, grid, st); break;
+        default: fatal("launch_pfbch_synth_fused", "unsupported shape");
+        }
+        LC_LAUNCH_CHECK();
+        return (long long)n_frames;
+    }
     const long long n_tiles = (long long)(n_frames / kTile);
     if (n_tiles == 0 || n_tiles > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;
     SynArgs a;

@@ -1151,9 +1151,10 @@ def test_pfbch_streams_dev(L, orc, M, m):
         assert np.abs(got[s].reshape(nfr, M) - want).max() / np.abs(want).max() < 1e-5
 
 
-@pytest.mark.parametrize("M,m,nfr", [(256, 5, 16 * 40 + 9), (256, 2, 16 * 33), (64, 3, 50)])
+@pytest.mark.parametrize("M,m,nfr", [(256, 5, 16 * 40 + 9), (256, 2, 16 * 33), (64, 3, 50), (1024, 2, 4 * 77 + 3), (1024, 5, 203),
+                                     (1024, 4, 1300)])
 def test_pfbch_synthesis_fused_and_streams(L, orc, M, m, nfr):
-    """fused M=256 synthesizer (many tiles / instances, tail, state carry) and the multi-stream form"""
+    """fused M=256 / M=1024 synthesizers (many tiles / instances, tail, state carry) and the multi-stream form"""
     import ctypes as C
     X = orc.synth_input(nfr * M, seed=0xC5 + M + m)
     want = orc.Firpfbch(orc.SYNTHESIZER, M, kaiser=(m, 60.0)).execute_frames(X)
