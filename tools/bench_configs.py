@@ -190,6 +190,32 @@ def run(configs, steps, warmup, sink, device_index=0):
             ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
             report("t: firpfbch2_crcf analysis M=%d m=%d (tile kernel), 2^28 samples" % (M, m), n, 24, ms, ln)
             del x, y
+    if "sm" in args.configs:
+        # the smallest shapes of the reference's benchmarks (firpfbch2_crcf_benchmark.c:70-90, firpfbch_crcf_benchmark.c:80-81), m = 2
+        for kind, M in (("a2", 4), ("a2", 8), ("a2", 16), ("a2", 32), ("s2", 4), ("s2", 16), ("s2", 32), ("a1", 4), ("a1", 8), ("a1", 32)):
+            m, n = 2, 1 << 27
+            if kind == "a2":
+                q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+                x = torch.empty(2 * n, dtype=torch.float32, device=dev)
+                y = torch.empty(4 * n, dtype=torch.float32, device=dev)
+                L.synth_input_dev(x.data_ptr(), n, stream=st.cuda_stream)
+                ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // (M // 2), y.data_ptr(), st.cuda_stream))
+                report("sm: firpfbch2_crcf analysis M=%d m=2, 2^27 samples" % M, n, 24, ms, ln)
+            elif kind == "s2":
+                q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+                x = torch.empty(4 * n, dtype=torch.float32, device=dev)
+                y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+                L.synth_input_dev(x.data_ptr(), 2 * n, stream=st.cuda_stream)
+                ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // (M // 2), y.data_ptr(), st.cuda_stream))
+                report("sm: firpfbch2_crcf synthesis M=%d m=2, 2^27 output samples" % M, n, 24, ms, ln)
+            else:
+                q = L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+                x = torch.empty(2 * n, dtype=torch.float32, device=dev)
+                y = torch.empty(2 * n, dtype=torch.float32, device=dev)
+                L.synth_input_dev(x.data_ptr(), n, stream=st.cuda_stream)
+                ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
+                report("sm: firpfbch_crcf analysis M=%d m=2, 2^27 samples" % M, n, 16, ms, ln)
+            del x, y
     if "tp" in args.configs:
         # firpfbch_crcf analysis at the reference's own benchmark shapes (firpfbch_crcf_benchmark.c:80-85: m = 2) and m = 5
         for M, m in ((64, 2), (64, 5), (128, 2), (256, 2), (512, 2), (512, 5), (1024, 2)):
