@@ -19,6 +19,7 @@
 #include "pfbch2_fused.cuh"
 #include "pfbch2_cluster.cuh"
 #include "pfbch2_tile.cuh"
+#include "pfbch2_small.cuh"
 
 struct firpfbch2_crcf_s {
     int type;
@@ -30,6 +31,7 @@ struct firpfbch2_crcf_s {
     float2 *d_tw_fused = nullptr;  // fused kernel's inter-stage twiddles
     bool fused = false;            // M = 1024: one CTA per frame (pfbch2_fused.cu)
     bool clustered = false;        // M = 4096: one frame per cluster of 8 CTAs (pfbch2_cluster.cu)
+    bool small = false;            // M = 4 ... 32: several instances per warp (pfbch2_small.cu)
     bool tiled = false;            // M = 64 ... 512: register windows + shared-memory tile of 8 frames (pfbch2_tile.cu)
     float2 *d_hist = nullptr;      // last H samples (analyzer: inputs; synthesizer: scaled IDFT rows)
     int flag = 0;                  // frame parity (firpfbch2.c:57)
@@ -52,6 +54,9 @@ void analyze_dev(firpfbch2_crcf q, const float2 *d_hist, const float2 *d_x, int 
     else if (q->clustered && n_frames >= 32 && !getenv("LIQUID_CUDA_NO_FUSED"))
         done = (unsigned long long)lc::pfb::launch_pfbch2_cluster(d_hist, d_x, (int)q->H, q->d_taps_scaled, q->d_tw_fused,
                                                                   d_y, q->M, q->L, n_frames, parity0, st);
+    else if (q->small && ((uintptr_t)d_y % 16) == 0 && ((uintptr_t)d_x % 16) == 0 && !getenv("LIQUID_CUDA_NO_FUSED"))
+        done = (unsigned long long)lc::pfb::launch_pfbch2_small(d_hist, d_x, (int)q->H, q->d_taps_scaled, d_y, q->M, q->L,
+                                                                n_frames, parity0, st);
     else if (q->tiled && !getenv("LIQUID_CUDA_NO_FUSED"))
         done = (unsigned long long)lc::pfb::launch_pfbch2_tile(d_hist, d_x, (int)q->H, q->d_taps_scaled, q->d_tw_fused,
                                                                d_y, q->M, q->L, n_frames, parity0, st);
@@ -130,6 +135,15 @@ firpfbch2_crcf firpfbch2_crcf_create(int _type, unsigned int _M, unsigned int _m
     const bool want_fused = _type == LIQUID_ANALYZER && lc::pfb::fused_pfbch2_supported(M, L);
     const bool want_cluster = _type == LIQUID_ANALYZER && lc::pfb::cluster_pfbch2_supported(M, L);
     const bool want_tile = _type == LIQUID_ANALYZER && lc::pfb::tile_pfbch2_supported(M, L);
+    if (_type == LIQUID_SYNTHESIZER && lc::pfb::small_pfbch2_synth_supported(M, 2 * L)) q->small = true;
+    const bool want_small = _type == LIQUID_ANALYZER && lc::pfb::small_pfbch2_supported(M, L);
+    if (want_small) {
+        std::vector<float> ts(taps);
+        for (float &v : ts) v *= 1.0f / (float)M;
+        LC_CUDA_CHECK(cudaMalloc(&q->d_taps_scaled, ts.size() * sizeof(float)));
+        LC_CUDA_CHECK(cudaMemcpy(q->d_taps_scaled, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice));
+        q->small = true;
+    }
     if (_type == LIQUID_SYNTHESIZER && lc::pfb::tile_pfbch2_synth_supported(M, 2 * L)) {
         std::vector<float2> tw;
         lc::pfb::tile_pfbch2_synth_make_twiddles(tw, M);
@@ -245,6 +259,11 @@ void firpfbch2_crcf_execute_block_dev(firpfbch2_crcf _q, const void *_d_x, unsig
     if (_q->type == LIQUID_ANALYZER) {
         analyze_dev(_q, _q->d_hist, (const float2 *)_d_x, _q->flag, _n_frames, (float2 *)_d_y, st);
         lc::roll_history(_q->d_hist, _q->H, _q->hist_tmp, (const float2 *)_d_x, _n_frames * _q->M2, st);
+    } else if (_q->small && _n_frames >= 2 * _q->L && ((uintptr_t)_d_x % 16) == 0 && !getenv("LIQUID_CUDA_NO_FUSED")) {
+        float2 *d_new = (float2 *)_q->hist_tmp.get(sizeof(float2) * _q->H);
+        lc::pfb::launch_pfbch2_small_synth(_q->d_hist, (int)(_q->H / _q->M), (const float2 *)_d_x, _q->d_taps, (float2 *)_d_y,
+                                           d_new, _q->M, 2 * _q->L, _n_frames, _q->flag, st);
+        LC_CUDA_CHECK(cudaMemcpyAsync(_q->d_hist, d_new, sizeof(float2) * _q->H, cudaMemcpyDeviceToDevice, st));
     } else if (_q->tiled && _n_frames >= 2 * _q->L && !getenv("LIQUID_CUDA_NO_FUSED")) {
         // fused synthesizer: the rows of v stay on the chip, the kernel leaves the last 4m of them as the new state
         float2 *d_new = (float2 *)_q->hist_tmp.get(sizeof(float2) * _q->H);

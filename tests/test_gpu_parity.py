@@ -643,6 +643,55 @@ def test_pfbch2_tile_synthesizer_vs_oracle_odd_splits_and_generic(L, orc, monkey
     assert np.abs(hist - hist3).max() / max(np.abs(hist).max(), 1e-30) < 2e-6
 
 
+# ------------------------------------------------------------------ the smallest shapes, M = 4 ... 32 (pfbch2_small.cu)
+@pytest.mark.parametrize("M,m", [(4, 2), (4, 5), (8, 2), (8, 4), (16, 2), (16, 5), (32, 2), (32, 4)])
+def test_pfbch2_small_analyzer_vs_oracle_odd_splits_and_generic(L, orc, monkeypatch, M, m):
+    """the low end of the reference's benchmark shapes (firpfbch2_crcf_benchmark.c:70-71: M = 4, 16): several instances
+    per warp, odd start parity, ragged tiles, state carried, single-frame execute calls; against the oracle and the
+    shape-generic path"""
+    nfr = 33 + 200 + 5000 + 3
+    x = orc.synth_input(nfr * M // 2, seed=0x41 + M + m)
+    want = orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0).execute_frames(x)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+    cuts = [0, 33, 233, 5233, 5234, nfr]
+    got = np.concatenate([q.execute_block(x[a * M // 2:b * M // 2]) for a, b in zip(cuts[:-1], cuts[1:])])
+    check_channels(got, want, x)
+    q.reset()
+    whole = q.execute_block(x)
+    assert np.array_equal(whole.view(np.uint32), got.view(np.uint32))          # independent of the block cut
+    monkeypatch.setenv("LIQUID_CUDA_NO_FUSED", "1")
+    q.reset()
+    generic = q.execute_block(x)
+    monkeypatch.delenv("LIQUID_CUDA_NO_FUSED")
+    assert np.abs(whole - generic).max() < 1e-6
+
+
+@pytest.mark.parametrize("M,m", [(4, 2), (4, 4), (8, 2), (16, 2), (16, 4), (32, 2), (32, 4)])
+def test_pfbch2_small_synthesizer_vs_oracle_odd_splits_and_generic(L, orc, monkeypatch, M, m):
+    """synthesizer at M = 4 ... 32 (firpfbch2_crcf_benchmark.c:84-85): warm-up tiles, ragged tiles, odd parity, state handed
+    between the fused kernel and the two-kernel path"""
+    nfr = 65 + 5 + 200 + 5000
+    X = orc.synth_input(nfr * M, seed=0x51 + M + m)
+    want = orc.Firpfbch2(orc.SYNTHESIZER, M, m, As=60.0).execute_frames(X)
+    scale = np.abs(want).max()
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+    cuts = [0, 65, 70, 270, nfr]                      # 5 frames: below 4m (two-kernel path in between)
+    got = np.concatenate([q.execute_block(X[a * M:b * M]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert np.abs(got - want).max() / scale < 1e-5
+    hist, flag = q.get_state()
+    q.reset()
+    whole = q.execute_block(X)
+    assert np.abs(whole - want).max() / scale < 1e-5
+    assert np.abs(whole - got).max() / scale < 2e-6
+    monkeypatch.setenv("LIQUID_CUDA_NO_FUSED", "1")
+    q.reset()
+    generic = q.execute_block(X)
+    hist3, flag3 = q.get_state()
+    monkeypatch.delenv("LIQUID_CUDA_NO_FUSED")
+    assert np.abs(whole - generic).max() / scale < 2e-6
+    assert flag == flag3 and np.abs(hist - hist3).max() / max(np.abs(hist).max(), 1e-30) < 2e-6
+
+
 # ------------------------------------------------------------------ root-Nyquist Kaiser prototypes (SURVEY 8f item 1)
 def test_pfbch_rnyquist_kaiser_prototypes_vs_reference(L, orc, refrn):
     """firpfbch_crcf_create_rnyquist with ARKAISER / RKAISER against the compiled reference's outputs and
