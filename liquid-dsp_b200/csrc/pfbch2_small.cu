@@ -331,6 +331,150 @@ __global__ void __launch_bounds__(kThreads) pfbch2_frame_synth_kernel(const Smal
     }
 }
 
+// ---------------------------------------------------------------------------------- firpfbch (critically sampled), M = 4 / 8 / 32
+// firpfbch.c:369-409: X_s[u] = sum_n h[(M-1-u) + nM] x[(s-n)M + u], Y_s = forward DFT.  (M = 16 has its own kernel in
+// pfbch_fused.cu.)  M = 8 / 32: an instance of M lanes, thread u owns window u, whole-frame register DFTs, as above;
+// M = 4: one thread per frame.  grid.y = stream.
+struct PfbSmallArgs {
+    const float2 *hist;
+    const float2 *x;
+    float2 *y;
+    const float *taps;         // [P][M]: taps[n][i] = h[i + nM]
+    long long n_frames;
+    long long stream_stride;
+    int H;
+    int n_tiles;
+    int tiles_per_inst;
+};
+
+template <int M>
+__device__ __forceinline__ void transform_row_fwd(float2 *row)
+{
+    float2 v[M];
+    const float4 *r4 = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+    for (int i = 0; i < M / 2; i++) {
+        const float4 t = r4[i];
+        v[2 * i] = make_float2(t.x, t.y);
+        v[2 * i + 1] = make_float2(t.z, t.w);
+    }
+    RegDft<M, -1>::run(v);
+    float4 *w4 = reinterpret_cast<float4 *>(row);
+#pragma unroll
+    for (int i = 0; i < M / 2; i++) w4[i] = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
+}
+
+template <int M, int P>
+__global__ void __launch_bounds__(kThreads) pfbch_small_kernel(const PfbSmallArgs a)
+{
+    constexpr int PITCH = kPitch<M>, INST = kThreads / M, HL = P - 1;
+    extern __shared__ __align__(16) float2 tiles[];              // [INST][kFr][PITCH]
+    const int inst_l = threadIdx.x / M, u = threadIdx.x % M;
+    float2 *tile = tiles + inst_l * (kFr * PITCH);
+    const long long inst = (long long)blockIdx.x * INST + inst_l;
+    const long long t0 = inst * a.tiles_per_inst;
+    long long ntl = (long long)a.n_tiles - t0;
+    if (ntl > a.tiles_per_inst) ntl = a.tiles_per_inst;
+    const int nt = ntl > 0 ? (int)ntl : 0;
+    if (nt == 0) return;
+    const unsigned int imask = (M == 32) ? 0xffffffffu : (((1u << M) - 1u) << ((threadIdx.x & 31) / M * M));
+    const float2 *x = a.x + (long long)blockIdx.y * a.stream_stride;
+    float2 *y = a.y + (long long)blockIdx.y * a.stream_stride;
+
+    float h[P];
+#pragma unroll
+    for (int n = 0; n < P; n++) h[n] = __ldg(a.taps + n * M + (M - 1 - u));   // branch M-1-u feeds input u
+    float2 win[HL + kFr], nx[kFr];
+    auto fetch = [&](int it) {
+        const long long f0 = (t0 + it) * kFr;
+#pragma unroll
+        for (int f = 0; f < kFr; f++) nx[f] = (it < nt && f0 + f < a.n_frames) ? __ldg(x + (f0 + f) * M + u) : make_float2(0.f, 0.f);
+    };
+    fetch(0);
+    {
+        const long long f0 = t0 * kFr;
+#pragma unroll
+        for (int i = 0; i < HL; i++) win[i] = ld_hist0(a.hist, x, (f0 - HL + i) * M + u, a.H);
+    }
+    for (int it = 0; it < nt; it++) {
+        const long long f0 = (t0 + it) * kFr;
+#pragma unroll
+        for (int f = 0; f < kFr; f++) win[HL + f] = nx[f];
+        fetch(it + 1);
+#pragma unroll
+        for (int f = 0; f < kFr; f++) {
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int n = P - 1; n >= 0; n--) acc = __ffma2_rn(bc(h[n]), win[HL + f - n], acc);
+            tile[f * PITCH + u] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < HL; i++) win[i] = win[kFr + i];
+        __syncwarp(imask);
+        if (M <= kFr) {
+#pragma unroll
+            for (int i = 0; i < (kFr / M > 0 ? kFr / M : 1); i++) transform_row_fwd<M>(tile + (u + M * i) * PITCH);
+        } else if (u < kFr) {
+            transform_row_fwd<M>(tile + u * PITCH);
+        }
+        __syncwarp(imask);
+        // the tile is 16 M contiguous outputs = 8 M float4: float4 w = i M + u is row 2i + 2u / M, columns 2u % M, + 1
+        float4 *yt = reinterpret_cast<float4 *>(y + f0 * M);
+#pragma unroll
+        for (int i = 0; i < kFr / 2; i++) {
+            const int r = 2 * i + (2 * u) / M, c = (2 * u) % M;
+            if (f0 + r < a.n_frames) __stcs(yt + i * M + u, *reinterpret_cast<const float4 *>(tile + r * PITCH + c));
+        }
+        __syncwarp(imask);
+    }
+}
+
+// M = 4: one thread per frame (frame = 32 bytes in, 32 bytes out), the P frames its windows span re-read through L1
+template <int P>
+__global__ void __launch_bounds__(kThreads) pfbch_frame4_kernel(const PfbSmallArgs a)
+{
+    constexpr int M = 4;
+    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= a.n_frames) return;
+    const float2 *x = a.x + (long long)blockIdx.y * a.stream_stride;
+    float2 *y = a.y + (long long)blockIdx.y * a.stream_stride;
+    float2 X[M];
+#pragma unroll
+    for (int u = 0; u < M; u++) X[u] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int n = P - 1; n >= 0; n--) {
+        const long long f = t - n;
+        float2 s[M];
+        if (f >= 0) {
+            const float4 *p = reinterpret_cast<const float4 *>(x + f * M);
+            const float4 q0 = __ldg(p), q1 = __ldg(p + 1);
+            s[0] = make_float2(q0.x, q0.y);
+            s[1] = make_float2(q0.z, q0.w);
+            s[2] = make_float2(q1.x, q1.y);
+            s[3] = make_float2(q1.z, q1.w);
+        } else {
+#pragma unroll
+            for (int u = 0; u < M; u++) s[u] = ld_hist0(a.hist, x, f * M + u, a.H);
+        }
+#pragma unroll
+        for (int u = 0; u < M; u++) X[u] = __ffma2_rn(bc(__ldg(a.taps + n * M + (M - 1 - u))), s[u], X[u]);
+    }
+    RegDft<M, -1>::run(X);
+    float4 *yo = reinterpret_cast<float4 *>(y + t * M);
+    __stcs(yo, make_float4(X[0].x, X[0].y, X[1].x, X[1].y));
+    __stcs(yo + 1, make_float4(X[2].x, X[2].y, X[3].x, X[3].y));
+}
+
+template <int M, int P>
+void launch_pfb_small_MP(const PfbSmallArgs &a, dim3 grid, cudaStream_t st)
+{
+    constexpr size_t smem = sizeof(float2) * (size_t)(kThreads / M) * kFr * kPitch<M>;
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch_small_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pfbch_small_kernel<M, P><<<grid, kThreads, smem, st>>>(a);
+}
+
 // grid: enough instances to fill the GPU, at most 64 tiles (1024 frames) each
 void plan(SmallArgs &a, unsigned int M, long long n_frames, unsigned int &grid, long long min_tpi)
 {
@@ -399,6 +543,53 @@ namespace pfb {
 bool small_pfbch2_supported(unsigned int M, unsigned int L)
 {
     return (M == 4 || M == 8 || M == 16 || M == 32) && (L == 4 || L == 8 || L == 10);
+}
+
+bool small_pfbch_supported(unsigned int M, unsigned int p)
+{
+    return (M == 4 || M == 8 || M == 32) && (p == 4 || p == 8 || p == 10);
+}
+
+long long launch_pfbch_small(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, float2 *d_y, unsigned int M,
+                             unsigned int p, unsigned long long n_frames, unsigned int n_streams, long long stream_stride,
+                             cudaStream_t st)
+{
+    if (n_frames == 0 || n_frames > (1ull << 34) || n_streams == 0 || n_streams > 65535) return 0;
+    PfbSmallArgs a = {};
+    a.hist = d_hist;
+    a.x = d_x;
+    a.y = d_y;
+    a.taps = d_taps;
+    a.H = H;
+    a.n_frames = (long long)n_frames;
+    a.stream_stride = stream_stride;
+    if (M == 4) {
+        dim3 g((unsigned int)((n_frames + kThreads - 1) / kThreads), n_streams, 1);
+        if (p == 4) pfbch_frame4_kernel<4><<<g, kThreads, 0, st>>>(a);
+        else if (p == 8) pfbch_frame4_kernel<8><<<g, kThreads, 0, st>>>(a);
+        else pfbch_frame4_kernel<10><<<g, kThreads, 0, st>>>(a);
+        LC_LAUNCH_CHECK();
+        return (long long)n_frames;
+    }
+    const long long n_tiles = ((long long)n_frames + kFr - 1) / kFr;
+    const long long inst_per_cta = kThreads / M;
+    long long tpi = 64;
+    while (tpi > 1 && (n_tiles / tpi) * n_streams < 148ll * 4 * inst_per_cta) tpi >>= 1;
+    a.n_tiles = (int)n_tiles;
+    a.tiles_per_inst = (int)tpi;
+    const long long n_inst = (n_tiles + tpi - 1) / tpi;
+    dim3 grid((unsigned int)((n_inst + inst_per_cta - 1) / inst_per_cta), n_streams, 1);
+#define LC_PFB(MM, PP) launch_pfb_small_MP<MM, PP>(a, grid, st)
+    if (M == 8 && p == 4) LC_PFB(8, 4);
+    else if (M == 8 && p == 8) LC_PFB(8, 8);
+    else if (M == 8 && p == 10) LC_PFB(8, 10);
+    else if (M == 32 && p == 4) LC_PFB(32, 4);
+    else if (M == 32 && p == 8) LC_PFB(32, 8);
+    else if (M == 32 && p == 10) LC_PFB(32, 10);
+    else fatal("launch_pfbch_small", "unsupported shape");
+#undef LC_PFB
+    LC_LAUNCH_CHECK();
+    return (long long)n_frames;
 }
 
 bool small_pfbch2_synth_supported(unsigned int M, unsigned int n_taps)

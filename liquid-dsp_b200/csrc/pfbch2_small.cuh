@@ -18,5 +18,12 @@ long long launch_pfbch2_small_synth(const float2 *d_hist_rows, int hist_rows, co
                                     float2 *d_y, float2 *d_hist_out, unsigned int M, unsigned int n_taps,
                                     unsigned long long n_frames, int parity0, cudaStream_t st);
 
+// firpfbch (critically sampled) analyzer, M = 4 / 8 / 32, p = 2m in {4, 8, 10}: same contract as launch_pfbch_fused
+// (pfbch_fused.cuh), every frame covered.  d_x and d_y must be 16-byte aligned.
+bool small_pfbch_supported(unsigned int M, unsigned int p);
+long long launch_pfbch_small(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, float2 *d_y, unsigned int M,
+                             unsigned int p, unsigned long long n_frames, unsigned int n_streams, long long stream_stride,
+                             cudaStream_t st);
+
 }  // namespace pfb
 }  // namespace lc

@@ -20,6 +20,7 @@
 //   X_s[u] = sum_n h[(M-1-u) + nM] x[(s-n)M + u],   Y_s = DFT_forward_unscaled(X_s).
 #include "pfbch_fused.cuh"
 #include "pfbch2_tile.cuh"
+#include "pfbch2_small.cuh"
 #include "fused_common.cuh"
 
 #include <cmath>
@@ -587,7 +588,7 @@ namespace pfb {
 
 bool fused_pfbch_supported(unsigned int M, unsigned int p)
 {
-    return (M == 16 && (p == 4 || p == 8)) || (M == 256 && (p == 4 || p == 10)) || tile_pfbch_supported(M, p) ||
+    return (M == 16 && (p == 4 || p == 8)) || (M == 256 && (p == 4 || p == 10)) || tile_pfbch_supported(M, p) || small_pfbch_supported(M, p) ||
            (M == 1024 && (p == 4 || p == 8 || p == 10));
 }
 
@@ -598,6 +599,10 @@ bool fused_pfbch_synth_supported(unsigned int M, unsigned int p)
 
 void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign, unsigned int M, unsigned int p)
 {
+    if (sign < 0 && small_pfbch_supported(M, p)) {
+        tw.assign(1, make_float2(1.f, 0.f));                  // these kernels need no table
+        return;
+    }
     if (sign < 0 && tile_pfbch_supported(M, p)) {
         tile_pfbch_make_twiddles(tw, M);                      // analyzers for M = 64 / 128 / 512 (pfbch2_tile.cu)
         return;
@@ -631,6 +636,8 @@ long long launch_pfbch_fused(const float2 *d_hist, const float2 *d_x, int H, con
 {
     if (tile_pfbch_supported(M, p))
         return launch_pfbch_tile(d_hist, d_x, H, d_taps, d_tw, d_y, M, p, n_frames, n_streams, stream_stride, st);
+    if (small_pfbch_supported(M, p))
+        return launch_pfbch_small(d_hist, d_x, H, d_taps, d_y, M, p, n_frames, n_streams, stream_stride, st);
     if (M == 1024) {
         const long long nq = (long long)((n_frames + kQFr - 1) / kQFr);
         if (nq == 0 || nq > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;

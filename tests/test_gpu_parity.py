@@ -1162,7 +1162,8 @@ def test_pfbch2_cluster_matches_generic_path(L, orc, monkeypatch):
 @pytest.mark.parametrize("M,m,nfr", [(16, 4, 16 * 37 + 5), (16, 2, 16 * 300), (256, 5, 16 * 21 + 3), (256, 2, 16 * 40),
                                      (64, 2, 1500), (64, 5, 8 * 77 + 3), (128, 4, 8 * 90 + 1), (128, 2, 1111),
                                      (512, 2, 8 * 61 + 5), (512, 5, 8 * 40 + 7), (512, 4, 333),
-                                     (1024, 2, 4 * 177 + 3), (1024, 5, 4 * 50 + 1), (1024, 4, 301)])
+                                     (1024, 2, 4 * 177 + 3), (1024, 5, 4 * 50 + 1), (1024, 4, 301),
+                                     (4, 2, 5003), (4, 5, 777), (8, 2, 3001), (8, 4, 16 * 40 + 9), (32, 2, 2000), (32, 5, 16 * 33 + 5)])
 def test_pfbch_fused_analysis_vs_oracle_and_generic(L, orc, monkeypatch, M, m, nfr):
     """fused M=16 / M=256 analyzers and the tile analyzers for M = 64 / 128 / 512 / 1024 (the reference's own benchmark shapes,
     firpfbch_crcf_benchmark.c:80-85): many tiles and instances, a tail that is not a multiple of the
@@ -1181,7 +1182,7 @@ def test_pfbch_fused_analysis_vs_oracle_and_generic(L, orc, monkeypatch, M, m, n
     assert np.abs(got - generic).max() / np.abs(want).max() < 2e-6
 
 
-@pytest.mark.parametrize("M,m", [(16, 4), (256, 5), (64, 3), (64, 2), (512, 5), (128, 4), (1024, 2)])
+@pytest.mark.parametrize("M,m", [(16, 4), (256, 5), (64, 3), (64, 2), (512, 5), (128, 4), (1024, 2), (4, 2), (8, 4), (32, 2)])
 def test_pfbch_streams_dev(L, orc, M, m):
     """stateless multi-stream analyzer form (BASELINE config 4 shape): every stream from the reset state"""
     import ctypes as C
