@@ -614,6 +614,19 @@ def main():
             except Exception as e:          # noqa: BLE001
                 other[cfg] = {"error": str(e)}
             torch.cuda.empty_cache()
+        # the reference's own benchmark list (firpfbch2_crcf_benchmark.c / firpfbch_crcf_benchmark.c: M = 4 ... 1024, m = 2)
+        shapes = {}
+        try:
+            bench_configs.run(["rb"], args.other_steps, 2,
+                              lambda line: shapes.__setitem__(line["config"][4:], {"GSps": round(line["value"] / 1e3, 1),
+                                                                                   "roofline_frac": round(line["roofline"]["frac"], 3)}),
+                              device_index=local_rank)
+        except Exception as e:              # noqa: BLE001
+            shapes["error"] = str(e)
+        other["reference_benchmark_shapes"] = {"note": "2^27 samples per shape, one stateful stream, same timing code as the configs above; "
+                                                       "24 B per sample (firpfbch2) / 16 B per sample (firpfbch) against the measured HBM peak",
+                                               "shapes": shapes}
+        torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

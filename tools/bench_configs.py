@@ -7,6 +7,8 @@ events, inputs larger than L2.  Not the driver's headline bench (that is bench.p
 
   c1 c2 c4 c5   BASELINE configs 1, 2, 4, 5 (c3 is bench.py)          c3m c5m  c3 / c5 against the filter length m
   g             shape-generic one-kernel analyzers (M = 256, 64, 2048)  s        synthesizers (firpfbch2 M=1024, firpfbch M=1024 / 256)
+  rb            the reference's own benchmark shapes (M = 4 ... 1024, m = 2), firpfbch2 analysis / synthesis, firpfbch analysis
+  sm            the smallest shapes, M = 4 ... 32
   t ts tp       firpfbch2 tile kernels (analysis / synthesis), M = 64 ... 512; firpfbch analysis M = 64 ... 1024
   fft           fft_execute_batch_dev, n = 16 / 256 / 1024 / 4096       d        dotprod_crcf batch entry point
   p             firpfb_crcf block form
@@ -190,6 +192,28 @@ def run(configs, steps, warmup, sink, device_index=0):
             ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
             report("t: firpfbch2_crcf analysis M=%d m=%d (tile kernel), 2^28 samples" % (M, m), n, 24, ms, ln)
             del x, y
+    if "rb" in args.configs:
+        # the reference's own benchmark list, shape by shape (src/multichannel/bench/firpfbch2_crcf_benchmark.c:70-90 analysis and
+        # synthesis, firpfbch_crcf_benchmark.c:80-85 analysis; M = 4 ... 1024, m = 2), 2^27 samples each, one stateful stream
+        for kind in ("firpfbch2 analysis", "firpfbch2 synthesis", "firpfbch analysis"):
+            for M in (4, 16, 64, 256, 512, 1024):
+                m, n = 2, 1 << 27
+                if kind == "firpfbch2 analysis":
+                    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+                    n_in, n_out, nfr, bps = n, 2 * n, n // (M // 2), 24
+                elif kind == "firpfbch2 synthesis":
+                    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+                    n_in, n_out, nfr, bps = 2 * n, n, n // (M // 2), 24
+                else:
+                    q = L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+                    n_in, n_out, nfr, bps = n, n, n // M, 16
+                x = torch.empty(2 * n_in, dtype=torch.float32, device=dev)
+                y = torch.empty(2 * n_out, dtype=torch.float32, device=dev)
+                L.synth_input_dev(x.data_ptr(), n_in, stream=st.cuda_stream)
+                ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), nfr, y.data_ptr(), st.cuda_stream))
+                report("rb: %s M=%d m=2" % (kind, M), n, bps, ms, ln)
+                q.destroy()
+                del x, y
     if "sm" in args.configs:
         # the smallest shapes of the reference's benchmarks (firpfbch2_crcf_benchmark.c:70-90, firpfbch_crcf_benchmark.c:80-81), m = 2
         for kind, M in (("a2", 4), ("a2", 8), ("a2", 16), ("a2", 32), ("s2", 4), ("s2", 16), ("s2", 32), ("a1", 4), ("a1", 8), ("a1", 32)):
