@@ -211,7 +211,26 @@ firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restric
         const unsigned int stream = tile_id / tiles_per_stream;
         const long long o0 = (long long)(tile_id - stream * tiles_per_stream) * kWarpTile + (long long)lane * RO;
         float2 *yo = y + stream * (unsigned long long)n + o0;
-        if (o0 + RO <= n) {
+        const long long t_first = o0 - (long long)lane * RO;     // first output of the warp tile
+        if (t_first + kWarpTile <= n) {
+            // whole tile inside the stream: the lanes' 128-byte runs go through the (consumed) sample buffer so that every
+            // store instruction writes 512 contiguous bytes (see firfilt_ffa_kernel)
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < RO; r++)
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xb + (unsigned int)(r * ROW) * 8), "f"(acc[r].x), "f"(acc[r].y) : "memory");
+            __syncwarp();
+            float4 *yt = reinterpret_cast<float4 *>(y + stream * (unsigned long long)n + t_first);
+            const unsigned int xw = xs_warp + buf;
+#pragma unroll
+            for (int i = 0; i < kWarpTile / 64; i++) {
+                const int q = 64 * i + 2 * lane;
+                float2 a0, a1;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a0.x), "=f"(a0.y) : "r"(xw + (unsigned int)((q % RO) * ROW + q / RO) * 8));
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a1.x), "=f"(a1.y) : "r"(xw + (unsigned int)(((q + 1) % RO) * ROW + (q + 1) / RO) * 8));
+                __stcs(yt + 32 * i + lane, make_float4(a0.x, a0.y, a1.x, a1.y));
+            }
+        } else if (o0 + RO <= n) {
 #pragma unroll
             for (int r = 0; r < RO; r += 2)
                 __stcs(reinterpret_cast<float4 *>(yo + r), make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y));
@@ -219,6 +238,211 @@ firfilt_regblock_kernel(const float2 *__restrict__ hist, const float2 *__restric
 #pragma unroll
             for (int r = 0; r < RO; r++)
                 if (o0 + r < n) yo[r] = acc[r];
+        }
+        tile_id = upcoming;
+        buf ^= C::kBufBytes;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-parallel fast-FIR form of the kernel above for NT = 64 (BASELINE config 2), which is FP32-pipe bound: with
+// x0[k] = x[2k], x1[k] = x[2k+1], H0[i] = h[2i], H1[i] = h[2i+1] (32 taps each),
+//     A = H0 * x0,   B = H1 * x1,   C = (H0 + H1) * (x0 + x1)      (three 32-tap convolutions per output PAIR)
+//     y[2k] = A[k] + B[k-1],        y[2k+1] = C[k] - A[k] - B[k]
+// which is 800 packed FFMA2 + 55 packed adds per 16 outputs instead of 1024 FFMA2.  A lane still owns 16 consecutive
+// outputs (8 pairs) of a warp tile and the same staged samples; the three tap sets sit in shared memory and pass
+// through a short register window (a sample meets 8 - 9 consecutive taps, one new tap per sample: LDS.32 broadcast), so
+// the taps need a dozen registers instead of 64.  Accumulator plan (17 pairs live at most):
+// b[0..8] = B[k-1 .. k+7]; y0[p] starts as B[p-1] and takes A[p]; t[p] starts as B[p-1] - B[p] and takes C[p];
+// y1[p] = t[p] - y0[p].  The sums H0 + H1 and x0 + x1 are rounded once more than the direct form (errors of a few 1e-7
+// of the output scale: inside the parity tolerance, tested against the oracle and the direct kernel).
+template <int NT>
+__global__ void __launch_bounds__(kRbThreads, 2)
+firfilt_ffa_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
+                   const float *__restrict__ taps, unsigned int n_taps, float scale,
+                   float2 *__restrict__ y, unsigned long long n_, unsigned int tiles_per_stream_,
+                   unsigned int n_tiles_, unsigned int *__restrict__ tile_counter)
+{
+    constexpr int RO = 16, HT = NT / 2, NP = RO / 2;            // HT taps per sub-filter, NP output pairs per lane
+    using C = RbCfg<NT, RO>;
+    constexpr int ROW = C::ROW, NS = C::NS, NPASS = C::NPASS, kWarpTile = C::kWarpTile;
+    extern __shared__ float2 xs_dyn[];          // per warp: 2 buffers of RO * ROW samples; then the three tap sets
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int xs_warp = (unsigned int)__cvta_generic_to_shared(xs_dyn) + (unsigned int)warp * (2 * C::kBufBytes);
+    float *tap_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(xs_dyn) + C::kSmem);   // [3][HT]: H0, H1, H0 + H1
+    const unsigned int tap_u32 = (unsigned int)__cvta_generic_to_shared(tap_s);
+    const unsigned int fill_thr = xs_warp + (unsigned int)((lane % RO) * ROW + lane / RO) * 8;
+    const unsigned int read_thr = xs_warp + (unsigned int)lane * 8;
+    long long n = (long long)n_;
+    unsigned int tiles_per_stream = tiles_per_stream_, n_tiles = n_tiles_;
+    asm volatile("" : "+l"(n), "+r"(tiles_per_stream), "+r"(n_tiles));
+    const unsigned int stride = gridDim.x * kRbWarps;
+
+    for (int i = threadIdx.x; i < HT; i += kRbThreads) {
+        const float h0 = (2 * i < (int)n_taps) ? __ldg(taps + 2 * i) * scale : 0.0f;
+        const float h1 = (2 * i + 1 < (int)n_taps) ? __ldg(taps + 2 * i + 1) * scale : 0.0f;
+        tap_s[i] = h0;
+        tap_s[HT + i] = h1;
+        tap_s[2 * HT + i] = h0 + h1;
+    }
+    __syncthreads();
+
+    auto prefetch = [&](unsigned int tile_id, unsigned int dst) {
+        const unsigned int stream = tile_id / tiles_per_stream;
+        const long long first = (long long)(tile_id - stream * tiles_per_stream) * kWarpTile - (long long)(NT - 1);
+        const float2 *xstr = x + stream * (unsigned long long)n;
+        if (first >= 0 && first + NS <= n) {
+            const float2 *src = xstr + first + lane;
+#pragma unroll
+            for (int i = 0; i < NPASS; i++)
+                if (i < NPASS - 1 || lane + i * 32 < NS)
+                    cp_async8_plain(dst + (unsigned int)(i * (32 / RO)) * 8, src + i * 32);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < NPASS; i++) {
+                const int q = lane + i * 32;
+                if (q < NS) {
+                    const long long idx = first + q;
+                    const float2 *src = xstr;
+                    bool valid = false;
+                    if (idx >= 0 && idx < n) { src = xstr + idx; valid = true; }
+                    else if (idx < 0 && hist != nullptr && H + idx >= 0) { src = hist + (H + idx); valid = true; }
+                    cp_async8_zfill(dst + (unsigned int)(i * (32 / RO)) * 8, src, valid);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto next_tile = [&](unsigned int current) -> unsigned int {
+        if (tile_counter == nullptr) return current + stride;
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    // tile-relative sample d of this lane (d = 0 .. NT + RO - 2) is stream sample o0 - (NT-1) + d
+    auto sample = [&](unsigned int xb, int d) -> float2 {
+        float2 sv;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sv.x), "=f"(sv.y) : "r"(xb + (unsigned int)((d % RO) * ROW + d / RO) * 8));
+        return sv;
+    };
+    auto tap = [&](int set, int i) -> float {
+        float t;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(tap_u32 + (unsigned int)(set * HT + i) * 4));
+        return t;
+    };
+
+    unsigned int tile_id = (tile_counter == nullptr) ? blockIdx.x * kRbWarps + warp : next_tile(0);
+    unsigned int buf = 0;
+    if (tile_id < n_tiles) prefetch(tile_id, fill_thr);
+    while (tile_id < n_tiles) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const unsigned int upcoming = next_tile(tile_id);
+        if (upcoming < n_tiles) prefetch(upcoming, fill_thr + (buf ^ C::kBufBytes));
+        const unsigned int xb = read_thr + buf;
+
+        // With K0 the pair index of the lane's first output: x1 sample e (e = 0 .. HT+NP-1) = x1[K0 - HT + e] is tile sample
+        // d = 2e, x0 sample e (e = 0 .. HT+NP-2) = x0[K0 - HT + 1 + e] is tile sample d = 2e + 1.
+        // ---- B[j], j = -1 .. NP-1 (b[j + 1]):  B[K0 + j] = sum_i H1[i] x1[K0 + j - i], i.e. x1 sample e meets tap i = HT + j - e
+        float2 b[NP + 1];
+#pragma unroll
+        for (int j = 0; j <= NP; j++) b[j] = make_float2(0.f, 0.f);
+        {
+            // samples and taps are loaded kAhead steps before they are used (everything is unrolled, so the small
+            // rings below are plain registers): the FFMA2 bursts of a step never wait for their own loads
+            constexpr int kAhead = 4, NE = HT + NP;
+            float h1w[HT + NP + 1];                              // h1w[i + NP] = H1[i]: only a window of NP + 1 + kAhead is live
+            float2 sv[NE];
+#pragma unroll
+            for (int e = 0; e < kAhead; e++) {
+                sv[e] = sample(xb, 2 * e);
+                if (HT - 1 - e >= 0) h1w[HT - 1 - e + NP] = tap(1, HT - 1 - e);
+            }
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                if (e + kAhead < NE) {
+                    sv[e + kAhead] = sample(xb, 2 * (e + kAhead));
+                    // the tap that enters the window at sample e': i = HT - 1 - e' (meets j = -1)
+                    if (HT - 1 - (e + kAhead) >= 0) h1w[HT - 1 - (e + kAhead) + NP] = tap(1, HT - 1 - (e + kAhead));
+                }
+#pragma unroll
+                for (int j = -1; j < NP; j++) {
+                    const int i = HT + j - e;
+                    if (i >= 0 && i < HT) b[j + 1] = __ffma2_rn(make_float2(h1w[i + NP], h1w[i + NP]), sv[e], b[j + 1]);
+                }
+            }
+        }
+        float2 y0[NP], t[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            y0[p] = b[p];                                        // B[p - 1]
+            t[p] = __fadd2_rn(b[p], make_float2(-b[p + 1].x, -b[p + 1].y));
+        }
+        // ---- A[p] into y0[p], C[p] into t[p]: x0 sample e meets tap i = HT - 1 + p - e of H0 (and of H0 + H1, with x0 + x1)
+        {
+            constexpr int kAhead = 3, NE = HT + NP - 1;
+            float h0w[HT + NP], hsw[HT + NP];
+            float2 s0[NE], ss[NE];
+            auto load_step = [&](int e) {
+                s0[e] = sample(xb, 2 * e + 1);
+                ss[e] = sample(xb, 2 * e + 2);                   // x1[K0 - HT + 1 + e]: the partner of this x0 sample
+                if (HT - 1 - e >= 0) {
+                    h0w[HT - 1 - e + NP] = tap(0, HT - 1 - e);
+                    hsw[HT - 1 - e + NP] = tap(2, HT - 1 - e);
+                }
+            };
+#pragma unroll
+            for (int e = 0; e < kAhead; e++) load_step(e);
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                if (e + kAhead < NE) load_step(e + kAhead);
+                const float2 sum = __fadd2_rn(s0[e], ss[e]);
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    const int i = HT - 1 + p - e;
+                    if (i >= 0 && i < HT) {
+                        y0[p] = __ffma2_rn(make_float2(h0w[i + NP], h0w[i + NP]), s0[e], y0[p]);
+                        t[p] = __ffma2_rn(make_float2(hsw[i + NP], hsw[i + NP]), sum, t[p]);
+                    }
+                }
+            }
+        }
+        const unsigned int stream = tile_id / tiles_per_stream;
+        const long long o0 = (long long)(tile_id - stream * tiles_per_stream) * kWarpTile + (long long)lane * RO;
+        float2 *yo = y + stream * (unsigned long long)n + o0;
+        const long long t_first = o0 - (long long)lane * RO;     // first output of the warp tile
+        if (t_first + kWarpTile <= n) {
+            // Whole tile inside the stream: the lanes' 128-byte runs go through the (consumed) sample buffer so that every
+            // store instruction writes 512 contiguous bytes.  Stored straight from the registers, one instruction touched 32
+            // different lines (16 bytes each, 128 bytes apart), and that -- not the FFMA2 count -- bounded the kernel:
+            // the direct and the fast-FIR form both took 5.4 ms per 2^30 samples.
+            __syncwarp();                                        // every lane has read its last sample
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const float2 y1 = __fadd2_rn(t[p], make_float2(-y0[p].x, -y0[p].y));
+                // output q = lane RO + r sits at slot (q % RO) ROW + q / RO, as the samples did
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xb + (unsigned int)((2 * p) * ROW) * 8), "f"(y0[p].x), "f"(y0[p].y) : "memory");
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xb + (unsigned int)((2 * p + 1) * ROW) * 8), "f"(y1.x), "f"(y1.y) : "memory");
+            }
+            __syncwarp();
+            float4 *yt = reinterpret_cast<float4 *>(y + stream * (unsigned long long)n + t_first);
+            const unsigned int xw = xs_warp + buf;
+#pragma unroll
+            for (int i = 0; i < kWarpTile / 64; i++) {
+                // outputs q = 64 i + 2 lane, + 1
+                const int q = 64 * i + 2 * lane;
+                float2 a0, a1;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a0.x), "=f"(a0.y) : "r"(xw + (unsigned int)((q % RO) * ROW + q / RO) * 8));
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a1.x), "=f"(a1.y) : "r"(xw + (unsigned int)(((q + 1) % RO) * ROW + (q + 1) / RO) * 8));
+                __stcs(yt + 32 * i + lane, make_float4(a0.x, a0.y, a1.x, a1.y));
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const float2 y1 = __fadd2_rn(t[p], make_float2(-y0[p].x, -y0[p].y));
+                if (o0 + 2 * p < n) yo[2 * p] = y0[p];
+                if (o0 + 2 * p + 1 < n) yo[2 * p + 1] = y1;
+            }
         }
         tile_id = upcoming;
         buf ^= C::kBufBytes;
@@ -339,7 +563,21 @@ void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps,
         };
         if (n_taps <= 16) run(firfilt_regblock_kernel<16, 16>, RbCfg<16, 16>{});
         else if (n_taps <= 32) run(firfilt_regblock_kernel<32, 16>, RbCfg<32, 16>{});
-        else run(firfilt_regblock_kernel<64, 16>, RbCfg<64, 16>{});
+        else if (getenv("LIQUID_CUDA_FIRFILT_DIRECT")) run(firfilt_regblock_kernel<64, 16>, RbCfg<64, 16>{});
+        else {
+            // 2-parallel fast-FIR form, the tap sets behind the sample buffers
+            using C = RbCfg<64, 16>;
+            constexpr size_t smem = C::kSmem + 3 * 32 * sizeof(float);
+            const unsigned long long tiles_rb = (n + C::kWarpTile - 1) / C::kWarpTile;
+            const unsigned long long total_rb = tiles_rb * n_streams;
+            unsigned long long grid = (unsigned long long)sms * 2;
+            const unsigned long long need = (total_rb + kRbWarps - 1) / kRbWarps;
+            if (grid > need) grid = need;
+            LC_CUDA_CHECK(cudaFuncSetAttribute(firfilt_ffa_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (d_tile_counter) LC_CUDA_CHECK(cudaMemsetAsync(d_tile_counter, 0, sizeof(unsigned int), st));
+            firfilt_ffa_kernel<64><<<(unsigned int)grid, kRbThreads, smem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n,
+                                                                                (unsigned int)tiles_rb, (unsigned int)total_rb, d_tile_counter);
+        }
         LC_LAUNCH_CHECK();
         return;
     }
