@@ -415,6 +415,43 @@ def test_firfilt_full_size_spot_checks_vs_oracle(L, orc):
     L.lib.liquid_cuda_free(d_y)
 
 
+@pytest.mark.parametrize("n_taps", [33, 40, 63, 64])
+def test_firfilt_fast_fir_form_vs_direct_and_oracle(L, orc, monkeypatch, n_taps):
+    """33 - 64 taps take the 2-parallel fast-FIR kernel with the transposed store path: against the oracle and the direct
+    register-blocked kernel, on streams whose length is not a multiple of the 512-output warp tile, state carried"""
+    import ctypes as C
+    rng = np.random.default_rng(n_taps)
+    h = (rng.standard_normal(n_taps) / np.sqrt(n_taps)).astype(np.float32)
+    n_streams, n = 5, 512 * 9 + 130
+    x = orc.synth_input(n_streams * n, seed=0x61 + n_taps).reshape(n_streams, n)
+    outs = {}
+    for direct in (False, True):
+        if direct:
+            monkeypatch.setenv("LIQUID_CUDA_FIRFILT_DIRECT", "1")
+        q = L.firfilt_crcf.create(h)
+        d_x = L.lib.liquid_cuda_malloc(x.nbytes); d_y = L.lib.liquid_cuda_malloc(x.nbytes)
+        L.lib.liquid_cuda_memcpy_h2d(d_x, x.ctypes.data_as(C.c_void_p), x.nbytes)
+        q.execute_streams_dev(d_x, n_streams, n, d_y, 0)
+        L.lib.liquid_cuda_sync()
+        got = np.empty_like(x)
+        L.lib.liquid_cuda_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_y, x.nbytes)
+        L.lib.liquid_cuda_free(d_x); L.lib.liquid_cuda_free(d_y)
+        # one stateful stream cut at an awkward place
+        q2 = L.firfilt_crcf.create(h)
+        cut = 512 * 3 + 77
+        st = np.concatenate([q2.execute_block(x[0][:cut]), q2.execute_block(x[0][cut:])])
+        outs[direct] = (got, st)
+    monkeypatch.delenv("LIQUID_CUDA_FIRFILT_DIRECT")
+    o = orc.Firfilt(h=h)
+    for s in range(n_streams):
+        o.reset()
+        want = o.execute_block(x[s])
+        assert np.abs(outs[False][0][s] - want).max() < 2e-6
+        assert np.abs(outs[True][0][s] - want).max() < 2e-6
+    assert np.abs(outs[False][1] - outs[False][0][0]).max() < 2e-6
+    assert np.abs(outs[False][0] - outs[True][0]).max() < 2e-6
+
+
 def test_firfilt_freqresponse_groupdelay(L):
     h = np.array([0.1, 0.5, 1.0, 0.5, 0.1], np.float32)
     q = L.firfilt_crcf.create(h)
