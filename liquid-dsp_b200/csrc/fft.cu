@@ -6,7 +6,9 @@
 // The factorisation is NOT the reference's (any float32 FFT agrees with it to ~1e-7 relative):
 //   power-of-two N : Stockham autosort, radix-4 stages (+ one radix-2 stage when log2 N is odd),
 //                    whole transform in shared memory, several transforms per CTA when N is small
-//   other N        : table-driven O(N^2) DFT, one CTA per transform (slow, correct, on-device)
+//   other composite N with prime factors <= 13 (N <= 12288): mixed-radix Stockham autosort in shared memory
+//                    (stands in for fft_mixed_radix.c:128-191), factors 4, 2, 3, 5, 7, 11, 13, radix-R register DFTs
+//   any other N    : table-driven O(N^2) DFT, one CTA per transform (slow, correct, on-device)
 // Twiddles come from a per-plan table computed in double on the host.
 #include <cmath>
 
@@ -87,6 +89,87 @@ dft_any_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const float
     }
 }
 
+// ---- mixed-radix Stockham autosort for composite n
+// One pass of radix R over a transform of n points: butterfly j (j < n / R) with k = j mod Ns (Ns = the product of the
+// radices already done) takes in[j + r n/R], r < R, multiplies by e^{sgn j 2 pi r k / (Ns R)} (the plan's table, step
+// n / (Ns R)), does the R-point DFT (roots from the same table, step n / R) and writes out[(j / Ns) Ns R + k + q Ns].
+template <int R>
+__device__ __forceinline__ void mixed_pass(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ tw,
+                                           unsigned int n, unsigned int Ns, unsigned int per_cta, bool to_global,
+                                           float2 *__restrict__ y, unsigned long long first, unsigned long long batch,
+                                           int post_mode, float pa, float pb)
+{
+    const unsigned int nb = n / R, tstep = n / (Ns * R), rstep = n / R;
+    for (unsigned int w = threadIdx.x; w < per_cta * nb; w += blockDim.x) {
+        const unsigned int f = w / nb, j = w - f * nb;
+        const unsigned int k = j % Ns;
+        const float2 *src = in + f * n;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            v[r] = src[j + r * nb];
+            if (r > 0) v[r] = lcd::cmul(v[r], __ldg(tw + (unsigned int)r * k * tstep));     // r k tstep < n
+        }
+        float2 o[R];
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            float2 acc = v[0];
+#pragma unroll
+            for (int r = 1; r < R; r++) acc = lcd::cadd(acc, lcd::cmul(v[r], __ldg(tw + ((q * r) % R) * rstep)));
+            o[q] = acc;
+        }
+        const unsigned int j0 = (j / Ns) * Ns * R + k;
+        if (to_global) {
+            const unsigned long long b = first + f;
+            if (b < batch) {
+#pragma unroll
+                for (int q = 0; q < R; q++) y[b * n + j0 + q * Ns] = fft_post(o[q], post_mode, pa, pb);
+            }
+        } else {
+            float2 *dst = out + f * n;
+#pragma unroll
+            for (int q = 0; q < R; q++) dst[j0 + q * Ns] = o[q];
+        }
+    }
+}
+
+struct MixedRadices {
+    unsigned char r[16];
+    unsigned int count;
+};
+
+// per_cta transforms per CTA, two ping-pong buffers of per_cta * n points; in place (x == y) is fine: a CTA has read all the
+// inputs of its transforms before it writes any of their outputs
+__global__ void __launch_bounds__(kFftThreads)
+fft_mixed_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const float2 *__restrict__ tw, unsigned int n,
+                 MixedRadices rad, unsigned int per_cta, unsigned long long batch, int post_mode, float pa, float pb)
+{
+    extern __shared__ float2 smem[];
+    float2 *buf0 = smem, *buf1 = smem + (size_t)per_cta * n;
+    const unsigned long long first = (unsigned long long)blockIdx.x * per_cta;
+    for (unsigned int w = threadIdx.x; w < per_cta * n; w += blockDim.x) {
+        const unsigned long long b = first + w / n;
+        buf0[w] = b < batch ? __ldg(x + first * n + w) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    unsigned int Ns = 1;
+    for (unsigned int s = 0; s < rad.count; s++) {
+        const bool last = (s + 1 == rad.count);
+        const unsigned int R = rad.r[s];
+#define LC_PASS(RR) case RR: mixed_pass<RR>(buf0, buf1, tw, n, Ns, per_cta, last, y, first, batch, post_mode, pa, pb); break;
+        switch (R) {
+            LC_PASS(2) LC_PASS(3) LC_PASS(4) LC_PASS(5) LC_PASS(7) LC_PASS(11) LC_PASS(13)
+        default: break;
+        }
+#undef LC_PASS
+        Ns *= R;
+        __syncthreads();
+        float2 *t = buf0;
+        buf0 = buf1;
+        buf1 = t;
+    }
+}
+
 }  // namespace
 
 namespace lc {
@@ -105,12 +188,30 @@ void FftPlanDev::init(unsigned int n_, int sign_)
     LC_CUDA_CHECK(cudaMemcpy(d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
     // transforms above 3072 (power of two) / 6144 (other) points need more than the default 48 KB of dynamic
     // shared memory; every kernel a plan may launch is opted in, whatever n this particular plan has
-    static std::atomic<unsigned long long> configured{0};
+    static std::atomic<unsigned long long> configured{0}, configured_mixed{0};
     if (first_time_on_device(configured)) {
         LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         LC_CUDA_CHECK(cudaFuncSetAttribute(fft_pow2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         LC_CUDA_CHECK(cudaFuncSetAttribute(dft_any_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
+    // composite sizes: factors 4 first, then 2, 3, 5, 7, 11, 13; anything left over means no mixed-radix plan
+    n_rad = 0;
+    if (!is_pow2(n) && n >= 6 && (size_t)n * 2 * sizeof(float2) <= 192 * 1024) {
+        unsigned int rest = n, cnt = 0;
+        unsigned char fac[16];
+        const unsigned int cand[7] = {4, 2, 3, 5, 7, 11, 13};
+        for (unsigned int c : cand)
+            while (rest % c == 0 && cnt < 16) {
+                fac[cnt++] = (unsigned char)c;
+                rest /= c;
+            }
+        if (rest == 1 && cnt >= 2) {
+            n_rad = cnt;
+            for (unsigned int i = 0; i < cnt; i++) radices[i] = fac[i];
+        }
+    }
+    if (first_time_on_device(configured_mixed))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(fft_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (is_pow2(n) && n >= 2) {
         const std::vector<float2> twp = lcfft::pass_ordered_twiddles(tw, n);
         LC_CUDA_CHECK(cudaMalloc(&d_twp, sizeof(float2) * n));
@@ -157,6 +258,20 @@ void FftPlanDev::run(const float2 *d_x, float2 *d_y, unsigned long long batch, c
             done += nb;
         }
         return;
+    }
+    if (n_rad > 0 && !getenv("LIQUID_CUDA_FFT_NO_MIXED")) {
+        MixedRadices rad;
+        rad.count = n_rad;
+        for (unsigned int i = 0; i < 16; i++) rad.r[i] = radices[i];
+        unsigned int per_cta = n >= 1024 ? 1 : 2048 / n;               // ~2048 points per CTA
+        if ((unsigned long long)per_cta > batch) per_cta = (unsigned int)batch;
+        const size_t smem = (size_t)per_cta * n * 2 * sizeof(float2);
+        const unsigned long long ctas = (batch + per_cta - 1) / per_cta;
+        if (ctas < (1ull << 31)) {
+            fft_mixed_kernel<<<(unsigned int)ctas, kFftThreads, smem, st>>>(d_x, d_y, d_tw, n, rad, per_cta, batch, post_mode, a, b);
+            LC_LAUNCH_CHECK();
+            return;
+        }
     }
     if ((size_t)n * sizeof(float2) > 200 * 1024)
         fatal("fft_execute", "transform size too large for this build (non power-of-two sizes above 25600 are not supported)");
@@ -210,7 +325,7 @@ void fft_destroy_plan(fftplan _p)
 void fft_print_plan(fftplan _p)
 {
     printf("fft plan [%s], n=%u, %s\n", _p->dir == LIQUID_FFT_FORWARD ? "forward" : "reverse", _p->n,
-           lc::is_pow2(_p->n) ? "CUDA Stockham radix-4" : "CUDA DFT");
+           lc::is_pow2(_p->n) ? "CUDA Stockham radix-4" : (_p->dev.n_rad ? "CUDA mixed-radix Stockham" : "CUDA DFT"));
 }
 
 void fft_execute_batch_dev(fftplan _p, const void *_d_x, void *_d_y, unsigned long long _batch, void *_stream)

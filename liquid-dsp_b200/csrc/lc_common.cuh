@@ -126,6 +126,8 @@ struct FftPlanDev {
     int sign = 0;              // -1 forward (e^{-j}), +1 backward (e^{+j})
     float2 *d_tw = nullptr;    // [n], device
     float2 *d_twp = nullptr;   // [n], device: the same values in the pass order of the shared-memory FFT (power-of-two n)
+    unsigned char radices[16] = {0};   // mixed-radix factorisation of a composite n (factors 2 ... 13), n_rad = 0: none
+    unsigned int n_rad = 0;
     void init(unsigned int n_, int sign_);
     void destroy();
     // y[b][k] = post( sum_i x[b][i] e^{sign j 2 pi i k / n} ); post = identity (mode 0),

@@ -570,6 +570,36 @@ def test_fft_pow2_vs_numpy_and_plan_api(L, orc, n):
     assert np.abs(back / n - xin).max() < 1e-5
 
 
+@pytest.mark.parametrize("n", [6, 12, 18, 20, 30, 100, 300, 360, 1000, 1155, 1200, 2197, 3000, 6000, 7000, 12288])
+def test_fft_composite_sizes_mixed_radix_vs_numpy(L, orc, monkeypatch, n):
+    """composite sizes take the mixed-radix Stockham kernel (fft_mixed_radix.c:128-191 in the reference; factors 4, 2, 3,
+    5, 7, 11, 13): forward and backward against numpy in double, several transforms per CTA and a ragged batch, and
+    against the table-driven DFT the sizes ran on before"""
+    nb = 5
+    x = orc.synth_input(n * nb, seed=170 + n)
+    xin, yout = x[:n].copy(), np.empty(n, np.complex64)
+    for d, np_fft in ((L.LIQUID_FFT_FORWARD, np.fft.fft), (L.LIQUID_FFT_BACKWARD, lambda a, axis=-1: np.fft.ifft(a, axis=axis) * n)):
+        p = L.fftplan(n, xin, yout, d)
+        yb = p.execute_batch(x)
+        want = np_fft(x.reshape(nb, n).astype(np.complex128), axis=1).reshape(-1)
+        assert np.abs(yb - want).max() / np.abs(want).max() < 3e-6
+    if n <= 3000:
+        monkeypatch.setenv("LIQUID_CUDA_FFT_NO_MIXED", "1")
+        yd = L.fftplan(n, xin, yout, L.LIQUID_FFT_BACKWARD).execute_batch(x)
+        monkeypatch.delenv("LIQUID_CUDA_FFT_NO_MIXED")
+        assert np.abs(yb - yd).max() / np.abs(yd).max() < 3e-6
+
+
+@pytest.mark.parametrize("n", [16384, 25600])
+def test_fft_large_sizes_on_the_table_driven_path(L, orc, n):
+    """sizes that fit neither the shared-memory FFTs nor the mixed-radix buffers still transform (O(n^2), 200 KB of
+    shared memory opted in): the limit the error message names is real"""
+    x = orc.synth_input(n, seed=9 + n)
+    y = L.fft_run(x, L.LIQUID_FFT_FORWARD)
+    want = np.fft.fft(x.astype(np.complex128))
+    assert np.abs(y - want).max() / np.abs(want).max() < 1e-5
+
+
 def test_fft_reference_fixtures(L, refout):
     for n in (128, 256, 1024, 4096):
         x = refout["fft_%d_x" % n]

@@ -192,6 +192,20 @@ def run(configs, steps, warmup, sink, device_index=0):
             ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
             report("t: firpfbch2_crcf analysis M=%d m=%d (tile kernel), 2^28 samples" % (M, m), n, 24, ms, ln)
             del x, y
+    if "fftc" in args.configs:
+        # composite transform sizes (mixed-radix Stockham; LIQUID_CUDA_FFT_NO_MIXED=1 gives the table-driven DFT they ran on before)
+        import numpy as np
+        for nfft in (100, 300, 1000, 3000, 6000):
+            npts = 1 << 26
+            batch = npts // nfft
+            xin, yout = np.zeros(nfft, np.complex64), np.zeros(nfft, np.complex64)
+            p = L.fftplan(nfft, xin, yout, L.LIQUID_FFT_FORWARD)
+            x = torch.empty(2 * batch * nfft, dtype=torch.float32, device=dev)
+            y = torch.empty(2 * batch * nfft, dtype=torch.float32, device=dev)
+            L.synth_input_dev(x.data_ptr(), batch * nfft, stream=st.cuda_stream)
+            ms, ln = timed(lambda: p.execute_batch_dev(x.data_ptr(), y.data_ptr(), batch, st.cuda_stream))
+            report("fftc: fft_execute_batch_dev n=%d, 2^26 points" % nfft, batch * nfft, 16, ms, ln)
+            del x, y
     if "rb" in args.configs:
         # the reference's own benchmark list, shape by shape (src/multichannel/bench/firpfbch2_crcf_benchmark.c:70-90 analysis and
         # synthesis, firpfbch_crcf_benchmark.c:80-85 analysis; M = 4 ... 1024, m = 2), 2^27 samples each, one stateful stream
