@@ -481,7 +481,6 @@ void plan(SmallArgs &a, unsigned int M, long long n_frames, unsigned int &grid, 
     const long long n_tiles = (n_frames + kFr - 1) / kFr;
     const long long inst_per_cta = kThreads / (M / 2);
     long long tpi = 64;
-    if (const char *e = getenv("LIQUID_CUDA_SMALL_TPI")) tpi = atoll(e);
     while (tpi > min_tpi && (n_tiles / tpi) < 148ll * 4 * inst_per_cta) tpi >>= 1;
     a.n_frames = n_frames;
     a.n_tiles = (int)n_tiles;
