@@ -759,6 +759,44 @@ def test_pfbch2_small_synthesizer_vs_oracle_odd_splits_and_generic(L, orc, monke
     assert flag == flag3 and np.abs(hist - hist3).max() / max(np.abs(hist).max(), 1e-30) < 2e-6
 
 
+# ------------------------------------------------------------------ random block cuts across every dedicated kernel
+def test_channelizers_random_cuts_vs_oracle(L, orc):
+    """every shape with a dedicated kernel (M = 4 ... 1024; m = 2, 4, 5), analysis and synthesis of both channelizers, fed
+    in seeded random block sizes that include single frames, blocks below the synthesizers' 4m-frame threshold (two-kernel
+    path in between, state handed over) and ragged tiles: one stream of outputs whatever the cuts"""
+    rng = np.random.default_rng(20261019)
+    for M in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
+        for m in (2, 4, 5):
+            nfr = int(rng.integers(300, 700)) if M >= 256 else int(rng.integers(1500, 4000))
+            sizes = []
+            left = nfr
+            while left > 0:
+                k = int(rng.choice([1, 1, 2, 3, 7, 8, 9, 15, 16, 17, 40, 64, 65, 200, 1000]))
+                k = min(k, left)
+                sizes.append(k)
+                left -= k
+            cuts = np.concatenate([[0], np.cumsum(sizes)])
+            for kind in ("a2", "s2", "a1", "s1"):
+                if kind[1] == "2":
+                    typ = L.LIQUID_ANALYZER if kind[0] == "a" else L.LIQUID_SYNTHESIZER
+                    per_in = M // 2 if kind[0] == "a" else M
+                    x = orc.synth_input(nfr * per_in, seed=int(rng.integers(1 << 30)))
+                    want = orc.Firpfbch2(orc.ANALYZER if kind[0] == "a" else orc.SYNTHESIZER, M, m, As=60.0).execute_frames(x)
+                    q = L.firpfbch2_crcf.create_kaiser(typ, M, m, 60.0)
+                else:
+                    typ = L.LIQUID_ANALYZER if kind[0] == "a" else L.LIQUID_SYNTHESIZER
+                    per_in = M
+                    x = orc.synth_input(nfr * per_in, seed=int(rng.integers(1 << 30)))
+                    want = orc.Firpfbch(orc.ANALYZER if kind[0] == "a" else orc.SYNTHESIZER, M, kaiser=(m, 60.0)).execute_frames(x)
+                    q = L.firpfbch_crcf.create_kaiser(typ, M, m, 60.0)
+                got = np.concatenate([np.asarray(q.execute_block(x[a * per_in:b * per_in])).reshape(-1)
+                                      for a, b in zip(cuts[:-1], cuts[1:])])
+                q.destroy()
+                want = np.asarray(want).reshape(-1)
+                err = np.abs(got - want).max() / np.abs(want).max()
+                assert err < 1e-5, (kind, M, m, err)
+
+
 # ------------------------------------------------------------------ root-Nyquist Kaiser prototypes (SURVEY 8f item 1)
 def test_pfbch_rnyquist_kaiser_prototypes_vs_reference(L, orc, refrn):
     """firpfbch_crcf_create_rnyquist with ARKAISER / RKAISER against the compiled reference's outputs and
