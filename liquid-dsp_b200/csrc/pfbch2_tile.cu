@@ -620,6 +620,174 @@ __global__ void __launch_bounds__(kThreads, NT <= 8 ? 2 : 1) pfbch2_tile_synth_k
     }
 }
 
+// firpfbch (critically sampled) synthesizer, firpfbch.c:314-336: v_s = unscaled backward DFT of frame s,
+// y[sM + i] = sum_n h[i + nM] v_{s-n}[i].  The kernel above without the frame parity: thread u owns the columns u and
+// u + M/2 of v and forms both outputs every frame; the object's state (the last p rows of v) is recomputed by the caller.
+struct PfbSynthArgs {
+    const float2 *hist;        // hist_rows rows of v preceding frame 0 (single-stream stateful use), or null
+    const float2 *x;           // [n_streams][stream_stride]
+    float2 *y;
+    const float *taps;         // [P][M]: taps[n][i] = h[i + nM]
+    const float2 *tw;          // backward twiddles, as TileArgs::tw
+    long long n_frames;
+    long long stream_stride;
+    int hist_rows;
+    int n_tiles;
+    int tiles_per_inst;
+};
+
+template <int M, int NT>
+__global__ void __launch_bounds__(kThreads, NT <= 4 ? 2 : 1) pfbch_tile_synth_kernel(const PfbSynthArgs a)
+{
+    using LY = TileLayout<M>;
+    constexpr int M2 = M / 2, R2 = M2 / 16;
+    constexpr int PR = LY::PR, SS = LY::SS, FS = LY::FS, NBUF = LY::NBUF;
+    constexpr int HL = NT - 1;                  // rows of history an output looks back at
+    constexpr int WT = (HL + kFr - 1) / kFr;    // warm-up tiles of an instance that starts inside the stream
+    constexpr int RPT = 16 / R2;                // pass-B' rows per thread (grouped order)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int inst_l = threadIdx.x / M2, u = threadIdx.x % M2;
+    float2 *tile0 = reinterpret_cast<float2 *>(smem_raw) + inst_l * (NBUF * kFr * FS);
+    float2 *tws = reinterpret_cast<float2 *>(smem_raw) + (kThreads / M2) * (NBUF * kFr * FS);
+    const long long inst = (long long)blockIdx.x * (kThreads / M2) + inst_l;
+    const long long t0 = inst * a.tiles_per_inst;
+    long long ntl = (long long)a.n_tiles - t0;
+    if (ntl > a.tiles_per_inst) ntl = a.tiles_per_inst;
+    const int nt = ntl > 0 ? (int)ntl : 0;
+    const float2 *xstr = a.x + (long long)blockIdx.y * a.stream_stride;
+    float2 *ystr = a.y + (long long)blockIdx.y * a.stream_stride;
+
+    auto inst_barrier = [&]() {
+        if (M2 == kThreads) __syncthreads();
+        else if (M2 == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + inst_l), "n"(M2) : "memory");
+    };
+    // pass-A' role: frame f2, sub-problem p2 (fastest), column t2
+    const int f2 = u / (2 * R2), p2 = u & 1, t2 = (u % (2 * R2)) >> 1;
+    // the thread's 16 inputs of tile `it`: grouped order rows k1 = t2 + R2 i of (f2, p2); wide order items j = u + M2 i.
+    // They are prefetched into REGISTERS one tile ahead (issued when pass B' has consumed the previous set, needed at
+    // the top of the next tile): staging them through a cp.async slot cost a third of the kernel's shared-memory
+    // wavefronts (ncu: mio_throttle 22 % of the stall samples, shared-memory pipe 59 % busy at 0.67 of the roofline).
+    float2 nx[16];
+    auto fetch = [&](int it) {
+        const long long f0 = (t0 + it) * kFr;
+#pragma unroll
+        for (int i = 0; i < (LY::WIDE ? 32 * kFr / M2 : RPT); i++) {
+            int f, off;
+            if (LY::WIDE) { const int j = u + M2 * i; f = j >> 5; off = j & 31; }
+            else          { f = f2; off = 2 * (t2 + R2 * i) + p2; }
+            const bool ok = it < nt && f0 + f < a.n_frames;
+            const float2 *src = xstr + (f0 + f) * M + off;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; k2++) nx[i * R2 + k2] = ok ? __ldg(src + 32 * k2) : make_float2(0.f, 0.f);
+        }
+    };
+    const int it0 = (t0 > 0 && nt > 0) ? -WT : 0;
+    fetch(it0);
+    // the inter-pass twiddles by column: tws[t2][k1] = e^{+j 2 pi k1 t2 / (M/2)}
+    for (int i = u; i < 16 * R2; i += M2) tws[(i % R2) * kTwPitch + i / R2] = __ldg(a.tw + M2 + i);
+    float h0[NT], h1[NT];
+#pragma unroll
+    for (int q = 0; q < NT; q++) {
+        h0[q] = __ldg(a.taps + q * M + u);
+        h1[q] = __ldg(a.taps + q * M + u + M2);
+    }
+    const float2 w2 = __ldg(a.tw + u);                            // W_M^u
+    float2 wlo[HL + kFr], whi[HL + kFr];                          // columns u and u + M/2 of v, oldest first
+#pragma unroll
+    for (int i = 0; i < HL; i++) {
+        wlo[i] = whi[i] = make_float2(0.f, 0.f);
+        if (t0 == 0 && a.hist != nullptr) {
+            wlo[i] = __ldg(a.hist + (size_t)(a.hist_rows - HL + i) * M + u);
+            whi[i] = __ldg(a.hist + (size_t)(a.hist_rows - HL + i) * M + u + M2);
+        }
+    }
+    const float4 *twc = reinterpret_cast<const float4 *>(tws + t2 * kTwPitch);
+    const int mac_off = (u / R2) * PR + (u % R2);
+    const int sp_off = f2 * FS + p2 * SS;
+    __syncthreads();
+
+    for (int it = it0; it < nt; it++) {
+        const long long f0 = (t0 + it) * kFr;
+        float2 *tile = tile0 + ((it - it0) % NBUF) * (kFr * FS);
+        // ---- pass B': rows of the sub-problems, out of the input slot
+        if (LY::WIDE) {
+#pragma unroll
+            for (int i = 0; i < 32 * kFr / M2; i++) {
+                const int j = u + M2 * i;
+                float2 r[R2];
+#pragma unroll
+                for (int k2 = 0; k2 < R2; k2++) r[k2] = nx[i * R2 + k2];
+                RegDft<R2, +1>::run(r);
+                float2 *row = tile + (j >> 5) * FS + (j & 1) * SS + ((j & 31) >> 1) * PR;
+#pragma unroll
+                for (int c = 0; c < R2; c++) row[c] = r[c];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < RPT; i++) {
+                float2 r[R2];
+#pragma unroll
+                for (int k2 = 0; k2 < R2; k2++) r[k2] = nx[i * R2 + k2];
+                RegDft<R2, +1>::run(r);
+                float2 *row = tile + sp_off + (t2 + R2 * i) * PR;
+#pragma unroll
+                for (int c = 0; c < R2; c++) row[c] = r[c];
+            }
+        }
+        fetch(it + 1);                                            // the values are consumed: load the next tile's
+        if (LY::WIDE) inst_barrier();
+        else __syncwarp();
+        // ---- pass A': twiddle and 16-point DFT down column t2 of (f2, p2), in place
+        {
+            float2 *sp = tile + sp_off;
+            float2 v[16];
+#pragma unroll
+            for (int k1 = 0; k1 < 16; k1++) v[k1] = sp[k1 * PR + t2];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float4 t = twc[k];
+                if (k > 0) v[2 * k] = cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+                v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+            }
+            RegDft<16, +1>::run(v);
+#pragma unroll
+            for (int r1 = 0; r1 < 16; r1++) sp[r1 * PR + t2] = v[r1];
+        }
+        inst_barrier();
+        // ---- FIR: last radix-2 stage, window push, dot products
+        const float2 *src = tile + mac_off;
+#pragma unroll
+        for (int f = 0; f < kFr; f++) {
+            const float2 e0 = src[f * FS];
+            const float2 t = cmul2_rot(src[f * FS + SS], w2);
+            wlo[HL + f] = __fadd2_rn(e0, t);
+            whi[HL + f] = __fadd2_rn(e0, neg2(t));
+        }
+        if (it >= 0) {
+#pragma unroll
+            for (int f = 0; f < kFr; f++) {
+                float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+                for (int n = NT - 1; n >= 0; n--) {
+                    a0 = __ffma2_rn(bc(h0[n]), wlo[HL + f - n], a0);
+                    a1 = __ffma2_rn(bc(h1[n]), whi[HL + f - n], a1);
+                }
+                if (f0 + f < a.n_frames) {
+                    __stcs(ystr + (f0 + f) * M + u, a0);
+                    __stcs(ystr + (f0 + f) * M + u + M2, a1);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < HL; i++) {
+            wlo[i] = wlo[kFr + i];
+            whi[i] = whi[kFr + i];
+        }
+        if (NBUF == 1) inst_barrier();
+    }
+}
+
 // ---------------------------------------------------------------------------------- synthesizer, M = 1024
 // Same transposed flow with a radix-4 last stage: one instance = one CTA of 256 threads, thread u owns the FOUR columns
 // u + 256 q of v.  Per frame four 256-point problems X_p[k] = X[4k + p]: 64 threads per frame, lane = (p fastest, row):
@@ -893,6 +1061,64 @@ long long launch_pfbch_tile(const float2 *d_hist, const float2 *d_x, int H, cons
     case 128: launch_pfb_M<128>(a, p, grid, st); break;
     case 512: launch_pfb_M<512>(a, p, grid, st); break;
     default: fatal("launch_pfbch_tile", "unsupported channel count");
+    }
+    LC_LAUNCH_CHECK();
+    return (long long)n_frames;
+}
+
+bool tile_pfbch_synth_supported(unsigned int M, unsigned int p)
+{
+    return (M == 64 || M == 128 || M == 512) && (p == 4 || p == 8 || p == 10);
+}
+
+template <int M, int P>
+void launch_pfb_synth_MP(const PfbSynthArgs &a, dim3 grid, cudaStream_t st)
+{
+    constexpr size_t smem = tile_synth_smem_bytes<M>();
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch_tile_synth_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pfbch_tile_synth_kernel<M, P><<<grid, kThreads, smem, st>>>(a);
+}
+
+template <int M>
+void launch_pfb_synth_M(const PfbSynthArgs &a, unsigned int p, dim3 grid, cudaStream_t st)
+{
+    switch (p) {
+    case 4: launch_pfb_synth_MP<M, 4>(a, grid, st); break;
+    case 8: launch_pfb_synth_MP<M, 8>(a, grid, st); break;
+    case 10: launch_pfb_synth_MP<M, 10>(a, grid, st); break;
+    default: lc::fatal("launch_pfbch_tile_synth", "unsupported tap count");
+    }
+}
+
+long long launch_pfbch_tile_synth(const float2 *d_hist_rows, int hist_rows, const float2 *d_x, const float *d_taps,
+                                  const float2 *d_tw, float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
+                                  unsigned int n_streams, long long stream_stride, cudaStream_t st)
+{
+    const long long n_tiles = (long long)((n_frames + kFr - 1) / kFr);
+    if (n_tiles == 0 || n_tiles > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;
+    PfbSynthArgs a;
+    a.hist = d_hist_rows;
+    a.hist_rows = hist_rows;
+    a.x = d_x;
+    a.y = d_y;
+    a.taps = d_taps;
+    a.tw = d_tw;
+    a.n_frames = (long long)n_frames;
+    a.stream_stride = stream_stride;
+    a.n_tiles = (int)n_tiles;
+    const long long inst_per_cta = kThreads / (M / 2);
+    long long tpi = 64;
+    while (tpi > 4 && (n_tiles / tpi) * n_streams < 148ll * 4 * inst_per_cta) tpi >>= 1;
+    a.tiles_per_inst = (int)tpi;
+    const long long n_inst = (n_tiles + tpi - 1) / tpi;
+    dim3 grid((unsigned int)((n_inst + inst_per_cta - 1) / inst_per_cta), n_streams, 1);
+    switch (M) {
+    case 64: launch_pfb_synth_M<64>(a, p, grid, st); break;
+    case 128: launch_pfb_synth_M<128>(a, p, grid, st); break;
+    case 512: launch_pfb_synth_M<512>(a, p, grid, st); break;
+    default: fatal("launch_pfbch_tile_synth", "unsupported channel count");
     }
     LC_LAUNCH_CHECK();
     return (long long)n_frames;

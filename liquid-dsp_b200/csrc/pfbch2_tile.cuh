@@ -35,5 +35,12 @@ long long launch_pfbch_tile(const float2 *d_hist, const float2 *d_x, int H, cons
                             float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
                             unsigned int n_streams, long long stream_stride, cudaStream_t st);
 
+// firpfbch synthesizer, M = 64 / 128 / 512, p in {4, 8, 10}: same contract as launch_pfbch_synth_fused (pfbch_fused.cuh),
+// every frame covered; d_tw: tile_pfbch2_make_twiddles (backward).
+bool tile_pfbch_synth_supported(unsigned int M, unsigned int p);
+long long launch_pfbch_tile_synth(const float2 *d_hist_rows, int hist_rows, const float2 *d_x, const float *d_taps,
+                                  const float2 *d_tw, float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
+                                  unsigned int n_streams, long long stream_stride, cudaStream_t st);
+
 }  // namespace pfb
 }  // namespace lc

@@ -605,11 +605,15 @@ bool fused_pfbch_supported(unsigned int M, unsigned int p)
 
 bool fused_pfbch_synth_supported(unsigned int M, unsigned int p)
 {
-    return (M == 256 && (p == 4 || p == 10)) || (M == 1024 && (p == 4 || p == 8 || p == 10));
+    return (M == 256 && (p == 4 || p == 10)) || (M == 1024 && (p == 4 || p == 8 || p == 10)) || tile_pfbch_synth_supported(M, p);
 }
 
 void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign, unsigned int M, unsigned int p)
 {
+    if (sign > 0 && tile_pfbch_synth_supported(M, p)) {
+        tile_pfbch2_make_twiddles(tw, M);                     // synthesizers for M = 64 / 128 / 512 (pfbch2_tile.cu): backward table
+        return;
+    }
     if (sign < 0 && small_pfbch_supported(M, p)) {
         tw.assign(1, make_float2(1.f, 0.f));                  // these kernels need no table
         return;
@@ -708,6 +712,8 @@ long long launch_pfbch_synth_fused(const float2 *d_hist_rows, int n_hist_rows, c
                                    unsigned long long n_frames, unsigned int n_streams, long long stream_stride,
                                    cudaStream_t st)
 {
+    if (tile_pfbch_synth_supported(M, p))
+        return launch_pfbch_tile_synth(d_hist_rows, n_hist_rows, d_x, d_taps, d_tw, d_y, M, p, n_frames, n_streams, stream_stride, st);
     if (M == 1024) {
         const long long nq = (long long)((n_frames + kQFr - 1) / kQFr);
         if (nq == 0 || nq > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;

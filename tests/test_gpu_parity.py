@@ -1307,7 +1307,8 @@ def test_pfbch_streams_dev(L, orc, M, m):
 
 
 @pytest.mark.parametrize("M,m,nfr", [(256, 5, 16 * 40 + 9), (256, 2, 16 * 33), (64, 3, 50), (1024, 2, 4 * 77 + 3), (1024, 5, 203),
-                                     (1024, 4, 1300)])
+                                     (1024, 4, 1300), (64, 2, 1500), (64, 5, 8 * 77 + 3), (128, 4, 700), (512, 2, 8 * 61 + 5),
+                                     (512, 5, 333)])
 def test_pfbch_synthesis_fused_and_streams(L, orc, M, m, nfr):
     """fused M=256 / M=1024 synthesizers (many tiles / instances, tail, state carry) and the multi-stream form"""
     import ctypes as C

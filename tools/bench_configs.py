@@ -159,7 +159,7 @@ def run(configs, steps, warmup, sink, device_index=0):
         report("s: firpfbch2_crcf synthesis M=1024 m=7, 2^27 output samples", n, 24, ms, ln,
                {"note": "throughput in OUTPUT samples/s; algorithmic bytes 16 in + 8 out per output sample"})
         del X, y
-        for M, m in ((1024, 2), (256, 5)):
+        for M, m in ((1024, 2), (256, 5), (64, 2), (128, 2), (512, 2), (512, 5)):
             n = 1 << 27
             q = L.firpfbch_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
             X = torch.empty(2 * n, dtype=torch.float32, device=dev)
