@@ -20,6 +20,7 @@
 #include "../../include/liquid_cuda.h"
 #include "pfb_kernels.cuh"
 #include "host_pipeline.cuh"
+#include "pfbch2_tile.cuh"
 
 struct firpfbch_cccf_s {
     int type;
@@ -29,6 +30,7 @@ struct firpfbch_cccf_s {
     firpfbch_crcf real = nullptr;   // set when every tap is real: the crcf object carries state and kernels
     float2 *d_taps = nullptr;       // [p][M]: taps[n][i] = h[i + nM]
     float2 *d_hist = nullptr;
+    float2 *d_tw_tile = nullptr;    // forward twiddles of the complex-tap tile analyzer (M = 64 ... 512), or null
     unsigned int phase = 0;         // analyzer: pushes since reset, mod M
     lc::FftPlanDev fft;
     lc::DevBuf scratch, stage_in, stage_out, hist_tmp, one;
@@ -42,6 +44,11 @@ namespace {
 void analyze_generic_cc(firpfbch_cccf q, const float2 *d_x, float2 *d_y, unsigned long long n, unsigned int first,
                         unsigned int k, cudaStream_t st)
 {
+    if (q->d_tw_tile && q->phase == 0 && first == q->M && k == 0 && !getenv("LIQUID_CUDA_NO_FUSED")) {
+        // whole frames from an aligned state: the tile kernel of pfbch2_tile.cu with complex taps
+        lc::pfb::launch_pfbch_tile_cc(q->d_hist, d_x, (int)q->H, q->d_taps, q->d_tw_tile, d_y, q->M, q->p, n, st);
+        return;
+    }
     if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL")) {
         lc::pfb::launch_pfbch_analyze_pow2_cc(q->d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_twp, d_y, q->M, q->p, n,
                                               q->phase, first, k, st);
@@ -86,6 +93,12 @@ firpfbch_cccf firpfbch_cccf_create(int _type, unsigned int _M, unsigned int _p, 
     LC_CUDA_CHECK(cudaMemcpy(q->d_taps, q->h.data(), sizeof(float2) * q->h.size(), cudaMemcpyHostToDevice));
     LC_CUDA_CHECK(cudaMalloc(&q->d_hist, sizeof(float2) * q->H));
     q->fft.init(_M, _type == LIQUID_ANALYZER ? -1 : +1);     // firpfbch.c:131-135
+    if (_type == LIQUID_ANALYZER && lc::pfb::tile_pfbch_cc_supported(_M, _p)) {
+        std::vector<float2> tw;
+        lc::pfb::tile_pfbch_make_twiddles(tw, _M);
+        LC_CUDA_CHECK(cudaMalloc(&q->d_tw_tile, tw.size() * sizeof(float2)));
+        LC_CUDA_CHECK(cudaMemcpy(q->d_tw_tile, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
     LC_CUDA_CHECK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
     firpfbch_cccf_reset(q);
     return q;
@@ -138,6 +151,7 @@ void firpfbch_cccf_destroy(firpfbch_cccf _q)
         cudaStreamSynchronize(_q->stream);
         cudaFree(_q->d_taps);
         cudaFree(_q->d_hist);
+        cudaFree(_q->d_tw_tile);
         _q->fft.destroy();
         _q->scratch.release();
         _q->stage_in.release();

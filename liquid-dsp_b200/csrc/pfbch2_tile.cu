@@ -287,23 +287,30 @@ struct PfbTileArgs {
 // a cp.async slot in shared memory elsewhere (M = 64, p = 10: 0.93 against 0.75 with 160 B of spills)
 template <int M, int P> constexpr bool kPfbRegPrefetch = (P <= 4) || (M >= 512);
 
-template <int M, int P>
+template <int M, int P, typename TapT>
 constexpr size_t pfb_tile_smem_bytes()
 {
     using LY = TileLayout<M>;
-    return sizeof(float2) * ((kPfbRegPrefetch<M, P> ? (size_t)0 : (size_t)2 * kFr * kThreads)
+    return sizeof(float2) * (((kPfbRegPrefetch<M, P> || sizeof(TapT) == 8) ? (size_t)0 : (size_t)2 * kFr * kThreads)
                              + (size_t)(kThreads / (M / 2)) * LY::NBUF * kFr * LY::FS + (size_t)(M / 32) * kTwPitch);
 }
 
-template <int M, int P>
-__global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileArgs a)
+// tap types: float (firpfbch_crcf) or float2 (firpfbch_cccf: plain complex product, two packed FFMA2 per tap)
+__device__ __forceinline__ float2 tap_mac(float h, float2 s, float2 acc) { return __ffma2_rn(bc(h), s, acc); }
+__device__ __forceinline__ float2 tap_mac(float2 h, float2 s, float2 acc)
+{
+    return __ffma2_rn(make_float2(-h.y, h.y), make_float2(s.y, s.x), __ffma2_rn(bc(h.x), s, acc));
+}
+
+template <int M, int P, typename TapT>
+__global__ void __launch_bounds__(kThreads, (sizeof(TapT) == 4 || P <= 4) ? 2 : 1) pfbch_tile_kernel(const PfbTileArgs a)
 {
     using LY = TileLayout<M>;
     constexpr int M2 = M / 2, R2 = M2 / 16;
     constexpr int PR = LY::PR, SS = LY::SS, FS = LY::FS, NBUF = LY::NBUF;
     constexpr int HL = P - 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr bool REGPF = kPfbRegPrefetch<M, P>;
+    constexpr bool REGPF = kPfbRegPrefetch<M, P> || sizeof(TapT) == 8;
     constexpr int kSlotUnits = REGPF ? 0 : 2 * kFr * kThreads;
     float2 *slot = reinterpret_cast<float2 *>(smem_raw);          // [2 kFr][kThreads]: a thread's own 16 samples of a tile
     const int inst_l = threadIdx.x / M2, u = threadIdx.x % M2;
@@ -344,11 +351,12 @@ __global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileAr
     fetch(0);
     for (int i = u; i < 16 * R2; i += M2) tws[(i % R2) * kTwPitch + i / R2] = __ldg(a.tw + M2 + i);
 
-    float h0[P], h1[P];
+    const TapT *taps = reinterpret_cast<const TapT *>(a.taps);
+    TapT h0[P], h1[P];
 #pragma unroll
     for (int n = 0; n < P; n++) {
-        h0[n] = __ldg(a.taps + n * M + (M - 1 - u));              // branch M-1-u feeds input u
-        h1[n] = __ldg(a.taps + n * M + (M2 - 1 - u));             // branch M-1-(u + M/2)
+        h0[n] = __ldg(taps + n * M + (M - 1 - u));                // branch M-1-u feeds input u
+        h1[n] = __ldg(taps + n * M + (M2 - 1 - u));               // branch M-1-(u + M/2)
     }
     const float2 w2 = __ldg(a.tw + u);                            // W_M^u, forward
     float2 w0[HL + kFr], w1[HL + kFr];
@@ -389,8 +397,8 @@ __global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileAr
             float2 d0 = make_float2(0.f, 0.f), d1 = d0;
 #pragma unroll
             for (int n = P - 1; n >= 0; n--) {
-                d0 = __ffma2_rn(bc(h0[n]), w0[HL + f - n], d0);
-                d1 = __ffma2_rn(bc(h1[n]), w1[HL + f - n], d1);
+                d0 = tap_mac(h0[n], w0[HL + f - n], d0);
+                d1 = tap_mac(h1[n], w1[HL + f - n], d1);
             }
             mac_dst[f * FS] = __fadd2_rn(d0, d1);
             mac_dst[f * FS + SS] = cmul2_rot(__fadd2_rn(d0, neg2(d1)), w2);
@@ -408,23 +416,23 @@ __global__ void __launch_bounds__(kThreads, 2) pfbch_tile_kernel(const PfbTileAr
     if (!REGPF) cp_async_wait<0>();
 }
 
-template <int M, int P>
+template <int M, int P, typename TapT>
 void launch_pfb_MP(const PfbTileArgs &a, dim3 grid, cudaStream_t st)
 {
-    constexpr size_t smem = pfb_tile_smem_bytes<M, P>();
+    constexpr size_t smem = pfb_tile_smem_bytes<M, P, TapT>();
     static std::atomic<unsigned long long> configured{0};
     if (lc::first_time_on_device(configured))
-        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch_tile_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pfbch_tile_kernel<M, P><<<grid, kThreads, smem, st>>>(a);
+        LC_CUDA_CHECK(cudaFuncSetAttribute(pfbch_tile_kernel<M, P, TapT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pfbch_tile_kernel<M, P, TapT><<<grid, kThreads, smem, st>>>(a);
 }
 
-template <int M>
+template <int M, typename TapT>
 void launch_pfb_M(const PfbTileArgs &a, unsigned int P, dim3 grid, cudaStream_t st)
 {
     switch (P) {
-    case 4: launch_pfb_MP<M, 4>(a, grid, st); break;
-    case 8: launch_pfb_MP<M, 8>(a, grid, st); break;
-    case 10: launch_pfb_MP<M, 10>(a, grid, st); break;
+    case 4: launch_pfb_MP<M, 4, TapT>(a, grid, st); break;
+    case 8: launch_pfb_MP<M, 8, TapT>(a, grid, st); break;
+    case 10: launch_pfb_MP<M, 10, TapT>(a, grid, st); break;
     default: lc::fatal("launch_pfbch_tile", "unsupported tap count");
     }
 }
@@ -1034,9 +1042,11 @@ void tile_pfbch_make_twiddles(std::vector<float2> &tw, unsigned int M)
     for (float2 &t : tw) t.y = -t.y;                              // forward transform
 }
 
-long long launch_pfbch_tile(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, const float2 *d_tw,
-                            float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
-                            unsigned int n_streams, long long stream_stride, cudaStream_t st)
+namespace {
+template <typename TapT>
+long long launch_pfbch_tile_T(const float2 *d_hist, const float2 *d_x, int H, const TapT *d_taps, const float2 *d_tw,
+                              float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
+                              unsigned int n_streams, long long stream_stride, cudaStream_t st)
 {
     const long long n_tiles = (long long)((n_frames + kFr - 1) / kFr);
     if (n_tiles == 0 || n_tiles > (1ll << 30) || n_streams == 0 || n_streams > 65535) return 0;
@@ -1044,7 +1054,7 @@ long long launch_pfbch_tile(const float2 *d_hist, const float2 *d_x, int H, cons
     a.hist = d_hist;
     a.x = d_x;
     a.y = d_y;
-    a.taps = d_taps;
+    a.taps = reinterpret_cast<const float *>(d_taps);
     a.tw = d_tw;
     a.H = H;
     a.n_frames = (long long)n_frames;
@@ -1057,13 +1067,35 @@ long long launch_pfbch_tile(const float2 *d_hist, const float2 *d_x, int H, cons
     const long long n_inst = (n_tiles + tpi - 1) / tpi;
     dim3 grid((unsigned int)((n_inst + inst_per_cta - 1) / inst_per_cta), n_streams, 1);
     switch (M) {
-    case 64: launch_pfb_M<64>(a, p, grid, st); break;
-    case 128: launch_pfb_M<128>(a, p, grid, st); break;
-    case 512: launch_pfb_M<512>(a, p, grid, st); break;
-    default: fatal("launch_pfbch_tile", "unsupported channel count");
+    case 64: launch_pfb_M<64, TapT>(a, p, grid, st); break;
+    case 128: launch_pfb_M<128, TapT>(a, p, grid, st); break;
+    case 256:
+        if (sizeof(TapT) == 8) { launch_pfb_M<256, float2>(a, p, grid, st); break; }
+        lc::fatal("launch_pfbch_tile", "unsupported channel count");
+    case 512: launch_pfb_M<512, TapT>(a, p, grid, st); break;
+    default: lc::fatal("launch_pfbch_tile", "unsupported channel count");
     }
     LC_LAUNCH_CHECK();
     return (long long)n_frames;
+}
+}  // namespace
+
+long long launch_pfbch_tile(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, const float2 *d_tw,
+                            float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
+                            unsigned int n_streams, long long stream_stride, cudaStream_t st)
+{
+    return launch_pfbch_tile_T<float>(d_hist, d_x, H, d_taps, d_tw, d_y, M, p, n_frames, n_streams, stream_stride, st);
+}
+
+bool tile_pfbch_cc_supported(unsigned int M, unsigned int p)
+{
+    return (M == 64 || M == 128 || M == 256 || M == 512) && (p == 4 || p == 8 || p == 10);
+}
+
+long long launch_pfbch_tile_cc(const float2 *d_hist, const float2 *d_x, int H, const float2 *d_taps, const float2 *d_tw,
+                               float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st)
+{
+    return launch_pfbch_tile_T<float2>(d_hist, d_x, H, d_taps, d_tw, d_y, M, p, n_frames, 1, 0, st);
 }
 
 bool tile_pfbch_synth_supported(unsigned int M, unsigned int p)

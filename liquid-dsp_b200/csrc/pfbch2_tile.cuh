@@ -42,5 +42,10 @@ long long launch_pfbch_tile_synth(const float2 *d_hist_rows, int hist_rows, cons
                                   const float2 *d_tw, float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames,
                                   unsigned int n_streams, long long stream_stride, cudaStream_t st);
 
+// the same analyzer with complex taps (firpfbch_cccf), M = 64 / 128 / 256 / 512; d_tw: tile_pfbch_make_twiddles (forward)
+bool tile_pfbch_cc_supported(unsigned int M, unsigned int p);
+long long launch_pfbch_tile_cc(const float2 *d_hist, const float2 *d_x, int H, const float2 *d_taps, const float2 *d_tw,
+                               float2 *d_y, unsigned int M, unsigned int p, unsigned long long n_frames, cudaStream_t st);
+
 }  // namespace pfb
 }  // namespace lc

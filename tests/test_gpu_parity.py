@@ -759,6 +759,26 @@ def test_pfbch2_small_synthesizer_vs_oracle_odd_splits_and_generic(L, orc, monke
     assert flag == flag3 and np.abs(hist - hist3).max() / max(np.abs(hist).max(), 1e-30) < 2e-6
 
 
+@pytest.mark.parametrize("M,p", [(64, 4), (64, 10), (128, 8), (256, 10), (256, 4), (512, 10), (512, 4)])
+def test_pfbch_cccf_complex_taps_tile_analyzer(L, orc, monkeypatch, M, p):
+    """firpfbch_cccf analysis with complex taps on the tile kernel (two packed FFMA2 per tap): against the oracle with the
+    state carried over awkward cuts (incl. single frames), and against the shape-generic complex-tap kernels"""
+    rng = np.random.default_rng(M + p)
+    h = ((rng.standard_normal(M * p) + 1j * rng.standard_normal(M * p)) / p).astype(np.complex64)
+    nfr = 8 * 41 + 5
+    x = orc.synth_input(nfr * M, seed=0xCC + M + p)
+    want = orc.FirpfbchCccf(orc.ANALYZER, M, p, h).execute_frames(x)
+    q = L.firpfbch_cccf.create(L.LIQUID_ANALYZER, M, p, h)
+    cuts = [0, 1, 2, 75, 76, 200, nfr]
+    got = np.concatenate([q.execute_block(x[a * M:b * M]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+    q.reset()
+    monkeypatch.setenv("LIQUID_CUDA_NO_FUSED", "1")
+    generic = q.execute_block(x)
+    monkeypatch.delenv("LIQUID_CUDA_NO_FUSED")
+    assert np.abs(got - generic).max() / np.abs(want).max() < 2e-6
+
+
 # ------------------------------------------------------------------ random block cuts across every dedicated kernel
 def test_channelizers_random_cuts_vs_oracle(L, orc):
     """every shape with a dedicated kernel (M = 4 ... 1024; m = 2, 4, 5), analysis and synthesis of both channelizers, fed

@@ -292,7 +292,7 @@ def run(configs, steps, warmup, sink, device_index=0):
         h = ((rng.standard_normal(M * 2 * m) + 1j * rng.standard_normal(M * 2 * m)) / (2 * m)).astype(np.complex64)
         q = L.firpfbch_cccf.create(L.LIQUID_ANALYZER, M, 2 * m, h)
         ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
-        report("f1b: firpfbch_cccf analysis M=256 p=10, complex taps (shape-generic MAC + FFT kernels), 2^27 samples", n, 16, ms, ln)
+        report("f1b: firpfbch_cccf analysis M=256 p=10, complex taps (tile kernel, two FFMA2 per tap), 2^27 samples", n, 16, ms, ln)
         del x, y
     if "f3" in args.configs:
         # firdecim_crcf (M=8, m=6: 96 taps, 2^28 inputs) and firinterp_crcf (M=8, m=6, 2^25 inputs)
