@@ -52,7 +52,7 @@ constexpr int kM = 1024;
 constexpr int kM2 = 512;
 constexpr int kMacWarps = 8;
 constexpr int kFftWarps = 8;
-constexpr int kMacThreads = 32 * kMacWarps;                    // 256
+static_assert(32 * kMacWarps == 256, "thread j of the MAC role owns the windows j + 256 q");
 constexpr int kThreads = 32 * (kMacWarps + kFftWarps);         // 512
 constexpr int kGroup = 4;                                      // frames per group (two FFT warps each)
 constexpr int kRingGroups = 4;                                 // X ring depth, in groups (power of two)
