@@ -15,6 +15,7 @@
 #include "lc_common.cuh"
 #include "fft_device.cuh"
 #include "fused_common.cuh"
+#include "tile_fft.cuh"
 #include "../../include/liquid_cuda.h"
 
 namespace {
@@ -66,6 +67,55 @@ fft_pow2_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const floa
     const GlobalDst dst{y, n, first, batch, post_mode, pa, pb};
     if (sgn > 0.0f) lcfft::stockham_run<+1, TWG>(sm, n, log2n, per_cta, src, dst);
     else            lcfft::stockham_run<-1, TWG>(sm, n, log2n, per_cta, src, dst);
+}
+
+// n = 64 ... 512: the tile transform of tile_fft.cuh (register DFTs, one instance barrier per 8 transforms) between global
+// memory and global memory; in place is fine (a tile's inputs are all read before any of its outputs is written)
+struct TileSrc {
+    const float2 *x;
+    unsigned int n;
+    __device__ __forceinline__ float2 load(long long t, unsigned int k) const { return __ldg(x + t * n + k); }
+    __device__ __forceinline__ float2 finish(long long, unsigned int, float2 raw) const { return raw; }
+};
+struct TileDst {
+    float2 *y;
+    unsigned int n;
+    int post_mode;
+    float pa, pb;
+    __device__ __forceinline__ void operator()(long long t, unsigned int k, float2 v) const
+    {
+        __stcs(y + t * n + k, fft_post(v, post_mode, pa, pb));
+    }
+};
+
+template <int M, int SIGN>
+__global__ void __launch_bounds__(lctile::kThreads, 2)
+fft_tile_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const float2 *__restrict__ tw, long long batch,
+                int tiles_per_inst, int post_mode, float pa, float pb)
+{
+    extern __shared__ __align__(16) unsigned char smem_tile[];
+    lctile::run<M, SIGN>(smem_tile, tw, batch, tiles_per_inst, TileSrc{x, (unsigned int)M}, TileDst{y, (unsigned int)M, post_mode, pa, pb});
+}
+
+template <int M, int SIGN>
+void launch_fft_tile(const float2 *d_x, float2 *d_y, const float2 *d_tw, unsigned long long batch, cudaStream_t st, int post_mode,
+                     float a, float b)
+{
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(fft_tile_kernel<M, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lctile::smem_bytes<M>()));
+    unsigned int grid = 0;
+    int tpi = 1;
+    lctile::plan(M, batch, grid, tpi);
+    fft_tile_kernel<M, SIGN><<<grid, lctile::kThreads, lctile::smem_bytes<M>(), st>>>(d_x, d_y, d_tw, (long long)batch, tpi, post_mode, a, b);
+}
+
+template <int M>
+void launch_fft_tile_M(int sign, const float2 *d_x, float2 *d_y, const float2 *d_tw, unsigned long long batch, cudaStream_t st,
+                       int post_mode, float a, float b)
+{
+    if (sign > 0) launch_fft_tile<M, +1>(d_x, d_y, d_tw, batch, st, post_mode, a, b);
+    else          launch_fft_tile<M, -1>(d_x, d_y, d_tw, batch, st, post_mode, a, b);
 }
 
 // table-driven DFT, one CTA per transform; smem: n float2
@@ -212,6 +262,12 @@ void FftPlanDev::init(unsigned int n_, int sign_)
     }
     if (first_time_on_device(configured_mixed))
         LC_CUDA_CHECK(cudaFuncSetAttribute(fft_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (lctile::supported(n)) {
+        std::vector<float2> twt;
+        lctile::make_twiddles(twt, n, sign);
+        LC_CUDA_CHECK(cudaMalloc(&d_tw_tile, sizeof(float2) * twt.size()));
+        LC_CUDA_CHECK(cudaMemcpy(d_tw_tile, twt.data(), sizeof(float2) * twt.size(), cudaMemcpyHostToDevice));
+    }
     if (is_pow2(n) && n >= 2) {
         const std::vector<float2> twp = lcfft::pass_ordered_twiddles(tw, n);
         LC_CUDA_CHECK(cudaMalloc(&d_twp, sizeof(float2) * n));
@@ -223,6 +279,8 @@ void FftPlanDev::destroy()
 {
     if (d_tw) cudaFree(d_tw);
     if (d_twp) cudaFree(d_twp);
+    if (d_tw_tile) cudaFree(d_tw_tile);
+    d_tw_tile = nullptr;
     d_tw = nullptr;
     d_twp = nullptr;
 }
@@ -234,6 +292,16 @@ void FftPlanDev::run(const float2 *d_x, float2 *d_y, unsigned long long batch, c
     if (n == 1) {
         // degenerate transform: copy (+ post) through the generic kernel
         dft_any_kernel<<<(unsigned int)batch, 32, sizeof(float2), st>>>(d_x, d_y, d_tw, 1, post_mode, a, b);
+        LC_LAUNCH_CHECK();
+        return;
+    }
+    if (d_tw_tile && batch < (1ull << 40) && !getenv("LIQUID_CUDA_FFT_NO_TILE") && !getenv("LIQUID_CUDA_NO_FUSED")) {
+        switch (n) {
+        case 64: launch_fft_tile_M<64>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
+        case 128: launch_fft_tile_M<128>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
+        case 256: launch_fft_tile_M<256>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
+        default: launch_fft_tile_M<512>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
+        }
         LC_LAUNCH_CHECK();
         return;
     }

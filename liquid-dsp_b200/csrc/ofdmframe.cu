@@ -23,6 +23,7 @@
 #include "host_pipeline.cuh"
 #include "fft_device.cuh"
 #include "ofdm_common.cuh"
+#include "tile_fft.cuh"
 
 struct ofdmframegen_s {
     unsigned int M = 0, cp_len = 0, taper_len = 0;
@@ -33,12 +34,13 @@ struct ofdmframegen_s {
     std::vector<lc_cf> S0, s0, S1, s1;
     unsigned int pilot_pos = 0;          // bits of the pilot sequence consumed so far, mod 255
     // device side
-    int *d_code = nullptr;               // [M] -1 null, -2 data, r >= 0: pilot number r of the traversal i -> k = (i + M/2) % M
+    int *d_code = nullptr;               // [M] -1 null, -2 data, r >= 0: pilot number (mod 255) of the traversal i -> k = (i + M/2) % M
     float *d_pil = nullptr;              // [255] pilot values +-g_data, from the register's reset state
     float *d_taper = nullptr;            // [taper_len]
     float2 *d_postfix = nullptr;         // [taper_len] first samples of the previous symbol
     float2 *d_s1 = nullptr;              // [M] long PLCP symbol (time)
     lc::FftPlanDev ifft;
+    float2 *d_tw_tile = nullptr;         // backward twiddles of the tile transform (M = 64 ... 512), or null
     lc::DevBuf stage_in, stage_out, scratch;
     cudaStream_t stream = nullptr;
 };
@@ -54,15 +56,24 @@ struct MapArgs {
     float g;
 };
 
-// frequency-domain value of subcarrier k of symbol s of the block (s_mod = s mod 255: all index arithmetic in 32 bits)
+// pilot-table position of the first pilot of a symbol: (pos + (s mod 255) n_pilot) mod 255 -- one integer division per
+// symbol and thread, not one per subcarrier (the mapping, not the transform, bounded the symbol kernels)
+__device__ __forceinline__ unsigned int pilot_base(const MapArgs &a, unsigned int s_mod)
+{
+    return (s_mod * a.npm + a.pos) % kPilotPeriod;
+}
+
+// frequency-domain value of subcarrier k of symbol s of the block
 __device__ __forceinline__ float2 map_subcarrier(const MapArgs &a, const float2 *__restrict__ x, unsigned long long s,
-                                                 unsigned int s_mod, unsigned int k)
+                                                 unsigned int base, unsigned int k)
 {
     // branch-free: every load is issued unconditionally (x holds M values per symbol, used or not), so the 16 element
     // fetches of a butterfly overlap instead of queueing behind each other's type test
     const int c = __ldg(a.code + k);
     const float2 v = __ldg(x + s * a.M + k);
-    const float pv = __ldg(a.pil + (s_mod * a.npm + a.pos + (unsigned int)(c > 0 ? c : 0)) % kPilotPeriod);
+    unsigned int idx = base + (unsigned int)(c > 0 ? c : 0);      // both terms < 255
+    idx = idx >= kPilotPeriod ? idx - kPilotPeriod : idx;
+    const float pv = __ldg(a.pil + idx);
     const float2 d = make_float2(v.x * a.g, v.y * a.g);
     return c == -2 ? d : make_float2(c >= 0 ? pv : 0.f, 0.f);
 }
@@ -75,7 +86,7 @@ struct SymbolSrc {
     __device__ __forceinline__ float2 operator()(unsigned int f, unsigned int k) const
     {
         const unsigned long long s = s0 + f;
-        return s < s_end ? map_subcarrier(a, x, s, (s0_mod + f) % kPilotPeriod, k) : make_float2(0.f, 0.f);
+        return s < s_end ? map_subcarrier(a, x, s, pilot_base(a, (s0_mod + f) % kPilotPeriod), k) : make_float2(0.f, 0.f);
     }
 };
 
@@ -101,6 +112,68 @@ struct PrefixDst {
         }
     }
 };
+
+// M = 64 ... 512: the tile transform of tile_fft.cuh between the subcarrier map and the prefix writer -- row DFTs out of
+// register-prefetched subcarrier values, column DFTs in a conflict-free shared tile, the last radix-2 stage in the thread
+// that writes body and tapered prefix; one instance barrier per tile of 8 symbols instead of a block barrier per pass
+struct SymbolSrcT {
+    MapArgs a;
+    const float2 *x;
+    // the user's value of the subcarrier, loaded a tile ahead and left alone until it is used
+    __device__ __forceinline__ float2 load(long long s, unsigned int k) const { return __ldg(x + s * a.M + k); }
+    // ofdmframegen.c:279-311 at the point of use: data scaled, pilots from the table, nulls zero (the type and pilot
+    // tables sit in L1).  32-bit remainder by a constant (the 64-bit one is a subroutine): n_sym < 2^31 here
+    __device__ __forceinline__ float2 finish(long long s, unsigned int k, float2 v) const
+    {
+        const int c = __ldg(a.code + k);
+        unsigned int idx = pilot_base(a, (unsigned int)s % kPilotPeriod) + (unsigned int)(c > 0 ? c : 0);
+        idx = idx >= kPilotPeriod ? idx - kPilotPeriod : idx;
+        const float pv = __ldg(a.pil + idx);
+        return c == -2 ? make_float2(v.x * a.g, v.y * a.g) : make_float2(c >= 0 ? pv : 0.f, 0.f);
+    }
+};
+struct PrefixDstT {
+    float2 *y;
+    const float *taper;
+    unsigned int M, cp, tl;
+    __device__ __forceinline__ void operator()(long long s, unsigned int k, float2 v) const
+    {
+        float2 *base = y + s * (M + cp);
+        __stcs(base + cp + k, v);
+        if (k >= M - cp) {
+            const unsigned int i = k - (M - cp);
+            if (i < tl) {
+                const float w = __ldg(taper + i);
+                v = make_float2(v.x * w, v.y * w);
+            }
+            base[i] = v;
+        }
+    }
+};
+
+template <int M>
+__global__ void __launch_bounds__(lctile::kThreads, 2)
+ofdm_symbols_tile_kernel(MapArgs a, const float2 *__restrict__ x, const float2 *__restrict__ tw, const float *__restrict__ taper,
+                         float2 *__restrict__ y, unsigned int cp, unsigned int tl, long long n_sym, int tiles_per_inst)
+{
+    extern __shared__ __align__(16) unsigned char smem_tile[];
+    lctile::run<M, +1>(smem_tile, tw, n_sym, tiles_per_inst, SymbolSrcT{a, x}, PrefixDstT{y, taper, (unsigned int)M, cp, tl});
+}
+
+template <int M>
+void launch_symbols_tile(const MapArgs &a, const float2 *d_x, const float2 *d_tw, const float *d_taper, float2 *d_y,
+                         unsigned int cp, unsigned int tl, unsigned long long n, cudaStream_t st)
+{
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(ofdm_symbols_tile_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)lctile::smem_bytes<M>()));
+    unsigned int grid = 0;
+    int tpi = 1;
+    lctile::plan(M, n, grid, tpi);
+    ofdm_symbols_tile_kernel<M><<<grid, lctile::kThreads, lctile::smem_bytes<M>(), st>>>(a, d_x, d_tw, d_taper, d_y, cp, tl,
+                                                                                         (long long)n, tpi);
+}
 
 template <bool TWG>
 __global__ void __launch_bounds__(lcfft::kFftThreads, 3)
@@ -145,7 +218,7 @@ ofdm_map_kernel(MapArgs a, const float2 *__restrict__ x, float2 *__restrict__ X,
          g += (unsigned long long)gridDim.x * blockDim.x)
     {
         const unsigned long long sy = g / a.M;
-        X[g] = map_subcarrier(a, x, sy, (unsigned int)(sy % kPilotPeriod), (unsigned int)(g % a.M));
+        X[g] = map_subcarrier(a, x, sy, pilot_base(a, (unsigned int)(sy % kPilotPeriod)), (unsigned int)(g % a.M));
     }
 }
 
@@ -193,7 +266,22 @@ void symbols_dev(ofdmframegen q, const float2 *d_x, unsigned long long n, float2
     if (n == 0) return;
     const MapArgs a{q->d_code, q->d_pil, q->M, q->M_pilot % kPilotPeriod, q->pilot_pos, q->g_data};
     const unsigned int M = q->M;
-    if (lcfft::pow2_in_smem(M) && !getenv("LIQUID_CUDA_OFDM_GENERIC")) {
+    if (q->d_tw_tile && n < (1ull << 31) && !getenv("LIQUID_CUDA_OFDM_GENERIC") && !getenv("LIQUID_CUDA_NO_FUSED")) {
+        // the pilot position of symbol s is (pos + (s mod 255) npm) mod 255 with s counted from the start of the block
+        switch (M) {
+        case 64: launch_symbols_tile<64>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
+        case 128: launch_symbols_tile<128>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
+        case 256: launch_symbols_tile<256>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
+        default: launch_symbols_tile<512>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
+        }
+        LC_LAUNCH_CHECK();
+        if (q->taper_len) {
+            ofdm_overlap_kernel<<<grid_for(n * q->taper_len), kThreads, 0, st>>>(d_y, q->d_postfix, q->d_taper, M, q->cp_len, q->taper_len, n);
+            LC_LAUNCH_CHECK();
+            LC_CUDA_CHECK(cudaMemcpyAsync(q->d_postfix, d_y + (n - 1) * (M + q->cp_len) + q->cp_len, sizeof(float2) * q->taper_len,
+                                          cudaMemcpyDeviceToDevice, st));
+        }
+    } else if (lcfft::pow2_in_smem(M) && !getenv("LIQUID_CUDA_OFDM_GENERIC")) {
         static std::atomic<unsigned long long> configured{0};
         if (lc::first_time_on_device(configured)) {
             LC_CUDA_CHECK(cudaFuncSetAttribute(ofdm_symbols_pow2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -310,12 +398,18 @@ ofdmframegen ofdmframegen_create(unsigned int _M, unsigned int _cp_len, unsigned
     }
     LC_CUDA_CHECK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
     q->ifft.init(_M, +1);
+    if (lctile::supported(_M)) {
+        std::vector<float2> tw;
+        lctile::make_twiddles(tw, _M, +1);
+        LC_CUDA_CHECK(cudaMalloc(&q->d_tw_tile, tw.size() * sizeof(float2)));
+        LC_CUDA_CHECK(cudaMemcpy(q->d_tw_tile, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
     // pilot traversal order (writesymbol walks i and fills k = (i + M/2) % M) and the 255 pilot values
     std::vector<int> code(_M, -1);
     int r = 0;
     for (unsigned int i = 0; i < _M; i++) {
         const unsigned int k = (i + _M / 2) % _M;
-        if (p[k] == OFDMFRAME_SCTYPE_PILOT) code[k] = r++;
+        if (p[k] == OFDMFRAME_SCTYPE_PILOT) code[k] = (int)(r++ % kPilotPeriod);   // the rank is only ever used mod 255
         else if (p[k] == OFDMFRAME_SCTYPE_DATA) code[k] = -2;
     }
     std::vector<float> pil(kPilotPeriod);
@@ -360,6 +454,7 @@ void ofdmframegen_destroy(ofdmframegen _q)
     cudaFree(_q->d_taper);
     cudaFree(_q->d_postfix);
     cudaFree(_q->d_s1);
+    cudaFree(_q->d_tw_tile);
     _q->stage_in.release();
     _q->stage_out.release();
     _q->scratch.release();
