@@ -16,6 +16,7 @@
 #include "fft_device.cuh"
 #include "fused_common.cuh"
 #include "tile_fft.cuh"
+#include "quad_fft.cuh"
 #include "../../include/liquid_cuda.h"
 
 namespace {
@@ -116,6 +117,38 @@ void launch_fft_tile_M(int sign, const float2 *d_x, float2 *d_y, const float2 *d
 {
     if (sign > 0) launch_fft_tile<M, +1>(d_x, d_y, d_tw, batch, st, post_mode, a, b);
     else          launch_fft_tile<M, -1>(d_x, d_y, d_tw, batch, st, post_mode, a, b);
+}
+
+// n = 1024 / 2048 / 4096: the quad transform of quad_fft.cuh (first radix-4 / 8 / 16 stage in the loading thread, then
+// sixteen 256-point problems per tile); in place is fine for the same reason
+template <int RA, int SIGN>
+__global__ void __launch_bounds__(lcquad::kThreads, 2)
+fft_quad_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, const float2 *__restrict__ tw, long long batch,
+                int tiles_per_inst, int post_mode, float pa, float pb)
+{
+    extern __shared__ __align__(16) unsigned char smem_quad[];
+    lcquad::run<RA, SIGN, false>(smem_quad, tw, batch, tiles_per_inst, TileSrc{x, 256u * RA}, TileDst{y, 256u * RA, post_mode, pa, pb});
+}
+
+template <int RA, int SIGN>
+void launch_fft_quad(const float2 *d_x, float2 *d_y, const float2 *d_tw, unsigned long long batch, cudaStream_t st, int post_mode,
+                     float a, float b)
+{
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(fft_quad_kernel<RA, SIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lcquad::smem_bytes<RA>()));
+    unsigned int grid = 0;
+    int tpi = 1;
+    lcquad::plan(RA, batch, grid, tpi);
+    fft_quad_kernel<RA, SIGN><<<grid, lcquad::kThreads, lcquad::smem_bytes<RA>(), st>>>(d_x, d_y, d_tw, (long long)batch, tpi, post_mode, a, b);
+}
+
+template <int RA>
+void launch_fft_quad_RA(int sign, const float2 *d_x, float2 *d_y, const float2 *d_tw, unsigned long long batch, cudaStream_t st,
+                        int post_mode, float a, float b)
+{
+    if (sign > 0) launch_fft_quad<RA, +1>(d_x, d_y, d_tw, batch, st, post_mode, a, b);
+    else          launch_fft_quad<RA, -1>(d_x, d_y, d_tw, batch, st, post_mode, a, b);
 }
 
 // table-driven DFT, one CTA per transform; smem: n float2
@@ -262,9 +295,10 @@ void FftPlanDev::init(unsigned int n_, int sign_)
     }
     if (first_time_on_device(configured_mixed))
         LC_CUDA_CHECK(cudaFuncSetAttribute(fft_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    if (lctile::supported(n)) {
+    if (lctile::supported(n) || lcquad::supported(n)) {
         std::vector<float2> twt;
-        lctile::make_twiddles(twt, n, sign);
+        if (lctile::supported(n)) lctile::make_twiddles(twt, n, sign);
+        else lcquad::make_twiddles(twt, n, sign);
         LC_CUDA_CHECK(cudaMalloc(&d_tw_tile, sizeof(float2) * twt.size()));
         LC_CUDA_CHECK(cudaMemcpy(d_tw_tile, twt.data(), sizeof(float2) * twt.size(), cudaMemcpyHostToDevice));
     }
@@ -300,7 +334,10 @@ void FftPlanDev::run(const float2 *d_x, float2 *d_y, unsigned long long batch, c
         case 64: launch_fft_tile_M<64>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
         case 128: launch_fft_tile_M<128>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
         case 256: launch_fft_tile_M<256>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
-        default: launch_fft_tile_M<512>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
+        case 512: launch_fft_tile_M<512>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
+        case 1024: launch_fft_quad_RA<4>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
+        case 2048: launch_fft_quad_RA<8>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
+        default: launch_fft_quad_RA<16>(sign, d_x, d_y, d_tw_tile, batch, st, post_mode, a, b); break;
         }
         LC_LAUNCH_CHECK();
         return;

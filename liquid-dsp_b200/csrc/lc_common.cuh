@@ -126,7 +126,7 @@ struct FftPlanDev {
     int sign = 0;              // -1 forward (e^{-j}), +1 backward (e^{+j})
     float2 *d_tw = nullptr;    // [n], device
     float2 *d_twp = nullptr;   // [n], device: the same values in the pass order of the shared-memory FFT (power-of-two n)
-    float2 *d_tw_tile = nullptr;   // n = 64 ... 512: the table of the tile transform (tile_fft.cuh)
+    float2 *d_tw_tile = nullptr;   // n = 64 ... 512: the table of the tile transform (tile_fft.cuh); n = 1024 ... 4096: of the quad transform (quad_fft.cuh)
     unsigned char radices[16] = {0};   // mixed-radix factorisation of a composite n (factors 2 ... 13), n_rad = 0: none
     unsigned int n_rad = 0;
     void init(unsigned int n_, int sign_);

@@ -24,6 +24,7 @@
 #include "fft_device.cuh"
 #include "ofdm_common.cuh"
 #include "tile_fft.cuh"
+#include "quad_fft.cuh"
 
 struct ofdmframegen_s {
     unsigned int M = 0, cp_len = 0, taper_len = 0;
@@ -40,7 +41,7 @@ struct ofdmframegen_s {
     float2 *d_postfix = nullptr;         // [taper_len] first samples of the previous symbol
     float2 *d_s1 = nullptr;              // [M] long PLCP symbol (time)
     lc::FftPlanDev ifft;
-    float2 *d_tw_tile = nullptr;         // backward twiddles of the tile transform (M = 64 ... 512), or null
+    float2 *d_tw_tile = nullptr;         // backward twiddles of the tile (M = 64 ... 512) or quad (M = 1024 ... 4096) transform, or null
     lc::DevBuf stage_in, stage_out, scratch;
     cudaStream_t stream = nullptr;
 };
@@ -175,6 +176,31 @@ void launch_symbols_tile(const MapArgs &a, const float2 *d_x, const float2 *d_tw
                                                                                          (long long)n, tpi);
 }
 
+// M = 1024 / 2048 / 4096: the quad transform of quad_fft.cuh between the same two functors
+template <int RA>
+__global__ void __launch_bounds__(lcquad::kThreads, 2)
+ofdm_symbols_quad_kernel(MapArgs a, const float2 *__restrict__ x, const float2 *__restrict__ tw, const float *__restrict__ taper,
+                         float2 *__restrict__ y, unsigned int cp, unsigned int tl, long long n_sym, int tiles_per_inst)
+{
+    extern __shared__ __align__(16) unsigned char smem_quad[];
+    lcquad::run<RA, +1, (RA >= 8)>(smem_quad, tw, n_sym, tiles_per_inst, SymbolSrcT{a, x}, PrefixDstT{y, taper, 256u * RA, cp, tl});
+}
+
+template <int RA>
+void launch_symbols_quad(const MapArgs &a, const float2 *d_x, const float2 *d_tw, const float *d_taper, float2 *d_y,
+                         unsigned int cp, unsigned int tl, unsigned long long n, cudaStream_t st)
+{
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(ofdm_symbols_quad_kernel<RA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)lcquad::smem_bytes<RA>()));
+    unsigned int grid = 0;
+    int tpi = 1;
+    lcquad::plan(RA, n, grid, tpi);
+    ofdm_symbols_quad_kernel<RA><<<grid, lcquad::kThreads, lcquad::smem_bytes<RA>(), st>>>(a, d_x, d_tw, d_taper, d_y, cp, tl,
+                                                                                           (long long)n, tpi);
+}
+
 template <bool TWG>
 __global__ void __launch_bounds__(lcfft::kFftThreads, 3)
 ofdm_symbols_pow2_kernel(MapArgs a, const float2 *__restrict__ x, const float2 *__restrict__ tw, const float *__restrict__ taper,
@@ -272,7 +298,10 @@ void symbols_dev(ofdmframegen q, const float2 *d_x, unsigned long long n, float2
         case 64: launch_symbols_tile<64>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
         case 128: launch_symbols_tile<128>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
         case 256: launch_symbols_tile<256>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
-        default: launch_symbols_tile<512>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
+        case 512: launch_symbols_tile<512>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
+        case 1024: launch_symbols_quad<4>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
+        case 2048: launch_symbols_quad<8>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
+        default: launch_symbols_quad<16>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
         }
         LC_LAUNCH_CHECK();
         if (q->taper_len) {
@@ -398,9 +427,10 @@ ofdmframegen ofdmframegen_create(unsigned int _M, unsigned int _cp_len, unsigned
     }
     LC_CUDA_CHECK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
     q->ifft.init(_M, +1);
-    if (lctile::supported(_M)) {
+    if (lctile::supported(_M) || lcquad::supported(_M)) {
         std::vector<float2> tw;
-        lctile::make_twiddles(tw, _M, +1);
+        if (lctile::supported(_M)) lctile::make_twiddles(tw, _M, +1);
+        else lcquad::make_twiddles(tw, _M, +1);
         LC_CUDA_CHECK(cudaMalloc(&q->d_tw_tile, tw.size() * sizeof(float2)));
         LC_CUDA_CHECK(cudaMemcpy(q->d_tw_tile, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     }

@@ -590,6 +590,26 @@ def test_fft_composite_sizes_mixed_radix_vs_numpy(L, orc, monkeypatch, n):
         assert np.abs(yb - yd).max() / np.abs(yd).max() < 3e-6
 
 
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_fft_tile_and_quad_transforms_long_ragged_batches(L, orc, monkeypatch, n):
+    """n = 64 ... 512 run the tile transform (tile_fft.cuh), n = 1024 ... 4096 the quad transform (quad_fft.cuh): batches
+    long enough that an instance walks several tiles (both tile buffers, the register prefetch) and ragged against the tile
+    size, both directions against numpy in double and against the shared-memory Stockham kernel they replace"""
+    per_tile = 8 if n <= 512 else 4096 // n
+    for nb in (1, per_tile + 1, (10_000_000 // n) | 1):      # the long one: 10 M points, an odd number of transforms
+        x = orc.synth_input(n * nb, seed=270 + n + nb)
+        xin, yout = x[:n].copy(), np.empty(n, np.complex64)
+        for d, np_fft in ((L.LIQUID_FFT_FORWARD, np.fft.fft), (L.LIQUID_FFT_BACKWARD, lambda a, axis=-1: np.fft.ifft(a, axis=axis) * n)):
+            p = L.fftplan(n, xin, yout, d)
+            yb = p.execute_batch(x)
+            want = np_fft(x.reshape(nb, n).astype(np.complex128), axis=1).reshape(-1)
+            assert np.abs(yb - want).max() / np.abs(want).max() < 2e-6, (n, nb, d)
+            monkeypatch.setenv("LIQUID_CUDA_FFT_NO_TILE", "1")
+            ys = p.execute_batch(x)
+            monkeypatch.delenv("LIQUID_CUDA_FFT_NO_TILE")
+            assert np.abs(yb - ys).max() / np.abs(want).max() < 2e-6, (n, nb, d)
+
+
 @pytest.mark.parametrize("n", [16384, 25600])
 def test_fft_large_sizes_on_the_table_driven_path(L, orc, n):
     """sizes that fit neither the shared-memory FFTs nor the mixed-radix buffers still transform (O(n^2), 200 KB of

@@ -354,7 +354,7 @@ def run(configs, steps, warmup, sink, device_index=0):
         n_s = 1 << 27
         x = torch.empty(2 * n_s, dtype=torch.float32, device=dev)
         L.synth_input_dev(x.data_ptr(), n_s, stream=st.cuda_stream)
-        for M, cp, tl in ((64, 16, 4), (256, 32, 8), (512, 64, 8), (1024, 128, 16), (4096, 512, 64)):
+        for M, cp, tl in ((64, 16, 4), (256, 32, 8), (512, 64, 8), (1024, 128, 16), (2048, 256, 32), (4096, 512, 64)):
             y = torch.empty(2 * (n_s // M) * (M + cp), dtype=torch.float32, device=dev)
             q = L.ofdmframegen(M, cp, tl)
             ms, ln = timed(lambda: q.writesymbols_dev(x.data_ptr(), n_s // M, y.data_ptr(), st.cuda_stream))
@@ -392,7 +392,7 @@ def run(configs, steps, warmup, sink, device_index=0):
     if "fft" in args.configs:
         # a11: the batched complex FFT on its own (fft_execute_batch_dev), 2^28 points per step, out of place
         import numpy as np
-        for nn in (16, 64, 128, 256, 512, 1024, 4096):
+        for nn in (4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192):
             n = 1 << 28
             x = torch.empty(2 * n, dtype=torch.float32, device=dev)
             y = torch.empty(2 * n, dtype=torch.float32, device=dev)
