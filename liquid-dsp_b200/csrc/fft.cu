@@ -119,6 +119,69 @@ void launch_fft_tile_M(int sign, const float2 *d_x, float2 *d_y, const float2 *d
     else          launch_fft_tile<M, -1>(d_x, d_y, d_tw, batch, st, post_mode, a, b);
 }
 
+// n = 4 / 8 / 16 / 32: one thread per transform, a warp per 32 consecutive transforms.  Read by the thread itself, a transform is
+// 8 n bytes at a stride of 8 n: every load instruction of the warp touched 32 lines (n = 16: 0.31 of the roofline).  Here
+// the warp moves its 32 n points with 128-bit accesses in stream order and the threads pick their rows out of a padded
+// per-warp staging tile (row pitch n + 1 units: the row reads are conflict-free); same path back.  No block barrier.
+template <int N> struct SmallCfg { static constexpr int WPC = N == 32 ? 4 : 8; };      // warps per CTA (static shared memory < 48 KB)
+template <int N, int SIGN>
+__global__ void __launch_bounds__(32 * SmallCfg<N>::WPC)
+fft_small_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, unsigned long long batch, int post_mode, float pa, float pb)
+{
+    constexpr int PITCH = N + 1, PER_LANE = N / 2;                    // float4 (two points) per lane per chunk
+    constexpr int WPC = SmallCfg<N>::WPC;
+    __shared__ float2 stage[WPC][32 * PITCH];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    float2 *st = stage[wl];
+    const unsigned long long n_chunks = (batch + 31) / 32, total = batch * N;
+    const unsigned long long w0 = (unsigned long long)blockIdx.x * WPC + wl, wstep = (unsigned long long)gridDim.x * WPC;
+    for (unsigned long long ch = w0; ch < n_chunks; ch += wstep) {
+        const unsigned long long base = ch * 32 * N;                   // first point of the chunk
+        const float4 *x4 = reinterpret_cast<const float4 *>(x + base);
+        float4 in[PER_LANE];
+#pragma unroll
+        for (int j = 0; j < PER_LANE; j++) {
+            const int i = j * 32 + lane;                               // float4 index inside the chunk
+            in[j] = base + 2ull * i < total ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < PER_LANE; j++) {
+            const int pnt = 2 * (j * 32 + lane);
+            float2 *d = st + (pnt / N) * PITCH + (pnt % N);
+            d[0] = make_float2(in[j].x, in[j].y);
+            d[1] = make_float2(in[j].z, in[j].w);
+        }
+        __syncwarp();
+        float2 v[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) v[k] = st[lane * PITCH + k];
+        lcf::RegDft<N, SIGN>::run(v);
+#pragma unroll
+        for (int k = 0; k < N; k++) st[lane * PITCH + k] = fft_post(v[k], post_mode, pa, pb);
+        __syncwarp();
+        float4 *y4 = reinterpret_cast<float4 *>(y + base);
+#pragma unroll
+        for (int j = 0; j < PER_LANE; j++) {
+            const int i = j * 32 + lane, pnt = 2 * i;
+            const float2 *sp = st + (pnt / N) * PITCH + (pnt % N);
+            const float2 a = sp[0], b = sp[1];
+            if (base + 2ull * i < total) __stcs(y4 + i, make_float4(a.x, a.y, b.x, b.y));
+        }
+        __syncwarp();
+    }
+}
+
+template <int N>
+void launch_fft_small(int sign, const float2 *d_x, float2 *d_y, unsigned long long batch, cudaStream_t st, int post_mode, float a, float b)
+{
+    const unsigned long long n_chunks = (batch + 31) / 32;
+    constexpr int WPC = SmallCfg<N>::WPC;
+    unsigned long long ctas = (n_chunks + WPC - 1) / WPC;
+    if (ctas > 148ull * 8 * 4) ctas = 148ull * 8 * 4;
+    if (sign > 0) fft_small_kernel<N, +1><<<(unsigned int)ctas, 32 * WPC, 0, st>>>(d_x, d_y, batch, post_mode, a, b);
+    else          fft_small_kernel<N, -1><<<(unsigned int)ctas, 32 * WPC, 0, st>>>(d_x, d_y, batch, post_mode, a, b);
+}
+
 // n = 1024 / 2048 / 4096: the quad transform of quad_fft.cuh (first radix-4 / 8 / 16 stage in the loading thread, then
 // sixteen 256-point problems per tile); in place is fine for the same reason
 template <int RA, int SIGN>
@@ -326,6 +389,15 @@ void FftPlanDev::run(const float2 *d_x, float2 *d_y, unsigned long long batch, c
     if (n == 1) {
         // degenerate transform: copy (+ post) through the generic kernel
         dft_any_kernel<<<(unsigned int)batch, 32, sizeof(float2), st>>>(d_x, d_y, d_tw, 1, post_mode, a, b);
+        LC_LAUNCH_CHECK();
+        return;
+    }
+    if ((n == 4 || n == 8 || n == 16 || n == 32) && (((uintptr_t)d_x | (uintptr_t)d_y) & 15) == 0 && !getenv("LIQUID_CUDA_FFT_NO_TILE") &&
+        !getenv("LIQUID_CUDA_NO_FUSED")) {
+        if (n == 4) launch_fft_small<4>(sign, d_x, d_y, batch, st, post_mode, a, b);
+        else if (n == 8) launch_fft_small<8>(sign, d_x, d_y, batch, st, post_mode, a, b);
+        else if (n == 16) launch_fft_small<16>(sign, d_x, d_y, batch, st, post_mode, a, b);
+        else launch_fft_small<32>(sign, d_x, d_y, batch, st, post_mode, a, b);
         LC_LAUNCH_CHECK();
         return;
     }

@@ -590,12 +590,13 @@ def test_fft_composite_sizes_mixed_radix_vs_numpy(L, orc, monkeypatch, n):
         assert np.abs(yb - yd).max() / np.abs(yd).max() < 3e-6
 
 
-@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
 def test_fft_tile_and_quad_transforms_long_ragged_batches(L, orc, monkeypatch, n):
-    """n = 64 ... 512 run the tile transform (tile_fft.cuh), n = 1024 ... 4096 the quad transform (quad_fft.cuh): batches
+    """n = 4 ... 32 run one thread per transform behind a per-warp staging tile (fft_small_kernel),
+    n = 64 ... 512 run the tile transform (tile_fft.cuh), n = 1024 ... 4096 the quad transform (quad_fft.cuh): batches
     long enough that an instance walks several tiles (both tile buffers, the register prefetch) and ragged against the tile
     size, both directions against numpy in double and against the shared-memory Stockham kernel they replace"""
-    per_tile = 8 if n <= 512 else 4096 // n
+    per_tile = 32 if n <= 32 else 8 if n <= 512 else 4096 // n
     for nb in (1, per_tile + 1, (10_000_000 // n) | 1):      # the long one: 10 M points, an odd number of transforms
         x = orc.synth_input(n * nb, seed=270 + n + nb)
         xin, yout = x[:n].copy(), np.empty(n, np.complex64)
