@@ -310,7 +310,7 @@ namespace pfb {
 
 bool fused_pfbch2_supported(unsigned int M, unsigned int L)
 {
-    return M == 1024 && (L == 4 || L == 8 || L == 10 || L == 14);
+    return M == 1024 && (L == 4 || L == 6 || L == 8 || L == 10 || L == 12 || L == 14);
 }
 
 void fused_pfbch2_make_twiddles(std::vector<float2> &tw)
@@ -375,8 +375,10 @@ long long launch_pfbch2_fused(const float2 *d_hist, const float2 *d_x, int H, co
 #endif
     switch (L) {
     case 4: launch_L<4>(a, parity0 & 1, (unsigned int)ctas, st); break;
+    case 6: launch_L<6>(a, parity0 & 1, (unsigned int)ctas, st); break;
     case 8: launch_L<8>(a, parity0 & 1, (unsigned int)ctas, st); break;
     case 10: launch_L<10>(a, parity0 & 1, (unsigned int)ctas, st); break;
+    case 12: launch_L<12>(a, parity0 & 1, (unsigned int)ctas, st); break;
     case 14: launch_L<14>(a, parity0 & 1, (unsigned int)ctas, st); break;
     default: fatal("launch_pfbch2_fused", "unsupported tap count");
     }

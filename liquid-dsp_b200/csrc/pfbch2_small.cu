@@ -506,8 +506,10 @@ void launch_analyzer_M(const SmallArgs &a, unsigned int L, unsigned int grid, cu
 {
     switch (L) {
     case 4: launch_analyzer_ML<M, 4>(a, grid, st); break;
+    case 6: launch_analyzer_ML<M, 6>(a, grid, st); break;
     case 8: launch_analyzer_ML<M, 8>(a, grid, st); break;
     case 10: launch_analyzer_ML<M, 10>(a, grid, st); break;
+    case 12: launch_analyzer_ML<M, 12>(a, grid, st); break;
     default: lc::fatal("launch_pfbch2_small", "unsupported tap count");
     }
 }
@@ -529,6 +531,7 @@ void launch_synth_M(const SmallArgs &a, unsigned int NT, unsigned int grid, cuda
 {
     switch (NT) {
     case 8: launch_synth_MN<M, 8>(a, grid, st); break;
+    case 12: launch_synth_MN<M, 12>(a, grid, st); break;
     case 16: launch_synth_MN<M, 16>(a, grid, st); break;
     default: lc::fatal("launch_pfbch2_small_synth", "unsupported tap count");
     }
@@ -541,12 +544,12 @@ namespace pfb {
 
 bool small_pfbch2_supported(unsigned int M, unsigned int L)
 {
-    return (M == 4 || M == 8 || M == 16 || M == 32) && (L == 4 || L == 8 || L == 10);
+    return (M == 4 || M == 8 || M == 16 || M == 32) && (L == 4 || L == 6 || L == 8 || L == 10 || L == 12);
 }
 
 bool small_pfbch_supported(unsigned int M, unsigned int p)
 {
-    return (M == 4 || M == 8 || M == 32) && (p == 4 || p == 8 || p == 10);
+    return (M == 4 || M == 8 || M == 32) && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12);
 }
 
 long long launch_pfbch_small(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, float2 *d_y, unsigned int M,
@@ -565,8 +568,10 @@ long long launch_pfbch_small(const float2 *d_hist, const float2 *d_x, int H, con
     if (M == 4) {
         dim3 g((unsigned int)((n_frames + kThreads - 1) / kThreads), n_streams, 1);
         if (p == 4) pfbch_frame4_kernel<4><<<g, kThreads, 0, st>>>(a);
+        else if (p == 6) pfbch_frame4_kernel<6><<<g, kThreads, 0, st>>>(a);
         else if (p == 8) pfbch_frame4_kernel<8><<<g, kThreads, 0, st>>>(a);
-        else pfbch_frame4_kernel<10><<<g, kThreads, 0, st>>>(a);
+        else if (p == 10) pfbch_frame4_kernel<10><<<g, kThreads, 0, st>>>(a);
+        else pfbch_frame4_kernel<12><<<g, kThreads, 0, st>>>(a);
         LC_LAUNCH_CHECK();
         return (long long)n_frames;
     }
@@ -580,11 +585,15 @@ long long launch_pfbch_small(const float2 *d_hist, const float2 *d_x, int H, con
     dim3 grid((unsigned int)((n_inst + inst_per_cta - 1) / inst_per_cta), n_streams, 1);
 #define LC_PFB(MM, PP) launch_pfb_small_MP<MM, PP>(a, grid, st)
     if (M == 8 && p == 4) LC_PFB(8, 4);
+    else if (M == 8 && p == 6) LC_PFB(8, 6);
     else if (M == 8 && p == 8) LC_PFB(8, 8);
     else if (M == 8 && p == 10) LC_PFB(8, 10);
+    else if (M == 8 && p == 12) LC_PFB(8, 12);
     else if (M == 32 && p == 4) LC_PFB(32, 4);
+    else if (M == 32 && p == 6) LC_PFB(32, 6);
     else if (M == 32 && p == 8) LC_PFB(32, 8);
     else if (M == 32 && p == 10) LC_PFB(32, 10);
+    else if (M == 32 && p == 12) LC_PFB(32, 12);
     else fatal("launch_pfbch_small", "unsupported shape");
 #undef LC_PFB
     LC_LAUNCH_CHECK();
@@ -593,7 +602,7 @@ long long launch_pfbch_small(const float2 *d_hist, const float2 *d_x, int H, con
 
 bool small_pfbch2_synth_supported(unsigned int M, unsigned int n_taps)
 {
-    return (M == 4 || M == 8 || M == 16 || M == 32) && (n_taps == 8 || n_taps == 16);
+    return (M == 4 || M == 8 || M == 16 || M == 32) && (n_taps == 8 || n_taps == 12 || n_taps == 16);
 }
 
 long long launch_pfbch2_small(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps_scaled, float2 *d_y,
@@ -614,8 +623,10 @@ long long launch_pfbch2_small(const float2 *d_hist, const float2 *d_x, int H, co
         const unsigned int g = (unsigned int)((n_frames + kThreads - 1) / kThreads);
 #define LC_FRAME(MM, LL) pfbch2_frame_kernel<MM, LL><<<g, kThreads, 0, st>>>(a)
         if (L == 4) LC_FRAME(4, 4);
+        else if (L == 6) LC_FRAME(4, 6);
         else if (L == 8) LC_FRAME(4, 8);
         else if (L == 10) LC_FRAME(4, 10);
+        else if (L == 12) LC_FRAME(4, 12);
         else fatal("launch_pfbch2_small", "unsupported shape");
 #undef LC_FRAME
         LC_LAUNCH_CHECK();
@@ -651,6 +662,7 @@ long long launch_pfbch2_small_synth(const float2 *d_hist_rows, int hist_rows, co
         const unsigned int g = (unsigned int)((n_frames + kThreads - 1) / kThreads);
 #define LC_FRAME(MM, NN) pfbch2_frame_synth_kernel<MM, NN><<<g, kThreads, 0, st>>>(a)
         if (n_taps == 8) LC_FRAME(4, 8);
+        else if (n_taps == 12) LC_FRAME(4, 12);
         else if (n_taps == 16) LC_FRAME(4, 16);
         else fatal("launch_pfbch2_small_synth", "unsupported shape");
 #undef LC_FRAME

@@ -431,8 +431,10 @@ void launch_pfb_M(const PfbTileArgs &a, unsigned int P, dim3 grid, cudaStream_t 
 {
     switch (P) {
     case 4: launch_pfb_MP<M, 4, TapT>(a, grid, st); break;
+    case 6: launch_pfb_MP<M, 6, TapT>(a, grid, st); break;
     case 8: launch_pfb_MP<M, 8, TapT>(a, grid, st); break;
     case 10: launch_pfb_MP<M, 10, TapT>(a, grid, st); break;
+    case 12: launch_pfb_MP<M, 12, TapT>(a, grid, st); break;
     default: lc::fatal("launch_pfbch_tile", "unsupported tap count");
     }
 }
@@ -976,8 +978,10 @@ void launch_synth_M(const SynthArgs &a, unsigned int NT, int par0, unsigned int 
 {
     switch (NT) {
     case 8: launch_synth_MN<M, 8>(a, par0, grid, st); break;
+    case 12: launch_synth_MN<M, 12>(a, par0, grid, st); break;
     case 16: launch_synth_MN<M, 16>(a, par0, grid, st); break;
     case 20: launch_synth_MN<M, 20>(a, par0, grid, st); break;
+    case 24: launch_synth_MN<M, 24>(a, par0, grid, st); break;
     default: lc::fatal("launch_pfbch2_tile_synth", "unsupported tap count");
     }
 }
@@ -997,8 +1001,10 @@ void launch_M(const TileArgs &a, unsigned int L, unsigned int grid, cudaStream_t
 {
     switch (L) {
     case 4: launch_ML<M, 4>(a, grid, st); break;
+    case 6: launch_ML<M, 6>(a, grid, st); break;
     case 8: launch_ML<M, 8>(a, grid, st); break;
     case 10: launch_ML<M, 10>(a, grid, st); break;
+    case 12: launch_ML<M, 12>(a, grid, st); break;
     case 14: launch_ML<M, 14>(a, grid, st); break;
     default: lc::fatal("launch_pfbch2_tile", "unsupported tap count");
     }
@@ -1011,7 +1017,7 @@ namespace pfb {
 
 bool tile_pfbch2_supported(unsigned int M, unsigned int L)
 {
-    return (M == 64 || M == 128 || M == 256 || M == 512) && (L == 4 || L == 8 || L == 10 || L == 14);
+    return (M == 64 || M == 128 || M == 256 || M == 512) && (L == 4 || L == 6 || L == 8 || L == 10 || L == 12 || L == 14);
 }
 
 void tile_pfbch2_make_twiddles(std::vector<float2> &tw, unsigned int M)
@@ -1033,7 +1039,7 @@ void tile_pfbch2_make_twiddles(std::vector<float2> &tw, unsigned int M)
 bool tile_pfbch_supported(unsigned int M, unsigned int p)
 {
     // (M = 256 stays on pfbch_fused_256_kernel: this kernel measured 0.91 against 0.90 at p = 4 but 0.74 against 0.87 at p = 10)
-    return (M == 64 || M == 128 || M == 512) && (p == 4 || p == 8 || p == 10);
+    return ((M == 64 || M == 128 || M == 512) && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12)) || (M == 256 && (p == 6 || p == 8 || p == 12));
 }
 
 void tile_pfbch_make_twiddles(std::vector<float2> &tw, unsigned int M)
@@ -1070,8 +1076,8 @@ long long launch_pfbch_tile_T(const float2 *d_hist, const float2 *d_x, int H, co
     case 64: launch_pfb_M<64, TapT>(a, p, grid, st); break;
     case 128: launch_pfb_M<128, TapT>(a, p, grid, st); break;
     case 256:
-        if (sizeof(TapT) == 8) { launch_pfb_M<256, float2>(a, p, grid, st); break; }
-        lc::fatal("launch_pfbch_tile", "unsupported channel count");
+        launch_pfb_M<256, TapT>(a, p, grid, st);
+        break;
     case 512: launch_pfb_M<512, TapT>(a, p, grid, st); break;
     default: lc::fatal("launch_pfbch_tile", "unsupported channel count");
     }
@@ -1089,7 +1095,7 @@ long long launch_pfbch_tile(const float2 *d_hist, const float2 *d_x, int H, cons
 
 bool tile_pfbch_cc_supported(unsigned int M, unsigned int p)
 {
-    return (M == 64 || M == 128 || M == 256 || M == 512) && (p == 4 || p == 8 || p == 10);
+    return (M == 64 || M == 128 || M == 256 || M == 512) && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12);
 }
 
 long long launch_pfbch_tile_cc(const float2 *d_hist, const float2 *d_x, int H, const float2 *d_taps, const float2 *d_tw,
@@ -1100,7 +1106,7 @@ long long launch_pfbch_tile_cc(const float2 *d_hist, const float2 *d_x, int H, c
 
 bool tile_pfbch_synth_supported(unsigned int M, unsigned int p)
 {
-    return (M == 64 || M == 128 || M == 512) && (p == 4 || p == 8 || p == 10);
+    return (M == 64 || M == 128 || M == 512) && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12);
 }
 
 template <int M, int P>
@@ -1118,8 +1124,10 @@ void launch_pfb_synth_M(const PfbSynthArgs &a, unsigned int p, dim3 grid, cudaSt
 {
     switch (p) {
     case 4: launch_pfb_synth_MP<M, 4>(a, grid, st); break;
+    case 6: launch_pfb_synth_MP<M, 6>(a, grid, st); break;
     case 8: launch_pfb_synth_MP<M, 8>(a, grid, st); break;
     case 10: launch_pfb_synth_MP<M, 10>(a, grid, st); break;
+    case 12: launch_pfb_synth_MP<M, 12>(a, grid, st); break;
     default: lc::fatal("launch_pfbch_tile_synth", "unsupported tap count");
     }
 }
@@ -1158,8 +1166,8 @@ long long launch_pfbch_tile_synth(const float2 *d_hist_rows, int hist_rows, cons
 
 bool tile_pfbch2_synth_supported(unsigned int M, unsigned int n_taps)
 {
-    return ((M == 64 || M == 128 || M == 256 || M == 512) && (n_taps == 8 || n_taps == 16 || n_taps == 20)) ||
-           (M == 1024 && (n_taps == 8 || n_taps == 16));
+    return ((M == 64 || M == 128 || M == 256 || M == 512) && (n_taps == 8 || n_taps == 12 || n_taps == 16 || n_taps == 20 || n_taps == 24)) ||
+           (M == 1024 && (n_taps == 8 || n_taps == 12 || n_taps == 16));
 }
 
 void tile_pfbch2_synth_make_twiddles(std::vector<float2> &tw, unsigned int M)
@@ -1206,6 +1214,7 @@ long long launch_pfbch2_tile_synth(const float2 *d_hist_rows, int hist_rows, con
         a.tiles_per_inst = (int)tpi;
         const unsigned int grid = (unsigned int)((n_tiles + tpi - 1) / tpi);
         if (n_taps == 8) launch_quad_synth_N<8>(a, parity0 & 1, grid, st);
+        else if (n_taps == 12) launch_quad_synth_N<12>(a, parity0 & 1, grid, st);
         else if (n_taps == 16) launch_quad_synth_N<16>(a, parity0 & 1, grid, st);
         else fatal("launch_pfbch2_tile_synth", "unsupported tap count");
         LC_LAUNCH_CHECK();

@@ -599,13 +599,14 @@ namespace pfb {
 
 bool fused_pfbch_supported(unsigned int M, unsigned int p)
 {
-    return (M == 16 && (p == 4 || p == 8)) || (M == 256 && (p == 4 || p == 10)) || tile_pfbch_supported(M, p) || small_pfbch_supported(M, p) ||
-           (M == 1024 && (p == 4 || p == 8 || p == 10));
+    return (M == 16 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12)) || (M == 256 && (p == 4 || p == 10)) || tile_pfbch_supported(M, p) ||
+           small_pfbch_supported(M, p) || (M == 1024 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12));
 }
 
 bool fused_pfbch_synth_supported(unsigned int M, unsigned int p)
 {
-    return (M == 256 && (p == 4 || p == 10)) || (M == 1024 && (p == 4 || p == 8 || p == 10)) || tile_pfbch_synth_supported(M, p);
+    return (M == 256 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12)) || (M == 1024 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12)) ||
+           tile_pfbch_synth_supported(M, p);
 }
 
 void fused_pfbch_make_twiddles(std::vector<float2> &tw, int sign, unsigned int M, unsigned int p)
@@ -672,8 +673,10 @@ long long launch_pfbch_fused(const float2 *d_hist, const float2 *d_x, int H, con
         dim3 grid((unsigned int)((nq + tpi - 1) / tpi), n_streams, 1);
         switch (p) {
         case 4: launch_quad_P<4>(q, grid, st); break;
+        case 6: launch_quad_P<6>(q, grid, st); break;
         case 8: launch_quad_P<8>(q, grid, st); break;
         case 10: launch_quad_P<10>(q, grid, st); break;
+        case 12: launch_quad_P<12>(q, grid, st); break;
         default: fatal("launch_pfbch_fused", "unsupported shape");
         }
         LC_LAUNCH_CHECK();
@@ -699,7 +702,10 @@ long long launch_pfbch_fused(const float2 *d_hist, const float2 *d_x, int H, con
     const long long n_inst = (n_tiles + tpi - 1) / tpi;
     dim3 grid((unsigned int)((n_inst + inst_per_cta - 1) / inst_per_cta), n_streams, 1);
     if (M == 16 && p == 4) pfbch_fused_16_kernel<4><<<grid, kThreads, 0, st>>>(a);
+    else if (M == 16 && p == 6) pfbch_fused_16_kernel<6><<<grid, kThreads, 0, st>>>(a);
     else if (M == 16 && p == 8) pfbch_fused_16_kernel<8><<<grid, kThreads, 0, st>>>(a);
+    else if (M == 16 && p == 10) pfbch_fused_16_kernel<10><<<grid, kThreads, 0, st>>>(a);
+    else if (M == 16 && p == 12) pfbch_fused_16_kernel<12><<<grid, kThreads, 0, st>>>(a);
     else if (M == 256 && p == 4) pfbch_fused_256_kernel<4><<<grid, kThreads, 0, st>>>(a);
     else if (M == 256 && p == 10) pfbch_fused_256_kernel<10><<<grid, kThreads, 0, st>>>(a);
     else fatal("launch_pfbch_fused", "unsupported shape");
@@ -732,8 +738,10 @@ long long launch_pfbch_synth_fused(const float2 *d_hist_rows, int n_hist_rows, c
         dim3 grid((unsigned int)((nq + tpi - 1) / tpi), n_streams, 1);
         switch (p) {
         case 4: launch_quad_synth_P<4>(q, (long long)n_frames, grid, st); break;
+        case 6: launch_quad_synth_P<6>(q, (long long)n_frames, grid, st); break;
         case 8: launch_quad_synth_P<8>(q, (long long)n_frames, grid, st); break;
         case 10: launch_quad_synth_P<10>(q, (long long)n_frames, grid, st); break;
+        case 12: launch_quad_synth_P<12>(q, (long long)n_frames, grid, st); break;
         default: fatal("launch_pfbch_synth_fused", "unsupported shape");
         }
         LC_LAUNCH_CHECK();
@@ -755,6 +763,9 @@ long long launch_pfbch_synth_fused(const float2 *d_hist_rows, int n_hist_rows, c
     a.tiles_per_inst = (int)tpi;
     dim3 grid((unsigned int)((n_tiles + tpi - 1) / tpi), n_streams, 1);
     if (p == 4) pfbch_synth_fused_256_kernel<4><<<grid, kThreads, 0, st>>>(a);
+    else if (p == 6) pfbch_synth_fused_256_kernel<6><<<grid, kThreads, 0, st>>>(a);
+    else if (p == 8) pfbch_synth_fused_256_kernel<8><<<grid, kThreads, 0, st>>>(a);
+    else if (p == 12) pfbch_synth_fused_256_kernel<12><<<grid, kThreads, 0, st>>>(a);
     else if (p == 10) pfbch_synth_fused_256_kernel<10><<<grid, kThreads, 0, st>>>(a);
     else fatal("launch_pfbch_synth_fused", "unsupported shape");
     LC_LAUNCH_CHECK();

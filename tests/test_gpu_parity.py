@@ -780,7 +780,7 @@ def test_pfbch2_small_synthesizer_vs_oracle_odd_splits_and_generic(L, orc, monke
     assert flag == flag3 and np.abs(hist - hist3).max() / max(np.abs(hist).max(), 1e-30) < 2e-6
 
 
-@pytest.mark.parametrize("M,p", [(64, 4), (64, 10), (128, 8), (256, 10), (256, 4), (512, 10), (512, 4)])
+@pytest.mark.parametrize("M,p", [(64, 4), (64, 10), (128, 8), (256, 10), (256, 4), (512, 10), (512, 4), (64, 6), (128, 12), (256, 6), (512, 12)])
 def test_pfbch_cccf_complex_taps_tile_analyzer(L, orc, monkeypatch, M, p):
     """firpfbch_cccf analysis with complex taps on the tile kernel (two packed FFMA2 per tap): against the oracle with the
     state carried over awkward cuts (incl. single frames), and against the shape-generic complex-tap kernels"""
@@ -801,13 +801,14 @@ def test_pfbch_cccf_complex_taps_tile_analyzer(L, orc, monkeypatch, M, p):
 
 
 # ------------------------------------------------------------------ random block cuts across every dedicated kernel
-def test_channelizers_random_cuts_vs_oracle(L, orc):
-    """every shape with a dedicated kernel (M = 4 ... 1024; m = 2, 4, 5), analysis and synthesis of both channelizers, fed
+@pytest.mark.parametrize("ms,seed", [((2, 4, 5), 20261019), ((3, 6), 20261020)])
+def test_channelizers_random_cuts_vs_oracle(L, orc, ms, seed):
+    """every shape with a dedicated kernel (M = 4 ... 1024; m = 2 ... 6), analysis and synthesis of both channelizers, fed
     in seeded random block sizes that include single frames, blocks below the synthesizers' 4m-frame threshold (two-kernel
     path in between, state handed over) and ragged tiles: one stream of outputs whatever the cuts"""
-    rng = np.random.default_rng(20261019)
+    rng = np.random.default_rng(seed)
     for M in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
-        for m in (2, 4, 5):
+        for m in ms:
             nfr = int(rng.integers(300, 700)) if M >= 256 else int(rng.integers(1500, 4000))
             sizes = []
             left = nfr

@@ -136,6 +136,26 @@ def run(configs, steps, warmup, sink, device_index=0):
             ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
             report("c3m: firpfbch2_crcf analysis M=1024 m=%d, 2^29 samples" % m, n, 24, ms, ln)
             del x, y
+    if "m36" in args.configs:
+        # m = 3 and m = 6 on the dedicated kernels (instantiated in round 2; these shapes ran on the shape-generic path before)
+        for M in (16, 256, 1024):
+            for m in (3, 6):
+                n = 1 << 27
+                q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
+                H = q.get_state_len()
+                x = torch.zeros(2 * (H + n), dtype=torch.float32, device=dev)
+                y = torch.empty(4 * n, dtype=torch.float32, device=dev)
+                L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
+                ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
+                report("m36: firpfbch2_crcf analysis M=%d m=%d, 2^27 samples" % (M, m), n, 24, ms, ln)
+                q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+                ms, ln = timed(lambda: q.execute_block_dev(y.data_ptr(), (n // 2) // (M // 2), x.data_ptr(), st.cuda_stream))
+                report("m36: firpfbch2_crcf synthesis M=%d m=%d, 2^26 output samples" % (M, m), n // 2, 24, ms, ln)
+                for typ, name in ((L.LIQUID_ANALYZER, "analysis"), (L.LIQUID_SYNTHESIZER, "synthesis")):
+                    q = L.firpfbch_crcf.create_kaiser(typ, M, m, 60.0)
+                    ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n // M, y.data_ptr(), st.cuda_stream))
+                    report("m36: firpfbch_crcf %s M=%d m=%d, 2^27 samples" % (name, M, m), n, 16, ms, ln)
+                del x, y
     if "c5m" in args.configs:
         # the cluster kernel (M=4096) at the filter lengths it is instantiated for
         for m in (4, 7, 9):
