@@ -27,7 +27,10 @@ constexpr int kTwPitch = 18;
 
 inline bool supported(unsigned int n) { return n == 1024 || n == 2048 || n == 4096; }
 
-template <int RA> struct Pitch { static constexpr int SP = 272 + 16 / RA; };
+template <int RA> struct Pitch {
+    static constexpr int SP = 272 + 16 / RA;
+    static constexpr size_t kBytes = sizeof(float2) * ((size_t)2 * 16 * SP + 16 * 18);      // = smem_bytes<RA>(), usable in device code
+};
 template <int RA> constexpr size_t smem_bytes() { return sizeof(float2) * ((size_t)2 * 16 * Pitch<RA>::SP + 16 * kTwPitch); }
 
 // host: tw1[p-1][u] = e^{sign j 2 pi u p / N}, p = 1 ... RA-1, u < 256; then tw256[k1][r2] = e^{sign j 2 pi k1 r2 / 256}
@@ -62,9 +65,14 @@ inline void plan(unsigned int RA, unsigned long long n, unsigned int &grid, int 
 // the whole kernel body: call from a __global__ function launched with kThreads threads and smem_bytes<RA>() of dynamic
 // shared memory (passed in as smem_raw)
 // TWLD: the phase-1 twiddles are re-read (L1) in every tile instead of living in 2 (RA - 1) registers
-template <int RA, int SIGN, bool TWLD, class Src, class Dst>
+// Post: post(tr0, n_valid) runs in every thread after the tile's outputs have gone to dst (which may be per-thread or
+// shared-memory state of the caller's; a block barrier separates post of one tile from dst of the next)
+struct NoPost {
+    __device__ __forceinline__ void operator()(long long, int) const {}
+};
+template <int RA, int SIGN, bool TWLD, class Src, class Dst, class Post = NoPost>
 __device__ __forceinline__ void run(unsigned char *smem_raw, const float2 *__restrict__ tw, long long n_tr, int tiles_per_inst,
-                                    Src src, Dst dst)
+                                    Src src, Dst &&dst, Post &&post = NoPost())
 {
     constexpr int FR = 16 / RA, SP = Pitch<RA>::SP, GRP = 16 * RA;
     float2 *tile0 = reinterpret_cast<float2 *>(smem_raw);
@@ -139,6 +147,7 @@ __device__ __forceinline__ void run(unsigned char *smem_raw, const float2 *__res
 #pragma unroll
             for (int k2 = 0; k2 < 16; k2++) dst(tr0 + f2, (unsigned int)(RA * c + pp + GRP * k2), v[k2]);
         }
+        post(tr0, (int)(n_tr - tr0 < FR ? n_tr - tr0 : FR));
     }
 }
 #endif

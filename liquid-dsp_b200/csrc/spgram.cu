@@ -25,6 +25,8 @@
 
 #include "lc_common.cuh"
 #include "fft_device.cuh"
+#include "tile_fft.cuh"
+#include "quad_fft.cuh"
 #include "../../include/liquid_cuda.h"
 #include "host_pipeline.cuh"
 
@@ -164,6 +166,129 @@ spgram_accumulate_pow2_kernel(const float2 *__restrict__ hist, const float2 *__r
     }
 }
 
+// ---- nfft = 64 ... 4096 on the tile / quad transforms (tile_fft.cuh, quad_fft.cuh): the same chunked fold as
+// spgram_accumulate_pow2_kernel -- instance (tile) or CTA (quad) c folds `chunk` consecutive transforms in order and leaves
+// partial spectrum c for spgram_combine_kernel -- without the block-wide shared-memory passes
+struct TaperSrcT {
+    const float2 *hist, *x;
+    const float *w;
+    int H;
+    unsigned int window_len;
+    Segs segs;
+    // the raw sample (zero beyond the window), loaded a tile ahead; the taper is applied where the value is consumed
+    __device__ __forceinline__ float2 load(long long t, unsigned int k) const
+    {
+        if (k >= window_len) return make_float2(0.f, 0.f);
+        return ld_sample(hist, x, segs.end_of((unsigned long long)t) - (long long)(window_len - 1) + k, H);
+    }
+    __device__ __forceinline__ float2 finish(long long, unsigned int k, float2 raw) const
+    {
+        if (k >= window_len) return raw;
+        const float c = __ldg(w + k);
+        return make_float2(raw.x * c, raw.y * c);
+    }
+};
+
+// tile transform: thread u is handed outputs u and u + M/2 of every transform of its instance, in order
+struct FoldDstT {
+    float lo, hi, alpha, keep;
+    unsigned int M2;
+    __device__ __forceinline__ void operator()(long long, unsigned int k, float2 X)
+    {
+        const float P = X.x * X.x + X.y * X.y;
+        float &a = k < M2 ? lo : hi;
+        a = (alpha < 0.0f) ? a + P : keep * a + alpha * P;
+    }
+};
+
+template <int M>
+__global__ void __launch_bounds__(lctile::kThreads, 2)
+spgram_accumulate_tile_kernel(TaperSrcT src, const float2 *__restrict__ tw, long long T, int tiles_per_inst, unsigned int n_chunks,
+                              const float *__restrict__ psd, float *__restrict__ partial, float alpha)
+{
+    extern __shared__ __align__(16) unsigned char smem_tile[];
+    constexpr int M2 = M / 2;
+    const unsigned int u = threadIdx.x % M2;
+    const unsigned int inst = blockIdx.x * (lctile::kThreads / M2) + threadIdx.x / M2;
+    FoldDstT dst{inst == 0 ? psd[u] : 0.0f, inst == 0 ? psd[u + M2] : 0.0f, alpha, 1.0f - alpha, (unsigned int)M2};
+    lctile::run<M, -1>(smem_tile, tw, T, tiles_per_inst, src, dst);
+    if (inst < n_chunks) {
+        partial[(size_t)inst * M + u] = dst.lo;
+        partial[(size_t)inst * M + u + M2] = dst.hi;
+    }
+}
+
+// quad transform: the FR transforms of a tile leave through different thread groups, so |X|^2 goes through a
+// shared [FR][N] buffer and thread tid folds bins tid + 256 b in transform order after a block barrier
+template <int RA>
+struct PowerDstQ {
+    float *pbuf;
+    __device__ __forceinline__ void operator()(long long t, unsigned int k, float2 X) const
+    {
+        pbuf[(unsigned int)(t % (16 / RA)) * (256 * RA) + k] = X.x * X.x + X.y * X.y;
+    }
+};
+template <int RA>
+struct FoldPostQ {
+    const float *pbuf;
+    float acc[RA];
+    float alpha, keep;
+    __device__ __forceinline__ void operator()(long long, int n_valid)
+    {
+        __syncthreads();
+        for (int f = 0; f < n_valid; f++) {
+#pragma unroll
+            for (int b = 0; b < RA; b++) {
+                const float P = pbuf[f * (256 * RA) + threadIdx.x + 256 * b];
+                acc[b] = (alpha < 0.0f) ? acc[b] + P : keep * acc[b] + alpha * P;
+            }
+        }
+    }
+};
+
+template <int RA>
+__global__ void __launch_bounds__(lcquad::kThreads, 2)
+spgram_accumulate_quad_kernel(TaperSrcT src, const float2 *__restrict__ tw, long long T, int tiles_per_inst,
+                              const float *__restrict__ psd, float *__restrict__ partial, float alpha)
+{
+    extern __shared__ __align__(16) unsigned char smem_quad[];
+    constexpr int N = 256 * RA;
+    float *pbuf = reinterpret_cast<float *>(smem_quad + lcquad::Pitch<RA>::kBytes);
+    FoldPostQ<RA> post;
+    post.pbuf = pbuf;
+    post.alpha = alpha;
+    post.keep = 1.0f - alpha;
+#pragma unroll
+    for (int b = 0; b < RA; b++) post.acc[b] = blockIdx.x == 0 ? psd[threadIdx.x + 256 * b] : 0.0f;
+    lcquad::run<RA, -1, (RA >= 8)>(smem_quad, tw, T, tiles_per_inst, src, PowerDstQ<RA>{pbuf}, post);
+#pragma unroll
+    for (int b = 0; b < RA; b++) partial[(size_t)blockIdx.x * N + threadIdx.x + 256 * b] = post.acc[b];
+}
+
+template <int M>
+void launch_accumulate_tile(const TaperSrcT &src, const float2 *d_tw, unsigned long long T, int tpi, unsigned int n_chunks,
+                            const float *d_psd, float *d_part, float alpha, cudaStream_t st)
+{
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(spgram_accumulate_tile_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)lctile::smem_bytes<M>()));
+    const unsigned int ipc = lctile::kThreads / (M / 2);
+    spgram_accumulate_tile_kernel<M><<<(n_chunks + ipc - 1) / ipc, lctile::kThreads, lctile::smem_bytes<M>(), st>>>(
+        src, d_tw, (long long)T, tpi, n_chunks, d_psd, d_part, alpha);
+}
+
+template <int RA>
+void launch_accumulate_quad(const TaperSrcT &src, const float2 *d_tw, unsigned long long T, int tpi, unsigned int n_chunks,
+                            const float *d_psd, float *d_part, float alpha, cudaStream_t st)
+{
+    const size_t smem = lcquad::smem_bytes<RA>() + sizeof(float) * 4096;
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(spgram_accumulate_quad_kernel<RA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spgram_accumulate_quad_kernel<RA><<<n_chunks, lcquad::kThreads, smem, st>>>(src, d_tw, (long long)T, tpi, d_psd, d_part, alpha);
+}
+
 // any nfft: tapered, zero-padded segments [T][nfft] for the batched DFT
 __global__ void __launch_bounds__(kThreads)
 spgram_gather_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ w,
@@ -298,6 +423,32 @@ void accumulate_transforms(spgramcf q, const float2 *d_x, unsigned long long T, 
 {
     if (T == 0) return;
     const unsigned int nfft = q->nfft;
+    if (q->fft.d_tw_tile && T < (1ull << 31) && !getenv("LIQUID_CUDA_SPGRAM_NO_TILE") && !getenv("LIQUID_CUDA_NO_FUSED")) {
+        // transforms per tile, instances per CTA; chunks = about two waves of the CTAs that fit (2 per SM)
+        const unsigned int per_tile = nfft <= 512 ? lctile::kFr : 4096 / nfft;
+        const unsigned int ipc = nfft <= 512 ? lctile::kThreads / (nfft / 2) : 1;
+        const unsigned long long n_tiles = (T + per_tile - 1) / per_tile;
+        const unsigned long long target = 148ull * 2 * 2 * ipc;
+        unsigned long long tpi = (n_tiles + target - 1) / target;
+        if (tpi < 1) tpi = 1;
+        const unsigned int n_chunks = (unsigned int)((n_tiles + tpi - 1) / tpi);
+        float *d_part = (float *)q->partials.get(sizeof(float) * (size_t)n_chunks * nfft);
+        const TaperSrcT src{q->d_buf, d_x, q->d_w, (int)q->window_len, q->window_len, segs};
+        switch (nfft) {
+        case 64: launch_accumulate_tile<64>(src, q->fft.d_tw_tile, T, (int)tpi, n_chunks, q->d_psd, d_part, alpha, st); break;
+        case 128: launch_accumulate_tile<128>(src, q->fft.d_tw_tile, T, (int)tpi, n_chunks, q->d_psd, d_part, alpha, st); break;
+        case 256: launch_accumulate_tile<256>(src, q->fft.d_tw_tile, T, (int)tpi, n_chunks, q->d_psd, d_part, alpha, st); break;
+        case 512: launch_accumulate_tile<512>(src, q->fft.d_tw_tile, T, (int)tpi, n_chunks, q->d_psd, d_part, alpha, st); break;
+        case 1024: launch_accumulate_quad<4>(src, q->fft.d_tw_tile, T, (int)tpi, n_chunks, q->d_psd, d_part, alpha, st); break;
+        case 2048: launch_accumulate_quad<8>(src, q->fft.d_tw_tile, T, (int)tpi, n_chunks, q->d_psd, d_part, alpha, st); break;
+        default: launch_accumulate_quad<16>(src, q->fft.d_tw_tile, T, (int)tpi, n_chunks, q->d_psd, d_part, alpha, st); break;
+        }
+        LC_LAUNCH_CHECK();
+        spgram_combine_kernel<<<(nfft + kThreads - 1) / kThreads, kThreads, 0, st>>>(d_part, q->d_psd, nfft, n_chunks,
+                                                                                  (unsigned int)(tpi * per_tile), T, alpha);
+        LC_LAUNCH_CHECK();
+        return;
+    }
     if (lcfft::pow2_in_smem(nfft)) {
         static std::atomic<unsigned long long> configured{0};
         if (lc::first_time_on_device(configured))

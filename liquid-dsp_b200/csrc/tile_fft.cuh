@@ -4,8 +4,9 @@
 // issues the global load of input k of transform t a tile AHEAD and must not touch the value (arithmetic on it would
 // make the prefetch wait for the memory latency there and then),  float2 finish(long long t, unsigned k, float2 raw)
 // turns it into the transform input when it is consumed -- and a destination functor  void dst(long long t, unsigned n,
-// float2 v)  (output n of transform t); the
-// transform never makes a trip through HBM or a block-wide shared-memory pass:
+// float2 v)  (output n of transform t; a thread is handed the same two outputs u and u + M/2 of every transform of its
+// instance, in transform order, so a destination passed as an lvalue may keep per-thread state -- spgram.cu folds
+// |X|^2 into two registers); the transform never makes a trip through HBM or a block-wide shared-memory pass:
 //   an instance = M/2 threads walks tiles of 8 transforms.  Decimation in time, X_p[k] = X[2k + p]:
 //     pass B'  R2 = M/32-point register DFTs over the rows X_p[k1 + 16 k2], inputs prefetched into registers a tile ahead
 //     pass A'  inter-pass twiddle and 16-point register DFTs down the columns of the shared tile (conflict-free layout
@@ -74,7 +75,7 @@ inline void plan(unsigned int M, unsigned long long n, unsigned int &grid, int &
 // shared memory (passed in as smem_raw)
 template <int M, int SIGN, class Src, class Dst>
 __device__ __forceinline__ void run(unsigned char *smem_raw, const float2 *__restrict__ tw, long long n_tr, int tiles_per_inst,
-                                    Src src, Dst dst)
+                                    Src src, Dst &&dst)
 {
     using LY = Layout<M>;
     constexpr int M2 = M / 2, R2 = M2 / 16;

@@ -1269,6 +1269,29 @@ def test_spgramcf_vs_reference_fixture_and_oracle(L, orc, refrn):
     assert np.abs(q.execute() - o.execute()).max() < 2e-6 * np.abs(o.execute()).max()
 
 
+@pytest.mark.parametrize("nfft,wl", [(64, 64), (128, 50), (256, 128), (512, 301), (1024, 512), (2048, 1100), (4096, 2048)])
+def test_spgramcf_tile_and_quad_transforms(L, orc, monkeypatch, nfft, wl):
+    """nfft = 64 ... 4096 fold their transforms on the tile / quad transforms: several chunks per call, ragged tiles, the
+    exponential average (order matters) and the plain sum, against the oracle and against the shared-memory kernel"""
+    from test_oracle import lin_close
+    n = 700 * nfft + 37
+    x = (orc.synth_input(n, seed=0x5A + nfft) * np.float32(0.2)
+         + np.exp(2j * np.pi * 0.07 * np.arange(n)).astype(np.complex64)).astype(np.complex64)
+    q, o = L.spgramcf.create_kaiser(nfft, wl, 7.0), orc.Spgramcf(nfft, window_len=wl, beta=7.0)
+    for part, alpha in ((x[:3 * nfft], 0.5), (x[3 * nfft:n // 2], 0.05), (x[n // 2:n // 2 + 11], 0.05), (x[n // 2 + 11:], 0.004)):
+        q.accumulate_psd(part, alpha)
+        o.accumulate_psd(part, alpha)
+        assert q.num_transforms() == o.num_transforms()
+        assert lin_close(q.write_accumulation(), o.write_accumulation(), rel=2e-5), (nfft, alpha)
+    est = q.estimate_psd(x)
+    assert lin_close(est, o.estimate_psd(x), rel=2e-5)
+    monkeypatch.setenv("LIQUID_CUDA_SPGRAM_NO_TILE", "1")
+    q2 = L.spgramcf.create_kaiser(nfft, wl, 7.0)
+    est2 = q2.estimate_psd(x)
+    monkeypatch.delenv("LIQUID_CUDA_SPGRAM_NO_TILE")
+    assert lin_close(est, est2, rel=2e-5)
+
+
 # ------------------------------------------------------------------ cluster-of-8 M=4096 kernel specifics
 @pytest.mark.parametrize("m", [4, 7, 9])
 def test_pfbch2_cluster_4096_vs_oracle_odd_splits(L, orc, m):
