@@ -117,11 +117,18 @@ struct PrefixDst {
 // M = 64 ... 512: the tile transform of tile_fft.cuh between the subcarrier map and the prefix writer -- row DFTs out of
 // register-prefetched subcarrier values, column DFTs in a conflict-free shared tile, the last radix-2 stage in the thread
 // that writes body and tapered prefix; one instance barrier per tile of 8 symbols instead of a block barrier per pass
+// W32: 32-bit element offsets (every shape but M = 512, where they cost a spill and 10 % of the rate)
+template <bool W32>
 struct SymbolSrcT {
     MapArgs a;
     const float2 *x;
     // the user's value of the subcarrier, loaded a tile ahead and left alone until it is used
-    __device__ __forceinline__ float2 load(long long s, unsigned int k) const { return __ldg(x + s * a.M + k); }
+    // (32-bit element offsets: the launcher takes this path only while n (M + cp) < 2^32 -- the 64-bit products were a
+    // fifth of the M = 64 kernel's instructions and pushed it into spills)
+    __device__ __forceinline__ float2 load(long long s, unsigned int k) const 
+    {
+        return W32 ? __ldg(x + ((unsigned int)s * a.M + k)) : __ldg(x + s * a.M + k);
+    }
     // ofdmframegen.c:279-311 at the point of use: data scaled, pilots from the table, nulls zero (the type and pilot
     // tables sit in L1).  32-bit remainder by a constant (the 64-bit one is a subroutine): n_sym < 2^31 here
     __device__ __forceinline__ float2 finish(long long s, unsigned int k, float2 v) const
@@ -133,13 +140,14 @@ struct SymbolSrcT {
         return c == -2 ? make_float2(v.x * a.g, v.y * a.g) : make_float2(c >= 0 ? pv : 0.f, 0.f);
     }
 };
+template <bool W32>
 struct PrefixDstT {
     float2 *y;
     const float *taper;
     unsigned int M, cp, tl;
     __device__ __forceinline__ void operator()(long long s, unsigned int k, float2 v) const
     {
-        float2 *base = y + s * (M + cp);
+        float2 *base = W32 ? y + (unsigned int)s * (M + cp) : y + s * (M + cp);
         __stcs(base + cp + k, v);
         if (k >= M - cp) {
             const unsigned int i = k - (M - cp);
@@ -158,7 +166,7 @@ ofdm_symbols_tile_kernel(MapArgs a, const float2 *__restrict__ x, const float2 *
                          float2 *__restrict__ y, unsigned int cp, unsigned int tl, long long n_sym, int tiles_per_inst)
 {
     extern __shared__ __align__(16) unsigned char smem_tile[];
-    lctile::run<M, +1>(smem_tile, tw, n_sym, tiles_per_inst, SymbolSrcT{a, x}, PrefixDstT{y, taper, (unsigned int)M, cp, tl});
+    lctile::run<M, +1>(smem_tile, tw, n_sym, tiles_per_inst, SymbolSrcT<M != 512>{a, x}, PrefixDstT<M != 512>{y, taper, (unsigned int)M, cp, tl});
 }
 
 template <int M>
@@ -183,7 +191,7 @@ ofdm_symbols_quad_kernel(MapArgs a, const float2 *__restrict__ x, const float2 *
                          float2 *__restrict__ y, unsigned int cp, unsigned int tl, long long n_sym, int tiles_per_inst)
 {
     extern __shared__ __align__(16) unsigned char smem_quad[];
-    lcquad::run<RA, +1, (RA >= 8)>(smem_quad, tw, n_sym, tiles_per_inst, SymbolSrcT{a, x}, PrefixDstT{y, taper, 256u * RA, cp, tl});
+    lcquad::run<RA, +1, (RA >= 8)>(smem_quad, tw, n_sym, tiles_per_inst, SymbolSrcT<true>{a, x}, PrefixDstT<true>{y, taper, 256u * RA, cp, tl});
 }
 
 template <int RA>
@@ -292,7 +300,7 @@ void symbols_dev(ofdmframegen q, const float2 *d_x, unsigned long long n, float2
     if (n == 0) return;
     const MapArgs a{q->d_code, q->d_pil, q->M, q->M_pilot % kPilotPeriod, q->pilot_pos, q->g_data};
     const unsigned int M = q->M;
-    if (q->d_tw_tile && n < (1ull << 31) && !getenv("LIQUID_CUDA_OFDM_GENERIC") && !getenv("LIQUID_CUDA_NO_FUSED")) {
+    if (q->d_tw_tile && n * (M + q->cp_len) < (1ull << 32) && !getenv("LIQUID_CUDA_OFDM_GENERIC") && !getenv("LIQUID_CUDA_NO_FUSED")) {
         // the pilot position of symbol s is (pos + (s mod 255) npm) mod 255 with s counted from the start of the block
         switch (M) {
         case 64: launch_symbols_tile<64>(a, d_x, q->d_tw_tile, q->d_taper, d_y, q->cp_len, q->taper_len, n, st); break;
