@@ -544,7 +544,7 @@ void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps,
 {
     // short filters on 16-byte aligned, even-length streams: register-blocked packed kernel
     // (tile ids are 32-bit inside the kernel: streams * ceil(n / 512) must stay below 2^31)
-    if (n_taps <= 64 && (n % 2) == 0 && ((uintptr_t)d_y % 16) == 0 && ((n + 511) / 512) * n_streams < (1ull << 31) &&
+    if (n_taps <= 256 && (n % 2) == 0 && ((uintptr_t)d_y % 16) == 0 && ((n + 511) / 512) * n_streams < (1ull << 31) &&
         !getenv("LIQUID_CUDA_NO_REGBLOCK")) {
         int dev = 0, sms = 148;
         LC_CUDA_CHECK(cudaGetDevice(&dev));
@@ -561,23 +561,37 @@ void launch(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps,
             kern<<<(unsigned int)grid, kRbThreads, C::kSmem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n,
                                                                     (unsigned int)tiles_rb, (unsigned int)total_rb, d_tile_counter);
         };
-        if (n_taps <= 16) run(firfilt_regblock_kernel<16, 16>, RbCfg<16, 16>{});
-        else if (n_taps <= 32) run(firfilt_regblock_kernel<32, 16>, RbCfg<32, 16>{});
-        else if (getenv("LIQUID_CUDA_FIRFILT_DIRECT")) run(firfilt_regblock_kernel<64, 16>, RbCfg<64, 16>{});
-        else {
-            // 2-parallel fast-FIR form, the tap sets behind the sample buffers
-            using C = RbCfg<64, 16>;
-            constexpr size_t smem = C::kSmem + 3 * 32 * sizeof(float);
+        // 2-parallel fast-FIR form (the tap sets behind the sample buffers), instantiated for 16 / 32 / 64 / 96 / 128 / 192 / 256 taps; the direct
+        // register-blocked form stays reachable for the parity tests (LIQUID_CUDA_FIRFILT_DIRECT, up to 64 taps)
+        auto run_ffa = [&](auto nt_c) {
+            constexpr int NT = decltype(nt_c)::value;
+            using C = RbCfg<NT, 16>;
+            constexpr size_t smem = C::kSmem + 3 * (NT / 2) * sizeof(float);
             const unsigned long long tiles_rb = (n + C::kWarpTile - 1) / C::kWarpTile;
             const unsigned long long total_rb = tiles_rb * n_streams;
             unsigned long long grid = (unsigned long long)sms * 2;
             const unsigned long long need = (total_rb + kRbWarps - 1) / kRbWarps;
             if (grid > need) grid = need;
-            LC_CUDA_CHECK(cudaFuncSetAttribute(firfilt_ffa_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (d_tile_counter) LC_CUDA_CHECK(cudaMemsetAsync(d_tile_counter, 0, sizeof(unsigned int), st));
-            firfilt_ffa_kernel<64><<<(unsigned int)grid, kRbThreads, smem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n,
-                                                                                (unsigned int)tiles_rb, (unsigned int)total_rb, d_tile_counter);
-        }
+            LC_CUDA_CHECK(cudaFuncSetAttribute(firfilt_ffa_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // tiles of up to 32 taps take a warp a fraction of a microsecond: drawn one by one from the global counter, all
+            // 2368 warps queue on one address (measured at 16 taps: 183 GS/s with the counter, 388 GS/s with static striding;
+            // ncu reports 0.33 ms for the launch that CUDA events time at 0.77 ms).  From 64 taps on the counter wins (254 vs 245)
+            unsigned int *ctr = NT <= 32 ? nullptr : d_tile_counter;
+            if (ctr) LC_CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+            firfilt_ffa_kernel<NT><<<(unsigned int)grid, kRbThreads, smem, st>>>(d_hist, d_x, H, d_taps, n_taps, scale, d_y, n,
+                                                                                (unsigned int)tiles_rb, (unsigned int)total_rb, ctr);
+        };
+        const bool direct = getenv("LIQUID_CUDA_FIRFILT_DIRECT") != nullptr && n_taps <= 64;
+        if (direct && n_taps <= 16) run(firfilt_regblock_kernel<16, 16>, RbCfg<16, 16>{});
+        else if (direct && n_taps <= 32) run(firfilt_regblock_kernel<32, 16>, RbCfg<32, 16>{});
+        else if (direct) run(firfilt_regblock_kernel<64, 16>, RbCfg<64, 16>{});
+        else if (n_taps <= 16) run_ffa(std::integral_constant<int, 16>{});
+        else if (n_taps <= 32) run_ffa(std::integral_constant<int, 32>{});
+        else if (n_taps <= 64) run_ffa(std::integral_constant<int, 64>{});
+        else if (n_taps <= 96) run_ffa(std::integral_constant<int, 96>{});
+        else if (n_taps <= 128) run_ffa(std::integral_constant<int, 128>{});
+        else if (n_taps <= 192) run_ffa(std::integral_constant<int, 192>{});
+        else run_ffa(std::integral_constant<int, 256>{});
         LC_LAUNCH_CHECK();
         return;
     }

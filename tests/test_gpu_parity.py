@@ -415,10 +415,11 @@ def test_firfilt_full_size_spot_checks_vs_oracle(L, orc):
     L.lib.liquid_cuda_free(d_y)
 
 
-@pytest.mark.parametrize("n_taps", [33, 40, 63, 64])
+@pytest.mark.parametrize("n_taps", [1, 2, 7, 16, 17, 31, 32, 33, 40, 63, 64, 65, 96, 97, 128, 129, 192, 193, 256])
 def test_firfilt_fast_fir_form_vs_direct_and_oracle(L, orc, monkeypatch, n_taps):
-    """33 - 64 taps take the 2-parallel fast-FIR kernel with the transposed store path: against the oracle and the direct
-    register-blocked kernel, on streams whose length is not a multiple of the 512-output warp tile, state carried"""
+    """1 - 256 taps take the 2-parallel fast-FIR kernel (instantiated for 16 / 32 / 64 / 96 / 128 / 192 / 256 taps) with the transposed
+    store path: against the oracle and the direct register-blocked kernel (up to 64 taps) or the tiled kernel (above), on
+    streams whose length is not a multiple of the 512-output warp tile, state carried"""
     import ctypes as C
     rng = np.random.default_rng(n_taps)
     h = (rng.standard_normal(n_taps) / np.sqrt(n_taps)).astype(np.float32)
@@ -428,6 +429,8 @@ def test_firfilt_fast_fir_form_vs_direct_and_oracle(L, orc, monkeypatch, n_taps)
     for direct in (False, True):
         if direct:
             monkeypatch.setenv("LIQUID_CUDA_FIRFILT_DIRECT", "1")
+            if n_taps > 64:
+                monkeypatch.setenv("LIQUID_CUDA_NO_REGBLOCK", "1")
         q = L.firfilt_crcf.create(h)
         d_x = L.lib.liquid_cuda_malloc(x.nbytes); d_y = L.lib.liquid_cuda_malloc(x.nbytes)
         L.lib.liquid_cuda_memcpy_h2d(d_x, x.ctypes.data_as(C.c_void_p), x.nbytes)
@@ -442,6 +445,7 @@ def test_firfilt_fast_fir_form_vs_direct_and_oracle(L, orc, monkeypatch, n_taps)
         st = np.concatenate([q2.execute_block(x[0][:cut]), q2.execute_block(x[0][cut:])])
         outs[direct] = (got, st)
     monkeypatch.delenv("LIQUID_CUDA_FIRFILT_DIRECT")
+    monkeypatch.delenv("LIQUID_CUDA_NO_REGBLOCK", raising=False)
     o = orc.Firfilt(h=h)
     for s in range(n_streams):
         o.reset()

@@ -94,6 +94,18 @@ def run(configs, steps, warmup, sink, device_index=0):
         report("c2: firfilt_crcf 64 taps, 1024 streams x 2^20 samples", ns * n, 16, ms, ln,
                {"fp32_pipe_bound_MSps": fp_peak})
         del x, y
+    if "ff" in args.configs:
+        # firfilt_crcf block form across filter lengths (256 streams x 2^20 samples): which lengths sit on which kernel
+        for nt in (8, 16, 24, 32, 48, 64, 65, 96, 128, 160, 192, 256, 257):
+            ns, n = 256, 1 << 20
+            q = L.firfilt_crcf.create_kaiser(nt, 0.25, 60.0, 0.0)
+            x = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+            y = torch.empty(2 * ns * n, dtype=torch.float32, device=dev)
+            L.synth_input_dev(x.data_ptr(), ns * n, stream=st.cuda_stream)
+            ms, ln = timed(lambda: q.execute_streams_dev(x.data_ptr(), ns, n, y.data_ptr(), st.cuda_stream))
+            fp_peak = 148 * 4 * 0.5 * 32 * 1.92e9 / nt / 1e6      # MS/s at 100 % FMA-pipe use (nt packed FMA per sample)
+            report("ff: firfilt_crcf %d taps, 256 streams x 2^20 samples" % nt, ns * n, 16, ms, ln, {"fp32_pipe_bound_MSps": fp_peak})
+            del x, y
     if "c4" in args.configs:
         # firpfbch_crcf synthesis + analysis round trip, M=256, m=5, 32 streams x 2^22 samples on this GPU
         M, m, ns, n = 256, 5, 32, 1 << 22
