@@ -507,6 +507,46 @@ dotprod_batch_kernel(const float *__restrict__ h, unsigned int n, const float2 *
     }
 }
 
+// n = 8 ... 255 on 16-byte aligned vectors (even n and stride): G = 2 / 4 / 8 / 16 lanes per dot product, each lane reading
+// 16 bytes (two samples) at a time so that a group's load instruction is one contiguous run of 16 G bytes, a log2(G)-step
+// shuffle reduction, and the warp's 32 / G results stored by its first lanes as one run.  (One warp per vector left every
+// lane with two samples and ten shuffles at n = 64: 0.60 of the roofline.)
+template <int G>
+__global__ void __launch_bounds__(kThreads)
+dotprod_group_kernel(const float *__restrict__ h, unsigned int n, const float2 *__restrict__ x, unsigned long long n_vec,
+                     unsigned long long stride, float2 *__restrict__ y)
+{
+    constexpr int VPW = 32 / G;                                       // vectors per warp
+    const unsigned int lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
+    unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long n_wv = (n_vec + VPW - 1) / VPW;
+    for (; w < n_wv; w += nw) {
+        const unsigned long long v = w * VPW + grp;
+        float2 acc = make_float2(0.f, 0.f), acc2 = acc;
+        if (v < n_vec) {
+            const float4 *xv = reinterpret_cast<const float4 *>(x + v * stride);
+            const float2 *hv = reinterpret_cast<const float2 *>(h);
+#pragma unroll 4
+            for (unsigned int i = sub; i < n / 2; i += G) {
+                const float4 s = __ldg(xv + i);
+                const float2 c = __ldg(hv + i);
+                acc = __ffma2_rn(make_float2(c.x, c.x), make_float2(s.x, s.y), acc);
+                acc2 = __ffma2_rn(make_float2(c.y, c.y), make_float2(s.z, s.w), acc2);
+            }
+        }
+        float re = acc.x + acc2.x, im = acc.y + acc2.y;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            re += __shfl_xor_sync(0xffffffffu, re, o);
+            im += __shfl_xor_sync(0xffffffffu, im, o);
+        }
+        // lane g of the warp fetches group g's result and stores it: VPW consecutive outputs in one run
+        const float rre = __shfl_sync(0xffffffffu, re, (lane % VPW) * G), rim = __shfl_sync(0xffffffffu, im, (lane % VPW) * G);
+        if (lane < VPW && w * VPW + lane < n_vec) y[w * VPW + lane] = make_float2(rre, rim);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 firpfb_block_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H,
                     const float *__restrict__ sub, unsigned int sub_len, const unsigned int *__restrict__ idx,
@@ -620,6 +660,17 @@ void launch_state_output(const float2 *d_hist, const float *d_taps, unsigned int
 void launch_dotprod_batch(const float *d_h, unsigned int n, const float2 *d_x, unsigned long long n_vec,
                           unsigned long long stride, float2 *d_y, cudaStream_t st)
 {
+    if (n >= 8 && n < 256 && (n % 2) == 0 && (stride % 2) == 0 && ((uintptr_t)d_x % 16) == 0 && ((uintptr_t)d_h % 8) == 0) {
+        const unsigned int G = n < 32 ? 2 : n < 64 ? 4 : n < 128 ? 8 : 16;
+        const unsigned long long n_wv = (n_vec + 32 / G - 1) / (32 / G);
+        const unsigned int grid = grid_cap((n_wv * 32 + kThreads - 1) / kThreads);
+        if (G == 2) dotprod_group_kernel<2><<<grid, kThreads, 0, st>>>(d_h, n, d_x, n_vec, stride, d_y);
+        else if (G == 4) dotprod_group_kernel<4><<<grid, kThreads, 0, st>>>(d_h, n, d_x, n_vec, stride, d_y);
+        else if (G == 8) dotprod_group_kernel<8><<<grid, kThreads, 0, st>>>(d_h, n, d_x, n_vec, stride, d_y);
+        else dotprod_group_kernel<16><<<grid, kThreads, 0, st>>>(d_h, n, d_x, n_vec, stride, d_y);
+        LC_LAUNCH_CHECK();
+        return;
+    }
     int per_warp = n >= 32;
     unsigned long long threads = per_warp ? n_vec * 32 : n_vec;
     dotprod_batch_kernel<<<grid_cap((threads + kThreads - 1) / kThreads), kThreads, 0, st>>>(d_h, n, d_x, n_vec, stride, d_y, per_warp);

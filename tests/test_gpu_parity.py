@@ -483,6 +483,26 @@ def test_dotprod_struct_vs_ordinal(L):
         assert abs(L.dotprod_crcf(h).execute(x) - want) < 1e-4 * max(1.0, np.sqrt(n))
 
 
+@pytest.mark.parametrize("n,stride", [(4, 4), (8, 8), (10, 12), (16, 16), (30, 30), (32, 32), (34, 40), (64, 64), (64, 65), (100, 128), (128, 128), (254, 256), (256, 256), (1000, 1000)])
+def test_dotprod_batch_dev_vs_numpy(L, orc, n, stride):
+    """the batched device entry point: one thread (n < 8), 2 / 4 / 8 / 16 lanes (8 <= n < 256, aligned) or one warp per
+    vector; ragged vector counts, strides longer than the vector, an odd stride (the unaligned path)"""
+    import ctypes as C
+    rng = np.random.default_rng(n + stride)
+    h = rng.standard_normal(n).astype(np.float32)
+    for n_vec in (1, 7, 1031):
+        x = orc.synth_input(n_vec * stride, seed=0xD0 + n)
+        d_x = L.lib.liquid_cuda_malloc(x.nbytes); d_y = L.lib.liquid_cuda_malloc(8 * n_vec)
+        L.lib.liquid_cuda_memcpy_h2d(d_x, x.ctypes.data_as(C.c_void_p), x.nbytes)
+        L.dotprod_crcf(h).execute_batch_dev(d_x, n_vec, stride, d_y, 0)
+        L.lib.liquid_cuda_sync()
+        got = np.empty(n_vec, np.complex64)
+        L.lib.liquid_cuda_memcpy_d2h(got.ctypes.data_as(C.c_void_p), d_y, got.nbytes)
+        L.lib.liquid_cuda_free(d_x); L.lib.liquid_cuda_free(d_y)
+        want = (x.reshape(n_vec, stride)[:, :n].astype(np.complex128) * h.astype(np.float64)).sum(axis=1)
+        assert np.abs(got - want).max() < 1e-5 * np.sqrt(n), (n, stride, n_vec)
+
+
 def test_firpfb_reference_kat_and_oracle(L, orc, kat):
     k = kat["firpfb"]
     q = L.firpfb_crcf(k["M"], np.array(k["h"], np.float32))

@@ -414,7 +414,7 @@ def run(configs, steps, warmup, sink, device_index=0):
         n_s = 1 << 28
         x = torch.empty(2 * n_s, dtype=torch.float32, device=dev)
         L.synth_input_dev(x.data_ptr(), n_s, stream=st.cuda_stream)
-        for nt in (64, 1024):
+        for nt in (8, 16, 32, 64, 128, 256, 1024):
             y = torch.empty(2 * (n_s // nt), dtype=torch.float32, device=dev)
             q = L.dotprod_crcf(L.liquid_firdes_kaiser(nt, 0.2, 60.0, 0.0))
             ms, ln = timed(lambda: q.execute_batch_dev(x.data_ptr(), n_s // nt, nt, y.data_ptr(), st.cuda_stream))
