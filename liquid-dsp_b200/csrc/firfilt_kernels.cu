@@ -720,13 +720,86 @@ firpfb_tile_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x
     }
 }
 
+// Four consecutive outputs per thread: output 4 t + r meets sample 4 t + r + k at tap k, so a four-sample shift register
+// takes ONE new sample per tap step for four outputs (the kernel above reads sub_len samples per output and is bound by
+// shared-memory bandwidth: 12 LDS.64 + 12 LDS.32 per output at sub_len = 12).  Samples are staged transposed,
+// slot(q) = (q % 4) ROW + q / 4 with ROW = 4 (mod 16): the 8-byte cp.async fill of 16 consecutive q and the threads'
+// reads (consecutive t -> consecutive slots) are both conflict-free.  Same fmaf chain per output (oldest sample first):
+// identical bits (tested against the kernels above).
+__global__ void __launch_bounds__(kThreads)
+firpfb_tile4_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ sub,
+                    unsigned int sub_len, unsigned int n_filters, const unsigned int *__restrict__ idx, float scale,
+                    float2 *__restrict__ y, unsigned long long n, unsigned int ROW)
+{
+    extern __shared__ float2 smem_p[];
+    const unsigned int halo = sub_len - 1;
+    const unsigned int row = sub_len | 1;                                // padded row length of the bank
+    float2 *xs = smem_p;                                                 // staged sample q = sample i0 - halo + q, transposed
+    float *bank = reinterpret_cast<float *>(xs + 4 * ROW);
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * kPfbTile;
+    const unsigned int nt = (n - i0 < kPfbTile) ? (unsigned int)(n - i0) : kPfbTile;
+    for (unsigned int e = threadIdx.x; e < n_filters * sub_len; e += blockDim.x)
+        bank[(e / sub_len) * row + e % sub_len] = __ldg(sub + e);
+    for (unsigned int q = threadIdx.x; q < kPfbTile + halo; q += blockDim.x) {
+        const long long s = (long long)i0 - (long long)halo + q;
+        float2 *dstp = xs + (q & 3) * ROW + (q >> 2);
+        if (s >= 0 && s < (long long)n) {
+            const unsigned int dst = (unsigned int)__cvta_generic_to_shared(dstp);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(x + s) : "memory");
+        } else {
+            *dstp = (s < 0) ? __ldg(hist + (H + s)) : make_float2(0.f, 0.f);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (unsigned int t = threadIdx.x; 4 * t < nt; t += blockDim.x) {
+        // filter rows of the four outputs (outputs beyond the end of the block reuse row 0 and are not stored)
+        const float *hf[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) hf[r] = bank + ((4 * t + r < nt) ? __ldg(idx + i0 + 4 * t + r) : 0u) * row;
+        float2 w[4];
+#pragma unroll
+        for (int r = 0; r < 3; r++) w[r + 1] = xs[(r & 3) * ROW + t];    // samples 4 t + 0 .. 2 (slots of q = 4 t + r)
+        float re[4] = {0.f, 0.f, 0.f, 0.f}, im[4] = {0.f, 0.f, 0.f, 0.f};
+        for (unsigned int k = 0; k < sub_len; k++) {
+            // window after the shift: w[r] = sample 4 t + r + k
+            w[0] = w[1]; w[1] = w[2]; w[2] = w[3];
+            const unsigned int q = 4 * t + 3 + k;
+            w[3] = xs[(q & 3) * ROW + (q >> 2)];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const float c = hf[r][k];
+                re[r] = fmaf(c, w[r].x, re[r]);
+                im[r] = fmaf(c, w[r].y, im[r]);
+            }
+        }
+        float2 *yo = y + i0 + 4 * t;
+        if (4 * t + 3 < nt && ((uintptr_t)yo % 16) == 0) {
+            __stcs(reinterpret_cast<float4 *>(yo), make_float4(re[0] * scale, im[0] * scale, re[1] * scale, im[1] * scale));
+            __stcs(reinterpret_cast<float4 *>(yo) + 1, make_float4(re[2] * scale, im[2] * scale, re[3] * scale, im[3] * scale));
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (4 * t + r < nt) yo[r] = make_float2(re[r] * scale, im[r] * scale);
+        }
+    }
+}
+
 void launch_firpfb_block(const float2 *d_hist, const float2 *d_x, int H, const float *d_sub, unsigned int sub_len,
                          const unsigned int *d_idx, float scale, float2 *d_y, unsigned long long n, cudaStream_t st,
                          unsigned int n_filters)
 {
     const size_t smem = sizeof(float2) * ((kPfbTile + sub_len) & ~1u) + sizeof(float) * (size_t)n_filters * (sub_len | 1);
     const unsigned long long tiles = (n + kPfbTile - 1) / kPfbTile;
-    if (n_filters && smem <= 48 * 1024 && n >= 4ull * kPfbTile && tiles < (1ull << 31) && !getenv("LIQUID_CUDA_FIRPFB_SIMPLE")) {
+    // ROW = 4 (mod 16) and >= ceil((tile + halo) / 4)
+    const unsigned int need = (kPfbTile + sub_len - 1 + 3) / 4;
+    const unsigned int ROW = ((need + 11) / 16) * 16 + 4;
+    const size_t smem4 = sizeof(float2) * 4 * ROW + sizeof(float) * (size_t)n_filters * (sub_len | 1);
+    if (n_filters && smem4 <= 48 * 1024 && n >= 4ull * kPfbTile && tiles < (1ull << 31) && !getenv("LIQUID_CUDA_FIRPFB_SIMPLE") &&
+        !getenv("LIQUID_CUDA_FIRPFB_TILE1")) {
+        firpfb_tile4_kernel<<<(unsigned int)tiles, kThreads, smem4, st>>>(d_hist, d_x, H, d_sub, sub_len, n_filters, d_idx, scale, d_y, n, ROW);
+    } else if (n_filters && smem <= 48 * 1024 && n >= 4ull * kPfbTile && tiles < (1ull << 31) && !getenv("LIQUID_CUDA_FIRPFB_SIMPLE")) {
         firpfb_tile_kernel<<<(unsigned int)tiles, kThreads, smem, st>>>(d_hist, d_x, H, d_sub, sub_len, n_filters, d_idx, scale, d_y, n);
     } else {
         firpfb_block_kernel<<<grid_cap((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(d_hist, d_x, H, d_sub, sub_len, d_idx, scale, d_y, n);

@@ -563,6 +563,12 @@ def test_firpfb_long_blocks_tiled_kernel(L, orc, monkeypatch, M, m):
         outs[plain] = np.concatenate([q.execute_block(x[:17001], idx[:17001]), q.execute_block(x[17001:], idx[17001:])])
     monkeypatch.delenv("LIQUID_CUDA_FIRPFB_SIMPLE", raising=False)
     assert np.array_equal(outs[False].view(np.uint32), outs[True].view(np.uint32))
+    # the one-output-per-thread tile kernel the four-output one replaced
+    monkeypatch.setenv("LIQUID_CUDA_FIRPFB_TILE1", "1")
+    q = L.firpfb_crcf.create_kaiser(M, m, 0.4, 60.0)
+    tile1 = np.concatenate([q.execute_block(x[:17001], idx[:17001]), q.execute_block(x[17001:], idx[17001:])])
+    monkeypatch.delenv("LIQUID_CUDA_FIRPFB_TILE1")
+    assert np.array_equal(outs[False].view(np.uint32), tile1.view(np.uint32))
     qo = orc.Firpfb(M, kaiser=(m, 0.4, 60.0))
     for i in range(1500):
         qo.push(x[i])
