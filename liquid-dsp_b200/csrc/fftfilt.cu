@@ -24,6 +24,7 @@
 #include "../../include/liquid_cuda.h"
 #include "host_pipeline.cuh"
 #include "fft_device.cuh"
+#include "quad_fft.cuh"
 
 struct fftfilt_crcf_s {
     unsigned int h_len = 0, n = 0;
@@ -107,6 +108,54 @@ fftfilt_pow2_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ 
     lcfft::stockham_run<+1, TWG>(sb, N, log2N, per_cta, ProductSrc{X, Hf, log2N}, KeepDst{y, n, scale, b0, n_blocks});
 }
 
+// ---- 2n = 1024 / 2048 / 4096: the chained quad transforms of quad_fft.cuh (forward, product with H and backward in
+// registers and two shared tiles, no block-wide Stockham passes)
+struct SegmentSrcT {
+    const float2 *hist, *x;
+    unsigned int n;
+    // transform t covers stream samples (t - 1) n ... (t + 1) n - 1; the n samples before the call live in hist
+    __device__ __forceinline__ float2 load(long long t, unsigned int k) const
+    {
+        const long long idx = (t - 1) * (long long)n + k;
+        return idx >= 0 ? __ldg(x + idx) : __ldg(hist + (n + idx));
+    }
+    __device__ __forceinline__ float2 finish(long long, unsigned int, float2 raw) const { return raw; }
+};
+struct KeepDstT {
+    float2 *y;
+    unsigned int n;
+    float scale;
+    __device__ __forceinline__ void operator()(long long t, unsigned int k, float2 v) const
+    {
+        __stcs(y + t * n + (k - n), make_float2(v.x * scale, v.y * scale));
+    }
+};
+
+template <int RA>
+__global__ void __launch_bounds__(lcquad::kThreads, 2)
+fftfilt_quad_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, const float2 *__restrict__ Hf,
+                    const float2 *__restrict__ tw_f, const float2 *__restrict__ tw_b, float2 *__restrict__ y, long long n_blocks,
+                    int tiles_per_inst, float scale)
+{
+    extern __shared__ __align__(16) unsigned char smem_quad[];
+    lcquad::run_chain<RA, true>(smem_quad, tw_f, tw_b, Hf, n_blocks, tiles_per_inst, SegmentSrcT{hist, x, 128u * RA},
+                                KeepDstT{y, 128u * RA, scale});
+}
+
+template <int RA>
+void launch_fftfilt_quad(fftfilt_crcf q, const float2 *d_x, unsigned long long n_blocks, float2 *d_y, cudaStream_t st)
+{
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(fftfilt_quad_kernel<RA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)lcquad::chain_smem_bytes<RA>()));
+    unsigned int grid = 0;
+    int tpi = 1;
+    lcquad::plan(RA, n_blocks, grid, tpi);
+    fftfilt_quad_kernel<RA><<<grid, lcquad::kThreads, lcquad::chain_smem_bytes<RA>(), st>>>(
+        q->d_hist, d_x, q->d_H, q->fwd.d_tw_tile, q->bwd.d_tw_tile, d_y, (long long)n_blocks, tpi, q->scale);
+}
+
 // ---- any other n: through scratch ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 fftfilt_gather_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, unsigned int n, float2 *__restrict__ seg,
@@ -158,7 +207,13 @@ void blocks_dev(fftfilt_crcf q, const float2 *d_x, unsigned long long n_blocks, 
 {
     if (n_blocks == 0) return;
     const unsigned int n = q->n, N = 2 * n;
-    if (lcfft::pow2_in_smem(N) && pow2_smem(N, 1) <= 200 * 1024 && !getenv("LIQUID_CUDA_FFTFILT_GENERIC")) {
+    if (lcquad::supported(N) && q->fwd.d_tw_tile && q->bwd.d_tw_tile && n_blocks < (1ull << 31) && !getenv("LIQUID_CUDA_FFTFILT_GENERIC") &&
+        !getenv("LIQUID_CUDA_FFTFILT_STOCKHAM") && !getenv("LIQUID_CUDA_NO_FUSED")) {
+        if (N == 1024) launch_fftfilt_quad<4>(q, d_x, n_blocks, d_y, st);
+        else if (N == 2048) launch_fftfilt_quad<8>(q, d_x, n_blocks, d_y, st);
+        else launch_fftfilt_quad<16>(q, d_x, n_blocks, d_y, st);
+        LC_LAUNCH_CHECK();
+    } else if (lcfft::pow2_in_smem(N) && pow2_smem(N, 1) <= 200 * 1024 && !getenv("LIQUID_CUDA_FFTFILT_GENERIC")) {
         static std::atomic<unsigned long long> configured{0};
         if (lc::first_time_on_device(configured)) {
             LC_CUDA_CHECK(cudaFuncSetAttribute(fftfilt_pow2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

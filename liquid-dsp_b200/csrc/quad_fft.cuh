@@ -150,6 +150,129 @@ __device__ __forceinline__ void run(unsigned char *smem_raw, const float2 *__res
         post(tr0, (int)(n_tr - tr0 < FR ? n_tr - tr0 : FR));
     }
 }
+
+// Forward transform, product with a frequency response, backward transform, in one kernel and without an exchange in
+// between: after phase 2 of the forward transform a thread holds X[RA c + pp + 16 RA k2], k2 < 16 -- with k2 = g + (16 / RA) q
+// these are, for each g, exactly the RA inputs u' + 256 q (u' = RA c + pp + 16 RA g) that ONE thread of the backward
+// transform's phase 1 needs.  So the thread multiplies its 16 values by H, does the 16 / RA first-stage DFTs of the backward
+// transform in registers and writes the backward sub-problems into the second tile buffer.  Two block barriers per tile.
+// tw_f / tw_b: the forward / backward tables of make_twiddles; Hf[N] in natural order.  UPPER: only outputs N/2 ... N-1
+// are handed to dst (overlap-save keeps the second half).
+template <int RA, bool UPPER, class Src, class Dst>
+__device__ __forceinline__ void run_chain(unsigned char *smem_raw, const float2 *__restrict__ tw_f, const float2 *__restrict__ tw_b,
+                                          const float2 *__restrict__ Hf, long long n_tr, int tiles_per_inst, Src src, Dst &&dst)
+{
+    constexpr int FR = 16 / RA, NG = 16 / RA, SP = Pitch<RA>::SP, GRP = 16 * RA;
+    float2 *bufA = reinterpret_cast<float2 *>(smem_raw);
+    float2 *bufB = bufA + 16 * SP;
+    float2 *twsf = bufB + 16 * SP;                                    // [r2][k1], pitch 18: forward, then backward
+    float2 *twsb = twsf + 16 * kTwPitch;
+    const int u = threadIdx.x;
+    const long long n_tiles = (n_tr + FR - 1) / FR;
+    const long long t0 = (long long)blockIdx.x * tiles_per_inst;
+    long long ntl = n_tiles - t0;
+    if (ntl > tiles_per_inst) ntl = tiles_per_inst;
+    const int nt = ntl > 0 ? (int)ntl : 0;
+
+    float2 nx[16];
+    auto fetch = [&](int it) {
+        const long long tr0 = (t0 + it) * FR;
+#pragma unroll
+        for (int f = 0; f < FR; f++) {
+            const bool ok = it < nt && tr0 + f < n_tr;
+#pragma unroll
+            for (int q = 0; q < RA; q++) nx[f * RA + q] = ok ? src.load(tr0 + f, (unsigned int)(u + 256 * q)) : make_float2(0.f, 0.f);
+        }
+    };
+    fetch(0);
+    twsf[(u & 15) * kTwPitch + (u >> 4)] = __ldg(tw_f + (RA - 1) * 256 + u);
+    twsb[(u & 15) * kTwPitch + (u >> 4)] = __ldg(tw_b + (RA - 1) * 256 + u);
+    const int f2 = u / GRP, pp = u % RA, c = (u % GRP) / RA;
+    const float4 *twcf = reinterpret_cast<const float4 *>(twsf + c * kTwPitch);
+    const float4 *twcb = reinterpret_cast<const float4 *>(twsb + c * kTwPitch);
+    const int z_off = (u >> 4) * 17 + (u & 15);
+    __syncthreads();
+
+    for (int it = 0; it < nt; it++) {
+        const long long tr0 = (t0 + it) * FR;
+        // ---- forward phase 1 -> buffer A
+#pragma unroll
+        for (int f = 0; f < FR; f++) {
+            float2 d[RA];
+#pragma unroll
+            for (int q = 0; q < RA; q++) d[q] = src.finish(tr0 + f, (unsigned int)(u + 256 * q), nx[f * RA + q]);
+            RegDft<RA, -1>::run(d);
+            float2 *zf = bufA + f * RA * SP + z_off;
+            zf[0] = d[0];
+#pragma unroll
+            for (int p = 1; p < RA; p++) zf[p * SP] = cmul2_rot(d[p], __ldg(tw_f + (p - 1) * 256 + u));
+        }
+        fetch(it + 1);
+        __syncthreads();
+        float2 v[16];
+        // ---- forward phase 2
+        {
+            float2 *sp = bufA + (f2 * RA + pp) * SP;
+#pragma unroll
+            for (int r1 = 0; r1 < 16; r1++) v[r1] = sp[r1 * 17 + c];
+            RegDft<16, -1>::run(v);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float4 t = twcf[k];
+                if (k > 0) v[2 * k] = cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+                v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+            }
+#pragma unroll
+            for (int k1 = 0; k1 < 16; k1++) sp[k1 * 17 + c] = v[k1];
+            if (GRP == kThreads) __syncthreads();
+            else asm volatile("bar.sync %0, %1;" ::"r"(1 + f2), "n"(GRP) : "memory");
+#pragma unroll
+            for (int cc = 0; cc < 16; cc++) v[cc] = sp[c * 17 + cc];
+            RegDft<16, -1>::run(v);
+        }
+        // ---- product with H and backward phase 1 -> buffer B
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) v[k2] = cmul2_rot(v[k2], __ldg(Hf + RA * c + pp + GRP * k2));
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            float2 d[RA];
+#pragma unroll
+            for (int q = 0; q < RA; q++) d[q] = v[g + NG * q];
+            RegDft<RA, +1>::run(d);
+            const int up = RA * c + pp + GRP * g;
+            float2 *zb = bufB + f2 * RA * SP + (up >> 4) * 17 + (up & 15);
+            zb[0] = d[0];
+#pragma unroll
+            for (int p = 1; p < RA; p++) zb[p * SP] = cmul2_rot(d[p], __ldg(tw_b + (p - 1) * 256 + up));
+        }
+        __syncthreads();
+        // ---- backward phase 2
+        {
+            float2 *sp = bufB + (f2 * RA + pp) * SP;
+#pragma unroll
+            for (int r1 = 0; r1 < 16; r1++) v[r1] = sp[r1 * 17 + c];
+            RegDft<16, +1>::run(v);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float4 t = twcb[k];
+                if (k > 0) v[2 * k] = cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+                v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+            }
+#pragma unroll
+            for (int k1 = 0; k1 < 16; k1++) sp[k1 * 17 + c] = v[k1];
+            if (GRP == kThreads) __syncthreads();
+            else asm volatile("bar.sync %0, %1;" ::"r"(1 + f2), "n"(GRP) : "memory");
+#pragma unroll
+            for (int cc = 0; cc < 16; cc++) v[cc] = sp[c * 17 + cc];
+            RegDft<16, +1>::run(v);
+        }
+        if (tr0 + f2 < n_tr) {
+#pragma unroll
+            for (int k2 = UPPER ? 8 : 0; k2 < 16; k2++) dst(tr0 + f2, (unsigned int)(RA * c + pp + GRP * k2), v[k2]);
+        }
+    }
+}
+template <int RA> constexpr size_t chain_smem_bytes() { return sizeof(float2) * ((size_t)2 * 16 * Pitch<RA>::SP + 2 * 16 * kTwPitch); }
 #endif
 
 }  // namespace lcquad
