@@ -627,6 +627,20 @@ def main():
                                                        "24 B per sample (firpfbch2) / 16 B per sample (firpfbch) against the measured HBM peak",
                                                "shapes": shapes}
         torch.cuda.empty_cache()
+        # the kernels the channelizers reduce to or feed (SURVEY a8 / a9 / a11 / a13 and the 8(f) rows), shape by shape:
+        # firfilt over filter lengths, dotprod batch, firpfb, the batched FFT over sizes, ofdmframegen, spgramcf, fftfilt
+        callees = {}
+        for cfg in ("ff", "d", "p", "fft", "f6", "f2", "f5"):
+            try:
+                bench_configs.run([cfg], args.other_steps, 2,
+                                  lambda line: callees.__setitem__(line["config"], {"GSps": round(line["value"] / 1e3, 1),
+                                                                                    "roofline_frac": round(line["roofline"]["frac"], 3),
+                                                                                    "bytes_per_sample": line["roofline"]["algorithmic_bytes_per_sample"]}),
+                                  device_index=local_rank)
+            except Exception as e:          # noqa: BLE001
+                callees[cfg] = {"error": str(e)}
+            torch.cuda.empty_cache()
+        other["callees_and_next_rows"] = callees
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
