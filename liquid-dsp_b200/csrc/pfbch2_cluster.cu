@@ -63,7 +63,12 @@ constexpr int kFrameBytes = 64 * 64 * 8 / kCluster;            // bytes of Z one
 template <int L> struct Rings;
 template <> struct Rings<18> { static constexpr int XS = 12, D = 9; };
 template <> struct Rings<14> { static constexpr int XS = 14, D = 7; };
+template <> struct Rings<16> { static constexpr int XS = 16, D = 8; };
+template <> struct Rings<12> { static constexpr int XS = 12, D = 6; };
+template <> struct Rings<10> { static constexpr int XS = 10, D = 10; };
 template <> struct Rings<8>  { static constexpr int XS = 16, D = 8; };
+template <> struct Rings<6>  { static constexpr int XS = 12, D = 6; };
+template <> struct Rings<4>  { static constexpr int XS = 8, D = 4; };
 constexpr int kMaxXS = 16;
 
 // shared memory carve-up (bytes); barriers first so that their offsets do not depend on L
@@ -502,7 +507,7 @@ namespace pfb {
 
 bool cluster_pfbch2_supported(unsigned int M, unsigned int L)
 {
-    return M == 4096 && (L == 8 || L == 14 || L == 18);
+    return M == 4096 && (L == 4 || L == 6 || L == 8 || L == 10 || L == 12 || L == 14 || L == 16 || L == 18);
 }
 
 void cluster_pfbch2_make_twiddles(std::vector<float2> &tw)
@@ -544,8 +549,13 @@ long long launch_pfbch2_cluster(const float2 *d_hist, const float2 *d_x, int H, 
     a.tw = d_tw;
     a.H = H;
     switch (L) {
+    case 4: return run_L<4>(a, n_groups, parity0 & 1, st);
+    case 6: return run_L<6>(a, n_groups, parity0 & 1, st);
     case 8: return run_L<8>(a, n_groups, parity0 & 1, st);
+    case 10: return run_L<10>(a, n_groups, parity0 & 1, st);
+    case 12: return run_L<12>(a, n_groups, parity0 & 1, st);
     case 14: return run_L<14>(a, n_groups, parity0 & 1, st);
+    case 16: return run_L<16>(a, n_groups, parity0 & 1, st);
     case 18: return run_L<18>(a, n_groups, parity0 & 1, st);
     default: fatal("launch_pfbch2_cluster", "unsupported tap count");
     }

@@ -1330,7 +1330,7 @@ def test_spgramcf_tile_and_quad_transforms(L, orc, monkeypatch, nfft, wl):
 
 
 # ------------------------------------------------------------------ cluster-of-8 M=4096 kernel specifics
-@pytest.mark.parametrize("m", [4, 7, 9])
+@pytest.mark.parametrize("m", [2, 3, 4, 5, 6, 7, 8, 9])
 def test_pfbch2_cluster_4096_vs_oracle_odd_splits(L, orc, m):
     """the cluster kernel (M=4096, one frame per 8 CTAs, DSMEM exchange) across: odd start parity,
     frame counts that are not a multiple of the 4-frame group, several clusters, state carried

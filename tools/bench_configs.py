@@ -170,15 +170,15 @@ def run(configs, steps, warmup, sink, device_index=0):
                 del x, y
     if "c5m" in args.configs:
         # the cluster kernel (M=4096) at the filter lengths it is instantiated for
-        for m in (4, 7, 9):
-            M, n = 4096, 1 << 29
+        for m in (2, 3, 4, 5, 6, 7, 8, 9):
+            M, n = 4096, 1 << 28
             q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)
             H = q.get_state_len()
             x = torch.zeros(2 * (H + n), dtype=torch.float32, device=dev)
             y = torch.empty(4 * n, dtype=torch.float32, device=dev)
             L.synth_input_dev(x.data_ptr() + 8 * H, n, stream=st.cuda_stream)
             ms, ln = timed(lambda: q.execute_segment_dev(x.data_ptr(), x.data_ptr() + 8 * H, 0, n // (M // 2), y.data_ptr(), st.cuda_stream))
-            report("c5m: firpfbch2_crcf analysis M=4096 m=%d, 2^29 samples" % m, n, 24, ms, ln)
+            report("c5m: firpfbch2_crcf analysis M=4096 m=%d, 2^28 samples" % m, n, 24, ms, ln)
             del x, y
     if "s" in args.configs:
         # synthesizers (a4, a6): firpfbch2 M=1024 m=7 (2^27 output samples) and firpfbch M=1024 m=2 / M=256 m=5
