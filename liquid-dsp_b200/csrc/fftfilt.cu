@@ -25,6 +25,7 @@
 #include "host_pipeline.cuh"
 #include "fft_device.cuh"
 #include "quad_fft.cuh"
+#include "tile_fft.cuh"
 
 struct fftfilt_crcf_s {
     unsigned int h_len = 0, n = 0;
@@ -156,6 +157,33 @@ void launch_fftfilt_quad(fftfilt_crcf q, const float2 *d_x, unsigned long long n
         q->d_hist, d_x, q->d_H, q->fwd.d_tw_tile, q->bwd.d_tw_tile, d_y, (long long)n_blocks, tpi, q->scale);
 }
 
+// ---- 2n = 256 / 512: the chained tile transforms of tile_fft.cuh (the backward transform is the transpose of the forward
+// one and starts from the pair of outputs the forward transform leaves in each thread)
+template <int M>
+__global__ void __launch_bounds__(lctile::kThreads, 2)
+fftfilt_tile_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, const float2 *__restrict__ Hf,
+                    const float2 *__restrict__ tw_f, const float2 *__restrict__ tw_b, float2 *__restrict__ y, long long n_blocks,
+                    int tiles_per_inst, float scale)
+{
+    extern __shared__ __align__(16) unsigned char smem_tile[];
+    lctile::run_chain<M, true>(smem_tile, tw_f, tw_b, Hf, n_blocks, tiles_per_inst, SegmentSrcT{hist, x, (unsigned int)M / 2},
+                               KeepDstT{y, (unsigned int)M / 2, scale});
+}
+
+template <int M>
+void launch_fftfilt_tile(fftfilt_crcf q, const float2 *d_x, unsigned long long n_blocks, float2 *d_y, cudaStream_t st)
+{
+    static std::atomic<unsigned long long> configured{0};
+    if (lc::first_time_on_device(configured))
+        LC_CUDA_CHECK(cudaFuncSetAttribute(fftfilt_tile_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)lctile::chain_smem_bytes<M>()));
+    unsigned int grid = 0;
+    int tpi = 1;
+    lctile::plan(M, n_blocks, grid, tpi);
+    fftfilt_tile_kernel<M><<<grid, lctile::kThreads, lctile::chain_smem_bytes<M>(), st>>>(
+        q->d_hist, d_x, q->d_H, q->fwd.d_tw_tile, q->bwd.d_tw_tile, d_y, (long long)n_blocks, tpi, q->scale);
+}
+
 // ---- any other n: through scratch ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 fftfilt_gather_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, unsigned int n, float2 *__restrict__ seg,
@@ -212,6 +240,11 @@ void blocks_dev(fftfilt_crcf q, const float2 *d_x, unsigned long long n_blocks, 
         if (N == 1024) launch_fftfilt_quad<4>(q, d_x, n_blocks, d_y, st);
         else if (N == 2048) launch_fftfilt_quad<8>(q, d_x, n_blocks, d_y, st);
         else launch_fftfilt_quad<16>(q, d_x, n_blocks, d_y, st);
+        LC_LAUNCH_CHECK();
+    } else if ((N == 256 || N == 512) && q->fwd.d_tw_tile && q->bwd.d_tw_tile && n_blocks < (1ull << 31) &&
+               !getenv("LIQUID_CUDA_FFTFILT_GENERIC") && !getenv("LIQUID_CUDA_FFTFILT_STOCKHAM") && !getenv("LIQUID_CUDA_NO_FUSED")) {
+        if (N == 256) launch_fftfilt_tile<256>(q, d_x, n_blocks, d_y, st);
+        else launch_fftfilt_tile<512>(q, d_x, n_blocks, d_y, st);
         LC_LAUNCH_CHECK();
     } else if (lcfft::pow2_in_smem(N) && pow2_smem(N, 1) <= 200 * 1024 && !getenv("LIQUID_CUDA_FFTFILT_GENERIC")) {
         static std::atomic<unsigned long long> configured{0};

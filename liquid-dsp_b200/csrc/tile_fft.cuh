@@ -178,6 +178,144 @@ __device__ __forceinline__ void run(unsigned char *smem_raw, const float2 *__res
         if (NBUF == 1) inst_barrier();
     }
 }
+
+// Forward transform, product with a frequency response, backward transform in one kernel (fftfilt_crcf, 2n = 64 ... 512).
+// The forward transform is run<M, -1> above with a destination that keeps out[u] and out[u + M/2] in the owning thread;
+// the backward transform is its TRANSPOSE (decimation in frequency), which starts exactly from that pair:
+//   a[u] = X[u] + X[u + M/2],  b[u] = (X[u] - X[u + M/2]) W_M^(+u)           in the owning thread, written to the tile
+//   16-point DFTs down the columns (u = 16-row index * R2 + column), twiddle W_(M/2)^(column k1), in place
+//   R2-point DFTs along the rows -> x[2 (k1 + 16 k2) + p]
+// so no exchange is needed between the two transforms.  tw_f / tw_b: forward / backward tables of make_twiddles, Hf[M]
+// natural order.  UPPER: only outputs M/2 ... M-1 go to dst.  Same tile buffers as run(): the backward transform of
+// tile `it` works in the buffer the forward transform just left (its reads are complete after the instance barrier).
+template <int M, bool UPPER, class Src, class Dst>
+__device__ __forceinline__ void run_chain(unsigned char *smem_raw, const float2 *__restrict__ tw_f, const float2 *__restrict__ tw_b,
+                                          const float2 *__restrict__ Hf, long long n_tr, int tiles_per_inst, Src src, Dst &&dst)
+{
+    using LY = Layout<M>;
+    constexpr int M2 = M / 2, R2 = M2 / 16;
+    constexpr int PR = LY::PR, SS = LY::SS, FS = LY::FS, NBUF = LY::NBUF;
+    constexpr int RPT = 16 / R2;
+    static_assert(!LY::WIDE, "the chained form is written for M = 256 / 512");
+    const int inst_l = threadIdx.x / M2, u = threadIdx.x % M2;
+    float2 *tile0 = reinterpret_cast<float2 *>(smem_raw) + inst_l * (NBUF * kFr * FS);
+    float2 *twsf = reinterpret_cast<float2 *>(smem_raw) + (kThreads / M2) * (NBUF * kFr * FS);
+    float2 *twsb = twsf + R2 * kTwPitch;
+    const long long inst = (long long)blockIdx.x * (kThreads / M2) + inst_l;
+    const long long n_tiles = (n_tr + kFr - 1) / kFr;
+    const long long t0 = inst * tiles_per_inst;
+    long long ntl = n_tiles - t0;
+    if (ntl > tiles_per_inst) ntl = tiles_per_inst;
+    const int nt = ntl > 0 ? (int)ntl : 0;
+
+    auto inst_barrier = [&]() {
+        if (M2 == kThreads) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + inst_l), "n"(M2) : "memory");
+    };
+    const int f2 = u / (2 * R2), p2 = u & 1, t2 = (u % (2 * R2)) >> 1;
+    float2 nx[16];
+    auto fetch = [&](int it) {
+        const long long tr0 = (t0 + it) * kFr;
+        const bool ok = it < nt && tr0 + f2 < n_tr;
+#pragma unroll
+        for (int i = 0; i < RPT; i++)
+#pragma unroll
+            for (int k2 = 0; k2 < R2; k2++)
+                nx[i * R2 + k2] = ok ? src.load(tr0 + f2, (unsigned int)(2 * (t2 + R2 * i) + p2 + 32 * k2)) : make_float2(0.f, 0.f);
+    };
+    fetch(0);
+    for (int i = u; i < 16 * R2; i += M2) {
+        twsf[(i % R2) * kTwPitch + i / R2] = __ldg(tw_f + M2 + i);
+        twsb[(i % R2) * kTwPitch + i / R2] = __ldg(tw_b + M2 + i);
+    }
+    const float2 w2f = __ldg(tw_f + u), w2b = __ldg(tw_b + u);
+    const float2 h_lo = __ldg(Hf + u), h_hi = __ldg(Hf + u + M2);
+    const float4 *twcf = reinterpret_cast<const float4 *>(twsf + t2 * kTwPitch);
+    const float4 *twcb = reinterpret_cast<const float4 *>(twsb + t2 * kTwPitch);
+    const int mac_off = (u / R2) * PR + (u % R2);
+    const int sp_off = f2 * FS + p2 * SS;
+    __syncthreads();
+
+    for (int it = 0; it < nt; it++) {
+        const long long tr0 = (t0 + it) * kFr;
+        float2 *tile = tile0 + (it % NBUF) * (kFr * FS);
+        float2 *sp = tile + sp_off;
+        // ---- forward: rows, columns (as run<M, -1>)
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            float2 r[R2];
+#pragma unroll
+            for (int k2 = 0; k2 < R2; k2++) r[k2] = src.finish(tr0 + f2, (unsigned int)(2 * (t2 + R2 * i) + p2 + 32 * k2), nx[i * R2 + k2]);
+            RegDft<R2, -1>::run(r);
+            float2 *row = sp + (t2 + R2 * i) * PR;
+#pragma unroll
+            for (int c = 0; c < R2; c++) row[c] = r[c];
+        }
+        fetch(it + 1);
+        __syncwarp();
+        {
+            float2 v[16];
+#pragma unroll
+            for (int k1 = 0; k1 < 16; k1++) v[k1] = sp[k1 * PR + t2];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float4 t = twcf[k];
+                if (k > 0) v[2 * k] = cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+                v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+            }
+            RegDft<16, -1>::run(v);
+#pragma unroll
+            for (int r1 = 0; r1 < 16; r1++) sp[r1 * PR + t2] = v[r1];
+        }
+        inst_barrier();
+        // ---- last forward stage, product with H, first backward stage: all in the thread that owns u and u + M/2
+        float2 *own = tile + mac_off;
+#pragma unroll
+        for (int f = 0; f < kFr; f++) {
+            const float2 e0 = own[f * FS];
+            const float2 t = cmul2_rot(own[f * FS + SS], w2f);
+            const float2 xl = cmul2_rot(__fadd2_rn(e0, t), h_lo);
+            const float2 xh = cmul2_rot(__fadd2_rn(e0, neg2(t)), h_hi);
+            own[f * FS] = __fadd2_rn(xl, xh);
+            own[f * FS + SS] = cmul2_rot(__fadd2_rn(xl, neg2(xh)), w2b);
+        }
+        inst_barrier();
+        // ---- backward: columns (DFT, then twiddle), rows
+        {
+            float2 v[16];
+#pragma unroll
+            for (int r1 = 0; r1 < 16; r1++) v[r1] = sp[r1 * PR + t2];
+            RegDft<16, +1>::run(v);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float4 t = twcb[k];
+                if (k > 0) v[2 * k] = cmul2_rot(v[2 * k], make_float2(t.x, t.y));
+                v[2 * k + 1] = cmul2_rot(v[2 * k + 1], make_float2(t.z, t.w));
+            }
+#pragma unroll
+            for (int k1 = 0; k1 < 16; k1++) sp[k1 * PR + t2] = v[k1];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            float2 r[R2];
+            const float2 *row = sp + (t2 + R2 * i) * PR;
+#pragma unroll
+            for (int c = 0; c < R2; c++) r[c] = row[c];
+            RegDft<R2, +1>::run(r);
+            if (tr0 + f2 < n_tr) {
+#pragma unroll
+                for (int k2 = UPPER ? R2 / 2 : 0; k2 < R2; k2++) dst(tr0 + f2, (unsigned int)(2 * (t2 + R2 * i + 16 * k2) + p2), r[k2]);
+            }
+        }
+        if (NBUF == 1) inst_barrier();
+    }
+}
+template <int M>
+constexpr size_t chain_smem_bytes()
+{
+    return sizeof(float2) * ((size_t)(kThreads / (M / 2)) * Layout<M>::NBUF * kFr * Layout<M>::FS + (size_t)2 * (M / 32) * kTwPitch);
+}
 #endif
 
 }  // namespace lctile

@@ -1260,7 +1260,7 @@ def test_fftfilt_vs_reference_fixture_and_oracle(L, orc, refrn2, monkeypatch):
             assert np.abs(q.execute_block(x) - want).max() < 2e-6 * np.abs(want).max(), (tag, generic)
         monkeypatch.delenv("LIQUID_CUDA_FFTFILT_GENERIC", raising=False)
     x = orc.synth_input(1 << 20, seed=0x41)
-    for h_len, n in ((129, 128), (513, 512), (77, 512), (1025, 1024), (300, 2048), (2049, 2048), (200, 500)):
+    for h_len, n in ((129, 128), (40, 128), (257, 256), (100, 256), (513, 512), (77, 512), (1025, 1024), (300, 2048), (2049, 2048), (200, 500)):
         h = orc.firdes_kaiser(h_len, 0.15, 60.0)
         q = L.fftfilt_crcf(h, n)
         nb = len(x) // n
@@ -1268,8 +1268,9 @@ def test_fftfilt_vs_reference_fixture_and_oracle(L, orc, refrn2, monkeypatch):
         got = np.concatenate([q.execute_block(x[:cut]), q.execute_block(x[cut:nb * n])])
         want = orc.Fftfilt(h, n).execute_blocks(x[:nb * n])
         assert np.abs(got - want).max() < 4e-6 * np.abs(want).max(), (h_len, n)
-        if n in (512, 1024, 2048):
-            # 2n = 1024 ... 4096 run the chained quad transforms: against the shared-memory Stockham kernel they replaced
+        if n in (128, 256, 512, 1024, 2048):
+            # 2n = 256 / 512 run the chained tile transforms, 2n = 1024 ... 4096 the chained quad transforms: against the
+            # shared-memory Stockham kernel they replaced
             monkeypatch.setenv("LIQUID_CUDA_FFTFILT_STOCKHAM", "1")
             q2 = L.fftfilt_crcf(h, n)
             old = np.concatenate([q2.execute_block(x[:cut]), q2.execute_block(x[cut:nb * n])])

@@ -374,7 +374,7 @@ def run(configs, steps, warmup, sink, device_index=0):
         x = torch.empty(2 * n_s, dtype=torch.float32, device=dev)
         y = torch.empty(2 * n_s, dtype=torch.float32, device=dev)
         L.synth_input_dev(x.data_ptr(), n_s, stream=st.cuda_stream)
-        for h_len, n in ((257, 256), (513, 512), (1025, 1024), (2049, 2048)):
+        for h_len, n in ((129, 128), (257, 256), (513, 512), (1025, 1024), (2049, 2048)):
             h = L.liquid_firdes_kaiser(h_len, 0.2, 60.0, 0.0)
             q = L.fftfilt_crcf(h, n)
             ms, ln = timed(lambda: q.execute_block_dev(x.data_ptr(), n_s // n, y.data_ptr(), st.cuda_stream))
