@@ -471,9 +471,13 @@ void launch_pfbch2_synth_fir(const float2 *d_hist_rows, const float2 *d_v, int h
         bool done = false;
         switch (n_taps) {
         case 8: done = launch_synth_fir_reg<8>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
+        case 12: done = launch_synth_fir_reg<12>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
         case 16: done = launch_synth_fir_reg<16>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
         case 20: done = launch_synth_fir_reg<20>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
+        case 24: done = launch_synth_fir_reg<24>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
         case 28: done = launch_synth_fir_reg<28>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
+        case 32: done = launch_synth_fir_reg<32>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
+        case 36: done = launch_synth_fir_reg<36>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames, parity0, st); break;
         default: break;
         }
         if (done) return;

@@ -939,6 +939,20 @@ def test_pfbch_full_size_spot_checks_vs_oracle(L, orc, M, m, n_streams, log2n):
         L.lib.liquid_cuda_free(d)
 
 
+@pytest.mark.parametrize("M,m", [(2048, 3), (2048, 6), (2048, 8), (4096, 9), (1024, 7)])
+def test_pfbch2_two_kernel_synthesizer_register_fir(L, orc, M, m):
+    """synthesizer shapes without a fused kernel (batched IDFT, then the register-window FIR instantiated for 4m = 8 ... 36):
+    against the oracle, state carried over an awkward cut and over blocks below the 64-frame threshold"""
+    nfr = 64 * 3 + 17
+    X = orc.synth_input(nfr * M, seed=0x77 + M + m)
+    want = orc.Firpfbch2(orc.SYNTHESIZER, M, m, As=60.0).execute_frames(X)
+    q = L.firpfbch2_crcf.create_kaiser(L.LIQUID_SYNTHESIZER, M, m, 60.0)
+    cuts = [0, 70, 71, 75, 150, nfr]
+    got = np.concatenate([q.execute_block(X[a * M:b * M]) for a, b in zip(cuts[:-1], cuts[1:])])
+    q.destroy()
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5, (M, m)
+
+
 # ------------------------------------------------------------------ one-kernel shape-generic analyzers
 @pytest.mark.parametrize("M,m,nfr", [(8, 5, 37), (64, 3, 50), (256, 4, 33), (2048, 3, 19), (512, 6, 21)])
 def test_generic_one_kernel_analyzers_equal_two_kernel_path(L, orc, monkeypatch, M, m, nfr):
