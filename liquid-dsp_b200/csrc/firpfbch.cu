@@ -40,7 +40,11 @@ namespace {
 void analyze_generic(firpfbch_crcf q, const float2 *d_hist, const float2 *d_x, float2 *d_y, unsigned long long n,
                      unsigned int phase, unsigned int first, unsigned int k, cudaStream_t st)
 {
-    if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL")) {
+    // (see firpfbch2.cu: column-walking MAC + tile / quad transform for large aligned blocks)
+    const bool two_fast = phase == 0 && k == 0 && first >= q->M && first % q->M == 0 && q->M % 128 == 0 && n >= 64 &&
+                          q->fft.d_tw_tile != nullptr && !getenv("LIQUID_CUDA_ONE_KERNEL") && !getenv("LIQUID_CUDA_NO_FUSED") &&
+                          !getenv("LIQUID_CUDA_MAC_PLAIN");
+    if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL") && !two_fast) {
         lc::pfb::launch_pfbch_analyze_pow2(d_hist, d_x, (int)q->H, q->d_taps, q->fft.d_twp, d_y, q->M, q->p, n, phase, first, k, st);
         return;
     }

@@ -442,6 +442,108 @@ pfbch_synth_fir_kernel(const float2 *__restrict__ hist, const float2 *__restrict
     }
 }
 
+// ---- column-walking MAC kernels of the two-kernel fallback (shapes without a dedicated kernel: M = 2048, the critically
+// sampled M = 4096, filter lengths above the instantiated ones).  The element-per-thread MAC kernels above re-read every
+// sample 2m times with 64-bit index arithmetic per tap; here a thread owns ONE window (transform input), keeps its 2m
+// samples and taps in registers and walks a chunk of frames: one new sample per push, coalesced across the windows of a
+// warp, eight pushes loaded ahead of their use.  Same fmaf sequence per output (newest sample first): identical bits.
+constexpr int kColThreads = 128;
+constexpr int kColGroup = 8;                               // pushes per group
+
+// firpfbch2 analyzer: window w takes a sample every other frame and is read every frame with the tap set of the
+// frame's parity.  Frames are counted from b = the chunk's first frame rounded down to the window's push parity.
+template <int L>
+__global__ void __launch_bounds__(kColThreads)
+pfbch2_mac_cols_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ taps,
+                       float2 *__restrict__ X, unsigned int M, long long n_frames, int parity0, long long t_first, int fpc)
+{
+    const unsigned int M2 = M >> 1;
+    const unsigned int w = blockIdx.x * kColThreads + threadIdx.x;
+    const bool lower = w < M2;
+    const long long off = lower ? (long long)(M2 - 1 - w) : (long long)(M - 1 - w);
+    const long long c0 = (long long)blockIdx.y * fpc;                   // first frame of the chunk (relative to the block)
+    long long c1 = c0 + fpc;
+    if (c1 > n_frames) c1 = n_frames;
+    // absolute frame tt = t_first + t; the window is pushed on frames whose parity (parity0 + tt) & 1 equals (lower ? 0 : 1)
+    const long long tt0 = t_first + c0;
+    const int par0 = (parity0 + (int)(tt0 & 1)) & 1;
+    const long long b = (par0 == (lower ? 0 : 1)) ? tt0 : tt0 - 1;      // a push frame at or just before the chunk
+    const int pb = (parity0 + (int)(b & 1)) & 1;                         // tap set of frame b (= lower ? 0 : 1)
+    float h0[L], h1[L];                                                  // tap sets of frames b + 2r and b + 2r + 1
+#pragma unroll
+    for (int n = 0; n < L; n++) {
+        h0[n] = __ldg(taps + (size_t)pb * L * M + (size_t)n * M + w);
+        h1[n] = __ldg(taps + (size_t)(1 - pb) * L * M + (size_t)n * M + w);
+    }
+    float2 A[L - 1 + kColGroup];                                         // A[L - 1 + r] = sample of push frame b + 2 (j0 + r)
+#pragma unroll
+    for (int n = 1; n < L; n++) A[L - 1 - n] = lcd::ld_stream(hist, x, (b - 2LL * n) * (long long)M2 + off, H);
+    for (long long i0 = 0; b + i0 < t_first + c1; i0 += 2 * kColGroup) {
+#pragma unroll
+        for (int r = 0; r < kColGroup; r++) {
+            const long long tu = b + i0 + 2 * r;
+            A[L - 1 + r] = tu < t_first + c1 ? lcd::ld_stream(hist, x, tu * (long long)M2 + off, H) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < kColGroup; r++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const long long tt = b + i0 + 2 * r + e;
+                if (tt >= tt0 && tt < t_first + c1) {
+                    float re = 0.f, im = 0.f;
+#pragma unroll
+                    for (int n = 0; n < L; n++) {
+                        const float c = e ? h1[n] : h0[n];
+                        re = fmaf(c, A[L - 1 + r - n].x, re);
+                        im = fmaf(c, A[L - 1 + r - n].y, im);
+                    }
+                    X[(tt - t_first) * (long long)M + w] = make_float2(re, im);
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < L - 1; n++) A[n] = A[n + kColGroup];
+    }
+}
+
+// firpfbch analyzer, block-aligned (phase 0, k = 0): transform input u of frame t reads x[(t - n) M + u] with tap
+// taps[n M + (M - 1 - u)]
+template <int P>
+__global__ void __launch_bounds__(kColThreads)
+pfbch_mac_cols_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ taps,
+                      float2 *__restrict__ X, unsigned int M, long long n_frames, long long f_first, int fpc)
+{
+    const unsigned int u = blockIdx.x * kColThreads + threadIdx.x;
+    const long long c0 = (long long)blockIdx.y * fpc;
+    long long c1 = c0 + fpc;
+    if (c1 > n_frames) c1 = n_frames;
+    float h[P];
+#pragma unroll
+    for (int n = 0; n < P; n++) h[n] = __ldg(taps + (size_t)n * M + (M - 1 - u));
+    float2 A[P - 1 + kColGroup];
+#pragma unroll
+    for (int n = 1; n < P; n++) A[P - 1 - n] = lcd::ld_stream(hist, x, (f_first + c0 - n) * (long long)M + u, H);
+    for (long long t0 = c0; t0 < c1; t0 += kColGroup) {
+#pragma unroll
+        for (int r = 0; r < kColGroup; r++)
+            A[P - 1 + r] = t0 + r < c1 ? lcd::ld_stream(hist, x, (f_first + t0 + r) * (long long)M + u, H) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kColGroup; r++) {
+            if (t0 + r < c1) {
+                float re = 0.f, im = 0.f;
+#pragma unroll
+                for (int n = 0; n < P; n++) {
+                    re = fmaf(h[n], A[P - 1 + r - n].x, re);
+                    im = fmaf(h[n], A[P - 1 + r - n].y, im);
+                }
+                X[(t0 + r) * (long long)M + u] = make_float2(re, im);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < P - 1; n++) A[n] = A[n + kColGroup];
+    }
+}
+
 inline unsigned int grid_for(unsigned long long total)
 {
     unsigned long long b = (total + kThreads - 1) / kThreads;
@@ -458,6 +560,28 @@ void launch_pfbch2_mac(const float2 *d_hist, const float2 *d_x, int H, const flo
                        unsigned int M, unsigned int L, unsigned long long n_frames, int parity0, cudaStream_t st,
                        long long t_first)
 {
+    if (M % (2 * kColThreads) == 0 && n_frames >= 64 && !getenv("LIQUID_CUDA_MAC_PLAIN")) {
+        const int fpc = 256;
+        const unsigned long long chunks = (n_frames + fpc - 1) / fpc;
+        if (chunks <= 65535) {
+            dim3 grid(M / kColThreads, (unsigned int)chunks);
+            bool done = true;
+            switch (L) {
+#define LC_COLS(LL)                                                                                                        \
+    case LL:                                                                                                               \
+        pfbch2_mac_cols_kernel<LL><<<grid, kColThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, (long long)n_frames, parity0, \
+                                                                 t_first, fpc);                                            \
+        break;
+                LC_COLS(2) LC_COLS(4) LC_COLS(6) LC_COLS(8) LC_COLS(10) LC_COLS(12) LC_COLS(14) LC_COLS(16) LC_COLS(18) LC_COLS(20)
+#undef LC_COLS
+            default: done = false;
+            }
+            if (done) {
+                LC_LAUNCH_CHECK();
+                return;
+            }
+        }
+    }
     pfbch2_mac_kernel<<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, L, n_frames, parity0, t_first);
     LC_LAUNCH_CHECK();
 }
@@ -491,6 +615,28 @@ void launch_pfbch_mac(const float2 *d_hist, const float2 *d_x, int H, const floa
                       unsigned int M, unsigned int p, unsigned long long n_frames, unsigned int phase,
                       unsigned int first, unsigned int k, cudaStream_t st)
 {
+    if (phase == 0 && k == 0 && first >= M && first % M == 0 && M % kColThreads == 0 && n_frames >= 64 && !getenv("LIQUID_CUDA_MAC_PLAIN")) {
+        const int fpc = 256;
+        const unsigned long long chunks = (n_frames + fpc - 1) / fpc;
+        if (chunks <= 65535) {
+            dim3 grid(M / kColThreads, (unsigned int)chunks);
+            const long long f_first = (long long)(first / M) - 1;         // frame of x the first run reads last
+            bool done = true;
+            switch (p) {
+#define LC_COLS(PP)                                                                                                       \
+    case PP:                                                                                                              \
+        pfbch_mac_cols_kernel<PP><<<grid, kColThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, (long long)n_frames, f_first, fpc); \
+        break;
+                LC_COLS(2) LC_COLS(4) LC_COLS(6) LC_COLS(8) LC_COLS(10) LC_COLS(12) LC_COLS(14) LC_COLS(16) LC_COLS(18) LC_COLS(20)
+#undef LC_COLS
+            default: done = false;
+            }
+            if (done) {
+                LC_LAUNCH_CHECK();
+                return;
+            }
+        }
+    }
     pfbch_mac_kernel<float><<<grid_for(n_frames * M), kThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, p, n_frames, phase, first, k);
     LC_LAUNCH_CHECK();
 }

@@ -953,6 +953,35 @@ def test_pfbch2_two_kernel_synthesizer_register_fir(L, orc, M, m):
     assert np.abs(got - want).max() / np.abs(want).max() < 1e-5, (M, m)
 
 
+@pytest.mark.parametrize("M,m", [(2048, 2), (2048, 7), (4096, 3), (1024, 9), (256, 8), (512, 1)])
+def test_column_walking_mac_fallback(L, orc, monkeypatch, M, m):
+    """shapes without a dedicated analyzer, long blocks: column-walking MAC kernel + tile / quad transform.  Both
+    channelizers against the oracle over awkward cuts (odd frame counts move the firpfbch2 parity; blocks below 64 frames
+    take the one-kernel path), and the MAC bit for bit against the element-per-thread kernel"""
+    nfr = 64 * 3 + 37
+    x2 = orc.synth_input(nfr * M // 2, seed=0xB1 + M + m)
+    x1 = orc.synth_input(nfr * M, seed=0xB2 + M + m)
+    cuts = [0, 65, 66, 131, 140, nfr]
+    for kind, x, per in (("pfbch2", x2, M // 2), ("pfbch", x1, M)):
+        mk = (lambda: L.firpfbch2_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0)) if kind == "pfbch2" else \
+             (lambda: L.firpfbch_crcf.create_kaiser(L.LIQUID_ANALYZER, M, m, 60.0))
+        want = (orc.Firpfbch2(orc.ANALYZER, M, m, As=60.0) if kind == "pfbch2" else orc.Firpfbch(orc.ANALYZER, M, kaiser=(m, 60.0))).execute_frames(x)
+        q = mk()
+        got = np.concatenate([np.asarray(q.execute_block(x[a * per:b * per])).reshape(-1) for a, b in zip(cuts[:-1], cuts[1:])])
+        check_channels(got.reshape(nfr, M), np.asarray(want).reshape(nfr, M), x)
+        monkeypatch.setenv("LIQUID_CUDA_MAC_PLAIN", "1")
+        monkeypatch.setenv("LIQUID_CUDA_TWO_KERNEL", "1")
+        q2 = mk()
+        plain = np.concatenate([np.asarray(q2.execute_block(x[a * per:b * per])).reshape(-1) for a, b in zip(cuts[:-1], cuts[1:])])
+        monkeypatch.delenv("LIQUID_CUDA_MAC_PLAIN")
+        q3 = mk()
+        cols = np.concatenate([np.asarray(q3.execute_block(x[a * per:b * per])).reshape(-1) for a, b in zip(cuts[:-1], cuts[1:])])
+        monkeypatch.delenv("LIQUID_CUDA_TWO_KERNEL")
+        # the same transform after two MAC kernels with the same fmaf sequence: identical bits
+        assert np.array_equal(plain.view(np.uint32), cols.view(np.uint32)), (kind, M, m)
+        assert np.abs(got - plain).max() / np.abs(np.asarray(want)).max() < 2e-6
+
+
 # ------------------------------------------------------------------ one-kernel shape-generic analyzers
 @pytest.mark.parametrize("M,m,nfr", [(8, 5, 37), (64, 3, 50), (256, 4, 33), (2048, 3, 19), (512, 6, 21)])
 def test_generic_one_kernel_analyzers_equal_two_kernel_path(L, orc, monkeypatch, M, m, nfr):
