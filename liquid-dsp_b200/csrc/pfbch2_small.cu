@@ -510,6 +510,7 @@ void launch_analyzer_M(const SmallArgs &a, unsigned int L, unsigned int grid, cu
     case 8: launch_analyzer_ML<M, 8>(a, grid, st); break;
     case 10: launch_analyzer_ML<M, 10>(a, grid, st); break;
     case 12: launch_analyzer_ML<M, 12>(a, grid, st); break;
+    case 14: launch_analyzer_ML<M, 14>(a, grid, st); break;
     default: lc::fatal("launch_pfbch2_small", "unsupported tap count");
     }
 }
@@ -544,7 +545,7 @@ namespace pfb {
 
 bool small_pfbch2_supported(unsigned int M, unsigned int L)
 {
-    return (M == 4 || M == 8 || M == 16 || M == 32) && (L == 4 || L == 6 || L == 8 || L == 10 || L == 12);
+    return (M == 4 || M == 8 || M == 16 || M == 32) && (L == 4 || L == 6 || L == 8 || L == 10 || L == 12 || L == 14);
 }
 
 bool small_pfbch_supported(unsigned int M, unsigned int p)
@@ -627,6 +628,7 @@ long long launch_pfbch2_small(const float2 *d_hist, const float2 *d_x, int H, co
         else if (L == 8) LC_FRAME(4, 8);
         else if (L == 10) LC_FRAME(4, 10);
         else if (L == 12) LC_FRAME(4, 12);
+        else if (L == 14) LC_FRAME(4, 14);
         else fatal("launch_pfbch2_small", "unsupported shape");
 #undef LC_FRAME
         LC_LAUNCH_CHECK();

@@ -831,9 +831,9 @@ def test_pfbch_cccf_complex_taps_tile_analyzer(L, orc, monkeypatch, M, p):
 
 
 # ------------------------------------------------------------------ random block cuts across every dedicated kernel
-@pytest.mark.parametrize("ms,seed", [((2, 4, 5), 20261019), ((3, 6), 20261020)])
+@pytest.mark.parametrize("ms,seed", [((2, 4, 5), 20261019), ((3, 6), 20261020), ((7,), 20261021)])
 def test_channelizers_random_cuts_vs_oracle(L, orc, ms, seed):
-    """every shape with a dedicated kernel (M = 4 ... 1024; m = 2 ... 6), analysis and synthesis of both channelizers, fed
+    """every shape with a dedicated kernel (M = 4 ... 1024; m = 2 ... 7; at m = 7 only the firpfbch2 analyzers have one), analysis and synthesis of both channelizers, fed
     in seeded random block sizes that include single frames, blocks below the synthesizers' 4m-frame threshold (two-kernel
     path in between, state handed over) and ragged tiles: one stream of outputs whatever the cuts"""
     rng = np.random.default_rng(seed)
