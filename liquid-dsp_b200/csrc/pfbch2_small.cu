@@ -534,6 +534,9 @@ void launch_synth_M(const SmallArgs &a, unsigned int NT, unsigned int grid, cuda
     case 8: launch_synth_MN<M, 8>(a, grid, st); break;
     case 12: launch_synth_MN<M, 12>(a, grid, st); break;
     case 16: launch_synth_MN<M, 16>(a, grid, st); break;
+    case 20: launch_synth_MN<M, 20>(a, grid, st); break;
+    case 24: launch_synth_MN<M, 24>(a, grid, st); break;
+    case 28: launch_synth_MN<M, 28>(a, grid, st); break;
     default: lc::fatal("launch_pfbch2_small_synth", "unsupported tap count");
     }
 }
@@ -603,7 +606,8 @@ long long launch_pfbch_small(const float2 *d_hist, const float2 *d_x, int H, con
 
 bool small_pfbch2_synth_supported(unsigned int M, unsigned int n_taps)
 {
-    return (M == 4 || M == 8 || M == 16 || M == 32) && (n_taps == 8 || n_taps == 12 || n_taps == 16);
+    return ((M == 4 || M == 8 || M == 16 || M == 32) && (n_taps == 8 || n_taps == 12 || n_taps == 16)) ||
+           ((M == 8 || M == 16 || M == 32) && (n_taps == 20 || n_taps == 24 || n_taps == 28));
 }
 
 long long launch_pfbch2_small(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps_scaled, float2 *d_y,
