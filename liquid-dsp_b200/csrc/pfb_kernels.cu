@@ -705,7 +705,7 @@ bool launch_synth_fir_win(const float2 *d_hist_rows, const float2 *d_v, int hist
     case PP:                                                                                                         \
         pfbch_synth_fir_win_kernel<TapT, PP><<<grid, 128, 0, st>>>(d_hist_rows, d_v, hist_rows, d_taps, d_y, M, n_frames); \
         break;
-        LC_WIN(2) LC_WIN(3) LC_WIN(4) LC_WIN(5) LC_WIN(6) LC_WIN(7) LC_WIN(8) LC_WIN(10) LC_WIN(12) LC_WIN(14) LC_WIN(16)
+        LC_WIN(2) LC_WIN(3) LC_WIN(4) LC_WIN(5) LC_WIN(6) LC_WIN(7) LC_WIN(8) LC_WIN(10) LC_WIN(12) LC_WIN(14) LC_WIN(16) LC_WIN(18) LC_WIN(20)
 #undef LC_WIN
     default: return false;
     }
@@ -840,7 +840,7 @@ static void launch_pfbch_analyze_pow2_t(const float2 *d_hist, const float2 *d_x,
                                         unsigned int k, cudaStream_t st)
 {
     static std::atomic<unsigned long long> configured{0};
-#define LC_WIN_ALL LC_WIN(2) LC_WIN(3) LC_WIN(4) LC_WIN(5) LC_WIN(6) LC_WIN(7) LC_WIN(8) LC_WIN(10) LC_WIN(12) LC_WIN(14) LC_WIN(16)
+#define LC_WIN_ALL LC_WIN(2) LC_WIN(3) LC_WIN(4) LC_WIN(5) LC_WIN(6) LC_WIN(7) LC_WIN(8) LC_WIN(10) LC_WIN(12) LC_WIN(14) LC_WIN(16) LC_WIN(18) LC_WIN(20)
     if (first_time_on_device(configured)) {
         ensure_big_smem(pfbch_analyze_pow2_kernel<TapT>);
 #define LC_WIN(PP) ensure_big_smem(pfbch_analyze_pow2_win_kernel<TapT, PP>);
