@@ -553,7 +553,7 @@ bool small_pfbch2_supported(unsigned int M, unsigned int L)
 
 bool small_pfbch_supported(unsigned int M, unsigned int p)
 {
-    return (M == 4 || M == 8 || M == 32) && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12);
+    return ((M == 4 || M == 8 || M == 32) && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12)) || ((M == 8 || M == 32) && p == 14);   // (M = 4, p = 14: the generic kernel measured faster)
 }
 
 long long launch_pfbch_small(const float2 *d_hist, const float2 *d_x, int H, const float *d_taps, float2 *d_y, unsigned int M,
@@ -575,7 +575,8 @@ long long launch_pfbch_small(const float2 *d_hist, const float2 *d_x, int H, con
         else if (p == 6) pfbch_frame4_kernel<6><<<g, kThreads, 0, st>>>(a);
         else if (p == 8) pfbch_frame4_kernel<8><<<g, kThreads, 0, st>>>(a);
         else if (p == 10) pfbch_frame4_kernel<10><<<g, kThreads, 0, st>>>(a);
-        else pfbch_frame4_kernel<12><<<g, kThreads, 0, st>>>(a);
+        else if (p == 12) pfbch_frame4_kernel<12><<<g, kThreads, 0, st>>>(a);
+        else pfbch_frame4_kernel<14><<<g, kThreads, 0, st>>>(a);
         LC_LAUNCH_CHECK();
         return (long long)n_frames;
     }
@@ -593,11 +594,13 @@ long long launch_pfbch_small(const float2 *d_hist, const float2 *d_x, int H, con
     else if (M == 8 && p == 8) LC_PFB(8, 8);
     else if (M == 8 && p == 10) LC_PFB(8, 10);
     else if (M == 8 && p == 12) LC_PFB(8, 12);
+    else if (M == 8 && p == 14) LC_PFB(8, 14);
     else if (M == 32 && p == 4) LC_PFB(32, 4);
     else if (M == 32 && p == 6) LC_PFB(32, 6);
     else if (M == 32 && p == 8) LC_PFB(32, 8);
     else if (M == 32 && p == 10) LC_PFB(32, 10);
     else if (M == 32 && p == 12) LC_PFB(32, 12);
+    else if (M == 32 && p == 14) LC_PFB(32, 14);
     else fatal("launch_pfbch_small", "unsupported shape");
 #undef LC_PFB
     LC_LAUNCH_CHECK();

@@ -435,6 +435,7 @@ void launch_pfb_M(const PfbTileArgs &a, unsigned int P, dim3 grid, cudaStream_t 
     case 8: launch_pfb_MP<M, 8, TapT>(a, grid, st); break;
     case 10: launch_pfb_MP<M, 10, TapT>(a, grid, st); break;
     case 12: launch_pfb_MP<M, 12, TapT>(a, grid, st); break;
+    case 14: launch_pfb_MP<M, 14, TapT>(a, grid, st); break;
     default: lc::fatal("launch_pfbch_tile", "unsupported tap count");
     }
 }
@@ -1039,7 +1040,7 @@ void tile_pfbch2_make_twiddles(std::vector<float2> &tw, unsigned int M)
 bool tile_pfbch_supported(unsigned int M, unsigned int p)
 {
     // (M = 256 stays on pfbch_fused_256_kernel: this kernel measured 0.91 against 0.90 at p = 4 but 0.74 against 0.87 at p = 10)
-    return ((M == 64 || M == 128 || M == 512) && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12)) || (M == 256 && (p == 6 || p == 8 || p == 12));
+    return ((M == 64 || M == 128 || M == 512) && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12 || p == 14)) || (M == 256 && (p == 6 || p == 8 || p == 12 || p == 14));
 }
 
 void tile_pfbch_make_twiddles(std::vector<float2> &tw, unsigned int M)

@@ -599,7 +599,7 @@ namespace pfb {
 
 bool fused_pfbch_supported(unsigned int M, unsigned int p)
 {
-    return (M == 16 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12)) || (M == 256 && (p == 4 || p == 10)) || tile_pfbch_supported(M, p) ||
+    return (M == 16 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12 || p == 14)) || (M == 256 && (p == 4 || p == 10)) || tile_pfbch_supported(M, p) ||
            small_pfbch_supported(M, p) || (M == 1024 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12));
 }
 
@@ -706,6 +706,7 @@ long long launch_pfbch_fused(const float2 *d_hist, const float2 *d_x, int H, con
     else if (M == 16 && p == 8) pfbch_fused_16_kernel<8><<<grid, kThreads, 0, st>>>(a);
     else if (M == 16 && p == 10) pfbch_fused_16_kernel<10><<<grid, kThreads, 0, st>>>(a);
     else if (M == 16 && p == 12) pfbch_fused_16_kernel<12><<<grid, kThreads, 0, st>>>(a);
+    else if (M == 16 && p == 14) pfbch_fused_16_kernel<14><<<grid, kThreads, 0, st>>>(a);
     else if (M == 256 && p == 4) pfbch_fused_256_kernel<4><<<grid, kThreads, 0, st>>>(a);
     else if (M == 256 && p == 10) pfbch_fused_256_kernel<10><<<grid, kThreads, 0, st>>>(a);
     else fatal("launch_pfbch_fused", "unsupported shape");
