@@ -1107,7 +1107,7 @@ long long launch_pfbch_tile_cc(const float2 *d_hist, const float2 *d_x, int H, c
 
 bool tile_pfbch_synth_supported(unsigned int M, unsigned int p)
 {
-    return (M == 64 || M == 128 || M == 512) && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12);
+    return (M == 64 || M == 128 || M == 512) && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12 || p == 14);
 }
 
 template <int M, int P>
@@ -1129,6 +1129,7 @@ void launch_pfb_synth_M(const PfbSynthArgs &a, unsigned int p, dim3 grid, cudaSt
     case 8: launch_pfb_synth_MP<M, 8>(a, grid, st); break;
     case 10: launch_pfb_synth_MP<M, 10>(a, grid, st); break;
     case 12: launch_pfb_synth_MP<M, 12>(a, grid, st); break;
+    case 14: launch_pfb_synth_MP<M, 14>(a, grid, st); break;
     default: lc::fatal("launch_pfbch_tile_synth", "unsupported tap count");
     }
 }

@@ -600,12 +600,12 @@ namespace pfb {
 bool fused_pfbch_supported(unsigned int M, unsigned int p)
 {
     return (M == 16 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12 || p == 14)) || (M == 256 && (p == 4 || p == 10)) || tile_pfbch_supported(M, p) ||
-           small_pfbch_supported(M, p) || (M == 1024 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12));
+           small_pfbch_supported(M, p) || (M == 1024 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12 || p == 14));
 }
 
 bool fused_pfbch_synth_supported(unsigned int M, unsigned int p)
 {
-    return (M == 256 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12)) || (M == 1024 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12)) ||
+    return (M == 256 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12 || p == 14)) || (M == 1024 && (p == 4 || p == 6 || p == 8 || p == 10 || p == 12 || p == 14)) ||
            tile_pfbch_synth_supported(M, p);
 }
 
@@ -677,6 +677,7 @@ long long launch_pfbch_fused(const float2 *d_hist, const float2 *d_x, int H, con
         case 8: launch_quad_P<8>(q, grid, st); break;
         case 10: launch_quad_P<10>(q, grid, st); break;
         case 12: launch_quad_P<12>(q, grid, st); break;
+        case 14: launch_quad_P<14>(q, grid, st); break;
         default: fatal("launch_pfbch_fused", "unsupported shape");
         }
         LC_LAUNCH_CHECK();
@@ -743,6 +744,7 @@ long long launch_pfbch_synth_fused(const float2 *d_hist_rows, int n_hist_rows, c
         case 8: launch_quad_synth_P<8>(q, (long long)n_frames, grid, st); break;
         case 10: launch_quad_synth_P<10>(q, (long long)n_frames, grid, st); break;
         case 12: launch_quad_synth_P<12>(q, (long long)n_frames, grid, st); break;
+        case 14: launch_quad_synth_P<14>(q, (long long)n_frames, grid, st); break;
         default: fatal("launch_pfbch_synth_fused", "unsupported shape");
         }
         LC_LAUNCH_CHECK();
@@ -767,6 +769,7 @@ long long launch_pfbch_synth_fused(const float2 *d_hist_rows, int n_hist_rows, c
     else if (p == 6) pfbch_synth_fused_256_kernel<6><<<grid, kThreads, 0, st>>>(a);
     else if (p == 8) pfbch_synth_fused_256_kernel<8><<<grid, kThreads, 0, st>>>(a);
     else if (p == 12) pfbch_synth_fused_256_kernel<12><<<grid, kThreads, 0, st>>>(a);
+    else if (p == 14) pfbch_synth_fused_256_kernel<14><<<grid, kThreads, 0, st>>>(a);
     else if (p == 10) pfbch_synth_fused_256_kernel<10><<<grid, kThreads, 0, st>>>(a);
     else fatal("launch_pfbch_synth_fused", "unsupported shape");
     LC_LAUNCH_CHECK();
