@@ -41,7 +41,7 @@ void analyze_generic(firpfbch_crcf q, const float2 *d_hist, const float2 *d_x, f
                      unsigned int phase, unsigned int first, unsigned int k, cudaStream_t st)
 {
     // (see firpfbch2.cu: column-walking MAC + tile / quad transform for large aligned blocks)
-    const bool two_fast = phase == 0 && k == 0 && first >= q->M && first % q->M == 0 && q->M % 128 == 0 && n >= 64 &&
+    const bool two_fast = phase == 0 && k == 0 && first >= q->M && first % q->M == 0 && q->M % 64 == 0 && n >= 64 &&
                           q->fft.d_tw_tile != nullptr && !getenv("LIQUID_CUDA_ONE_KERNEL") && !getenv("LIQUID_CUDA_NO_FUSED") &&
                           !getenv("LIQUID_CUDA_MAC_PLAIN");
     if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL") && !two_fast) {

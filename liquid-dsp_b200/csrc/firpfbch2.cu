@@ -65,7 +65,7 @@ void analyze_dev(firpfbch2_crcf q, const float2 *d_hist, const float2 *d_x, int 
     float2 *d_yr = d_y + done * q->M;
     // large blocks of a shape whose transform runs on the tile / quad kernels: column-walking MAC kernel + batched transform
     // (two kernels at the HBM rate) beat the one-kernel shared-memory analyzer, whose fill re-reads every sample 2m times
-    const bool two_fast = q->M % 256 == 0 && n_frames - done >= 64 && q->fft.d_tw_tile != nullptr && !getenv("LIQUID_CUDA_ONE_KERNEL") &&
+    const bool two_fast = q->M % 64 == 0 && n_frames - done >= 64 && q->fft.d_tw_tile != nullptr && !getenv("LIQUID_CUDA_ONE_KERNEL") &&
                           !getenv("LIQUID_CUDA_NO_FUSED") && !getenv("LIQUID_CUDA_MAC_PLAIN");
     if (lc::pfb::analyze_pow2_supported(q->M) && !getenv("LIQUID_CUDA_TWO_KERNEL") && !two_fast) {
         // power-of-two M: polyphase MAC, backward FFT and /M in one kernel (shared memory)

@@ -458,7 +458,7 @@ pfbch2_mac_cols_kernel(const float2 *__restrict__ hist, const float2 *__restrict
                        float2 *__restrict__ X, unsigned int M, long long n_frames, int parity0, long long t_first, int fpc)
 {
     const unsigned int M2 = M >> 1;
-    const unsigned int w = blockIdx.x * kColThreads + threadIdx.x;
+    const unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;      // blockDim.x divides M/2: a CTA's windows share a half
     const bool lower = w < M2;
     const long long off = lower ? (long long)(M2 - 1 - w) : (long long)(M - 1 - w);
     const long long c0 = (long long)blockIdx.y * fpc;                   // first frame of the chunk (relative to the block)
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kColThreads)
 pfbch_mac_cols_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, int H, const float *__restrict__ taps,
                       float2 *__restrict__ X, unsigned int M, long long n_frames, long long f_first, int fpc)
 {
-    const unsigned int u = blockIdx.x * kColThreads + threadIdx.x;
+    const unsigned int u = blockIdx.x * blockDim.x + threadIdx.x;
     const long long c0 = (long long)blockIdx.y * fpc;
     long long c1 = c0 + fpc;
     if (c1 > n_frames) c1 = n_frames;
@@ -560,16 +560,17 @@ void launch_pfbch2_mac(const float2 *d_hist, const float2 *d_x, int H, const flo
                        unsigned int M, unsigned int L, unsigned long long n_frames, int parity0, cudaStream_t st,
                        long long t_first)
 {
-    if (M % (2 * kColThreads) == 0 && n_frames >= 64 && !getenv("LIQUID_CUDA_MAC_PLAIN")) {
+    const unsigned int col_threads = (M / 2) % kColThreads == 0 ? kColThreads : (M / 2) % 64 == 0 ? 64 : 32;
+    if ((M / 2) % 32 == 0 && n_frames >= 64 && !getenv("LIQUID_CUDA_MAC_PLAIN")) {
         const int fpc = 256;
         const unsigned long long chunks = (n_frames + fpc - 1) / fpc;
         if (chunks <= 65535) {
-            dim3 grid(M / kColThreads, (unsigned int)chunks);
+            dim3 grid(M / col_threads, (unsigned int)chunks);
             bool done = true;
             switch (L) {
 #define LC_COLS(LL)                                                                                                        \
     case LL:                                                                                                               \
-        pfbch2_mac_cols_kernel<LL><<<grid, kColThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, (long long)n_frames, parity0, \
+        pfbch2_mac_cols_kernel<LL><<<grid, col_threads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, (long long)n_frames, parity0, \
                                                                  t_first, fpc);                                            \
         break;
                 LC_COLS(2) LC_COLS(4) LC_COLS(6) LC_COLS(8) LC_COLS(10) LC_COLS(12) LC_COLS(14) LC_COLS(16) LC_COLS(18) LC_COLS(20)
@@ -615,17 +616,18 @@ void launch_pfbch_mac(const float2 *d_hist, const float2 *d_x, int H, const floa
                       unsigned int M, unsigned int p, unsigned long long n_frames, unsigned int phase,
                       unsigned int first, unsigned int k, cudaStream_t st)
 {
-    if (phase == 0 && k == 0 && first >= M && first % M == 0 && M % kColThreads == 0 && n_frames >= 64 && !getenv("LIQUID_CUDA_MAC_PLAIN")) {
+    const unsigned int col_threads = M % kColThreads == 0 ? kColThreads : 64;
+    if (phase == 0 && k == 0 && first >= M && first % M == 0 && M % 64 == 0 && n_frames >= 64 && !getenv("LIQUID_CUDA_MAC_PLAIN")) {
         const int fpc = 256;
         const unsigned long long chunks = (n_frames + fpc - 1) / fpc;
         if (chunks <= 65535) {
-            dim3 grid(M / kColThreads, (unsigned int)chunks);
+            dim3 grid(M / col_threads, (unsigned int)chunks);
             const long long f_first = (long long)(first / M) - 1;         // frame of x the first run reads last
             bool done = true;
             switch (p) {
 #define LC_COLS(PP)                                                                                                       \
     case PP:                                                                                                              \
-        pfbch_mac_cols_kernel<PP><<<grid, kColThreads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, (long long)n_frames, f_first, fpc); \
+        pfbch_mac_cols_kernel<PP><<<grid, col_threads, 0, st>>>(d_hist, d_x, H, d_taps, d_X, M, (long long)n_frames, f_first, fpc); \
         break;
                 LC_COLS(2) LC_COLS(4) LC_COLS(6) LC_COLS(8) LC_COLS(10) LC_COLS(12) LC_COLS(14) LC_COLS(16) LC_COLS(18) LC_COLS(20)
 #undef LC_COLS

@@ -953,7 +953,7 @@ def test_pfbch2_two_kernel_synthesizer_register_fir(L, orc, M, m):
     assert np.abs(got - want).max() / np.abs(want).max() < 1e-5, (M, m)
 
 
-@pytest.mark.parametrize("M,m", [(2048, 2), (2048, 7), (4096, 3), (1024, 9), (256, 8), (512, 1)])
+@pytest.mark.parametrize("M,m", [(2048, 2), (2048, 7), (4096, 3), (1024, 9), (256, 8), (512, 1), (64, 9), (128, 8), (192, 3)])
 def test_column_walking_mac_fallback(L, orc, monkeypatch, M, m):
     """shapes without a dedicated analyzer, long blocks: column-walking MAC kernel + tile / quad transform.  Both
     channelizers against the oracle over awkward cuts (odd frame counts move the firpfbch2 parity; blocks below 64 frames
